@@ -1,0 +1,207 @@
+/*
+ * include/lprb200.h -- C ABI of liblprb200.so, the B200-native (sm_100a) dense simplex pivot path
+ * that sits behind the solver classes of Storm-Tarran/LPR_381_Group_V22.
+ *
+ * The reference has no FFI today: the drop-in boundary is the public surface of
+ * its C# solver classes.  Each entry point below names the reference member whose BODY it
+ * replaces (paths relative to LPR_381_Group_V22/); the P/Invoke shim that keeps the C#
+ * signatures is in csharp/ and described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", cdecl, plain pointers and sizes; no exception crosses the boundary.
+ *   - every function returns LPR_OK (0) or a negative LPR_E_* code; the message is available
+ *     from lpr_last_error() (thread local).  Solver outcomes (optimal / unbounded / ...) are NOT
+ *     errors: they come back in *status.
+ *   - host arrays are caller owned, row-major IEEE binary64 (C# double[] / double[,] are
+ *     blittable and pinned by the marshaller) and are copied during the call.
+ *   - device memory is owned by the opaque handle; *_destroy frees it.
+ *   - a handle is not thread safe; different handles may be used from different threads.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns LPR_E_CUDA.
+ */
+#ifndef LPRB200_H
+#define LPRB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPR_VERSION 100
+
+/* return codes */
+#define LPR_OK 0
+#define LPR_E_BADARG (-1)
+#define LPR_E_CUDA (-2)
+#define LPR_E_NOMEM (-3)
+#define LPR_E_STATE (-4)
+#define LPR_E_CAPACITY (-5)
+
+/* solver status (written to *status) */
+#define LPR_RUNNING 0
+#define LPR_OPTIMAL 1
+#define LPR_UNBOUNDED 2
+#define LPR_INFEASIBLE 3
+#define LPR_ITER_LIMIT 4
+#define LPR_NODE_LIMIT 5
+#define LPR_PIVOT_TOO_SMALL 6
+#define LPR_NO_CUT_NEEDED 7
+#define LPR_NO_PIVOT_COL 8
+#define LPR_CUT_STEP_DONE 9
+
+/* pivot rule ids: the exact selection / tolerance variant */
+#define LPR_RULE_PRIMAL 0  /* Simplex/PrimalSimplexSolver.cs:152-211                      */
+#define LPR_RULE_PRIMAL2 1 /* Simplex/PrimalSimplexSolver2.cs:102-164                     */
+#define LPR_RULE_DUAL 2    /* Simplex/DualSimplex.cs:27-70,150-178                        */
+#define LPR_RULE_SENS 3    /* SensitivityAnalysis/SensitivityAnalyzer.cs:98-201           */
+
+/* constraint relation codes (IO/InputFileParser.cs:70-82 Constraint.Relation) */
+#define LPR_REL_LE 0
+#define LPR_REL_GE 1
+#define LPR_REL_EQ 2
+
+typedef struct lpr_tab lpr_tab; /* dense simplex tableau resident in HBM            */
+typedef struct lpr_rev lpr_rev; /* revised simplex state (A, B^-1, ...) in HBM      */
+typedef struct lpr_bb lpr_bb;   /* branch & bound simplex open-node pool in HBM     */
+typedef struct lpr_knap lpr_knap; /* knapsack branch & bound pool in HBM            */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int lpr_version(void);
+const char* lpr_last_error(void);
+int lpr_device_count(int* count);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t lpr_launch_count(void);
+
+/* ---- dense tableau: PrimalSimplexSolver / PrimalSimplexSolver2 / DualSimplexSolver -------- */
+/* Replaces the `double[,] tableau` field (PrimalSimplexSolver.cs:12,58; PrimalSimplexSolver2.cs:12,34).
+ * rows x cols host array (row 0 = objective row, last column = RHS); row_cap/col_cap >= rows/cols
+ * reserve room for appended cut / bound rows and columns (0 = no headroom). */
+int lpr_tab_create(int device, int rows, int cols, int row_cap, int col_cap, const double* host,
+                   lpr_tab** out);
+/* PrimalSimplexSolver..ctor (PrimalSimplexSolver.cs:27-87): builds the (m+1) x (n+m+1) tableau on
+ * the device from the model: >= rows negated, = treated as <=, row 0 = -c (c when !is_max), slack
+ * identity, basis = slacks.  coef is m x coef_stride, coef_count[i] (NULL => n) entries of row i
+ * are valid and only the first n are read (:68-72). */
+int lpr_tab_create_primal(int device, int n, int m, const double* objective, const double* coef,
+                          int coef_stride, const int* coef_count, const int* relation,
+                          const double* rhs, int is_maximization, lpr_tab** out);
+/* Synthetic dense LP of SURVEY.md 8(d) generated directly in HBM (counter based splitmix64, bit
+ * identical to the oracle's generator): A = 0.1+u, b = (n/4)(1+u), c = 1+u, maximise. */
+int lpr_tab_create_dense_lp(int device, uint64_t seed, int m, int n, lpr_tab** out);
+int lpr_tab_destroy(lpr_tab* h);
+int lpr_tab_dims(const lpr_tab* h, int* rows, int* cols, int* ld);
+int lpr_tab_upload(lpr_tab* h, const double* host);      /* rows x cols dense                */
+int lpr_tab_read(lpr_tab* h, double* host);              /* GetFinalTableau()  :269-273      */
+int lpr_tab_read_row(lpr_tab* h, int row, double* host); /* cols values                      */
+int lpr_tab_read_col(lpr_tab* h, int col, double* host); /* rows values                      */
+int lpr_tab_get_basis(lpr_tab* h, int* basis);           /* BasicVariables :275-278, rows-1  */
+int lpr_tab_set_basis(lpr_tab* h, const int* basis);
+/* Solve() loop (PrimalSimplexSolver.cs:102-150; PrimalSimplexSolver2.cs:46-97; DualSimplex.cs:14-114;
+ * SensitivityAnalyzer.cs:121-201) entirely on the device.  max_pivots < 0 = no cap.  pivot_log
+ * receives (row, col) pairs in tableau indices.  flags bit0 = "printSteps" (only meaningful for
+ * RULE_PRIMAL2 / RULE_DUAL whose iteration counters advance only when printing). */
+int lpr_tab_solve(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
+                  int64_t* n_pivots, int* pivot_log, int64_t log_cap);
+/* one pivot (FindEnteringVariable + FindLeavingVariable + Pivot) for snapshot-accurate tracing */
+int lpr_tab_step(lpr_tab* h, int rule, int* enter_col, int* leave_row, int* status);
+/* Pivot(row, col) at a caller chosen position (PrimalSimplexSolver.cs:193-211 arithmetic;
+ * skip_eps/skip_mode select the |f| skip of the other solvers: 0 none, 1 skip |f|<=eps, 2 skip |f|<eps) */
+int lpr_tab_pivot_at(lpr_tab* h, int row, int col, double skip_eps, int skip_mode);
+/* ExtractSolution (PrimalSimplexSolver.cs:213-252) for the first n columns */
+int lpr_tab_extract_solution(lpr_tab* h, int n, double* x);
+/* FinalZ = T[0, cols-1] (:113) */
+int lpr_tab_objective(lpr_tab* h, double* z);
+/* device time (CUDA events on the handle's stream) and kernel launches of the last solve */
+int lpr_tab_last_solve_ms(const lpr_tab* h, float* ms);
+/* append one row (Gomory cut, CuttingPlaneSolver.cs:110) -- needs row headroom */
+int lpr_tab_append_row(lpr_tab* h, const double* row);
+/* Gomory fractional cut rows 1-4 of CuttingPlaneSolver.cs:76-107 generated on the device:
+ * returns the chosen constraint row (0-based among constraint rows, -1 = none) and the cut. */
+int lpr_tab_gomory_cut(lpr_tab* h, int* chosen_row, double* cut_host /* cols, may be NULL */,
+                       int append);
+/* CuttingPlaneSolver.CuttingPlaneSolution (CuttingPlaneSolver.cs:64-229), recursion as a loop;
+ * cut_log: (chosen_row, pivot_col, n_dual_pivots, n_primal_pivots) per cut */
+int lpr_tab_cutting_plane(lpr_tab* h, int max_cuts, int* status, int* n_cuts, int* cut_log,
+                          int cut_log_cap);
+
+/* ---- RevisedPrimalSimplexSolver (Simplex/RevisedPrimalSimplexSolver.cs) -------------------- */
+/* ctor :41-80 (Relation ignored: every row is <=).  A is m x n row-major. */
+int lpr_rev_create(int device, int m, int n, const double* A, const double* b, const double* c,
+                   int is_minimization, lpr_rev** out);
+int lpr_rev_create_dense_lp(int device, uint64_t seed, int m, int n, lpr_rev** out);
+int lpr_rev_destroy(lpr_rev* h);
+/* Solve() :82-251.  refactor_every > 0 recomputes B^-1 from the basis columns every that many
+ * iterations (FP64 tensor-core GEMM based inversion; the reference never refactorises, Q7).
+ * log: (leaveRow, enter, leaveVar) triples.  status: OPTIMAL / INFEASIBLE (:91) / UNBOUNDED (:179)
+ * / PIVOT_TOO_SMALL (:267) / ITER_LIMIT. */
+int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status, int64_t* n_iter,
+                  int* log, int64_t log_cap);
+int lpr_rev_refactor(lpr_rev* h);
+int lpr_rev_read_basis(lpr_rev* h, int* basis);   /* BasicVariables :39, m entries          */
+int lpr_rev_read_x(lpr_rev* h, double* x);        /* SolutionVector :277-287, n entries     */
+int lpr_rev_read_z(lpr_rev* h, double* z);        /* FinalZ :286                            */
+int lpr_rev_read_y(lpr_rev* h, double* y);        /* dual prices y = c_B B^-1 :93, m        */
+int lpr_rev_read_xb(lpr_rev* h, double* xb);      /* x_B = B^-1 b :89, m                    */
+int lpr_rev_read_binv(lpr_rev* h, double* binv);  /* m x m                                  */
+int lpr_rev_last_solve_ms(const lpr_rev* h, float* ms);
+int lpr_rev_last_refactor_ms(const lpr_rev* h, float* ms);
+
+/* ---- BranchBoundSimplexSolver (IntegerProgramming/BranchBoundSimplexSolver.cs) ------------- */
+/* building blocks, each on a device tableau */
+int lpr_tab_round4(lpr_tab* h);                                  /* RoundTableau :552-567      */
+int lpr_tab_bb_node_solve(lpr_tab* h, int64_t max_pivots, int* status, int64_t* n_pivots,
+                          int* pivot_log, int64_t log_cap);     /* DoDualSimplex :289-468     */
+int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound, int type,
+                              lpr_tab** child);                  /* AddConstraint :694-803     */
+int lpr_tab_bb_branch_var(lpr_tab* h, int n_vars, int* var, double* value,
+                          double* x /* n_vars, may be NULL */); /* :805-857, :899-921          */
+/* BranchAndBoundAdapter.SolveFromPrimal + BranchAndBound.ExecuteBranchAndBound (:1006-1233):
+ * depth-first tree on ONE device, reference order (used for parity; max_nodes = 20 is the
+ * reference cap, < 0 lifts it).  node_log: (depth, branch_var, is_integer, pruned) per node. */
+int lpr_bb_solve(int device, int rows, int cols, const double* final_tableau, int n_vars,
+                 int enable_pruning, int64_t max_nodes, double* x, double* z, int* has_solution,
+                 int64_t* nodes, int64_t* pivots, int* node_log, double* node_z,
+                 int64_t node_log_cap, int* status);
+/* Partitionable open-node pool for the multi-GPU driver (one process per GPU; incumbents and
+ * node records are exchanged by the host layer over NCCL): see DESIGN.md "B&B pool". */
+int lpr_bb_create(int device, int rows, int cols, const double* root_tableau, int n_vars,
+                  int enable_pruning, lpr_bb** out);
+int lpr_bb_destroy(lpr_bb* h);
+int lpr_bb_open_count(lpr_bb* h, int64_t* n);
+/* expand up to max_nodes open nodes (deepest first); returns nodes processed / pivots done */
+int lpr_bb_run(lpr_bb* h, int64_t max_nodes, int64_t* processed, int64_t* pivots);
+/* incumbent as (z, dfs_key[], x[]) -- the key makes ties deterministic across GPU counts */
+int lpr_bb_get_incumbent(lpr_bb* h, int* has, double* z, double* x, int* key, int* key_len);
+int lpr_bb_set_incumbent(lpr_bb* h, double z, const double* x, const int* key, int key_len);
+/* work stealing: pop up to max_nodes shallowest open nodes into a host byte buffer / push them */
+int lpr_bb_export_nodes(lpr_bb* h, int max_nodes, void* buf, int64_t buf_cap, int64_t* bytes,
+                        int* n_exported);
+int lpr_bb_import_nodes(lpr_bb* h, const void* buf, int64_t bytes);
+
+/* ---- Knapsack branch & bound (Program.cs:430-471; KnapsackBranchBoundSimplex is missing from
+ *      the reference, specification in DESIGN.md) ----------------------------------------------- */
+/* KnapsackBranchBoundSolver.Solve(int,int[],int[]) -- DP arbiter, on the device */
+int lpr_knap_dp(int device, int capacity, int n, const int* weights, const int* values,
+                double* best, uint8_t* chosen);
+int lpr_knap_create(int device, double capacity, int n, const double* weights,
+                    const double* values, lpr_knap** out);
+int lpr_knap_destroy(lpr_knap* h);
+/* run rounds of best-bound frontier expansion until the pool is empty or max_nodes reached */
+int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status);
+int lpr_knap_open_count(lpr_knap* h, int64_t* n);
+int lpr_knap_get_incumbent(lpr_knap* h, double* best, uint8_t* chosen /* n, original ids */,
+                           uint64_t* key /* key_words */, int* key_bits);
+int lpr_knap_set_incumbent(lpr_knap* h, double best, const uint8_t* chosen, const uint64_t* key,
+                           int key_bits);
+int lpr_knap_export_nodes(lpr_knap* h, int max_nodes, void* buf, int64_t buf_cap, int64_t* bytes,
+                          int* n_exported);
+int lpr_knap_import_nodes(lpr_knap* h, const void* buf, int64_t bytes);
+/* KnapsackBranchBoundSimplex.Solve() single device convenience */
+int lpr_knap_solve(int device, double capacity, int n, const double* weights,
+                   const double* values, int64_t max_nodes, double* best, uint8_t* chosen,
+                   int64_t* nodes, int* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPRB200_H */

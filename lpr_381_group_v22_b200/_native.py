@@ -1,0 +1,154 @@
+"""ctypes binding of liblprb200.so (the C ABI declared in include/lprb200.h).
+
+This is the only place the package touches native code.  There is NO CPU fallback: if the
+shared library is missing the import of any solver raises, and without a CUDA device every
+compute entry point returns LPR_E_CUDA which is raised here as LprError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "liblprb200.so")
+
+OK = 0
+RUNNING, OPTIMAL, UNBOUNDED, INFEASIBLE, ITER_LIMIT, NODE_LIMIT, PIVOT_TOO_SMALL, NO_CUT_NEEDED, \
+    NO_PIVOT_COL, CUT_STEP_DONE = range(10)
+STATUS_NAMES = ["running", "optimal", "unbounded", "infeasible", "iter_limit", "node_limit",
+                "pivot_too_small", "no_cut_needed", "no_pivot_col", "cut_step_done"]
+RULE_PRIMAL, RULE_PRIMAL2, RULE_DUAL, RULE_SENS = range(4)
+REL = {"<=": 0, ">=": 1, "=": 2}
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+lp = C.POINTER(C.c_int64)
+bp = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+
+
+class LprError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liblprb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/lprb200.h declares
+SIGNATURES = {
+    "lpr_version": (C.c_int, []),
+    "lpr_last_error": (C.c_char_p, []),
+    "lpr_device_count": (C.c_int, [ip]),
+    "lpr_launch_count": (C.c_int64, []),
+    "lpr_tab_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.POINTER(vp)]),
+    "lpr_tab_create_primal": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, ip, ip, dp, C.c_int,
+                                        C.POINTER(vp)]),
+    "lpr_tab_create_dense_lp": (C.c_int, [C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]),
+    "lpr_tab_destroy": (C.c_int, [vp]),
+    "lpr_tab_dims": (C.c_int, [vp, ip, ip, ip]),
+    "lpr_tab_upload": (C.c_int, [vp, dp]),
+    "lpr_tab_read": (C.c_int, [vp, dp]),
+    "lpr_tab_read_row": (C.c_int, [vp, C.c_int, dp]),
+    "lpr_tab_read_col": (C.c_int, [vp, C.c_int, dp]),
+    "lpr_tab_get_basis": (C.c_int, [vp, ip]),
+    "lpr_tab_set_basis": (C.c_int, [vp, ip]),
+    "lpr_tab_solve": (C.c_int, [vp, C.c_int, C.c_int64, C.c_int, ip, lp, ip, C.c_int64]),
+    "lpr_tab_step": (C.c_int, [vp, C.c_int, ip, ip, ip]),
+    "lpr_tab_pivot_at": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int]),
+    "lpr_tab_extract_solution": (C.c_int, [vp, C.c_int, dp]),
+    "lpr_tab_objective": (C.c_int, [vp, dp]),
+    "lpr_tab_last_solve_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "lpr_tab_append_row": (C.c_int, [vp, dp]),
+    "lpr_tab_gomory_cut": (C.c_int, [vp, ip, dp, C.c_int]),
+    "lpr_tab_cutting_plane": (C.c_int, [vp, C.c_int, ip, ip, ip, C.c_int]),
+    "lpr_rev_create": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_int, C.POINTER(vp)]),
+    "lpr_rev_create_dense_lp": (C.c_int, [C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]),
+    "lpr_rev_destroy": (C.c_int, [vp]),
+    "lpr_rev_solve": (C.c_int, [vp, C.c_int64, C.c_int, ip, lp, ip, C.c_int64]),
+    "lpr_rev_refactor": (C.c_int, [vp]),
+    "lpr_rev_read_basis": (C.c_int, [vp, ip]),
+    "lpr_rev_read_x": (C.c_int, [vp, dp]),
+    "lpr_rev_read_z": (C.c_int, [vp, dp]),
+    "lpr_rev_read_y": (C.c_int, [vp, dp]),
+    "lpr_rev_read_xb": (C.c_int, [vp, dp]),
+    "lpr_rev_read_binv": (C.c_int, [vp, dp]),
+    "lpr_rev_last_solve_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "lpr_rev_last_refactor_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "lpr_tab_round4": (C.c_int, [vp]),
+    "lpr_tab_bb_node_solve": (C.c_int, [vp, C.c_int64, ip, lp, ip, C.c_int64]),
+    "lpr_tab_bb_add_constraint": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(vp)]),
+    "lpr_tab_bb_branch_var": (C.c_int, [vp, C.c_int, ip, dp, dp]),
+    "lpr_bb_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int64, dp, dp, ip, lp, lp,
+                               ip, dp, C.c_int64, ip]),
+    "lpr_bb_create": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "lpr_bb_destroy": (C.c_int, [vp]),
+    "lpr_bb_open_count": (C.c_int, [vp, lp]),
+    "lpr_bb_run": (C.c_int, [vp, C.c_int64, lp, lp]),
+    "lpr_bb_get_incumbent": (C.c_int, [vp, ip, dp, dp, ip, ip]),
+    "lpr_bb_set_incumbent": (C.c_int, [vp, C.c_double, dp, ip, C.c_int]),
+    "lpr_bb_export_nodes": (C.c_int, [vp, C.c_int, vp, C.c_int64, lp, ip]),
+    "lpr_bb_import_nodes": (C.c_int, [vp, vp, C.c_int64]),
+    "lpr_knap_dp": (C.c_int, [C.c_int, C.c_int, C.c_int, ip, ip, dp, bp]),
+    "lpr_knap_create": (C.c_int, [C.c_int, C.c_double, C.c_int, dp, dp, C.POINTER(vp)]),
+    "lpr_knap_destroy": (C.c_int, [vp]),
+    "lpr_knap_run": (C.c_int, [vp, C.c_int64, lp, ip]),
+    "lpr_knap_open_count": (C.c_int, [vp, lp]),
+    "lpr_knap_get_incumbent": (C.c_int, [vp, dp, bp, u64p, ip]),
+    "lpr_knap_set_incumbent": (C.c_int, [vp, C.c_double, bp, u64p, C.c_int]),
+    "lpr_knap_export_nodes": (C.c_int, [vp, C.c_int, vp, C.c_int64, lp, ip]),
+    "lpr_knap_import_nodes": (C.c_int, [vp, vp, C.c_int64]),
+    "lpr_knap_solve": (C.c_int, [C.c_int, C.c_double, C.c_int, dp, dp, C.c_int64, dp, bp, lp, ip]),
+}
+
+
+def lib():
+    """Load liblprb200.so (built in-tree by __graft_entry__.build()).  Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "lpr_381_group_v22_b200 has no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        missing = [name for name in SIGNATURES if not hasattr(l, name)]
+        if missing:
+            raise ImportError(f"{LIB_PATH} does not export {missing}: stale build? run __graft_entry__.build()")
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise LprError(rc, lib().lpr_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().lpr_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+def launch_count():
+    return int(lib().lpr_launch_count())
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def pd(a):
+    return a.ctypes.data_as(dp) if a is not None else None
+
+
+def pi(a):
+    return a.ctypes.data_as(ip) if a is not None else None

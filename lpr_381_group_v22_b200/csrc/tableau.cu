@@ -1,0 +1,1337 @@
+// tableau.cu -- dense simplex tableau in HBM: selection kernels, the rank-1 pivot sweep and the
+// device-side Solve() loops of PrimalSimplexSolver / PrimalSimplexSolver2 / DualSimplexSolver /
+// SensitivityAnalyzer (reference file:line cited per kernel; semantics in SURVEY.md Appendix A).
+//
+// Layout: row-major fp64, leading dimension padded to a multiple of 16 doubles so every row
+// starts on a 128-byte line; padding columns are kept at 0.  Arithmetic: IEEE binary64 with
+// separate multiply and subtract roundings (__dmul_rn/__dsub_rn are never contracted) and
+// IEEE division, which makes every element bit-identical to the reference's scalar loops.
+#include "tableau.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+namespace lpr {
+
+std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+std::atomic<int64_t> g_launches{0};
+
+int select_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(LPR_E_CUDA, "no CUDA device available (%s); liblprb200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(LPR_E_BADARG, "device %d out of range [0,%d)", device, n);
+  LPR_CUDA(cudaSetDevice(device));
+  return LPR_OK;
+}
+int sm_count(int device) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return sms > 0 ? sms : 148;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+// =============================================================================================
+// device helpers
+// =============================================================================================
+constexpr int kSelThreads = 1024;
+constexpr int kSweepThreads = 256;
+constexpr double kPosInf = __builtin_huge_val();
+
+#define TAT(T, ld, i, j) (T)[(size_t)(i) * (size_t)(ld) + (size_t)(j)]
+
+// Sequential "running best with hysteresis" scan (accept k iff val_k < best - eps, best starts at
+// b0) evaluated in parallel: the first index of the minimum is the answer unless an earlier
+// candidate could have blocked it, in which case thread 0 replays the scan literally.  Used for
+// PrimalSimplexSolver2.cs:102-141, DualSimplex.cs:27-70, SensitivityAnalyzer.cs:139-196 and
+// RevisedPrimalSimplexSolver.cs:104-121.  All threads of the block must call it.
+template <class Cand>
+__device__ int block_hyst_min(int n, Cand cand, double b0, double eps, MinIdx* sm, int* smi) {
+  __shared__ int sh_res;
+  MinIdx m = minidx_identity();
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    double val;
+    if (cand(k, val) && val == val) m = minidx_combine(m, MinIdx{val, k});
+  }
+  m = block_minidx(m, sm);
+  if (m.i == INT_MAX) return -1;
+  if (!(m.v < __dsub_rn(b0, eps))) return -1;
+  int bad = 0;
+  for (int k = threadIdx.x; k < m.i; k += blockDim.x) {
+    double val;
+    if (cand(k, val) && val == val && !(m.v < __dsub_rn(val, eps))) bad++;
+  }
+  bad = block_sum_int(bad, smi);
+  if (bad == 0) return m.i;
+  if (threadIdx.x == 0) {
+    double best = b0;
+    int idx = -1;
+    for (int k = 0; k < n; k++) {
+      double val;
+      if (cand(k, val) && val < __dsub_rn(best, eps)) {
+        best = val;
+        idx = k;
+      }
+    }
+    sh_res = idx;
+  }
+  __syncthreads();
+  int r = sh_res;
+  __syncthreads();
+  return r;
+}
+
+// first index of the minimum over valid candidates
+template <class Cand>
+__device__ int block_first_min(int n, Cand cand, MinIdx* sm, double* vout = nullptr) {
+  MinIdx m = minidx_identity();
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    double val;
+    if (cand(k, val)) m = minidx_combine(m, MinIdx{val, k});
+  }
+  m = block_minidx(m, sm);
+  if (vout) *vout = m.v;
+  return m.i == INT_MAX ? -1 : m.i;
+}
+
+// =============================================================================================
+// k_select<RULE>: one CTA.  Commits the previous pivot, picks (leave row, enter col) with the
+// rule's exact tolerances and tie breaks, stages the normalised pivot row (prow) and the
+// pre-update factor column (col[cur]) for the sweep.
+// =============================================================================================
+enum : int { F_PRINT = 1, F_FUSED = 2 };
+
+template <int RULE>
+__global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, int* mask) {
+  __shared__ MinIdx sm[32];
+  __shared__ int smi[32];
+  TabState* st = v.st;
+  const int tid = threadIdx.x;
+  const int R = v.R, C = v.C, ld = v.ld;
+  double* T = v.T;
+
+  const int status = st->status;
+  const int did = st->do_sweep;
+  long long npiv = st->npiv;
+  const long long maxp = st->max_piv;
+  int phase = st->phase;
+  __syncthreads();
+  if (status != LPR_RUNNING) {
+    if (tid == 0) st->do_sweep = 0;
+    return;
+  }
+  if (did) npiv++;
+  auto finish = [&](int s) {
+    if (tid == 0) {
+      st->status = s;
+      st->do_sweep = 0;
+      st->npiv = npiv;
+      st->phase = phase;
+    }
+  };
+  // PrimalSimplexSolver2.cs:75,90 / DualSimplex.cs:94,108: the counter only advances when
+  // printSteps is set and is tested AFTER the pivot.
+  if (did && (RULE == LPR_RULE_PRIMAL2 || RULE == LPR_RULE_DUAL)) {
+    long long iter = (flags & F_PRINT) ? npiv : 0;
+    if (maxp >= 0 && iter >= maxp) {
+      finish(LPR_ITER_LIMIT);
+      return;
+    }
+  }
+
+  int e = -1, p = -1;
+  int skip_basis_update = 0;
+  if (RULE == LPR_RULE_PRIMAL) {
+    // FindEnteringVariable PrimalSimplexSolver.cs:152-167: min T[0,j] < 0.0, lowest j
+    e = block_first_min(C - 1, [&](int j, double& val) { val = T[j]; return val < 0.0; }, sm);
+    if (e < 0) { finish(LPR_OPTIMAL); return; }
+    // FindLeavingVariable :169-191: a > 1e-9, ratio >= 0, ratio < DBL_MAX, lowest row
+    int k = block_first_min(R - 1, [&](int q, double& val) {
+      double a = TAT(T, ld, q + 1, e);
+      if (!(a > 1e-9)) return false;
+      val = __ddiv_rn(TAT(T, ld, q + 1, C - 1), a);
+      return val >= 0.0 && val < DBL_MAX;
+    }, sm);
+    if (k < 0) { finish(LPR_UNBOUNDED); return; }
+    p = k + 1;
+    if (maxp >= 0 && npiv >= maxp) { finish(LPR_ITER_LIMIT); return; }
+  } else if (RULE == LPR_RULE_PRIMAL2) {
+    const double EPS = 1e-10;
+    // FindEnteringColumn PrimalSimplexSolver2.cs:102-117
+    e = block_hyst_min(C - 1, [&](int j, double& val) { val = T[j]; return true; }, 0.0, EPS, sm, smi);
+    if (e < 0) { finish(LPR_OPTIMAL); return; }
+    // FindLeavingRow :120-141 (precedence quirk reduces to ratio > EPS && ratio < best - EPS)
+    int k = block_hyst_min(R - 1, [&](int q, double& val) {
+      double a = TAT(T, ld, q + 1, e);
+      if (!(a > EPS)) return false;
+      val = __ddiv_rn(TAT(T, ld, q + 1, C - 1), a);
+      return val > EPS;
+    }, kPosInf, EPS, sm, smi);
+    if (k < 0) { finish(LPR_UNBOUNDED); return; }
+    p = k + 1;
+    if (fabs(TAT(T, ld, p, e)) <= EPS) { finish(LPR_PIVOT_TOO_SMALL); return; }
+    skip_basis_update = 1;
+  } else if (RULE == LPR_RULE_DUAL) {
+    const double EPS = 1e-9;
+    // DualSimplex.cs:27-37 most negative RHS among constraint rows
+    int k = block_hyst_min(R - 1, [&](int q, double& val) { val = TAT(T, ld, q + 1, C - 1); return true; },
+                           0.0, EPS, sm, smi);
+    if (k < 0) { finish(LPR_OPTIMAL); return; }
+    p = k + 1;
+    // :50-70 min |obj_j / a_j| over a_j < -EPS, |obj_j| > EPS
+    e = block_hyst_min(C - 1, [&](int j, double& val) {
+      double a = TAT(T, ld, p, j);
+      if (!(a < -EPS)) return false;
+      double num = T[j];
+      if (!(fabs(num) > EPS)) return false;
+      val = fabs(__ddiv_rn(num, a));
+      return true;
+    }, kPosInf, EPS, sm, smi);
+    if (e < 0) { finish(LPR_INFEASIBLE); return; }
+    if (fabs(TAT(T, ld, p, e)) <= EPS) { finish(LPR_PIVOT_TOO_SMALL); return; }
+    skip_basis_update = 1;
+  } else if (RULE == LPR_RULE_SENS) {
+    const double EPS = 1e-9;
+    // phase pivots counter lives in st->pivot's slot? no: use st->have_prev as the per-phase count
+    int phase_piv = st->have_prev + (did ? 1 : 0);
+    if (phase == 0) {
+      // DualSimplexIfNeeded SensitivityAnalyzer.cs:168-201
+      int k = block_hyst_min(R - 1, [&](int q, double& val) { val = TAT(T, ld, q + 1, C - 1); return true; },
+                             0.0, EPS, sm, smi);
+      if (k < 0) {
+        phase = 1;
+        phase_piv = 0;
+      } else {
+        p = k + 1;
+        if (maxp >= 0 && phase_piv > maxp) { finish(LPR_ITER_LIMIT); return; }
+        e = block_hyst_min(C - 1, [&](int j, double& val) {
+          double a = TAT(T, ld, p, j);
+          if (!(a < -EPS)) return false;
+          val = __ddiv_rn(T[j], -a);
+          return true;
+        }, kPosInf, EPS, sm, smi);
+        if (e < 0) { finish(LPR_INFEASIBLE); return; }
+      }
+    }
+    if (phase == 1) {
+      // ReOptimize :121-166 with IsOptimal :85-96 (non-basic columns only)
+      for (int j = tid; j < C; j += blockDim.x) mask[j] = 0;
+      __syncthreads();
+      for (int i = tid; i < R - 1; i += blockDim.x) {
+        int b = v.basis[i];
+        if (b >= 0 && b < C) mask[b] = 1;
+      }
+      __syncthreads();
+      int notopt = 0;
+      for (int j = tid; j < C - 1; j += blockDim.x)
+        if (!mask[j] && T[j] < -EPS) notopt++;
+      notopt = block_sum_int(notopt, smi);
+      if (notopt == 0) { finish(LPR_OPTIMAL); return; }
+      if (maxp >= 0 && phase_piv > maxp) { finish(LPR_ITER_LIMIT); return; }
+      e = block_first_min(C - 1, [&](int j, double& val) { val = T[j]; return !mask[j] && val < 0.0; }, sm);
+      if (e < 0) { finish(LPR_OPTIMAL); return; }
+      int k = block_hyst_min(R - 1, [&](int q, double& val) {
+        double a = TAT(T, ld, q + 1, e);
+        if (!(a > EPS)) return false;
+        val = __ddiv_rn(TAT(T, ld, q + 1, C - 1), a);
+        return true;
+      }, kPosInf, EPS, sm, smi);
+      if (k < 0) { finish(LPR_UNBOUNDED); return; }
+      p = k + 1;
+    }
+    if (fabs(TAT(T, ld, p, e)) < EPS) { finish(LPR_PIVOT_TOO_SMALL); return; }
+    if (tid == 0) st->have_prev = phase_piv;
+  }
+
+  // ---- stage pivot row and factor column (Pivot: PrimalSimplexSolver.cs:193-200) -----------
+  const double piv = TAT(T, ld, p, e);
+  const int cur = st->cur;
+  double* colb = cur ? v.col[1] : v.col[0];
+  for (int j = tid; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? __ddiv_rn(TAT(T, ld, p, j), piv) : 0.0;
+  for (int i = tid; i < R; i += blockDim.x) colb[i] = TAT(T, ld, i, e);
+  if (tid == 0) {
+    st->enter = e;
+    st->leave = p;
+    st->next_enter = -1;
+    st->do_sweep = 1;
+    st->npiv = npiv;
+    st->phase = phase;
+    st->pivot = piv;
+    if (v.log && npiv < v.log_cap) {
+      v.log[2 * npiv] = p;
+      v.log[2 * npiv + 1] = e;
+    }
+    if (!skip_basis_update && v.basis && p >= 1) v.basis[p - 1] = e;  // PrimalSimplexSolver.cs:142
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused primal path (RULE_PRIMAL, the bench hot path).  The sweep of pivot t also emits the
+// post-update column of the NEXT entering variable and the post-update RHS column into side
+// buffers, so selecting pivot t+1 costs O(R + C) contiguous reads instead of two strided
+// column gathers, and the tableau is read and written exactly once per pivot.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads) k_primal_init(TabView v) {
+  __shared__ MinIdx sm[32];
+  TabState* st = v.st;
+  const double* T = v.T;
+  const int R = v.R, C = v.C, ld = v.ld;
+  int e = block_first_min(C - 1, [&](int j, double& val) { val = T[j]; return val < 0.0; }, sm);
+  double* colb = v.col[0];
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    v.rhs[i] = TAT(T, ld, i, C - 1);
+    if (e >= 0) colb[i] = TAT(T, ld, i, e);
+  }
+  if (threadIdx.x == 0) {
+    st->enter = e;
+    st->cur = 0;
+    st->do_sweep = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads) k_primal_select_fused(TabView v) {
+  __shared__ MinIdx sm[32];
+  TabState* st = v.st;
+  const int tid = threadIdx.x;
+  const int R = v.R, C = v.C, ld = v.ld;
+  const double* T = v.T;
+  const int status = st->status;
+  const int did = st->do_sweep;
+  long long npiv = st->npiv;
+  const long long maxp = st->max_piv;
+  int cur = st->cur;
+  int e = st->enter;
+  const int nxt = st->next_enter;
+  __syncthreads();
+  if (status != LPR_RUNNING) {
+    if (tid == 0) st->do_sweep = 0;
+    return;
+  }
+  if (did) {  // commit pivot t: the sweep has produced col[cur^1] for `nxt`
+    npiv++;
+    cur ^= 1;
+    e = nxt;
+  }
+  auto finish = [&](int s) {
+    if (tid == 0) {
+      st->status = s;
+      st->do_sweep = 0;
+      st->npiv = npiv;
+      st->cur = cur;
+      st->enter = e;
+    }
+  };
+  if (e < 0) { finish(LPR_OPTIMAL); return; }
+  const double* colb = cur ? v.col[1] : v.col[0];
+  // FindLeavingVariable PrimalSimplexSolver.cs:169-191 on the staged (contiguous) column + RHS
+  int k = block_first_min(R - 1, [&](int q, double& val) {
+    double a = colb[q + 1];
+    if (!(a > 1e-9)) return false;
+    val = __ddiv_rn(v.rhs[q + 1], a);
+    return val >= 0.0 && val < DBL_MAX;
+  }, sm);
+  if (k < 0) { finish(LPR_UNBOUNDED); return; }
+  const int p = k + 1;
+  if (maxp >= 0 && npiv >= maxp) { finish(LPR_ITER_LIMIT); return; }
+  const double piv = colb[p];
+  const double f0 = colb[0];
+  // normalise the pivot row (:197-199) and, fused, evaluate the updated objective row
+  // T[0,j] - f0*prow[j] (:206-208) to pick the next entering column (:152-167).
+  MinIdx m = minidx_identity();
+  for (int j = tid; j < ld; j += blockDim.x) {
+    double pr = 0.0;
+    if (j < C) {
+      pr = __ddiv_rn(TAT(T, ld, p, j), piv);
+      if (j < C - 1) {
+        double z = __dsub_rn(T[j], __dmul_rn(f0, pr));
+        if (z < 0.0) m = minidx_combine(m, MinIdx{z, j});
+      }
+    }
+    v.prow[j] = pr;
+  }
+  m = block_minidx(m, sm);
+  if (tid == 0) {
+    st->enter = e;
+    st->leave = p;
+    st->next_enter = (m.i == INT_MAX) ? -1 : m.i;
+    st->do_sweep = 1;
+    st->npiv = npiv;
+    st->cur = cur;
+    st->pivot = piv;
+    if (v.log && npiv < v.log_cap) {
+      v.log[2 * npiv] = p;
+      v.log[2 * npiv + 1] = e;
+    }
+    if (v.basis) v.basis[p - 1] = e;  // :142
+  }
+}
+
+// =============================================================================================
+// k_sweep: the rank-1 row-elimination update (Pivot: PrimalSimplexSolver.cs:201-210 and its
+// five siblings).  Every element of the tableau is read once and written once per pivot:
+//   row p      : T[p,j] = prow[j]                          (normalised pivot row)
+//   row i != p : T[i,j] = T[i,j] - (f_i * prow[j])          (separate mul and sub roundings)
+// Thread mapping: a thread owns ONE 16-byte (double2) column chunk and walks down rows, so its
+// two prow values live in registers and the only per-row traffic is the 128-bit load/store of
+// the tableau plus a warp-uniform load of f_i.  Work is split into (column group, row) units,
+// column-group major, and dealt in equal contiguous ranges to a grid of sms*k CTAs (no tail
+// wave).  UNROLL independent 128-bit loads are in flight per thread.
+//   SKIP: 0 none | 1 skip rows with |f| <= eps | 2 skip rows with |f| < eps
+//   OOP : out-of-place (B&B pivots, BranchBoundSimplexSolver.cs:161-192) with -0.0 -> 0.0
+//   EMIT: fused primal path, write next factor column / RHS side buffers
+// =============================================================================================
+template <int SKIP, bool OOP, bool EMIT, int UNROLL>
+__global__ void __launch_bounds__(kSweepThreads) k_sweep(TabView v, double eps, int reverse) {
+  const TabState* st = v.st;
+  if (!st->do_sweep) return;
+  const int p = st->leave;
+  const int e_next = EMIT ? st->next_enter : -1;
+  const int cur = st->cur;
+  const int R = v.R, C = v.C;
+  const int ldv = v.ld >> 1;
+  const double* __restrict__ f = cur ? v.col[1] : v.col[0];
+  double* __restrict__ cn = cur ? v.col[0] : v.col[1];
+  const double2* __restrict__ src = reinterpret_cast<const double2*>(OOP ? (st->src ? v.T2 : v.T) : v.T);
+  double2* __restrict__ dst = reinterpret_cast<double2*>(OOP ? (st->src ? v.T : v.T2) : v.T);
+  const double2* __restrict__ prow2 = reinterpret_cast<const double2*>(v.prow);
+  const int rhs_chunk = (C - 1) >> 1, rhs_odd = (C - 1) & 1;
+  const int e_chunk = e_next >= 0 ? (e_next >> 1) : -1, e_odd = e_next & 1;
+
+  auto update = [&](double2 x, double fv, double2 pr, int row) -> double2 {
+    double2 y;
+    if (row == p) {
+      y = pr;
+    } else {
+      y.x = __dsub_rn(x.x, __dmul_rn(fv, pr.x));
+      y.y = __dsub_rn(x.y, __dmul_rn(fv, pr.y));
+      if (OOP) {
+        if (y.x == 0.0) y.x = 0.0;
+        if (y.y == 0.0) y.y = 0.0;
+      }
+    }
+    return y;
+  };
+  auto skipped = [&](double fv, int row) -> bool {
+    if (SKIP == 0 || row == p) return false;
+    return SKIP == 1 ? (fabs(fv) <= eps) : (fabs(fv) < eps);
+  };
+
+  const int nfull = ldv / kSweepThreads;
+  const long long U = (long long)nfull * R;
+  int bid = reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  long long u0 = U * bid / gridDim.x;
+  const long long u1 = U * (bid + 1) / gridDim.x;
+  while (u0 < u1) {
+    const int cg = (int)(u0 / R);
+    const int r0 = (int)(u0 - (long long)cg * R);
+    const int r1 = (int)min((long long)R, r0 + (u1 - u0));
+    const int chunk = cg * kSweepThreads + threadIdx.x;
+    const double2 pr = prow2[chunk];
+    const bool own_e = EMIT && chunk == e_chunk, own_r = EMIT && chunk == rhs_chunk;
+    const double2* s = src + chunk;
+    double2* d = dst + chunk;
+    for (int r = r0; r < r1; r += UNROLL) {
+      double2 x[UNROLL];
+      double fv[UNROLL];
+#pragma unroll
+      for (int k = 0; k < UNROLL; k++) {
+        const int row = r + k;
+        if (row < r1) {
+          fv[k] = f[row];
+          if (!skipped(fv[k], row) || OOP) x[k] = s[(size_t)row * ldv];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < UNROLL; k++) {
+        const int row = r + k;
+        if (row < r1) {
+          if (skipped(fv[k], row)) {
+            if (OOP) d[(size_t)row * ldv] = x[k];
+            continue;
+          }
+          double2 y = update(x[k], fv[k], pr, row);
+          d[(size_t)row * ldv] = y;
+          if (own_e) cn[row] = e_odd ? y.y : y.x;
+          if (own_r) v.rhs[row] = rhs_odd ? y.y : y.x;
+        }
+      }
+    }
+    u0 += (r1 - r0);
+  }
+  // ragged remainder: the last (ldv % 256) chunks of every row, one thread per row
+  const int rem0 = nfull * kSweepThreads;
+  if (rem0 < ldv) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    for (int row = gid; row < R; row += nth) {
+      const double fv = f[row];
+      if (skipped(fv, row)) {
+        if (OOP)
+          for (int c = rem0; c < ldv; c++) dst[(size_t)row * ldv + c] = src[(size_t)row * ldv + c];
+        continue;
+      }
+      for (int c = rem0; c < ldv; c++) {
+        double2 y = update(src[(size_t)row * ldv + c], fv, prow2[c], row);
+        dst[(size_t)row * ldv + c] = y;
+        if (EMIT && c == e_chunk) cn[row] = e_odd ? y.y : y.x;
+        if (EMIT && c == rhs_chunk) v.rhs[row] = rhs_odd ? y.y : y.x;
+      }
+    }
+  }
+}
+
+// state reset before a solve
+__global__ void k_state_reset(TabState* st, long long max_piv, int src) {
+  st->status = LPR_RUNNING;
+  st->enter = -1;
+  st->leave = -1;
+  st->next_enter = -1;
+  st->do_sweep = 0;
+  st->cur = 0;
+  st->src = src;
+  st->phase = 0;
+  st->have_prev = 0;
+  st->dropped = 0;
+  st->npiv = 0;
+  st->max_piv = max_piv;
+  st->pivot = 0.0;
+}
+
+// ---- construction kernels ---------------------------------------------------------------------
+__global__ void k_fill_zero(double* T, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) T[i] = 0.0;
+}
+// PrimalSimplexSolver..ctor :56-83 for the synthetic dense LP of SURVEY 8(d) (all rows <=, max)
+__global__ void k_build_dense_lp(double* T, int ld, int m, int n, uint64_t seed, int* basis) {
+  const int C = n + m + 1;
+  const int row = blockIdx.y;  // 0..m
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ld; j += gridDim.x * blockDim.x) {
+    double val = 0.0;
+    if (row == 0) {
+      if (j < n) val = -(1.0 + u01(seed, 2, (uint64_t)j));  // :61-62 row 0 = -c
+    } else {
+      const int i = row - 1;
+      if (j < n)
+        val = 0.1 + u01(seed, 0, (uint64_t)i * (uint64_t)n + (uint64_t)j);
+      else if (j == n + i)
+        val = 1.0;  // :75-76
+      else if (j == C - 1)
+        val = ((double)n / 4.0) * (1.0 + u01(seed, 1, (uint64_t)i));  // :82
+      if (j == 0) basis[i] = n + i;                                    // :78
+    }
+    TAT(T, ld, row, j) = val;
+  }
+}
+// PrimalSimplexSolver..ctor :27-87 from a host-provided model already copied to the device
+__global__ void k_build_primal(double* T, int ld, int m, int n, const double* obj, const double* coef,
+                               int coef_stride, const int* coef_count, const int* relation,
+                               const double* rhs, int is_max, int* basis) {
+  const int C = n + m + 1;
+  const int row = blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ld; j += gridDim.x * blockDim.x) {
+    double val = 0.0;
+    if (row == 0) {
+      if (j < n) val = is_max ? -obj[j] : obj[j];
+    } else {
+      const int i = row - 1;
+      const bool ge = relation && relation[i] == LPR_REL_GE;  // :36-41
+      const int cnt = coef_count ? coef_count[i] : n;
+      if (j < n) {
+        if (j < cnt) {
+          double a = coef[(size_t)i * coef_stride + j];
+          val = ge ? -a : a;
+        }
+      } else if (j == n + i) {
+        val = 1.0;
+      } else if (j == C - 1) {
+        val = ge ? -rhs[i] : rhs[i];
+      }
+      if (j == 0) basis[i] = n + i;
+    }
+    TAT(T, ld, row, j) = val;
+  }
+}
+
+// ExtractSolution PrimalSimplexSolver.cs:213-252: one warp per decision column
+__global__ void k_extract_solution(TabView v, int n, double* x) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const int R = v.R, C = v.C, ld = v.ld;
+  for (int j = warp; j < n; j += nw) {
+    // sequential semantics: scan rows 1..R-1, stop at the first violation.  A column is basic iff
+    // there is exactly one "1" and it is not preceded/followed by a violation before the scan
+    // breaks; emulate by finding the first violating row and counting ones before it.
+    int firstBad = INT_MAX, ones = 0, firstOne = INT_MAX, secondOne = INT_MAX;
+    for (int i = 1 + lane; i < R; i += 32) {
+      double t = TAT(v.T, ld, i, j);
+      if (fabs(t - 1.0) < 1e-9) {
+        ones++;
+        if (i < firstOne) { secondOne = firstOne; firstOne = i; }
+        else if (i < secondOne) secondOne = i;
+      } else if (fabs(t) > 1e-9) {
+        if (i < firstBad) firstBad = i;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      int ob = __shfl_xor_sync(0xffffffffu, firstBad, o);
+      int o1 = __shfl_xor_sync(0xffffffffu, firstOne, o);
+      int o2 = __shfl_xor_sync(0xffffffffu, secondOne, o);
+      firstBad = min(firstBad, ob);
+      // merge two sorted pairs
+      int a1 = min(firstOne, o1);
+      int a2 = min(max(firstOne, o1), min(secondOne, o2));
+      firstOne = a1;
+      secondOne = a2;
+    }
+    (void)ones;
+    // a second "1" or a non-zero entry anywhere makes the column non-basic (the scan would reach
+    // it: breaks only happen at such rows), so position does not matter.
+    bool basic = (firstOne != INT_MAX) && (secondOne == INT_MAX) && (firstBad == INT_MAX);
+    if (lane == 0) x[j] = basic ? TAT(v.T, ld, firstOne, C - 1) : 0.0;
+  }
+}
+
+// ---- Gomory cut (CuttingPlaneSolver.cs:76-107) ------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads) k_gomory_cut(TabView v, double* cut, int* chosen_out) {
+  __shared__ MinIdx sm[32];
+  const int R = v.R, C = v.C, ld = v.ld;
+  // row whose RHS fractional part is closest to 0.5; first minimum (List.Sort on <= 16 entries is
+  // an insertion sort; exact ties beyond that are unpinned in the reference)
+  int k = block_first_min(R - 1, [&](int q, double& val) {
+    double fr = net_frac(TAT(v.T, ld, q + 1, C - 1));
+    if (!(fr > 1e-9)) return false;
+    val = fabs(__dsub_rn(fr, 0.5));
+    return true;
+  }, sm);
+  if (threadIdx.x == 0) *chosen_out = k;
+  if (k < 0) return;
+  for (int j = threadIdx.x; j < C; j += blockDim.x) cut[j] = -net_frac(TAT(v.T, ld, k + 1, j));
+}
+// append `row` (C doubles on device) as tableau row R
+__global__ void k_append_row(double* T, int ld, int R, int C, const double* row) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ld; j += gridDim.x * blockDim.x)
+    TAT(T, ld, R, j) = (j < C) ? row[j] : 0.0;
+}
+// pivot column on the cut row (CuttingPlaneSolver.cs:113-132) + staging, then generic sweep
+__global__ void __launch_bounds__(kSelThreads) k_cut_select(TabView v, int cut_row) {
+  __shared__ MinIdx sm[32];
+  __shared__ int smi[32];
+  const double EPS = 1e-9;
+  TabState* st = v.st;
+  const int R = v.R, C = v.C, ld = v.ld;
+  double* T = v.T;
+  int e = block_hyst_min(C - 1, [&](int j, double& val) {
+    double a = TAT(T, ld, cut_row, j);
+    if (!(a < -EPS)) return false;
+    double num = T[j];
+    if (!(fabs(num) > EPS)) return false;
+    val = fabs(__ddiv_rn(num, a));
+    return true;
+  }, kPosInf, EPS, sm, smi);
+  if (e < 0) {
+    if (threadIdx.x == 0) { st->status = LPR_NO_PIVOT_COL; st->do_sweep = 0; st->enter = -1; }
+    return;
+  }
+  const double piv = TAT(T, ld, cut_row, e);
+  if (fabs(piv) <= EPS) {
+    if (threadIdx.x == 0) { st->status = LPR_PIVOT_TOO_SMALL; st->do_sweep = 0; }
+    return;
+  }
+  double* colb = st->cur ? v.col[1] : v.col[0];
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? __ddiv_rn(TAT(T, ld, cut_row, j), piv) : 0.0;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) colb[i] = TAT(T, ld, i, e);
+  if (threadIdx.x == 0) {
+    st->enter = e;
+    st->leave = cut_row;
+    st->next_enter = -1;
+    st->do_sweep = 1;
+    st->pivot = piv;
+  }
+}
+// stage a caller-chosen pivot (lpr_tab_pivot_at)
+__global__ void __launch_bounds__(kSelThreads) k_stage_pivot(TabView v, int p, int e) {
+  TabState* st = v.st;
+  const int R = v.R, C = v.C, ld = v.ld;
+  const double piv = TAT(v.T, ld, p, e);
+  double* colb = st->cur ? v.col[1] : v.col[0];
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? __ddiv_rn(TAT(v.T, ld, p, j), piv) : 0.0;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) colb[i] = TAT(v.T, ld, i, e);
+  if (threadIdx.x == 0) {
+    st->enter = e;
+    st->leave = p;
+    st->next_enter = -1;
+    st->do_sweep = 1;
+    st->pivot = piv;
+  }
+}
+// flags used by the cutting-plane driver (CuttingPlaneSolver.cs:19-45): out[0] any RHS < -eps,
+// out[1] objective not optimal, out[2] any fractional RHS
+__global__ void __launch_bounds__(kSelThreads) k_cut_flags(TabView v, int* out) {
+  __shared__ int smi[32];
+  const int R = v.R, C = v.C, ld = v.ld;
+  int neg = 0, nopt = 0, fr = 0;
+  for (int i = 1 + threadIdx.x; i < R; i += blockDim.x) {
+    double rhs = TAT(v.T, ld, i, C - 1);
+    if (rhs < -1e-9) neg++;
+    if (net_frac(rhs) > 1e-9) fr++;
+  }
+  for (int j = threadIdx.x; j < C - 1; j += blockDim.x)
+    if (v.T[j] < -1e-9) nopt++;
+  neg = block_sum_int(neg, smi);
+  nopt = block_sum_int(nopt, smi);
+  fr = block_sum_int(fr, smi);
+  if (threadIdx.x == 0) {
+    out[0] = neg > 0;
+    out[1] = nopt > 0;
+    out[2] = fr > 0;
+  }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+int tab_alloc(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab** out) {
+  if (!out) return fail(LPR_E_BADARG, "out is null");
+  *out = nullptr;
+  if (rows < 1 || cols < 2) return fail(LPR_E_BADARG, "tableau needs rows >= 1 and cols >= 2 (got %d x %d)", rows, cols);
+  int rc = select_device(device);
+  if (rc) return rc;
+  lpr_tab* h = new (std::nothrow) lpr_tab();
+  if (!h) return fail(LPR_E_NOMEM, "host allocation failed");
+  h->device = device;
+  h->R = rows;
+  h->C = cols;
+  h->Rcap = std::max(rows, row_cap);
+  h->Ccap = std::max(cols, col_cap);
+  h->ld = round_up(h->Ccap, 16);
+  h->sms = sm_count(device);
+  const size_t bytes = (size_t)h->Rcap * h->ld * sizeof(double);
+  cudaError_t e;
+#define TRY(x)                                                                                   \
+  if ((e = (x)) != cudaSuccess) {                                                                \
+    lpr_tab_destroy(h);                                                                          \
+    return fail(e == cudaErrorMemoryAllocation ? LPR_E_NOMEM : LPR_E_CUDA, "%s failed: %s", #x, \
+                cudaGetErrorString(e));                                                          \
+  }
+  TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  TRY(cudaMalloc(&h->T, bytes));
+  TRY(cudaMalloc(&h->col[0], sizeof(double) * h->Rcap));
+  TRY(cudaMalloc(&h->col[1], sizeof(double) * h->Rcap));
+  TRY(cudaMalloc(&h->rhs, sizeof(double) * h->Rcap));
+  TRY(cudaMalloc(&h->prow, sizeof(double) * h->ld));
+  TRY(cudaMalloc(&h->basis, sizeof(int) * h->Rcap));
+  TRY(cudaMalloc(&h->st, sizeof(TabState)));
+  TRY(cudaMallocHost(&h->st_host, sizeof(TabState) * 2));
+  TRY(cudaEventCreate(&h->ev0));
+  TRY(cudaEventCreate(&h->ev1));
+  TRY(cudaEventCreateWithFlags(&h->evb[0], cudaEventDisableTiming));
+  TRY(cudaEventCreateWithFlags(&h->evb[1], cudaEventDisableTiming));
+  TRY(cudaMemsetAsync(h->basis, 0xff, sizeof(int) * h->Rcap, h->stream));
+  TRY(cudaMemsetAsync(h->st, 0, sizeof(TabState), h->stream));
+#undef TRY
+  *out = h;
+  return LPR_OK;
+}
+
+int tab_ensure_log(lpr_tab* h, long long cap) {
+  if (cap <= h->log_cap) return LPR_OK;
+  if (h->log) cudaFree(h->log);
+  h->log = nullptr;
+  h->log_cap = 0;
+  LPR_CUDA(cudaMalloc(&h->log, sizeof(int) * 2 * (size_t)cap));
+  h->log_cap = cap;
+  return LPR_OK;
+}
+int tab_ensure_T2(lpr_tab* h) {
+  if (h->T2) return LPR_OK;
+  LPR_CUDA(cudaMalloc(&h->T2, (size_t)h->Rcap * h->ld * sizeof(double)));
+  return LPR_OK;
+}
+
+static int sweep_grid(const lpr_tab* h) {
+  static const int per_sm = std::max(1, env_int("LPR_SWEEP_CTAS_PER_SM", 4));
+  const long long units = (long long)(h->ld / 2 / kSweepThreads) * h->R;
+  long long g = (long long)h->sms * per_sm;
+  // small tableaux: do not launch CTAs that would own no unit, but keep enough threads for the
+  // one-thread-per-row remainder path
+  long long need = std::max<long long>(units, (h->R + kSweepThreads - 1) / kSweepThreads);
+  g = std::max<long long>(1, std::min(g, need));
+  return (int)g;
+}
+
+// launch the sweep that applies the staged pivot; mode selects the instantiation
+static int launch_sweep(lpr_tab* h, int skip, double eps, bool emit, int reverse) {
+  const int g = sweep_grid(h);
+  TabView v = h->view();
+  if (emit)
+    k_sweep<0, false, true, 8><<<g, kSweepThreads, 0, h->stream>>>(v, eps, reverse);
+  else if (skip == 0)
+    k_sweep<0, false, false, 8><<<g, kSweepThreads, 0, h->stream>>>(v, eps, reverse);
+  else if (skip == 1)
+    k_sweep<1, false, false, 8><<<g, kSweepThreads, 0, h->stream>>>(v, eps, reverse);
+  else
+    k_sweep<2, false, false, 8><<<g, kSweepThreads, 0, h->stream>>>(v, eps, reverse);
+  LPR_LAUNCH_CHECK();
+  return LPR_OK;
+}
+int launch_sweep_oop(lpr_tab* h) {
+  const int g = sweep_grid(h);
+  k_sweep<0, true, false, 8><<<g, kSweepThreads, 0, h->stream>>>(h->view(), 0.0, 0);
+  LPR_LAUNCH_CHECK();
+  return LPR_OK;
+}
+
+static int launch_select(lpr_tab* h, int rule, int flags, int* mask) {
+  TabView v = h->view();
+  switch (rule) {
+    case LPR_RULE_PRIMAL:
+      if (flags & F_FUSED)
+        k_primal_select_fused<<<1, kSelThreads, 0, h->stream>>>(v);
+      else
+        k_select<LPR_RULE_PRIMAL><<<1, kSelThreads, 0, h->stream>>>(v, flags, mask);
+      break;
+    case LPR_RULE_PRIMAL2: k_select<LPR_RULE_PRIMAL2><<<1, kSelThreads, 0, h->stream>>>(v, flags, mask); break;
+    case LPR_RULE_DUAL: k_select<LPR_RULE_DUAL><<<1, kSelThreads, 0, h->stream>>>(v, flags, mask); break;
+    case LPR_RULE_SENS: k_select<LPR_RULE_SENS><<<1, kSelThreads, 0, h->stream>>>(v, flags, mask); break;
+    default: return fail(LPR_E_BADARG, "unknown rule %d", rule);
+  }
+  LPR_LAUNCH_CHECK();
+  return LPR_OK;
+}
+
+int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
+                       int64_t* n_pivots, int* pivot_log, int64_t log_cap) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  if (rule < 0 || rule > LPR_RULE_SENS) return fail(LPR_E_BADARG, "unknown rule %d", rule);
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  static const int fused_default = env_int("LPR_TAB_FUSED", 1);
+  static const int batch = std::max(1, env_int("LPR_TAB_BATCH", 32));
+  static const int serp = env_int("LPR_TAB_SERPENTINE", 0);
+  const bool fused = (rule == LPR_RULE_PRIMAL) && fused_default && !(flags & 4);
+  int kflags = (flags & F_PRINT) | (fused ? F_FUSED : 0);
+  if (pivot_log && log_cap > 0) {
+    long long want = log_cap;
+    if (max_pivots >= 0) want = std::min<long long>(want, max_pivots + 1);
+    want = std::min<long long>(want, 1LL << 24);
+    rc = tab_ensure_log(h, want);
+    if (rc) return rc;
+  }
+  int* mask = nullptr;
+  if (rule == LPR_RULE_SENS) LPR_CUDA(cudaMalloc(&mask, sizeof(int) * h->C));
+  TabView v = h->view();
+  if (!(pivot_log && log_cap > 0)) { v.log = nullptr; v.log_cap = 0; }
+  lpr_tab view_holder = *h;  // shallow copy so launch helpers see the (possibly) disabled log
+  view_holder.log = v.log;
+  view_holder.log_cap = v.log_cap;
+  lpr_tab* hv = &view_holder;
+
+  int skip = 0;
+  double eps = 0.0;
+  if (rule == LPR_RULE_PRIMAL2) { skip = 1; eps = 1e-10; }
+  if (rule == LPR_RULE_DUAL) { skip = 1; eps = 1e-9; }
+  if (rule == LPR_RULE_SENS) { skip = 2; eps = 1e-9; }
+
+  LPR_CUDA(cudaEventRecord(h->ev0, h->stream));
+  k_state_reset<<<1, 1, 0, h->stream>>>(h->st, (long long)max_pivots, 0);
+  LPR_LAUNCH_CHECK();
+  if (fused) {
+    k_primal_init<<<1, kSelThreads, 0, h->stream>>>(v);
+    LPR_LAUNCH_CHECK();
+  }
+  // Launch batches of (select, sweep) pairs ahead of the device; the status word of batch b is
+  // inspected while batch b+1 is already queued, so the GPU never waits for the host.
+  int final_status = LPR_RUNNING;
+  long long pivot_parity = 0;
+  int pending = 0;  // batches whose status copy has not been inspected yet
+  int slot = 0;
+  int bsize = std::min(batch, 4);  // small LPs finish in a few pivots: start small, grow
+  while (true) {
+    for (int b = 0; b < bsize; b++) {
+      rc = launch_select(hv, rule, kflags, mask);
+      if (rc) return rc;
+      rc = launch_sweep(hv, skip, eps, fused, serp ? (int)(pivot_parity & 1) : 0);
+      if (rc) return rc;
+      pivot_parity++;
+    }
+    // a trailing select commits the last sweep of the batch so the status word is current
+    rc = launch_select(hv, rule, kflags, mask);
+    if (rc) return rc;
+    LPR_CUDA(cudaMemcpyAsync(&h->st_host[slot], h->st, sizeof(TabState), cudaMemcpyDeviceToHost, h->stream));
+    LPR_CUDA(cudaEventRecord(h->evb[slot], h->stream));
+    // the select above may have staged the next pivot: apply it before the next batch's select
+    rc = launch_sweep(hv, skip, eps, fused, serp ? (int)(pivot_parity & 1) : 0);
+    if (rc) return rc;
+    pivot_parity++;
+    pending++;
+    if (pending == 2 || bsize < batch) {
+      const int old = (pending == 2) ? (slot ^ 1) : slot;
+      LPR_CUDA(cudaEventSynchronize(h->evb[old]));
+      pending--;
+      if (h->st_host[old].status != LPR_RUNNING) break;
+    }
+    slot ^= 1;
+    bsize = std::min(batch, bsize * 2);
+  }
+  LPR_CUDA(cudaEventRecord(h->ev1, h->stream));
+  LPR_CUDA(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(TabState), cudaMemcpyDeviceToHost, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  LPR_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  final_status = h->st_host[0].status;
+  const long long npiv = h->st_host[0].npiv;
+  if (mask) cudaFree(mask);
+  if (status) *status = final_status;
+  if (n_pivots) *n_pivots = npiv;
+  if (pivot_log && log_cap > 0 && npiv > 0) {
+    long long cnt = std::min<long long>(std::min<long long>(npiv, log_cap), h->log_cap);
+    LPR_CUDA(cudaMemcpy(pivot_log, h->log, sizeof(int) * 2 * (size_t)cnt, cudaMemcpyDeviceToHost));
+  }
+  return LPR_OK;
+}
+
+}  // namespace lpr
+
+using namespace lpr;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int lpr_version(void) { return LPR_VERSION; }
+const char* lpr_last_error(void) { return last_error().c_str(); }
+int lpr_device_count(int* count) {
+  if (!count) return fail(LPR_E_BADARG, "count is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(LPR_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return LPR_OK;
+}
+int64_t lpr_launch_count(void) { return g_launches.load(); }
+
+int lpr_tab_destroy(lpr_tab* h) {
+  if (!h) return LPR_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->T);
+  cudaFree(h->T2);
+  cudaFree(h->col[0]);
+  cudaFree(h->col[1]);
+  cudaFree(h->rhs);
+  cudaFree(h->prow);
+  cudaFree(h->basis);
+  cudaFree(h->st);
+  cudaFree(h->log);
+  if (h->st_host) cudaFreeHost(h->st_host);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->evb[0]) cudaEventDestroy(h->evb[0]);
+  if (h->evb[1]) cudaEventDestroy(h->evb[1]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return LPR_OK;
+}
+
+int lpr_tab_upload(lpr_tab* h, const double* host) {
+  if (!h || !host) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  const size_t n = (size_t)h->Rcap * h->ld;
+  k_fill_zero<<<h->sms * 4, 256, 0, h->stream>>>(h->T, n);
+  LPR_LAUNCH_CHECK();
+  LPR_CUDA(cudaMemcpy2DAsync(h->T, sizeof(double) * h->ld, host, sizeof(double) * h->C, sizeof(double) * h->C,
+                             h->R, cudaMemcpyHostToDevice, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  return LPR_OK;
+}
+
+int lpr_tab_create(int device, int rows, int cols, int row_cap, int col_cap, const double* host, lpr_tab** out) {
+  lpr_tab* h = nullptr;
+  int rc = tab_alloc(device, rows, cols, row_cap, col_cap, &h);
+  if (rc) return rc;
+  if (host) {
+    rc = lpr_tab_upload(h, host);
+  } else {
+    k_fill_zero<<<h->sms * 4, 256, 0, h->stream>>>(h->T, (size_t)h->Rcap * h->ld);
+    count_launch();
+    rc = cudaStreamSynchronize(h->stream) == cudaSuccess ? LPR_OK : fail(LPR_E_CUDA, "zero fill failed");
+  }
+  if (rc) {
+    lpr_tab_destroy(h);
+    return rc;
+  }
+  // default basis = trailing identity block (slack columns), as PrimalSimplexSolver.cs:78
+  std::vector<int> b(std::max(1, rows - 1));
+  for (int i = 0; i < rows - 1; i++) b[i] = cols - rows + i;
+  if (rows > 1) cudaMemcpy(h->basis, b.data(), sizeof(int) * (rows - 1), cudaMemcpyHostToDevice);
+  *out = h;
+  return LPR_OK;
+}
+
+int lpr_tab_create_primal(int device, int n, int m, const double* objective, const double* coef, int coef_stride,
+                          const int* coef_count, const int* relation, const double* rhs, int is_max,
+                          lpr_tab** out) {
+  if (n < 1 || m < 1 || !objective || !coef || !rhs || coef_stride < 1)
+    return fail(LPR_E_BADARG, "bad model (n=%d m=%d)", n, m);
+  lpr_tab* h = nullptr;
+  int rc = tab_alloc(device, m + 1, n + m + 1, 0, 0, &h);
+  if (rc) return rc;
+  double *d_obj = nullptr, *d_coef = nullptr, *d_rhs = nullptr;
+  int *d_cnt = nullptr, *d_rel = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_obj); cudaFree(d_coef); cudaFree(d_rhs); cudaFree(d_cnt); cudaFree(d_rel);
+  };
+#define TRY(x)                                                    \
+  if ((x) != cudaSuccess) {                                       \
+    cleanup();                                                    \
+    lpr_tab_destroy(h);                                           \
+    return fail(LPR_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); \
+  }
+  TRY(cudaMalloc(&d_obj, sizeof(double) * n));
+  TRY(cudaMalloc(&d_coef, sizeof(double) * (size_t)m * coef_stride));
+  TRY(cudaMalloc(&d_rhs, sizeof(double) * m));
+  TRY(cudaMemcpyAsync(d_obj, objective, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  TRY(cudaMemcpyAsync(d_coef, coef, sizeof(double) * (size_t)m * coef_stride, cudaMemcpyHostToDevice, h->stream));
+  TRY(cudaMemcpyAsync(d_rhs, rhs, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+  if (coef_count) {
+    TRY(cudaMalloc(&d_cnt, sizeof(int) * m));
+    TRY(cudaMemcpyAsync(d_cnt, coef_count, sizeof(int) * m, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (relation) {
+    TRY(cudaMalloc(&d_rel, sizeof(int) * m));
+    TRY(cudaMemcpyAsync(d_rel, relation, sizeof(int) * m, cudaMemcpyHostToDevice, h->stream));
+  }
+  dim3 grid(std::max(1, std::min(64, (h->ld + 255) / 256)), m + 1);
+  k_build_primal<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, d_obj, d_coef, coef_stride, d_cnt, d_rel, d_rhs,
+                                              is_max, h->basis);
+  count_launch();
+  TRY(cudaGetLastError());
+  TRY(cudaStreamSynchronize(h->stream));
+#undef TRY
+  cleanup();
+  *out = h;
+  return LPR_OK;
+}
+
+int lpr_tab_create_dense_lp(int device, uint64_t seed, int m, int n, lpr_tab** out) {
+  if (n < 1 || m < 1) return fail(LPR_E_BADARG, "bad shape (m=%d n=%d)", m, n);
+  lpr_tab* h = nullptr;
+  int rc = tab_alloc(device, m + 1, n + m + 1, 0, 0, &h);
+  if (rc) return rc;
+  dim3 grid(std::max(1, std::min(64, (h->ld + 255) / 256)), m + 1);
+  k_build_dense_lp<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, seed, h->basis);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    lpr_tab_destroy(h);
+    return fail(LPR_E_CUDA, "dense LP build failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return LPR_OK;
+}
+
+int lpr_tab_dims(const lpr_tab* h, int* rows, int* cols, int* ld) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  if (rows) *rows = h->R;
+  if (cols) *cols = h->C;
+  if (ld) *ld = h->ld;
+  return LPR_OK;
+}
+
+int lpr_tab_read(lpr_tab* h, double* host) {
+  if (!h || !host) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  LPR_CUDA(cudaMemcpy2DAsync(host, sizeof(double) * h->C, h->T, sizeof(double) * h->ld, sizeof(double) * h->C, h->R,
+                             cudaMemcpyDeviceToHost, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  return LPR_OK;
+}
+int lpr_tab_read_row(lpr_tab* h, int row, double* host) {
+  if (!h || !host || row < 0 || row >= h->R) return fail(LPR_E_BADARG, "bad row %d", row);
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  LPR_CUDA(cudaMemcpyAsync(host, h->T + (size_t)row * h->ld, sizeof(double) * h->C, cudaMemcpyDeviceToHost, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  return LPR_OK;
+}
+int lpr_tab_read_col(lpr_tab* h, int col, double* host) {
+  if (!h || !host || col < 0 || col >= h->C) return fail(LPR_E_BADARG, "bad col %d", col);
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  LPR_CUDA(cudaMemcpy2DAsync(host, sizeof(double), h->T + col, sizeof(double) * h->ld, sizeof(double), h->R,
+                             cudaMemcpyDeviceToHost, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  return LPR_OK;
+}
+int lpr_tab_get_basis(lpr_tab* h, int* basis) {
+  if (!h || !basis) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  if (h->R > 1) {
+    LPR_CUDA(cudaMemcpyAsync(basis, h->basis, sizeof(int) * (h->R - 1), cudaMemcpyDeviceToHost, h->stream));
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return LPR_OK;
+}
+int lpr_tab_set_basis(lpr_tab* h, const int* basis) {
+  if (!h || !basis) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  if (h->R > 1) {
+    LPR_CUDA(cudaMemcpyAsync(h->basis, basis, sizeof(int) * (h->R - 1), cudaMemcpyHostToDevice, h->stream));
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return LPR_OK;
+}
+
+int lpr_tab_solve(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status, int64_t* n_pivots,
+                  int* pivot_log, int64_t log_cap) {
+  return tab_solve_internal(h, rule, max_pivots, flags, status, n_pivots, pivot_log, log_cap);
+}
+
+int lpr_tab_step(lpr_tab* h, int rule, int* enter_col, int* leave_row, int* status) {
+  int st = 0;
+  int64_t np = 0;
+  int log[2] = {-1, -1};
+  // PRIMAL2 / DUAL test their counter after the pivot: a cap of 1 with the print flag stops
+  // after exactly one pivot; the other rules test before the pivot.
+  int flags = (rule == LPR_RULE_PRIMAL2 || rule == LPR_RULE_DUAL) ? 1 : 0;
+  int rc = tab_solve_internal(h, rule, 1, flags, &st, &np, log, 1);
+  if (rc) return rc;
+  if (np >= 1) {
+    if (leave_row) *leave_row = log[0];
+    if (enter_col) *enter_col = log[1];
+    if (st == LPR_ITER_LIMIT) st = LPR_RUNNING;
+  } else {
+    if (leave_row) *leave_row = -1;
+    if (enter_col) *enter_col = -1;
+  }
+  if (status) *status = st;
+  return LPR_OK;
+}
+
+int lpr_tab_pivot_at(lpr_tab* h, int row, int col, double skip_eps, int skip_mode) {
+  if (!h || row < 0 || row >= h->R || col < 0 || col >= h->C) return fail(LPR_E_BADARG, "bad pivot (%d,%d)", row, col);
+  if (skip_mode < 0 || skip_mode > 2) return fail(LPR_E_BADARG, "bad skip_mode %d", skip_mode);
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  k_state_reset<<<1, 1, 0, h->stream>>>(h->st, -1, 0);
+  LPR_LAUNCH_CHECK();
+  k_stage_pivot<<<1, kSelThreads, 0, h->stream>>>(h->view(), row, col);
+  LPR_LAUNCH_CHECK();
+  rc = launch_sweep(h, skip_mode, skip_eps, false, 0);
+  if (rc) return rc;
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  return LPR_OK;
+}
+
+int lpr_tab_extract_solution(lpr_tab* h, int n, double* x) {
+  if (!h || !x || n < 0 || n > h->C - 1) return fail(LPR_E_BADARG, "bad n %d", n);
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  if (n == 0) return LPR_OK;
+  double* dx = nullptr;
+  LPR_CUDA(cudaMalloc(&dx, sizeof(double) * n));
+  const int blocks = std::max(1, std::min(h->sms * 8, (n + 7) / 8));
+  k_extract_solution<<<blocks, 256, 0, h->stream>>>(h->view(), n, dx);
+  count_launch();
+  cudaError_t e = cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(dx);
+  if (e != cudaSuccess) return fail(LPR_E_CUDA, "extract_solution: %s", cudaGetErrorString(e));
+  return LPR_OK;
+}
+
+int lpr_tab_objective(lpr_tab* h, double* z) {
+  if (!h || !z) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  LPR_CUDA(cudaMemcpyAsync(z, h->T + (h->C - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  return LPR_OK;
+}
+
+int lpr_tab_last_solve_ms(const lpr_tab* h, float* ms) {
+  if (!h || !ms) return fail(LPR_E_BADARG, "null argument");
+  *ms = h->last_ms;
+  return LPR_OK;
+}
+
+int lpr_tab_append_row(lpr_tab* h, const double* row) {
+  if (!h || !row) return fail(LPR_E_BADARG, "null argument");
+  if (h->R + 1 > h->Rcap) return fail(LPR_E_CAPACITY, "no row headroom (rows=%d cap=%d)", h->R, h->Rcap);
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  double* d = nullptr;
+  LPR_CUDA(cudaMalloc(&d, sizeof(double) * h->C));
+  cudaError_t e = cudaMemcpyAsync(d, row, sizeof(double) * h->C, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    k_append_row<<<std::max(1, (h->ld + 255) / 256), 256, 0, h->stream>>>(h->T, h->ld, h->R, h->C, d);
+    count_launch();
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(LPR_E_CUDA, "append_row: %s", cudaGetErrorString(e));
+  h->R += 1;
+  return LPR_OK;
+}
+
+int lpr_tab_gomory_cut(lpr_tab* h, int* chosen_row, double* cut_host, int append) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  if (append && h->R + 1 > h->Rcap) return fail(LPR_E_CAPACITY, "no row headroom (rows=%d cap=%d)", h->R, h->Rcap);
+  double* dcut = nullptr;
+  int* dch = nullptr;
+  LPR_CUDA(cudaMalloc(&dcut, sizeof(double) * h->C));
+  cudaError_t e = cudaMalloc(&dch, sizeof(int));
+  int chosen = -1;
+  if (e == cudaSuccess) {
+    k_gomory_cut<<<1, kSelThreads, 0, h->stream>>>(h->view(), dcut, dch);
+    count_launch();
+    e = cudaMemcpyAsync(&chosen, dch, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  }
+  if (e == cudaSuccess && chosen >= 0) {
+    if (cut_host) e = cudaMemcpy(cut_host, dcut, sizeof(double) * h->C, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && append) {
+      k_append_row<<<std::max(1, (h->ld + 255) / 256), 256, 0, h->stream>>>(h->T, h->ld, h->R, h->C, dcut);
+      count_launch();
+      e = cudaStreamSynchronize(h->stream);
+      if (e == cudaSuccess) h->R += 1;
+    }
+  }
+  cudaFree(dcut);
+  cudaFree(dch);
+  if (e != cudaSuccess) return fail(LPR_E_CUDA, "gomory_cut: %s", cudaGetErrorString(e));
+  if (chosen_row) *chosen_row = chosen;
+  return LPR_OK;
+}
+
+// CuttingPlaneSolver.CuttingPlaneSolution (CuttingPlaneSolver.cs:64-229); the recursion of :220
+// is a loop.  Every tableau operation runs on the device; the host only sequences the steps.
+int lpr_tab_cutting_plane(lpr_tab* h, int max_cuts, int* status, int* n_cuts, int* cut_log, int cut_log_cap) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  int* dflags = nullptr;
+  LPR_CUDA(cudaMalloc(&dflags, sizeof(int) * 4));
+  int st = LPR_RUNNING, cuts = 0;
+  auto read_flags = [&](int* f3) -> int {
+    k_cut_flags<<<1, kSelThreads, 0, h->stream>>>(h->view(), dflags);
+    count_launch();
+    cudaError_t e = cudaMemcpyAsync(f3, dflags, sizeof(int) * 3, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    return e == cudaSuccess ? LPR_OK : fail(LPR_E_CUDA, "cut flags: %s", cudaGetErrorString(e));
+  };
+  while (true) {
+    if (max_cuts >= 0 && cuts >= max_cuts) { st = LPR_ITER_LIMIT; break; }
+    if (h->R + 1 > h->Rcap) { st = LPR_ITER_LIMIT; break; }
+    int chosen = -1;
+    rc = lpr_tab_gomory_cut(h, &chosen, nullptr, 1);  // steps 1-5 (:76-111)
+    if (rc) break;
+    if (chosen < 0) { st = LPR_NO_CUT_NEEDED; break; }
+    const int cut_row = h->R - 1;
+    int nd = 0, np = 0, pcol = -1;
+    auto log_cut = [&]() {
+      if (cut_log && cuts < cut_log_cap) {
+        cut_log[4 * cuts + 0] = chosen;
+        cut_log[4 * cuts + 1] = pcol;
+        cut_log[4 * cuts + 2] = nd;
+        cut_log[4 * cuts + 3] = np;
+      }
+      cuts++;
+    };
+    // step 6-7 (:113-176): pivot on the cut row
+    k_state_reset<<<1, 1, 0, h->stream>>>(h->st, -1, 0);
+    count_launch();
+    k_cut_select<<<1, kSelThreads, 0, h->stream>>>(h->view(), cut_row);
+    count_launch();
+    rc = launch_sweep(h, 1, 1e-9, false, 0);
+    if (rc) break;
+    TabState hs;
+    if (cudaMemcpyAsync(&hs, h->st, sizeof hs, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      rc = fail(LPR_E_CUDA, "cutting plane state read failed");
+      break;
+    }
+    pcol = hs.enter;
+    if (hs.status == LPR_NO_PIVOT_COL || hs.status == LPR_PIVOT_TOO_SMALL) {
+      log_cut();
+      st = hs.status;
+      break;
+    }
+    int fl[3];
+    if ((rc = read_flags(fl))) break;
+    bool needDual = fl[0], needPrimal = fl[1];
+    if (needDual) {  // :186-194, printSteps: true
+      int dst = 0;
+      int64_t dn = 0;
+      rc = tab_solve_internal(h, LPR_RULE_DUAL, 10000, 1, &dst, &dn, nullptr, 0);
+      if (rc) break;
+      nd = (int)dn;
+      if (dst != LPR_OPTIMAL) {
+        log_cut();
+        st = dst == LPR_PIVOT_TOO_SMALL ? LPR_PIVOT_TOO_SMALL : LPR_INFEASIBLE;
+        break;
+      }
+      if ((rc = read_flags(fl))) break;
+      needPrimal = fl[1];
+    }
+    if (needPrimal) {  // :196-212, printSteps: true; the bool result is ignored by the reference
+      int pst = 0;
+      int64_t pn = 0;
+      rc = tab_solve_internal(h, LPR_RULE_PRIMAL2, 10000, 1, &pst, &pn, nullptr, 0);
+      if (rc) break;
+      np = (int)pn;
+      if (pst == LPR_PIVOT_TOO_SMALL) {
+        log_cut();
+        st = LPR_PIVOT_TOO_SMALL;
+        break;
+      }
+    }
+    log_cut();
+    if ((rc = read_flags(fl))) break;
+    if (!fl[1] && !fl[0]) {  // :215-226
+      if (fl[2]) continue;
+      st = LPR_OPTIMAL;
+      break;
+    }
+    st = LPR_CUT_STEP_DONE;  // :228
+    break;
+  }
+  cudaFree(dflags);
+  if (rc) return rc;
+  if (status) *status = st;
+  if (n_cuts) *n_cuts = cuts;
+  return LPR_OK;
+}
+
+}  // extern "C"

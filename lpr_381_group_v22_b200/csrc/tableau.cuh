@@ -1,0 +1,73 @@
+// tableau.cuh -- device tableau handle shared by tableau.cu / cutting.cu / bb.cu.
+#pragma once
+#include "common.cuh"
+
+namespace lpr {
+
+// Device-resident solver state: written only by the single-CTA select kernels, read by sweeps.
+struct TabState {
+  int status;      // LPR_RUNNING / OPTIMAL / ...
+  int enter;       // entering column of the pivot being applied (or -1)
+  int leave;       // leaving row of the pivot being applied
+  int next_enter;  // fused primal path: entering column of the NEXT pivot (-1 = optimal after this one)
+  int do_sweep;    // 1 when the following sweep launch must apply (leave, enter)
+  int cur;         // which colbuf holds the factor column of the pivot being applied
+  int src;         // out-of-place (B&B) path: which of T/T2 holds the current tableau
+  int phase;       // rule specific phase (SENS / BB: 0 dual, 1 primal)
+  int have_prev;   // B&B: at least one pivot done (previous tableau is in the other buffer)
+  int dropped;     // B&B: the last tableau was dropped (:392-400)
+  long long npiv;
+  long long max_piv;
+  double pivot;
+};
+
+struct TabView {
+  double* T;    // current tableau (in-place rules) or buffer 0 (out-of-place)
+  double* T2;   // buffer 1 (out-of-place rules), may be null
+  int ld;       // leading dimension in doubles (multiple of 16 => rows are 128 B aligned)
+  int R, C;     // logical rows / cols (last col = RHS)
+  double* col[2];  // factor column double buffer, each Rcap doubles
+  double* rhs;     // RHS column copy (fused primal path)
+  double* prow;    // normalised pivot row, ld doubles (padding = 0)
+  int* basis;      // R-1 entries
+  TabState* st;
+  int* log;  // (row, col) pairs
+  long long log_cap;
+};
+
+}  // namespace lpr
+
+struct lpr_tab {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int R = 0, C = 0, Rcap = 0, Ccap = 0, ld = 0;
+  double* T = nullptr;
+  double* T2 = nullptr;  // lazily allocated second buffer (out-of-place B&B pivots)
+  double* col[2] = {nullptr, nullptr};
+  double* rhs = nullptr;
+  double* prow = nullptr;
+  int* basis = nullptr;
+  lpr::TabState* st = nullptr;
+  lpr::TabState* st_host = nullptr;  // pinned mirror
+  int* log = nullptr;
+  long long log_cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evb[2] = {nullptr, nullptr};
+  float last_ms = 0.f;
+  int sms = 148;
+  lpr::TabView view() const {
+    lpr::TabView v;
+    v.T = T; v.T2 = T2; v.ld = ld; v.R = R; v.C = C;
+    v.col[0] = col[0]; v.col[1] = col[1]; v.rhs = rhs; v.prow = prow;
+    v.basis = basis; v.st = st; v.log = log; v.log_cap = log_cap;
+    return v;
+  }
+};
+
+namespace lpr {
+// internal helpers implemented in tableau.cu
+int tab_alloc(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab** out);
+int tab_ensure_log(lpr_tab* h, long long cap);
+int tab_ensure_T2(lpr_tab* h);
+int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
+                       int64_t* n_pivots, int* pivot_log, int64_t log_cap);
+}  // namespace lpr

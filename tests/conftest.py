@@ -1,0 +1,42 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build liblprb200.so / the oracle if stale (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB) or os.environ.get("LPR_REBUILD"):
+        g.build()
+    else:
+        import oracle_lib
+        oracle_lib.build()
+    yield
+
+
+def _has_gpu():
+    try:
+        import lpr_381_group_v22_b200 as L
+        return L.device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)

@@ -1,0 +1,288 @@
+"""GPU parity tests for the dense tableau path (PrimalSimplexSolver / PrimalSimplexSolver2 /
+DualSimplexSolver / cutting plane) through the C ABI, against the CPU oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import lpr_381_group_v22_b200 as L
+from lpr_381_group_v22_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_bit_equal(a, b, what="tableau"):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if not np.array_equal(bits(a), bits(b)):
+        bad = np.argwhere(bits(a) != bits(b))
+        i = tuple(bad[0])
+        raise AssertionError(f"{what}: {len(bad)} elements differ, first at {i}: {a[i]!r} vs {b[i]!r}")
+
+
+def cli_model(obj, cons):
+    cons = [L.Constraint(*c) for c in cons]
+    L.add_cli_bound_rows(len(obj), cons)
+    return obj, cons
+
+
+def oracle_cons(cons):
+    return [(c.Coefficients, c.Relation, c.RHS) for c in cons]
+
+
+MODEL_A = ([2, 3, 3, 5, 2, 4], [([11, 8, 6, 14, 10, 10], "<=", 40)])
+MODEL_B = ([2, 3, 4], [([1, 2, 3], "<=", 10), ([3, 2, 1], ">=", 15)])
+
+
+@pytest.mark.parametrize("model", [MODEL_A, MODEL_B])
+@pytest.mark.parametrize("cli", [True, False])
+@pytest.mark.parametrize("trace", [True, False])
+def test_fixture_models_primal(model, cli, trace):
+    obj, cons = model
+    cons = [L.Constraint(*c) for c in cons]
+    if cli:
+        L.add_cli_bound_rows(len(obj), cons)
+    s = L.PrimalSimplexSolver(obj, cons, trace=trace)
+    s.Solve()
+    T0, b0 = O.primal_build(obj, oracle_cons(cons))
+    ref = O.primal_solve(T0, b0)
+    assert s.Status == ref["status"]
+    assert s.PivotLog == [tuple(x) for x in ref["log"].tolist()]
+    assert s.BasicVariables == ref["basis"].tolist()
+    assert_bit_equal(s.GetFinalTableau(), ref["T"])
+    assert bits(np.array(s.SolutionVector)).tolist() == bits(O.primal_extract(ref["T"], len(obj))).tolist()
+    assert s.FinalZ == ref["T"][0, -1]
+    if trace:
+        assert len(s.IterationSnapshots) == ref["n_pivots"] + 2
+
+
+def test_appendix_c_known_answers():
+    obj, cons = cli_model(*MODEL_A)
+    s = L.PrimalSimplexSolver(obj, cons)
+    s.Solve()
+    assert s.PivotLog == [(5, 3), (7, 5), (3, 1), (4, 2), (1, 0), (1, 4)]
+    assert s.BasicVariables == [4, 7, 1, 2, 3, 11, 5]
+    assert s.FinalZ.hex() == "0x1.ecccccccccccdp+3"
+    assert s.SolutionVector == [0.0, 1.0, 1.0, 1.0, 0.2, 1.0]
+    obj, cons = cli_model(*MODEL_B)
+    s = L.PrimalSimplexSolver(obj, cons)
+    s.Solve()
+    assert s.PivotLog == [(5, 2), (4, 1), (3, 0)]
+    assert s.FinalZ == 9.0 and s.SolutionVector == [1.0, 1.0, 1.0]
+    assert s.GetFinalTableau()[:, -1].tolist() == [9.0, 4.0, -9.0, 1.0, 1.0, 1.0]  # Q3: infeasible "optimum"
+
+
+def test_build_matches_oracle_ctor():
+    rng = np.random.default_rng(5)
+    n, m = 7, 5
+    obj = rng.normal(size=n).round(3).tolist()
+    cons = []
+    for i in range(m):
+        k = [n, n + 3, n - 2, n, n + 1][i]  # ragged coefficient lists (only the first n are read)
+        cons.append(L.Constraint(rng.normal(size=k).round(3).tolist(), ["<=", ">=", "=", ">=", "<="][i],
+                                 float(rng.normal())))
+    for is_max in (True, False):
+        with L.DeviceTableau.from_model(obj, cons, is_max) as t:
+            T0, b0 = O.primal_build(obj, oracle_cons(cons), is_max)
+            assert_bit_equal(t.read(), T0)
+            assert t.basis.tolist() == b0.tolist()
+
+
+@pytest.mark.parametrize("m,n,seed", [(8, 16, 1), (33, 70, 2), (64, 128, 3), (100, 37, 4), (255, 513, 5)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_random_dense_lp_bitexact(m, n, seed, fused):
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    ref = O.primal_solve(T0, b0)
+    with L.DeviceTableau.from_host(T0) as t:
+        r = t.solve(L.RULE_PRIMAL, fused=fused)
+        assert r["status"] == ref["status"] == L.OPTIMAL
+        assert r["n_pivots"] == ref["n_pivots"]
+        assert r["log"].tolist() == ref["log"].tolist()
+        assert t.basis.tolist() == ref["basis"].tolist()
+        assert_bit_equal(t.read(), ref["T"])
+        assert_bit_equal(t.extract_solution(n), O.primal_extract(ref["T"], n), "solution")
+
+
+def test_device_generator_matches_oracle():
+    m, n, seed = 40, 90, 381
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    with L.DeviceTableau.dense_lp(seed, m, n) as t:
+        assert_bit_equal(t.read(), T0)
+        assert t.basis.tolist() == b0.tolist()
+
+
+def test_max_pivots_and_step():
+    m, n, seed = 30, 60, 9
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    ref = O.primal_solve(T0, b0, max_pivots=5)
+    assert ref["status"] == O.ITER_LIMIT
+    with L.DeviceTableau.from_host(T0) as t:
+        r = t.solve(L.RULE_PRIMAL, max_pivots=5)
+        assert r["status"] == L.ITER_LIMIT and r["n_pivots"] == 5
+        assert_bit_equal(t.read(), ref["T"])
+    with L.DeviceTableau.from_host(T0) as t:
+        for k in range(5):
+            e, l, st = t.step(L.RULE_PRIMAL)
+            assert (l, e) == tuple(ref["log"][k]) and st == L.RUNNING
+        assert_bit_equal(t.read(), ref["T"])
+
+
+def test_unbounded_and_degenerate():
+    # unbounded: max x1 with x1 - x2 <= 1
+    T = np.array([[-1.0, 0.0, 0.0, 0.0], [1.0, -1.0, 1.0, 1.0]])
+    # second pivot: entering x2 has only a negative entry
+    ref = O.primal_solve(T)
+    with L.DeviceTableau.from_host(T) as t:
+        r = t.solve(L.RULE_PRIMAL)
+        assert r["status"] == ref["status"]
+        assert r["log"].tolist() == ref["log"].tolist()
+        assert_bit_equal(t.read(), ref["T"])
+    s = L.PrimalSimplexSolver([1.0, 1.0], [L.Constraint([1.0, -1.0], "<=", 1.0)])
+    s.Solve()
+    assert s.Status == L.UNBOUNDED and s.SolutionVector is None and s.FinalZ == 0.0
+    # ties: duplicated columns / rows => lowest index wins in both rules
+    T = np.array([[-3.0, -3.0, -1.0, 0, 0, 0, 0.0], [1, 1, 1, 1, 0, 0, 4.0], [1, 1, 0, 0, 1, 0, 4.0],
+                  [2, 2, 1, 0, 0, 1, 8.0]])
+    ref = O.primal_solve(T)
+    with L.DeviceTableau.from_host(T) as t:
+        for fused in (True, False):
+            t.upload(T)
+            r = t.solve(L.RULE_PRIMAL, fused=fused)
+            assert r["log"].tolist() == ref["log"].tolist()
+            assert_bit_equal(t.read(), ref["T"])
+
+
+def _random_tableau(rng, R, C, neg_rhs=False):
+    T = rng.integers(-4, 9, size=(R, C)).astype(float)
+    T[1:, C - 1 - (R - 1):C - 1] = np.eye(R - 1)
+    T[0, C - 1 - (R - 1):] = 0.0
+    T[1:, -1] = rng.integers(1, 20, size=R - 1)
+    T[0, :C - R] = -rng.integers(1, 9, size=C - R)
+    if neg_rhs:
+        T[0, :C - R] = rng.integers(1, 9, size=C - R)
+        T[1:, :C - R] = -np.abs(T[1:, :C - R]) - 1
+        T[1:, -1] = -rng.integers(1, 20, size=R - 1)
+    return T
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_primal2_rule(seed):
+    rng = np.random.default_rng(seed)
+    T = _random_tableau(rng, 6 + seed, 14 + 2 * seed)
+    T[1:, :4] = np.abs(T[1:, :4]) + 1  # bounded
+    for ps in (False, True):
+        ref = O.primal2_solve(T, 10000, ps)
+        s = L.PrimalSimplexSolver2(T[0], [r for r in T[1:]])
+        ok = s.Solve(10000, ps)
+        assert ok == (ref["status"] == O.OPTIMAL)
+        assert s.PivotLog == [tuple(x) for x in ref["log"].tolist()]
+        obj, rows = s.GetRows(False)
+        assert_bit_equal(np.vstack([obj[None, :], np.array(rows)]), ref["T"])
+    ref = O.primal2_solve(T, 2, True)  # iteration cap only live when printing (Q16)
+    with L.DeviceTableau.from_host(T) as t:
+        r = t.solve(L.RULE_PRIMAL2, max_pivots=2, print_steps=True)
+        assert r["status"] == ref["status"] and r["n_pivots"] == ref["n_pivots"]
+        assert_bit_equal(t.read(), ref["T"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_dual_rule(seed):
+    rng = np.random.default_rng(100 + seed)
+    T = _random_tableau(rng, 5 + seed, 12 + 2 * seed, neg_rhs=True)
+    ref = O.dual_solve(T, 10000, True)
+    obj = T[0].copy()
+    rows = [r.copy() for r in T[1:]]
+    d = L.DualSimplexSolver()
+    ok = d.Solve(obj, rows, 10000, True)
+    assert ok == (ref["status"] == O.OPTIMAL)
+    assert d.PivotLog == [tuple(x) for x in ref["log"].tolist()]
+    assert_bit_equal(np.vstack([obj[None, :], np.array(rows)]), ref["T"])
+
+
+def test_hysteresis_fallback_paths():
+    # near-ties inside the 1e-9/1e-10 windows force the literal sequential replay
+    T = np.array([[-1.0, -1.0 - 5e-11, -1.0 - 1.2e-10, -0.5, 0, 0, 0.0],
+                  [1, 1, 1, 1, 1, 0, 4.0], [1, 1, 1 + 5e-11, 2, 0, 1, 4.0]])
+    ref = O.primal2_solve(T)
+    with L.DeviceTableau.from_host(T) as t:
+        r = t.solve(L.RULE_PRIMAL2)
+        assert r["log"].tolist() == ref["log"].tolist()
+        assert_bit_equal(t.read(), ref["T"])
+    T = np.array([[1.0, 2.0, 3.0, 0, 0, 0, 0.0], [-1, -2, -1, 1, 0, 0, -2.0], [-1, -1, -3, 0, 1, 0, -2.0 - 5e-10],
+                  [-2, -1, -1, 0, 0, 1, -2.0 - 1.2e-9]])
+    ref = O.dual_solve(T)
+    with L.DeviceTableau.from_host(T) as t:
+        r = t.solve(L.RULE_DUAL, max_pivots=10000, print_steps=True)
+        assert r["log"].tolist() == ref["log"].tolist()
+        assert_bit_equal(t.read(), ref["T"])
+
+
+def test_pivot_at_and_reads():
+    rng = np.random.default_rng(3)
+    T = rng.normal(size=(9, 21))
+    ref = T.copy()
+    O.lib().orc_primal_pivot(9, 21, ref.ctypes.data_as(O._dp), 4, 7, 1)
+    with L.DeviceTableau.from_host(T) as t:
+        t.pivot_at(4, 7)
+        assert_bit_equal(t.read(), ref)
+        assert_bit_equal(t.read_row(4), ref[4], "row")
+        assert_bit_equal(t.read_col(7), ref[:, 7], "col")
+
+
+def test_gomory_cut_and_cutting_plane_model_a():
+    obj, cons = cli_model(*MODEL_A)
+    s = L.PrimalSimplexSolver(obj, cons)
+    s.Solve()
+    Tf = s.GetFinalTableau()
+    row, cut = O.gomory_cut(Tf)
+    with L.DeviceTableau.from_host(Tf, row_cap=Tf.shape[0] + 16) as t:
+        r2, c2 = t.gomory_cut()
+        assert r2 == row == 0
+        assert_bit_equal(c2, cut, "cut")
+        ref = O.cutting_plane(Tf)
+        res = t.cutting_plane()
+        assert res["status"] == ref["status"] == L.OPTIMAL
+        assert res["log"].tolist() == ref["log"].tolist() == [[0, 0, 1, 1]]
+        assert_bit_equal(t.read(), ref["T"])
+        assert t.read()[0, -1] == 15.0
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_cutting_plane_random_ip(seed):
+    m, n = 4 + seed, 6 + seed
+    A, b, c = O.gen_dense_ip(1000 + seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    lp = O.primal_solve(T0, b0)
+    ref = O.cutting_plane(lp["T"], max_cuts=12)
+    with L.DeviceTableau.from_host(lp["T"], row_cap=lp["T"].shape[0] + 16) as t:
+        res = t.cutting_plane(max_cuts=12)
+        assert res["status"] == ref["status"]
+        assert res["log"].tolist() == ref["log"].tolist()
+        assert_bit_equal(t.read(), ref["T"])
+
+
+def test_full_size_window_cfg2():
+    """BASELINE cfg2 shape (4097 x 12289): the first pivots bit-exact against the oracle, generated
+    on device, plus size-independent invariants afterwards."""
+    m, n, seed, K = 4096, 8192, 383, 6
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    del A
+    ref = O.primal_solve(T0, b0, max_pivots=K, threads=8)
+    with L.DeviceTableau.dense_lp(seed, m, n) as t:
+        r = t.solve(L.RULE_PRIMAL, max_pivots=K)
+        assert r["log"].tolist() == ref["log"].tolist()
+        got = t.read()
+        assert_bit_equal(got, ref["T"])
+        # basic columns are unit vectors; objective row of basic columns is 0
+        basis = t.basis
+        for i in (0, 1, m // 2, m - 1):
+            col = got[:, basis[i]]
+            assert col[i + 1] == 1.0 and np.count_nonzero(col) == 1
