@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native dense simplex pivot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): synthetic dense LP m=4096 n=8192 fp64, primal tableau simplex
+(reference layout 4097 x 12289, SURVEY.md 8d generator, seed 383).  One "step" = one full Solve()
+from the slack basis to optimality.  Metric = simplex pivots/s (whole job, all N GPUs).
+
+  value     : pivots/s with the tableau already resident in HBM (generated on the device), timed
+              with CUDA events on the library's stream, max over ranks.
+  e2e       : the same solve through the C ABI with HOST (pinned) model arrays: H2D of A/b/c,
+              device-side tableau build, Solve(), D2H of the final tableau + basis + x + z.
+  roofline  : HBM roofline of the dominant kernel (the rank-1 sweep) and of the whole pivot.
+  cpu_baseline : the CPU oracle (C++ restatement of the reference's C# loops, single thread like the
+              reference) on a bounded sample of the same workload, on this box's host cores.
+
+With N > 1 (torchrun, one process per GPU) the tableau path runs as independent replicas (it does
+not shard: DESIGN.md "multi-GPU"); B&B nodes/s at N GPUs is reported under "bb".
+`--impl reference` times the CPU oracle with all host threads (the reference arm of the contract).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+M, NV, SEED = 4096, 8192, 383
+R, CC = M + 1, NV + M + 1
+BYTES_PER_PIVOT = 16.0 * R * CC + 8.0 * (CC - 1) + 16.0 * (R - 1) + 8.0 * (R + CC)
+BYTES_SWEEP = 16.0 * R * CC + 8.0 * (R + CC)  # tableau read+write once, staged column and row read
+NOMINAL_HBM_GBS = 8000.0
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def barrier_max(dist, local, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
+
+
+def pinned(shape):
+    import numpy as np
+    try:
+        import torch
+        return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    except Exception:
+        return np.empty(shape)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """CPU oracle (C++ restatement of PrimalSimplexSolver.cs:102-211; the image has no .NET) with all
+    host threads, on a bounded sample of the cfg2 workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    import oracle_lib as O
+    threads = os.cpu_count() or 1
+    sample = int(os.environ.get("LPR_REF_SAMPLE_PIVOTS", "16"))
+    A, b, c = O.gen_dense_lp(SEED, M, NV)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(M)])
+    del A
+    total = args.warmup + args.steps
+    t_step = []
+    T, basis = T0, b0
+    for s in range(total):
+        t = time.perf_counter()
+        r = O.primal_solve(T, basis, max_pivots=sample, threads=threads, log_cap=sample)
+        dt = time.perf_counter() - t
+        T, basis = r["T"], r["basis"]  # continue the same solve: every pivot costs the same
+        if s >= args.warmup:
+            t_step.append(dt)
+    sec = sum(t_step)
+    val = sample * len(t_step) / sec
+    line = {
+        "impl": "reference", "metric": "simplex pivots/s (dense 4096x8192 fp64 primal tableau)",
+        "value": val, "unit": "pivots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sec / len(t_step), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2 dense LP m=4096 n=8192 primal tableau simplex, tableau 4097x12289",
+                   "step": f"{sample} consecutive pivots of the same solve (bounded sample)", "seed": SEED},
+        "cpu_baseline": {"value": val, "unit": "pivots/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} pivots per step x {len(t_step)} steps; C++ restatement of the "
+                                   "reference C# loops (no .NET toolchain in the image), row loop of Pivot "
+                                   f"split over {threads} threads (bit-identical)"},
+        "e2e": {"value": val, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "tableau_gbs": 16.0 * R * CC * val / 1e9,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--max-pivots", type=int, default=int(os.environ.get("LPR_BENCH_MAX_PIVOTS", "-1")),
+                    help="cap pivots per step (debug); default: solve to optimality")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    import numpy as np
+    import lpr_381_group_v22_b200 as L
+    from lpr_381_group_v22_b200 import _native as N
+
+    if L.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: lpr_381_group_v22_b200 has no CPU fallback")
+    dev = local
+    peaks, peak_kind = measured_peaks()
+    lib = N.lib()
+
+    def solve_resident(max_pivots):
+        """one step with the inputs resident in HBM: returns (pivots, device ms, status)"""
+        t = L.DeviceTableau.dense_lp(SEED, M, NV, device=dev)
+        r = t.solve(L.RULE_PRIMAL, max_pivots=max_pivots, log_cap=0)
+        ms = t.last_solve_ms
+        z = t.objective()
+        t.close()
+        return r["n_pivots"], ms, r["status"], z
+
+    # -------- value: inputs resident in HBM --------------------------------------------------
+    for _ in range(args.warmup):
+        solve_resident(args.max_pivots)
+    barrier(dist, local)
+    sampler = ClockSampler(dev)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = L.launch_count()
+    t0 = time.perf_counter()
+    piv_total, ms_total, status, zval = 0, 0.0, None, None
+    for _ in range(args.steps):
+        p, ms, status, zval = solve_resident(args.max_pivots)
+        piv_total += p
+        ms_total += ms
+    t1 = time.perf_counter()
+    launches = L.launch_count() - l0
+    clocks = sampler.stop(t0, t1)
+    barrier(dist, local)
+    ms_max = barrier_max(dist, local, ms_total)      # device time (CUDA events), max over ranks
+    wall_max = barrier_max(dist, local, (t1 - t0) * 1e3)
+    pivots_per_step = piv_total / args.steps
+    value = world * piv_total / (ms_max / 1e3)
+
+    # -------- dominant kernel duration: event pairs around each sweep launch (short pass) ----
+    sweep_us = None
+    try:
+        t = L.DeviceTableau.dense_lp(SEED, M, NV, device=dev)
+        st, npv = C.c_int(), C.c_int64()
+        N.check(lib.lpr_tab_solve(t._h, L.RULE_PRIMAL, 96, 8, C.byref(st), C.byref(npv), None, 0))  # flag 8 = time sweeps
+        us = C.c_float()
+        if hasattr(lib, "lpr_tab_last_sweep_us"):
+            lib.lpr_tab_last_sweep_us.argtypes = [N.vp, C.POINTER(C.c_float)]
+            N.check(lib.lpr_tab_last_sweep_us(t._h, C.byref(us)))
+            sweep_us = us.value if us.value > 0 else None
+        t.close()
+    except Exception as ex:  # measurement aid only
+        sweep_us = None
+
+    # -------- e2e: host buffers through the C ABI (rank-local replica) --------------------------
+    import oracle_lib as O  # only to GENERATE the host-side model arrays (same generator as the device one)
+    A, b, c = O.gen_dense_lp(SEED, M, NV)
+    Ah, bh, ch = pinned((M, NV)), pinned((M,)), pinned((NV,))
+    Ah[:] = A; bh[:] = b; ch[:] = c
+    del A
+    outT, outx = pinned((R, CC)), pinned((NV,))
+    outb = np.zeros(M, dtype=np.int32)
+    h2d = 8 * (M * NV + M + NV)
+    d2h = 8 * (R * CC + NV + 1) + 4 * M
+
+    def solve_e2e(max_pivots):
+        h = N.vp()
+        N.check(lib.lpr_tab_create_primal(dev, NV, M, N.pd(ch), N.pd(Ah), NV, None, None, N.pd(bh), 1, C.byref(h)))
+        st, npv, z = C.c_int(), C.c_int64(), C.c_double()
+        N.check(lib.lpr_tab_solve(h, L.RULE_PRIMAL, max_pivots, 0, C.byref(st), C.byref(npv), None, 0))
+        N.check(lib.lpr_tab_objective(h, C.byref(z)))
+        N.check(lib.lpr_tab_extract_solution(h, NV, N.pd(outx)))
+        N.check(lib.lpr_tab_get_basis(h, N.pi(outb)))
+        N.check(lib.lpr_tab_read(h, N.pd(outT)))
+        lib.lpr_tab_destroy(h)
+        return npv.value, z.value
+
+    solve_e2e(args.max_pivots)  # warm-up
+    barrier(dist, local)
+    te0 = time.perf_counter()
+    e2e_piv = 0
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        p, ze = solve_e2e(args.max_pivots)
+        e2e_piv += p
+    te = time.perf_counter() - te0
+    te_max = barrier_max(dist, local, te)
+    e2e_value = world * e2e_piv / te_max
+    assert ze == zval, "e2e and resident solves disagree"
+
+    # -------- cpu baseline: oracle, single thread like the reference, bounded sample (rank 0) ----
+    cpu = None
+    if rank == 0 and world == 1:
+        sample = int(os.environ.get("LPR_CPU_SAMPLE_PIVOTS", "96"))
+        T0, b0 = O.primal_build(list(ch), [(Ah[i], "<=", bh[i]) for i in range(M)])
+        tc = time.perf_counter()
+        r = O.primal_solve(T0, b0, max_pivots=sample, threads=1, log_cap=0)
+        dtc = time.perf_counter() - tc
+        cpu = {"value": sample / dtc, "unit": "pivots/s", "cores": 1, "kind": "port",
+               "sample": f"first {sample} pivots of the same cfg2 solve ({dtc:.1f} s); C++ restatement of "
+                         "PrimalSimplexSolver.cs:152-211 (no .NET toolchain in the image), single thread like "
+                         f"the reference; host has {os.cpu_count()} cores"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    per_pivot_us = ms_max * 1e3 / piv_total
+    achieved_pivot = BYTES_PER_PIVOT / (per_pivot_us * 1e-6) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "sweep_dram_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    peak = float(peaks["hbm_gbs"])
+    kern_us = sweep_us if sweep_us else per_pivot_us
+    achieved = BYTES_SWEEP / (kern_us * 1e-6) / 1e9
+    line = {
+        "metric": "simplex pivots/s (dense 4096x8192 fp64 primal tableau)",
+        "value": value, "unit": "pivots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2 dense LP m=4096 n=8192 primal tableau simplex, tableau 4097x12289 "
+                               "(BASELINE.json configs[1])",
+                   "step": "one full Solve() from the slack basis to optimality",
+                   "pivots_per_step": pivots_per_step, "status": L.STATUS_NAMES[status], "seed": SEED,
+                   "l2": "tableau 402.8 MB > 126 MB L2 (inputs larger than L2; no flush needed)",
+                   "parallelism": "replicas" if world > 1 else "single GPU"},
+        "tableau_gbs": 16.0 * R * CC * value / world / 1e9,
+        "wall_ms_per_step": wall_max / args.steps,
+        "e2e": {"value": e2e_value, "unit": "pivots/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "what": "lpr_tab_create_primal(host A,b,c pinned) + lpr_tab_solve + "
+                                            "objective + extract_solution + basis + lpr_tab_read(final tableau)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "lpr::k_sweep<0,false,true,8> (rank-1 row elimination sweep)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)",
+                     "bytes_per_launch": BYTES_SWEEP, "kernel_us": kern_us,
+                     "kernel_us_how": "CUDA event pairs around each sweep launch, 96-pivot pass" if sweep_us
+                     else "whole-pivot time (no per-kernel pass)",
+                     "traffic": traffic,
+                     "per_pivot": {"bytes": BYTES_PER_PIVOT, "us": per_pivot_us, "achieved": achieved_pivot,
+                                   "frac_of_measured": achieved_pivot / peak,
+                                   "frac_of_nominal_8tbs": achieved_pivot / NOMINAL_HBM_GBS}},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

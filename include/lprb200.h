@@ -99,7 +99,9 @@ int lpr_tab_set_basis(lpr_tab* h, const int* basis);
 /* Solve() loop (PrimalSimplexSolver.cs:102-150; PrimalSimplexSolver2.cs:46-97; DualSimplex.cs:14-114;
  * SensitivityAnalyzer.cs:121-201) entirely on the device.  max_pivots < 0 = no cap.  pivot_log
  * receives (row, col) pairs in tableau indices.  flags bit0 = "printSteps" (only meaningful for
- * RULE_PRIMAL2 / RULE_DUAL whose iteration counters advance only when printing). */
+ * RULE_PRIMAL2 / RULE_DUAL whose iteration counters advance only when printing);
+ * bit2 = use the unfused reference-shaped kernels (select reads the tableau directly);
+ * bit3 = bracket every sweep launch with CUDA events (see lpr_tab_last_sweep_us). */
 int lpr_tab_solve(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
                   int64_t* n_pivots, int* pivot_log, int64_t log_cap);
 /* one pivot (FindEnteringVariable + FindLeavingVariable + Pivot) for snapshot-accurate tracing */
@@ -113,6 +115,9 @@ int lpr_tab_extract_solution(lpr_tab* h, int n, double* x);
 int lpr_tab_objective(lpr_tab* h, double* z);
 /* device time (CUDA events on the handle's stream) and kernel launches of the last solve */
 int lpr_tab_last_solve_ms(const lpr_tab* h, float* ms);
+/* average duration of the sweep kernel in the last lpr_tab_solve run with flags bit3 set (each sweep
+ * launch bracketed by a CUDA event pair on the handle's stream; roofline measurement aid) */
+int lpr_tab_last_sweep_us(const lpr_tab* h, float* us);
 /* append one row (Gomory cut, CuttingPlaneSolver.cs:110) -- needs row headroom */
 int lpr_tab_append_row(lpr_tab* h, const double* row);
 /* Gomory fractional cut rows 1-4 of CuttingPlaneSolver.cs:76-107 generated on the device:

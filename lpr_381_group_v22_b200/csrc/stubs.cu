@@ -1,19 +1,7 @@
 // stubs.cu -- TEMPORARY: entry points not implemented yet return LPR_E_STATE.
 #include "common.cuh"
 extern "C" {
-int lpr_rev_create(int device, int m, int n, const double* A, const double* b, const double* c, int is_minimization, lpr_rev** out) { return lpr::fail(LPR_E_STATE, "lpr_rev_create: not implemented yet"); }
-int lpr_rev_create_dense_lp(int device, uint64_t seed, int m, int n, lpr_rev** out) { return lpr::fail(LPR_E_STATE, "lpr_rev_create_dense_lp: not implemented yet"); }
-int lpr_rev_destroy(lpr_rev* h) { return lpr::fail(LPR_E_STATE, "lpr_rev_destroy: not implemented yet"); }
-int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status, int64_t* n_iter, int* log, int64_t log_cap) { return lpr::fail(LPR_E_STATE, "lpr_rev_solve: not implemented yet"); }
 int lpr_rev_refactor(lpr_rev* h) { return lpr::fail(LPR_E_STATE, "lpr_rev_refactor: not implemented yet"); }
-int lpr_rev_read_basis(lpr_rev* h, int* basis) { return lpr::fail(LPR_E_STATE, "lpr_rev_read_basis: not implemented yet"); }
-int lpr_rev_read_x(lpr_rev* h, double* x) { return lpr::fail(LPR_E_STATE, "lpr_rev_read_x: not implemented yet"); }
-int lpr_rev_read_z(lpr_rev* h, double* z) { return lpr::fail(LPR_E_STATE, "lpr_rev_read_z: not implemented yet"); }
-int lpr_rev_read_y(lpr_rev* h, double* y) { return lpr::fail(LPR_E_STATE, "lpr_rev_read_y: not implemented yet"); }
-int lpr_rev_read_xb(lpr_rev* h, double* xb) { return lpr::fail(LPR_E_STATE, "lpr_rev_read_xb: not implemented yet"); }
-int lpr_rev_read_binv(lpr_rev* h, double* binv) { return lpr::fail(LPR_E_STATE, "lpr_rev_read_binv: not implemented yet"); }
-int lpr_rev_last_solve_ms(const lpr_rev* h, float* ms) { return lpr::fail(LPR_E_STATE, "lpr_rev_last_solve_ms: not implemented yet"); }
-int lpr_rev_last_refactor_ms(const lpr_rev* h, float* ms) { return lpr::fail(LPR_E_STATE, "lpr_rev_last_refactor_ms: not implemented yet"); }
 int lpr_tab_round4(lpr_tab* h) { return lpr::fail(LPR_E_STATE, "lpr_tab_round4: not implemented yet"); }
 int lpr_tab_bb_node_solve(lpr_tab* h, int64_t max_pivots, int* status, int64_t* n_pivots, int* pivot_log, int64_t log_cap) { return lpr::fail(LPR_E_STATE, "lpr_tab_bb_node_solve: not implemented yet"); }
 int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound, int type, lpr_tab** child) { return lpr::fail(LPR_E_STATE, "lpr_tab_bb_add_constraint: not implemented yet"); }

@@ -7,6 +7,7 @@
 // separate multiply and subtract roundings (__dmul_rn/__dsub_rn are never contracted) and
 // IEEE division, which makes every element bit-identical to the reference's scalar loops.
 #include "tableau.cuh"
+#include "select.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -53,72 +54,21 @@ static int env_int(const char* name, int dflt) {
 // =============================================================================================
 // device helpers
 // =============================================================================================
-constexpr int kSelThreads = 1024;
-constexpr int kSweepThreads = 256;
-constexpr double kPosInf = __builtin_huge_val();
-
-#define TAT(T, ld, i, j) (T)[(size_t)(i) * (size_t)(ld) + (size_t)(j)]
-
-// Sequential "running best with hysteresis" scan (accept k iff val_k < best - eps, best starts at
-// b0) evaluated in parallel: the first index of the minimum is the answer unless an earlier
-// candidate could have blocked it, in which case thread 0 replays the scan literally.  Used for
-// PrimalSimplexSolver2.cs:102-141, DualSimplex.cs:27-70, SensitivityAnalyzer.cs:139-196 and
-// RevisedPrimalSimplexSolver.cs:104-121.  All threads of the block must call it.
-template <class Cand>
-__device__ int block_hyst_min(int n, Cand cand, double b0, double eps, MinIdx* sm, int* smi) {
-  __shared__ int sh_res;
-  MinIdx m = minidx_identity();
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
-    double val;
-    if (cand(k, val) && val == val) m = minidx_combine(m, MinIdx{val, k});
-  }
-  m = block_minidx(m, sm);
-  if (m.i == INT_MAX) return -1;
-  if (!(m.v < __dsub_rn(b0, eps))) return -1;
-  int bad = 0;
-  for (int k = threadIdx.x; k < m.i; k += blockDim.x) {
-    double val;
-    if (cand(k, val) && val == val && !(m.v < __dsub_rn(val, eps))) bad++;
-  }
-  bad = block_sum_int(bad, smi);
-  if (bad == 0) return m.i;
-  if (threadIdx.x == 0) {
-    double best = b0;
-    int idx = -1;
-    for (int k = 0; k < n; k++) {
-      double val;
-      if (cand(k, val) && val < __dsub_rn(best, eps)) {
-        best = val;
-        idx = k;
-      }
-    }
-    sh_res = idx;
-  }
-  __syncthreads();
-  int r = sh_res;
-  __syncthreads();
-  return r;
-}
-
-// first index of the minimum over valid candidates
-template <class Cand>
-__device__ int block_first_min(int n, Cand cand, MinIdx* sm, double* vout = nullptr) {
-  MinIdx m = minidx_identity();
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
-    double val;
-    if (cand(k, val)) m = minidx_combine(m, MinIdx{val, k});
-  }
-  m = block_minidx(m, sm);
-  if (vout) *vout = m.v;
-  return m.i == INT_MAX ? -1 : m.i;
-}
-
 // =============================================================================================
 // k_select<RULE>: one CTA.  Commits the previous pivot, picks (leave row, enter col) with the
 // rule's exact tolerances and tie breaks, stages the normalised pivot row (prow) and the
 // pre-update factor column (col[cur]) for the sweep.
 // =============================================================================================
 enum : int { F_PRINT = 1, F_FUSED = 2 };
+
+// Programmatic dependent launch (sm_90+): every kernel of the pivot chain first waits for its
+// predecessor's results, then lets its successor start launching; with the launch attribute set
+// by launch_pdl() this hides the launch latency between the dependent kernels of one pivot.
+// Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 template <int RULE>
 __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, int* mask) {
@@ -128,6 +78,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, in
   const int tid = threadIdx.x;
   const int R = v.R, C = v.C, ld = v.ld;
   double* T = v.T;
+  pdl_wait_then_release();
 
   const int status = st->status;
   const int did = st->do_sweep;
@@ -308,12 +259,22 @@ __global__ void __launch_bounds__(kSelThreads) k_primal_init(TabView v) {
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads) k_primal_select_fused(TabView v) {
+// Multi-CTA select: CTA b owns columns [256 b, 256 b + 256).  Every CTA repeats the (cheap,
+// L2-resident) ratio test so no grid-wide barrier is needed before the pivot row is normalised;
+// per-CTA entering candidates are combined by the last CTA to finish (atomic ticket), which is
+// also the only writer of the state block -- by then every other CTA has read it.
+__global__ void __launch_bounds__(256) k_primal_select_fused(TabView v, MinIdx* cand, unsigned* ticket) {
   __shared__ MinIdx sm[32];
+  __shared__ int sh_last;
+  __shared__ double sh_piv;
   TabState* st = v.st;
   const int tid = threadIdx.x;
   const int R = v.R, C = v.C, ld = v.ld;
   const double* T = v.T;
+  const int j = blockIdx.x * blockDim.x + tid;
+  pdl_wait_then_release();
+  // independent of the state: this CTA's slice of the objective row
+  const double t0j = (j < C - 1) ? T[j] : 0.0;
   const int status = st->status;
   const int did = st->do_sweep;
   long long npiv = st->npiv;
@@ -321,9 +282,8 @@ __global__ void __launch_bounds__(kSelThreads) k_primal_select_fused(TabView v) 
   int cur = st->cur;
   int e = st->enter;
   const int nxt = st->next_enter;
-  __syncthreads();
   if (status != LPR_RUNNING) {
-    if (tid == 0) st->do_sweep = 0;
+    if (blockIdx.x == 0 && tid == 0 && did) st->do_sweep = 0;  // idempotent: no reader needs the old value
     return;
   }
   if (did) {  // commit pivot t: the sweep has produced col[cur^1] for `nxt`
@@ -331,57 +291,101 @@ __global__ void __launch_bounds__(kSelThreads) k_primal_select_fused(TabView v) 
     cur ^= 1;
     e = nxt;
   }
-  auto finish = [&](int s) {
-    if (tid == 0) {
-      st->status = s;
-      st->do_sweep = 0;
-      st->npiv = npiv;
-      st->cur = cur;
-      st->enter = e;
-    }
-  };
-  if (e < 0) { finish(LPR_OPTIMAL); return; }
+  int term = LPR_RUNNING, p = -1;
   const double* colb = cur ? v.col[1] : v.col[0];
-  // FindLeavingVariable PrimalSimplexSolver.cs:169-191 on the staged (contiguous) column + RHS
-  int k = block_first_min(R - 1, [&](int q, double& val) {
-    double a = colb[q + 1];
-    if (!(a > 1e-9)) return false;
-    val = __ddiv_rn(v.rhs[q + 1], a);
-    return val >= 0.0 && val < DBL_MAX;
-  }, sm);
-  if (k < 0) { finish(LPR_UNBOUNDED); return; }
-  const int p = k + 1;
-  if (maxp >= 0 && npiv >= maxp) { finish(LPR_ITER_LIMIT); return; }
-  const double piv = colb[p];
-  const double f0 = colb[0];
-  // normalise the pivot row (:197-199) and, fused, evaluate the updated objective row
-  // T[0,j] - f0*prow[j] (:206-208) to pick the next entering column (:152-167).
-  MinIdx m = minidx_identity();
-  for (int j = tid; j < ld; j += blockDim.x) {
-    double pr = 0.0;
-    if (j < C) {
-      pr = __ddiv_rn(TAT(T, ld, p, j), piv);
-      if (j < C - 1) {
-        double z = __dsub_rn(T[j], __dmul_rn(f0, pr));
-        if (z < 0.0) m = minidx_combine(m, MinIdx{z, j});
+  double f0 = 0.0, piv = 0.0;
+  if (e < 0) {
+    term = LPR_OPTIMAL;
+  } else {
+    // FindLeavingVariable PrimalSimplexSolver.cs:169-191 on the staged (contiguous) column + RHS.
+    // All loads of a pass are issued before any use: one memory round trip per 4096 rows.
+    f0 = colb[0];
+    MinIdx best = minidx_identity();
+    double best_a = 0.0;
+    constexpr int UR = 16;
+    for (int base = 1; base < R; base += 256 * UR) {
+      double a[UR], b[UR];
+#pragma unroll
+      for (int q = 0; q < UR; q++) {
+        const int i = base + q * 256 + tid;
+        a[q] = (i < R) ? colb[i] : 0.0;
+        b[q] = (i < R) ? v.rhs[i] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < UR; q++) {
+        const int i = base + q * 256 + tid;
+        if (i < R && a[q] > 1e-9) {
+          const double val = __ddiv_rn(b[q], a[q]);
+          if (val >= 0.0 && val < DBL_MAX) {
+            MinIdx cnd{val, i - 1};
+            MinIdx nb = minidx_combine(best, cnd);
+            if (nb.i != best.i) best_a = a[q];
+            best = nb;
+          }
+        }
       }
     }
-    v.prow[j] = pr;
+    const MinIdx mine = best;
+    best = block_minidx(best, sm);
+    const int k = (best.i == INT_MAX) ? -1 : best.i;
+    if (k >= 0 && mine.i == k) sh_piv = best_a;  // exactly one thread owns row k
+    __syncthreads();
+    if (k < 0) term = LPR_UNBOUNDED;
+    else if (maxp >= 0 && npiv >= maxp) term = LPR_ITER_LIMIT;
+    p = k + 1;
+    if (k >= 0) piv = sh_piv;
   }
-  m = block_minidx(m, sm);
+  MinIdx m = minidx_identity();
+  if (term == LPR_RUNNING) {
+    // normalise the pivot row (:197-199) and, fused, evaluate the updated objective row
+    // T[0,j] - f0*prow[j] (:206-208) to pick the next entering column (:152-167).
+    if (j < ld) {
+      double pr = 0.0;
+      if (j < C) {
+        pr = __ddiv_rn(TAT(T, ld, p, j), piv);
+        if (j < C - 1) {
+          double z = __dsub_rn(t0j, __dmul_rn(f0, pr));
+          if (z < 0.0) m = MinIdx{z, j};
+        }
+      }
+      v.prow[j] = pr;
+    }
+    m = block_minidx(m, sm);
+  }
   if (tid == 0) {
-    st->enter = e;
-    st->leave = p;
-    st->next_enter = (m.i == INT_MAX) ? -1 : m.i;
-    st->do_sweep = 1;
+    cand[blockIdx.x] = m;
+    __threadfence();
+    unsigned t = atomicAdd(ticket, 1u);
+    sh_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sh_last) return;
+  __threadfence();
+  if (term == LPR_RUNNING) {
+    MinIdx r = minidx_identity();
+    for (int b = tid; b < (int)gridDim.x; b += blockDim.x) r = minidx_combine(r, cand[b]);
+    r = block_minidx(r, sm);
+    m = r;
+  }
+  if (tid == 0) {
+    *ticket = 0;
     st->npiv = npiv;
     st->cur = cur;
-    st->pivot = piv;
-    if (v.log && npiv < v.log_cap) {
-      v.log[2 * npiv] = p;
-      v.log[2 * npiv + 1] = e;
+    st->enter = e;
+    if (term != LPR_RUNNING) {
+      st->status = term;
+      st->do_sweep = 0;
+    } else {
+      st->leave = p;
+      st->next_enter = (m.i == INT_MAX) ? -1 : m.i;
+      st->do_sweep = 1;
+      st->pivot = piv;
+      if (v.log && npiv < v.log_cap) {
+        v.log[2 * npiv] = p;
+        v.log[2 * npiv + 1] = e;
+      }
+      if (v.basis) v.basis[p - 1] = e;  // :142
     }
-    if (v.basis) v.basis[p - 1] = e;  // :142
   }
 }
 
@@ -390,113 +394,99 @@ __global__ void __launch_bounds__(kSelThreads) k_primal_select_fused(TabView v) 
 // five siblings).  Every element of the tableau is read once and written once per pivot:
 //   row p      : T[p,j] = prow[j]                          (normalised pivot row)
 //   row i != p : T[i,j] = T[i,j] - (f_i * prow[j])          (separate mul and sub roundings)
-// Thread mapping: a thread owns ONE 16-byte (double2) column chunk and walks down rows, so its
-// two prow values live in registers and the only per-row traffic is the 128-bit load/store of
-// the tableau plus a warp-uniform load of f_i.  Work is split into (column group, row) units,
-// column-group major, and dealt in equal contiguous ranges to a grid of sms*k CTAs (no tail
-// wave).  UNROLL independent 128-bit loads are in flight per thread.
+// Mapping (picked with tools/sweep_bench.cu on a B200: contiguous spans beat column-fixed
+// threads by ~10%): the R x ld tableau is one flat array of 16-byte double2 chunks; a persistent
+// grid of sms*k CTAs gets equal contiguous spans (no tail wave); a CTA walks its span in tiles of
+// 256*UNROLL chunks with UNROLL independent 128-bit loads in flight per thread.  prow (<= 100 KB)
+// and the factor column are read through the L1 read-only path.  `reverse` walks the span
+// backwards: alternating the direction between pivots lets the next sweep start on the chunks
+// the previous one left in L2.
 //   SKIP: 0 none | 1 skip rows with |f| <= eps | 2 skip rows with |f| < eps
 //   OOP : out-of-place (B&B pivots, BranchBoundSimplexSolver.cs:161-192) with -0.0 -> 0.0
 //   EMIT: fused primal path, write next factor column / RHS side buffers
 // =============================================================================================
 template <int SKIP, bool OOP, bool EMIT, int UNROLL>
+__device__ __forceinline__ void sweep_body(const double2* __restrict__ src, double2* __restrict__ dst,
+                                           const double* __restrict__ f, const double2* __restrict__ prow2,
+                                           double* __restrict__ cn, double* __restrict__ rhsb, int R, int C,
+                                           int ld, int p, int e_next, double eps, int reverse) {
+  const unsigned ldv = (unsigned)(ld >> 1);
+  const unsigned long long n = (unsigned long long)R * ldv;
+  constexpr unsigned TILE = kSweepThreads * UNROLL;
+  const unsigned long long ntiles = (n + TILE - 1) / TILE;
+  const unsigned long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const unsigned rhs_chunk = (unsigned)((C - 1) >> 1);
+  const int rhs_odd = (C - 1) & 1;
+  const unsigned e_chunk = e_next >= 0 ? (unsigned)(e_next >> 1) : 0xffffffffu;
+  const int e_odd = e_next & 1;
+  for (unsigned long long tt = t0; tt < t1; tt++) {
+    const unsigned long long t = reverse ? (ntiles - 1 - tt) : tt;  // full mirror: last tiles first
+    const unsigned long long q0 = t * TILE + threadIdx.x;
+    unsigned row = (unsigned)(q0 / ldv);
+    unsigned c = (unsigned)(q0 - (unsigned long long)row * ldv);
+    double2 x[UNROLL];
+    double fv[UNROLL];
+    unsigned rw[UNROLL], cc[UNROLL];
+    bool act[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; k++) {
+      const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
+      rw[k] = row;
+      cc[k] = c;
+      act[k] = q < n;
+      if (act[k]) {
+        if (SKIP != 0) {  // the skip decision needs f before the load is issued
+          fv[k] = __ldg(f + row);
+          bool sk = ((int)row != p) && ((SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps));
+          if (sk && !OOP) act[k] = false;
+        }
+        if (act[k]) x[k] = src[q];
+      }
+      c += kSweepThreads;  // ldv may be < 256: wrap as often as needed
+      while (c >= ldv) { c -= ldv; row++; }
+    }
+#pragma unroll
+    for (int k = 0; k < UNROLL; k++) {
+      if (!act[k]) continue;
+      const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
+      if (SKIP == 0) fv[k] = __ldg(f + rw[k]);  // L1-resident: loaded late to keep registers low
+      const double2 pr = __ldg(prow2 + cc[k]);
+      double2 y;
+      bool sk = false;
+      if (SKIP != 0 && OOP && (int)rw[k] != p) sk = (SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps);
+      if ((int)rw[k] == p) {
+        y = pr;
+      } else if (sk) {
+        y = x[k];
+      } else {
+        y.x = __dsub_rn(x[k].x, __dmul_rn(fv[k], pr.x));
+        y.y = __dsub_rn(x[k].y, __dmul_rn(fv[k], pr.y));
+        if (OOP) {
+          if (y.x == 0.0) y.x = 0.0;
+          if (y.y == 0.0) y.y = 0.0;
+        }
+      }
+      dst[q] = y;
+      if (EMIT) {
+        if (cc[k] == e_chunk) cn[rw[k]] = e_odd ? y.y : y.x;
+        if (cc[k] == rhs_chunk) rhsb[rw[k]] = rhs_odd ? y.y : y.x;
+      }
+    }
+  }
+}
+
+template <int SKIP, bool OOP, bool EMIT, int UNROLL>
 __global__ void __launch_bounds__(kSweepThreads) k_sweep(TabView v, double eps, int reverse) {
+  pdl_wait_then_release();
   const TabState* st = v.st;
   if (!st->do_sweep) return;
-  const int p = st->leave;
-  const int e_next = EMIT ? st->next_enter : -1;
   const int cur = st->cur;
-  const int R = v.R, C = v.C;
-  const int ldv = v.ld >> 1;
-  const double* __restrict__ f = cur ? v.col[1] : v.col[0];
-  double* __restrict__ cn = cur ? v.col[0] : v.col[1];
-  const double2* __restrict__ src = reinterpret_cast<const double2*>(OOP ? (st->src ? v.T2 : v.T) : v.T);
-  double2* __restrict__ dst = reinterpret_cast<double2*>(OOP ? (st->src ? v.T : v.T2) : v.T);
-  const double2* __restrict__ prow2 = reinterpret_cast<const double2*>(v.prow);
-  const int rhs_chunk = (C - 1) >> 1, rhs_odd = (C - 1) & 1;
-  const int e_chunk = e_next >= 0 ? (e_next >> 1) : -1, e_odd = e_next & 1;
-
-  auto update = [&](double2 x, double fv, double2 pr, int row) -> double2 {
-    double2 y;
-    if (row == p) {
-      y = pr;
-    } else {
-      y.x = __dsub_rn(x.x, __dmul_rn(fv, pr.x));
-      y.y = __dsub_rn(x.y, __dmul_rn(fv, pr.y));
-      if (OOP) {
-        if (y.x == 0.0) y.x = 0.0;
-        if (y.y == 0.0) y.y = 0.0;
-      }
-    }
-    return y;
-  };
-  auto skipped = [&](double fv, int row) -> bool {
-    if (SKIP == 0 || row == p) return false;
-    return SKIP == 1 ? (fabs(fv) <= eps) : (fabs(fv) < eps);
-  };
-
-  const int nfull = ldv / kSweepThreads;
-  const long long U = (long long)nfull * R;
-  int bid = reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-  long long u0 = U * bid / gridDim.x;
-  const long long u1 = U * (bid + 1) / gridDim.x;
-  while (u0 < u1) {
-    const int cg = (int)(u0 / R);
-    const int r0 = (int)(u0 - (long long)cg * R);
-    const int r1 = (int)min((long long)R, r0 + (u1 - u0));
-    const int chunk = cg * kSweepThreads + threadIdx.x;
-    const double2 pr = prow2[chunk];
-    const bool own_e = EMIT && chunk == e_chunk, own_r = EMIT && chunk == rhs_chunk;
-    const double2* s = src + chunk;
-    double2* d = dst + chunk;
-    for (int r = r0; r < r1; r += UNROLL) {
-      double2 x[UNROLL];
-      double fv[UNROLL];
-#pragma unroll
-      for (int k = 0; k < UNROLL; k++) {
-        const int row = r + k;
-        if (row < r1) {
-          fv[k] = f[row];
-          if (!skipped(fv[k], row) || OOP) x[k] = s[(size_t)row * ldv];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < UNROLL; k++) {
-        const int row = r + k;
-        if (row < r1) {
-          if (skipped(fv[k], row)) {
-            if (OOP) d[(size_t)row * ldv] = x[k];
-            continue;
-          }
-          double2 y = update(x[k], fv[k], pr, row);
-          d[(size_t)row * ldv] = y;
-          if (own_e) cn[row] = e_odd ? y.y : y.x;
-          if (own_r) v.rhs[row] = rhs_odd ? y.y : y.x;
-        }
-      }
-    }
-    u0 += (r1 - r0);
-  }
-  // ragged remainder: the last (ldv % 256) chunks of every row, one thread per row
-  const int rem0 = nfull * kSweepThreads;
-  if (rem0 < ldv) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nth = gridDim.x * blockDim.x;
-    for (int row = gid; row < R; row += nth) {
-      const double fv = f[row];
-      if (skipped(fv, row)) {
-        if (OOP)
-          for (int c = rem0; c < ldv; c++) dst[(size_t)row * ldv + c] = src[(size_t)row * ldv + c];
-        continue;
-      }
-      for (int c = rem0; c < ldv; c++) {
-        double2 y = update(src[(size_t)row * ldv + c], fv, prow2[c], row);
-        dst[(size_t)row * ldv + c] = y;
-        if (EMIT && c == e_chunk) cn[row] = e_odd ? y.y : y.x;
-        if (EMIT && c == rhs_chunk) v.rhs[row] = rhs_odd ? y.y : y.x;
-      }
-    }
-  }
+  const double* f = cur ? v.col[1] : v.col[0];
+  double* cn = cur ? v.col[0] : v.col[1];
+  const double2* src = reinterpret_cast<const double2*>(OOP ? (st->src ? v.T2 : v.T) : v.T);
+  double2* dst = reinterpret_cast<double2*>(OOP ? (st->src ? v.T : v.T2) : v.T);
+  sweep_body<SKIP, OOP, EMIT, UNROLL>(src, dst, f, reinterpret_cast<const double2*>(v.prow), cn, v.rhs, v.R, v.C,
+                                      v.ld, st->leave, EMIT ? st->next_enter : -1, eps, reverse);
 }
 
 // state reset before a solve
@@ -742,6 +732,9 @@ int tab_alloc(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab*
   TRY(cudaMalloc(&h->prow, sizeof(double) * h->ld));
   TRY(cudaMalloc(&h->basis, sizeof(int) * h->Rcap));
   TRY(cudaMalloc(&h->st, sizeof(TabState)));
+  TRY(cudaMalloc(&h->selcand, sizeof(MinIdx) * (h->ld / 256 + 2)));
+  TRY(cudaMalloc(&h->ticket, sizeof(unsigned)));
+  TRY(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream));
   TRY(cudaMallocHost(&h->st_host, sizeof(TabState) * 2));
   TRY(cudaEventCreate(&h->ev0));
   TRY(cudaEventCreate(&h->ev1));
@@ -770,28 +763,57 @@ int tab_ensure_T2(lpr_tab* h) {
 }
 
 static int sweep_grid(const lpr_tab* h) {
-  static const int per_sm = std::max(1, env_int("LPR_SWEEP_CTAS_PER_SM", 4));
-  const long long units = (long long)(h->ld / 2 / kSweepThreads) * h->R;
+  // waves of resident CTAs: grid = sms * (resident CTAs per SM) * LPR_SWEEP_WAVES, capped by the tile count
+  static int resident = 0;
+  if (!resident) {
+    int r = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_sweep<0, false, true, 8>, kSweepThreads, 0);
+    resident = std::max(1, r);
+  }
+  static const int waves = std::max(1, env_int("LPR_SWEEP_WAVES", 4));
+  static const int per_sm_env = env_int("LPR_SWEEP_CTAS_PER_SM", 0);
+  const int per_sm = per_sm_env > 0 ? per_sm_env : resident * waves;
+  const long long chunks = (long long)h->R * (h->ld / 2);
+  const long long tiles = (chunks + kSweepThreads * 8 - 1) / (kSweepThreads * 8);
   long long g = (long long)h->sms * per_sm;
-  // small tableaux: do not launch CTAs that would own no unit, but keep enough threads for the
-  // one-thread-per-row remainder path
-  long long need = std::max<long long>(units, (h->R + kSweepThreads - 1) / kSweepThreads);
-  g = std::max<long long>(1, std::min(g, need));
+  g = std::max<long long>(1, std::min(g, tiles));
   return (int)g;
+}
+
+// kernel launch with the programmatic-stream-serialization attribute (PDL)
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+  static const int pdl = env_int("LPR_PDL", 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // launch the sweep that applies the staged pivot; mode selects the instantiation
 static int launch_sweep(lpr_tab* h, int skip, double eps, bool emit, int reverse) {
   const int g = sweep_grid(h);
   TabView v = h->view();
-  if (emit)
-    k_sweep<0, false, true, 8><<<g, kSweepThreads, 0, h->stream>>>(v, eps, reverse);
+  static const int unroll = env_int("LPR_SWEEP_UNROLL", 8);
+  if (emit && unroll == 4)
+    launch_pdl(k_sweep<0, false, true, 4>, g, kSweepThreads, h->stream, v, eps, reverse);
+  else if (emit && unroll == 16)
+    launch_pdl(k_sweep<0, false, true, 16>, g, kSweepThreads, h->stream, v, eps, reverse);
+  else if (emit)
+    launch_pdl(k_sweep<0, false, true, 8>, g, kSweepThreads, h->stream, v, eps, reverse);
   else if (skip == 0)
-    k_sweep<0, false, false, 8><<<g, kSweepThreads, 0, h->stream>>>(v, eps, reverse);
+    launch_pdl(k_sweep<0, false, false, 8>, g, kSweepThreads, h->stream, v, eps, reverse);
   else if (skip == 1)
-    k_sweep<1, false, false, 8><<<g, kSweepThreads, 0, h->stream>>>(v, eps, reverse);
+    launch_pdl(k_sweep<1, false, false, 8>, g, kSweepThreads, h->stream, v, eps, reverse);
   else
-    k_sweep<2, false, false, 8><<<g, kSweepThreads, 0, h->stream>>>(v, eps, reverse);
+    launch_pdl(k_sweep<2, false, false, 8>, g, kSweepThreads, h->stream, v, eps, reverse);
   LPR_LAUNCH_CHECK();
   return LPR_OK;
 }
@@ -807,13 +829,13 @@ static int launch_select(lpr_tab* h, int rule, int flags, int* mask) {
   switch (rule) {
     case LPR_RULE_PRIMAL:
       if (flags & F_FUSED)
-        k_primal_select_fused<<<1, kSelThreads, 0, h->stream>>>(v);
+        launch_pdl(k_primal_select_fused, (h->ld + 255) / 256, 256, h->stream, v, h->selcand, h->ticket);
       else
-        k_select<LPR_RULE_PRIMAL><<<1, kSelThreads, 0, h->stream>>>(v, flags, mask);
+        launch_pdl(k_select<LPR_RULE_PRIMAL>, 1, kSelThreads, h->stream, v, flags, mask);
       break;
-    case LPR_RULE_PRIMAL2: k_select<LPR_RULE_PRIMAL2><<<1, kSelThreads, 0, h->stream>>>(v, flags, mask); break;
-    case LPR_RULE_DUAL: k_select<LPR_RULE_DUAL><<<1, kSelThreads, 0, h->stream>>>(v, flags, mask); break;
-    case LPR_RULE_SENS: k_select<LPR_RULE_SENS><<<1, kSelThreads, 0, h->stream>>>(v, flags, mask); break;
+    case LPR_RULE_PRIMAL2: launch_pdl(k_select<LPR_RULE_PRIMAL2>, 1, kSelThreads, h->stream, v, flags, mask); break;
+    case LPR_RULE_DUAL: launch_pdl(k_select<LPR_RULE_DUAL>, 1, kSelThreads, h->stream, v, flags, mask); break;
+    case LPR_RULE_SENS: launch_pdl(k_select<LPR_RULE_SENS>, 1, kSelThreads, h->stream, v, flags, mask); break;
     default: return fail(LPR_E_BADARG, "unknown rule %d", rule);
   }
   LPR_LAUNCH_CHECK();
@@ -828,7 +850,7 @@ int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int*
   if (rc) return rc;
   static const int fused_default = env_int("LPR_TAB_FUSED", 1);
   static const int batch = std::max(1, env_int("LPR_TAB_BATCH", 32));
-  static const int serp = env_int("LPR_TAB_SERPENTINE", 0);
+  static const int serp = env_int("LPR_TAB_SERPENTINE", 1);
   const bool fused = (rule == LPR_RULE_PRIMAL) && fused_default && !(flags & 4);
   int kflags = (flags & F_PRINT) | (fused ? F_FUSED : 0);
   if (pivot_log && log_cap > 0) {
@@ -853,6 +875,11 @@ int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int*
   if (rule == LPR_RULE_DUAL) { skip = 1; eps = 1e-9; }
   if (rule == LPR_RULE_SENS) { skip = 2; eps = 1e-9; }
 
+  // flags bit 3: bracket every sweep launch with a CUDA event pair (roofline measurement pass)
+  const bool time_sweeps = (flags & 8) != 0;
+  std::vector<cudaEvent_t> sw_ev;
+  const int kMaxTimed = 256;
+  h->last_sweep_us = 0.f;
   LPR_CUDA(cudaEventRecord(h->ev0, h->stream));
   k_state_reset<<<1, 1, 0, h->stream>>>(h->st, (long long)max_pivots, 0);
   LPR_LAUNCH_CHECK();
@@ -871,8 +898,18 @@ int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int*
     for (int b = 0; b < bsize; b++) {
       rc = launch_select(hv, rule, kflags, mask);
       if (rc) return rc;
+      const bool timed = time_sweeps && (int)sw_ev.size() < 2 * kMaxTimed;
+      if (timed) {
+        cudaEvent_t a, b2;
+        LPR_CUDA(cudaEventCreate(&a));
+        LPR_CUDA(cudaEventCreate(&b2));
+        sw_ev.push_back(a);
+        sw_ev.push_back(b2);
+        LPR_CUDA(cudaEventRecord(a, h->stream));
+      }
       rc = launch_sweep(hv, skip, eps, fused, serp ? (int)(pivot_parity & 1) : 0);
       if (rc) return rc;
+      if (timed) LPR_CUDA(cudaEventRecord(sw_ev.back(), h->stream));
       pivot_parity++;
     }
     // a trailing select commits the last sweep of the batch so the status word is current
@@ -900,6 +937,21 @@ int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int*
   LPR_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   final_status = h->st_host[0].status;
   const long long npiv = h->st_host[0].npiv;
+  if (time_sweeps) {
+    // only the first npiv sweeps did work (later launches are no-ops); skip the first few (warm-up)
+    double sum = 0.0;
+    int cnt = 0;
+    const int real = (int)std::min<long long>(npiv, (long long)sw_ev.size() / 2);
+    for (int k = std::min(4, real / 2); k < real; k++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sw_ev[2 * k], sw_ev[2 * k + 1]) == cudaSuccess) {
+        sum += ms;
+        cnt++;
+      }
+    }
+    if (cnt) h->last_sweep_us = (float)(sum * 1e3 / cnt);
+    for (auto ev : sw_ev) cudaEventDestroy(ev);
+  }
   if (mask) cudaFree(mask);
   if (status) *status = final_status;
   if (n_pivots) *n_pivots = npiv;
@@ -946,6 +998,8 @@ int lpr_tab_destroy(lpr_tab* h) {
   cudaFree(h->prow);
   cudaFree(h->basis);
   cudaFree(h->st);
+  cudaFree(h->selcand);
+  cudaFree(h->ticket);
   cudaFree(h->log);
   if (h->st_host) cudaFreeHost(h->st_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1128,7 +1182,7 @@ int lpr_tab_step(lpr_tab* h, int rule, int* enter_col, int* leave_row, int* stat
   if (np >= 1) {
     if (leave_row) *leave_row = log[0];
     if (enter_col) *enter_col = log[1];
-    if (st == LPR_ITER_LIMIT) st = LPR_RUNNING;
+    st = LPR_RUNNING;  // a pivot was applied; a terminal state is reported by the next call
   } else {
     if (leave_row) *leave_row = -1;
     if (enter_col) *enter_col = -1;
@@ -1181,6 +1235,12 @@ int lpr_tab_objective(lpr_tab* h, double* z) {
 int lpr_tab_last_solve_ms(const lpr_tab* h, float* ms) {
   if (!h || !ms) return fail(LPR_E_BADARG, "null argument");
   *ms = h->last_ms;
+  return LPR_OK;
+}
+
+int lpr_tab_last_sweep_us(const lpr_tab* h, float* us) {
+  if (!h || !us) return fail(LPR_E_BADARG, "null argument");
+  *us = h->last_sweep_us;
   return LPR_OK;
 }
 

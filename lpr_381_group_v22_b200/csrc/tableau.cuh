@@ -49,10 +49,13 @@ struct lpr_tab {
   int* basis = nullptr;
   lpr::TabState* st = nullptr;
   lpr::TabState* st_host = nullptr;  // pinned mirror
+  lpr::MinIdx* selcand = nullptr;    // per-CTA entering candidates of the multi-CTA select
+  unsigned* ticket = nullptr;        // "last CTA done" counter
   int* log = nullptr;
   long long log_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evb[2] = {nullptr, nullptr};
   float last_ms = 0.f;
+  float last_sweep_us = 0.f;  // average sweep-kernel duration of the last solve run with flag 8
   int sms = 148;
   lpr::TabView view() const {
     lpr::TabView v;

@@ -1,0 +1,93 @@
+"""GPU parity tests for RevisedPrimalSimplexSolver (B^-1 resident in HBM) against the oracle.
+Pivot sequence / basis / status exact; z, x, y, x_B within 1e-9 relative (north-star tolerance)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import lpr_381_group_v22_b200 as L
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def close(a, b, what):
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    scale = max(1.0, float(np.max(np.abs(b))) if b.size else 1.0)
+    err = float(np.max(np.abs(a - b))) if b.size else 0.0
+    assert err <= RTOL * scale, f"{what}: max abs err {err:.3e} (scale {scale:.3e})"
+
+
+def solve_both(A, b, c, is_min=False, **kw):
+    m, n = A.shape
+    ref = O.rev_solve(A, b, c, is_min, want_binv=True)
+    s = L.RevisedPrimalSimplexSolver(list(c), [L.Constraint(A[i], "<=", b[i]) for i in range(m)], is_min, **kw)
+    return ref, s
+
+
+def test_fixture_models():
+    # README model through CLI option 2 ('+ + +' => no bound rows, '>=' ignored: Q6)
+    A = np.array([[1, 2, 3], [3, 2, 1.0]])
+    ref, s = solve_both(A, [10, 15], [2, 3, 4])
+    s.Solve()
+    assert s.PivotLog == [(0, 2, 3), (1, 0, 4)] == [tuple(x) for x in ref["log"].tolist()]
+    assert s.BasicVariables == [2, 0] and s.FinalZ == 16.25 and s.SolutionVector == [4.375, 0.0, 1.875]
+    # data/TextFile.txt through CLI option 2 ('bin' => six x_j <= 1 rows)
+    A = np.vstack([[11, 8, 6, 14, 10, 10], np.eye(6)])
+    b = [40] + [1] * 6
+    obj = [2, 3, 3, 5, 2, 4]
+    ref, s = solve_both(A, b, obj)
+    s.Solve()
+    assert s.PivotLog == [(4, 3, 10), (6, 5, 12), (2, 1, 8), (3, 2, 9), (0, 0, 6), (0, 4, 0)]
+    assert s.BasicVariables == [4, 7, 1, 2, 3, 11, 5] == ref["basis"].tolist()
+    close(s.FinalZ, 15.4, "z")
+    close(s.SolutionVector, [0, 1, 1, 1, 0.2, 1], "x")
+    close(s.DualPrices, ref["y"], "y")
+    close(s.BInverse, ref["Binv"], "Binv")
+
+
+@pytest.mark.parametrize("m,n,seed", [(6, 12, 1), (31, 64, 2), (64, 129, 3), (120, 75, 4), (200, 400, 5)])
+@pytest.mark.parametrize("is_min", [False])
+def test_random_dense_lp(m, n, seed, is_min):
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    ref, s = solve_both(A, b, c, is_min)
+    s.Solve()
+    assert ref["status"] == O.OPTIMAL and s.Status == L.OPTIMAL
+    assert s.PivotLog == [tuple(x) for x in ref["log"].tolist()]
+    assert s.BasicVariables == ref["basis"].tolist()
+    close(s.FinalZ, ref["z"], "z")
+    close(s.SolutionVector, ref["x"], "x")
+    close(s.DualPrices, ref["y"], "y")
+    close(s.BasicValues, ref["xB"], "xB")
+    close(s.BInverse, ref["Binv"], "Binv")
+
+
+def test_minimization_and_exceptions():
+    # min problem: c negated (:51); optimal at origin => zero iterations
+    A, b, c = O.gen_dense_lp(7, 10, 20)
+    ref, s = solve_both(A, b, c, True)
+    s.Solve()
+    assert s.PivotLog == [] and s.FinalZ == 0.0 == ref["z"]
+    # unbounded: max x1 s.t. -x1 + x2 <= 1
+    s = L.RevisedPrimalSimplexSolver([1.0, 0.0], [L.Constraint([-1.0, 1.0], "<=", 1.0)], False)
+    with pytest.raises(Exception, match="Unbounded problem"):
+        s.Solve()
+    # infeasible start: negative rhs (Relation ignored => basis value negative)
+    s = L.RevisedPrimalSimplexSolver([1.0, 1.0], [L.Constraint([1.0, 1.0], "<=", -2.0)], False)
+    with pytest.raises(Exception, match="Infeasible basis"):
+        s.Solve()
+    with pytest.raises(ValueError):
+        L.RevisedPrimalSimplexSolver([1.0, 1.0], [L.Constraint([1.0], "<=", 1.0)], False)
+
+
+def test_agrees_with_tableau_solver_objective():
+    m, n, seed = 80, 160, 11
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    cons = [L.Constraint(A[i], "<=", b[i]) for i in range(m)]
+    r = L.RevisedPrimalSimplexSolver(list(c), cons, False)
+    r.Solve()
+    p = L.PrimalSimplexSolver(list(c), cons, trace=False)
+    p.Solve()
+    close(r.FinalZ, p.FinalZ, "z revised vs tableau")
+    # duals of the tableau solver = row 0 under the slack columns (SensitivityAnalyzer.cs:212-222)
+    close(r.DualPrices, p.GetFinalTableau()[0, n:n + m], "duals")
