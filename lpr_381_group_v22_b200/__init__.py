@@ -9,9 +9,12 @@ from .io import Constraint, InputFileParser, add_cli_bound_rows, add_upper_bound
 from .simplex import (DualSimplexSolver, InvalidOperationException, PrimalSimplexSolver, PrimalSimplexSolver2,
                       RevisedPrimalSimplexSolver)
 from .tableau import DeviceTableau
+from .integer_programming import (BranchAndBoundAdapter, BranchBoundSimplexSolver, CuttingPlaneSolver,
+                                  KnapsackBranchBoundSimplex, KnapsackBranchBoundSolver)
 
 __all__ = [
     "Constraint", "InputFileParser", "add_cli_bound_rows", "add_upper_bound_constraints", "DeviceTableau",
     "PrimalSimplexSolver", "PrimalSimplexSolver2", "DualSimplexSolver", "RevisedPrimalSimplexSolver",
-    "InvalidOperationException", "LprError", "device_count", "launch_count",
+    "BranchAndBoundAdapter", "BranchBoundSimplexSolver", "CuttingPlaneSolver", "KnapsackBranchBoundSimplex",
+    "KnapsackBranchBoundSolver", "InvalidOperationException", "LprError", "device_count", "launch_count",
 ]

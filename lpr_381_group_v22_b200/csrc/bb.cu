@@ -1,0 +1,1075 @@
+// bb.cu -- BranchBoundSimplexSolver (IntegerProgramming/BranchBoundSimplexSolver.cs) on the device.
+//
+// A node of the tree IS its final (4-d.p. rounded) tableau, exactly as in the reference, which warm
+// starts every child from the parent's final tableau (:1105-1108).  Per batch of open nodes:
+//   k_bb_eval        GetObjective / ExtractSolution / CheckIntegerBasicVar        (:805-857,:892-921)
+//   k_bb_addc_*      AddConstraint: round, basic-column detection, bound row,     (:642-803)
+//                    elimination with 4-d.p. rounding after every step
+//   k_bb_select +    DoDualSimplex with tableauOverride: dual phase, primal phase, (:115-279,:289-468)
+//   k_bb_sweep       out-of-place Gauss-Jordan pivots, -0.0 -> 0.0, "drop last tableau" quirk
+//   k_bb_round       RoundAllTableaux on the children                               (:1124,:1187)
+// Every kernel is batched over the node LPs of the round (blockIdx.y / one CTA per LP), which is
+// what turns a launch-latency bound tree walk into an HBM/L2 bound one.  The host keeps the
+// open-node stack, DFS keys and the incumbent.  With batch = 1 the visit order, 20-node cap and
+// strict-improvement incumbent of ExecuteBranchAndBound (:1006-1233) are reproduced exactly.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "sweep.cuh"
+#include "tableau.cuh"
+
+namespace lpr {
+
+struct BBLp {
+  double* buf[2];  // ping-pong tableaux (out-of-place pivots)
+  double* col;     // factor column scratch
+  double* prow;    // pivot row scratch (ld doubles)
+  int* log;        // optional (row, col) pairs
+  int log_cap;
+  int R, C, ld;
+  // state
+  int status, src, phase, do_sweep, leave, enter, dropped, entered_primal;
+  long long npiv, max_piv;
+};
+
+struct BBEval {  // per node outputs of k_bb_eval
+  double z;
+  double branch_val;
+  int branch_var;
+  int all_integer;
+};
+
+struct BBAddc {  // one AddConstraint job
+  const double* parent;
+  double* child;
+  int* key;     // C ints: first-"1" row of basic columns, -1 for non-basic
+  int* order;   // C ints: basic columns in elimination order
+  int R, C;     // parent dims
+  int ldp, ldc;
+  int n_vars, var, type;
+  double bound;
+};
+
+constexpr int kBBT = 1024;
+
+// ---- elementwise helpers --------------------------------------------------------------------
+__global__ void k_bb_negzero(BBLp* lps) {
+  BBLp& lp = lps[blockIdx.y];
+  double* T = lp.buf[lp.src];
+  const size_t n = (size_t)lp.R * lp.ld;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (T[i] == 0.0) T[i] = 0.0;  // :307-313
+}
+__global__ void k_bb_round(BBLp* lps) {
+  BBLp& lp = lps[blockIdx.y];
+  if (lp.status != LPR_OPTIMAL) return;
+  double* T = lp.buf[lp.src];
+  const size_t n = (size_t)lp.R * lp.ld;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    T[i] = net_round4(T[i]);  // RoundTableau :552-567
+}
+__global__ void k_round4(double* T, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    T[i] = net_round4(T[i]);
+}
+
+// ---- DoDualSimplex state machine (:289-468), one CTA per LP --------------------------------------
+__global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps) {
+  __shared__ MinIdx sm[32];
+  __shared__ int smi[32];
+  BBLp& lp = lps[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int status = lp.status;
+  const int did = lp.do_sweep;
+  __syncthreads();
+  if (status != LPR_RUNNING) return;
+  int src = lp.src, phase = lp.phase;
+  long long npiv = lp.npiv;
+  if (did) {
+    src ^= 1;
+    npiv++;
+  }
+  const int R = lp.R, C = lp.C, ld = lp.ld;
+  const double* T = lp.buf[src];
+  auto finish = [&](int s, int new_src, long long np, int dropped) {
+    if (tid == 0) {
+      lp.status = s;
+      lp.do_sweep = 0;
+      lp.src = new_src;
+      lp.npiv = np;
+      lp.phase = phase;
+      lp.dropped = dropped;
+    }
+  };
+  int r = -1, c = -1;
+  bool go_final = false;
+  if (phase == 0) {
+    // all RHS (objective row included) >= -1e-9 ?  (:315-320)
+    int bad = 0;
+    for (int i = tid; i < R; i += blockDim.x)
+      if (!(TAT(T, ld, i, C - 1) >= -1e-9)) bad++;
+    bad = block_sum_int(bad, smi);
+    if (bad) {
+      if (lp.max_piv >= 0 && npiv >= lp.max_piv) { finish(LPR_ITER_LIMIT, src, npiv, 0); return; }
+      // PerformDualPivot :115-201: row = first index of the most negative RHS (exact < 0)
+      r = block_first_min(R, [&](int i, double& val) { val = TAT(T, ld, i, C - 1); return val < 0.0; }, sm);
+      if (r >= 0) {
+        int other = 0;
+        for (int j = tid; j < C - 1; j += blockDim.x) {
+          double a = TAT(T, ld, r, j);
+          double th = (a < 0.0) ? fabs(__ddiv_rn(T[j], a)) : kPosInf;
+          if (!(th == 0.0 || th == kPosInf)) other++;
+        }
+        other = block_sum_int(other, smi);
+        if (other == 0) {  // all thetas in {0, inf}: IndexOf(0)
+          c = block_first_min(C - 1, [&](int j, double& val) {
+            double a = TAT(T, ld, r, j);
+            if (!(a < 0.0)) return false;
+            val = fabs(__ddiv_rn(T[j], a));
+            return val == 0.0;
+          }, sm);
+        } else {  // min over theta > 0 (inf included), IndexOf => first
+          c = block_first_min(C - 1, [&](int j, double& val) {
+            double a = TAT(T, ld, r, j);
+            val = (a < 0.0) ? fabs(__ddiv_rn(T[j], a)) : kPosInf;
+            return val > 0.0;
+          }, sm);
+        }
+      }
+      if (r < 0 || c < 0) { finish(LPR_INFEASIBLE, src, npiv, 0); return; }  // :324-331
+    } else {
+      int notopt = 0;  // :345-348
+      for (int j = tid; j < C - 1; j += blockDim.x)
+        if (!(T[j] >= 0.0)) notopt++;
+      notopt = block_sum_int(notopt, smi);
+      if (!notopt) { finish(LPR_OPTIMAL, src, npiv, 0); return; }
+      phase = 1;
+    }
+  }
+  if (phase == 1 && r < 0) {
+    int notopt = 0;  // :367-373
+    for (int j = tid; j < C - 1; j += blockDim.x)
+      if (!(T[j] >= 0.0)) notopt++;
+    notopt = block_sum_int(notopt, smi);
+    if (!notopt) {
+      go_final = true;
+    } else if (lp.max_piv >= 0 && npiv >= lp.max_piv) {
+      finish(LPR_ITER_LIMIT, src, npiv, 0);
+      return;
+    } else {
+      // PerformPrimalPivot :203-279 (isMinimization == false)
+      c = block_first_min(C - 1, [&](int j, double& val) { val = T[j]; return val < 0.0; }, sm);
+      if (c < 0 || R <= 1) {
+        go_final = true;
+      } else {
+        int notneg = 0, posfin = 0, zero = 0;
+        for (int i = 1 + tid; i < R; i += blockDim.x) {
+          double a = TAT(T, ld, i, c);
+          double th = (a != 0.0) ? __ddiv_rn(TAT(T, ld, i, C - 1), a) : kPosInf;
+          if (!(th < 0.0)) notneg++;
+          if (th > 0.0 && th != kPosInf) posfin++;
+          if (th == 0.0) zero++;
+        }
+        notneg = block_sum_int(notneg, smi);
+        posfin = block_sum_int(posfin, smi);
+        zero = block_sum_int(zero, smi);
+        if (notneg == 0) {
+          go_final = true;  // all thetas negative :228-231
+        } else if (posfin == 0) {
+          if (!zero) {
+            go_final = true;
+          } else {
+            int k = block_first_min(R - 1, [&](int q, double& val) {
+              double a = TAT(T, ld, q + 1, c);
+              val = (a != 0.0) ? __ddiv_rn(TAT(T, ld, q + 1, C - 1), a) : kPosInf;
+              return val == 0.0;
+            }, sm);
+            r = k + 1;
+          }
+        } else {
+          int k = block_first_min(R - 1, [&](int q, double& val) {
+            double a = TAT(T, ld, q + 1, c);
+            val = (a != 0.0) ? __ddiv_rn(TAT(T, ld, q + 1, C - 1), a) : kPosInf;
+            return val > 0.0 && val != kPosInf;
+          }, sm);
+          r = k + 1;
+        }
+        if (!go_final && (r < 1 || TAT(T, ld, r, c) == 0.0)) go_final = true;
+      }
+    }
+  }
+  if (go_final) {
+    // :392-400: any negative RHS after the primal phase => drop the last tableau
+    int neg = 0;
+    for (int i = tid; i < R; i += blockDim.x)
+      if (!(TAT(T, ld, i, C - 1) >= 0.0)) neg++;
+    neg = block_sum_int(neg, smi);
+    if (neg) {
+      if (npiv == 0)
+        finish(LPR_INFEASIBLE, src, npiv, 0);  // pivotColumns.RemoveAt(-1) throws => branch "failed"
+      else
+        finish(LPR_OPTIMAL, src ^ 1, npiv - 1, 1);
+    } else {
+      finish(LPR_OPTIMAL, src, npiv, 0);
+    }
+    return;
+  }
+  // stage the pivot: normalised row with -0.0 -> 0.0 (:174-178), pre-update column
+  const double piv = TAT(T, ld, r, c);
+  for (int j = tid; j < ld; j += blockDim.x) {
+    double v = 0.0;
+    if (j < C) {
+      v = __ddiv_rn(TAT(T, ld, r, j), piv);
+      if (v == 0.0) v = 0.0;
+    }
+    lp.prow[j] = v;
+  }
+  for (int i = tid; i < R; i += blockDim.x) lp.col[i] = TAT(T, ld, i, c);
+  if (tid == 0) {
+    if (lp.log && npiv < lp.log_cap) {
+      lp.log[2 * npiv] = r;
+      lp.log[2 * npiv + 1] = c;
+    }
+    lp.src = src;
+    lp.npiv = npiv;
+    lp.phase = phase;
+    lp.leave = r;
+    lp.enter = c;
+    lp.do_sweep = 1;
+  }
+}
+
+__global__ void __launch_bounds__(kSweepThreads) k_bb_sweep(BBLp* lps) {
+  const BBLp& lp = lps[blockIdx.y];
+  if (!lp.do_sweep || lp.status != LPR_RUNNING) return;
+  sweep_body<0, true, false, 8>(reinterpret_cast<const double2*>(lp.buf[lp.src]),
+                                reinterpret_cast<double2*>(lp.buf[lp.src ^ 1]), lp.col,
+                                reinterpret_cast<const double2*>(lp.prow), nullptr, nullptr, lp.R, lp.C, lp.ld,
+                                lp.leave, -1, 0.0, 0);
+}
+// number of LPs of the batch still running (host polls it)
+__global__ void k_bb_count_running(const BBLp* lps, int n, int* out) {
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += (lps[i].status == LPR_RUNNING);
+  __shared__ int smi[32];
+  c = block_sum_int(c, smi);
+  if (threadIdx.x == 0) *out = c;
+}
+
+// ---- node evaluation (:805-857, :892-921), one CTA per node -------------------------------------
+__global__ void __launch_bounds__(kBBT) k_bb_eval(const double* const* tabs, const int* dims /* R,C,ld */, int n_vars,
+                                                  BBEval* out, double* xout) {
+  __shared__ MinIdx sm[32];
+  __shared__ int smi[32];
+  const int node = blockIdx.x;
+  const double* T = tabs[node];
+  const int R = dims[3 * node], C = dims[3 * node + 1], ld = dims[3 * node + 2];
+  double* x = xout + (size_t)node * n_vars;
+  int nonint = 0;
+  for (int i = threadIdx.x; i < n_vars; i += blockDim.x) {
+    double xi = 0.0;
+    for (int j = 0; j < R; j++) {  // first row (objective row included) holding a rounded 1
+      double val = net_round4(TAT(T, ld, j, i));
+      if (fabs(val - 1.0) <= 1e-6) {
+        xi = net_round4(TAT(T, ld, j, C - 1));
+        break;
+      }
+    }
+    x[i] = xi;
+    double rr = net_round4(xi);  // IsInteger :595-599
+    if (!(fabs(rr - rint(rr)) <= 1e-6)) nonint++;
+  }
+  nonint = block_sum_int(nonint, smi);
+  __syncthreads();
+  int var = block_first_min(n_vars, [&](int i, double& val) {
+    double xi = x[i];
+    double rr = net_round4(xi);
+    if (fabs(rr - rint(rr)) <= 1e-6) return false;
+    double fp = __dsub_rn(xi, floor(xi));
+    val = fabs(__dsub_rn(fp, 0.5));
+    return true;
+  }, sm);
+  if (threadIdx.x == 0) {
+    out[node].z = net_round4(TAT(T, ld, 0, C - 1));  // GetObjective :892-897
+    out[node].branch_var = var;
+    out[node].branch_val = var >= 0 ? x[var] : 0.0;
+    out[node].all_integer = (nonint == 0);
+  }
+}
+
+// ---- AddConstraint (:694-803) -------------------------------------------------------------------
+// child rows 0..R-1 = Round(parent) with a zero column inserted before the RHS; row R = the bound row
+__global__ void k_bb_addc_copy(const BBAddc* jobs) {
+  const BBAddc& jb = jobs[blockIdx.y];
+  const int R = jb.R, C = jb.C, C2 = C + 1;
+  const size_t total = (size_t)(R + 1) * jb.ldc;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(k / jb.ldc), j = (int)(k % jb.ldc);
+    double v = 0.0;
+    if (i < R) {
+      if (j < C - 1)
+        v = net_round4(net_round4(jb.parent[(size_t)i * jb.ldp + j]));
+      else if (j == C)
+        v = net_round4(net_round4(jb.parent[(size_t)i * jb.ldp + (C - 1)]));
+    } else if (j < C2) {
+      if (j < jb.n_vars && j == jb.var) v = net_round4(1.0);  // :727-730
+      if (j == C2 - 1) v = net_round4(jb.bound);              // :732
+      if (j == C - 1) v = (jb.type == 1) ? -1.0 : 1.0;        // :734-742 (overrides a coefficient there)
+      v = net_round4(v);                                      // :747
+    }
+    jb.child[k] = v;
+  }
+}
+// IdentifyBasicVariables :642-662: column sums over ALL rows (objective row and RHS column included)
+__global__ void k_bb_colsum(const BBAddc* jobs) {
+  const BBAddc& jb = jobs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= jb.C) return;
+  double sum = 0.0;
+  int first1 = jb.R;
+  for (int i = 0; i < jb.R; i++) {
+    double v = net_round4(net_round4(jb.parent[(size_t)i * jb.ldp + k]));
+    sum = __dadd_rn(sum, v);
+    if (first1 == jb.R && v == 1.0) first1 = i;
+  }
+  sum = net_round4(sum);
+  jb.key[k] = (fabs(sum - 1.0) <= 1e-6) ? first1 : -1;
+}
+// ordering (:664-685, stable by first-"1" row) and the elimination loop (:752-797); one CTA per job
+__global__ void __launch_bounds__(kBBT) k_bb_addc_elim(const BBAddc* jobs) {
+  __shared__ MinIdx sm[32];
+  __shared__ int sh_nb;
+  const BBAddc& jb = jobs[blockIdx.x];
+  const int R = jb.R, C = jb.C, C2 = C + 1, ldc = jb.ldc;
+  const int tid = threadIdx.x;
+  double* child = jb.child;
+  double* v = child + (size_t)R * ldc;  // the new constraint row
+  // rank basic columns by (key, column): position = number of basic columns ordered before
+  if (tid == 0) sh_nb = 0;
+  __syncthreads();
+  int local = 0;
+  for (int k = tid; k < C; k += blockDim.x) {
+    const int kk = jb.key[k];
+    if (kk < 0) continue;
+    int pos = 0;
+    for (int q = 0; q < C; q++) {
+      const int kq = jb.key[q];
+      if (kq >= 0 && (kq < kk || (kq == kk && q < k))) pos++;
+    }
+    jb.order[pos] = k;
+    local++;
+  }
+  if (local) atomicAdd(&sh_nb, local);
+  __syncthreads();
+  const int nb = sh_nb;
+  int pos = 0;
+  while (true) {
+    // next basic column (in order) whose current coefficient in the new row is non-zero
+    int q = block_first_min(nb - pos, [&](int t, double& val) {
+      const int col = jb.order[pos + t];
+      val = (double)t;
+      return fabs(net_round4(v[col])) > 1e-6;
+    }, sm);
+    if (q < 0) break;
+    q += pos;
+    const int col = jb.order[q];
+    const double coef = net_round4(v[col]);
+    const int prw = block_first_min(R, [&](int rr, double& val) {
+      val = (double)rr;
+      return fabs(net_round4(child[(size_t)rr * ldc + col]) - 1.0) <= 1e-6;
+    }, sm);
+    __syncthreads();
+    if (prw >= 0) {
+      for (int cc = tid; cc < C2; cc += blockDim.x) {
+        const double pv = net_round4(child[(size_t)prw * ldc + cc]);
+        const double cv = net_round4(v[cc]);
+        const double nv = (jb.type == 1) ? __dsub_rn(pv, __dmul_rn(coef, cv)) : __dsub_rn(cv, __dmul_rn(coef, pv));
+        v[cc] = net_round4(nv);
+      }
+    }
+    __syncthreads();
+    pos = q + 1;
+  }
+  for (int cc = tid; cc < C2; cc += blockDim.x) v[cc] = net_round4(v[cc]);  // :799
+}
+
+}  // namespace lpr
+
+using namespace lpr;
+
+// =============================================================================================
+// host side: slab pool, batched node processing
+// =============================================================================================
+struct BBNode {
+  double* slab = nullptr;
+  int R = 0, C = 0, depth = 0;
+  std::vector<uint8_t> key;  // DFS path: 0 = lower (<= floor) child, 1 = upper (>= ceil) child
+};
+
+static int key_cmp(const std::vector<uint8_t>& a, const std::vector<uint8_t>& b) {
+  const size_t n = std::min(a.size(), b.size());
+  for (size_t i = 0; i < n; i++)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  if (a.size() == b.size()) return 0;
+  return a.size() < b.size() ? -1 : 1;  // an ancestor precedes its descendants (pre-order)
+}
+
+struct lpr_bb {
+  int device = 0, sms = 148;
+  cudaStream_t stream = nullptr;
+  int n_vars = 0, R0 = 0, C0 = 0, max_depth = 0, Rmax = 0, ldmax = 0;
+  size_t slab_doubles = 0;
+  bool prune = false;
+  std::vector<double*> free_slabs;
+  std::vector<double*> chunks;  // cudaMalloc'ed blocks the slabs are carved from
+  std::vector<BBNode> open;     // stack: back() is the next node in DFS order
+  bool has_inc = false;
+  double inc_z = -INFINITY;
+  std::vector<double> inc_x;
+  std::vector<uint8_t> inc_key;
+  int64_t processed = 0, pivots = 0, depth_overflow = 0;
+  // batch scratch
+  int cap = 0;  // max nodes per batch
+  BBLp* d_lps = nullptr;
+  BBLp* h_lps = nullptr;
+  BBAddc* d_jobs = nullptr;
+  BBAddc* h_jobs = nullptr;
+  BBEval* d_eval = nullptr;
+  BBEval* h_eval = nullptr;
+  double* d_x = nullptr;
+  double* h_x = nullptr;
+  const double** d_tabs = nullptr;
+  const double** h_tabs = nullptr;
+  int* d_dims = nullptr;
+  int* h_dims = nullptr;
+  double* d_col = nullptr;   // 2*cap x Rmax
+  double* d_prow = nullptr;  // 2*cap x ldmax
+  int* d_key = nullptr;      // 2*cap x ldmax
+  int* d_order = nullptr;    // 2*cap x ldmax
+  int* d_running = nullptr;
+  int* h_running = nullptr;
+  // optional node log (sequential mode)
+  int* node_log = nullptr;
+  double* node_z = nullptr;
+  int64_t node_log_cap = 0;
+};
+
+static int bb_take_slab(lpr_bb* h, double** out) {
+  if (h->free_slabs.empty()) {
+    // grow by chunks of 64 slabs (bounded by what cudaMalloc can give)
+    const int per = 64;
+    double* blk = nullptr;
+    cudaError_t e = cudaMalloc(&blk, sizeof(double) * h->slab_doubles * per);
+    int got = per;
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      got = 4;
+      e = cudaMalloc(&blk, sizeof(double) * h->slab_doubles * got);
+      if (e != cudaSuccess) return fail(LPR_E_NOMEM, "B&B node pool: out of device memory (%zu open nodes)", h->open.size());
+    }
+    h->chunks.push_back(blk);
+    for (int i = got - 1; i >= 0; i--) h->free_slabs.push_back(blk + (size_t)i * h->slab_doubles);
+  }
+  *out = h->free_slabs.back();
+  h->free_slabs.pop_back();
+  return LPR_OK;
+}
+static void bb_give_slab(lpr_bb* h, double* s) {
+  if (s) h->free_slabs.push_back(s);
+}
+
+static int bb_alloc_scratch(lpr_bb* h, int cap) {
+  h->cap = cap;
+  const int nlp = 2 * cap;
+#define A_DEV(ptr, type, count) LPR_CUDA(cudaMalloc(&h->ptr, sizeof(type) * (size_t)(count)))
+#define A_HOST(ptr, type, count) LPR_CUDA(cudaMallocHost(&h->ptr, sizeof(type) * (size_t)(count)))
+  A_DEV(d_lps, BBLp, nlp);
+  A_HOST(h_lps, BBLp, nlp);
+  A_DEV(d_jobs, BBAddc, nlp);
+  A_HOST(h_jobs, BBAddc, nlp);
+  A_DEV(d_eval, BBEval, cap);
+  A_HOST(h_eval, BBEval, cap);
+  A_DEV(d_x, double, (size_t)cap * h->n_vars);
+  A_HOST(h_x, double, (size_t)cap * h->n_vars);
+  A_DEV(d_tabs, const double*, cap);
+  A_HOST(h_tabs, const double*, cap);
+  A_DEV(d_dims, int, 3 * cap);
+  A_HOST(h_dims, int, 3 * cap);
+  A_DEV(d_col, double, (size_t)nlp * h->Rmax);
+  A_DEV(d_prow, double, (size_t)nlp * h->ldmax);
+  A_DEV(d_key, int, (size_t)nlp * h->ldmax);
+  A_DEV(d_order, int, (size_t)nlp * h->ldmax);
+  A_DEV(d_running, int, 1);
+  A_HOST(h_running, int, 1);
+#undef A_DEV
+#undef A_HOST
+  return LPR_OK;
+}
+
+// run the DoDualSimplex loop for nlp LPs whose descriptors are in h_lps[0..nlp)
+static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps, int nlp, int* d_running,
+                          int* h_running, int max_elems) {
+  LPR_CUDA(cudaMemcpyAsync(d_lps, h_lps, sizeof(BBLp) * nlp, cudaMemcpyHostToDevice, stream));
+  const long long tiles = ((long long)max_elems / 2 + kSweepThreads * 8 - 1) / (kSweepThreads * 8);
+  const int gx = (int)std::max<long long>(1, std::min<long long>(tiles, std::max(1, sms * 6 / std::max(1, nlp))));
+  dim3 gs(gx, nlp);
+  dim3 ge(std::max(1, std::min(sms, (int)(((long long)max_elems + 8191) / 8192))), nlp);
+  k_bb_negzero<<<ge, 256, 0, stream>>>(d_lps);
+  LPR_LAUNCH_CHECK();
+  int chunk = 2;
+  while (true) {
+    for (int q = 0; q < chunk; q++) {
+      k_bb_select<<<nlp, kBBT, 0, stream>>>(d_lps);
+      LPR_LAUNCH_CHECK();
+      k_bb_sweep<<<gs, kSweepThreads, 0, stream>>>(d_lps);
+      LPR_LAUNCH_CHECK();
+    }
+    k_bb_select<<<nlp, kBBT, 0, stream>>>(d_lps);  // commits the last sweep; may stage the next pivot
+    LPR_LAUNCH_CHECK();
+    k_bb_count_running<<<1, 256, 0, stream>>>(d_lps, nlp, d_running);
+    LPR_LAUNCH_CHECK();
+    LPR_CUDA(cudaMemcpyAsync(h_running, d_running, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    k_bb_sweep<<<gs, kSweepThreads, 0, stream>>>(d_lps);
+    LPR_LAUNCH_CHECK();
+    LPR_CUDA(cudaStreamSynchronize(stream));
+    if (*h_running == 0) break;
+    chunk = std::min(16, chunk * 2);
+  }
+  k_bb_round<<<ge, 256, 0, stream>>>(d_lps);  // children are stored rounded (:1124, :1187)
+  LPR_LAUNCH_CHECK();
+  LPR_CUDA(cudaMemcpyAsync(h_lps, d_lps, sizeof(BBLp) * nlp, cudaMemcpyDeviceToHost, stream));
+  LPR_CUDA(cudaStreamSynchronize(stream));
+  return LPR_OK;
+}
+
+static int bb_run_addc(cudaStream_t stream, int sms, BBAddc* h_jobs, BBAddc* d_jobs, int njobs, int maxC,
+                       size_t max_child_elems) {
+  LPR_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(BBAddc) * njobs, cudaMemcpyHostToDevice, stream));
+  dim3 gc(std::max(1, std::min(sms * 2, (int)((max_child_elems + 4095) / 4096))), njobs);
+  k_bb_addc_copy<<<gc, 256, 0, stream>>>(d_jobs);
+  LPR_LAUNCH_CHECK();
+  dim3 gs((maxC + 127) / 128, njobs);
+  k_bb_colsum<<<gs, 128, 0, stream>>>(d_jobs);
+  LPR_LAUNCH_CHECK();
+  k_bb_addc_elim<<<njobs, kBBT, 0, stream>>>(d_jobs);
+  LPR_LAUNCH_CHECK();
+  return LPR_OK;
+}
+
+static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processed_out, int64_t* pivots_out,
+                      bool* hit_limit) {
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  int64_t done = 0, piv = 0;
+  if (hit_limit) *hit_limit = false;
+  while (!h->open.empty()) {
+    if (max_nodes >= 0 && done >= max_nodes) {
+      if (hit_limit) *hit_limit = true;
+      break;
+    }
+    int nb = (int)std::min<int64_t>(std::min<int64_t>(batch, h->cap), (int64_t)h->open.size());
+    if (max_nodes >= 0) nb = (int)std::min<int64_t>(nb, max_nodes - done);
+    std::vector<BBNode> cur;
+    for (int i = 0; i < nb; i++) {  // cur[0] is the DFS-next node
+      cur.push_back(std::move(h->open.back()));
+      h->open.pop_back();
+    }
+    for (int i = 0; i < nb; i++) {
+      h->h_tabs[i] = cur[i].slab;
+      h->h_dims[3 * i] = cur[i].R;
+      h->h_dims[3 * i + 1] = cur[i].C;
+      h->h_dims[3 * i + 2] = h->ldmax;
+    }
+    LPR_CUDA(cudaMemcpyAsync(h->d_tabs, h->h_tabs, sizeof(double*) * nb, cudaMemcpyHostToDevice, h->stream));
+    LPR_CUDA(cudaMemcpyAsync(h->d_dims, h->h_dims, sizeof(int) * 3 * nb, cudaMemcpyHostToDevice, h->stream));
+    k_bb_eval<<<nb, kBBT, 0, h->stream>>>(h->d_tabs, h->d_dims, h->n_vars, h->d_eval, h->d_x);
+    LPR_LAUNCH_CHECK();
+    LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(BBEval) * nb, cudaMemcpyDeviceToHost, h->stream));
+    LPR_CUDA(cudaMemcpyAsync(h->h_x, h->d_x, sizeof(double) * (size_t)nb * h->n_vars, cudaMemcpyDeviceToHost, h->stream));
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
+
+    // host bookkeeping in DFS (pop) order: prune, incumbent, branch (:1060-1076)
+    struct Job { int node; int side; };
+    std::vector<Job> jobs;
+    for (int i = 0; i < nb; i++) {
+      const BBEval& ev = h->h_eval[i];
+      const int64_t q = h->processed++;
+      done++;
+      bool pruned = false;
+      if (h->prune && h->has_inc) {  // ShouldPrunebranch :985-1004 (+ DFS-key tie rule)
+        if (ev.z < h->inc_z || (ev.z == h->inc_z && key_cmp(cur[i].key, h->inc_key) > 0)) pruned = true;
+      }
+      if (!pruned && ev.all_integer) {  // UpdateOptimalSolution :935-983
+        if (!h->has_inc || ev.z > h->inc_z || (ev.z == h->inc_z && key_cmp(cur[i].key, h->inc_key) < 0)) {
+          h->has_inc = true;
+          h->inc_z = ev.z;
+          h->inc_x.assign(h->h_x + (size_t)i * h->n_vars, h->h_x + (size_t)(i + 1) * h->n_vars);
+          h->inc_key = cur[i].key;
+        }
+      }
+      if (h->node_log && q < h->node_log_cap) {
+        h->node_log[4 * q + 0] = cur[i].depth;
+        h->node_log[4 * q + 1] = pruned ? -1 : ev.branch_var;
+        h->node_log[4 * q + 2] = pruned ? 0 : ev.all_integer;
+        h->node_log[4 * q + 3] = pruned ? 1 : 0;
+        if (h->node_z) h->node_z[q] = ev.z;
+      }
+      if (pruned || ev.branch_var < 0) continue;
+      if (cur[i].depth + 1 > h->max_depth) {
+        h->depth_overflow++;
+        continue;
+      }
+      jobs.push_back({i, 0});
+      jobs.push_back({i, 1});
+    }
+    // children: AddConstraint + DoDualSimplex, batched
+    const int nj = (int)jobs.size();
+    std::vector<double*> slabA(nj, nullptr), slabB(nj, nullptr);
+    if (nj > 0) {
+      int maxC = 0;
+      size_t max_elems = 0;
+      for (int j = 0; j < nj; j++) {
+        if ((rc = bb_take_slab(h, &slabA[j]))) return rc;
+        if ((rc = bb_take_slab(h, &slabB[j]))) return rc;
+        const BBNode& nd = cur[jobs[j].node];
+        const BBEval& ev = h->h_eval[jobs[j].node];
+        BBAddc& jb = h->h_jobs[j];
+        jb.parent = nd.slab;
+        jb.child = slabA[j];
+        jb.key = h->d_key + (size_t)j * h->ldmax;
+        jb.order = h->d_order + (size_t)j * h->ldmax;
+        jb.R = nd.R;
+        jb.C = nd.C;
+        jb.ldp = h->ldmax;
+        jb.ldc = h->ldmax;
+        jb.n_vars = h->n_vars;
+        jb.var = ev.branch_var;
+        jb.type = jobs[j].side;
+        // (int)Math.Floor / (int)Math.Ceiling :870-871
+        jb.bound = jobs[j].side == 0 ? (double)(int)std::floor(ev.branch_val) : (double)(int)std::ceil(ev.branch_val);
+        maxC = std::max(maxC, nd.C);
+        max_elems = std::max(max_elems, (size_t)(nd.R + 1) * h->ldmax);
+        BBLp& lp = h->h_lps[j];
+        memset(&lp, 0, sizeof lp);
+        lp.buf[0] = slabA[j];
+        lp.buf[1] = slabB[j];
+        lp.col = h->d_col + (size_t)j * h->Rmax;
+        lp.prow = h->d_prow + (size_t)j * h->ldmax;
+        lp.log = nullptr;
+        lp.log_cap = 0;
+        lp.R = nd.R + 1;
+        lp.C = nd.C + 1;
+        lp.ld = h->ldmax;
+        lp.status = LPR_RUNNING;
+        lp.max_piv = -1;
+      }
+      if ((rc = bb_run_addc(h->stream, h->sms, h->h_jobs, h->d_jobs, nj, maxC, max_elems))) return rc;
+      if ((rc = bb_solve_batch(h->stream, h->sms, h->h_lps, h->d_lps, nj, h->d_running, h->h_running, (int)max_elems)))
+        return rc;
+    }
+    // push feasible children so that the DFS order is preserved: children of cur[0] end on top,
+    // lower branch above upper branch (:1210-1213)
+    for (int i = nb - 1; i >= 0; i--) {
+      for (int side = 1; side >= 0; side--) {
+        for (int j = 0; j < nj; j++) {
+          if (jobs[j].node != i || jobs[j].side != side) continue;
+          const BBLp& lp = h->h_lps[j];
+          piv += lp.npiv;
+          if (lp.status == LPR_OPTIMAL) {
+            BBNode ch;
+            ch.slab = lp.src ? slabB[j] : slabA[j];
+            bb_give_slab(h, lp.src ? slabA[j] : slabB[j]);
+            ch.R = lp.R;
+            ch.C = lp.C;
+            ch.depth = cur[i].depth + 1;
+            ch.key = cur[i].key;
+            ch.key.push_back((uint8_t)side);
+            h->open.push_back(std::move(ch));
+          } else {
+            bb_give_slab(h, slabA[j]);
+            bb_give_slab(h, slabB[j]);
+          }
+        }
+      }
+    }
+    for (int i = 0; i < nb; i++) bb_give_slab(h, cur[i].slab);
+  }
+  h->pivots += piv;
+  if (processed_out) *processed_out = done;
+  if (pivots_out) *pivots_out = piv;
+  return LPR_OK;
+}
+
+extern "C" {
+
+int lpr_bb_destroy(lpr_bb* h) {
+  if (!h) return LPR_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (double* c : h->chunks) cudaFree(c);
+  cudaFree(h->d_lps); cudaFree(h->d_jobs); cudaFree(h->d_eval); cudaFree(h->d_x); cudaFree(h->d_tabs);
+  cudaFree(h->d_dims); cudaFree(h->d_col); cudaFree(h->d_prow); cudaFree(h->d_key); cudaFree(h->d_order);
+  cudaFree(h->d_running);
+  if (h->h_lps) cudaFreeHost(h->h_lps);
+  if (h->h_jobs) cudaFreeHost(h->h_jobs);
+  if (h->h_eval) cudaFreeHost(h->h_eval);
+  if (h->h_x) cudaFreeHost(h->h_x);
+  if (h->h_tabs) cudaFreeHost(h->h_tabs);
+  if (h->h_dims) cudaFreeHost(h->h_dims);
+  if (h->h_running) cudaFreeHost(h->h_running);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return LPR_OK;
+}
+
+static int bb_create_empty(int device, int rows, int cols, int n_vars, int enable_pruning, lpr_bb** out) {
+  if (!out) return fail(LPR_E_BADARG, "out is null");
+  *out = nullptr;
+  if (rows < 1 || cols < 2 || n_vars < 1 || n_vars > cols - 1)
+    return fail(LPR_E_BADARG, "bad B&B shape rows=%d cols=%d n_vars=%d", rows, cols, n_vars);
+  int rc = select_device(device);
+  if (rc) return rc;
+  lpr_bb* h = new (std::nothrow) lpr_bb();
+  if (!h) return fail(LPR_E_NOMEM, "host allocation failed");
+  h->device = device;
+  h->sms = sm_count(device);
+  h->n_vars = n_vars;
+  h->R0 = rows;
+  h->C0 = cols;
+  const char* md = getenv("LPR_BB_MAX_DEPTH");
+  h->max_depth = md ? std::max(1, atoi(md)) : 128;
+  h->Rmax = rows + h->max_depth;
+  h->ldmax = round_up(cols + h->max_depth, 16);
+  h->slab_doubles = (size_t)h->Rmax * h->ldmax;
+  h->prune = enable_pruning != 0;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(LPR_E_CUDA, "stream creation failed");
+  }
+  const char* bc = getenv("LPR_BB_BATCH");
+  rc = bb_alloc_scratch(h, bc ? std::max(1, atoi(bc)) : 32);
+  if (rc) {
+    lpr_bb_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return LPR_OK;
+}
+
+static int bb_push_host_node(lpr_bb* h, int R, int C, int depth, const uint8_t* key, int key_len, const double* dense,
+                             bool round) {
+  if (R > h->Rmax || C > h->ldmax) return fail(LPR_E_CAPACITY, "node %dx%d exceeds the slab size", R, C);
+  BBNode nd;
+  int rc = bb_take_slab(h, &nd.slab);
+  if (rc) return rc;
+  LPR_CUDA(cudaMemsetAsync(nd.slab, 0, sizeof(double) * h->slab_doubles, h->stream));
+  LPR_CUDA(cudaMemcpy2DAsync(nd.slab, sizeof(double) * h->ldmax, dense, sizeof(double) * C, sizeof(double) * C, R,
+                             cudaMemcpyHostToDevice, h->stream));
+  if (round) {
+    k_round4<<<h->sms * 2, 256, 0, h->stream>>>(nd.slab, (size_t)R * h->ldmax);  // :1021
+    LPR_LAUNCH_CHECK();
+  }
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  nd.R = R;
+  nd.C = C;
+  nd.depth = depth;
+  nd.key.assign(key, key + key_len);
+  h->open.push_back(std::move(nd));
+  return LPR_OK;
+}
+
+int lpr_bb_create(int device, int rows, int cols, const double* root_tableau, int n_vars, int enable_pruning,
+                  lpr_bb** out) {
+  lpr_bb* h = nullptr;
+  int rc = bb_create_empty(device, rows, cols, n_vars, enable_pruning, &h);
+  if (rc) return rc;
+  if (root_tableau) {
+    rc = bb_push_host_node(h, rows, cols, 0, nullptr, 0, root_tableau, true);
+    if (rc) {
+      lpr_bb_destroy(h);
+      return rc;
+    }
+  }
+  *out = h;
+  return LPR_OK;
+}
+
+int lpr_bb_open_count(lpr_bb* h, int64_t* n) {
+  if (!h || !n) return fail(LPR_E_BADARG, "null argument");
+  *n = (int64_t)h->open.size();
+  return LPR_OK;
+}
+
+int lpr_bb_run(lpr_bb* h, int64_t max_nodes, int64_t* processed, int64_t* pivots) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  return bb_process(h, max_nodes, h->cap, processed, pivots, nullptr);
+}
+
+int lpr_bb_get_incumbent(lpr_bb* h, int* has, double* z, double* x, int* key, int* key_len) {
+  if (!h || !has) return fail(LPR_E_BADARG, "null argument");
+  *has = h->has_inc ? 1 : 0;
+  if (z) *z = h->inc_z;
+  if (x && h->has_inc) std::copy(h->inc_x.begin(), h->inc_x.end(), x);
+  if (key_len) {
+    const int capk = *key_len;
+    *key_len = (int)h->inc_key.size();
+    if (key)
+      for (int i = 0; i < std::min<int>(capk, (int)h->inc_key.size()); i++) key[i] = h->inc_key[i];
+  }
+  return LPR_OK;
+}
+
+int lpr_bb_set_incumbent(lpr_bb* h, double z, const double* x, const int* key, int key_len) {
+  if (!h || !x || key_len < 0 || (key_len > 0 && !key)) return fail(LPR_E_BADARG, "bad incumbent");
+  std::vector<uint8_t> k(key_len);
+  for (int i = 0; i < key_len; i++) k[i] = (uint8_t)key[i];
+  if (!h->has_inc || z > h->inc_z || (z == h->inc_z && key_cmp(k, h->inc_key) < 0)) {
+    h->has_inc = true;
+    h->inc_z = z;
+    h->inc_x.assign(x, x + h->n_vars);
+    h->inc_key = k;
+  }
+  return LPR_OK;
+}
+
+// node record: int32 R, C, depth, key_len; key bytes padded to 8; R*C doubles
+int lpr_bb_export_nodes(lpr_bb* h, int max_nodes, void* buf, int64_t buf_cap, int64_t* bytes, int* n_exported) {
+  if (!h || !buf || !bytes || !n_exported) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  char* p = (char*)buf;
+  int64_t used = 0;
+  int n = 0;
+  // shallowest nodes sit at the bottom of the stack: give those away (largest subtrees)
+  while (n < max_nodes && !h->open.empty()) {
+    BBNode& nd = h->open.front();
+    const int64_t kl = (int64_t)nd.key.size(), kpad = (kl + 7) / 8 * 8;
+    const int64_t need = 16 + kpad + (int64_t)sizeof(double) * nd.R * nd.C;
+    if (used + need > buf_cap) break;
+    int32_t hdr[4] = {nd.R, nd.C, nd.depth, (int32_t)kl};
+    memcpy(p + used, hdr, 16);
+    memset(p + used + 16, 0, kpad);
+    if (kl) memcpy(p + used + 16, nd.key.data(), kl);
+    LPR_CUDA(cudaMemcpy2D(p + used + 16 + kpad, sizeof(double) * nd.C, nd.slab, sizeof(double) * h->ldmax,
+                          sizeof(double) * nd.C, nd.R, cudaMemcpyDeviceToHost));
+    used += need;
+    bb_give_slab(h, nd.slab);
+    h->open.erase(h->open.begin());
+    n++;
+  }
+  *bytes = used;
+  *n_exported = n;
+  return LPR_OK;
+}
+
+int lpr_bb_import_nodes(lpr_bb* h, const void* buf, int64_t bytes) {
+  if (!h || (!buf && bytes > 0)) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  const char* p = (const char*)buf;
+  int64_t off = 0;
+  std::vector<BBNode> incoming;
+  while (off + 16 <= bytes) {
+    int32_t hdr[4];
+    memcpy(hdr, p + off, 16);
+    const int64_t kl = hdr[3], kpad = (kl + 7) / 8 * 8;
+    const int64_t need = 16 + kpad + (int64_t)sizeof(double) * hdr[0] * hdr[1];
+    if (off + need > bytes) return fail(LPR_E_BADARG, "truncated node record");
+    rc = bb_push_host_node(h, hdr[0], hdr[1], hdr[2], (const uint8_t*)(p + off + 16), (int)kl,
+                           (const double*)(p + off + 16 + kpad), false);
+    if (rc) return rc;
+    off += need;
+  }
+  // keep the stack sorted so that back() is the DFS-first open node
+  std::stable_sort(h->open.begin(), h->open.end(),
+                   [](const BBNode& a, const BBNode& b) { return key_cmp(a.key, b.key) > 0; });
+  return LPR_OK;
+}
+
+int lpr_bb_solve(int device, int rows, int cols, const double* final_tableau, int n_vars, int enable_pruning,
+                 int64_t max_nodes, double* x, double* z, int* has_solution, int64_t* nodes, int64_t* pivots,
+                 int* node_log, double* node_z, int64_t node_log_cap, int* status) {
+  if (!final_tableau) return fail(LPR_E_BADARG, "null tableau");
+  lpr_bb* h = nullptr;
+  int rc = lpr_bb_create(device, rows, cols, final_tableau, n_vars, enable_pruning, &h);
+  if (rc) return rc;
+  h->node_log = node_log;
+  h->node_z = node_z;
+  h->node_log_cap = node_log ? node_log_cap : 0;
+  bool limit = false;
+  int64_t done = 0, piv = 0;
+  // sequential reference order: one node per round
+  rc = bb_process(h, max_nodes, 1, &done, &piv, &limit);
+  if (rc == LPR_OK) {
+    if (has_solution) *has_solution = h->has_inc ? 1 : 0;
+    if (z) *z = h->has_inc ? h->inc_z : -INFINITY;
+    if (x)
+      for (int i = 0; i < n_vars; i++) x[i] = h->has_inc ? h->inc_x[i] : 0.0;
+    if (nodes) *nodes = done;
+    if (pivots) *pivots = piv;
+    if (status) *status = limit ? LPR_NODE_LIMIT : LPR_OPTIMAL;
+  }
+  lpr_bb_destroy(h);
+  return rc;
+}
+
+// ---- building blocks on a single lpr_tab (parity tests, C# shim of DualSimplexSolverBB) --------------
+int lpr_tab_round4(lpr_tab* h) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  k_round4<<<h->sms * 2, 256, 0, h->stream>>>(h->T, (size_t)h->R * h->ld);
+  LPR_LAUNCH_CHECK();
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  return LPR_OK;
+}
+
+int lpr_tab_bb_node_solve(lpr_tab* h, int64_t max_pivots, int* status, int64_t* n_pivots, int* pivot_log,
+                          int64_t log_cap) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  if ((rc = tab_ensure_T2(h))) return rc;
+  if (pivot_log && log_cap > 0 && (rc = tab_ensure_log(h, std::min<long long>(log_cap, 1 << 22)))) return rc;
+  BBLp* d_lp = nullptr;
+  BBLp* h_lp = nullptr;
+  int *d_run = nullptr, *h_run = nullptr;
+  LPR_CUDA(cudaMalloc(&d_lp, sizeof(BBLp)));
+  LPR_CUDA(cudaMallocHost(&h_lp, sizeof(BBLp)));
+  LPR_CUDA(cudaMalloc(&d_run, sizeof(int)));
+  LPR_CUDA(cudaMallocHost(&h_run, sizeof(int)));
+  memset(h_lp, 0, sizeof(BBLp));
+  h_lp->buf[0] = h->T;
+  h_lp->buf[1] = h->T2;
+  h_lp->col = h->col[0];
+  h_lp->prow = h->prow;
+  h_lp->log = (pivot_log && log_cap > 0) ? h->log : nullptr;
+  h_lp->log_cap = (pivot_log && log_cap > 0) ? (int)std::min<long long>(h->log_cap, log_cap) : 0;
+  h_lp->R = h->R;
+  h_lp->C = h->C;
+  h_lp->ld = h->ld;
+  h_lp->status = LPR_RUNNING;
+  h_lp->max_piv = max_pivots;
+  // note: the building block returns the un-rounded final tableau (rounding is the caller's step :1124)
+  LPR_CUDA(cudaMemcpyAsync(d_lp, h_lp, sizeof(BBLp), cudaMemcpyHostToDevice, h->stream));
+  {
+    const size_t elems = (size_t)h->R * h->ld;
+    dim3 ge(std::max(1, std::min(h->sms, (int)((elems + 8191) / 8192))), 1);
+    const long long tiles = ((long long)elems / 2 + kSweepThreads * 8 - 1) / (kSweepThreads * 8);
+    dim3 gs((int)std::max<long long>(1, std::min<long long>(tiles, h->sms * 6)), 1);
+    k_bb_negzero<<<ge, 256, 0, h->stream>>>(d_lp);
+    LPR_LAUNCH_CHECK();
+    int chunk = 2;
+    while (true) {
+      for (int q = 0; q < chunk; q++) {
+        k_bb_select<<<1, kBBT, 0, h->stream>>>(d_lp);
+        LPR_LAUNCH_CHECK();
+        k_bb_sweep<<<gs, kSweepThreads, 0, h->stream>>>(d_lp);
+        LPR_LAUNCH_CHECK();
+      }
+      k_bb_select<<<1, kBBT, 0, h->stream>>>(d_lp);
+      LPR_LAUNCH_CHECK();
+      k_bb_count_running<<<1, 256, 0, h->stream>>>(d_lp, 1, d_run);
+      LPR_LAUNCH_CHECK();
+      LPR_CUDA(cudaMemcpyAsync(h_run, d_run, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      k_bb_sweep<<<gs, kSweepThreads, 0, h->stream>>>(d_lp);
+      LPR_LAUNCH_CHECK();
+      LPR_CUDA(cudaStreamSynchronize(h->stream));
+      if (*h_run == 0) break;
+      chunk = std::min(16, chunk * 2);
+    }
+  }
+  LPR_CUDA(cudaMemcpy(h_lp, d_lp, sizeof(BBLp), cudaMemcpyDeviceToHost));
+  if (h_lp->src == 1) std::swap(h->T, h->T2);  // the result lives in the other ping-pong buffer
+  if (status) *status = h_lp->status;
+  if (n_pivots) *n_pivots = h_lp->npiv;
+  if (pivot_log && log_cap > 0 && h_lp->npiv > 0) {
+    // the log keeps the dropped pivot too (the reference removes it from pivotRows :398-399)
+    long long cnt = std::min<long long>(std::min<long long>(h_lp->npiv, log_cap), h->log_cap);
+    LPR_CUDA(cudaMemcpy(pivot_log, h->log, sizeof(int) * 2 * (size_t)cnt, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_lp);
+  cudaFreeHost(h_lp);
+  cudaFree(d_run);
+  cudaFreeHost(h_run);
+  return LPR_OK;
+}
+
+int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound, int type, lpr_tab** child) {
+  if (!parent || !child || n_vars < 0 || n_vars > parent->C - 1 || var < 0 || var >= std::max(1, n_vars))
+    return fail(LPR_E_BADARG, "bad AddConstraint arguments");
+  int rc = select_device(parent->device);
+  if (rc) return rc;
+  lpr_tab* ch = nullptr;
+  rc = tab_alloc(parent->device, parent->R + 1, parent->C + 1, 0, 0, &ch);
+  if (rc) return rc;
+  BBAddc jb;
+  int *d_key = nullptr, *d_order = nullptr;
+  BBAddc* d_jb = nullptr;
+  cudaError_t e = cudaMalloc(&d_key, sizeof(int) * parent->C);
+  if (e == cudaSuccess) e = cudaMalloc(&d_order, sizeof(int) * parent->C);
+  if (e == cudaSuccess) e = cudaMalloc(&d_jb, sizeof(BBAddc));
+  if (e != cudaSuccess) {
+    cudaFree(d_key); cudaFree(d_order); cudaFree(d_jb);
+    lpr_tab_destroy(ch);
+    return fail(LPR_E_NOMEM, "AddConstraint scratch allocation failed");
+  }
+  jb.parent = parent->T;
+  jb.child = ch->T;
+  jb.key = d_key;
+  jb.order = d_order;
+  jb.R = parent->R;
+  jb.C = parent->C;
+  jb.ldp = parent->ld;
+  jb.ldc = ch->ld;
+  jb.n_vars = n_vars;
+  jb.var = var;
+  jb.type = type;
+  jb.bound = bound;
+  cudaStreamSynchronize(parent->stream);
+  rc = bb_run_addc(ch->stream, ch->sms, &jb, d_jb, 1, parent->C, (size_t)(parent->R + 1) * ch->ld);
+  if (rc == LPR_OK && cudaStreamSynchronize(ch->stream) != cudaSuccess) rc = fail(LPR_E_CUDA, "AddConstraint failed");
+  cudaFree(d_key); cudaFree(d_order); cudaFree(d_jb);
+  if (rc) {
+    lpr_tab_destroy(ch);
+    return rc;
+  }
+  *child = ch;
+  return LPR_OK;
+}
+
+int lpr_tab_bb_branch_var(lpr_tab* h, int n_vars, int* var, double* value, double* x) {
+  if (!h || n_vars < 1 || n_vars > h->C - 1) return fail(LPR_E_BADARG, "bad arguments");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  const double** d_tabs = nullptr;
+  int* d_dims = nullptr;
+  BBEval* d_ev = nullptr;
+  double* d_x = nullptr;
+  LPR_CUDA(cudaMalloc(&d_tabs, sizeof(double*)));
+  LPR_CUDA(cudaMalloc(&d_dims, sizeof(int) * 3));
+  LPR_CUDA(cudaMalloc(&d_ev, sizeof(BBEval)));
+  LPR_CUDA(cudaMalloc(&d_x, sizeof(double) * n_vars));
+  const double* tp = h->T;
+  int dims[3] = {h->R, h->C, h->ld};
+  BBEval ev;
+  cudaError_t e = cudaMemcpyAsync(d_tabs, &tp, sizeof(double*), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_dims, dims, sizeof dims, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    k_bb_eval<<<1, kBBT, 0, h->stream>>>(d_tabs, d_dims, n_vars, d_ev, d_x);
+    count_launch();
+    e = cudaMemcpyAsync(&ev, d_ev, sizeof ev, cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (e == cudaSuccess && x) e = cudaMemcpyAsync(x, d_x, sizeof(double) * n_vars, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_tabs); cudaFree(d_dims); cudaFree(d_ev); cudaFree(d_x);
+  if (e != cudaSuccess) return fail(LPR_E_CUDA, "branch_var: %s", cudaGetErrorString(e));
+  if (var) *var = ev.branch_var;
+  if (value) *value = ev.branch_val;
+  return LPR_OK;
+}
+
+}  // extern "C"

@@ -8,6 +8,7 @@
 // IEEE division, which makes every element bit-identical to the reference's scalar loops.
 #include "tableau.cuh"
 #include "select.cuh"
+#include "sweep.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -60,15 +61,6 @@ static int env_int(const char* name, int dflt) {
 // pre-update factor column (col[cur]) for the sweep.
 // =============================================================================================
 enum : int { F_PRINT = 1, F_FUSED = 2 };
-
-// Programmatic dependent launch (sm_90+): every kernel of the pivot chain first waits for its
-// predecessor's results, then lets its successor start launching; with the launch attribute set
-// by launch_pdl() this hides the launch latency between the dependent kernels of one pivot.
-// Without the attribute both instructions are no-ops.
-__device__ __forceinline__ void pdl_wait_then_release() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
 
 template <int RULE>
 __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, int* mask) {
@@ -405,76 +397,6 @@ __global__ void __launch_bounds__(256) k_primal_select_fused(TabView v, MinIdx* 
 //   OOP : out-of-place (B&B pivots, BranchBoundSimplexSolver.cs:161-192) with -0.0 -> 0.0
 //   EMIT: fused primal path, write next factor column / RHS side buffers
 // =============================================================================================
-template <int SKIP, bool OOP, bool EMIT, int UNROLL>
-__device__ __forceinline__ void sweep_body(const double2* __restrict__ src, double2* __restrict__ dst,
-                                           const double* __restrict__ f, const double2* __restrict__ prow2,
-                                           double* __restrict__ cn, double* __restrict__ rhsb, int R, int C,
-                                           int ld, int p, int e_next, double eps, int reverse) {
-  const unsigned ldv = (unsigned)(ld >> 1);
-  const unsigned long long n = (unsigned long long)R * ldv;
-  constexpr unsigned TILE = kSweepThreads * UNROLL;
-  const unsigned long long ntiles = (n + TILE - 1) / TILE;
-  const unsigned long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
-  const unsigned rhs_chunk = (unsigned)((C - 1) >> 1);
-  const int rhs_odd = (C - 1) & 1;
-  const unsigned e_chunk = e_next >= 0 ? (unsigned)(e_next >> 1) : 0xffffffffu;
-  const int e_odd = e_next & 1;
-  for (unsigned long long tt = t0; tt < t1; tt++) {
-    const unsigned long long t = reverse ? (ntiles - 1 - tt) : tt;  // full mirror: last tiles first
-    const unsigned long long q0 = t * TILE + threadIdx.x;
-    unsigned row = (unsigned)(q0 / ldv);
-    unsigned c = (unsigned)(q0 - (unsigned long long)row * ldv);
-    double2 x[UNROLL];
-    double fv[UNROLL];
-    unsigned rw[UNROLL], cc[UNROLL];
-    bool act[UNROLL];
-#pragma unroll
-    for (int k = 0; k < UNROLL; k++) {
-      const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
-      rw[k] = row;
-      cc[k] = c;
-      act[k] = q < n;
-      if (act[k]) {
-        if (SKIP != 0) {  // the skip decision needs f before the load is issued
-          fv[k] = __ldg(f + row);
-          bool sk = ((int)row != p) && ((SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps));
-          if (sk && !OOP) act[k] = false;
-        }
-        if (act[k]) x[k] = src[q];
-      }
-      c += kSweepThreads;  // ldv may be < 256: wrap as often as needed
-      while (c >= ldv) { c -= ldv; row++; }
-    }
-#pragma unroll
-    for (int k = 0; k < UNROLL; k++) {
-      if (!act[k]) continue;
-      const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
-      if (SKIP == 0) fv[k] = __ldg(f + rw[k]);  // L1-resident: loaded late to keep registers low
-      const double2 pr = __ldg(prow2 + cc[k]);
-      double2 y;
-      bool sk = false;
-      if (SKIP != 0 && OOP && (int)rw[k] != p) sk = (SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps);
-      if ((int)rw[k] == p) {
-        y = pr;
-      } else if (sk) {
-        y = x[k];
-      } else {
-        y.x = __dsub_rn(x[k].x, __dmul_rn(fv[k], pr.x));
-        y.y = __dsub_rn(x[k].y, __dmul_rn(fv[k], pr.y));
-        if (OOP) {
-          if (y.x == 0.0) y.x = 0.0;
-          if (y.y == 0.0) y.y = 0.0;
-        }
-      }
-      dst[q] = y;
-      if (EMIT) {
-        if (cc[k] == e_chunk) cn[rw[k]] = e_odd ? y.y : y.x;
-        if (cc[k] == rhs_chunk) rhsb[rw[k]] = rhs_odd ? y.y : y.x;
-      }
-    }
-  }
-}
-
 template <int SKIP, bool OOP, bool EMIT, int UNROLL>
 __global__ void __launch_bounds__(kSweepThreads) k_sweep(TabView v, double eps, int reverse) {
   pdl_wait_then_release();

@@ -1,0 +1,148 @@
+"""GPU parity tests for BranchBoundSimplexSolver (AddConstraint / DoDualSimplex / ExecuteBranchAndBound)
+through the C ABI against the CPU oracle.  Bit-exact tableaux, identical visit order and incumbent."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import lpr_381_group_v22_b200 as L
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_bit_equal(a, b, what="tableau"):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if not np.array_equal(bits(a), bits(b)):
+        bad = np.argwhere(bits(a) != bits(b))
+        i = tuple(bad[0])
+        raise AssertionError(f"{what}: {len(bad)} elements differ, first at {i}: {a[i]!r} vs {b[i]!r}")
+
+
+def model_a_final():
+    obj = [2, 3, 3, 5, 2, 4]
+    cons = [L.Constraint([11, 8, 6, 14, 10, 10], "<=", 40)]
+    L.add_cli_bound_rows(6, cons)
+    s = L.PrimalSimplexSolver(obj, cons)
+    s.Solve()
+    return s
+
+
+def ip_final(seed, m, n):
+    A, b, c = O.gen_dense_ip(seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    return O.primal_solve(T0, b0)["T"]
+
+
+def test_round4_matches_oracle():
+    rng = np.random.default_rng(0)
+    T = rng.normal(size=(13, 29)) * 10
+    T[0, :5] = [0.00005, -0.00005, 0.00015, -0.00004, 2.5e-5]
+    T[1, :4] = [1e17, -1e17, 0.49999999999999994e-4, 12345.67895]
+    with L.DeviceTableau.from_host(T) as t:
+        t.round4()
+        assert_bit_equal(t.read(), O.bb_round(T))
+
+
+def test_net_round_equals_rint_on_edges():
+    xs = [0.5, 1.5, 2.5, -0.5, -1.5, 0.49999999999999994, -0.49999999999999994, 1e15 + 0.5, 4503599627370497.0,
+          0.0, -0.0, 2.4999999999999996, 1e300, -3.5, 7.5e-5 * 1e4]
+    for x in xs:
+        a, b = O.lib().orc_net_round(x), float(np.rint(x))
+        assert np.float64(a).view(np.uint64) == np.float64(b).view(np.uint64), x
+
+
+@pytest.mark.parametrize("var,typ", [(4, 0), (4, 1), (0, 0), (2, 1)])
+def test_add_constraint_model_a(var, typ):
+    s = model_a_final()
+    Tf = s.GetFinalTableau()
+    val = O.bb_extract(O.bb_round(Tf), 6)[var]
+    bound = np.floor(val) if typ == 0 else np.ceil(val)
+    ref = O.bb_add_constraint(Tf, 6, var, bound, typ)
+    with L.DeviceTableau.from_host(Tf) as t:
+        with t.bb_add_constraint(6, var, bound, typ) as ch:
+            assert_bit_equal(ch.read(), ref)
+
+
+def test_branch_var_and_node_solve_model_a():
+    s = model_a_final()
+    Tf = O.bb_round(s.GetFinalTableau())
+    with L.DeviceTableau.from_host(Tf) as t:
+        var, val, x = t.bb_branch_var(6)
+        rv, rval = O.bb_branch_var(Tf, 6)
+        assert (var, val) == (rv, rval) == (4, 0.2)
+        assert_bit_equal(x, O.bb_extract(Tf, 6), "x")
+        for typ, bound in ((0, 0.0), (1, 1.0)):
+            ref_child = O.bb_add_constraint(Tf, 6, var, bound, typ)
+            ref = O.bb_node_solve(ref_child)
+            with t.bb_add_constraint(6, var, bound, typ) as ch:
+                r = ch.bb_node_solve()
+                assert r["status"] == ref["status"] == L.OPTIMAL
+                assert r["log"].tolist() == ref["log"].tolist()
+                assert_bit_equal(ch.read(), ref["T"])
+
+
+def test_bb_model_a_appendix_c3():
+    s = model_a_final()
+    x, z = L.BranchAndBoundAdapter.SolveFromPrimal(s, enablePruning=False, isMin=False)
+    run = L.BranchAndBoundAdapter.LastRun
+    ref = O.bb_solve(s.GetFinalTableau(), 6, prune=False, max_nodes=20)
+    assert x == [0.0, 1.0, 1.0, 1.0, 0.0, 1.0] and z == 15.0
+    assert run["nodes"] == ref["nodes"] == 20
+    assert run["node_log"].tolist() == ref["node_log"].tolist()
+    assert_bit_equal(run["node_z"], ref["node_z"], "node z")
+    assert run["pivots"] == ref["pivots"]
+    x, z = L.BranchAndBoundAdapter.SolveFromPrimal(s, enablePruning=True)
+    assert L.BranchAndBoundAdapter.LastRun["nodes"] == 5 and z == 15.0
+
+
+@pytest.mark.parametrize("seed,m,n", [(11, 3, 5), (12, 4, 6), (13, 5, 8), (14, 6, 6), (15, 8, 12)])
+@pytest.mark.parametrize("prune", [False, True])
+def test_bb_random_ip_matches_oracle(seed, m, n, prune):
+    Tf = ip_final(seed, m, n)
+    cap = 60
+    ref = O.bb_solve(Tf, n, prune=prune, max_nodes=cap)
+    bb = L.BranchBoundSimplexSolver.BranchAndBound()
+    bb.SetNumVars(n)
+    x, z = bb.ExecuteBranchAndBound([Tf], prune, max_nodes=cap)
+    run = bb.LastRun
+    assert run["nodes"] == ref["nodes"]
+    assert run["status"] == ref["status"]
+    assert run["node_log"].tolist() == ref["node_log"].tolist()
+    assert_bit_equal(run["node_z"], ref["node_z"], "node z")
+    assert run["has_solution"] == ref["has_solution"]
+    if ref["has_solution"]:
+        assert z == ref["z"]
+        assert_bit_equal(np.array(x), ref["x"], "incumbent")
+
+
+@pytest.mark.parametrize("seed,m,n", [(21, 6, 9), (22, 8, 10), (23, 10, 14)])
+def test_bb_pool_batched_equals_sequential(seed, m, n):
+    """Throughput mode (batches of open nodes, pruning on): same incumbent as the sequential oracle."""
+    import ctypes as C
+    from lpr_381_group_v22_b200 import _native as N
+    Tf = ip_final(seed, m, n)
+    ref = O.bb_solve(Tf, n, prune=True, max_nodes=-1)
+    h = N.vp()
+    N.check(N.lib().lpr_bb_create(0, Tf.shape[0], Tf.shape[1], N.pd(N.f64(Tf)), n, 1, C.byref(h)))
+    done, piv, left = C.c_int64(), C.c_int64(), C.c_int64()
+    total = 0
+    while True:
+        N.check(N.lib().lpr_bb_run(h, 64, C.byref(done), C.byref(piv)))
+        total += done.value
+        N.check(N.lib().lpr_bb_open_count(h, C.byref(left)))
+        if left.value == 0:
+            break
+    has, z, klen = C.c_int(), C.c_double(), C.c_int(0)
+    x = np.zeros(n)
+    N.check(N.lib().lpr_bb_get_incumbent(h, C.byref(has), C.byref(z), N.pd(x), None, C.byref(klen)))
+    N.lib().lpr_bb_destroy(h)
+    assert bool(has.value) == ref["has_solution"]
+    if ref["has_solution"]:
+        assert z.value == ref["z"]
+        assert_bit_equal(x, ref["x"], "incumbent")
+    assert total >= 1
