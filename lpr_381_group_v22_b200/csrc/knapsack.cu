@@ -1,0 +1,525 @@
+// knapsack.cu -- branch & bound knapsack (Program.cs:430-471) and its DP arbiter on the device.
+//
+// The reference's KnapsackBranchBoundSimplex / KnapsackBranchBoundSolver bodies are missing
+// (IntegerProgramming/KnapsackBranchBoundSolver.cs:9-11 is an empty class); the call site is the only
+// contract.  Specification implemented here (and by oracle/lpr_oracle.cpp orc_knap_bb):
+//   * items ranked by value/weight descending, ties by lower original id;
+//   * a node fixes some ranked positions to 0/1; its relaxation takes the fixed-1 items, then fills
+//     the free items greedily in rank order and stops at the first one that does not fit (critical
+//     item k): bound = value + v_k * (cap_left / w_k); no critical item or cap_left == 0 => candidate;
+//   * children: x_k = 0 (DFS-first) then x_k = 1; nodes with bound <= incumbent are fathomed;
+//   * the answer is the DFS-first optimal candidate.  Nodes carry their DFS path as a bit string so
+//     that (value, path) selects the same incumbent for ANY exploration order / GPU count.
+// Device layout: the open-node pool is an array of fixed-size records in HBM
+//   [ fixmask : W words | fixval : W words | key : W words | depth, pad ]   W = ceil(n/64)
+// (3.8 KB at n = 10^4).  One warp evaluates one node with ballot/shuffle scans over the
+// ranked item arrays (L2 resident); a second kernel writes the two children of surviving nodes.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace lpr {
+
+struct KnapEval {
+  double val;  // candidate value or bound
+  int crit;    // critical ranked position, -1 = none
+  int type;    // 0 infeasible, 1 candidate, 2 branch
+};
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+__device__ __forceinline__ double warp_incl_scan(double x, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x = __dadd_rn(x, y);
+  }
+  return x;
+}
+
+// one warp per node
+__global__ void __launch_bounds__(128) k_knap_eval(const uint64_t* __restrict__ pool, size_t rec_words, int W,
+                                                   long long first, int count, int n, double capacity,
+                                                   const double* __restrict__ w, const double* __restrict__ v,
+                                                   KnapEval* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (node >= count) return;
+  const uint64_t* rec = pool + (size_t)(first + node) * rec_words;
+  const uint32_t* mask32 = reinterpret_cast<const uint32_t*>(rec);
+  const uint32_t* val32 = reinterpret_cast<const uint32_t*>(rec + W);
+  // pass 1: fixed-1 items
+  double cw = 0.0, cv = 0.0;
+  for (int base = 0; base < n; base += 32) {
+    const int p = base + lane;
+    const uint32_t m = mask32[base >> 5], f = val32[base >> 5];
+    if (p < n && ((m & f) >> lane) & 1u) {
+      cw = __dadd_rn(cw, w[p]);
+      cv = __dadd_rn(cv, v[p]);
+    }
+  }
+  cw = warp_sum(cw);
+  cv = warp_sum(cv);
+  double cap = __dsub_rn(capacity, cw);
+  KnapEval ev;
+  if (cap < 0.0) {
+    ev.val = 0.0;
+    ev.crit = -1;
+    ev.type = 0;
+    if (lane == 0) out[node] = ev;
+    return;
+  }
+  // pass 2: greedy fill of the free items in rank order until the first that does not fit
+  double val = cv;
+  int crit = -1;
+  for (int base = 0; base < n && crit < 0; base += 32) {
+    const int p = base + lane;
+    const uint32_t m = mask32[base >> 5];
+    const bool free = p < n && !((m >> lane) & 1u);
+    const double wi = free ? w[p] : 0.0, vi = free ? v[p] : 0.0;
+    const double incl = warp_incl_scan(wi, lane);
+    const bool fits = !free || (incl <= cap);
+    const unsigned nofit = __ballot_sync(0xffffffffu, !fits);
+    if (nofit) {
+      const int l = __ffs(nofit) - 1;
+      crit = base + l;
+      // take the free items before the critical one
+      const double wpre = __shfl_sync(0xffffffffu, __dsub_rn(incl, wi), l);
+      double vpre = warp_sum(lane < l ? vi : 0.0);
+      cap = __dsub_rn(cap, wpre);
+      val = __dadd_rn(val, vpre);
+    } else {
+      cap = __dsub_rn(cap, __shfl_sync(0xffffffffu, incl, 31));
+      val = __dadd_rn(val, warp_sum(vi));
+    }
+  }
+  if (crit < 0 || cap == 0.0) {
+    ev.val = val;
+    ev.crit = crit;
+    ev.type = 1;
+  } else {
+    ev.val = __dadd_rn(val, __dmul_rn(v[crit], __ddiv_rn(cap, w[crit])));
+    ev.crit = crit;
+    ev.type = 2;
+  }
+  if (lane == 0) out[node] = ev;
+}
+
+// children of surviving nodes: job = (parent record index, critical position); two records per job
+__global__ void k_knap_expand(uint64_t* pool, size_t rec_words, int W, const long long* parent, const int* crit,
+                              int njobs, long long dst_first, const uint64_t* __restrict__ src_pool) {
+  const int job = blockIdx.x;
+  if (job >= njobs) return;
+  const uint64_t* src = src_pool + (size_t)parent[job] * rec_words;
+  const int depth = (int)src[3 * (size_t)W];
+  const int k = crit[job];
+  // stack order: the x_k = 1 child below the x_k = 0 child (the zero child is DFS-first)
+  uint64_t* one = pool + (size_t)(dst_first + 2 * (long long)job) * rec_words;
+  uint64_t* zero = one + rec_words;
+  for (int t = threadIdx.x; t < (int)rec_words; t += blockDim.x) {
+    uint64_t x = src[t], x1 = x, x0 = x;
+    const int word = t % W, sect = t / W;
+    if (t < 3 * W) {
+      if (sect == 0 && word == (k >> 6)) {  // fixmask: mark k fixed
+        x0 |= 1ull << (k & 63);
+        x1 |= 1ull << (k & 63);
+      } else if (sect == 1 && word == (k >> 6)) {  // fixval
+        x1 |= 1ull << (k & 63);
+      } else if (sect == 2 && word == (depth >> 6)) {  // key: append the branch bit
+        x1 |= 1ull << (depth & 63);
+      }
+    } else if (t == 3 * W) {
+      x0 = x1 = (uint64_t)(depth + 1);
+    }
+    zero[t] = x0;
+    one[t] = x1;
+  }
+}
+
+// selection of a candidate node, in ORIGINAL item ids (warp per call)
+__global__ void k_knap_selection(const uint64_t* rec, int W, int n, double capacity, const double* w, int crit,
+                                 const int* rank, uint8_t* chosen) {
+  const uint32_t* mask32 = reinterpret_cast<const uint32_t*>(rec);
+  const uint32_t* val32 = reinterpret_cast<const uint32_t*>(rec + W);
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const bool fixed = (mask32[p >> 5] >> (p & 31)) & 1u;
+    const bool one = (val32[p >> 5] >> (p & 31)) & 1u;
+    bool take = fixed ? one : (crit < 0 || p < crit);
+    chosen[rank[p]] = take ? 1 : 0;
+  }
+  (void)capacity;
+  (void)w;
+}
+
+// ---- DP arbiter: KnapsackBranchBoundSolver.Solve(int, int[], int[]) ----------------------------------
+__global__ void k_dp_item(const long long* __restrict__ prev, long long* __restrict__ next, uint32_t* __restrict__ take,
+                          int cap, int wi, long long vi) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  bool t = false;
+  if (c <= cap) {
+    long long best = prev[c];
+    if (wi <= c) {
+      long long alt = prev[c - wi] + vi;
+      if (alt > best) {
+        best = alt;
+        t = true;
+      }
+    }
+    next[c] = best;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, t);
+  if ((threadIdx.x & 31) == 0 && c <= cap + 31) take[c >> 5] = b;
+}
+__global__ void k_dp_backtrack(const uint32_t* take, size_t words_per_item, int n, int cap, const int* w,
+                               uint8_t* chosen) {
+  if (threadIdx.x || blockIdx.x) return;
+  int c = cap;
+  for (int i = n - 1; i >= 0; i--) {
+    const uint32_t word = take[(size_t)i * words_per_item + (c >> 5)];
+    const bool t = (word >> (c & 31)) & 1u;
+    chosen[i] = t ? 1 : 0;
+    if (t) c -= w[i];
+  }
+}
+
+}  // namespace lpr
+
+using namespace lpr;
+
+struct lpr_knap {
+  int device = 0, sms = 148;
+  cudaStream_t stream = nullptr;
+  int n = 0, W = 0;
+  size_t rec_words = 0;
+  double capacity = 0.0;
+  std::vector<int> rank;  // ranked position -> original id
+  double *d_w = nullptr, *d_v = nullptr;
+  int* d_rank = nullptr;
+  uint64_t* pool = nullptr;
+  long long pool_cap = 0, open = 0;
+  KnapEval *d_eval = nullptr, *h_eval = nullptr;
+  long long *d_parent = nullptr, *h_parent = nullptr;
+  int *d_crit = nullptr, *h_crit = nullptr;
+  uint64_t* stage = nullptr;  // batch staging (the batch is moved off the stack before children are pushed)
+  int batch = 0;
+  // incumbent
+  bool has_inc = false;
+  double inc_val = -INFINITY;
+  std::vector<uint64_t> inc_key;
+  int inc_key_bits = 0;
+  std::vector<uint8_t> inc_chosen;
+  int64_t processed = 0;
+};
+
+static int knap_key_cmp(const uint64_t* a, int abits, const uint64_t* b, int bbits) {
+  const int n = std::min(abits, bbits);
+  for (int i = 0; i < n; i++) {
+    const int ba = (a[i >> 6] >> (i & 63)) & 1, bb = (b[i >> 6] >> (i & 63)) & 1;
+    if (ba != bb) return ba < bb ? -1 : 1;
+  }
+  if (abits == bbits) return 0;
+  return abits < bbits ? -1 : 1;
+}
+
+extern "C" {
+
+int lpr_knap_destroy(lpr_knap* h) {
+  if (!h) return LPR_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_w); cudaFree(h->d_v); cudaFree(h->d_rank); cudaFree(h->pool); cudaFree(h->d_eval);
+  cudaFree(h->d_parent); cudaFree(h->d_crit); cudaFree(h->stage);
+  if (h->h_eval) cudaFreeHost(h->h_eval);
+  if (h->h_parent) cudaFreeHost(h->h_parent);
+  if (h->h_crit) cudaFreeHost(h->h_crit);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return LPR_OK;
+}
+
+int lpr_knap_create(int device, double capacity, int n, const double* weights, const double* values,
+                    lpr_knap** out) {
+  if (!out) return fail(LPR_E_BADARG, "out is null");
+  *out = nullptr;
+  if (n < 1 || !weights || !values) return fail(LPR_E_BADARG, "bad knapsack instance (n=%d)", n);
+  for (int i = 0; i < n; i++)
+    if (!(weights[i] > 0.0)) return fail(LPR_E_BADARG, "weight %d must be positive", i);
+  int rc = select_device(device);
+  if (rc) return rc;
+  lpr_knap* h = new (std::nothrow) lpr_knap();
+  if (!h) return fail(LPR_E_NOMEM, "host allocation failed");
+  h->device = device;
+  h->sms = sm_count(device);
+  h->n = n;
+  h->W = (n + 63) / 64;
+  h->rec_words = 3 * (size_t)h->W + 2;
+  h->capacity = capacity;
+  // rank by value/weight descending, ties by lower original id (host side setup, O(n log n))
+  h->rank.resize(n);
+  std::iota(h->rank.begin(), h->rank.end(), 0);
+  std::vector<double> ratio(n);
+  for (int i = 0; i < n; i++) ratio[i] = values[i] / weights[i];
+  std::stable_sort(h->rank.begin(), h->rank.end(), [&](int a, int b) { return ratio[a] > ratio[b]; });
+  std::vector<double> rw(n), rv(n);
+  for (int p = 0; p < n; p++) {
+    rw[p] = weights[h->rank[p]];
+    rv[p] = values[h->rank[p]];
+  }
+  const char* be = getenv("LPR_KNAP_BATCH");
+  h->batch = be ? std::max(32, atoi(be)) : 16384;
+  const char* pe = getenv("LPR_KNAP_POOL_MB");
+  const size_t pool_bytes = (size_t)(pe ? std::max(16, atoi(pe)) : 4096) << 20;
+  h->pool_cap = std::max<long long>((long long)(pool_bytes / (h->rec_words * 8)), 4LL * h->batch);
+  cudaError_t e;
+#define TRY(x)                                                                                   \
+  if ((e = (x)) != cudaSuccess) {                                                                \
+    lpr_knap_destroy(h);                                                                         \
+    return fail(e == cudaErrorMemoryAllocation ? LPR_E_NOMEM : LPR_E_CUDA, "%s failed: %s", #x, \
+                cudaGetErrorString(e));                                                          \
+  }
+  TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  TRY(cudaMalloc(&h->d_w, sizeof(double) * n));
+  TRY(cudaMalloc(&h->d_v, sizeof(double) * n));
+  TRY(cudaMalloc(&h->d_rank, sizeof(int) * n));
+  TRY(cudaMalloc(&h->pool, sizeof(uint64_t) * h->rec_words * (size_t)h->pool_cap));
+  TRY(cudaMalloc(&h->stage, sizeof(uint64_t) * h->rec_words * (size_t)h->batch));
+  TRY(cudaMalloc(&h->d_eval, sizeof(KnapEval) * h->batch));
+  TRY(cudaMallocHost(&h->h_eval, sizeof(KnapEval) * h->batch));
+  TRY(cudaMalloc(&h->d_parent, sizeof(long long) * h->batch));
+  TRY(cudaMallocHost(&h->h_parent, sizeof(long long) * h->batch));
+  TRY(cudaMalloc(&h->d_crit, sizeof(int) * h->batch));
+  TRY(cudaMallocHost(&h->h_crit, sizeof(int) * h->batch));
+  TRY(cudaMemcpyAsync(h->d_w, rw.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  TRY(cudaMemcpyAsync(h->d_v, rv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  TRY(cudaMemcpyAsync(h->d_rank, h->rank.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+  // root node: nothing fixed, empty key
+  TRY(cudaMemsetAsync(h->pool, 0, sizeof(uint64_t) * h->rec_words, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+#undef TRY
+  h->open = 1;
+  h->inc_chosen.assign(n, 0);
+  *out = h;
+  return LPR_OK;
+}
+
+int lpr_knap_open_count(lpr_knap* h, int64_t* n) {
+  if (!h || !n) return fail(LPR_E_BADARG, "null argument");
+  *n = h->open;
+  return LPR_OK;
+}
+
+int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  int64_t done = 0;
+  int st = LPR_OPTIMAL;
+  const size_t rb = sizeof(uint64_t) * h->rec_words;
+  std::vector<uint64_t> rec(h->rec_words);
+  while (h->open > 0) {
+    if (max_nodes >= 0 && done >= max_nodes) {
+      st = LPR_NODE_LIMIT;
+      break;
+    }
+    long long nb = std::min<long long>(h->batch, h->open);
+    if (max_nodes >= 0) nb = std::min<long long>(nb, max_nodes - done);
+    const long long first = h->open - nb;  // deepest nodes sit at the top of the stack
+    // move the batch off the stack so that children can be written over it
+    LPR_CUDA(cudaMemcpyAsync(h->stage, h->pool + (size_t)first * h->rec_words, rb * nb, cudaMemcpyDeviceToDevice, h->stream));
+    k_knap_eval<<<(int)((nb * 32 + 127) / 128), 128, 0, h->stream>>>(h->stage, h->rec_words, h->W, 0, (int)nb, h->n,
+                                                                      h->capacity, h->d_w, h->d_v, h->d_eval);
+    LPR_LAUNCH_CHECK();
+    LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(KnapEval) * nb, cudaMemcpyDeviceToHost, h->stream));
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
+    h->open = first;
+    done += nb;
+    h->processed += nb;
+    auto fetch = [&](long long idx) -> int {
+      LPR_CUDA(cudaMemcpy(rec.data(), h->stage + (size_t)idx * h->rec_words, rb, cudaMemcpyDeviceToHost));
+      return LPR_OK;
+    };
+    // 1) incumbent from the candidates of this batch: max value, ties -> DFS-first key
+    for (long long i = 0; i < nb; i++) {
+      const KnapEval& ev = h->h_eval[i];
+      if (ev.type != 1) continue;
+      bool better = !h->has_inc || ev.val > h->inc_val;
+      bool tie = h->has_inc && ev.val == h->inc_val;
+      if (!better && !tie) continue;
+      if ((rc = fetch(i))) return rc;
+      const int kbits = (int)rec[3 * (size_t)h->W];
+      const uint64_t* key = rec.data() + 2 * (size_t)h->W;
+      if (tie && knap_key_cmp(key, kbits, h->inc_key.data(), h->inc_key_bits) >= 0) continue;
+      h->has_inc = true;
+      h->inc_val = ev.val;
+      h->inc_key.assign(key, key + h->W);
+      h->inc_key_bits = kbits;
+      uint8_t* d_ch = nullptr;
+      LPR_CUDA(cudaMalloc(&d_ch, h->n));
+      k_knap_selection<<<1, 256, 0, h->stream>>>(h->stage + (size_t)i * h->rec_words, h->W, h->n, h->capacity, h->d_w,
+                                                 ev.crit, h->d_rank, d_ch);
+      count_launch();
+      cudaError_t e = cudaMemcpyAsync(h->inc_chosen.data(), d_ch, h->n, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      cudaFree(d_ch);
+      if (e != cudaSuccess) return fail(LPR_E_CUDA, "selection readback failed: %s", cudaGetErrorString(e));
+    }
+    // 2) surviving branch nodes -> children
+    int nj = 0;
+    for (long long i = 0; i < nb; i++) {
+      const KnapEval& ev = h->h_eval[i];
+      if (ev.type != 2) continue;
+      if (h->has_inc) {
+        if (ev.val < h->inc_val) continue;
+        if (ev.val == h->inc_val) {  // keep only if the node precedes the incumbent in DFS order
+          if ((rc = fetch(i))) return rc;
+          const int kbits = (int)rec[3 * (size_t)h->W];
+          if (knap_key_cmp(rec.data() + 2 * (size_t)h->W, kbits, h->inc_key.data(), h->inc_key_bits) > 0) continue;
+        }
+      }
+      h->h_parent[nj] = i;
+      h->h_crit[nj] = ev.crit;
+      nj++;
+    }
+    if (nj > 0) {
+      if (h->open + 2LL * nj > h->pool_cap)
+        return fail(LPR_E_CAPACITY, "knapsack node pool full (%lld records); raise LPR_KNAP_POOL_MB", h->pool_cap);
+      // keep DFS order inside the batch: later batch entries (deeper / DFS-earlier) stay on top
+      LPR_CUDA(cudaMemcpyAsync(h->d_parent, h->h_parent, sizeof(long long) * nj, cudaMemcpyHostToDevice, h->stream));
+      LPR_CUDA(cudaMemcpyAsync(h->d_crit, h->h_crit, sizeof(int) * nj, cudaMemcpyHostToDevice, h->stream));
+      k_knap_expand<<<nj, 128, 0, h->stream>>>(h->pool, h->rec_words, h->W, h->d_parent, h->d_crit, nj, h->open, h->stage);
+      LPR_LAUNCH_CHECK();
+      LPR_CUDA(cudaStreamSynchronize(h->stream));
+      h->open += 2LL * nj;
+    }
+  }
+  if (processed) *processed = done;
+  if (status) *status = st;
+  return LPR_OK;
+}
+
+int lpr_knap_get_incumbent(lpr_knap* h, double* best, uint8_t* chosen, uint64_t* key, int* key_bits) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  if (best) *best = h->has_inc ? h->inc_val : -INFINITY;
+  if (chosen) memcpy(chosen, h->inc_chosen.data(), h->n);
+  if (key && h->has_inc) memcpy(key, h->inc_key.data(), sizeof(uint64_t) * h->W);
+  if (key_bits) *key_bits = h->has_inc ? h->inc_key_bits : -1;
+  return LPR_OK;
+}
+
+int lpr_knap_set_incumbent(lpr_knap* h, double best, const uint8_t* chosen, const uint64_t* key, int key_bits) {
+  if (!h || !chosen || key_bits < 0 || (key_bits > 0 && !key)) return fail(LPR_E_BADARG, "bad incumbent");
+  std::vector<uint64_t> k(h->W, 0);
+  if (key) memcpy(k.data(), key, sizeof(uint64_t) * h->W);
+  if (!h->has_inc || best > h->inc_val ||
+      (best == h->inc_val && knap_key_cmp(k.data(), key_bits, h->inc_key.data(), h->inc_key_bits) < 0)) {
+    h->has_inc = true;
+    h->inc_val = best;
+    h->inc_key = k;
+    h->inc_key_bits = key_bits;
+    h->inc_chosen.assign(chosen, chosen + h->n);
+  }
+  return LPR_OK;
+}
+
+// records are position independent: export = bottom (shallowest) records of the stack
+int lpr_knap_export_nodes(lpr_knap* h, int max_nodes, void* buf, int64_t buf_cap, int64_t* bytes, int* n_exported) {
+  if (!h || !buf || !bytes || !n_exported) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  const size_t rb = sizeof(uint64_t) * h->rec_words;
+  long long k = std::min<long long>(std::min<long long>(max_nodes, h->open), (long long)(buf_cap / (int64_t)rb));
+  if (k < 0) k = 0;
+  if (k > 0) {
+    LPR_CUDA(cudaMemcpy(buf, h->pool, rb * k, cudaMemcpyDeviceToHost));
+    // close the gap: move the top k records into the hole (order inside the pool does not matter,
+    // the DFS keys decide ties)
+    const long long rest = h->open - k;
+    const long long mv = std::min(k, rest);
+    if (mv > 0)
+      LPR_CUDA(cudaMemcpy(h->pool, h->pool + (size_t)(h->open - mv) * h->rec_words, rb * mv, cudaMemcpyDeviceToDevice));
+    h->open -= k;
+  }
+  *bytes = (int64_t)(rb * k);
+  *n_exported = (int)k;
+  return LPR_OK;
+}
+
+int lpr_knap_import_nodes(lpr_knap* h, const void* buf, int64_t bytes) {
+  if (!h || (!buf && bytes > 0)) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  const size_t rb = sizeof(uint64_t) * h->rec_words;
+  if (bytes % (int64_t)rb) return fail(LPR_E_BADARG, "byte count is not a multiple of the record size");
+  const long long k = bytes / (int64_t)rb;
+  if (h->open + k > h->pool_cap) return fail(LPR_E_CAPACITY, "knapsack node pool full");
+  if (k > 0) LPR_CUDA(cudaMemcpy(h->pool + (size_t)h->open * h->rec_words, buf, rb * k, cudaMemcpyHostToDevice));
+  h->open += k;
+  return LPR_OK;
+}
+
+int lpr_knap_solve(int device, double capacity, int n, const double* weights, const double* values, int64_t max_nodes,
+                   double* best, uint8_t* chosen, int64_t* nodes, int* status) {
+  lpr_knap* h = nullptr;
+  int rc = lpr_knap_create(device, capacity, n, weights, values, &h);
+  if (rc) return rc;
+  int64_t done = 0;
+  int st = LPR_OPTIMAL;
+  rc = lpr_knap_run(h, max_nodes, &done, &st);
+  if (rc == LPR_OK) {
+    if (best) *best = h->has_inc ? h->inc_val : 0.0;
+    if (chosen) memcpy(chosen, h->inc_chosen.data(), n);
+    if (nodes) *nodes = done;
+    if (status) *status = st;
+  }
+  lpr_knap_destroy(h);
+  return rc;
+}
+
+int lpr_knap_dp(int device, int capacity, int n, const int* weights, const int* values, double* best,
+                uint8_t* chosen) {
+  if (n < 1 || !weights || !values || !best) return fail(LPR_E_BADARG, "bad DP arguments");
+  int rc = select_device(device);
+  if (rc) return rc;
+  if (capacity < 0) capacity = 0;
+  const size_t cells = (size_t)capacity + 1;
+  const size_t wpi = (cells + 31) / 32 + 1;  // take-bit words per item
+  long long *d_a = nullptr, *d_b = nullptr;
+  uint32_t* d_take = nullptr;
+  int* d_w = nullptr;
+  uint8_t* d_ch = nullptr;
+  cudaError_t e = cudaMalloc(&d_a, sizeof(long long) * cells);
+  if (e == cudaSuccess) e = cudaMalloc(&d_b, sizeof(long long) * cells);
+  if (e == cudaSuccess) e = cudaMalloc(&d_take, sizeof(uint32_t) * wpi * (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_w, sizeof(int) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_ch, n);
+  if (e == cudaSuccess) e = cudaMemset(d_a, 0, sizeof(long long) * cells);
+  if (e == cudaSuccess) e = cudaMemcpy(d_w, weights, sizeof(int) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const int blocks = (int)((cells + 255) / 256);
+    for (int i = 0; i < n; i++) {
+      k_dp_item<<<blocks, 256>>>(d_a, d_b, d_take + (size_t)i * wpi, capacity, weights[i], (long long)values[i]);
+      count_launch();
+      std::swap(d_a, d_b);
+    }
+    k_dp_backtrack<<<1, 32>>>(d_take, wpi, n, capacity, d_w, d_ch);
+    count_launch();
+    long long bv = 0;
+    e = cudaMemcpy(&bv, d_a + capacity, sizeof(long long), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && chosen) e = cudaMemcpy(chosen, d_ch, n, cudaMemcpyDeviceToHost);
+    *best = (double)bv;
+  }
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_take); cudaFree(d_w); cudaFree(d_ch);
+  if (e != cudaSuccess)
+    return fail(e == cudaErrorMemoryAllocation ? LPR_E_NOMEM : LPR_E_CUDA, "knapsack DP failed: %s", cudaGetErrorString(e));
+  return LPR_OK;
+}
+
+}  // extern "C"
