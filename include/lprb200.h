@@ -150,6 +150,8 @@ int lpr_rev_read_xb(lpr_rev* h, double* xb);      /* x_B = B^-1 b :89, m        
 int lpr_rev_read_binv(lpr_rev* h, double* binv);  /* m x m                                  */
 int lpr_rev_last_solve_ms(const lpr_rev* h, float* ms);
 int lpr_rev_last_refactor_ms(const lpr_rev* h, float* ms);
+/* max |I - B X| before the refresh and the GEMM flop count (4 m^3) of the last refactorisation */
+int lpr_rev_last_refactor_info(const lpr_rev* h, double* residual, double* flops);
 
 /* ---- BranchBoundSimplexSolver (IntegerProgramming/BranchBoundSimplexSolver.cs) ------------- */
 /* building blocks, each on a device tableau */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "lpr_rev_read_binv": (C.c_int, [vp, dp]),
     "lpr_rev_last_solve_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "lpr_rev_last_refactor_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "lpr_rev_last_refactor_info": (C.c_int, [vp, dp, dp]),
     "lpr_tab_round4": (C.c_int, [vp]),
     "lpr_tab_bb_node_solve": (C.c_int, [vp, C.c_int64, ip, lp, ip, C.c_int64]),
     "lpr_tab_bb_add_constraint": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(vp)]),

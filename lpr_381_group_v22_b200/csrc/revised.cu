@@ -106,6 +106,14 @@ __global__ void __launch_bounds__(kT) k_rc(RevView v) {
   v.rc[j] = __dsub_rn(v.c[j], s);  // :98
 }
 
+__global__ void __launch_bounds__(kT) k_y_force(RevView v) {
+  const int j = blockIdx.x * kT + threadIdx.x;
+  if (j >= v.m) return;
+  double s = 0.0;
+  for (int rs = 0; rs < v.YS; rs++) s = __dadd_rn(s, v.ypart[(size_t)rs * v.ldB + j]);
+  v.y[j] = s;
+}
+
 __global__ void __launch_bounds__(kT) k_y(RevView v) {
   if (v.st->status != LPR_RUNNING) return;
   const int j = blockIdx.x * kT + threadIdx.x;
@@ -388,6 +396,27 @@ __global__ void __launch_bounds__(kT) k_update(RevView v) {
   reinterpret_cast<double2*>(v.ypart)[(size_t)rs * ldv + chunk] = acc;
 }
 
+// y partials from the current B^-1 (after a refactorisation): same summation shape as k_update
+__global__ void __launch_bounds__(kT) k_ypart(RevView v) {
+  const int m = v.m;
+  const int ldv = v.ldB >> 1;
+  const int chunk = blockIdx.x * kT + threadIdx.x;
+  const int rs = blockIdx.y;
+  const int r0 = (int)((long long)m * rs / v.YS), r1 = (int)((long long)m * (rs + 1) / v.YS);
+  if (chunk >= ldv) return;
+  const double2* __restrict__ B2 = reinterpret_cast<const double2*>(v.Binv) + chunk;
+  double2 acc = make_double2(0.0, 0.0);
+  for (int row = r0; row < r1; row++) {
+    const double cb = v.cB[row];
+    if (cb != 0.0 || v.dense) {
+      const double2 x = B2[(size_t)row * ldv];
+      acc.x = __dadd_rn(acc.x, __dmul_rn(cb, x.x));
+      acc.y = __dadd_rn(acc.y, __dmul_rn(cb, x.y));
+    }
+  }
+  reinterpret_cast<double2*>(v.ypart)[(size_t)rs * ldv + chunk] = acc;
+}
+
 __global__ void k_rev_reset(RevState* st, long long max_iter) {
   st->status = LPR_RUNNING;
   st->enter = -1;
@@ -460,6 +489,10 @@ __global__ void k_rev_solution(RevView v, const double* c_orig, double* x, doubl
 
 }  // namespace lpr
 
+namespace lpr {
+int refactor_binv(cudaStream_t stream, int m, int n, const double* A, int ldA, double* Binv, int ldB,
+                  const int* basis, double* residual_out, double* flops_out);
+}
 using namespace lpr;
 
 struct lpr_rev {
@@ -475,6 +508,7 @@ struct lpr_rev {
   RevState* st_host = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evb[2] = {nullptr, nullptr};
   float last_ms = 0.f, last_refactor_ms = 0.f;
+  double last_refactor_residual = 0.0, last_refactor_flops = 0.0;
   bool solved = false;
   RevView view() const {
     RevView v;
@@ -636,8 +670,6 @@ int lpr_rev_create_dense_lp(int device, uint64_t seed, int m, int n, lpr_rev** o
   return LPR_OK;
 }
 
-int lpr_rev_refactor(lpr_rev* h);
-
 int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status, int64_t* n_iter, int* log,
                   int64_t log_cap) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
@@ -724,6 +756,38 @@ int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status,
   return LPR_OK;
 }
 
+int lpr_rev_refactor(lpr_rev* h) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  cudaEvent_t a, b;
+  LPR_CUDA(cudaEventCreate(&a));
+  LPR_CUDA(cudaEventCreate(&b));
+  LPR_CUDA(cudaEventRecord(a, h->stream));
+  double res = 0.0, flops = 0.0;
+  rc = refactor_binv(h->stream, h->m, h->n, h->A, h->ldA, h->Binv, h->ldB, h->basis, &res, &flops);
+  if (rc == LPR_OK) {
+    // the dual vector of the next pricing pass must come from the refreshed inverse
+    RevView v = h->view();
+    dim3 gu((h->ldB / 2 + kT - 1) / kT, h->YS);
+    k_ypart<<<gu, kT, 0, h->stream>>>(v);
+    count_launch();
+    // k_y checks the status word: it is RUNNING or terminal; recompute unconditionally with a local copy
+    k_y_force<<<(h->m + kT - 1) / kT, kT, 0, h->stream>>>(v);
+    count_launch();
+    cudaEventRecord(b, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(LPR_E_CUDA, "refactor: y recompute failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    h->last_refactor_ms = ms;
+    h->last_refactor_residual = res;
+    h->last_refactor_flops = flops;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return rc;
+}
+
 #define REV_READ(name, field, count, type)                                                        \
   int name(lpr_rev* h, type* out) {                                                               \
     if (!h || !out) return fail(LPR_E_BADARG, "null argument");                                   \
@@ -757,6 +821,12 @@ int lpr_rev_last_solve_ms(const lpr_rev* h, float* ms) {
 int lpr_rev_last_refactor_ms(const lpr_rev* h, float* ms) {
   if (!h || !ms) return fail(LPR_E_BADARG, "null argument");
   *ms = h->last_refactor_ms;
+  return LPR_OK;
+}
+int lpr_rev_last_refactor_info(const lpr_rev* h, double* residual, double* flops) {
+  if (!h) return fail(LPR_E_BADARG, "null argument");
+  if (residual) *residual = h->last_refactor_residual;
+  if (flops) *flops = h->last_refactor_flops;
   return LPR_OK;
 }
 

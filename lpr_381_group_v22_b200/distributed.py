@@ -1,0 +1,288 @@
+"""Multi-GPU branch & bound: one process per GPU, the open-node pool partitioned across ranks.
+
+The tableau and revised simplex paths do not shard (DESIGN.md "multi-GPU": replicas only).  The two
+branch & bound solvers do: nodes are independent units, so every rank owns a slice of the open-node
+pool in its GPU's HBM and expands it in batches; between batches the ranks
+
+  1. all-reduce the incumbent value (NCCL all-reduce MAX over NVLink -- the north star's "allreduce-min"
+     on the negated objective) and break ties on the DFS path key, so the incumbent -- and therefore
+     the final answer -- is the same for every rank count,
+  2. all-gather the open-node counts (termination = all zero),
+  3. steal work: ranks that ran dry receive the shallowest nodes of the fullest ranks (peer
+     send/recv of node records).
+
+The orchestration below only needs a `pool` object with the small interface of BBPool/KnapPool, which
+is what the world_size-2 gloo tests exercise with a CPU stand-in pool.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+# ------------------------------------------------------------------------------------------------
+# pools (thin wrappers over the C ABI)
+# ------------------------------------------------------------------------------------------------
+class BBPool:
+    """Open-node pool of the branch & bound simplex solver (lpr_bb_*)."""
+
+    def __init__(self, root_tableau, n_vars, prune=True, device=0, rows=None, cols=None):
+        self.n_vars = n_vars
+        h = N.vp()
+        if root_tableau is not None:
+            T = N.f64(root_tableau)
+            rows, cols = T.shape
+            N.check(N.lib().lpr_bb_create(device, rows, cols, N.pd(T), n_vars, int(prune), C.byref(h)))
+        else:
+            N.check(N.lib().lpr_bb_create(device, rows, cols, None, n_vars, int(prune), C.byref(h)))
+        self._h = h
+        self.rows, self.cols = rows, cols
+        self.pivots = 0
+
+    def close(self):
+        if self._h is not None:
+            N.lib().lpr_bb_destroy(self._h)
+            self._h = None
+
+    def open_count(self):
+        n = C.c_int64()
+        N.check(N.lib().lpr_bb_open_count(self._h, C.byref(n)))
+        return n.value
+
+    def run(self, max_nodes):
+        done, piv = C.c_int64(), C.c_int64()
+        N.check(N.lib().lpr_bb_run(self._h, max_nodes, C.byref(done), C.byref(piv)))
+        self.pivots += piv.value
+        return done.value
+
+    def get_incumbent(self):
+        has, z, klen = C.c_int(), C.c_double(), C.c_int(0)
+        x = np.zeros(self.n_vars)
+        N.check(N.lib().lpr_bb_get_incumbent(self._h, C.byref(has), C.byref(z), N.pd(x), None, C.byref(klen)))
+        if not has.value:
+            return None
+        key = np.zeros(max(1, klen.value), dtype=np.int32)
+        kl = C.c_int(klen.value)
+        N.check(N.lib().lpr_bb_get_incumbent(self._h, C.byref(has), C.byref(z), N.pd(x), N.pi(key), C.byref(kl)))
+        return z.value, tuple(int(k) for k in key[:klen.value]), x
+
+    def set_incumbent(self, value, key, payload):
+        k = N.i32(list(key)) if len(key) else None
+        x = N.f64(payload)
+        N.check(N.lib().lpr_bb_set_incumbent(self._h, float(value), N.pd(x), N.pi(k) if k is not None else None, len(key)))
+
+    def export_nodes(self, max_nodes):
+        per = 16 + 136 + 8 * (self.rows + 128) * (self.cols + 128)  # header + key + deepest possible tableau
+        cap = int(per) * max(1, max_nodes)
+        buf = np.empty(cap, dtype=np.uint8)
+        nbytes, n = C.c_int64(), C.c_int()
+        N.check(N.lib().lpr_bb_export_nodes(self._h, max_nodes, buf.ctypes.data_as(N.vp), cap, C.byref(nbytes), C.byref(n)))
+        return buf[:nbytes.value].copy(), n.value
+
+    def import_nodes(self, data):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        if data.size:
+            N.check(N.lib().lpr_bb_import_nodes(self._h, data.ctypes.data_as(N.vp), data.size))
+
+
+class KnapPool:
+    """Open-node pool of the knapsack branch & bound (lpr_knap_*)."""
+
+    def __init__(self, capacity, weights, values, device=0, with_root=True):
+        self.w = N.f64(weights)
+        self.v = N.f64(values)
+        self.n = len(self.w)
+        h = N.vp()
+        N.check(N.lib().lpr_knap_create(device, float(capacity), self.n, N.pd(self.w), N.pd(self.v), C.byref(h)))
+        self._h = h
+        self.rec_bytes = 8 * (3 * ((self.n + 63) // 64) + 2)
+        if not with_root:
+            self.export_nodes(1)
+
+    def close(self):
+        if self._h is not None:
+            N.lib().lpr_knap_destroy(self._h)
+            self._h = None
+
+    def open_count(self):
+        n = C.c_int64()
+        N.check(N.lib().lpr_knap_open_count(self._h, C.byref(n)))
+        return n.value
+
+    def run(self, max_nodes):
+        done, st = C.c_int64(), C.c_int()
+        N.check(N.lib().lpr_knap_run(self._h, max_nodes, C.byref(done), C.byref(st)))
+        return done.value
+
+    def get_incumbent(self):
+        best, kb = C.c_double(), C.c_int()
+        ch = np.zeros(self.n, dtype=np.uint8)
+        key = np.zeros((self.n + 63) // 64, dtype=np.uint64)
+        N.check(N.lib().lpr_knap_get_incumbent(self._h, C.byref(best), ch.ctypes.data_as(N.bp),
+                                               key.ctypes.data_as(N.u64p), C.byref(kb)))
+        if kb.value < 0:
+            return None
+        bits = tuple(int((int(key[i >> 6]) >> (i & 63)) & 1) for i in range(kb.value))
+        return best.value, bits, ch.astype(np.float64)
+
+    def set_incumbent(self, value, key, payload):
+        words = np.zeros((self.n + 63) // 64, dtype=np.uint64)
+        for i, b in enumerate(key):
+            if b:
+                words[i >> 6] |= np.uint64(1) << np.uint64(i & 63)
+        ch = np.ascontiguousarray(np.asarray(payload) != 0, dtype=np.uint8)
+        N.check(N.lib().lpr_knap_set_incumbent(self._h, float(value), ch.ctypes.data_as(N.bp),
+                                               words.ctypes.data_as(N.u64p), len(key)))
+
+    def export_nodes(self, max_nodes):
+        cap = self.rec_bytes * max(1, max_nodes)
+        buf = np.empty(cap, dtype=np.uint8)
+        nbytes, n = C.c_int64(), C.c_int()
+        N.check(N.lib().lpr_knap_export_nodes(self._h, max_nodes, buf.ctypes.data_as(N.vp), cap, C.byref(nbytes), C.byref(n)))
+        return buf[:nbytes.value].copy(), n.value
+
+    def import_nodes(self, data):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        if data.size:
+            N.check(N.lib().lpr_knap_import_nodes(self._h, data.ctypes.data_as(N.vp), data.size))
+
+
+# ------------------------------------------------------------------------------------------------
+# orchestration
+# ------------------------------------------------------------------------------------------------
+def better(a, b):
+    """incumbent order: larger value first, ties -> DFS-first key (a prefix precedes its extensions)."""
+    if b is None:
+        return a is not None
+    if a is None:
+        return False
+    if a[0] != b[0]:
+        return a[0] > b[0]
+    return tuple(a[1]) < tuple(b[1])
+
+
+class _Comm:
+    """torch.distributed plumbing (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, dist, device):
+        import torch
+        self.torch = torch
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.dev = device if (dist is not None and dist.get_backend() == "nccl") else "cpu"
+
+    def allreduce_max(self, value):
+        if self.dist is None:
+            return value
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allgather_ints(self, values):
+        if self.dist is None:
+            return [list(values)]
+        t = self.torch.tensor(list(values), dtype=self.torch.int64, device=self.dev)
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.tolist() for o in out]
+
+    def bcast_array(self, arr, src, dtype):
+        if self.dist is None:
+            return arr
+        t = self.torch.as_tensor(np.ascontiguousarray(arr, dtype=dtype)).to(self.dev)
+        self.dist.broadcast(t, src=src)
+        return t.cpu().numpy()
+
+    def send_bytes(self, data, dst):
+        t = self.torch.from_numpy(np.ascontiguousarray(data, dtype=np.uint8)).to(self.dev)
+        self.dist.send(t, dst=dst)
+
+    def recv_bytes(self, nbytes, src):
+        t = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.dev)
+        self.dist.recv(t, src=src)
+        return t.cpu().numpy()
+
+
+def exchange_incumbent(pool, comm, payload_len):
+    """all-reduce MAX of the value, then the DFS-first key among the ranks that hold that value; the
+    winner's payload (x or the chosen-item vector) is broadcast so every rank ends with the same incumbent."""
+    inc = pool.get_incumbent()
+    zmax = comm.allreduce_max(inc[0] if inc is not None else float("-inf"))
+    if zmax == float("-inf"):
+        return None
+    mine = inc is not None and inc[0] == zmax
+    lens = [v[0] for v in comm.allgather_ints([len(inc[1]) if mine else -1])]
+    kmax = max(max(lens), 1)
+    pad = [-1] * kmax
+    if mine:
+        pad[:len(inc[1])] = list(inc[1])
+    allk = comm.allgather_ints(pad)
+    key, owner = min((tuple(k[:lens[r]]), r) for r, k in enumerate(allk) if lens[r] >= 0)
+    payload = inc[2] if comm.rank == owner else np.zeros(payload_len)
+    payload = comm.bcast_array(payload, owner, np.float64)
+    best = (zmax, key, payload)
+    if better(best, inc):
+        pool.set_incumbent(*best)
+    return best
+
+
+def steal_plan(counts, min_keep=2):
+    """deterministic (donor, receiver, n) plan computed identically on every rank: ranks with no open
+    nodes receive half of the pool of the currently fullest rank."""
+    counts = list(counts)
+    plan = []
+    receivers = [r for r, c in enumerate(counts) if c == 0]
+    for r in receivers:
+        donor = max(range(len(counts)), key=lambda q: (counts[q], -q))
+        give = counts[donor] // 2
+        if counts[donor] < min_keep or give < 1:
+            continue
+        plan.append((donor, r, give))
+        counts[donor] -= give
+        counts[r] += give
+    return plan
+
+
+def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len=None, max_rounds=1 << 30,
+                    seed_nodes_per_rank=8):
+    """Drive `pool` (rank-local) to completion together with the other ranks.  Returns a dict with the
+    incumbent (identical on every rank), node counts and exchange statistics."""
+    comm = _Comm(dist, device)
+    rank, world = comm.rank, comm.world
+    processed, rounds, steals, moved = 0, 0, 0, 0
+    if payload_len is None:
+        payload_len = getattr(pool, "n_vars", None) or getattr(pool, "n")
+    # seeding: rank 0 owns the root; expand it a little so that the first steal round has work to share
+    if world > 1 and rank == 0:
+        guard = 0
+        while 0 < pool.open_count() < seed_nodes_per_rank * world and guard < 64:
+            processed += pool.run(max(1, seed_nodes_per_rank))
+            guard += 1
+    while rounds < max_rounds:
+        rounds += 1
+        counts = [v[0] for v in comm.allgather_ints([pool.open_count()])]
+        if sum(counts) == 0:
+            break
+        for donor, recv, give in steal_plan(counts):
+            if rank == donor:
+                data, n = pool.export_nodes(give)
+                hdr = np.array([data.size], dtype=np.int64).view(np.uint8)
+                comm.send_bytes(hdr, recv)
+                if data.size:
+                    comm.send_bytes(data, recv)
+                steals += 1
+                moved += n
+            elif rank == recv:
+                nbytes = int(comm.recv_bytes(8, donor).view(np.int64)[0])
+                if nbytes:
+                    pool.import_nodes(comm.recv_bytes(nbytes, donor))
+        if pool.open_count() > 0:
+            processed += pool.run(chunk_nodes)
+        exchange_incumbent(pool, comm, payload_len)
+    best = exchange_incumbent(pool, comm, payload_len) if world > 1 else pool.get_incumbent()
+    totals = comm.allgather_ints([processed, steals, moved])
+    return dict(incumbent=best, nodes_local=processed, nodes_total=sum(t[0] for t in totals),
+                steals=sum(t[1] for t in totals), nodes_moved=sum(t[2] for t in totals), rounds=rounds,
+                world=world, rank=rank)

@@ -91,3 +91,33 @@ def test_agrees_with_tableau_solver_objective():
     close(r.FinalZ, p.FinalZ, "z revised vs tableau")
     # duals of the tableau solver = row 0 under the slack columns (SensitivityAnalyzer.cs:212-222)
     close(r.DualPrices, p.GetFinalTableau()[0, n:n + m], "duals")
+
+
+def test_refactorisation_fp64_dmma():
+    """Periodic refactorisation (Newton-Schulz refresh on the FP64 tensor cores) must not move results
+    beyond the 1e-9 tolerance and must not change the pivot sequence."""
+    import ctypes as C
+    from lpr_381_group_v22_b200 import _native as N
+    m, n, seed = 150, 260, 21
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    ref = O.rev_solve(A, b, c, want_binv=True)
+    cons = [L.Constraint(A[i], "<=", b[i]) for i in range(m)]
+    s = L.RevisedPrimalSimplexSolver(list(c), cons, False, refactor_every=25)
+    s.Solve()
+    assert s.PivotLog == [tuple(x) for x in ref["log"].tolist()]
+    close(s.FinalZ, ref["z"], "z")
+    close(s.SolutionVector, ref["x"], "x")
+    close(s.DualPrices, ref["y"], "y")
+    close(s.BInverse, ref["Binv"], "Binv")
+    # explicit refresh at the optimum: residual |I - B X| is small before, B^-1 barely moves
+    before = s.BInverse
+    N.check(N.lib().lpr_rev_refactor(s._h))
+    res, fl = C.c_double(), C.c_double()
+    N.check(N.lib().lpr_rev_last_refactor_info(s._h, C.byref(res), C.byref(fl)))
+    after = s.BInverse
+    assert res.value < 1e-9 and fl.value == 4.0 * 192 ** 3
+    close(after, before, "Binv after refresh")
+    basis = s.BasicVariables
+    Bm = np.column_stack([A[:, v] if v < n else np.eye(m)[:, v - n] for v in basis])
+    assert np.max(np.abs(Bm @ after - np.eye(m))) <= np.max(np.abs(Bm @ before - np.eye(m))) + 1e-13
+    close(s.DualPrices, ref["y"], "y after refresh")
