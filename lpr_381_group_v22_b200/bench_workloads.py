@@ -1,0 +1,101 @@
+"""Synthetic workloads of BASELINE.json configs[3] (knapsack B&B) and configs[4] (B&B simplex) driven
+through the distributed node-pool driver; shared by bench.py and tools/bb_bench.py.  The instances are
+generated on the device / with the package's own generator (no oracle on this path)."""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _native as N
+from .distributed import BBPool, KnapPool, _Comm, run_distributed
+from .tableau import DeviceTableau
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def u01(seed, stream, idx):
+    """counter based generator of SURVEY.md 8(d): bit identical to the CUDA and oracle generators"""
+    with np.errstate(over="ignore"):
+        k = np.uint64(seed) + (np.uint64(stream) << np.uint64(40)) + np.asarray(idx, dtype=np.uint64)
+        return (_splitmix64(k) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+
+def gen_dense_ip(seed, m, n):
+    A = 1.0 + np.floor(20.0 * u01(seed, 0, np.arange(m * n, dtype=np.uint64))).reshape(m, n)
+    b = np.floor(A.sum(axis=1) / 4.0)
+    c = 1.0 + np.floor(30.0 * u01(seed, 2, np.arange(n, dtype=np.uint64)))
+    return A, b, c
+
+
+def gen_knapsack(seed, n):
+    w = 1.0 + np.floor(1000.0 * u01(seed, 0, np.arange(n, dtype=np.uint64)))
+    v = np.maximum(1.0, w + np.floor(200.0 * u01(seed, 1, np.arange(n, dtype=np.uint64))) - 100.0)
+    return w, v, float(np.floor(w.sum() / 2.0))
+
+
+def _sync_time(comm, t):
+    return comm.allreduce_max(t)
+
+
+def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk):
+    """LP relaxation with the tableau solver, then branch & bound simplex with reference semantics
+    (4-d.p. rounding, dual-then-primal node solves), node cap lifted to `max_nodes` per rank-round budget,
+    pruning on; the pool is partitioned across the ranks."""
+    comm = _Comm(dist, f"cuda:{device}")
+    A, b, c = gen_dense_ip(seed, m, n)
+    coef = N.f64(A); rhs = N.f64(b); obj = N.f64(c)
+    h = N.vp()
+    N.check(N.lib().lpr_tab_create_primal(device, n, m, N.pd(obj), N.pd(coef), n, None, None, N.pd(rhs), 1, C.byref(h)))
+    tab = DeviceTableau(h)
+    t0 = time.perf_counter()
+    lp = tab.solve(log_cap=0)
+    lp_ms = tab.last_solve_ms
+    final = tab.read()
+    tab.close()
+    root = final if comm.rank == 0 else None
+    pool = BBPool(root, n, prune=True, device=device, rows=final.shape[0], cols=final.shape[1])
+    if dist is not None:
+        dist.barrier()
+    t1 = time.perf_counter()
+    res = run_distributed(pool, dist, f"cuda:{device}", chunk_nodes=chunk, payload_len=n,
+                          max_rounds=max(1, max_nodes // max(1, chunk)))
+    dt = _sync_time(comm, time.perf_counter() - t1)
+    piv = sum(v[0] for v in comm.allgather_ints([pool.pivots]))
+    left = sum(v[0] for v in comm.allgather_ints([pool.open_count()]))
+    pool.close()
+    inc = res["incumbent"]
+    return dict(workload=f"cfg5 dense IP m={m} n={n} B&B simplex (root {final.shape[0]}x{final.shape[1]})",
+                n_gpus=comm.world, nodes=res["nodes_total"], seconds=dt, nodes_per_s=res["nodes_total"] / dt,
+                pivots_in_nodes=piv, pivots_per_node=piv / max(1, res["nodes_total"]),
+                node_pivots_per_s=piv / dt, lp_relaxation_pivots=lp["n_pivots"], lp_relaxation_ms=lp_ms,
+                incumbent_z=(inc[0] if inc else None), incumbent_nonzeros=(int(np.count_nonzero(inc[2])) if inc else None),
+                open_left=left, steals=res["steals"], nodes_moved=res["nodes_moved"], rounds=res["rounds"],
+                finished=(left == 0))
+
+
+def run_knap_cfg4(n_items, seed, device, dist, max_nodes, chunk):
+    comm = _Comm(dist, f"cuda:{device}")
+    w, v, cap = gen_knapsack(seed, n_items)
+    pool = KnapPool(cap, w, v, device=device, with_root=(comm.rank == 0))
+    if dist is not None:
+        dist.barrier()
+    t1 = time.perf_counter()
+    res = run_distributed(pool, dist, f"cuda:{device}", chunk_nodes=chunk, payload_len=n_items,
+                          max_rounds=max(1, max_nodes // max(1, chunk)), seed_nodes_per_rank=64)
+    dt = _sync_time(comm, time.perf_counter() - t1)
+    left = sum(x[0] for x in comm.allgather_ints([pool.open_count()]))
+    pool.close()
+    inc = res["incumbent"]
+    rec_bytes = 8 * (3 * ((n_items + 63) // 64) + 2)
+    return dict(workload=f"cfg4 knapsack n={n_items} weakly correlated, capacity {cap:.0f}", n_gpus=comm.world,
+                nodes=res["nodes_total"], seconds=dt, nodes_per_s=res["nodes_total"] / dt,
+                node_record_bytes=rec_bytes, record_gbs=3.0 * rec_bytes * res["nodes_total"] / dt / 1e9,
+                best_value=(inc[0] if inc else None), items_chosen=(int(np.count_nonzero(inc[2])) if inc else None),
+                weight_used=(float(np.dot(inc[2], w)) if inc else None), open_left=left, steals=res["steals"],
+                nodes_moved=res["nodes_moved"], rounds=res["rounds"], finished=(left == 0))

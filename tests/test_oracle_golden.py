@@ -192,3 +192,14 @@ def test_bb_quirks():
     T = np.array([[-1.0, 0.0, 0.0, 0.0], [1.0, 1.0, 0.0, -1e-12], [1.0, 0.0, 1.0, 2.0]])
     r = O.bb_node_solve(T)
     assert r["status"] in (O.OPTIMAL, O.INFEASIBLE)
+
+
+def test_package_generators_match_oracle():
+    """the numpy generators the bench uses for cfg4/cfg5 are bit-identical to the oracle's"""
+    from lpr_381_group_v22_b200.bench_workloads import gen_dense_ip, gen_knapsack
+    A, b, c = gen_dense_ip(385, 9, 14)
+    A2, b2, c2 = O.gen_dense_ip(385, 9, 14)
+    assert np.array_equal(A, A2) and np.array_equal(b, b2) and np.array_equal(c, c2)
+    w, v, cap = gen_knapsack(384, 100)
+    w2, v2, cap2 = O.gen_knapsack(384, 100)
+    assert np.array_equal(w, w2) and np.array_equal(v, v2) and cap == cap2
