@@ -306,6 +306,18 @@ def main():
                          "PrimalSimplexSolver.cs:152-211 (no .NET toolchain in the image), single thread like "
                          f"the reference; host has {os.cpu_count()} cores"}
 
+    # -------- branch & bound node pools (BASELINE configs[4] / configs[3]); partitioned across ranks ----
+    bb = knap = None
+    if not os.environ.get("LPR_BENCH_SKIP_BB"):
+        os.environ.setdefault("LPR_BB_PREALLOC_MB", "81920")  # node slabs carved before the timed region
+        from lpr_381_group_v22_b200.bench_workloads import run_bb_cfg5, run_knap_cfg4
+        try:
+            bb = run_bb_cfg5(512, 1024, 385, dev, dist, int(os.environ.get("LPR_BENCH_BB_NODES", "8192")), 512)
+            knap = run_knap_cfg4(10000, 384, dev, dist, 1 << 26, 32768)
+        except Exception as ex:  # the headline line must still be printed
+            bb = bb or {"error": repr(ex)}
+            knap = knap or {"error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -351,6 +363,8 @@ def main():
                                    "frac_of_measured": achieved_pivot / peak,
                                    "frac_of_nominal_8tbs": achieved_pivot / NOMINAL_HBM_GBS}},
         "cpu_baseline": cpu,
+        "bb": bb,
+        "knapsack": knap,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

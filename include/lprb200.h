@@ -177,6 +177,9 @@ int lpr_bb_destroy(lpr_bb* h);
 int lpr_bb_open_count(lpr_bb* h, int64_t* n);
 /* expand up to max_nodes open nodes (deepest first); returns nodes processed / pivots done */
 int lpr_bb_run(lpr_bb* h, int64_t max_nodes, int64_t* processed, int64_t* pivots);
+/* totals since creation; depth_overflow counts nodes whose children were NOT generated because they would
+ * exceed the slab depth headroom (LPR_BB_MAX_DEPTH, default 128) -- a non-zero value means the search was cut */
+int lpr_bb_stats(lpr_bb* h, int64_t* processed, int64_t* pivots, int64_t* depth_overflow, int* max_depth);
 /* incumbent as (z, dfs_key[], x[]) -- the key makes ties deterministic across GPU counts */
 int lpr_bb_get_incumbent(lpr_bb* h, int* has, double* z, double* x, int* key, int* key_len);
 int lpr_bb_set_incumbent(lpr_bb* h, double z, const double* x, const int* key, int key_len);

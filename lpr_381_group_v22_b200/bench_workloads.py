@@ -7,7 +7,7 @@ import time
 import numpy as np
 
 from . import _native as N
-from .distributed import BBPool, KnapPool, _Comm, run_distributed
+from .distributed import BBPool, KnapPool, _Comm, run_distributed, warmup_comm
 from .tableau import DeviceTableau
 
 
@@ -60,17 +60,21 @@ def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk):
     tab.close()
     root = final if comm.rank == 0 else None
     pool = BBPool(root, n, prune=True, device=device, rows=final.shape[0], cols=final.shape[1])
-    if dist is not None:
-        dist.barrier()
+    warmup_comm(dist, f"cuda:{device}")
     t1 = time.perf_counter()
     res = run_distributed(pool, dist, f"cuda:{device}", chunk_nodes=chunk, payload_len=n,
                           max_rounds=max(1, max_nodes // max(1, chunk)))
     dt = _sync_time(comm, time.perf_counter() - t1)
     piv = sum(v[0] for v in comm.allgather_ints([pool.pivots]))
     left = sum(v[0] for v in comm.allgather_ints([pool.open_count()]))
+    st = pool.stats()
+    ovf = sum(v[0] for v in comm.allgather_ints([st["depth_overflow"]]))
     pool.close()
     inc = res["incumbent"]
-    return dict(workload=f"cfg5 dense IP m={m} n={n} B&B simplex (root {final.shape[0]}x{final.shape[1]})",
+    return dict(depth_overflow=ovf, max_depth=st["max_depth"],
+                note="reference semantics (4-d.p. rounding, first-row-with-a-1 extraction, SURVEY Q8/Q10): "
+                     "many children need no pivot; depth_overflow > 0 means chains hit the slab depth headroom",
+                workload=f"cfg5 dense IP m={m} n={n} B&B simplex (root {final.shape[0]}x{final.shape[1]})",
                 n_gpus=comm.world, nodes=res["nodes_total"], seconds=dt, nodes_per_s=res["nodes_total"] / dt,
                 pivots_in_nodes=piv, pivots_per_node=piv / max(1, res["nodes_total"]),
                 node_pivots_per_s=piv / dt, lp_relaxation_pivots=lp["n_pivots"], lp_relaxation_ms=lp_ms,
@@ -83,11 +87,10 @@ def run_knap_cfg4(n_items, seed, device, dist, max_nodes, chunk):
     comm = _Comm(dist, f"cuda:{device}")
     w, v, cap = gen_knapsack(seed, n_items)
     pool = KnapPool(cap, w, v, device=device, with_root=(comm.rank == 0))
-    if dist is not None:
-        dist.barrier()
+    warmup_comm(dist, f"cuda:{device}")
     t1 = time.perf_counter()
     res = run_distributed(pool, dist, f"cuda:{device}", chunk_nodes=chunk, payload_len=n_items,
-                          max_rounds=max(1, max_nodes // max(1, chunk)), seed_nodes_per_rank=64)
+                          max_rounds=max(1, max_nodes // max(1, chunk)), seed_nodes_per_rank=64, low_water=64)
     dt = _sync_time(comm, time.perf_counter() - t1)
     left = sum(x[0] for x in comm.allgather_ints([pool.open_count()]))
     pool.close()

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <vector>
 
 #include "sweep.cuh"
@@ -271,11 +272,19 @@ __global__ void __launch_bounds__(kBBT) k_bb_eval(const double* const* tabs, con
   int nonint = 0;
   for (int i = threadIdx.x; i < n_vars; i += blockDim.x) {
     double xi = 0.0;
-    for (int j = 0; j < R; j++) {  // first row (objective row included) holding a rounded 1
-      double val = net_round4(TAT(T, ld, j, i));
-      if (fabs(val - 1.0) <= 1e-6) {
-        xi = net_round4(TAT(T, ld, j, C - 1));
-        break;
+    // first row (objective row included) holding a rounded 1; rows are fetched 8 at a time so the
+    // scan costs one memory round trip per 8 rows instead of one per row
+    bool found = false;
+    for (int j0 = 0; j0 < R && !found; j0 += 8) {
+      double t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) t[q] = (j0 + q < R) ? TAT(T, ld, j0 + q, i) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        if (!found && j0 + q < R && fabs(net_round4(t[q]) - 1.0) <= 1e-6) {
+          xi = net_round4(TAT(T, ld, j0 + q, C - 1));
+          found = true;
+        }
       }
     }
     x[i] = xi;
@@ -305,22 +314,25 @@ __global__ void __launch_bounds__(kBBT) k_bb_eval(const double* const* tabs, con
 __global__ void k_bb_addc_copy(const BBAddc* jobs) {
   const BBAddc& jb = jobs[blockIdx.y];
   const int R = jb.R, C = jb.C, C2 = C + 1;
-  const size_t total = (size_t)(R + 1) * jb.ldc;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(k / jb.ldc), j = (int)(k % jb.ldc);
-    double v = 0.0;
-    if (i < R) {
-      if (j < C - 1)
-        v = net_round4(net_round4(jb.parent[(size_t)i * jb.ldp + j]));
-      else if (j == C)
-        v = net_round4(net_round4(jb.parent[(size_t)i * jb.ldp + (C - 1)]));
-    } else if (j < C2) {
-      if (j < jb.n_vars && j == jb.var) v = net_round4(1.0);  // :727-730
-      if (j == C2 - 1) v = net_round4(jb.bound);              // :732
-      if (j == C - 1) v = (jb.type == 1) ? -1.0 : 1.0;        // :734-742 (overrides a coefficient there)
-      v = net_round4(v);                                      // :747
+  // rows are dealt to the CTAs of this job, columns to the threads: no integer division per element
+  for (int i = blockIdx.x; i <= R; i += gridDim.x) {
+    const double* prow = jb.parent + (size_t)i * jb.ldp;
+    double* crow = jb.child + (size_t)i * jb.ldc;
+    for (int j = threadIdx.x; j < jb.ldc; j += blockDim.x) {
+      double v = 0.0;
+      if (i < R) {
+        if (j < C - 1)
+          v = net_round4(net_round4(prow[j]));
+        else if (j == C)
+          v = net_round4(net_round4(prow[C - 1]));
+      } else if (j < C2) {
+        if (j < jb.n_vars && j == jb.var) v = net_round4(1.0);  // :727-730
+        if (j == C2 - 1) v = net_round4(jb.bound);              // :732
+        if (j == C - 1) v = (jb.type == 1) ? -1.0 : 1.0;        // :734-742 (overrides a coefficient there)
+        v = net_round4(v);                                      // :747
+      }
+      crow[j] = v;
     }
-    jb.child[k] = v;
   }
 }
 // IdentifyBasicVariables :642-662: column sums over ALL rows (objective row and RHS column included)
@@ -330,10 +342,18 @@ __global__ void k_bb_colsum(const BBAddc* jobs) {
   if (k >= jb.C) return;
   double sum = 0.0;
   int first1 = jb.R;
-  for (int i = 0; i < jb.R; i++) {
-    double v = net_round4(net_round4(jb.parent[(size_t)i * jb.ldp + k]));
-    sum = __dadd_rn(sum, v);
-    if (first1 == jb.R && v == 1.0) first1 = i;
+  for (int i0 = 0; i0 < jb.R; i0 += 8) {  // loads batched 8 rows at a time, sum kept in row order
+    double t[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) t[q] = (i0 + q < jb.R) ? jb.parent[(size_t)(i0 + q) * jb.ldp + k] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      if (i0 + q < jb.R) {
+        const double v = net_round4(net_round4(t[q]));
+        sum = __dadd_rn(sum, v);
+        if (first1 == jb.R && v == 1.0) first1 = i0 + q;
+      }
+    }
   }
   sum = net_round4(sum);
   jb.key[k] = (fabs(sum - 1.0) <= 1e-6) ? first1 : -1;
@@ -347,22 +367,49 @@ __global__ void __launch_bounds__(kBBT) k_bb_addc_elim(const BBAddc* jobs) {
   const int tid = threadIdx.x;
   double* child = jb.child;
   double* v = child + (size_t)R * ldc;  // the new constraint row
-  // rank basic columns by (key, column): position = number of basic columns ordered before
-  if (tid == 0) sh_nb = 0;
-  __syncthreads();
-  int local = 0;
-  for (int k = tid; k < C; k += blockDim.x) {
-    const int kk = jb.key[k];
-    if (kk < 0) continue;
-    int pos = 0;
-    for (int q = 0; q < C; q++) {
-      const int kq = jb.key[q];
-      if (kq >= 0 && (kq < kk || (kq == kk && q < k))) pos++;
-    }
-    jb.order[pos] = k;
-    local++;
+  // 1) compact the basic columns (ascending column) into order[C..2C) scratch-free: two passes over the
+  //    key array with a block-wide running offset; 2) rank them by (key, column) among themselves only
+  //    (nb ~ R entries, not C), position = number of basic columns ordered before.
+  __shared__ int sh_cnt[kBBT / 32];
+  __shared__ int sh_base;
+  int* list = jb.order + C;  // second half of the 2*ld scratch row: (col) compacted, keys re-read
+  if (tid == 0) {
+    sh_nb = 0;
+    sh_base = 0;
   }
-  if (local) atomicAdd(&sh_nb, local);
+  __syncthreads();
+  for (int k0 = 0; k0 < C; k0 += blockDim.x) {
+    const int k = k0 + tid;
+    const bool isb = k < C && jb.key[k] >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, isb);
+    const int lane = tid & 31, w = tid >> 5;
+    if (lane == 0) sh_cnt[w] = __popc(bal);
+    __syncthreads();
+    int off = sh_base;
+    for (int q = 0; q < w; q++) off += sh_cnt[q];
+    if (isb) list[off + __popc(bal & ((1u << lane) - 1u))] = k;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int q = 0; q < (int)(blockDim.x >> 5); q++) tot += sh_cnt[q];
+      sh_base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) sh_nb = sh_base;
+  __syncthreads();
+  {
+    const int nbl = sh_nb;
+    for (int a = tid; a < nbl; a += blockDim.x) {
+      const int k = list[a], kk = jb.key[k];
+      int pos = 0;
+      for (int b = 0; b < nbl; b++) {
+        const int q = list[b], kq = jb.key[q];
+        if (kq < kk || (kq == kk && q < k)) pos++;
+      }
+      jb.order[pos] = k;
+    }
+  }
   __syncthreads();
   const int nb = sh_nb;
   int pos = 0;
@@ -431,6 +478,8 @@ struct lpr_bb {
   std::vector<double> inc_x;
   std::vector<uint8_t> inc_key;
   int64_t processed = 0, pivots = 0, depth_overflow = 0;
+  double t_eval = 0, t_host = 0, t_addc = 0, t_solve = 0, t_push = 0;  // LPR_BB_PROFILE=1 prints these
+  int64_t n_batches = 0, n_children = 0;
   // batch scratch
   int cap = 0;  // max nodes per batch
   BBLp* d_lps = nullptr;
@@ -501,7 +550,7 @@ static int bb_alloc_scratch(lpr_bb* h, int cap) {
   A_DEV(d_col, double, (size_t)nlp * h->Rmax);
   A_DEV(d_prow, double, (size_t)nlp * h->ldmax);
   A_DEV(d_key, int, (size_t)nlp * h->ldmax);
-  A_DEV(d_order, int, (size_t)nlp * h->ldmax);
+  A_DEV(d_order, int, (size_t)nlp * 2 * h->ldmax);
   A_DEV(d_running, int, 1);
   A_HOST(h_running, int, 1);
 #undef A_DEV
@@ -548,7 +597,7 @@ static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps
 static int bb_run_addc(cudaStream_t stream, int sms, BBAddc* h_jobs, BBAddc* d_jobs, int njobs, int maxC,
                        size_t max_child_elems) {
   LPR_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(BBAddc) * njobs, cudaMemcpyHostToDevice, stream));
-  dim3 gc(std::max(1, std::min(sms * 2, (int)((max_child_elems + 4095) / 4096))), njobs);
+  dim3 gc(std::max(1, std::min(64, (sms * 8 + njobs - 1) / njobs)), njobs);
   k_bb_addc_copy<<<gc, 256, 0, stream>>>(d_jobs);
   LPR_LAUNCH_CHECK();
   dim3 gs((maxC + 127) / 128, njobs);
@@ -557,6 +606,10 @@ static int bb_run_addc(cudaStream_t stream, int sms, BBAddc* h_jobs, BBAddc* d_j
   k_bb_addc_elim<<<njobs, kBBT, 0, stream>>>(d_jobs);
   LPR_LAUNCH_CHECK();
   return LPR_OK;
+}
+
+static inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processed_out, int64_t* pivots_out,
@@ -572,6 +625,8 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
     }
     int nb = (int)std::min<int64_t>(std::min<int64_t>(batch, h->cap), (int64_t)h->open.size());
     if (max_nodes >= 0) nb = (int)std::min<int64_t>(nb, max_nodes - done);
+    double tp0 = now_s();
+    h->n_batches++;
     std::vector<BBNode> cur;
     for (int i = 0; i < nb; i++) {  // cur[0] is the DFS-next node
       cur.push_back(std::move(h->open.back()));
@@ -591,6 +646,8 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
     LPR_CUDA(cudaMemcpyAsync(h->h_x, h->d_x, sizeof(double) * (size_t)nb * h->n_vars, cudaMemcpyDeviceToHost, h->stream));
     LPR_CUDA(cudaStreamSynchronize(h->stream));
 
+    double tp1 = now_s();
+    h->t_eval += tp1 - tp0;
     // host bookkeeping in DFS (pop) order: prune, incumbent, branch (:1060-1076)
     struct Job { int node; int side; };
     std::vector<Job> jobs;
@@ -640,7 +697,7 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
         jb.parent = nd.slab;
         jb.child = slabA[j];
         jb.key = h->d_key + (size_t)j * h->ldmax;
-        jb.order = h->d_order + (size_t)j * h->ldmax;
+        jb.order = h->d_order + (size_t)j * 2 * h->ldmax;
         jb.R = nd.R;
         jb.C = nd.C;
         jb.ldp = h->ldmax;
@@ -666,10 +723,18 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
         lp.status = LPR_RUNNING;
         lp.max_piv = -1;
       }
+      double tp2 = now_s();
+      h->t_host += tp2 - tp1;
       if ((rc = bb_run_addc(h->stream, h->sms, h->h_jobs, h->d_jobs, nj, maxC, max_elems))) return rc;
+      if (getenv("LPR_BB_PROFILE")) cudaStreamSynchronize(h->stream);
+      double tp3 = now_s();
+      h->t_addc += tp3 - tp2;
       if ((rc = bb_solve_batch(h->stream, h->sms, h->h_lps, h->d_lps, nj, h->d_running, h->h_running, (int)max_elems)))
         return rc;
+      h->t_solve += now_s() - tp3;
+      h->n_children += nj;
     }
+    double tp4 = now_s();
     // push feasible children so that the DFS order is preserved: children of cur[0] end on top,
     // lower branch above upper branch (:1210-1213)
     for (int i = nb - 1; i >= 0; i--) {
@@ -696,6 +761,7 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
       }
     }
     for (int i = 0; i < nb; i++) bb_give_slab(h, cur[i].slab);
+    h->t_push += now_s() - tp4;
   }
   h->pivots += piv;
   if (processed_out) *processed_out = done;
@@ -708,6 +774,10 @@ extern "C" {
 int lpr_bb_destroy(lpr_bb* h) {
   if (!h) return LPR_OK;
   cudaSetDevice(h->device);
+  if (getenv("LPR_BB_PROFILE"))
+    fprintf(stderr, "[lpr_bb] nodes=%lld batches=%lld children=%lld pivots=%lld | eval %.3fs host %.3fs addc %.3fs solve %.3fs push %.3fs\n",
+            (long long)h->processed, (long long)h->n_batches, (long long)h->n_children, (long long)h->pivots, h->t_eval,
+            h->t_host, h->t_addc, h->t_solve, h->t_push);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (double* c : h->chunks) cudaFree(c);
   cudaFree(h->d_lps); cudaFree(h->d_jobs); cudaFree(h->d_eval); cudaFree(h->d_x); cudaFree(h->d_tabs);
@@ -748,6 +818,24 @@ static int bb_create_empty(int device, int rows, int cols, int n_vars, int enabl
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return fail(LPR_E_CUDA, "stream creation failed");
+  }
+  {  // pre-carve slabs so that steady-state node processing never calls cudaMalloc
+    const char* pm = getenv("LPR_BB_PREALLOC_MB");
+    size_t want = (size_t)(pm ? std::max(0, atoi(pm)) : 1024) << 20;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) want = std::min(want, free_b / 2);
+    size_t nsl = want / (sizeof(double) * h->slab_doubles);
+    while (nsl > 0) {
+      const size_t take = std::min<size_t>(nsl, 512);
+      double* blk = nullptr;
+      if (cudaMalloc(&blk, sizeof(double) * h->slab_doubles * take) != cudaSuccess) {
+        cudaGetLastError();
+        break;
+      }
+      h->chunks.push_back(blk);
+      for (size_t i = take; i-- > 0;) h->free_slabs.push_back(blk + i * h->slab_doubles);
+      nsl -= take;
+    }
   }
   const char* bc = getenv("LPR_BB_BATCH");
   rc = bb_alloc_scratch(h, bc ? std::max(1, atoi(bc)) : 32);
@@ -800,6 +888,15 @@ int lpr_bb_create(int device, int rows, int cols, const double* root_tableau, in
 int lpr_bb_open_count(lpr_bb* h, int64_t* n) {
   if (!h || !n) return fail(LPR_E_BADARG, "null argument");
   *n = (int64_t)h->open.size();
+  return LPR_OK;
+}
+
+int lpr_bb_stats(lpr_bb* h, int64_t* processed, int64_t* pivots, int64_t* depth_overflow, int* max_depth) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  if (processed) *processed = h->processed;
+  if (pivots) *pivots = h->pivots;
+  if (depth_overflow) *depth_overflow = h->depth_overflow;
+  if (max_depth) *max_depth = h->max_depth;
   return LPR_OK;
 }
 
@@ -1010,7 +1107,7 @@ int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound
   int *d_key = nullptr, *d_order = nullptr;
   BBAddc* d_jb = nullptr;
   cudaError_t e = cudaMalloc(&d_key, sizeof(int) * parent->C);
-  if (e == cudaSuccess) e = cudaMalloc(&d_order, sizeof(int) * parent->C);
+  if (e == cudaSuccess) e = cudaMalloc(&d_order, sizeof(int) * 2 * (size_t)parent->C);
   if (e == cudaSuccess) e = cudaMalloc(&d_jb, sizeof(BBAddc));
   if (e != cudaSuccess) {
     cudaFree(d_key); cudaFree(d_order); cudaFree(d_jb);

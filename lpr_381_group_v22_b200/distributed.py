@@ -56,6 +56,11 @@ class BBPool:
         self.pivots += piv.value
         return done.value
 
+    def stats(self):
+        done, piv, ovf, md = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        N.check(N.lib().lpr_bb_stats(self._h, C.byref(done), C.byref(piv), C.byref(ovf), C.byref(md)))
+        return dict(processed=done.value, pivots=piv.value, depth_overflow=ovf.value, max_depth=md.value)
+
     def get_incumbent(self):
         has, z, klen = C.c_int(), C.c_double(), C.c_int(0)
         x = np.zeros(self.n_vars)
@@ -228,16 +233,35 @@ def exchange_incumbent(pool, comm, payload_len):
     return best
 
 
-def steal_plan(counts, min_keep=2):
-    """deterministic (donor, receiver, n) plan computed identically on every rank: ranks with no open
-    nodes receive half of the pool of the currently fullest rank."""
+def warmup_comm(dist, device):
+    """NCCL sets up its point-to-point channels lazily (tens of ms per pair): touch every pair once,
+    outside any timed region, so that the first steal does not pay for it."""
+    if dist is None:
+        return
+    comm = _Comm(dist, device)
+    comm.allreduce_max(0.0)
+    token = np.zeros(8, dtype=np.uint8)
+    for a in range(comm.world):          # every unordered pair once, lower rank sends first
+        for b in range(a + 1, comm.world):
+            if comm.rank == a:
+                comm.send_bytes(token, b)
+                comm.recv_bytes(8, b)
+            elif comm.rank == b:
+                comm.recv_bytes(8, a)
+                comm.send_bytes(token, a)
+    dist.barrier()
+
+
+def steal_plan(counts, min_keep=2, low_water=0):
+    """deterministic (donor, receiver, n) plan computed identically on every rank: ranks whose pool is
+    empty (or at most `low_water`) receive half of the pool of the currently fullest rank."""
     counts = list(counts)
     plan = []
-    receivers = [r for r, c in enumerate(counts) if c == 0]
+    receivers = [r for r, c in enumerate(counts) if c <= low_water]
     for r in receivers:
         donor = max(range(len(counts)), key=lambda q: (counts[q], -q))
         give = counts[donor] // 2
-        if counts[donor] < min_keep or give < 1:
+        if donor == r or counts[donor] < min_keep or give < 1 or counts[donor] <= 2 * max(1, low_water):
             continue
         plan.append((donor, r, give))
         counts[donor] -= give
@@ -246,7 +270,7 @@ def steal_plan(counts, min_keep=2):
 
 
 def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len=None, max_rounds=1 << 30,
-                    seed_nodes_per_rank=8):
+                    seed_nodes_per_rank=8, low_water=0):
     """Drive `pool` (rank-local) to completion together with the other ranks.  Returns a dict with the
     incumbent (identical on every rank), node counts and exchange statistics."""
     comm = _Comm(dist, device)
@@ -265,7 +289,7 @@ def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len
         counts = [v[0] for v in comm.allgather_ints([pool.open_count()])]
         if sum(counts) == 0:
             break
-        for donor, recv, give in steal_plan(counts):
+        for donor, recv, give in steal_plan(counts, low_water=low_water):
             if rank == donor:
                 data, n = pool.export_nodes(give)
                 hdr = np.array([data.size], dtype=np.int64).view(np.uint8)
