@@ -47,6 +47,9 @@ def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk):
     """LP relaxation with the tableau solver, then branch & bound simplex with reference semantics
     (4-d.p. rounding, dual-then-primal node solves), node cap lifted to `max_nodes` per rank-round budget,
     pruning on; the pool is partitioned across the ranks."""
+    import os
+    os.environ.setdefault("LPR_BB_PREALLOC_MB", "81920")  # node slabs carved before the timed region
+    os.environ.setdefault("LPR_BB_MAX_DEPTH", "192")       # deep enough for the node budgets used here
     comm = _Comm(dist, f"cuda:{device}")
     A, b, c = gen_dense_ip(seed, m, n)
     coef = N.f64(A); rhs = N.f64(b); obj = N.f64(c)

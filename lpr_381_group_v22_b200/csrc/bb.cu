@@ -853,14 +853,15 @@ static int bb_push_host_node(lpr_bb* h, int R, int C, int depth, const uint8_t* 
   BBNode nd;
   int rc = bb_take_slab(h, &nd.slab);
   if (rc) return rc;
-  LPR_CUDA(cudaMemsetAsync(nd.slab, 0, sizeof(double) * h->slab_doubles, h->stream));
+  // `dense` may live on the host or on the device (cudaMemcpyDefault); padding columns are zeroed
+  if (h->ldmax > C)
+    LPR_CUDA(cudaMemset2DAsync(nd.slab + C, sizeof(double) * h->ldmax, 0, sizeof(double) * (h->ldmax - C), R, h->stream));
   LPR_CUDA(cudaMemcpy2DAsync(nd.slab, sizeof(double) * h->ldmax, dense, sizeof(double) * C, sizeof(double) * C, R,
-                             cudaMemcpyHostToDevice, h->stream));
+                             cudaMemcpyDefault, h->stream));
   if (round) {
     k_round4<<<h->sms * 2, 256, 0, h->stream>>>(nd.slab, (size_t)R * h->ldmax);  // :1021
     LPR_LAUNCH_CHECK();
   }
-  LPR_CUDA(cudaStreamSynchronize(h->stream));
   nd.R = R;
   nd.C = C;
   nd.depth = depth;
@@ -876,6 +877,7 @@ int lpr_bb_create(int device, int rows, int cols, const double* root_tableau, in
   if (rc) return rc;
   if (root_tableau) {
     rc = bb_push_host_node(h, rows, cols, 0, nullptr, 0, root_tableau, true);
+    if (rc == LPR_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(LPR_E_CUDA, "root upload failed");
     if (rc) {
       lpr_bb_destroy(h);
       return rc;
@@ -946,12 +948,14 @@ int lpr_bb_export_nodes(lpr_bb* h, int max_nodes, void* buf, int64_t buf_cap, in
     const int64_t kl = (int64_t)nd.key.size(), kpad = (kl + 7) / 8 * 8;
     const int64_t need = 16 + kpad + (int64_t)sizeof(double) * nd.R * nd.C;
     if (used + need > buf_cap) break;
+    std::vector<char> head(16 + kpad, 0);
     int32_t hdr[4] = {nd.R, nd.C, nd.depth, (int32_t)kl};
-    memcpy(p + used, hdr, 16);
-    memset(p + used + 16, 0, kpad);
-    if (kl) memcpy(p + used + 16, nd.key.data(), kl);
+    memcpy(head.data(), hdr, 16);
+    if (kl) memcpy(head.data() + 16, nd.key.data(), kl);
+    // cudaMemcpyDefault: buf may be pageable/pinned host memory or device memory (NCCL staging tensor)
+    LPR_CUDA(cudaMemcpy(p + used, head.data(), head.size(), cudaMemcpyDefault));
     LPR_CUDA(cudaMemcpy2D(p + used + 16 + kpad, sizeof(double) * nd.C, nd.slab, sizeof(double) * h->ldmax,
-                          sizeof(double) * nd.C, nd.R, cudaMemcpyDeviceToHost));
+                          sizeof(double) * nd.C, nd.R, cudaMemcpyDefault));
     used += need;
     bb_give_slab(h, nd.slab);
     h->open.erase(h->open.begin());
@@ -968,18 +972,20 @@ int lpr_bb_import_nodes(lpr_bb* h, const void* buf, int64_t bytes) {
   if (rc) return rc;
   const char* p = (const char*)buf;
   int64_t off = 0;
-  std::vector<BBNode> incoming;
+  std::vector<uint8_t> keybuf;
   while (off + 16 <= bytes) {
     int32_t hdr[4];
-    memcpy(hdr, p + off, 16);
+    LPR_CUDA(cudaMemcpy(hdr, p + off, 16, cudaMemcpyDefault));
     const int64_t kl = hdr[3], kpad = (kl + 7) / 8 * 8;
     const int64_t need = 16 + kpad + (int64_t)sizeof(double) * hdr[0] * hdr[1];
-    if (off + need > bytes) return fail(LPR_E_BADARG, "truncated node record");
-    rc = bb_push_host_node(h, hdr[0], hdr[1], hdr[2], (const uint8_t*)(p + off + 16), (int)kl,
-                           (const double*)(p + off + 16 + kpad), false);
+    if (kl < 0 || off + need > bytes) return fail(LPR_E_BADARG, "truncated node record");
+    keybuf.resize((size_t)kpad + 8);
+    if (kpad) LPR_CUDA(cudaMemcpy(keybuf.data(), p + off + 16, kpad, cudaMemcpyDefault));
+    rc = bb_push_host_node(h, hdr[0], hdr[1], hdr[2], keybuf.data(), (int)kl, (const double*)(p + off + 16 + kpad), false);
     if (rc) return rc;
     off += need;
   }
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
   // keep the stack sorted so that back() is the DFS-first open node
   std::stable_sort(h->open.begin(), h->open.end(),
                    [](const BBNode& a, const BBNode& b) { return key_cmp(a.key, b.key) > 0; });

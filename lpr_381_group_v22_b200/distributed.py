@@ -24,6 +24,25 @@ from . import _native as N
 # ------------------------------------------------------------------------------------------------
 # pools (thin wrappers over the C ABI)
 # ------------------------------------------------------------------------------------------------
+def _alloc_bytes(cap, torch_device):
+    """byte buffer for node records: a CUDA tensor when the records travel over NCCL (the library copies
+    device-to-device into it, so stolen nodes never touch host memory), a numpy array otherwise."""
+    if torch_device is not None and str(torch_device) != "cpu":
+        import torch
+        t = torch.empty(cap, dtype=torch.uint8, device=torch_device)
+        return t, C.c_void_p(t.data_ptr())
+    a = np.empty(cap, dtype=np.uint8)
+    return a, a.ctypes.data_as(N.vp)
+
+
+def _bytes_ptr(data):
+    if hasattr(data, "data_ptr"):  # torch tensor (host or device)
+        data = data.contiguous()
+        return C.c_void_p(data.data_ptr()), int(data.numel())
+    a = np.ascontiguousarray(data, dtype=np.uint8)
+    _bytes_ptr.keep = a
+    return a.ctypes.data_as(N.vp), int(a.size)
+
 class BBPool:
     """Open-node pool of the branch & bound simplex solver (lpr_bb_*)."""
 
@@ -77,18 +96,19 @@ class BBPool:
         x = N.f64(payload)
         N.check(N.lib().lpr_bb_set_incumbent(self._h, float(value), N.pd(x), N.pi(k) if k is not None else None, len(key)))
 
-    def export_nodes(self, max_nodes):
-        per = 16 + 136 + 8 * (self.rows + 128) * (self.cols + 128)  # header + key + deepest possible tableau
+    def export_nodes(self, max_nodes, torch_device=None):
+        md = self.stats()["max_depth"]
+        per = 16 + md + 16 + 8 * (self.rows + md) * (self.cols + md)  # header + key + deepest possible tableau
         cap = int(per) * max(1, max_nodes)
-        buf = np.empty(cap, dtype=np.uint8)
+        buf, ptr = _alloc_bytes(cap, torch_device)
         nbytes, n = C.c_int64(), C.c_int()
-        N.check(N.lib().lpr_bb_export_nodes(self._h, max_nodes, buf.ctypes.data_as(N.vp), cap, C.byref(nbytes), C.byref(n)))
-        return buf[:nbytes.value].copy(), n.value
+        N.check(N.lib().lpr_bb_export_nodes(self._h, max_nodes, ptr, cap, C.byref(nbytes), C.byref(n)))
+        return buf[:nbytes.value], n.value
 
     def import_nodes(self, data):
-        data = np.ascontiguousarray(data, dtype=np.uint8)
-        if data.size:
-            N.check(N.lib().lpr_bb_import_nodes(self._h, data.ctypes.data_as(N.vp), data.size))
+        ptr, size = _bytes_ptr(data)
+        if size:
+            N.check(N.lib().lpr_bb_import_nodes(self._h, ptr, size))
 
 
 class KnapPool:
@@ -140,17 +160,17 @@ class KnapPool:
         N.check(N.lib().lpr_knap_set_incumbent(self._h, float(value), ch.ctypes.data_as(N.bp),
                                                words.ctypes.data_as(N.u64p), len(key)))
 
-    def export_nodes(self, max_nodes):
+    def export_nodes(self, max_nodes, torch_device=None):
         cap = self.rec_bytes * max(1, max_nodes)
-        buf = np.empty(cap, dtype=np.uint8)
+        buf, ptr = _alloc_bytes(cap, torch_device)
         nbytes, n = C.c_int64(), C.c_int()
-        N.check(N.lib().lpr_knap_export_nodes(self._h, max_nodes, buf.ctypes.data_as(N.vp), cap, C.byref(nbytes), C.byref(n)))
-        return buf[:nbytes.value].copy(), n.value
+        N.check(N.lib().lpr_knap_export_nodes(self._h, max_nodes, ptr, cap, C.byref(nbytes), C.byref(n)))
+        return buf[:nbytes.value], n.value
 
     def import_nodes(self, data):
-        data = np.ascontiguousarray(data, dtype=np.uint8)
-        if data.size:
-            N.check(N.lib().lpr_knap_import_nodes(self._h, data.ctypes.data_as(N.vp), data.size))
+        ptr, size = _bytes_ptr(data)
+        if size:
+            N.check(N.lib().lpr_knap_import_nodes(self._h, ptr, size))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,12 +221,22 @@ class _Comm:
         return t.cpu().numpy()
 
     def send_bytes(self, data, dst):
-        t = self.torch.from_numpy(np.ascontiguousarray(data, dtype=np.uint8)).to(self.dev)
+        if hasattr(data, "data_ptr"):
+            t = data.contiguous()
+        else:
+            t = self.torch.from_numpy(np.ascontiguousarray(data, dtype=np.uint8)).to(self.dev)
         self.dist.send(t, dst=dst)
+        if self.dev != "cpu":
+            self.torch.cuda.current_stream(t.device).synchronize()  # keep `t` alive until NCCL has read it
 
-    def recv_bytes(self, nbytes, src):
+    def recv_bytes(self, nbytes, src, keep_on_device=False):
         t = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.dev)
         self.dist.recv(t, src=src)
+        if keep_on_device and self.dev != "cpu":
+            # NCCL recv only enqueues: the library reads this buffer from its own stream, so the bytes
+            # must have landed before the pointer is handed over
+            self.torch.cuda.current_stream(t.device).synchronize()
+            return t
         return t.cpu().numpy()
 
 
@@ -291,17 +321,21 @@ def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len
             break
         for donor, recv, give in steal_plan(counts, low_water=low_water):
             if rank == donor:
-                data, n = pool.export_nodes(give)
-                hdr = np.array([data.size], dtype=np.int64).view(np.uint8)
+                try:
+                    data, n = pool.export_nodes(give, comm.dev)  # device staging when the pool supports it
+                except TypeError:
+                    data, n = pool.export_nodes(give)
+                size = int(data.numel()) if hasattr(data, "numel") else int(data.size)
+                hdr = np.array([size], dtype=np.int64).view(np.uint8)
                 comm.send_bytes(hdr, recv)
-                if data.size:
+                if size:
                     comm.send_bytes(data, recv)
                 steals += 1
                 moved += n
             elif rank == recv:
                 nbytes = int(comm.recv_bytes(8, donor).view(np.int64)[0])
                 if nbytes:
-                    pool.import_nodes(comm.recv_bytes(nbytes, donor))
+                    pool.import_nodes(comm.recv_bytes(nbytes, donor, keep_on_device=True))
         if pool.open_count() > 0:
             processed += pool.run(chunk_nodes)
         exchange_incumbent(pool, comm, payload_len)
