@@ -104,4 +104,5 @@ def run_knap_cfg4(n_items, seed, device, dist, max_nodes, chunk):
                 node_record_bytes=rec_bytes, record_gbs=3.0 * rec_bytes * res["nodes_total"] / dt / 1e9,
                 best_value=(inc[0] if inc else None), items_chosen=(int(np.count_nonzero(inc[2])) if inc else None),
                 weight_used=(float(np.dot(inc[2], w)) if inc else None), open_left=left, steals=res["steals"],
-                nodes_moved=res["nodes_moved"], rounds=res["rounds"], finished=(left == 0))
+                nodes_moved=res["nodes_moved"], rounds=res["rounds"], finished=(left == 0),
+                phase_seconds_rank0=res["seconds_rank0"])

@@ -303,9 +303,12 @@ def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len
                     seed_nodes_per_rank=8, low_water=0):
     """Drive `pool` (rank-local) to completion together with the other ranks.  Returns a dict with the
     incumbent (identical on every rank), node counts and exchange statistics."""
+    import time
     comm = _Comm(dist, device)
     rank, world = comm.rank, comm.world
     processed, rounds, steals, moved = 0, 0, 0, 0
+    t_seed = t_steal = t_run = t_inc = 0.0
+    t_a = time.perf_counter()
     if payload_len is None:
         payload_len = getattr(pool, "n_vars", None) or getattr(pool, "n")
     # seeding: rank 0 owns the root; expand it a little so that the first steal round has work to share
@@ -314,8 +317,10 @@ def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len
         while 0 < pool.open_count() < seed_nodes_per_rank * world and guard < 64:
             processed += pool.run(max(1, seed_nodes_per_rank))
             guard += 1
+    t_seed = time.perf_counter() - t_a
     while rounds < max_rounds:
         rounds += 1
+        t_b = time.perf_counter()
         counts = [v[0] for v in comm.allgather_ints([pool.open_count()])]
         if sum(counts) == 0:
             break
@@ -336,11 +341,18 @@ def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len
                 nbytes = int(comm.recv_bytes(8, donor).view(np.int64)[0])
                 if nbytes:
                     pool.import_nodes(comm.recv_bytes(nbytes, donor, keep_on_device=True))
+        t_c = time.perf_counter()
         if pool.open_count() > 0:
             processed += pool.run(chunk_nodes)
+        t_d = time.perf_counter()
         exchange_incumbent(pool, comm, payload_len)
+        t_e = time.perf_counter()
+        t_steal += t_c - t_b
+        t_run += t_d - t_c
+        t_inc += t_e - t_d
     best = exchange_incumbent(pool, comm, payload_len) if world > 1 else pool.get_incumbent()
     totals = comm.allgather_ints([processed, steals, moved])
     return dict(incumbent=best, nodes_local=processed, nodes_total=sum(t[0] for t in totals),
                 steals=sum(t[1] for t in totals), nodes_moved=sum(t[2] for t in totals), rounds=rounds,
-                world=world, rank=rank)
+                world=world, rank=rank,
+                seconds_rank0=dict(seed=t_seed, steal_and_counts=t_steal, run=t_run, incumbent_exchange=t_inc))

@@ -286,3 +286,72 @@ def test_full_size_window_cfg2():
         for i in (0, 1, m // 2, m - 1):
             col = got[:, basis[i]]
             assert col[i + 1] == 1.0 and np.count_nonzero(col) == 1
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_sensitivity_resolve_rule(seed):
+    """SensitivityAnalyzer.ResolveAll (dual phase then primal re-optimisation, SensitivityAnalyzer.cs:121-201):
+    perturb the RHS / objective of an optimal tableau and re-solve on the device."""
+    m, n = 6 + seed, 9 + seed
+    A, b, c = O.gen_dense_lp(50 + seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    opt = O.primal_solve(T0, b0)
+    T = opt["T"].copy()
+    rng = np.random.default_rng(seed)
+    T[1 + rng.integers(0, m), -1] -= 5.0 * (1 + seed)        # RHS change => dual simplex needed
+    nb = [j for j in range(n + m) if j not in opt["basis"].tolist()]
+    T[0, nb[seed % len(nb)]] = -0.75                           # a reduced cost turns negative => primal phase
+    ref = O.sens_resolve(T, opt["basis"])
+    with L.DeviceTableau.from_host(T) as t:
+        t.basis = opt["basis"]
+        r = t.solve(L.RULE_SENS, max_pivots=10000)
+        assert r["status"] == ref["status"]
+        assert r["log"].tolist() == ref["log"].tolist()
+        assert t.basis.tolist() == ref["basis"].tolist()
+        assert_bit_equal(t.read(), ref["T"])
+
+
+def test_edge_shapes_and_errors():
+    # smallest legal tableau, single constraint / single variable
+    T = np.array([[-1.0, 0.0, 0.0], [2.0, 1.0, 4.0]])
+    ref = O.primal_solve(T)
+    with L.DeviceTableau.from_host(T) as t:
+        r = t.solve(L.RULE_PRIMAL)
+        assert r["log"].tolist() == ref["log"].tolist() == [[1, 0]]
+        assert_bit_equal(t.read(), ref["T"])
+        assert t.objective() == 2.0
+    # already optimal: zero pivots
+    T = np.array([[1.0, 2.0, 0.0, 0.0], [1.0, 1.0, 1.0, 3.0]])
+    with L.DeviceTableau.from_host(T) as t:
+        r = t.solve(L.RULE_PRIMAL)
+        assert r["status"] == L.OPTIMAL and r["n_pivots"] == 0
+        assert_bit_equal(t.read(), T)
+    # ragged width that is not a multiple of anything, rows > 256*16 are covered by the cfg2 test
+    rng = np.random.default_rng(1)
+    for (R, Cc) in ((2, 2), (3, 17), (5, 257), (40, 513)):
+        T = rng.normal(size=(R, Cc))
+        ref = T.copy()
+        O.lib().orc_primal_pivot(R, Cc, ref.ctypes.data_as(O._dp), R - 1, Cc // 2, 1)
+        with L.DeviceTableau.from_host(T) as t:
+            t.pivot_at(R - 1, Cc // 2)
+            assert_bit_equal(t.read(), ref)
+    with pytest.raises(L.LprError):
+        L.DeviceTableau.from_host(np.zeros((1, 1)))
+    with pytest.raises(L.LprError):
+        with L.DeviceTableau.from_host(np.zeros((2, 3))) as t:
+            t.pivot_at(5, 0)
+    with pytest.raises(L.LprError):
+        with L.DeviceTableau.from_host(np.zeros((2, 3))) as t:
+            t.append_row(np.zeros(3))  # no headroom
+
+
+def test_nan_and_inf_do_not_hang():
+    T = np.array([[-1.0, -2.0, 0.0, 0.0], [np.nan, 1.0, 1.0, 4.0], [1.0, np.inf, 0.0, 2.0]])
+    ref = O.primal_solve(T, max_pivots=10)
+    with L.DeviceTableau.from_host(T) as t:
+        r = t.solve(L.RULE_PRIMAL, max_pivots=10)
+        assert r["status"] == ref["status"] and r["log"].tolist() == ref["log"].tolist()
+        got = t.read()
+        assert np.array_equal(np.isnan(got), np.isnan(ref["T"]))
+        mask = ~np.isnan(got)
+        assert np.array_equal(got[mask], ref["T"][mask])
