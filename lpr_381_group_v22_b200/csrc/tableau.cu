@@ -692,11 +692,15 @@ static int sweep_grid(const lpr_tab* h) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_sweep<0, false, true, 8>, kSweepThreads, 0);
     resident = std::max(1, r);
   }
-  static const int waves = std::max(1, env_int("LPR_SWEEP_WAVES", 4));
+  // measured on B200 (tools/tab_bench.py): one tile per CTA with 4 loads in flight per thread is the
+  // fastest shape (123 us/pivot); LPR_SWEEP_WAVES / LPR_SWEEP_CTAS_PER_SM select a persistent grid instead
+  static const int waves = std::max(0, env_int("LPR_SWEEP_WAVES", 0));
   static const int per_sm_env = env_int("LPR_SWEEP_CTAS_PER_SM", 0);
-  const int per_sm = per_sm_env > 0 ? per_sm_env : resident * waves;
+  const int per_sm = per_sm_env > 0 ? per_sm_env : (waves > 0 ? resident * waves : (1 << 20));
+  static const int unroll_env = env_int("LPR_SWEEP_UNROLL", 4);
+  const int unroll = (unroll_env == 4 || unroll_env == 16) ? unroll_env : 8;
   const long long chunks = (long long)h->R * (h->ld / 2);
-  const long long tiles = (chunks + kSweepThreads * 8 - 1) / (kSweepThreads * 8);
+  const long long tiles = (chunks + kSweepThreads * unroll - 1) / (kSweepThreads * unroll);
   long long g = (long long)h->sms * per_sm;
   g = std::max<long long>(1, std::min(g, tiles));
   return (int)g;
@@ -723,7 +727,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
 static int launch_sweep(lpr_tab* h, int skip, double eps, bool emit, int reverse) {
   const int g = sweep_grid(h);
   TabView v = h->view();
-  static const int unroll = env_int("LPR_SWEEP_UNROLL", 8);
+  static const int unroll = env_int("LPR_SWEEP_UNROLL", 4);
   if (emit && unroll == 4)
     launch_pdl(k_sweep<0, false, true, 4>, g, kSweepThreads, h->stream, v, eps, reverse);
   else if (emit && unroll == 16)

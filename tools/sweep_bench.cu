@@ -79,6 +79,40 @@ __global__ void __launch_bounds__(256) k_v1m(double* T, int ld, int R, const dou
     for (int k = 0; k < U; k++) { unsigned long long q = q0 + k * 256; if (q < n) { double fv = __ldg(f + rw[k]); double2 pr = __ldg(p2 + cc[k]); double2 y; y.x = __dsub_rn(x[k].x, __dmul_rn(fv, pr.x)); y.y = __dsub_rn(x[k].y, __dmul_rn(fv, pr.y)); T2[q] = y; } }
   }
 }
+// ---- V1h: V1m with cache hints.  MODE 1: tableau loads bypass L1 (ld.global.L1::no_allocate) so prow/f stay
+// L1 resident.  MODE 2: additionally L2 eviction policies: tiles written in the last `keep` fraction of the
+// sweep get evict_last (they are the first ones the next, mirrored sweep reads), the others evict_first.
+__device__ __forceinline__ double2 ld_na(const double2* p) {
+  double2 r; asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p)); return r;
+}
+__device__ __forceinline__ double2 ld_pol(const double2* p, unsigned long long pol) {
+  double2 r; asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol)); return r;
+}
+__device__ __forceinline__ void st_pol(double2* p, double2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" :: "l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+template <int U, int MODE>
+__global__ void __launch_bounds__(256) k_v1h(double* T, int ld, int R, const double* __restrict__ f, const double* __restrict__ p, int rev, float keep) {
+  const unsigned ldv = ld >> 1; const unsigned long long n = (unsigned long long)R * ldv;
+  double2* T2 = (double2*)T; const double2* p2 = (const double2*)p;
+  const unsigned TILE = 256 * U; const unsigned long long nt = (n + TILE - 1) / TILE;
+  unsigned long long t0 = nt * blockIdx.x / gridDim.x, t1 = nt * (blockIdx.x + 1) / gridDim.x;
+  unsigned long long pol_first, pol_last;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+  for (unsigned long long tt = t0; tt < t1; tt++) {
+    unsigned long long t = rev ? nt - 1 - tt : tt; unsigned long long q0 = t * TILE + threadIdx.x;
+    // position of this tile in sweep order (0 = first processed, 1 = last)
+    const bool late = (double)tt >= (1.0 - keep) * (double)nt;
+    unsigned row = (unsigned)(q0 / ldv), c = (unsigned)(q0 - (unsigned long long)row * ldv);
+    double2 x[U]; unsigned rw[U], cc[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) { unsigned long long q = q0 + k * 256; rw[k] = row; cc[k] = c; if (q < n) x[k] = (MODE == 2) ? ld_pol(T2 + q, pol_first) : ld_na(T2 + q); c += 256; while (c >= ldv) { c -= ldv; row++; } }
+#pragma unroll
+    for (int k = 0; k < U; k++) { unsigned long long q = q0 + k * 256; if (q < n) { double fv = __ldg(f + rw[k]); double2 pr = __ldg(p2 + cc[k]); double2 y; y.x = __dsub_rn(x[k].x, __dmul_rn(fv, pr.x)); y.y = __dsub_rn(x[k].y, __dmul_rn(fv, pr.y));
+      if (MODE == 2) st_pol(T2 + q, y, late ? pol_last : pol_first); else T2[q] = y; } }
+  }
+}
 // ---- V2: row-major units: CTA takes (row, colgroup) units with colgroup fastest; p from L1 ----
 template <int U>
 __global__ void __launch_bounds__(256) k_v2(double* T, int ld, int R, const double* __restrict__ f, const double* __restrict__ p) {
@@ -158,6 +192,10 @@ int main(int argc, char** argv) {
     snprintf(nm, 64, "V1m U8 fwd %d/SM", per); rep(nm, timeit([&] { k_v1m<8><<<g, 256>>>(T, ld, R, f, p, 0); }, reps));
     snprintf(nm, 64, "V1m U8 alternate-mirror %d/SM", per); rep(nm, timeit([&] { k_v1m<8><<<g, 256>>>(T, ld, R, f, p, flip); flip ^= 1; }, reps));
     snprintf(nm, 64, "V1m U4 alternate-mirror %d/SM", per); rep(nm, timeit([&] { k_v1m<4><<<g, 256>>>(T, ld, R, f, p, flip); flip ^= 1; }, reps)); }
+  for (int per : {8, 16, 24}) { char nm[64]; int g = sms * per; int flip = 0;
+    snprintf(nm, 64, "V1h U8 noL1 alt-mirror %d/SM", per); rep(nm, timeit([&] { k_v1h<8, 1><<<g, 256>>>(T, ld, R, f, p, flip, 0.f); flip ^= 1; }, reps));
+    for (float keep : {0.15f, 0.25f, 0.35f}) { snprintf(nm, 64, "V1h U8 L2pol keep=%.2f %d/SM", keep, per); rep(nm, timeit([&] { k_v1h<8, 2><<<g, 256>>>(T, ld, R, f, p, flip, keep); flip ^= 1; }, reps)); }
+    snprintf(nm, 64, "V1h U4 noL1 alt-mirror %d/SM", per); rep(nm, timeit([&] { k_v1h<4, 1><<<g, 256>>>(T, ld, R, f, p, flip, 0.f); flip ^= 1; }, reps)); }
   for (int per : {12}) { char nm[64]; int g = sms * per;
     snprintf(nm, 64, "V3 colfixed32B U4 %d/SM", per); rep(nm, timeit([&] { k_v3<4><<<g, 128>>>(T, ld64, R, f, p); }, reps));
     snprintf(nm, 64, "V3 colfixed32B U8 %d/SM", per); rep(nm, timeit([&] { k_v3<8><<<g, 128>>>(T, ld64, R, f, p); }, reps)); }
