@@ -768,12 +768,23 @@ static int launch_select(lpr_tab* h, int rule, int flags, int* mask) {
   return LPR_OK;
 }
 
+int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_t* n_pivots, int* pivot_log,
+                      int64_t log_cap, bool time_sweeps);
+
 int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
                        int64_t* n_pivots, int* pivot_log, int64_t log_cap) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
   if (rule < 0 || rule > LPR_RULE_SENS) return fail(LPR_E_BADARG, "unknown rule %d", rule);
   int rc = select_device(h->device);
   if (rc) return rc;
+  {
+    // delayed-update path: K pivots per tableau sweep (tableau_blocked.cu); flags bit4 or
+    // LPR_TAB_BLOCK<=1 keep one sweep per pivot
+    static const int blk = env_int("LPR_TAB_BLOCK", 8);
+    static const int fused_on = env_int("LPR_TAB_FUSED", 1);
+    if (rule == LPR_RULE_PRIMAL && fused_on && blk > 1 && !(flags & (4 | 16)) && (max_pivots < 0 || max_pivots > 1))
+      return tab_solve_blocked(h, blk, max_pivots, status, n_pivots, pivot_log, log_cap, (flags & 8) != 0);
+  }
   static const int fused_default = env_int("LPR_TAB_FUSED", 1);
   static const int batch = std::max(1, env_int("LPR_TAB_BATCH", 32));
   static const int serp = env_int("LPR_TAB_SERPENTINE", 1);
@@ -926,6 +937,12 @@ int lpr_tab_destroy(lpr_tab* h) {
   cudaFree(h->st);
   cudaFree(h->selcand);
   cudaFree(h->ticket);
+  cudaFree(h->blk_pr);
+  cudaFree(h->blk_f);
+  cudaFree(h->blk_row0);
+  cudaFree(h->blk_rhs[0]);
+  cudaFree(h->blk_rhs[1]);
+  cudaFree(h->blk_p);
   cudaFree(h->log);
   if (h->st_host) cudaFreeHost(h->st_host);
   if (h->ev0) cudaEventDestroy(h->ev0);

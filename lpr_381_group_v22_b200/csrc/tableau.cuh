@@ -18,6 +18,7 @@ struct TabState {
   int dropped;     // B&B: the last tableau was dropped (:392-400)
   long long npiv;
   long long max_piv;
+  long long group_base;  // blocked path: npiv at the start of the current group of delayed pivots
   double pivot;
 };
 
@@ -49,6 +50,13 @@ struct lpr_tab {
   int* basis = nullptr;
   lpr::TabState* st = nullptr;
   lpr::TabState* st_host = nullptr;  // pinned mirror
+  // blocked (delayed-update) primal path: K pending rank-1 updates applied by one sweep
+  int blk_k = 0;
+  double* blk_pr = nullptr;    // K x ld   normalised pivot rows of the pending pivots
+  double* blk_f = nullptr;     // K x Rcap pre-update factor columns of the pending pivots
+  double* blk_row0 = nullptr;  // ld       mirror of the objective row (always current)
+  double* blk_rhs[2] = {nullptr, nullptr};  // Rcap mirror of the RHS column, double buffered
+  int* blk_p = nullptr;        // K        pivot rows of the pending pivots
   lpr::MinIdx* selcand = nullptr;    // per-CTA entering candidates of the multi-CTA select
   unsigned* ticket = nullptr;        // "last CTA done" counter
   int* log = nullptr;

@@ -121,11 +121,12 @@ class DeviceTableau:
         N.check(N.lib().lpr_tab_set_basis(self._h, N.pi(b)))
 
     # ---- solving ----------------------------------------------------------------------------
-    def solve(self, rule=N.RULE_PRIMAL, max_pivots=-1, print_steps=False, log_cap=1 << 16, fused=True):
+    def solve(self, rule=N.RULE_PRIMAL, max_pivots=-1, print_steps=False, log_cap=1 << 16, fused=True, blocked=True,
+              time_sweeps=False):
         st = C.c_int()
         npv = C.c_int64()
         log = np.zeros((max(1, log_cap), 2), dtype=np.int32)
-        flags = (1 if print_steps else 0) | (0 if fused else 4)
+        flags = (1 if print_steps else 0) | (0 if fused else 4) | (0 if blocked else 16) | (8 if time_sweeps else 0)
         N.check(N.lib().lpr_tab_solve(self._h, rule, max_pivots, flags, C.byref(st), C.byref(npv),
                                       N.pi(log) if log_cap > 0 else None, log_cap))
         return dict(status=st.value, n_pivots=npv.value, log=log[:min(npv.value, log_cap)].copy())

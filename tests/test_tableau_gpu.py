@@ -355,3 +355,33 @@ def test_nan_and_inf_do_not_hang():
         assert np.array_equal(np.isnan(got), np.isnan(ref["T"]))
         mask = ~np.isnan(got)
         assert np.array_equal(got[mask], ref["T"][mask])
+
+
+@pytest.mark.parametrize("m,n,seed", [(8, 16, 1), (33, 70, 2), (100, 37, 4), (255, 513, 5), (300, 300, 6)])
+@pytest.mark.parametrize("block", [2, 3, 8, 16])
+def test_blocked_delayed_update_is_bit_identical(m, n, seed, block, monkeypatch):
+    """K pending pivots applied by one sweep (tableau_blocked.cu) == one sweep per pivot == the oracle."""
+    import subprocess, sys, os, json
+    # LPR_TAB_BLOCK is read once per process: run the comparison in a child process
+    code = f"""
+import sys, json, numpy as np
+sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r}); sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import oracle_lib as O, lpr_381_group_v22_b200 as L
+A, b, c = O.gen_dense_lp({seed}, {m}, {n})
+T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range({m})])
+out = {{}}
+for cap in (-1, 7, 17):
+    ref = O.primal_solve(T0, b0, max_pivots=cap)
+    with L.DeviceTableau.from_host(T0) as t:
+        r = t.solve(L.RULE_PRIMAL, max_pivots=cap)
+        ok = (r["status"] == ref["status"] and r["n_pivots"] == ref["n_pivots"] and r["log"].tolist() == ref["log"].tolist()
+              and t.basis.tolist() == ref["basis"].tolist()
+              and np.array_equal(t.read().view(np.uint64), ref["T"].view(np.uint64)))
+        out[str(cap)] = bool(ok)
+print(json.dumps(out))
+"""
+    env = dict(os.environ, LPR_TAB_BLOCK=str(block))
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out == {"-1": True, "7": True, "17": True}, out
