@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(256) k_blk_select2(BlkView b, int group_pos, R
 // applies the s = npiv - group_base pending pivots to the whole tableau, once.  Thread owns one 16-byte
 // column chunk (its pending pivot-row values live in registers) and walks down rows; the KM factors of
 // the CTA's rows are staged once in shared memory and broadcast from there.
-constexpr int kBlkRowsMax = 256;  // rows per work item (shared-memory stage: 256 x KM doubles)
+// rows per work item RB (shared-memory stage: RB x KM doubles): small items keep the tail wave short
 
 // fast path: a full group (s == KM) on a row that is not one of the pending pivot rows -- 2 DMUL + 2 DADD
 // per pending pivot and chunk, nothing else
@@ -468,10 +468,10 @@ __device__ __forceinline__ double2 blk_apply_gen(double2 x, const double2* pr, c
   return x;
 }
 
-template <int UNROLL, int KM>
+template <int UNROLL, int KM, int kBlkRowsMax>
 __global__ void __launch_bounds__(kSweepThreads) k_blk_sweep(BlkView b) {
   __shared__ __align__(16) double sF[kBlkRowsMax * KM];
-  __shared__ unsigned sPiv[kBlkRowsMax / 32];
+  __shared__ unsigned sPiv[(kBlkRowsMax + 31) / 32];
   pdl_wait_then_release();
   const TabView& v = b.v;
   const TabState* st = v.st;
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_blk_sweep(BlkView b) {
     const int cg = it / nrb, rb = it - cg * nrb;
     const int r0 = rb * kBlkRowsMax, r1 = min(R, r0 + kBlkRowsMax);
     __syncthreads();
-    if (threadIdx.x < kBlkRowsMax / 32) sPiv[threadIdx.x] = full ? 0u : 0xffffffffu;  // partial group: slow path
+    if (threadIdx.x < (kBlkRowsMax + 31) / 32) sPiv[threadIdx.x] = full ? 0u : 0xffffffffu;  // partial group: slow path
     __syncthreads();
     if (full && threadIdx.x < KM) {
       const int q = pu[threadIdx.x] - r0;  // pu[] is a register array: pick this thread's entry without indexing
@@ -514,20 +514,27 @@ __global__ void __launch_bounds__(kSweepThreads) k_blk_sweep(BlkView b) {
     for (int u = 0; u < KM; u++) pr[u] = reinterpret_cast<const double2*>(b.PR + (size_t)u * ld)[chunk];
     __syncthreads();
     double2* d = T2 + chunk;
+    // software pipeline: the loads of the next UNROLL rows are in flight while the current rows go through
+    // their KM dependent multiply/subtract pairs (the DP work of a full group is ~2/3 of the memory time)
+    double2 xc[UNROLL], xn[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; k++)
+      if (r0 + k < r1) xc[k] = ld_stream(d + (size_t)(r0 + k) * ldv);
     for (int r = r0; r < r1; r += UNROLL) {
-      double2 x[UNROLL];
 #pragma unroll
       for (int k = 0; k < UNROLL; k++)
-        if (r + k < r1) x[k] = ld_stream(d + (size_t)(r + k) * ldv);
+        if (r + UNROLL + k < r1) xn[k] = ld_stream(d + (size_t)(r + UNROLL + k) * ldv);
 #pragma unroll
       for (int k = 0; k < UNROLL; k++) {
         const int row = r + k;
         if (row < r1) {
           const double2* fr = reinterpret_cast<const double2*>(sF + (size_t)(row - r0) * KM);
           const bool slow = (sPiv[(row - r0) >> 5] >> ((row - r0) & 31)) & 1u;  // CTA-uniform
-          d[(size_t)row * ldv] = slow ? blk_apply_gen<KM>(x[k], pr, fr, row, s, pu) : blk_apply_fast<KM>(x[k], pr, fr);
+          d[(size_t)row * ldv] = slow ? blk_apply_gen<KM>(xc[k], pr, fr, row, s, pu) : blk_apply_fast<KM>(xc[k], pr, fr);
         }
       }
+#pragma unroll
+      for (int k = 0; k < UNROLL; k++) xc[k] = xn[k];
     }
   }
   // ragged remainder: the last (ldv % 256) chunks of every row, one thread per row
@@ -617,7 +624,9 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
   static const int groups_per_batch = std::max(1, getenv("LPR_TAB_BATCH") ? atoi(getenv("LPR_TAB_BATCH")) / 4 : 8);
   const int gsel = (h->ld + 255) / 256;
   // sweep grid: contiguous (column group, row) unit ranges, ~4 waves of resident CTAs
-  const long long items = (long long)(h->ld / 2 / kSweepThreads) * ((h->R + kBlkRowsMax - 1) / kBlkRowsMax);
+  static const int rb_env = getenv("LPR_BLK_ROWS") ? atoi(getenv("LPR_BLK_ROWS")) : 64;
+  const int RB = (rb_env >= 256) ? 256 : (rb_env >= 128 ? 128 : 64);
+  const long long items = (long long)(h->ld / 2 / kSweepThreads) * ((h->R + RB - 1) / RB);
   long long gs = std::max<long long>(items, (h->R + kSweepThreads - 1) / kSweepThreads);
   gs = std::max<long long>(1, std::min<long long>(gs, (long long)h->sms * 64));
 
@@ -652,8 +661,16 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
         sw_ev.push_back(c2);
         LPR_CUDA(cudaEventRecord(a, h->stream));
       }
-      if ((K <= 8 ? launch_pdl_b(k_blk_sweep<8, 8>, (int)gs, kSweepThreads, h->stream, b)
-                  : launch_pdl_b(k_blk_sweep<8, 16>, (int)gs, kSweepThreads, h->stream, b)) != cudaSuccess)
+      cudaError_t se;
+      if (K <= 8)
+        se = RB == 256 ? launch_pdl_b(k_blk_sweep<4, 8, 256>, (int)gs, kSweepThreads, h->stream, b)
+           : RB == 128 ? launch_pdl_b(k_blk_sweep<4, 8, 128>, (int)gs, kSweepThreads, h->stream, b)
+                       : launch_pdl_b(k_blk_sweep<4, 8, 64>, (int)gs, kSweepThreads, h->stream, b);
+      else
+        se = RB == 256 ? launch_pdl_b(k_blk_sweep<4, 16, 256>, (int)gs, kSweepThreads, h->stream, b)
+           : RB == 128 ? launch_pdl_b(k_blk_sweep<4, 16, 128>, (int)gs, kSweepThreads, h->stream, b)
+                       : launch_pdl_b(k_blk_sweep<4, 16, 64>, (int)gs, kSweepThreads, h->stream, b);
+      if (se != cudaSuccess)
         return fail(LPR_E_CUDA, "blocked sweep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       count_launch();
       if (timed) LPR_CUDA(cudaEventRecord(sw_ev.back(), h->stream));
