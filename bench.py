@@ -210,10 +210,10 @@ def main():
     peaks, peak_kind = measured_peaks()
     lib = N.lib()
 
-    def solve_resident(max_pivots):
+    def solve_resident(max_pivots, blocked=True):
         """one step with the inputs resident in HBM: returns (pivots, device ms, status)"""
         t = L.DeviceTableau.dense_lp(SEED, M, NV, device=dev)
-        r = t.solve(L.RULE_PRIMAL, max_pivots=max_pivots, log_cap=0)
+        r = t.solve(L.RULE_PRIMAL, max_pivots=max_pivots, log_cap=0, blocked=blocked)
         ms = t.last_solve_ms
         z = t.objective()
         t.close()
@@ -242,20 +242,30 @@ def main():
     pivots_per_step = piv_total / args.steps
     value = world * piv_total / (ms_max / 1e3)
 
-    # -------- dominant kernel duration: event pairs around each sweep launch (short pass) ----
-    sweep_us = None
+    # -------- dominant kernel durations: event pairs around each sweep launch (short passes) ----
+    KBLK = int(os.environ.get("LPR_TAB_BLOCK", "16"))
+    sweep_us = blk_sweep_us = None
+    unblocked = None
     try:
+        # (a) one sweep per pivot (flags bit4): the north star's per-pivot rank-1 sweep
         t = L.DeviceTableau.dense_lp(SEED, M, NV, device=dev)
-        st, npv = C.c_int(), C.c_int64()
-        N.check(lib.lpr_tab_solve(t._h, L.RULE_PRIMAL, 96, 8, C.byref(st), C.byref(npv), None, 0))  # flag 8 = time sweeps
+        t.solve(L.RULE_PRIMAL, max_pivots=96, log_cap=0, blocked=False, time_sweeps=True)
         us = C.c_float()
-        if hasattr(lib, "lpr_tab_last_sweep_us"):
-            lib.lpr_tab_last_sweep_us.argtypes = [N.vp, C.POINTER(C.c_float)]
-            N.check(lib.lpr_tab_last_sweep_us(t._h, C.byref(us)))
-            sweep_us = us.value if us.value > 0 else None
+        N.check(lib.lpr_tab_last_sweep_us(t._h, C.byref(us)))
+        sweep_us = us.value if us.value > 0 else None
         t.close()
+        # (b) delayed-update path: one sweep per KBLK pivots
+        t = L.DeviceTableau.dense_lp(SEED, M, NV, device=dev)
+        t.solve(L.RULE_PRIMAL, max_pivots=16 * KBLK, log_cap=0, blocked=True, time_sweeps=True)
+        N.check(lib.lpr_tab_last_sweep_us(t._h, C.byref(us)))
+        blk_sweep_us = us.value if us.value > 0 else None
+        t.close()
+        # (c) throughput of the per-pivot path over a 1024-pivot window (same tableau, same pivots)
+        for _ in range(2):
+            pu, msu, _, _ = solve_resident(1024, blocked=False)
+        unblocked = {"pivots": pu, "ms": msu, "pivots_per_s": pu / (msu / 1e3), "us_per_pivot": msu * 1e3 / pu}
     except Exception as ex:  # measurement aid only
-        sweep_us = None
+        sys.stderr.write(f"[bench] per-kernel timing pass failed: {ex!r}\n")
 
     # -------- e2e: host buffers through the C ABI (rank-local replica) --------------------------
     import oracle_lib as O  # only to GENERATE the host-side model arrays (same generator as the device one)
@@ -325,16 +335,31 @@ def main():
         return
 
     per_pivot_us = ms_max * 1e3 / piv_total
-    achieved_pivot = BYTES_PER_PIVOT / (per_pivot_us * 1e-6) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "sweep_dram_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f)
     except Exception:
         pass
     peak = float(peaks["hbm_gbs"])
-    kern_us = sweep_us if sweep_us else per_pivot_us
-    achieved = BYTES_SWEEP / (kern_us * 1e-6) / 1e9
+    # dominant kernel of the timed region = the blocked sweep: it reads+writes the tableau once and reads the
+    # KBLK pending pivot rows / factor columns; ONE launch applies KBLK pivots
+    bytes_blk = 16.0 * R * CC + 8.0 * KBLK * (R + CC)
+    kern_us = blk_sweep_us if blk_sweep_us else None
+    achieved = bytes_blk / (kern_us * 1e-6) / 1e9 if kern_us else None
+    pivot_equiv = BYTES_PER_PIVOT / (per_pivot_us * 1e-6) / 1e9
+    per_pivot_kernel = None
+    if sweep_us and unblocked:
+        ach1 = BYTES_SWEEP / (sweep_us * 1e-6) / 1e9
+        achp = BYTES_PER_PIVOT / (unblocked["us_per_pivot"] * 1e-6) / 1e9
+        per_pivot_kernel = {
+            "what": "one rank-1 sweep per pivot (lpr_tab_solve flags bit4): the north star's per-pivot kernel",
+            "kernel": "lpr::k_sweep<0,false,true,4>", "kernel_us": sweep_us, "bytes_per_launch": BYTES_SWEEP,
+            "achieved": ach1, "frac_of_measured": ach1 / peak, "frac_of_nominal_8tbs": ach1 / NOMINAL_HBM_GBS,
+            "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+            "whole_pivot": {"us": unblocked["us_per_pivot"], "pivots_per_s": unblocked["pivots_per_s"],
+                            "bytes": BYTES_PER_PIVOT, "achieved": achp, "frac_of_measured": achp / peak,
+                            "frac_of_nominal_8tbs": achp / NOMINAL_HBM_GBS}}
     line = {
         "metric": "simplex pivots/s (dense 4096x8192 fp64 primal tableau)",
         "value": value, "unit": "pivots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -343,7 +368,7 @@ def main():
         "config": {"workload": "cfg2 dense LP m=4096 n=8192 primal tableau simplex, tableau 4097x12289 "
                                "(BASELINE.json configs[1])",
                    "step": "one full Solve() from the slack basis to optimality",
-                   "pivots_per_step": pivots_per_step, "status": L.STATUS_NAMES[status], "seed": SEED,
+                   "pivots_per_step": pivots_per_step, "delayed_update_block": KBLK, "status": L.STATUS_NAMES[status], "seed": SEED,
                    "l2": "tableau 402.8 MB > 126 MB L2 (inputs larger than L2; no flush needed)",
                    "parallelism": "replicas" if world > 1 else "single GPU"},
         "tableau_gbs": 16.0 * R * CC * value / world / 1e9,
@@ -353,16 +378,20 @@ def main():
                                             "objective + extract_solution + basis + lpr_tab_read(final tableau)"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "lpr::k_sweep<0,false,true,8> (rank-1 row elimination sweep)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm",
+                     "kernel": f"lpr::k_blk_sweep<4,{8 if KBLK <= 8 else 16},64> (applies {KBLK} delayed rank-1 updates per launch)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None,
                      "peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)",
-                     "bytes_per_launch": BYTES_SWEEP, "kernel_us": kern_us,
-                     "kernel_us_how": "CUDA event pairs around each sweep launch, 96-pivot pass" if sweep_us
-                     else "whole-pivot time (no per-kernel pass)",
-                     "traffic": traffic,
-                     "per_pivot": {"bytes": BYTES_PER_PIVOT, "us": per_pivot_us, "achieved": achieved_pivot,
-                                   "frac_of_measured": achieved_pivot / peak,
-                                   "frac_of_nominal_8tbs": achieved_pivot / NOMINAL_HBM_GBS}},
+                     "bytes_per_launch": bytes_blk, "pivots_per_launch": KBLK, "kernel_us": kern_us,
+                     "kernel_us_how": "CUDA event pairs around each sweep launch on the library stream, 16-group pass",
+                     "traffic": (traffic or {}).get("blocked_dram_bytes_per_launch"),
+                     "note": "bit-identical delayed-update path: every element still goes through the same "
+                             "multiply/subtract roundings in the same order, but the tableau is swept once per "
+                             f"{KBLK} pivots; pivot_equivalent = 16RC-per-pivot bytes x pivots/s",
+                     "pivot_equivalent": {"bytes_per_pivot": BYTES_PER_PIVOT, "us_per_pivot": per_pivot_us,
+                                          "gbs": pivot_equiv, "x_of_nominal_8tbs": pivot_equiv / NOMINAL_HBM_GBS},
+                     "per_pivot_kernel": per_pivot_kernel},
         "cpu_baseline": cpu,
         "bb": bb,
         "knapsack": knap,

@@ -780,7 +780,7 @@ int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int*
   {
     // delayed-update path: K pivots per tableau sweep (tableau_blocked.cu); flags bit4 or
     // LPR_TAB_BLOCK<=1 keep one sweep per pivot
-    static const int blk = env_int("LPR_TAB_BLOCK", 8);
+    static const int blk = env_int("LPR_TAB_BLOCK", 16);
     static const int fused_on = env_int("LPR_TAB_FUSED", 1);
     if (rule == LPR_RULE_PRIMAL && fused_on && blk > 1 && !(flags & (4 | 16)) && (max_pivots < 0 || max_pivots > 1))
       return tab_solve_blocked(h, blk, max_pivots, status, n_pivots, pivot_log, log_cap, (flags & 8) != 0);
