@@ -278,16 +278,27 @@ def main():
     h2d = 8 * (M * NV + M + NV)
     d2h = 8 * (R * CC + NV + 1) + 4 * M
 
+    e2e_phase = {}
+
     def solve_e2e(max_pivots):
+        tp = [time.perf_counter()]
         h = N.vp()
         N.check(lib.lpr_tab_create_primal(dev, NV, M, N.pd(ch), N.pd(Ah), NV, None, None, N.pd(bh), 1, C.byref(h)))
+        tp.append(time.perf_counter())
         st, npv, z = C.c_int(), C.c_int64(), C.c_double()
         N.check(lib.lpr_tab_solve(h, L.RULE_PRIMAL, max_pivots, 0, C.byref(st), C.byref(npv), None, 0))
+        tp.append(time.perf_counter())
         N.check(lib.lpr_tab_objective(h, C.byref(z)))
         N.check(lib.lpr_tab_extract_solution(h, NV, N.pd(outx)))
         N.check(lib.lpr_tab_get_basis(h, N.pi(outb)))
+        tp.append(time.perf_counter())
         N.check(lib.lpr_tab_read(h, N.pd(outT)))
+        tp.append(time.perf_counter())
         lib.lpr_tab_destroy(h)
+        tp.append(time.perf_counter())
+        for name, a, b2 in (("create_h2d_build", 0, 1), ("solve", 1, 2), ("z_x_basis", 2, 3), ("read_tableau_d2h", 3, 4),
+                            ("destroy", 4, 5)):
+            e2e_phase[name] = round((tp[b2] - tp[a]) * 1e3, 3)
         return npv.value, z.value
 
     solve_e2e(args.max_pivots)  # warm-up
@@ -374,7 +385,7 @@ def main():
         "tableau_gbs": 16.0 * R * CC * value / world / 1e9,
         "wall_ms_per_step": wall_max / args.steps,
         "e2e": {"value": e2e_value, "unit": "pivots/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "what": "lpr_tab_create_primal(host A,b,c pinned) + lpr_tab_solve + "
+                "steps": e2e_steps, "phase_ms_last_step": e2e_phase, "what": "lpr_tab_create_primal(host A,b,c pinned) + lpr_tab_solve + "
                                             "objective + extract_solution + basis + lpr_tab_read(final tableau)"},
         "gpu_launches": launches,
         "clocks": clocks,
