@@ -14,6 +14,8 @@
 //       column; the last CTA (atomic ticket) publishes the pivot.
 //   k_blk_sweep: applies the s pending updates; thread owns one 16-byte column chunk (its s pivot-row
 //       values live in registers) and walks down rows.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -36,6 +38,7 @@ struct BlkView {
   int Rcap;
   MinIdx* cand;
   unsigned* ticket;
+  long long* dbg;  // optional phase timestamps of the cluster select (LPR_BLK_TIMING=1), else null
 };
 
 __global__ void __launch_bounds__(kSelThreads) k_blk_init(BlkView b) {
@@ -435,6 +438,278 @@ __global__ void __launch_bounds__(256) k_blk_select2(BlkView b, int group_pos, R
 // the CTA's rows are staged once in shared memory and broadcast from there.
 // rows per work item RB (shared-memory stage: RB x KM doubles): small items keep the tail wave short
 
+// ---- select v3: ONE launch selects all K pivots of a group.  A thread-block cluster (8 portable / 16
+// non-portable CTAs x 512 threads) owns the whole selection: thread g owns rows g, g+T, ... of the entering
+// column and columns g, g+T, ... of the pivot row; the two argmin reductions of a pivot go through
+// distributed shared memory and the hardware cluster barrier instead of global-memory tickets and kernel
+// boundaries (~4 us per pivot instead of ~12).
+namespace cg = cooperative_groups;
+
+struct ClusterSlot {
+  double val;   // ratio / objective value
+  double aux;   // pivot element candidate (phase A), f0 (CTA that owns row 0)
+  int idx;
+  int has_f0;
+};
+
+// one-barrier block argmin: every warp publishes its candidate, every thread re-reduces the <= 32 entries
+__device__ __forceinline__ MinIdx block_minidx_1sync(MinIdx x, MinIdx* smem /* 32 entries, private to this call site */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  x = warp_minidx(x);
+  if (lane == 0) smem[w] = x;
+  __syncthreads();
+  MinIdx r = (lane < nw) ? smem[lane] : minidx_identity();
+  return warp_minidx(r);
+}
+
+template <int KM, int NT>
+__global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int ncta = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  const int nthr = ncta * NT;
+  const int gid = crank * NT + tid;
+  __shared__ MinIdx smA[2][32], smB[2][32];
+  __shared__ double s_pe[KM], s_fp[KM];
+  __shared__ int s_pu[KM];
+  __shared__ ClusterSlot s_a[2], s_b[2];
+  __shared__ double s_bc[4];
+  __shared__ int s_bi[2];
+  const TabView& v = b.v;
+  TabState* st = v.st;
+  const int R = v.R, C = v.C, ld = v.ld;
+  const double* T = v.T;
+  pdl_wait_then_release();
+  const int status = st->status;
+  long long npiv = st->npiv;
+  const long long npiv0 = npiv;
+  const long long maxp = st->max_piv;
+  int cur = st->cur;
+  int e = st->enter;
+  if (status != LPR_RUNNING) {
+    if (gid == 0) st->group_base = npiv;
+    return;
+  }
+  if (tid < KM) s_pu[tid] = -1;
+  __syncthreads();
+  int term = LPR_RUNNING;
+  int s = 0;
+  auto stamp = [&](int q, int k) {
+    if (b.dbg && gid == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      b.dbg[q * 8 + k] = t;
+    }
+  };
+  const bool own_row = gid < R;      // first (usually only) row / column of this thread
+  const bool own_col = gid < ld;
+  for (int q = 0; q < K; q++, s++) {
+    if (e < 0) { term = LPR_OPTIMAL; break; }
+    stamp(q, 0);
+    const double* rhs = cur ? b.rhs1 : b.rhs0;
+    double* rhs_next = cur ? b.rhs0 : b.rhs1;
+    const int buf = q & 1;
+    // ---- phase A: entering column of the current tableau (stale column + pending updates), ratio test ----
+    // the DRAM gather of the stale column and the L2 reads of the pending data are issued together
+    double col0 = 0.0, rv0 = 0.0;
+    double2 fq0[KM / 2];
+    if (own_row) {
+      col0 = TAT(T, ld, gid, e);
+      rv0 = rhs[gid];
+      const double2* fr = reinterpret_cast<const double2*>(b.F + (size_t)gid * KM);
+#pragma unroll
+      for (int h2 = 0; h2 < KM / 2; h2++) fq0[h2] = fr[h2];
+    }
+    if (tid < KM) s_pe[tid] = (tid < s) ? __ldcg(b.PR + (size_t)tid * ld + e) : 0.0;  // written by another CTA
+    __syncthreads();
+    stamp(q, 1);
+    MinIdx best = minidx_identity();
+    double best_a = 0.0;
+    auto col_update = [&](int i, double col, const double2* fq) -> double {
+#pragma unroll
+      for (int u = 0; u < KM; u++) {
+        const double fu = (u & 1) ? fq[u >> 1].y : fq[u >> 1].x;
+        const double upd = (i == s_pu[u]) ? s_pe[u] : __dsub_rn(col, __dmul_rn(fu, s_pe[u]));
+        col = (u < s) ? upd : col;
+      }
+      return col;
+    };
+    auto ratio_cand = [&](int i, double col, double rv) {
+      if (i >= 1 && col > 1e-9) {
+        const double val = __ddiv_rn(rv, col);
+        if (val >= 0.0 && val < DBL_MAX) {
+          MinIdx nb = minidx_combine(best, MinIdx{val, i - 1});
+          if (nb.i != best.i) best_a = col;
+          best = nb;
+        }
+      }
+    };
+    if (own_row) {
+      col0 = col_update(gid, col0, fq0);
+      if (col0 == 1.2345e300) stamp(q, 7);  // keep the dependency
+      stamp(q, 2);
+      b.F[(size_t)gid * KM + s] = col0;  // factor column of this pivot
+      if (gid == 0) s_bc[0] = col0;      // f0 = T[0, e]
+      ratio_cand(gid, col0, rv0);
+    }
+    for (int i = gid + nthr; i < R; i += nthr) {  // only when the cluster has fewer threads than rows
+      double2 fq[KM / 2];
+      const double2* fr = reinterpret_cast<const double2*>(b.F + (size_t)i * KM);
+#pragma unroll
+      for (int h2 = 0; h2 < KM / 2; h2++) fq[h2] = fr[h2];
+      const double col = col_update(i, TAT(T, ld, i, e), fq);
+      b.F[(size_t)i * KM + s] = col;
+      ratio_cand(i, col, rhs[i]);
+    }
+    stamp(q, 3);
+    {
+      const MinIdx mine = best;
+      best = block_minidx_1sync(best, smA[buf]);
+      if (best.i != INT_MAX && mine.i == best.i) s_bc[1] = best_a;
+      __syncthreads();
+      if (tid == 0) {
+        ClusterSlot c;
+        c.val = best.v;
+        c.idx = best.i;
+        c.aux = (best.i != INT_MAX) ? s_bc[1] : 0.0;
+        c.has_f0 = 0;
+        s_a[buf] = c;
+        if (crank == 0) s_b[buf].aux = s_bc[0];  // row 0 belongs to thread 0 of CTA 0
+      }
+    }
+    __threadfence();
+    cluster.sync();
+    int p = -1;
+    double piv = 0.0, f0 = 0.0;
+    {
+      // every CTA combines the ncta candidates (one warp, one DSMEM read per lane)
+      if (tid < 32) {
+        MinIdx r = minidx_identity();
+        double ra = 0.0;
+        if (tid < ncta) {
+          const ClusterSlot* peer = cluster.map_shared_rank(&s_a[buf], tid);
+          r = MinIdx{peer->val, peer->idx};
+          ra = peer->aux;
+        }
+        const MinIdx mine = r;
+        r = warp_minidx(r);
+        const unsigned owner = __ballot_sync(0xffffffffu, r.i != INT_MAX && mine.i == r.i && tid < ncta);
+        const double pa = __shfl_sync(0xffffffffu, ra, owner ? (__ffs(owner) - 1) : 0);
+        if (tid == 0) {
+          s_bi[1] = (r.i == INT_MAX) ? -1 : r.i;
+          s_bc[2] = pa;
+          const ClusterSlot* c0 = cluster.map_shared_rank(&s_b[buf], 0);
+          s_bc[3] = c0->aux;
+        }
+      }
+      __syncthreads();
+      const int k = s_bi[1];
+      if (k < 0) { term = LPR_UNBOUNDED; break; }
+      if (maxp >= 0 && npiv >= maxp) { term = LPR_ITER_LIMIT; break; }
+      p = k + 1;
+      piv = s_bc[2];
+      f0 = s_bc[3];
+    }
+    stamp(q, 4);
+    // ---- phase B: pivot row (stale row + pending updates), objective row / RHS mirrors, next entering ----
+    double x0 = 0.0, r0j0 = 0.0;
+    double pru0[KM];
+    if (own_col && gid < C) {
+      x0 = TAT(T, ld, p, gid);
+#pragma unroll
+      for (int u = 0; u < KM; u++) pru0[u] = b.PR[(size_t)u * ld + gid];
+      r0j0 = b.row0[gid];
+    }
+    if (tid < KM) s_fp[tid] = (tid < s) ? __ldcg(b.F + (size_t)p * KM + tid) : 0.0;  // written by another CTA
+    const double rhsp = __ldcg(rhs + p);
+    __syncthreads();
+    stamp(q, 5);
+    MinIdx m = minidx_identity();
+    auto row_update = [&](double x, const double* pru) -> double {
+#pragma unroll
+      for (int u = 0; u < KM; u++) {
+        const double upd = (p == s_pu[u]) ? pru[u] : __dsub_rn(x, __dmul_rn(s_fp[u], pru[u]));
+        x = (u < s) ? upd : x;
+      }
+      return x;
+    };
+    if (own_col) {
+      double pr = 0.0, z = 0.0;
+      if (gid < C) {
+        const double xx = row_update(x0, pru0);
+        if (xx == 1.2345e300) stamp(q, 0);
+        stamp(q, 6);
+        pr = __ddiv_rn(xx, piv);
+        z = __dsub_rn(r0j0, __dmul_rn(f0, pr));
+        if (gid < C - 1 && z < 0.0) m = MinIdx{z, gid};
+      }
+      b.PR[(size_t)s * ld + gid] = pr;
+      b.row0[gid] = z;
+    }
+    for (int j = gid + nthr; j < ld; j += nthr) {  // only when the cluster has fewer threads than columns
+      double pr = 0.0, z = 0.0;
+      if (j < C) {
+        double pru[KM];
+#pragma unroll
+        for (int u = 0; u < KM; u++) pru[u] = b.PR[(size_t)u * ld + j];
+        pr = __ddiv_rn(row_update(TAT(T, ld, p, j), pru), piv);
+        z = __dsub_rn(b.row0[j], __dmul_rn(f0, pr));
+        if (j < C - 1 && z < 0.0) m = minidx_combine(m, MinIdx{z, j});
+      }
+      b.PR[(size_t)s * ld + j] = pr;
+      b.row0[j] = z;
+    }
+    {
+      const double prc = __ddiv_rn(rhsp, piv);
+      if (own_row) rhs_next[gid] = (gid == p) ? prc : __dsub_rn(rv0, __dmul_rn(col0, prc));
+      for (int i = gid + nthr; i < R; i += nthr)
+        rhs_next[i] = (i == p) ? prc : __dsub_rn(rhs[i], __dmul_rn(b.F[(size_t)i * KM + s], prc));
+    }
+    stamp(q, 7);
+    m = block_minidx_1sync(m, smB[buf]);
+    if (tid == 0) {
+      s_b[buf].val = m.v;
+      s_b[buf].idx = m.i;
+      s_pu[s] = p;
+    }
+    __threadfence();
+    cluster.sync();
+    if (tid < 32) {
+      MinIdx r = minidx_identity();
+      if (tid < ncta) {
+        const ClusterSlot* peer = cluster.map_shared_rank(&s_b[buf], tid);
+        r = MinIdx{peer->val, peer->idx};
+      }
+      r = warp_minidx(r);
+      if (tid == 0) s_bi[1] = (r.i == INT_MAX) ? -1 : r.i;
+    }
+    if (gid == 0) {
+      b.pidx[s] = p;
+      if (v.log && npiv < v.log_cap) {
+        v.log[2 * npiv] = p;
+        v.log[2 * npiv + 1] = e;
+      }
+      if (v.basis) v.basis[p - 1] = e;  // :142
+      st->pivot = piv;
+      st->leave = p;
+    }
+    __syncthreads();
+    e = s_bi[1];
+    npiv++;
+    cur ^= 1;
+  }
+  // peers may still be reading this CTA's slots: leave together
+  cluster.sync();
+  if (gid == 0) {
+    st->group_base = npiv0;
+    st->npiv = npiv;
+    st->cur = cur;
+    st->enter = e;
+    if (term != LPR_RUNNING) st->status = term;
+  }
+}
+
 // fast path: a full group (s == KM) on a row that is not one of the pending pivot rows -- 2 DMUL + 2 DADD
 // per pending pivot and chunk, nothing else
 template <int KM>
@@ -609,6 +884,13 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
   if (!(pivot_log && log_cap > 0)) { b.v.log = nullptr; b.v.log_cap = 0; }
   b.PR = h->blk_pr; b.F = h->blk_f; b.row0 = h->blk_row0; b.rhs0 = h->blk_rhs[0]; b.rhs1 = h->blk_rhs[1];
   b.pidx = h->blk_p; b.Rcap = h->Rcap; b.cand = h->selcand; b.ticket = h->ticket;
+  b.dbg = nullptr;
+  long long* d_dbg = nullptr;
+  if (getenv("LPR_BLK_TIMING")) {
+    LPR_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 8 * KMAX));
+    LPR_CUDA(cudaMemset(d_dbg, 0, sizeof(long long) * 8 * KMAX));
+    b.dbg = d_dbg;
+  }
   // select v2 scratch (per-CTA ratio candidates, barrier counter, f0)
   static const int sel_v2 = getenv("LPR_BLK_SELECT_V2") ? atoi(getenv("LPR_BLK_SELECT_V2")) : 1;
   RatioCand* d_rc = nullptr;
@@ -621,6 +903,44 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
     LPR_CUDA(cudaMalloc(&d_f0, sizeof(double)));
     LPR_CUDA(cudaMemsetAsync(d_bar, 0, sizeof(unsigned), h->stream));
   }
+  // select v3: one cluster launch per group
+  static const int cl_env = getenv("LPR_BLK_CLUSTER") ? atoi(getenv("LPR_BLK_CLUSTER")) : 16;
+  int cluster_ctas = 0;
+  if (cl_env >= 2) {
+    cluster_ctas = std::min(cl_env, 16);
+    if (cluster_ctas > 8) {
+      cudaError_t ce = cudaFuncSetAttribute(k_blk_select_cluster<8, 512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_blk_select_cluster<16, 512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_blk_select_cluster<8, 1024>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_blk_select_cluster<16, 1024>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (ce != cudaSuccess) {
+        cudaGetLastError();
+        cluster_ctas = 8;
+      }
+    }
+  }
+  auto launch_cluster = [&](int ncta) -> cudaError_t {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncta);
+    static const int nt = (getenv("LPR_BLK_CLUSTER_THREADS") ? atoi(getenv("LPR_BLK_CLUSTER_THREADS")) : 512) >= 1024 ? 1024 : 512;
+    cfg.blockDim = dim3(nt);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const int pdl = getenv("LPR_PDL") ? atoi(getenv("LPR_PDL")) : 1;
+    cfg.numAttrs = pdl ? 2 : 1;
+    if (nt == 1024)
+      return (K <= 8) ? cudaLaunchKernelEx(&cfg, k_blk_select_cluster<8, 1024>, b, K)
+                      : cudaLaunchKernelEx(&cfg, k_blk_select_cluster<16, 1024>, b, K);
+    return (K <= 8) ? cudaLaunchKernelEx(&cfg, k_blk_select_cluster<8, 512>, b, K)
+                    : cudaLaunchKernelEx(&cfg, k_blk_select_cluster<16, 512>, b, K);
+  };
   static const int groups_per_batch = std::max(1, getenv("LPR_TAB_BATCH") ? atoi(getenv("LPR_TAB_BATCH")) / 4 : 8);
   const int gsel = (h->ld + 255) / 256;
   // sweep grid: contiguous (column group, row) unit ranges, ~4 waves of resident CTAs
@@ -640,7 +960,21 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
   int slot = 0, pending = 0, ngroups = 1;
   while (true) {
     for (int g = 0; g < ngroups; g++) {
-      for (int q = 0; q < K; q++) {
+      if (cluster_ctas >= 2) {
+        cudaError_t ce = launch_cluster(cluster_ctas);
+        if (ce != cudaSuccess && cluster_ctas > 8) {  // 16-CTA clusters not schedulable here: retry with 8
+          cudaGetLastError();
+          cluster_ctas = 8;
+          ce = launch_cluster(cluster_ctas);
+        }
+        if (ce != cudaSuccess) {
+          cudaGetLastError();
+          cluster_ctas = 0;  // fall back to the multi-launch select
+        } else {
+          count_launch();
+        }
+      }
+      for (int q = 0; q < K && cluster_ctas < 2; q++) {
         cudaError_t le;
         if (use_v2)
           le = (K <= 8) ? launch_pdl_b(k_blk_select2<8>, gsel, 256, h->stream, b, q, d_rc, d_bar, d_f0)
@@ -694,6 +1028,17 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
   cudaFree(d_rc);
   cudaFree(d_bar);
   cudaFree(d_f0);
+  if (d_dbg) {  // phase timestamps of the LAST group's select (ns, relative to the first stamp)
+    long long hd[8 * KMAX];
+    cudaMemcpy(hd, d_dbg, sizeof hd, cudaMemcpyDeviceToHost);
+    for (int q = 0; q < K && hd[q * 8]; q++) {
+      fprintf(stderr, "[blk timing] pivot %2d:", q);
+      for (int k = 1; k < 8; k++) fprintf(stderr, " %5lld", hd[q * 8 + k] - hd[q * 8 + k - 1]);
+      if (q + 1 < K && hd[(q + 1) * 8]) fprintf(stderr, " | next %5lld", hd[(q + 1) * 8] - hd[q * 8 + 7]);
+      fprintf(stderr, "  ns (stageA loadsChainA ratioStoreA reduceSyncDsmemA stageB loadsChainB divStoreB)\n");
+    }
+    cudaFree(d_dbg);
+  }
   const long long npiv = h->st_host[0].npiv;
   if (time_sweeps) {
     double sum = 0.0;
