@@ -462,6 +462,62 @@ __device__ __forceinline__ MinIdx block_minidx_1sync(MinIdx x, MinIdx* smem /* 3
   return warp_minidx(r);
 }
 
+// cluster-wide argmin without a block-level stage: every warp leader stores its candidate into slot
+// [crank*nw + w] of EVERY CTA of the cluster (distributed shared memory), one cluster barrier, then each CTA
+// reduces the ncta*nw candidates locally.  `aux` rides along (pivot element of the winning row).
+struct WarpCand {
+  double val;
+  double aux;
+  int idx;
+  int pad;
+};
+constexpr int kMaxClusterWarps = 16 * 32;  // 16 CTAs x up to 32 warps
+
+__device__ __forceinline__ void cluster_publish(cg::cluster_group& cluster, WarpCand* slots, int ncta, int crank,
+                                                MinIdx x, double aux) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const MinIdx mine = x;
+  x = warp_minidx(x);
+  const unsigned owner = __ballot_sync(0xffffffffu, x.i != INT_MAX && mine.i == x.i);
+  const double a = __shfl_sync(0xffffffffu, aux, owner ? (__ffs(owner) - 1) : 0);
+  if (lane < ncta) {  // lane r writes this warp's candidate into CTA r
+    WarpCand* dst = cluster.map_shared_rank(slots, lane);
+    WarpCand c;
+    c.val = x.v;
+    c.aux = a;
+    c.idx = x.i;
+    c.pad = 0;
+    dst[crank * nw + w] = c;
+  }
+}
+// after cluster.sync(): reduce the local copy (all threads get the result through shared memory)
+__device__ __forceinline__ void cluster_collect(const WarpCand* slots, int total, MinIdx* out, double* aux_out,
+                                                int* s_i, double* s_d) {
+  if (threadIdx.x < 32) {
+    MinIdx r = minidx_identity();
+    double ra = 0.0;
+    for (int k = threadIdx.x; k < total; k += 32) {
+      const WarpCand c = slots[k];
+      MinIdx nb = minidx_combine(r, MinIdx{c.val, c.idx});
+      if (nb.i != r.i) ra = c.aux;
+      r = nb;
+    }
+    const MinIdx mine = r;
+    r = warp_minidx(r);
+    const unsigned owner = __ballot_sync(0xffffffffu, r.i != INT_MAX && mine.i == r.i);
+    const double a = __shfl_sync(0xffffffffu, ra, owner ? (__ffs(owner) - 1) : 0);
+    if (threadIdx.x == 0) {
+      s_i[0] = r.i;
+      s_d[0] = r.v;
+      s_d[1] = a;
+    }
+  }
+  __syncthreads();
+  out->i = s_i[0];
+  out->v = s_d[0];
+  *aux_out = s_d[1];
+}
+
 template <int KM, int NT>
 __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -470,12 +526,13 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
   const int tid = threadIdx.x;
   const int nthr = ncta * NT;
   const int gid = crank * NT + tid;
-  __shared__ MinIdx smA[2][32], smB[2][32];
+  const int total_warps = ncta * (NT / 32);
+  __shared__ WarpCand slotA[2][kMaxClusterWarps / 2], slotB[2][kMaxClusterWarps / 2];  // NT <= 512: 16 warps x 16 CTAs
   __shared__ double s_pe[KM], s_fp[KM];
   __shared__ int s_pu[KM];
-  __shared__ ClusterSlot s_a[2], s_b[2];
-  __shared__ double s_bc[4];
-  __shared__ int s_bi[2];
+  __shared__ double s_f0[2];
+  __shared__ double s_d[2];
+  __shared__ int s_i[1];
   const TabView& v = b.v;
   TabState* st = v.st;
   const int R = v.R, C = v.C, ld = v.ld;
@@ -502,8 +559,12 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
       b.dbg[q * 8 + k] = t;
     }
   };
-  const bool own_row = gid < R;      // first (usually only) row / column of this thread
-  const bool own_col = gid < ld;
+  const bool own_row = gid < R;
+  const int j0 = gid, j1 = gid + nthr;          // the (up to) two columns of this thread
+  const bool own_c0 = j0 < ld, own_c1 = j1 < ld;
+  double fq0[KM];                                 // this thread's row of pending factors, kept in registers
+#pragma unroll
+  for (int u = 0; u < KM; u++) fq0[u] = 0.0;
   for (int q = 0; q < K; q++, s++) {
     if (e < 0) { term = LPR_OPTIMAL; break; }
     stamp(q, 0);
@@ -511,30 +572,16 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
     double* rhs_next = cur ? b.rhs0 : b.rhs1;
     const int buf = q & 1;
     // ---- phase A: entering column of the current tableau (stale column + pending updates), ratio test ----
-    // the DRAM gather of the stale column and the L2 reads of the pending data are issued together
+    if (tid < KM) s_pe[tid] = (tid < s) ? __ldcg(b.PR + (size_t)tid * ld + e) : 0.0;  // issued first: L2 trip
     double col0 = 0.0, rv0 = 0.0;
-    double2 fq0[KM / 2];
     if (own_row) {
-      col0 = TAT(T, ld, gid, e);
+      col0 = TAT(T, ld, gid, e);  // DRAM gather of the stale column
       rv0 = rhs[gid];
-      const double2* fr = reinterpret_cast<const double2*>(b.F + (size_t)gid * KM);
-#pragma unroll
-      for (int h2 = 0; h2 < KM / 2; h2++) fq0[h2] = fr[h2];
     }
-    if (tid < KM) s_pe[tid] = (tid < s) ? __ldcg(b.PR + (size_t)tid * ld + e) : 0.0;  // written by another CTA
     __syncthreads();
     stamp(q, 1);
     MinIdx best = minidx_identity();
     double best_a = 0.0;
-    auto col_update = [&](int i, double col, const double2* fq) -> double {
-#pragma unroll
-      for (int u = 0; u < KM; u++) {
-        const double fu = (u & 1) ? fq[u >> 1].y : fq[u >> 1].x;
-        const double upd = (i == s_pu[u]) ? s_pe[u] : __dsub_rn(col, __dmul_rn(fu, s_pe[u]));
-        col = (u < s) ? upd : col;
-      }
-      return col;
-    };
     auto ratio_cand = [&](int i, double col, double rv) {
       if (i >= 1 && col > 1e-9) {
         const double val = __ddiv_rn(rv, col);
@@ -546,119 +593,84 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
       }
     };
     if (own_row) {
-      col0 = col_update(gid, col0, fq0);
-      if (col0 == 1.2345e300) stamp(q, 7);  // keep the dependency
-      stamp(q, 2);
-      b.F[(size_t)gid * KM + s] = col0;  // factor column of this pivot
-      if (gid == 0) s_bc[0] = col0;      // f0 = T[0, e]
+#pragma unroll
+      for (int u = 0; u < KM; u++) {
+        const double upd = (gid == s_pu[u]) ? s_pe[u] : __dsub_rn(col0, __dmul_rn(fq0[u], s_pe[u]));
+        col0 = (u < s) ? upd : col0;
+      }
+#pragma unroll
+      for (int u = 0; u < KM; u++)
+        if (u == s) fq0[u] = col0;          // remember this pivot's factor for the next pivots of the group
+      b.F[(size_t)gid * KM + s] = col0;     // and publish it for the sweep
+      if (gid == 0) s_f0[0] = col0;         // f0 = T[0, e] (thread 0 of CTA 0)
       ratio_cand(gid, col0, rv0);
     }
     for (int i = gid + nthr; i < R; i += nthr) {  // only when the cluster has fewer threads than rows
-      double2 fq[KM / 2];
-      const double2* fr = reinterpret_cast<const double2*>(b.F + (size_t)i * KM);
-#pragma unroll
-      for (int h2 = 0; h2 < KM / 2; h2++) fq[h2] = fr[h2];
-      const double col = col_update(i, TAT(T, ld, i, e), fq);
+      double col = TAT(T, ld, i, e);
+      for (int u = 0; u < s; u++) {
+        const double fu = b.F[(size_t)i * KM + u];
+        col = (i == s_pu[u]) ? s_pe[u] : __dsub_rn(col, __dmul_rn(fu, s_pe[u]));
+      }
       b.F[(size_t)i * KM + s] = col;
       ratio_cand(i, col, rhs[i]);
     }
+    stamp(q, 2);
+    cluster_publish(cluster, slotA[buf], ncta, crank, best, best_a);
+    if (crank == 0 && tid == 0) {  // f0 travels with the barrier too: write it into every CTA
+      for (int r = 0; r < ncta; r++) *cluster.map_shared_rank(&s_f0[1], r) = s_f0[0];
+    }
+    cluster.sync();  // release/acquire at cluster scope: also orders the global writes above
     stamp(q, 3);
-    {
-      const MinIdx mine = best;
-      best = block_minidx_1sync(best, smA[buf]);
-      if (best.i != INT_MAX && mine.i == best.i) s_bc[1] = best_a;
-      __syncthreads();
-      if (tid == 0) {
-        ClusterSlot c;
-        c.val = best.v;
-        c.idx = best.i;
-        c.aux = (best.i != INT_MAX) ? s_bc[1] : 0.0;
-        c.has_f0 = 0;
-        s_a[buf] = c;
-        if (crank == 0) s_b[buf].aux = s_bc[0];  // row 0 belongs to thread 0 of CTA 0
-      }
-    }
-    __threadfence();
-    cluster.sync();
-    int p = -1;
-    double piv = 0.0, f0 = 0.0;
-    {
-      // every CTA combines the ncta candidates (one warp, one DSMEM read per lane)
-      if (tid < 32) {
-        MinIdx r = minidx_identity();
-        double ra = 0.0;
-        if (tid < ncta) {
-          const ClusterSlot* peer = cluster.map_shared_rank(&s_a[buf], tid);
-          r = MinIdx{peer->val, peer->idx};
-          ra = peer->aux;
-        }
-        const MinIdx mine = r;
-        r = warp_minidx(r);
-        const unsigned owner = __ballot_sync(0xffffffffu, r.i != INT_MAX && mine.i == r.i && tid < ncta);
-        const double pa = __shfl_sync(0xffffffffu, ra, owner ? (__ffs(owner) - 1) : 0);
-        if (tid == 0) {
-          s_bi[1] = (r.i == INT_MAX) ? -1 : r.i;
-          s_bc[2] = pa;
-          const ClusterSlot* c0 = cluster.map_shared_rank(&s_b[buf], 0);
-          s_bc[3] = c0->aux;
-        }
-      }
-      __syncthreads();
-      const int k = s_bi[1];
-      if (k < 0) { term = LPR_UNBOUNDED; break; }
-      if (maxp >= 0 && npiv >= maxp) { term = LPR_ITER_LIMIT; break; }
-      p = k + 1;
-      piv = s_bc[2];
-      f0 = s_bc[3];
-    }
+    MinIdx ra;
+    double piv = 0.0;
+    cluster_collect(slotA[buf], total_warps, &ra, &piv, s_i, s_d);
+    if (ra.i == INT_MAX) { term = LPR_UNBOUNDED; break; }
+    if (maxp >= 0 && npiv >= maxp) { term = LPR_ITER_LIMIT; break; }
+    const int p = ra.i + 1;
+    const double f0 = s_f0[1];
     stamp(q, 4);
     // ---- phase B: pivot row (stale row + pending updates), objective row / RHS mirrors, next entering ----
-    double x0 = 0.0, r0j0 = 0.0;
-    double pru0[KM];
-    if (own_col && gid < C) {
-      x0 = TAT(T, ld, p, gid);
-#pragma unroll
-      for (int u = 0; u < KM; u++) pru0[u] = b.PR[(size_t)u * ld + gid];
-      r0j0 = b.row0[gid];
-    }
-    if (tid < KM) s_fp[tid] = (tid < s) ? __ldcg(b.F + (size_t)p * KM + tid) : 0.0;  // written by another CTA
+    if (tid < KM) s_fp[tid] = (tid < s) ? __ldcg(b.F + (size_t)p * KM + tid) : 0.0;  // issued first: L2 trip
     const double rhsp = __ldcg(rhs + p);
+    double x0 = 0.0, x1 = 0.0, r00 = 0.0, r01 = 0.0;
+    double pru0[KM], pru1[KM];
+    if (own_c0 && j0 < C) {
+      x0 = TAT(T, ld, p, j0);
+      r00 = b.row0[j0];
+#pragma unroll
+      for (int u = 0; u < KM; u++) pru0[u] = b.PR[(size_t)u * ld + j0];
+    }
+    if (own_c1 && j1 < C) {
+      x1 = TAT(T, ld, p, j1);
+      r01 = b.row0[j1];
+#pragma unroll
+      for (int u = 0; u < KM; u++) pru1[u] = b.PR[(size_t)u * ld + j1];
+    }
     __syncthreads();
     stamp(q, 5);
     MinIdx m = minidx_identity();
-    auto row_update = [&](double x, const double* pru) -> double {
-#pragma unroll
-      for (int u = 0; u < KM; u++) {
-        const double upd = (p == s_pu[u]) ? pru[u] : __dsub_rn(x, __dmul_rn(s_fp[u], pru[u]));
-        x = (u < s) ? upd : x;
-      }
-      return x;
-    };
-    if (own_col) {
-      double pr = 0.0, z = 0.0;
-      if (gid < C) {
-        const double xx = row_update(x0, pru0);
-        if (xx == 1.2345e300) stamp(q, 0);
-        stamp(q, 6);
-        pr = __ddiv_rn(xx, piv);
-        z = __dsub_rn(r0j0, __dmul_rn(f0, pr));
-        if (gid < C - 1 && z < 0.0) m = MinIdx{z, gid};
-      }
-      b.PR[(size_t)s * ld + gid] = pr;
-      b.row0[gid] = z;
-    }
-    for (int j = gid + nthr; j < ld; j += nthr) {  // only when the cluster has fewer threads than columns
+    auto finish_col = [&](int j, double x, double r0j, const double* pru) {
       double pr = 0.0, z = 0.0;
       if (j < C) {
-        double pru[KM];
 #pragma unroll
-        for (int u = 0; u < KM; u++) pru[u] = b.PR[(size_t)u * ld + j];
-        pr = __ddiv_rn(row_update(TAT(T, ld, p, j), pru), piv);
-        z = __dsub_rn(b.row0[j], __dmul_rn(f0, pr));
+        for (int u = 0; u < KM; u++) {
+          const double upd = (p == s_pu[u]) ? pru[u] : __dsub_rn(x, __dmul_rn(s_fp[u], pru[u]));
+          x = (u < s) ? upd : x;
+        }
+        pr = __ddiv_rn(x, piv);
+        z = __dsub_rn(r0j, __dmul_rn(f0, pr));
         if (j < C - 1 && z < 0.0) m = minidx_combine(m, MinIdx{z, j});
       }
       b.PR[(size_t)s * ld + j] = pr;
       b.row0[j] = z;
+    };
+    if (own_c0) finish_col(j0, x0, r00, pru0);
+    if (own_c1) finish_col(j1, x1, r01, pru1);
+    for (int j = gid + 2 * nthr; j < ld; j += nthr) {  // only for very wide tableaux
+      double pru[KM];
+#pragma unroll
+      for (int u = 0; u < KM; u++) pru[u] = (j < C) ? b.PR[(size_t)u * ld + j] : 0.0;
+      finish_col(j, (j < C) ? TAT(T, ld, p, j) : 0.0, (j < C) ? b.row0[j] : 0.0, pru);
     }
     {
       const double prc = __ddiv_rn(rhsp, piv);
@@ -666,24 +678,9 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
       for (int i = gid + nthr; i < R; i += nthr)
         rhs_next[i] = (i == p) ? prc : __dsub_rn(rhs[i], __dmul_rn(b.F[(size_t)i * KM + s], prc));
     }
-    stamp(q, 7);
-    m = block_minidx_1sync(m, smB[buf]);
-    if (tid == 0) {
-      s_b[buf].val = m.v;
-      s_b[buf].idx = m.i;
-      s_pu[s] = p;
-    }
-    __threadfence();
-    cluster.sync();
-    if (tid < 32) {
-      MinIdx r = minidx_identity();
-      if (tid < ncta) {
-        const ClusterSlot* peer = cluster.map_shared_rank(&s_b[buf], tid);
-        r = MinIdx{peer->val, peer->idx};
-      }
-      r = warp_minidx(r);
-      if (tid == 0) s_bi[1] = (r.i == INT_MAX) ? -1 : r.i;
-    }
+    stamp(q, 6);
+    cluster_publish(cluster, slotB[buf], ncta, crank, m, 0.0);
+    if (tid == 0) s_pu[s] = p;
     if (gid == 0) {
       b.pidx[s] = p;
       if (v.log && npiv < v.log_cap) {
@@ -694,12 +691,16 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
       st->pivot = piv;
       st->leave = p;
     }
-    __syncthreads();
-    e = s_bi[1];
+    cluster.sync();
+    stamp(q, 7);
+    MinIdx rb;
+    double dummy;
+    cluster_collect(slotB[buf], total_warps, &rb, &dummy, s_i, s_d);
+    e = (rb.i == INT_MAX) ? -1 : rb.i;
     npiv++;
     cur ^= 1;
   }
-  // peers may still be reading this CTA's slots: leave together
+  // peers may still be writing into / reading from this CTA's shared memory: leave together
   cluster.sync();
   if (gid == 0) {
     st->group_base = npiv0;
@@ -911,8 +912,8 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
     if (cluster_ctas > 8) {
       cudaError_t ce = cudaFuncSetAttribute(k_blk_select_cluster<8, 512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_blk_select_cluster<16, 512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_blk_select_cluster<8, 1024>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_blk_select_cluster<16, 1024>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_blk_select_cluster<8, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_blk_select_cluster<16, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       if (ce != cudaSuccess) {
         cudaGetLastError();
         cluster_ctas = 8;
@@ -922,7 +923,7 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
   auto launch_cluster = [&](int ncta) -> cudaError_t {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta);
-    static const int nt = (getenv("LPR_BLK_CLUSTER_THREADS") ? atoi(getenv("LPR_BLK_CLUSTER_THREADS")) : 512) >= 1024 ? 1024 : 512;
+    static const int nt = (getenv("LPR_BLK_CLUSTER_THREADS") ? atoi(getenv("LPR_BLK_CLUSTER_THREADS")) : 256) <= 256 ? 256 : 512;
     cfg.blockDim = dim3(nt);
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[2];
@@ -935,9 +936,9 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
     cfg.attrs = attr;
     static const int pdl = getenv("LPR_PDL") ? atoi(getenv("LPR_PDL")) : 1;
     cfg.numAttrs = pdl ? 2 : 1;
-    if (nt == 1024)
-      return (K <= 8) ? cudaLaunchKernelEx(&cfg, k_blk_select_cluster<8, 1024>, b, K)
-                      : cudaLaunchKernelEx(&cfg, k_blk_select_cluster<16, 1024>, b, K);
+    if (nt == 256)
+      return (K <= 8) ? cudaLaunchKernelEx(&cfg, k_blk_select_cluster<8, 256>, b, K)
+                      : cudaLaunchKernelEx(&cfg, k_blk_select_cluster<16, 256>, b, K);
     return (K <= 8) ? cudaLaunchKernelEx(&cfg, k_blk_select_cluster<8, 512>, b, K)
                     : cudaLaunchKernelEx(&cfg, k_blk_select_cluster<16, 512>, b, K);
   };
@@ -1035,7 +1036,7 @@ int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_
       fprintf(stderr, "[blk timing] pivot %2d:", q);
       for (int k = 1; k < 8; k++) fprintf(stderr, " %5lld", hd[q * 8 + k] - hd[q * 8 + k - 1]);
       if (q + 1 < K && hd[(q + 1) * 8]) fprintf(stderr, " | next %5lld", hd[(q + 1) * 8] - hd[q * 8 + 7]);
-      fprintf(stderr, "  ns (stageA loadsChainA ratioStoreA reduceSyncDsmemA stageB loadsChainB divStoreB)\n");
+      fprintf(stderr, "  ns (stageA chainRatioA publishSyncA collectA stageB finishB publishSyncB)\n");
     }
     cudaFree(d_dbg);
   }
