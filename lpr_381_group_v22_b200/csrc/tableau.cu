@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace lpr {
@@ -485,6 +486,31 @@ __global__ void k_build_primal(double* T, int ld, int m, int n, const double* ob
   }
 }
 
+// same constructor, but the coefficient block was copied straight from the host into T[1.., 0..n) (no
+// staging buffer): negate ">=" rows in place and fill everything around the block
+__global__ void k_build_primal_inplace(double* T, int ld, int m, int n, const double* obj, const int* relation,
+                                       const double* rhs, int is_max, int* basis) {
+  const int C = n + m + 1;
+  const int row = blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ld; j += gridDim.x * blockDim.x) {
+    if (row == 0) {
+      TAT(T, ld, 0, j) = (j < n) ? (is_max ? -obj[j] : obj[j]) : 0.0;
+      continue;
+    }
+    const int i = row - 1;
+    const bool ge = relation && relation[i] == LPR_REL_GE;
+    if (j < n) {
+      if (ge) TAT(T, ld, row, j) = -TAT(T, ld, row, j);
+    } else {
+      double val = 0.0;
+      if (j == n + i) val = 1.0;
+      else if (j == C - 1) val = ge ? -rhs[i] : rhs[i];
+      TAT(T, ld, row, j) = val;
+    }
+    if (j == 0) basis[i] = n + i;
+  }
+}
+
 // ExtractSolution PrimalSimplexSolver.cs:213-252: one warp per decision column
 __global__ void k_extract_solution(TabView v, int n, double* x) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -623,6 +649,39 @@ __global__ void __launch_bounds__(kSelThreads) k_cut_flags(TabView v, int* out) 
 // =============================================================================================
 // host side
 // =============================================================================================
+// Small per-process cache of tableau-sized device buffers: solver objects are created and destroyed per
+// Solve() by the host API, and cudaMalloc/cudaFree of 400 MB cost milliseconds to tens of milliseconds.
+struct CachedBuf {
+  int device;
+  size_t bytes;
+  double* ptr;
+};
+static std::vector<CachedBuf> g_buf_cache;
+static std::mutex g_buf_mu;
+static size_t cache_limit_bytes() {
+  static const size_t lim = (size_t)std::max(0, env_int("LPR_CACHE_MB", 2048)) << 20;
+  return lim;
+}
+static double* cache_take(int device, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  for (size_t i = 0; i < g_buf_cache.size(); i++)
+    if (g_buf_cache[i].device == device && g_buf_cache[i].bytes == bytes) {
+      double* p = g_buf_cache[i].ptr;
+      g_buf_cache.erase(g_buf_cache.begin() + i);
+      return p;
+    }
+  return nullptr;
+}
+static bool cache_give(int device, size_t bytes, double* ptr) {
+  if (!ptr || bytes < (8u << 20)) return false;  // only worth it for big buffers
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  size_t held = 0;
+  for (auto& c : g_buf_cache) held += c.bytes;
+  if (held + bytes > cache_limit_bytes()) return false;
+  g_buf_cache.push_back(CachedBuf{device, bytes, ptr});
+  return true;
+}
+
 int tab_alloc(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab** out) {
   if (!out) return fail(LPR_E_BADARG, "out is null");
   *out = nullptr;
@@ -647,7 +706,8 @@ int tab_alloc(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab*
                 cudaGetErrorString(e));                                                          \
   }
   TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  TRY(cudaMalloc(&h->T, bytes));
+  h->T = cache_take(device, bytes);
+  if (!h->T) TRY(cudaMalloc(&h->T, bytes));
   TRY(cudaMalloc(&h->col[0], sizeof(double) * h->Rcap));
   TRY(cudaMalloc(&h->col[1], sizeof(double) * h->Rcap));
   TRY(cudaMalloc(&h->rhs, sizeof(double) * h->Rcap));
@@ -927,7 +987,7 @@ int lpr_tab_destroy(lpr_tab* h) {
   if (!h) return LPR_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->T);
+  if (!cache_give(h->device, (size_t)h->Rcap * h->ld * sizeof(double), h->T)) cudaFree(h->T);
   cudaFree(h->T2);
   cudaFree(h->col[0]);
   cudaFree(h->col[1]);
@@ -1010,22 +1070,32 @@ int lpr_tab_create_primal(int device, int n, int m, const double* objective, con
     return fail(LPR_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); \
   }
   TRY(cudaMalloc(&d_obj, sizeof(double) * n));
-  TRY(cudaMalloc(&d_coef, sizeof(double) * (size_t)m * coef_stride));
   TRY(cudaMalloc(&d_rhs, sizeof(double) * m));
   TRY(cudaMemcpyAsync(d_obj, objective, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-  TRY(cudaMemcpyAsync(d_coef, coef, sizeof(double) * (size_t)m * coef_stride, cudaMemcpyHostToDevice, h->stream));
   TRY(cudaMemcpyAsync(d_rhs, rhs, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
-  if (coef_count) {
-    TRY(cudaMalloc(&d_cnt, sizeof(int) * m));
-    TRY(cudaMemcpyAsync(d_cnt, coef_count, sizeof(int) * m, cudaMemcpyHostToDevice, h->stream));
-  }
   if (relation) {
     TRY(cudaMalloc(&d_rel, sizeof(int) * m));
     TRY(cudaMemcpyAsync(d_rel, relation, sizeof(int) * m, cudaMemcpyHostToDevice, h->stream));
   }
+  bool full_rows = coef_stride >= n;
+  if (coef_count)
+    for (int i = 0; i < m && full_rows; i++) full_rows = coef_count[i] >= n;
   dim3 grid(std::max(1, std::min(64, (h->ld + 255) / 256)), m + 1);
-  k_build_primal<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, d_obj, d_coef, coef_stride, d_cnt, d_rel, d_rhs,
-                                              is_max, h->basis);
+  if (full_rows) {
+    // every row provides its n coefficients: DMA them straight into the tableau (H2D once, no staging)
+    TRY(cudaMemcpy2DAsync(h->T + h->ld, sizeof(double) * h->ld, coef, sizeof(double) * coef_stride, sizeof(double) * n, m,
+                          cudaMemcpyHostToDevice, h->stream));
+    k_build_primal_inplace<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, d_obj, d_rel, d_rhs, is_max, h->basis);
+  } else {
+    TRY(cudaMalloc(&d_coef, sizeof(double) * (size_t)m * coef_stride));
+    TRY(cudaMemcpyAsync(d_coef, coef, sizeof(double) * (size_t)m * coef_stride, cudaMemcpyHostToDevice, h->stream));
+    if (coef_count) {
+      TRY(cudaMalloc(&d_cnt, sizeof(int) * m));
+      TRY(cudaMemcpyAsync(d_cnt, coef_count, sizeof(int) * m, cudaMemcpyHostToDevice, h->stream));
+    }
+    k_build_primal<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, d_obj, d_coef, coef_stride, d_cnt, d_rel, d_rhs,
+                                                is_max, h->basis);
+  }
   count_launch();
   TRY(cudaGetLastError());
   TRY(cudaStreamSynchronize(h->stream));

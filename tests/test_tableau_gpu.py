@@ -385,3 +385,22 @@ print(json.dumps(out))
     assert res.returncode == 0, res.stderr[-2000:]
     out = json.loads(res.stdout.strip().splitlines()[-1])
     assert out == {"-1": True, "7": True, "17": True}, out
+
+
+def test_build_paths_full_rows_and_cache_reuse():
+    """the fast constructor path (coefficient block DMA'd straight into the tableau) and the buffer cache"""
+    rng = np.random.default_rng(11)
+    n, m = 40, 30
+    obj = rng.normal(size=n).round(3).tolist()
+    for trial in range(3):  # repeated create/destroy of same-size tableaux reuses cached device buffers
+        cons = [L.Constraint(rng.normal(size=n).round(3).tolist(), ["<=", ">=", "="][i % 3], float(rng.normal()))
+                for i in range(m)]
+        for is_max in (True, False):
+            with L.DeviceTableau.from_model(obj, cons, is_max) as t:
+                T0, b0 = O.primal_build(obj, oracle_cons(cons), is_max)
+                assert_bit_equal(t.read(), T0)
+                assert t.basis.tolist() == b0.tolist()
+    big = rng.normal(size=(600, 2200))  # > 8 MB: goes through the cache on destroy
+    for _ in range(3):
+        with L.DeviceTableau.from_host(big) as t:
+            assert_bit_equal(t.read(), big)
