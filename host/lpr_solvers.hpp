@@ -1,0 +1,313 @@
+// host/lpr_solvers.hpp -- C++ host-side mirror of the reference's solver classes over the C ABI.
+//
+// The reference is compiled C# (no .NET toolchain in this image), so the host layer above liblprb200 is
+// also provided in C++: same class names, member names, argument meaning and error behaviour as
+//   Simplex/PrimalSimplexSolver.cs, Simplex/RevisedPrimalSimplexSolver.cs, Simplex/PrimalSimplexSolver2.cs,
+//   Simplex/DualSimplex.cs, IntegerProgramming/CuttingPlaneSolver.cs, IntegerProgramming/BranchAndBoundAdapter.cs
+//   and the knapsack classes of Program.cs:430-471.
+// Header only; link with -llprb200.  No arithmetic happens here: every pivot runs on the GPU.
+#pragma once
+#include <cmath>
+#include <array>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../include/lprb200.h"
+
+namespace LPR_381_Group_V22 {
+
+struct InvalidOperationException : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct ArgumentException : std::invalid_argument {
+  using std::invalid_argument::invalid_argument;
+};
+
+inline void Check(int rc) {
+  if (rc != LPR_OK) throw InvalidOperationException(std::string("liblprb200: ") + lpr_last_error());
+}
+
+namespace IO {
+// InputFileParser.Constraint (IO/InputFileParser.cs:70-82)
+struct Constraint {
+  std::vector<double> Coefficients;
+  std::string Relation;
+  double RHS;
+};
+}  // namespace IO
+
+namespace Simplex {
+
+// Simplex/PrimalSimplexSolver.cs
+class PrimalSimplexSolver {
+ public:
+  double FinalZ = 0.0;
+  std::vector<double> SolutionVector;  // empty == null (unbounded / not solved)
+  bool HasSolution = false;
+  std::vector<double> FinalTableau;    // rows x cols, row-major; empty == null
+  int Rows = 0, Cols = 0;
+  int Status = LPR_RUNNING;
+  std::vector<std::pair<int, int>> PivotLog;  // (row, col)
+
+  PrimalSimplexSolver(const std::vector<double>& objective, const std::vector<IO::Constraint>& constraints,
+                      bool isMaximization = true)
+      : n_((int)objective.size()), m_((int)constraints.size()) {
+    int stride = n_;
+    for (auto& c : constraints) stride = std::max<int>(stride, (int)c.Coefficients.size());
+    std::vector<double> coef((size_t)m_ * stride, 0.0), rhs(m_);
+    std::vector<int> cnt(m_), rel(m_);
+    for (int i = 0; i < m_; i++) {
+      const auto& c = constraints[i];
+      cnt[i] = (int)c.Coefficients.size();
+      for (int j = 0; j < cnt[i]; j++) coef[(size_t)i * stride + j] = c.Coefficients[j];
+      rel[i] = c.Relation == ">=" ? LPR_REL_GE : (c.Relation == "=" ? LPR_REL_EQ : LPR_REL_LE);
+      rhs[i] = c.RHS;
+    }
+    Check(lpr_tab_create_primal(0, n_, m_, objective.data(), coef.data(), stride, cnt.data(), rel.data(), rhs.data(),
+                                isMaximization ? 1 : 0, &tab_));
+    Rows = m_ + 1;
+    Cols = n_ + m_ + 1;
+  }
+  ~PrimalSimplexSolver() { lpr_tab_destroy(tab_); }
+  PrimalSimplexSolver(const PrimalSimplexSolver&) = delete;
+  PrimalSimplexSolver& operator=(const PrimalSimplexSolver&) = delete;
+
+  void Solve() {  // :102-150
+    std::vector<int> log(2 * 65536);
+    int64_t np = 0;
+    Check(lpr_tab_solve(tab_, LPR_RULE_PRIMAL, -1, 0, &Status, &np, log.data(), 65536));
+    for (int64_t k = 0; k < np && k < 65536; k++) PivotLog.emplace_back(log[2 * k], log[2 * k + 1]);
+    FinalTableau = GetFinalTableau();
+    if (Status == LPR_OPTIMAL) {  // :110-126
+      Check(lpr_tab_objective(tab_, &FinalZ));
+      SolutionVector.assign(n_, 0.0);
+      Check(lpr_tab_extract_solution(tab_, n_, SolutionVector.data()));
+      HasSolution = true;
+    }  // unbounded (:129-135): FinalZ stays 0, SolutionVector stays null
+  }
+  std::vector<double> GetFinalTableau() const {  // :269-273
+    std::vector<double> t((size_t)Rows * Cols);
+    Check(lpr_tab_read(tab_, t.data()));
+    return t;
+  }
+  std::vector<int> BasicVariables() const {  // :275-278
+    std::vector<int> b(m_);
+    Check(lpr_tab_get_basis(tab_, b.data()));
+    return b;
+  }
+  int NumVariables() const { return n_; }
+
+ private:
+  int n_, m_;
+  lpr_tab* tab_ = nullptr;
+};
+
+// Simplex/RevisedPrimalSimplexSolver.cs
+class RevisedPrimalSimplexSolver {
+ public:
+  double FinalZ = 0.0;
+  std::vector<double> SolutionVector;
+  std::vector<std::array<int, 3>> PivotLog;  // (leaveRow, enter, leaveVar)
+
+  RevisedPrimalSimplexSolver(const std::vector<double>& objective, const std::vector<IO::Constraint>& constraints,
+                             bool isMinimization)
+      : n_((int)objective.size()), m_((int)constraints.size()) {
+    if (objective.empty()) throw ArgumentException("Objective cannot be null or empty.");
+    if (constraints.empty()) throw ArgumentException("Constraints cannot be null or empty.");
+    std::vector<double> A((size_t)m_ * n_), b(m_);
+    for (int i = 0; i < m_; i++) {
+      if ((int)constraints[i].Coefficients.size() != n_)
+        throw ArgumentException("Constraint " + std::to_string(i + 1) + " has incorrect number of coefficients.");
+      for (int j = 0; j < n_; j++) A[(size_t)i * n_ + j] = constraints[i].Coefficients[j];
+      b[i] = constraints[i].RHS;  // Relation ignored (:55-61)
+    }
+    Check(lpr_rev_create(0, m_, n_, A.data(), b.data(), objective.data(), isMinimization ? 1 : 0, &rev_));
+  }
+  ~RevisedPrimalSimplexSolver() { lpr_rev_destroy(rev_); }
+  RevisedPrimalSimplexSolver(const RevisedPrimalSimplexSolver&) = delete;
+  RevisedPrimalSimplexSolver& operator=(const RevisedPrimalSimplexSolver&) = delete;
+
+  void Solve() {  // :82-251; exceptions :91, :179, :267
+    int st = 0;
+    int64_t nit = 0;
+    std::vector<int> log(3 * 65536);
+    Check(lpr_rev_solve(rev_, -1, 0, &st, &nit, log.data(), 65536));
+    for (int64_t k = 0; k < nit && k < 65536; k++) PivotLog.push_back({log[3 * k], log[3 * k + 1], log[3 * k + 2]});
+    if (st == LPR_INFEASIBLE) throw std::runtime_error("Infeasible basis (negative basic value).");
+    if (st == LPR_UNBOUNDED) throw std::runtime_error("Unbounded problem (no positive component in direction).");
+    if (st == LPR_PIVOT_TOO_SMALL) throw std::runtime_error("Pivot too small.");
+    SolutionVector.assign(n_, 0.0);
+    Check(lpr_rev_read_x(rev_, SolutionVector.data()));
+    Check(lpr_rev_read_z(rev_, &FinalZ));
+  }
+  std::vector<int> BasicVariables() const {
+    std::vector<int> b(m_);
+    Check(lpr_rev_read_basis(rev_, b.data()));
+    return b;
+  }
+  std::vector<double> DualPrices() const {  // y = c_B B^-1 (:93)
+    std::vector<double> y(m_);
+    Check(lpr_rev_read_y(rev_, y.data()));
+    return y;
+  }
+
+ private:
+  int n_, m_;
+  lpr_rev* rev_ = nullptr;
+};
+
+// shared by PrimalSimplexSolver2 / DualSimplexSolver: (objectiveRow, constraintRows) <-> device tableau
+inline lpr_tab* UploadRows(const std::vector<double>& obj, const std::vector<std::vector<double>>& rows, int headroom) {
+  if (rows.empty()) throw ArgumentException("No constraint rows.");
+  const int w = (int)obj.size();
+  for (auto& r : rows)
+    if ((int)r.size() != w) throw ArgumentException("All rows (obj & constraints) must have the same length.");
+  std::vector<double> T;
+  T.insert(T.end(), obj.begin(), obj.end());
+  for (auto& r : rows) T.insert(T.end(), r.begin(), r.end());
+  lpr_tab* h = nullptr;
+  Check(lpr_tab_create(0, (int)rows.size() + 1, w, (int)rows.size() + 1 + headroom, w, T.data(), &h));
+  return h;
+}
+inline void DownloadRows(lpr_tab* h, std::vector<double>& obj, std::vector<std::vector<double>>& rows) {
+  int R = 0, C = 0, ld = 0;
+  Check(lpr_tab_dims(h, &R, &C, &ld));
+  std::vector<double> T((size_t)R * C);
+  Check(lpr_tab_read(h, T.data()));
+  obj.assign(T.begin(), T.begin() + C);
+  rows.resize(R - 1);
+  for (int i = 1; i < R; i++) rows[i - 1].assign(T.begin() + (size_t)i * C, T.begin() + (size_t)(i + 1) * C);
+}
+
+// Simplex/PrimalSimplexSolver2.cs
+class PrimalSimplexSolver2 {
+ public:
+  double FinalZ = 0.0;
+  PrimalSimplexSolver2(const std::vector<double>& objectiveRow, const std::vector<std::vector<double>>& constraintRows)
+      : tab_(UploadRows(objectiveRow, constraintRows, 0)) {}
+  ~PrimalSimplexSolver2() { lpr_tab_destroy(tab_); }
+  bool Solve(int maxIters = 10000, bool printSteps = false) {  // :46-97
+    int st = 0;
+    int64_t np = 0;
+    Check(lpr_tab_solve(tab_, LPR_RULE_PRIMAL2, maxIters, printSteps ? 1 : 0, &st, &np, nullptr, 0));
+    if (st == LPR_PIVOT_TOO_SMALL) throw InvalidOperationException("Pivot too small/zero.");
+    optimal_ = (st == LPR_OPTIMAL);
+    if (optimal_) Check(lpr_tab_objective(tab_, &FinalZ));
+    return optimal_;
+  }
+  void GetRows(std::vector<double>& obj, std::vector<std::vector<double>>& rows, bool solveIfNeeded = true) {
+    if (!optimal_ && solveIfNeeded && !Solve())
+      throw InvalidOperationException("Could not reach an optimal tableau (unbounded or infeasible).");
+    DownloadRows(tab_, obj, rows);
+  }
+
+ private:
+  lpr_tab* tab_;
+  bool optimal_ = false;
+};
+
+// Simplex/DualSimplex.cs (global namespace in the reference)
+class DualSimplexSolver {
+ public:
+  // mutates objectiveRow / constraintRows in place, like the reference
+  bool Solve(std::vector<double>& objectiveRow, std::vector<std::vector<double>>& constraintRows, int maxIters = 10000,
+             bool printSteps = true) {
+    lpr_tab* h = UploadRows(objectiveRow, constraintRows, 0);
+    int st = 0;
+    int64_t np = 0;
+    int rc = lpr_tab_solve(h, LPR_RULE_DUAL, maxIters, printSteps ? 1 : 0, &st, &np, nullptr, 0);
+    if (rc == LPR_OK) DownloadRows(h, objectiveRow, constraintRows);
+    lpr_tab_destroy(h);
+    Check(rc);
+    if (st == LPR_PIVOT_TOO_SMALL) throw InvalidOperationException("Pivot too small/zero.");
+    return st == LPR_OPTIMAL;
+  }
+  static bool AnyNegativeRhs(const std::vector<std::vector<double>>& rows) {  // :180-185
+    for (auto& r : rows)
+      if (!r.empty() && r.back() < -1e-9) return true;
+    return false;
+  }
+};
+
+}  // namespace Simplex
+
+namespace IntegerProgramming {
+
+// IntegerProgramming/CuttingPlaneSolver.cs:64-229 (in place; cut rows are appended)
+class CuttingPlaneSolver {
+ public:
+  int Status = LPR_RUNNING;
+  void CuttingPlaneSolution(std::vector<double>& objectiveRow, std::vector<std::vector<double>>& constraintRows,
+                            int maxCuts = -1) {
+    lpr_tab* h = Simplex::UploadRows(objectiveRow, constraintRows, maxCuts < 0 ? 64 : maxCuts + 1);
+    int ncuts = 0;
+    int rc = lpr_tab_cutting_plane(h, maxCuts, &Status, &ncuts, nullptr, 0);
+    if (rc == LPR_OK) Simplex::DownloadRows(h, objectiveRow, constraintRows);
+    lpr_tab_destroy(h);
+    Check(rc);
+  }
+};
+
+// IntegerProgramming/BranchAndBoundAdapter.cs:9-24
+struct BranchAndBoundAdapter {
+  static std::pair<std::vector<double>, double> SolveFromPrimal(const Simplex::PrimalSimplexSolver& primal,
+                                                                bool enablePruning = false, bool isMin = false,
+                                                                int64_t maxNodes = 20 /* reference cap :1038 */) {
+    (void)isMin;  // ignored by the reference as well
+    if (primal.FinalTableau.empty()) throw InvalidOperationException("Primal simplex has not been solved yet.");
+    const int n = primal.HasSolution ? (int)primal.SolutionVector.size() : std::max(1, primal.Cols - 1);
+    std::vector<double> x(n);
+    double z = 0;
+    int has = 0, st = 0;
+    int64_t nodes = 0, piv = 0;
+    Check(lpr_bb_solve(0, primal.Rows, primal.Cols, primal.FinalTableau.data(), n, enablePruning ? 1 : 0, maxNodes,
+                       x.data(), &z, &has, &nodes, &piv, nullptr, nullptr, 0, &st));
+    if (!has) return {std::vector<double>(), -std::numeric_limits<double>::infinity()};
+    return {x, z};
+  }
+};
+
+// Program.cs:444-463 (the class is missing from the reference; contract from the call site)
+struct KnapsackItem {
+  int Id;
+  double Value, Weight;
+};
+class KnapsackBranchBoundSimplex {
+ public:
+  KnapsackBranchBoundSimplex(int capacity, std::vector<double> weights, std::vector<double> values)
+      : cap_(capacity), w_(std::move(weights)), v_(std::move(values)), chosen_(w_.size(), 0) {}
+  double Solve() {
+    int st = 0;
+    Check(lpr_knap_solve(0, cap_, (int)w_.size(), w_.data(), v_.data(), -1, &best_, chosen_.data(), &nodes_, &st));
+    return best_;
+  }
+  std::vector<KnapsackItem> GetSelectedItemsOriginal() const {
+    std::vector<KnapsackItem> out;
+    for (size_t i = 0; i < w_.size(); i++)
+      if (chosen_[i]) out.push_back({(int)i, v_[i], w_[i]});
+    return out;
+  }
+  int64_t Nodes() const { return nodes_; }
+
+ private:
+  double cap_;
+  std::vector<double> w_, v_;
+  std::vector<uint8_t> chosen_;
+  double best_ = 0;
+  int64_t nodes_ = 0;
+};
+struct KnapsackBranchBoundSolver {  // Program.cs:468 DP arbiter
+  static double Solve(int capacity, const std::vector<int>& weights, const std::vector<int>& values) {
+    double best = 0;
+    std::vector<uint8_t> ch(weights.size());
+    Check(lpr_knap_dp(0, capacity, (int)weights.size(), weights.data(), values.data(), &best, ch.data()));
+    return best;
+  }
+};
+
+}  // namespace IntegerProgramming
+}  // namespace LPR_381_Group_V22

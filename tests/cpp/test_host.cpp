@@ -1,0 +1,89 @@
+// C++ host-mirror smoke test: the reference's fixtures through host/lpr_solvers.hpp (Program.cs menu paths 1, 2,
+// 3, 5 and the cutting plane), checked against the known answers of SURVEY.md Appendix C.  Needs a GPU to RUN;
+// tests/test_cpp_host.py compiles and links it everywhere and runs it only under -m gpu.
+#include <array>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../host/lpr_solvers.hpp"
+
+using namespace LPR_381_Group_V22;
+using IO::Constraint;
+
+#define REQUIRE(cond)                                                   \
+  do {                                                                  \
+    if (!(cond)) {                                                      \
+      std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+      return 1;                                                         \
+    }                                                                   \
+  } while (0)
+
+static void add_cli_bound_rows(int n, std::vector<Constraint>& cons) {  // Program.cs:114-124
+  for (int i = 0; i < n; i++) {
+    std::vector<double> co(n + 3, 0.0);
+    co[i] = 1;
+    co[n + 1] = 1;
+    cons.push_back({co, "<=", 1.0});
+  }
+}
+
+int main() {
+  // data/TextFile.txt through menu option 1 / 3
+  std::vector<double> obj = {2, 3, 3, 5, 2, 4};
+  std::vector<Constraint> cons = {{{11, 8, 6, 14, 10, 10}, "<=", 40}};
+  add_cli_bound_rows(6, cons);
+  Simplex::PrimalSimplexSolver primal(obj, cons);
+  primal.Solve();
+  REQUIRE(primal.Status == LPR_OPTIMAL);
+  REQUIRE(primal.PivotLog.size() == 6 && primal.PivotLog[0] == std::make_pair(5, 3) && primal.PivotLog[5] == std::make_pair(1, 4));
+  REQUIRE(primal.FinalZ == 0x1.ecccccccccccdp+3);
+  REQUIRE((primal.SolutionVector == std::vector<double>{0, 1, 1, 1, 0.2, 1}));
+  REQUIRE((primal.BasicVariables() == std::vector<int>{4, 7, 1, 2, 3, 11, 5}));
+  auto bb = IntegerProgramming::BranchAndBoundAdapter::SolveFromPrimal(primal, false, false);
+  REQUIRE(bb.second == 15.0 && (bb.first == std::vector<double>{0, 1, 1, 1, 0, 1}));
+  // cutting plane on the final tableau (Appendix C4)
+  {
+    std::vector<double> o(primal.FinalTableau.begin(), primal.FinalTableau.begin() + primal.Cols);
+    std::vector<std::vector<double>> rows;
+    for (int i = 1; i < primal.Rows; i++)
+      rows.emplace_back(primal.FinalTableau.begin() + (size_t)i * primal.Cols, primal.FinalTableau.begin() + (size_t)(i + 1) * primal.Cols);
+    IntegerProgramming::CuttingPlaneSolver cp;
+    cp.CuttingPlaneSolution(o, rows);
+    REQUIRE(cp.Status == LPR_OPTIMAL && rows.size() == 8 && o.back() == 15.0);
+  }
+  // README model through menu option 2 (revised; '>=' ignored)
+  {
+    std::vector<Constraint> c2 = {{{1, 2, 3}, "<=", 10}, {{3, 2, 1}, ">=", 15}};
+    Simplex::RevisedPrimalSimplexSolver rev({2, 3, 4}, c2, false);
+    rev.Solve();
+    REQUIRE(rev.FinalZ == 16.25 && (rev.SolutionVector == std::vector<double>{4.375, 0, 1.875}));
+    REQUIRE((rev.BasicVariables() == std::vector<int>{2, 0}));
+    bool threw = false;
+    try {
+      Simplex::RevisedPrimalSimplexSolver bad({1.0, 0.0}, {{{-1.0, 1.0}, "<=", 1.0}}, false);
+      bad.Solve();
+    } catch (const std::runtime_error& ex) {
+      threw = std::string(ex.what()).find("Unbounded problem") != std::string::npos;
+    }
+    REQUIRE(threw);
+  }
+  // knapsack, Program.cs:433-470
+  {
+    IntegerProgramming::KnapsackBranchBoundSimplex ks(40, {11, 8, 6, 14, 10, 10}, {2, 3, 3, 5, 2, 4});
+    const double best = ks.Solve();
+    const double dp = IntegerProgramming::KnapsackBranchBoundSolver::Solve(40, {11, 8, 6, 14, 10, 10}, {2, 3, 3, 5, 2, 4});
+    REQUIRE(best == 15.0 && std::fabs(dp - best) < 1e-6);
+    auto items = ks.GetSelectedItemsOriginal();
+    REQUIRE(items.size() == 4 && items[0].Id == 1 && items[3].Id == 5);
+  }
+  // dual simplex in place
+  {
+    std::vector<double> o = {1, 2, 3, 0, 0, 0, 0};
+    std::vector<std::vector<double>> rows = {{-1, -2, -1, 1, 0, 0, -2}, {-1, -1, -3, 0, 1, 0, -3}, {-2, -1, -1, 0, 0, 1, -4}};
+    Simplex::DualSimplexSolver d;
+    REQUIRE(d.Solve(o, rows, 10000, true));
+    REQUIRE(!Simplex::DualSimplexSolver::AnyNegativeRhs(rows));
+  }
+  std::printf("cpp host mirror: all checks passed\n");
+  return 0;
+}
