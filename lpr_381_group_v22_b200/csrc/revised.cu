@@ -42,6 +42,7 @@ struct RevView {
   double* y;         // m
   double* rc;        // n
   double* u;         // m
+  double* ekey;      // n+m : entering-candidate keys (k_enter scratch)
   double* ab;        // 2*m interleaved (a_e[i], b[i])
   double* ecoef;     // m : eta column (1/piv at r, -u_i/piv elsewhere)
   double* brow;      // ldB : copy of row r of B^-1 before the update
@@ -59,10 +60,23 @@ struct RevView {
 constexpr int kT = 256;
 constexpr double kInfD = __builtin_huge_val();
 
+// streaming 128-bit load that does not allocate in L1 (the small vectors re-read by every thread stay there)
+__device__ __forceinline__ double2 ld_stream2(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+// PDL: wait for the producer kernel, then let the consumer start launching (no-ops without the attribute)
+__device__ __forceinline__ void rev_pdl() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- generic (value,index) helpers are in common.cuh ------------------------------------------
 
 // k_price: grid (colTiles, PS).  Thread owns one double2 column chunk and walks its row range.
 __global__ void __launch_bounds__(kT) k_price(RevView v) {
+  rev_pdl();
   const RevState* st = v.st;
   if (st->status != LPR_RUNNING) return;
   const int ldv = v.ldA >> 1;
@@ -97,30 +111,40 @@ __global__ void __launch_bounds__(kT) k_price(RevView v) {
   reinterpret_cast<double2*>(v.ppart)[(size_t)rs * ldv + chunk] = acc;
 }
 
+// fixed-order sum of the row-split partials with the loads batched 8 at a time
+__device__ __forceinline__ double sum_partials(const double* part, int splits, size_t stride, int j) {
+  double s = 0.0;
+  for (int r0 = 0; r0 < splits; r0 += 8) {
+    double t[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) t[q] = (r0 + q < splits) ? part[(size_t)(r0 + q) * stride + j] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (r0 + q < splits) s = __dadd_rn(s, t[q]);
+  }
+  return s;
+}
+
 __global__ void __launch_bounds__(kT) k_rc(RevView v) {
+  rev_pdl();
   if (v.st->status != LPR_RUNNING) return;
   const int j = blockIdx.x * kT + threadIdx.x;
   if (j >= v.n) return;
-  double s = 0.0;
-  for (int rs = 0; rs < v.PS; rs++) s = __dadd_rn(s, v.ppart[(size_t)rs * v.ldA + j]);
-  v.rc[j] = __dsub_rn(v.c[j], s);  // :98
+  v.rc[j] = __dsub_rn(v.c[j], sum_partials(v.ppart, v.PS, v.ldA, j));  // :98
 }
 
 __global__ void __launch_bounds__(kT) k_y_force(RevView v) {
   const int j = blockIdx.x * kT + threadIdx.x;
   if (j >= v.m) return;
-  double s = 0.0;
-  for (int rs = 0; rs < v.YS; rs++) s = __dadd_rn(s, v.ypart[(size_t)rs * v.ldB + j]);
-  v.y[j] = s;
+  v.y[j] = sum_partials(v.ypart, v.YS, v.ldB, j);
 }
 
 __global__ void __launch_bounds__(kT) k_y(RevView v) {
+  rev_pdl();
   if (v.st->status != LPR_RUNNING) return;
   const int j = blockIdx.x * kT + threadIdx.x;
   if (j >= v.m) return;
-  double s = 0.0;
-  for (int rs = 0; rs < v.YS; rs++) s = __dadd_rn(s, v.ypart[(size_t)rs * v.ldB + j]);
-  v.y[j] = s;
+  v.y[j] = sum_partials(v.ypart, v.YS, v.ldB, j);
 }
 
 // hysteresis scan (see tableau.cu block_hyst_min) specialised for "largest rc" (:104-121)
@@ -128,6 +152,7 @@ template <class Cand>
 __device__ int rev_hyst_min(int n, Cand cand, double b0, double eps, MinIdx* sm, int* smi) {
   __shared__ int sh_res;
   MinIdx m = minidx_identity();
+#pragma unroll 8
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     double val;
     if (cand(k, val) && val == val) m = minidx_combine(m, MinIdx{val, k});
@@ -136,6 +161,7 @@ __device__ int rev_hyst_min(int n, Cand cand, double b0, double eps, MinIdx* sm,
   if (m.i == INT_MAX) return -1;
   if (!(m.v < __dsub_rn(b0, eps))) return -1;
   int bad = 0;
+#pragma unroll 8
   for (int k = threadIdx.x; k < m.i; k += blockDim.x) {
     double val;
     if (cand(k, val) && val == val && !(m.v < __dsub_rn(val, eps))) bad++;
@@ -163,21 +189,51 @@ __device__ int rev_hyst_min(int n, Cand cand, double b0, double eps, MinIdx* sm,
 __global__ void __launch_bounds__(1024) k_enter(RevView v) {
   __shared__ MinIdx sm[32];
   __shared__ int smi[32];
+  rev_pdl();
   RevState* st = v.st;
   if (st->status != LPR_RUNNING) return;
   const int n = v.n, m = v.m;
   const double EPS = 1e-9;
+  // candidate keys (-rc for eligible non-basic variables, +inf otherwise) are materialised once into the
+  // u scratch-free `rc`-sized staging area: all loads of a thread are issued before any use
+  double* key = v.ekey;
+  for (int k0 = 0; k0 < n + m; k0 += 1024 * 8) {
+    double r[8];
+    int ib[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int k = k0 + q * 1024 + threadIdx.x;
+      ib[q] = (k < n + m) ? v.isbasic[k] : 1;
+      r[q] = (k < n + m) ? ((k < n) ? v.rc[k] : -v.y[k - n]) : 0.0;  // :100-102 slack rc = -y_k
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int k = k0 + q * 1024 + threadIdx.x;
+      if (k < n + m) key[k] = (!ib[q] && r[q] > EPS) ? -r[q] : kInfD;
+    }
+  }
+  __syncthreads();
   // val = -rc so that "rc > best + EPS" becomes "val < best - EPS"; first candidate always accepted
   int e = rev_hyst_min(n + m, [&](int k, double& val) {
-    if (v.isbasic[k]) return false;
-    double rc = (k < n) ? v.rc[k] : -v.y[k - n];  // :100-102 slack rc = -y_k
-    if (!(rc > EPS)) return false;
-    val = -rc;
-    return true;
+    val = key[k];
+    return val < kInfD;
   }, kInfD, EPS, sm, smi);
   // interleave (a_e, b) for the direction pass; slack columns need no gather
-  if (e >= 0 && e < n)
-    for (int i = threadIdx.x; i < m; i += blockDim.x) v.ab[2 * i] = v.A[(size_t)i * v.ldA + e];
+  if (e >= 0 && e < n) {
+    for (int i0 = 0; i0 < m; i0 += 1024 * 8) {  // strided DRAM gather: 8 independent loads in flight per thread
+      double t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int i = i0 + q * 1024 + threadIdx.x;
+        t[q] = (i < m) ? v.A[(size_t)i * v.ldA + e] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int i = i0 + q * 1024 + threadIdx.x;
+        if (i < m) v.ab[2 * i] = t[q];
+      }
+    }
+  }
   if (threadIdx.x == 0) {
     st->enter = e;
     st->need_final = (e < 0);
@@ -187,6 +243,7 @@ __global__ void __launch_bounds__(1024) k_enter(RevView v) {
 
 // k_dir: one warp per row: u_i = B^-1[i,:] . a_e  and  x_B[i] = B^-1[i,:] . b  (fixed tree)
 __global__ void __launch_bounds__(kT) k_dir(RevView v) {
+  rev_pdl();
   const RevState* st = v.st;
   if (st->status != LPR_RUNNING) return;
   const int e = st->enter;
@@ -229,6 +286,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
   __shared__ MinIdx sm[32];
   __shared__ int smi[32];
   __shared__ int sh_r;
+  rev_pdl();
   RevState* st = v.st;
   if (st->status != LPR_RUNNING) return;
   const int m = v.m, n = v.n;
@@ -238,6 +296,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
   const long long iter = st->iter;
   // :90-91 any x_B < -EPS => "Infeasible basis"
   int neg = 0;
+#pragma unroll 8
   for (int i = tid; i < m; i += blockDim.x)
     if (v.xB[i] < -EPS) neg++;
   neg = block_sum_int(neg, smi);
@@ -256,6 +315,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
   // :153-176 ratio test.  Simple case: the unique minimum is separated from every other ratio
   // by more than the tolerance window; otherwise thread 0 replays the scan literally.
   MinIdx mn = minidx_identity();
+#pragma unroll 8
   for (int i = tid; i < m; i += blockDim.x) {
     double ui = v.u[i];
     if (ui > EPS) {
@@ -272,6 +332,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
     }
   }
   int bad = 0;
+#pragma unroll 8
   for (int i = tid; i < m; i += blockDim.x) {
     double ui = v.u[i];
     if (i != mn.i && ui > EPS) {
@@ -311,9 +372,21 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
     return;
   }
   // eta column :269-272 and a copy of the pivot row of B^-1
-  for (int i = tid; i < m; i += blockDim.x)
-    v.ecoef[i] = (i == r) ? __ddiv_rn(1.0, pivot) : __ddiv_rn(-v.u[i], pivot);
-  for (int j = tid; j < v.ldB; j += blockDim.x) v.brow[j] = (j < m) ? v.Binv[(size_t)r * v.ldB + j] : 0.0;
+  for (int i0 = 0; i0 < v.ldB; i0 += 1024 * 8) {
+    double tu[8], tb[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int i = i0 + q * 1024 + tid;
+      tu[q] = (i < m) ? v.u[i] : 0.0;
+      tb[q] = (i < m) ? v.Binv[(size_t)r * v.ldB + i] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int i = i0 + q * 1024 + tid;
+      if (i < m) v.ecoef[i] = (i == r) ? __ddiv_rn(1.0, pivot) : __ddiv_rn(-tu[q], pivot);
+      if (i < v.ldB) v.brow[i] = tb[q];
+    }
+  }
   if (tid == 0) {
     const int leaveVar = v.basis[r];
     if (v.log && iter < v.log_cap) {
@@ -337,6 +410,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
 // (k ascending, |E_ik| < 1e-9 skipped, accumulation into a zero matrix), and the partial sums of
 // the next dual vector y' = c_B' B^-1' over this CTA's row range.
 __global__ void __launch_bounds__(kT) k_update(RevView v) {
+  rev_pdl();
   const RevState* st = v.st;
   if (!st->do_update || st->status != LPR_RUNNING) return;
   const int r = st->leave_row;
@@ -499,6 +573,7 @@ struct lpr_rev {
   int device = 0, sms = 148;
   cudaStream_t stream = nullptr;
   int m = 0, n = 0, ldA = 0, ldB = 0, PS = 1, YS = 1;
+  double* ekey = nullptr;
   double *A = nullptr, *Binv = nullptr, *b = nullptr, *c = nullptr, *c_orig = nullptr, *cB = nullptr,
          *xB = nullptr, *y = nullptr, *rc = nullptr, *u = nullptr, *ab = nullptr, *ecoef = nullptr,
          *brow = nullptr, *ppart = nullptr, *ypart = nullptr, *x = nullptr, *z = nullptr;
@@ -513,7 +588,7 @@ struct lpr_rev {
   RevView view() const {
     RevView v;
     v.m = m; v.n = n; v.ldA = ldA; v.ldB = ldB; v.A = A; v.Binv = Binv; v.b = b; v.c = c; v.cB = cB;
-    v.xB = xB; v.y = y; v.rc = rc; v.u = u; v.ab = ab; v.ecoef = ecoef; v.brow = brow; v.ppart = ppart;
+    v.xB = xB; v.y = y; v.rc = rc; v.u = u; v.ekey = ekey; v.ab = ab; v.ecoef = ecoef; v.brow = brow; v.ppart = ppart;
     v.ypart = ypart; v.PS = PS; v.YS = YS; v.basis = basis; v.isbasic = isbasic; v.st = st; v.log = log;
     v.log_cap = log_cap;
     static const int dense = getenv("LPR_REV_DENSE") ? atoi(getenv("LPR_REV_DENSE")) : 0;
@@ -562,6 +637,7 @@ static int rev_alloc(int device, int m, int n, lpr_rev** out) {
   TRY(cudaMalloc(&h->y, sizeof(double) * m));
   TRY(cudaMalloc(&h->rc, sizeof(double) * n));
   TRY(cudaMalloc(&h->u, sizeof(double) * m));
+  TRY(cudaMalloc(&h->ekey, sizeof(double) * ((size_t)n + m)));
   TRY(cudaMalloc(&h->ab, sizeof(double) * (2 * (size_t)m + 4)));
   TRY(cudaMalloc(&h->ecoef, sizeof(double) * m));
   TRY(cudaMalloc(&h->brow, sizeof(double) * h->ldB));
@@ -592,6 +668,23 @@ static int rev_ensure_log(lpr_rev* h, long long cap) {
   return LPR_OK;
 }
 
+// launch with the programmatic-stream-serialization attribute (PDL); every kernel of the chain starts with
+// griddepcontrol.wait so correctness does not depend on it
+static bool rev_launch(void (*kernel)(RevView), dim3 grid, int block, cudaStream_t stream, const RevView& v) {
+  static const int pdl = getenv("LPR_PDL") ? atoi(getenv("LPR_PDL")) : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(block);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, kernel, v) != cudaSuccess;
+}
+
 static int rev_init_basis(lpr_rev* h) {
   k_rev_init<<<h->sms * 4, 256, 0, h->stream>>>(h->view());
   LPR_LAUNCH_CHECK();
@@ -607,6 +700,7 @@ int lpr_rev_destroy(lpr_rev* h) {
   double* d[] = {h->A, h->Binv, h->b, h->c, h->c_orig, h->cB, h->xB, h->y, h->rc, h->u, h->ab, h->ecoef,
                  h->brow, h->ppart, h->ypart, h->x, h->z};
   for (double* p : d) cudaFree(p);
+  cudaFree(h->ekey);
   cudaFree(h->basis);
   cudaFree(h->isbasic);
   cudaFree(h->log);
@@ -700,20 +794,11 @@ int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status,
   long long next_refactor = refactor_every > 0 ? refactor_every : -1;
   while (true) {
     for (int q = 0; q < bsize; q++) {
-      k_price<<<gp, kT, 0, h->stream>>>(v);
-      LPR_LAUNCH_CHECK();
-      k_rc<<<(n + kT - 1) / kT, kT, 0, h->stream>>>(v);
-      LPR_LAUNCH_CHECK();
-      k_enter<<<1, 1024, 0, h->stream>>>(v);
-      LPR_LAUNCH_CHECK();
-      k_dir<<<gdir, kT, 0, h->stream>>>(v);
-      LPR_LAUNCH_CHECK();
-      k_ratio<<<1, 1024, 0, h->stream>>>(v);
-      LPR_LAUNCH_CHECK();
-      k_update<<<gu, kT, 0, h->stream>>>(v);
-      LPR_LAUNCH_CHECK();
-      k_y<<<(m + kT - 1) / kT, kT, 0, h->stream>>>(v);
-      LPR_LAUNCH_CHECK();
+      if (rev_launch(k_price, gp, kT, h->stream, v) || rev_launch(k_rc, dim3((n + kT - 1) / kT), kT, h->stream, v) ||
+          rev_launch(k_enter, dim3(1), 1024, h->stream, v) || rev_launch(k_dir, dim3(gdir), kT, h->stream, v) ||
+          rev_launch(k_ratio, dim3(1), 1024, h->stream, v) || rev_launch(k_update, gu, kT, h->stream, v) ||
+          rev_launch(k_y, dim3((m + kT - 1) / kT), kT, h->stream, v))
+        return fail(LPR_E_CUDA, "revised simplex kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       launched++;
       if (next_refactor > 0 && launched == next_refactor) {
         // periodic refactorisation needs the host to know the run is still alive
