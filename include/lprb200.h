@@ -103,7 +103,9 @@ int lpr_tab_set_basis(lpr_tab* h, const int* basis);
  * bit2 = use the unfused reference-shaped kernels (select reads the tableau directly);
  * bit3 = bracket every sweep launch with CUDA events (see lpr_tab_last_sweep_us);
  * bit4 = one tableau sweep per pivot (disable the delayed-update path that applies LPR_TAB_BLOCK=16 pivots
- *        per sweep for RULE_PRIMAL; both paths are bit-identical). */
+ *        per sweep for RULE_PRIMAL; both paths are bit-identical);
+ * bit5 = keep the selection and the sweep of the delayed-update path on one stream (by default the
+ *        selection of group g+1 overlaps the out-of-place sweep of group g). */
 int lpr_tab_solve(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
                   int64_t* n_pivots, int* pivot_log, int64_t log_cap);
 /* one pivot (FindEnteringVariable + FindLeavingVariable + Pivot) for snapshot-accurate tracing */

@@ -740,7 +740,9 @@ int tab_ensure_log(lpr_tab* h, long long cap) {
 }
 int tab_ensure_T2(lpr_tab* h) {
   if (h->T2) return LPR_OK;
-  LPR_CUDA(cudaMalloc(&h->T2, (size_t)h->Rcap * h->ld * sizeof(double)));
+  const size_t bytes = (size_t)h->Rcap * h->ld * sizeof(double);
+  h->T2 = cache_take(h->device, bytes);
+  if (!h->T2) LPR_CUDA(cudaMalloc(&h->T2, bytes));
   return LPR_OK;
 }
 
@@ -830,6 +832,9 @@ static int launch_select(lpr_tab* h, int rule, int flags, int* mask) {
 
 int tab_solve_blocked(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_t* n_pivots, int* pivot_log,
                       int64_t log_cap, bool time_sweeps);
+bool tab_pipe_applicable(const lpr_tab* h);
+int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_t* n_pivots, int* pivot_log,
+                        int64_t log_cap, bool time_sweeps);
 
 int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
                        int64_t* n_pivots, int* pivot_log, int64_t log_cap) {
@@ -842,8 +847,12 @@ int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int*
     // LPR_TAB_BLOCK<=1 keep one sweep per pivot
     static const int blk = env_int("LPR_TAB_BLOCK", 16);
     static const int fused_on = env_int("LPR_TAB_FUSED", 1);
-    if (rule == LPR_RULE_PRIMAL && fused_on && blk > 1 && !(flags & (4 | 16)) && (max_pivots < 0 || max_pivots > 1))
+    if (rule == LPR_RULE_PRIMAL && fused_on && blk > 1 && !(flags & (4 | 16)) && (max_pivots < 0 || max_pivots > 1)) {
+      // flags bit5 keeps selection and sweep on one stream (tableau_blocked.cu); default: overlapped
+      if (!(flags & 32) && tab_pipe_applicable(h))
+        return tab_solve_pipelined(h, blk, max_pivots, status, n_pivots, pivot_log, log_cap, (flags & 8) != 0);
       return tab_solve_blocked(h, blk, max_pivots, status, n_pivots, pivot_log, log_cap, (flags & 8) != 0);
+    }
   }
   static const int fused_default = env_int("LPR_TAB_FUSED", 1);
   static const int batch = std::max(1, env_int("LPR_TAB_BATCH", 32));
@@ -988,7 +997,8 @@ int lpr_tab_destroy(lpr_tab* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (!cache_give(h->device, (size_t)h->Rcap * h->ld * sizeof(double), h->T)) cudaFree(h->T);
-  cudaFree(h->T2);
+  if (!cache_give(h->device, (size_t)h->Rcap * h->ld * sizeof(double), h->T2)) cudaFree(h->T2);
+  tab_pipe_free(h);
   cudaFree(h->col[0]);
   cudaFree(h->col[1]);
   cudaFree(h->rhs);

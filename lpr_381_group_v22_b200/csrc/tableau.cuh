@@ -20,6 +20,7 @@ struct TabState {
   long long max_piv;
   long long group_base;  // blocked path: npiv at the start of the current group of delayed pivots
   double pivot;
+  double enter_val;  // pipelined path: T[0, enter] of the current tableau (f0 of the next pivot)
 };
 
 struct TabView {
@@ -57,6 +58,19 @@ struct lpr_tab {
   double* blk_row0 = nullptr;  // ld       mirror of the objective row (always current)
   double* blk_rhs[2] = {nullptr, nullptr};  // Rcap mirror of the RHS column, double buffered
   int* blk_p = nullptr;        // K        pivot rows of the pending pivots
+  // pipelined delayed-update path (tableau_pipelined.cu): two group slots, two streams
+  struct PipeRes {
+    int k = 0;
+    double* pr[2] = {nullptr, nullptr};   // K x ld   pivot rows of the group in this slot
+    double* f[2] = {nullptr, nullptr};    // Rcap x K factor columns (K contiguous per row)
+    int* pidx = nullptr;                  // 2 x K pivot rows
+    int* count = nullptr;                 // 2 group sizes
+    double* row0 = nullptr;               // ld  objective-row mirror
+    double* rhs = nullptr;                // Rcap RHS mirror
+    cudaStream_t s_sel = nullptr, s_sw = nullptr;
+    int sw_sms = 0;                       // SMs the sweep stream may use (green-context partition), 0 = all
+    cudaEvent_t ev_sel[2] = {nullptr, nullptr}, ev_sw[2] = {nullptr, nullptr}, ev_in = nullptr, ev_out = nullptr;
+  } pipe;
   lpr::MinIdx* selcand = nullptr;    // per-CTA entering candidates of the multi-CTA select
   unsigned* ticket = nullptr;        // "last CTA done" counter
   int* log = nullptr;
@@ -79,6 +93,7 @@ namespace lpr {
 int tab_alloc(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab** out);
 int tab_ensure_log(lpr_tab* h, long long cap);
 int tab_ensure_T2(lpr_tab* h);
+void tab_pipe_free(lpr_tab* h);  // tableau_pipelined.cu
 int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
                        int64_t* n_pivots, int* pivot_log, int64_t log_cap);
 }  // namespace lpr

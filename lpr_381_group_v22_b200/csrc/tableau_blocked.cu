@@ -20,7 +20,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "sweep.cuh"
+#include "blocked_apply.cuh"
 #include "tableau.cuh"
 
 namespace lpr {
@@ -709,39 +709,6 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
     st->enter = e;
     if (term != LPR_RUNNING) st->status = term;
   }
-}
-
-// fast path: a full group (s == KM) on a row that is not one of the pending pivot rows -- 2 DMUL + 2 DADD
-// per pending pivot and chunk, nothing else
-template <int KM>
-__device__ __forceinline__ double2 blk_apply_fast(double2 x, const double2* pr, const double2* fr) {
-  double2 fq[KM / 2];
-#pragma unroll
-  for (int h2 = 0; h2 < KM / 2; h2++) fq[h2] = fr[h2];
-#pragma unroll
-  for (int u = 0; u < KM; u++) {
-    const double f = (u & 1) ? fq[u >> 1].y : fq[u >> 1].x;
-    x.x = __dsub_rn(x.x, __dmul_rn(f, pr[u].x));
-    x.y = __dsub_rn(x.y, __dmul_rn(f, pr[u].y));
-  }
-  return x;
-}
-template <int KM>
-__device__ __forceinline__ double2 blk_apply_gen(double2 x, const double2* pr, const double2* fr, int row, int s,
-                                                 const int* pu) {
-  double2 fq[KM / 2];
-#pragma unroll
-  for (int h2 = 0; h2 < KM / 2; h2++) fq[h2] = fr[h2];
-#pragma unroll
-  for (int u = 0; u < KM; u++) {
-    const double f = (u & 1) ? fq[u >> 1].y : fq[u >> 1].x;
-    double2 y;
-    y.x = __dsub_rn(x.x, __dmul_rn(f, pr[u].x));
-    y.y = __dsub_rn(x.y, __dmul_rn(f, pr[u].y));
-    if (row == pu[u]) y = pr[u];
-    if (u < s) x = y;
-  }
-  return x;
 }
 
 template <int UNROLL, int KM, int kBlkRowsMax>

@@ -122,11 +122,12 @@ class DeviceTableau:
 
     # ---- solving ----------------------------------------------------------------------------
     def solve(self, rule=N.RULE_PRIMAL, max_pivots=-1, print_steps=False, log_cap=1 << 16, fused=True, blocked=True,
-              time_sweeps=False):
+              time_sweeps=False, pipelined=True):
         st = C.c_int()
         npv = C.c_int64()
         log = np.zeros((max(1, log_cap), 2), dtype=np.int32)
-        flags = (1 if print_steps else 0) | (0 if fused else 4) | (0 if blocked else 16) | (8 if time_sweeps else 0)
+        flags = (1 if print_steps else 0) | (0 if fused else 4) | (0 if blocked else 16) | (8 if time_sweeps else 0) | \
+            (0 if pipelined else 32)
         N.check(N.lib().lpr_tab_solve(self._h, rule, max_pivots, flags, C.byref(st), C.byref(npv),
                                       N.pi(log) if log_cap > 0 else None, log_cap))
         return dict(status=st.value, n_pivots=npv.value, log=log[:min(npv.value, log_cap)].copy())
@@ -154,6 +155,12 @@ class DeviceTableau:
         ms = C.c_float()
         N.check(N.lib().lpr_tab_last_solve_ms(self._h, C.byref(ms)))
         return ms.value
+
+    @property
+    def last_sweep_us(self):
+        us = C.c_float()
+        N.check(N.lib().lpr_tab_last_sweep_us(self._h, C.byref(us)))
+        return us.value
 
     # ---- cutting plane / B&B building blocks ------------------------------------------------------
     def append_row(self, row):

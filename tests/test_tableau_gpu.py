@@ -271,7 +271,7 @@ def test_cutting_plane_random_ip(seed):
 def test_full_size_window_cfg2():
     """BASELINE cfg2 shape (4097 x 12289): the first pivots bit-exact against the oracle, generated
     on device, plus size-independent invariants afterwards."""
-    m, n, seed, K = 4096, 8192, 383, 6
+    m, n, seed, K = 4096, 8192, 383, 40  # 16 + 16 + 8: two full delayed-update groups and a partial one
     A, b, c = O.gen_dense_lp(seed, m, n)
     T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
     del A
@@ -357,10 +357,13 @@ def test_nan_and_inf_do_not_hang():
         assert np.array_equal(got[mask], ref["T"][mask])
 
 
-@pytest.mark.parametrize("m,n,seed", [(8, 16, 1), (33, 70, 2), (100, 37, 4), (255, 513, 5), (300, 300, 6)])
+@pytest.mark.parametrize("m,n,seed", [(8, 16, 1), (33, 70, 2), (100, 37, 4), (255, 513, 5), (300, 300, 6),
+                                      (21, 2500, 7), (700, 90, 8)])
 @pytest.mark.parametrize("block", [2, 3, 8, 16])
 def test_blocked_delayed_update_is_bit_identical(m, n, seed, block, monkeypatch):
-    """K pending pivots applied by one sweep (tableau_blocked.cu) == one sweep per pivot == the oracle."""
+    """K pending pivots applied by one sweep == one sweep per pivot == the oracle, for the overlapped
+    (tableau_pipelined.cu: select of group g+1 runs beside the out-of-place sweep of group g) and the
+    single-stream (tableau_blocked.cu) plans."""
     import subprocess, sys, os, json
     # LPR_TAB_BLOCK is read once per process: run the comparison in a child process
     code = f"""
@@ -370,21 +373,28 @@ import oracle_lib as O, lpr_381_group_v22_b200 as L
 A, b, c = O.gen_dense_lp({seed}, {m}, {n})
 T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range({m})])
 out = {{}}
-for cap in (-1, 7, 17):
-    ref = O.primal_solve(T0, b0, max_pivots=cap)
+for cap in (-1, 7, 17, 40):
+  ref = O.primal_solve(T0, b0, max_pivots=cap)
+  for pipelined in (True, False):
     with L.DeviceTableau.from_host(T0) as t:
-        r = t.solve(L.RULE_PRIMAL, max_pivots=cap)
+        r = t.solve(L.RULE_PRIMAL, max_pivots=cap, pipelined=pipelined)
         ok = (r["status"] == ref["status"] and r["n_pivots"] == ref["n_pivots"] and r["log"].tolist() == ref["log"].tolist()
               and t.basis.tolist() == ref["basis"].tolist()
               and np.array_equal(t.read().view(np.uint64), ref["T"].view(np.uint64)))
-        out[str(cap)] = bool(ok)
+        # a second solve on the same handle continues from the (possibly swapped) current buffer
+        if ok and cap >= 0 and r["status"] == L.ITER_LIMIT:
+            ref2 = O.primal_solve(ref["T"], ref["basis"])
+            r2 = t.solve(L.RULE_PRIMAL, pipelined=pipelined)
+            ok = (r2["status"] == ref2["status"] and r2["log"].tolist() == ref2["log"].tolist()
+                  and np.array_equal(t.read().view(np.uint64), ref2["T"].view(np.uint64)))
+        out["%d:%d" % (cap, int(pipelined))] = bool(ok)
 print(json.dumps(out))
 """
     env = dict(os.environ, LPR_TAB_BLOCK=str(block))
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
     out = json.loads(res.stdout.strip().splitlines()[-1])
-    assert out == {"-1": True, "7": True, "17": True}, out
+    assert out and all(out.values()) and len(out) == 8, out
 
 
 def test_build_paths_full_rows_and_cache_reuse():
