@@ -353,9 +353,12 @@ def main():
     except Exception:
         pass
     peak = float(peaks["hbm_gbs"])
-    # dominant kernel of the timed region = the blocked sweep: it reads+writes the tableau once and reads the
-    # KBLK pending pivot rows / factor columns; ONE launch applies KBLK pivots
-    bytes_blk = 16.0 * R * CC + 8.0 * KBLK * (R + CC)
+    # dominant kernel of the timed region = the delayed-update sweep: it reads+writes the tableau once (columns
+    # 0..C-2; the RHS column lives in the select kernels' mirror) and reads the KBLK pending pivot rows / factor
+    # columns; ONE launch applies KBLK pivots.  It runs on the sweep partition (132 of 148 SMs) while the select
+    # cluster of the next group runs on the other 16 SMs, so kernel_us is the in-situ (overlapped) duration.
+    pipelined = os.environ.get("LPR_TAB_PIPE", "1") != "0"
+    bytes_blk = 16.0 * R * (CC - 1 if pipelined else CC) + 8.0 * KBLK * (R + CC)
     kern_us = blk_sweep_us if blk_sweep_us else None
     achieved = bytes_blk / (kern_us * 1e-6) / 1e9 if kern_us else None
     pivot_equiv = BYTES_PER_PIVOT / (per_pivot_us * 1e-6) / 1e9
@@ -390,12 +393,17 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm",
-                     "kernel": f"lpr::k_blk_sweep<4,{8 if KBLK <= 8 else 16},64> (applies {KBLK} delayed rank-1 updates per launch)",
+                     "kernel": (f"lpr::k_pipe_sweep_ca<16,2,16,32> (applies {KBLK} delayed rank-1 updates per launch, "
+                                "cp.async shared-memory ring, out of place, overlapped with lpr::k_pipe_select3<768,1>)")
+                     if pipelined else
+                     f"lpr::k_blk_sweep<4,{8 if KBLK <= 8 else 16},64> (applies {KBLK} delayed rank-1 updates per launch)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
                      "peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)",
                      "bytes_per_launch": bytes_blk, "pivots_per_launch": KBLK, "kernel_us": kern_us,
-                     "kernel_us_how": "CUDA event pairs around each sweep launch on the library stream, 16-group pass",
+                     "kernel_us_how": "CUDA event pairs around each sweep launch on the sweep stream, 16-group pass, "
+                                      "select cluster of the next group running concurrently",
+                     "group_period_us": per_pivot_us * KBLK,
                      "traffic": (traffic or {}).get("blocked_dram_bytes_per_launch"),
                      "note": "bit-identical delayed-update path: every element still goes through the same "
                              "multiply/subtract roundings in the same order, but the tableau is swept once per "

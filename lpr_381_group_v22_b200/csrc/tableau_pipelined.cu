@@ -41,8 +41,6 @@ namespace lpr {
 namespace cg = cooperative_groups;
 
 constexpr int PK = 16;            // pending pivots per group (storage and kernel instantiation)
-constexpr int PNT = 256;          // threads per select CTA
-constexpr int PWARPS = PNT / 32;
 constexpr int PMAXCTA = 16;
 constexpr unsigned FULLM = 0xffffffffu;
 
@@ -66,8 +64,6 @@ struct PipeArgs {
   int K;               // pivots to select in this launch
   long long* dbg;      // optional: per-phase clock64 stamps of the last launch
   long long* tl;       // optional: [select start, select end, sweep start, sweep end] globaltimer of this group
-  int prefetch;        // speculative L2 prefetch of the runner-up entering columns (0 = off)
-  unsigned* hits;      // optional: [pivots, pivots whose entering column had been prefetched]
 };
 
 struct CandA {
@@ -79,10 +75,8 @@ struct CandA {
 };
 struct CandB {
   unsigned long long key;  // ~bits of the (negative) objective entry, ~0 = none
-  double pr;               // normalised pivot-row entry of that column (prow[e] of the NEXT pivot's chain)
   int idx;
   int pad;
-  long long pad2;
 };
 
 // lexicographic (key, idx) minimum over the warp; *src = lane that holds it
@@ -115,362 +109,6 @@ __global__ void __launch_bounds__(kSelThreads) k_pipe_init(const double* T, int 
     count[0] = 0;
     count[1] = 0;
   }
-}
-
-template <int NC>
-__global__ void __launch_bounds__(PNT, 1) k_pipe_select(PipeArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int ncta = (int)cluster.num_blocks();
-  const int crank = (int)cluster.block_rank();
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int nthr = ncta * PNT;
-  const int gid = crank * PNT + tid;
-  const int total = ncta * PWARPS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sPR = reinterpret_cast<double*>(smem_raw);            // [NC][PK][PNT] this group's pivot-row slices
-  double* sFp = sPR + (size_t)NC * PK * PNT;                    // [PK][PNT]     previous group's factors of my row
-  double* sFc = sFp + (size_t)PK * PNT;                         // [PK][PNT]     this group's factors of my row
-  CandA* slotA = reinterpret_cast<CandA*>(sFc + (size_t)PK * PNT);   // [PMAXCTA * PWARPS]
-  CandB* slotB = reinterpret_cast<CandB*>(slotA + PMAXCTA * PWARPS);  // [PMAXCTA * PWARPS]
-  __shared__ double s_pe[2 * PK], s_fp[2 * PK];
-  __shared__ int s_pu[2 * PK];
-  __shared__ unsigned s_hit;
-  TabState* st = a.st;
-  const int R = a.R, C = a.C, ld = a.ld;
-  const int CW = C - 1;  // columns handled here: 0 .. C-2 (the RHS column is the rv mirror, padding stays 0)
-  const double* T = a.Told;
-  const int sp = a.sp;
-  const int status = st->status;
-  long long npiv = st->npiv;
-  const long long npiv0 = npiv;
-  const long long maxp = st->max_piv;
-  int e = st->enter;
-  double f0 = st->enter_val;
-  if (a.tl && gid == 0) {
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    a.tl[0] = t;
-  }
-  if (status != LPR_RUNNING) {  // uniform over the cluster: nobody reaches a barrier
-    if (gid == 0) {
-      *a.count = 0;
-      st->group_base = npiv;
-    }
-    return;
-  }
-  auto stamp = [&](int q, int k) {
-    if (a.dbg && gid == 0) a.dbg[q * 8 + k] = clock64();
-  };
-  const int i = gid + 1;  // my row of the entering column (row 0 is the objective-row mirror)
-  const bool own_row = i < R;
-  if (tid < 2 * PK) s_pu[tid] = (tid < sp) ? a.pup[tid] : -1;
-  double rv = own_row ? a.rhs[i] : 0.0;
-  bool hit_row = false;  // my row is the pivot row of some pending pivot: general update path
-#pragma unroll
-  for (int u = 0; u < PK; u++) {
-    sFp[u * PNT + tid] = (own_row && u < sp) ? a.Fp[(size_t)i * PK + u] : 0.0;
-    hit_row |= (u < sp) && (a.pup[u] == i);
-  }
-#pragma unroll
-  for (int u = 0; u < PK; u++) sFc[u * PNT + tid] = 0.0;
-  double r0[NC];
-  double ppv[NC][PK];  // previous group's pivot-row entries of my columns: constant during this launch
-#pragma unroll
-  for (int c = 0; c < NC; c++) {
-    const int j = gid + c * nthr;
-    r0[c] = (j < CW) ? a.row0[j] : 0.0;
-#pragma unroll
-    for (int u = 0; u < PK; u++) ppv[c][u] = (j < CW && u < sp) ? __ldg(a.PRp + (size_t)u * ld + j) : 0.0;
-  }
-  double zobj = (gid == 0) ? a.row0[CW] : 0.0;  // objective value T[0, C-1]
-  __syncthreads();
-  int term = LPR_RUNNING;
-  int s = 0;
-  double xpr[NC];          // my slices of the newest pivot row (stored for the sweep one phase later)
-#pragma unroll
-  for (int c = 0; c < NC; c++) xpr[c] = 0.0;
-  double prc_last = 0.0, pe_new = 0.0;
-  int spec0 = -1, spec1 = -1, pf0 = -1, pf1 = -1;
-  for (int q = 0; q < a.K; q++, s++) {
-    if (e < 0) { term = LPR_OPTIMAL; break; }
-    stamp(q, 0);
-    // ---- phase A: entering column of the current tableau = stale column + pending updates; ratio test ----
-    // deferred from the previous pivot: the sweep's copy of its pivot row.  Issued after that pivot's last
-    // barrier so no barrier release has to wait for these stores; they drain under the gather below.
-    if (s > 0) {
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        const int j = gid + c * nthr;
-        if (j < CW) a.PRc[(size_t)(s - 1) * ld + j] = xpr[c];
-      }
-      if (gid == 0) a.PRc[(size_t)(s - 1) * ld + CW] = prc_last;
-    }
-    if (tid < PK) s_pe[tid] = (tid < sp) ? __ldcg(a.PRp + (size_t)tid * ld + e) : 0.0;
-    else if (tid < 2 * PK) {  // rows 0 .. s-2 were stored two barriers ago; row s-1 arrived with the candidate
-      const int u = tid - PK;
-      s_pe[tid] = (u < s - 1) ? __ldcg(a.PRc + (size_t)u * ld + e) : ((u == s - 1) ? pe_new : 0.0);
-    }
-    double col = own_row ? TAT(T, ld, i, e) : 0.0;  // DRAM gather of the stale column
-    if (a.prefetch && own_row) {  // runner-up columns of the last pricing: likely entering columns of pivot q+1
-      if (spec0 >= 0) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(T + (size_t)i * ld + spec0));
-      if (spec1 >= 0) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(T + (size_t)i * ld + spec1));
-    }
-    if (a.hits && gid == 0) {
-      atomicAdd(a.hits, 1u);
-      if (e == pf0 || e == pf1) atomicAdd(a.hits + 1, 1u);
-    }
-    pf0 = spec0;
-    pf1 = spec1;
-    __syncthreads();
-    stamp(q, 1);
-    unsigned long long key = ~0ull;
-    int idx = INT_MAX;
-    if (own_row) {
-      const double* fpv = sFp + tid;
-      const double* fcv = sFc + tid;
-      if (!hit_row) {  // 2 DP instructions per pending pivot, nothing else on the dependency chain
-        if (sp == PK) {
-#pragma unroll
-          for (int u = 0; u < PK; u++) col = __dsub_rn(col, __dmul_rn(fpv[u * PNT], s_pe[u]));
-        } else {
-          for (int u = 0; u < sp; u++) col = __dsub_rn(col, __dmul_rn(fpv[u * PNT], s_pe[u]));
-        }
-#pragma unroll 4
-        for (int u = 0; u < s; u++) col = __dsub_rn(col, __dmul_rn(fcv[u * PNT], s_pe[PK + u]));
-      } else {
-        for (int u = 0; u < sp; u++)
-          col = (i == s_pu[u]) ? s_pe[u] : __dsub_rn(col, __dmul_rn(fpv[u * PNT], s_pe[u]));
-        for (int u = 0; u < s; u++)
-          col = (i == s_pu[PK + u]) ? s_pe[PK + u] : __dsub_rn(col, __dmul_rn(fcv[u * PNT], s_pe[PK + u]));
-      }
-      sFc[s * PNT + tid] = col;  // this pivot's factor, needed by the later pivots of the group
-      // FindLeavingVariable :169-191
-      if (col > 1e-9) {
-        const double val = __ddiv_rn(rv, col);
-        if (val >= 0.0 && val < DBL_MAX) {
-          key = (val == 0.0) ? 0ull : (unsigned long long)__double_as_longlong(val);
-          idx = i - 1;
-        }
-      }
-    }
-    stamp(q, 2);
-    {
-      int src;
-      warp_argmin_key(key, idx, src);
-      const double wpiv = __shfl_sync(FULLM, col, src);
-      const double wrhs = __shfl_sync(FULLM, rv, src);
-      if (lane < ncta) {  // lane r delivers this warp's candidate to CTA r
-        CandA c;
-        c.key = key;
-        c.piv = wpiv;
-        c.rhs = wrhs;
-        c.idx = idx;
-        c.pad = 0;
-        cluster.map_shared_rank(slotA, lane)[crank * PWARPS + w] = c;
-      }
-    }
-    cluster.sync();
-    stamp(q, 3);
-    // the sweep's copy of the factor column: after the barrier, so that it drains under the row read below
-    if (own_row) a.Fc[(size_t)i * PK + s] = col;
-    if (gid == 0) a.Fc[s] = f0;  // row 0: T[0,e]
-    int p;
-    double piv, rhsp;
-    {
-      unsigned long long bk = ~0ull;
-      int bi = INT_MAX;
-      double bp = 0.0, br = 0.0;
-      for (int k = lane; k < total; k += 32) {
-        const CandA c = slotA[k];
-        if (c.key < bk || (c.key == bk && c.idx < bi)) {
-          bk = c.key;
-          bi = c.idx;
-          bp = c.piv;
-          br = c.rhs;
-        }
-      }
-      int src;
-      warp_argmin_key(bk, bi, src);
-      piv = __shfl_sync(FULLM, bp, src);
-      rhsp = __shfl_sync(FULLM, br, src);
-      p = (bi == INT_MAX) ? -1 : bi + 1;
-    }
-    if (p < 0) { term = LPR_UNBOUNDED; break; }
-    if (maxp >= 0 && npiv >= maxp) { term = LPR_ITER_LIMIT; break; }
-    stamp(q, 4);
-    // ---- phase B: pivot row = stale row + pending updates, normalise, objective-row / RHS mirrors ----
-    if (tid < PK) s_fp[tid] = (tid < sp) ? __ldcg(a.Fp + (size_t)p * PK + tid) : 0.0;
-    else if (tid < 2 * PK) s_fp[tid] = (tid - PK < s) ? __ldcg(a.Fc + (size_t)p * PK + (tid - PK)) : 0.0;
-    if (tid < 32) {  // is p the pivot row of a pending pivot (rare)?  uniform general-path switch
-      const unsigned m = __ballot_sync(FULLM, p == s_pu[tid]);
-      if (tid == 0) s_hit = m;
-    }
-    double x[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const int j = gid + c * nthr;
-      x[c] = (j < CW) ? TAT(T, ld, p, j) : 0.0;
-    }
-    __syncthreads();
-    stamp(q, 5);
-    const bool hit_p = s_hit != 0u;
-    unsigned long long keyb = ~0ull;
-    int idxb = INT_MAX;
-    double prb = 0.0;
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const int j = gid + c * nthr;
-      if (j < CW) {
-        double xx = x[c];
-        double* prv = sPR + (size_t)c * PK * PNT + tid;
-        if (!hit_p) {
-          if (sp == PK) {
-#pragma unroll
-            for (int u = 0; u < PK; u++) xx = __dsub_rn(xx, __dmul_rn(s_fp[u], ppv[c][u]));
-          } else {
-#pragma unroll
-            for (int u = 0; u < PK; u++)
-              if (u < sp) xx = __dsub_rn(xx, __dmul_rn(s_fp[u], ppv[c][u]));
-          }
-#pragma unroll 4
-          for (int u = 0; u < s; u++) xx = __dsub_rn(xx, __dmul_rn(s_fp[PK + u], prv[u * PNT]));
-        } else {
-#pragma unroll
-          for (int u = 0; u < PK; u++)
-            if (u < sp) xx = (p == s_pu[u]) ? ppv[c][u] : __dsub_rn(xx, __dmul_rn(s_fp[u], ppv[c][u]));
-          for (int u = 0; u < s; u++) {
-            const double pv = prv[u * PNT];
-            xx = (p == s_pu[PK + u]) ? pv : __dsub_rn(xx, __dmul_rn(s_fp[PK + u], pv));
-          }
-        }
-        const double pr = __ddiv_rn(xx, piv);                  // :197-199
-        const double z = __dsub_rn(r0[c], __dmul_rn(f0, pr));  // :206-208 on the objective row
-        if (z < 0.0) {
-          const unsigned long long kb = ~(unsigned long long)__double_as_longlong(z);
-          if (kb < keyb) {  // columns of one thread ascend: strict < keeps the lowest index on ties
-            keyb = kb;
-            idxb = j;
-          }
-        }
-        prv[s * PNT] = pr;
-        r0[c] = z;
-        xpr[c] = pr;
-        if (idxb == j) prb = pr;
-      }
-    }
-    const double prc = __ddiv_rn(rhsp, piv);  // normalised pivot row at the RHS column
-    if (own_row) {
-      rv = (i == p) ? prc : __dsub_rn(rv, __dmul_rn(col, prc));
-      hit_row |= (i == p);
-    }
-    zobj = __dsub_rn(zobj, __dmul_rn(f0, prc));
-    stamp(q, 6);
-    prc_last = prc;
-    {
-      int src;
-      warp_argmin_key(keyb, idxb, src);
-      const double wpr = __shfl_sync(FULLM, prb, src);
-      if (lane < ncta) {
-        CandB c;
-        c.key = keyb;
-        c.pr = wpr;
-        c.idx = idxb;
-        c.pad = 0;
-        c.pad2 = 0;
-        cluster.map_shared_rank(slotB, lane)[crank * PWARPS + w] = c;
-      }
-    }
-    if (tid == 0) s_pu[PK + s] = p;
-    if (gid == 0) {
-      a.puc[s] = p;
-      if (a.log && npiv < a.log_cap) {
-        a.log[2 * npiv] = p;
-        a.log[2 * npiv + 1] = e;
-      }
-      if (a.basis) a.basis[p - 1] = e;  // :142
-      st->pivot = piv;
-      st->leave = p;
-    }
-    cluster.sync();
-    stamp(q, 7);
-    {
-      unsigned long long bk = ~0ull;
-      int bi = INT_MAX;
-      double bp = 0.0;
-      unsigned long long k2 = ~0ull, k3 = ~0ull;  // runner-ups among this lane's entries (speculation only)
-      int i2 = -1, i3 = -1;
-      for (int k = lane; k < total; k += 32) {
-        const CandB c = slotB[k];
-        if (c.key < bk || (c.key == bk && c.idx < bi)) {
-          k3 = k2; i3 = i2;
-          k2 = bk; i2 = bi;
-          bk = c.key;
-          bi = c.idx;
-          bp = c.pr;
-        } else if (c.key < k2) {
-          k3 = k2; i3 = i2;
-          k2 = c.key; i2 = c.idx;
-        } else if (c.key < k3) {
-          k3 = c.key; i3 = c.idx;
-        }
-      }
-      const unsigned long long lk = bk;
-      const int li = bi;
-      int src;
-      warp_argmin_key(bk, bi, src);
-      pe_new = __shfl_sync(FULLM, bp, src);
-      e = (bi == INT_MAX) ? -1 : bi;
-      f0 = (bi == INT_MAX) ? 0.0 : __longlong_as_double((long long)~bk);  // T[0,e] of the updated tableau
-      if (a.prefetch) {  // second and third best warp candidates overall (off the critical path: the gather is next)
-        unsigned long long ck = (li == bi) ? k2 : lk;   // this lane's best that is not the winner
-        int ci = (li == bi) ? i2 : li;
-        unsigned long long nk = (li == bi) ? k3 : k2;   // and its next one
-        int ni = (li == bi) ? i3 : i2;
-        if (ci == INT_MAX || ci < 0) { ck = ~0ull; ci = INT_MAX; }
-        if (ni == INT_MAX || ni < 0) { nk = ~0ull; ni = INT_MAX; }
-        unsigned long long wk = ck;
-        int wi = ci, ws;
-        warp_argmin_key(wk, wi, ws);
-        spec0 = (wi == INT_MAX) ? -1 : wi;
-        if (lane == ws) { ck = nk; ci = ni; }
-        wk = ck; wi = ci;
-        warp_argmin_key(wk, wi, ws);
-        spec1 = (wi == INT_MAX) ? -1 : wi;
-      }
-    }
-    npiv++;
-  }
-  // the last pivot's row for the sweep
-  if (s > 0) {
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const int j = gid + c * nthr;
-      if (j < CW) a.PRc[(size_t)(s - 1) * ld + j] = xpr[c];
-    }
-    if (gid == 0) a.PRc[(size_t)(s - 1) * ld + CW] = prc_last;
-  }
-  // mirrors back to global for the next group's launch
-#pragma unroll
-  for (int c = 0; c < NC; c++) {
-    const int j = gid + c * nthr;
-    if (j < CW) a.row0[j] = r0[c];
-  }
-  if (own_row) a.rhs[i] = rv;
-  if (gid == 0) {
-    a.row0[CW] = zobj;
-    *a.count = s;
-    st->group_base = npiv0;
-    st->npiv = npiv;
-    st->enter = e;
-    st->enter_val = f0;
-    if (term != LPR_RUNNING) st->status = term;
-    if (a.tl) {
-      long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      a.tl[1] = t;
-    }
-  }
-  cluster.sync();  // no CTA exits while a peer could still address its shared memory
 }
 
 // ---- select, third cut: more warps, no global stores inside the pivot loop ------------------------------
@@ -727,7 +365,7 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
       warp_argmin_key(keyb, idxb, src);
       if (lane == 0) {
         CandB c;
-        c.key = keyb; c.pr = 0.0; c.idx = idxb; c.pad = 0; c.pad2 = 0;
+        c.key = keyb; c.idx = idxb; c.pad = 0;
         wB[w] = c;
       }
     }
@@ -735,7 +373,7 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
     stamp(q, 6);
     if (w == 0) {
       CandB c;
-      c.key = ~0ull; c.pr = 0.0; c.idx = INT_MAX; c.pad = 0; c.pad2 = 0;
+      c.key = ~0ull; c.idx = INT_MAX; c.pad = 0;
       if (lane < NW) c = wB[lane];
       int src;
       warp_argmin_key(c.key, c.idx, src);
@@ -745,7 +383,7 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
     stamp(q, 7);
     {
       CandB c;
-      c.key = ~0ull; c.pr = 0.0; c.idx = INT_MAX; c.pad = 0; c.pad2 = 0;
+      c.key = ~0ull; c.idx = INT_MAX; c.pad = 0;
       if (lane < ncta) c = slotB[lane];
       int src;
       warp_argmin_key(c.key, c.idx, src);
@@ -813,112 +451,6 @@ struct PipeSweepArgs {
   int nch;  // 16-byte chunks per row that are swept: the columns 0 .. C-2 (RHS column = the select's rv mirror)
   long long* tl;
 };
-
-template <int UNROLL, int KM, int RB>
-__global__ void __launch_bounds__(kSweepThreads, 2) k_pipe_sweep(PipeSweepArgs a, int ncg, int nsplit) {
-  static_assert(RB % UNROLL == 0 && RB <= 32, "row block");
-  constexpr int STG = (RB * KM / 2 + kSweepThreads - 1) / kSweepThreads;  // double2 staging loads per thread
-  __shared__ __align__(16) double sF[2][RB * KM];
-  __shared__ unsigned sPiv[2];
-  const int s = *a.count;
-  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) {
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    a.tl[2] = t;
-  }
-  if (s <= 0) return;
-  const int R = a.R, ld = a.ld;
-  const int ldv = ld >> 1;
-  const double2* S2 = reinterpret_cast<const double2*>(a.src);
-  double2* D2 = reinterpret_cast<double2*>(a.dst);
-  int pu[KM];
-#pragma unroll
-  for (int u = 0; u < KM; u++) pu[u] = (u < s) ? a.pidx[u] : -1;
-  const bool full = (s == KM);
-  const int tid = threadIdx.x;
-  const int ntasks = ncg * nsplit;
-  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-    const int cgi = task % ncg, rs = task / ncg;
-    const int r_lo = (int)((long long)R * rs / nsplit), r_hi = (int)((long long)R * (rs + 1) / nsplit);
-    if (r_lo >= r_hi) continue;
-    const int chunk = cgi * kSweepThreads + tid;
-    const bool active = chunk < a.nch;
-    const int cc = active ? chunk : 0;
-    double2 pr[KM];
-#pragma unroll
-    for (int u = 0; u < KM; u++) pr[u] = __ldg(reinterpret_cast<const double2*>(a.PR + (size_t)u * ld) + cc);
-    const int nblk = (r_hi - r_lo + RB - 1) / RB;
-    auto stage_load = [&](int b, double2* stg) {
-      const int b0 = r_lo + b * RB;
-      const int n2 = (min(r_hi, b0 + RB) - b0) * KM / 2;
-      const double2* f2 = reinterpret_cast<const double2*>(a.F + (size_t)b0 * KM);
-#pragma unroll
-      for (int k = 0; k < STG; k++) {
-        const int t = tid + k * kSweepThreads;
-        if (t < n2) stg[k] = __ldg(f2 + t);
-      }
-    };
-    auto stage_store = [&](int b, const double2* stg) {
-      const int b0 = r_lo + b * RB;
-      const int n2 = (min(r_hi, b0 + RB) - b0) * KM / 2;
-      double2* d2 = reinterpret_cast<double2*>(sF[b & 1]);
-#pragma unroll
-      for (int k = 0; k < STG; k++) {
-        const int t = tid + k * kSweepThreads;
-        if (t < n2) d2[t] = stg[k];
-      }
-      if (tid < 32) {  // rows of this block that are pivot rows of the group take the general path
-        bool slow = !full;
-        const int row = b0 + tid;
-#pragma unroll
-        for (int u = 0; u < KM; u++) slow |= (row == pu[u]);
-        const unsigned m = __ballot_sync(FULLM, slow);
-        if (tid == 0) sPiv[b & 1] = m;
-      }
-    };
-    double2 stg[STG];
-    __syncthreads();  // the previous task is done with the ring
-    stage_load(0, stg);
-    stage_store(0, stg);
-    double2 xc[UNROLL], xn[UNROLL];
-    const double2* sp = S2 + cc;
-    double2* dp = D2 + cc;
-#pragma unroll
-    for (int k = 0; k < UNROLL; k++)
-      if (r_lo + k < r_hi) xc[k] = ld_stream(sp + (size_t)(r_lo + k) * ldv);
-    __syncthreads();
-    for (int b = 0; b < nblk; b++) {
-      const int b0 = r_lo + b * RB, b1 = min(r_hi, b0 + RB);
-      if (b + 1 < nblk) stage_load(b + 1, stg);
-      const double* sf = sF[b & 1];
-      const unsigned pm = sPiv[b & 1];
-      for (int r = b0; r < b1; r += UNROLL) {
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++)
-          if (r + UNROLL + k < r_hi) xn[k] = ld_stream(sp + (size_t)(r + UNROLL + k) * ldv);
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++) {
-          const int row = r + k;
-          if (row < b1) {
-            const double2* fr = reinterpret_cast<const double2*>(sf + (size_t)(row - b0) * KM);
-            const bool slow = (pm >> (row - b0)) & 1u;  // CTA-uniform
-            const double2 y = slow ? blk_apply_gen<KM>(xc[k], pr, fr, row, s, pu) : blk_apply_fast<KM>(xc[k], pr, fr);
-            if (active) dp[(size_t)row * ldv] = y;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++) xc[k] = xn[k];
-      }
-      if (b + 1 < nblk) stage_store(b + 1, stg);
-      __syncthreads();
-    }
-  }
-  if (a.tl && threadIdx.x == 0) {  // the LAST CTA's end
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    atomicMax(reinterpret_cast<unsigned long long*>(a.tl + 3), (unsigned long long)t);
-  }
-}
 
 // ---- sweep with an asynchronous shared-memory ring ---------------------------------------------------------
 // Same work split as k_pipe_sweep, but the tableau rows are staged through shared memory with cp.async
@@ -1217,27 +749,6 @@ static size_t ca_smem_bytes(int nstg) {
   return sizeof(double2) * (size_t)nstg * kSweepThreads + sizeof(double) * 2 * 32 * PK;
 }
 
-static size_t pipe_select_smem(int nc) {
-  return sizeof(double) * ((size_t)nc * PK * PNT + 2 * (size_t)PK * PNT) + sizeof(CandA) * PMAXCTA * PWARPS +
-         sizeof(CandB) * PMAXCTA * PWARPS;
-}
-
-// cluster geometry for a tableau, or ncta = 0 when the pipelined path does not apply
-static void pipe_geometry(const lpr_tab* h, int* ncta, int* nc) {
-  *ncta = 0;
-  *nc = 0;
-  const int need = std::max(h->R - 1, (h->C - 1 + 3) / 4);
-  int n = std::max(1, (need + PNT - 1) / PNT);
-  if (n > PMAXCTA) return;
-  // cluster sizes must divide nothing in particular, but keep them to 1, 2, 4, 8, 16
-  int c = 1;
-  while (c < n) c <<= 1;
-  const int nthr = c * PNT;
-  const int cols = (h->C - 1 + nthr - 1) / nthr;
-  *ncta = c;
-  *nc = std::max(1, cols);
-}
-
 // select v3 geometry: smallest cluster whose CTAs (256 row owners each) cover the rows; one column per thread
 // with 768-thread CTAs when that covers the row, else up to 4 columns per thread with 256-thread CTAs
 static void pipe_geometry3(const lpr_tab* h, int* ncta, int* nt, int* nc) {
@@ -1262,10 +773,6 @@ static SelectFn pipe_select3_fn(int nt, int nc) {
   if (nt == 768) return k_pipe_select3<768, 1>;
   return nc == 1 ? k_pipe_select3<256, 1>
                  : (nc == 2 ? k_pipe_select3<256, 2> : (nc == 3 ? k_pipe_select3<256, 3> : k_pipe_select3<256, 4>));
-}
-static int pipe_select_version() {
-  static const int v = getenv("LPR_PIPE_SELECT") ? atoi(getenv("LPR_PIPE_SELECT")) : 3;
-  return v;
 }
 static bool pipe_prepare3(int ncta, int nt, int nc) {
   static int ok[2][5][PMAXCTA + 1] = {};
@@ -1296,51 +803,12 @@ static bool pipe_prepare3(int ncta, int nt, int nc) {
   return good;
 }
 
-static SelectFn pipe_select_fn(int nc) {
-  return nc == 1 ? k_pipe_select<1> : (nc == 2 ? k_pipe_select<2> : (nc == 3 ? k_pipe_select<3> : k_pipe_select<4>));
-}
-
-// one-time: shared-memory opt-in, non-portable cluster size, and "can a cluster of this size be resident"
-static bool pipe_prepare(int ncta, int nc) {
-  static int ok[5][PMAXCTA + 1] = {};
-  const int k = nc;
-  if (ok[k][ncta]) return ok[k][ncta] > 0;
-  SelectFn fn = pipe_select_fn(nc);
-  const size_t smem = pipe_select_smem(nc);
-  bool good = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
-  if (good && ncta > 8)
-    good = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-  if (good) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ncta);
-    cfg.blockDim = dim3(PNT);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = ncta;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    good = cudaOccupancyMaxActiveClusters(&n, fn, &cfg) == cudaSuccess && n >= 1;
-  }
-  if (!good) cudaGetLastError();
-  ok[k][ncta] = good ? 1 : -1;
-  return good;
-}
-
 bool tab_pipe_applicable(const lpr_tab* h) {
   static const int on = getenv("LPR_TAB_PIPE") ? atoi(getenv("LPR_TAB_PIPE")) : 1;
   if (!on) return false;
-  int ncta, nc, nt = PNT;
-  if (pipe_select_version() >= 3) {
-    pipe_geometry3(h, &ncta, &nt, &nc);
-    return ncta && pipe_prepare3(ncta, nt, nc);
-  }
-  pipe_geometry(h, &ncta, &nc);
-  if (!ncta) return false;
-  return pipe_prepare(ncta, nc);
+  int ncta, nc, nt;
+  pipe_geometry3(h, &ncta, &nt, &nc);
+  return ncta && pipe_prepare3(ncta, nt, nc);
 }
 
 // Solve() for LPR_RULE_PRIMAL, K delayed pivots per sweep, selection overlapped with the previous sweep.
@@ -1358,30 +826,16 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
     if ((rc = tab_ensure_log(h, want))) return rc;
   }
   auto& P = h->pipe;
-  int ncta, nc, nt = PNT;
-  SelectFn fn;
-  size_t smem;
-  if (pipe_select_version() >= 3) {
-    pipe_geometry3(h, &ncta, &nt, &nc);
-    fn = pipe_select3_fn(nt, nc);
-    smem = pipe_select3_smem(nt, nc);
-  } else {
-    pipe_geometry(h, &ncta, &nc);
-    fn = pipe_select_fn(nc);
-    smem = pipe_select_smem(nc);
-  }
+  int ncta, nc, nt;
+  pipe_geometry3(h, &ncta, &nt, &nc);
+  SelectFn fn = pipe_select3_fn(nt, nc);
+  const size_t smem = pipe_select3_smem(nt, nc);
   double* buf[2] = {h->T, h->T2};
 
   long long* d_dbg = nullptr;
   if (getenv("LPR_BLK_TIMING")) {
     LPR_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 8 * PK));
     LPR_CUDA(cudaMemset(d_dbg, 0, sizeof(long long) * 8 * PK));
-  }
-  static const int prefetch_on = getenv("LPR_PIPE_PREFETCH") ? atoi(getenv("LPR_PIPE_PREFETCH")) : 0;
-  unsigned* d_hits = nullptr;
-  if (getenv("LPR_PIPE_HITS")) {
-    LPR_CUDA(cudaMalloc(&d_hits, sizeof(unsigned) * 2));
-    LPR_CUDA(cudaMemset(d_hits, 0, sizeof(unsigned) * 2));
   }
   long long* d_tl = nullptr;
   const int TLG = 24;
@@ -1392,8 +846,7 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
   // sweep geometry: persistent CTAs, (column group, row split) tasks; leave the select cluster its slots
   static const int overlap = getenv("LPR_PIPE_OVERLAP") ? atoi(getenv("LPR_PIPE_OVERLAP")) : 1;
   static const int reserve_env = getenv("LPR_PIPE_RESERVE") ? atoi(getenv("LPR_PIPE_RESERVE")) : -1;
-  static const int sweep_unroll = getenv("LPR_PIPE_UNROLL") ? atoi(getenv("LPR_PIPE_UNROLL")) : 4;
-  static const int sweep_kind = getenv("LPR_PIPE_SWEEP") ? atoi(getenv("LPR_PIPE_SWEEP")) : 1;
+  static const int sweep_kind = getenv("LPR_PIPE_SWEEP") ? atoi(getenv("LPR_PIPE_SWEEP")) : 2;
   static int resident = 0;
   if (!resident) {
     cudaFuncSetAttribute(k_pipe_sweep_ca<PK, 4, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ca_smem_bytes(16));
@@ -1402,12 +855,10 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
     int r = 0;
     if (sweep_kind == 1)
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep_ca<PK, 4, 16, 32>, kSweepThreads, ca_smem_bytes(16));
-    else if (sweep_kind == 2)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep_ca<PK, 2, 16, 32>, kSweepThreads, ca_smem_bytes(16));
     else if (sweep_kind >= 3)
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep_ca<PK, 4, 12, 32>, kSweepThreads, ca_smem_bytes(12));
     else
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep<4, PK, 32>, kSweepThreads, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep_ca<PK, 2, 16, 32>, kSweepThreads, ca_smem_bytes(16));
     resident = std::max(1, r);
   }
   const int nch = (h->C - 1 + 1) / 2;  // chunks that hold the columns 0 .. C-2
@@ -1448,8 +899,6 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
     a.K = K;
     a.dbg = d_dbg;
     a.tl = (d_tl && g < TLG) ? d_tl + 4 * g : nullptr;
-    a.prefetch = prefetch_on;
-    a.hits = d_hits;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta);
     cfg.blockDim = dim3(nt);
@@ -1486,18 +935,14 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
     w.tl = (d_tl && g < TLG) ? d_tl + 4 * g : nullptr;
     if (sweep_kind == 1)
       k_pipe_sweep_ca<PK, 4, 16, 32><<<gs, kSweepThreads, ca_smem_bytes(16), P.s_sw>>>(w, ncg, nsplit);
-    else if (sweep_kind == 2)
-      k_pipe_sweep_ca<PK, 2, 16, 32><<<gs, kSweepThreads, ca_smem_bytes(16), P.s_sw>>>(w, ncg, nsplit);
     else if (sweep_kind == 3)
       k_pipe_sweep_ca<PK, 4, 12, 32><<<gs, kSweepThreads, ca_smem_bytes(12), P.s_sw>>>(w, ncg, nsplit);
     else if (sweep_kind == 4)
       k_pipe_sweep_ca<PK, 4, 8, 32><<<gs, kSweepThreads, ca_smem_bytes(8), P.s_sw>>>(w, ncg, nsplit);
     else if (sweep_kind == 5)
       k_pipe_sweep_ca<PK, 2, 8, 32><<<gs, kSweepThreads, ca_smem_bytes(8), P.s_sw>>>(w, ncg, nsplit);
-    else if (sweep_unroll == 2)
-      k_pipe_sweep<2, PK, 32><<<gs, kSweepThreads, 0, P.s_sw>>>(w, ncg, nsplit);
     else
-      k_pipe_sweep<4, PK, 32><<<gs, kSweepThreads, 0, P.s_sw>>>(w, ncg, nsplit);
+      k_pipe_sweep_ca<PK, 2, 16, 32><<<gs, kSweepThreads, ca_smem_bytes(16), P.s_sw>>>(w, ncg, nsplit);
     if (cudaGetLastError() != cudaSuccess)
       return fail(LPR_E_CUDA, "pipelined sweep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     count_launch();
@@ -1549,13 +994,6 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
       fprintf(stderr, "  clk (stageA chainA publishSyncA collectA stageB chainB publishSyncB)\n");
     }
     cudaFree(d_dbg);
-  }
-  if (d_hits) {
-    unsigned hh[2];
-    cudaMemcpy(hh, d_hits, sizeof hh, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[pipe prefetch] %u pivots, entering column prefetched for %u (%.1f%%)\n", hh[0], hh[1],
-            hh[0] ? 100.0 * hh[1] / hh[0] : 0.0);
-    cudaFree(d_hits);
   }
   if (d_tl) {
     long long ht[4 * 24];
