@@ -10,21 +10,28 @@
 //     x <- (i == p_u) ? prow_u[j] : x - (f_u[i] * prow_u[j])
 // => every element still sees the same operations in the same order => same bits.
 //
-//   stream SEL (high priority): select(0) select(1) select(2) ...      one cluster launch per group
-//   stream SW                 :           sweep(0)  sweep(1)  ...      select(g+1) || sweep(g)
+//   stream SEL: select(0) select(1) select(2) ...      one cluster launch per group of K pivots
+//   stream SW :           sweep(0)  sweep(1)  ...      select(g+1) || sweep(g)
 //   select(g) waits for sweep(g-2) (its stale buffer / its group slot), sweep(g) waits for select(g).
+//   The two streams live in two CUDA green contexts: 16 SMs (one GPC-resident 16-CTA cluster) for the select,
+//   the other 132 SMs for the sweep -- two kernels on ordinary streams do not overlap reliably (whichever grid
+//   is dispatched first fills the machine; tools/gctx_probe.cu).
 //
-// k_pipe_select: one thread-block cluster (<= 16 CTAs x 256 threads).  Thread t owns row t+1 of the entering
-//   column (its factors of both pending groups stay on chip) and up to 4 columns of the pivot row (its slices
-//   of the current group's pivot rows stay in shared memory, the objective-row mirror and the RHS mirror in
-//   registers).  Row 0 is never gathered: T[0,e] is the objective-row mirror entry, and it comes back as the
-//   VALUE of the entering-column argmin.  The two argmins of a pivot are integer-key (value bits, index)
-//   reductions: redux.sync inside a warp, one DSMEM store per (warp, peer CTA), one cluster barrier, then
-//   every warp reduces the <= 128 candidates by itself (no block barrier, no second hop: the pivot element
-//   and the RHS of the winning row ride along with the candidate).
-// k_pipe_sweep: persistent CTAs; a CTA keeps ONE column group (its K pivot-row chunks live in registers) and
-//   walks a contiguous row range; factor records are staged in a shared-memory ring one row block ahead and
-//   the tableau loads run UNROLL rows ahead of the multiply/subtract chains across row-block boundaries.
+// k_pipe_select3: one thread-block cluster (<= 16 CTAs).  Threads 0..255 of a CTA own one row each of the
+//   entering column (factors of both pending groups in shared memory, RHS mirror in a register); every thread
+//   owns one column (768-thread CTAs, cfg2: 16 x 768 = C-1) or up to 4 (256-thread CTAs) of the pivot row:
+//   previous group's pivot-row entries in registers, this group's in shared memory, objective-row mirror in a
+//   register.  Row 0 is never gathered: T[0,e] is the objective-row mirror entry and comes back as the VALUE
+//   of the entering-column argmin; the RHS column is the rv mirror (the sweep does not touch it,
+//   k_pipe_writeback puts it back).  The two argmins of a pivot are integer-key (value bits, index)
+//   reductions: redux.sync in the warp, shared memory in the CTA, one DSMEM store per peer CTA, one cluster
+//   barrier, 16 candidates to collect; the pivot element and the RHS of the winning row ride along.  Nothing is
+//   stored to global memory inside the pivot loop (peers pull pivot-row / factor entries through DSMEM), so a
+//   barrier's release never waits on a store; everything the sweep needs is written once at the end.
+// k_pipe_sweep_ca: persistent CTAs; a CTA keeps ONE column group (its K pivot-row chunks live in registers) and
+//   walks a contiguous row range; tableau rows are staged through a cp.async shared-memory ring (thread-private
+//   16-byte cells, 14 rows in flight), factor records through a second ring one 32-row block ahead; two rows
+//   are updated together (4 independent FP64 dependency chains per thread).
 #include <cooperative_groups.h>
 #include <cuda.h>  // types only: the green-context entry points are resolved through cudaGetDriverEntryPoint
 
@@ -462,6 +469,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16_sa(unsigned smem_addr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -470,12 +480,14 @@ __device__ __forceinline__ void cp_async_wait() {
 
 template <int KM, int B, int NSTG, int RB>
 __global__ void __launch_bounds__(kSweepThreads, 2) k_pipe_sweep_ca(PipeSweepArgs a, int ncg, int nsplit) {
-  static_assert(NSTG % B == 0 && RB % B == 0 && RB <= 32 && B % 2 == 0, "ring geometry");
+  static_assert(NSTG % B == 0 && RB % B == 0 && RB <= 32 && B % 2 == 0 && (NSTG & (NSTG - 1)) == 0, "ring geometry");
+  constexpr unsigned kCell = sizeof(double2) * kSweepThreads;  // bytes between consecutive ring rows
   constexpr int PDB = NSTG / B - 1;  // batches in flight ahead of the one being computed
   constexpr int STG = (RB * KM / 2 + kSweepThreads - 1) / kSweepThreads;
   extern __shared__ __align__(16) unsigned char ca_smem[];
   double2* ring = reinterpret_cast<double2*>(ca_smem);                                  // [NSTG][256]
   double* sFb = reinterpret_cast<double*>(ca_smem + sizeof(double2) * NSTG * kSweepThreads);  // [2][RB*KM]
+  const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring + threadIdx.x);
   __shared__ unsigned sPiv[2];
   const int s = *a.count;
   if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -506,16 +518,18 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_pipe_sweep_ca(PipeSweepArg
     for (int u = 0; u < KM; u++) pr[u] = __ldg(reinterpret_cast<const double2*>(a.PR + (size_t)u * ld) + cc);
     const int nrows = r_hi - r_lo;
     const int nblk = (nrows + RB - 1) / RB;
-    const int nbat = (nrows + B - 1) / B;
-    const double2* sp = S2 + cc;
-    double2* dp = D2 + cc;
-    auto issue_batch = [&](int bi) {  // rows r_lo + bi*B .. +B-1 into their ring cells (one commit group)
-      if (bi < nbat) {
+    const double2* gpf = S2 + cc + (size_t)r_lo * ldv;  // next row to prefetch (running pointers: the loop
+    double2* gdst = D2 + cc + (size_t)r_lo * ldv;       // body is FP64-issue bound, every integer op counts)
+    int pf_left = nrows;                                // rows not yet requested
+    unsigned pf_cell = ring_sa;                         // shared-space address of the next ring cell to fill
+    const double2* cs_cell = ring + tid;                // next ring cell to consume
+    auto issue_batch = [&]() {  // the next B rows into their ring cells (one commit group, possibly empty)
 #pragma unroll
-        for (int k = 0; k < B; k++) {
-          const int rr = bi * B + k;
-          if (rr < nrows) cp_async16(ring + (size_t)(rr % NSTG) * kSweepThreads + tid, sp + (size_t)(r_lo + rr) * ldv);
-        }
+      for (int k = 0; k < B; k++) {
+        if (pf_left > 0) cp_async16_sa(pf_cell, gpf);
+        gpf += ldv;
+        pf_left--;
+        pf_cell = ring_sa + ((pf_cell - ring_sa + kCell) & (NSTG * kCell - 1));
       }
       cp_async_commit();
     };
@@ -550,47 +564,50 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_pipe_sweep_ca(PipeSweepArg
     double2 stg[STG];
     __syncthreads();  // the previous task is done with the factor ring
 #pragma unroll
-    for (int bi = 0; bi < PDB; bi++) issue_batch(bi);
+    for (int bi = 0; bi < PDB; bi++) issue_batch();
     stage_load(0, stg);
     stage_store(0, stg);
     __syncthreads();
     for (int b = 0; b < nblk; b++) {
       const int b0r = b * RB, b1r = min(nrows, b0r + RB);  // rows relative to r_lo
       if (b + 1 < nblk) stage_load(b + 1, stg);
-      const double* sf = sFb + (size_t)(b & 1) * RB * KM;
-      const unsigned pm = sPiv[b & 1];
+      const double2* fra = reinterpret_cast<const double2*>(sFb + (size_t)(b & 1) * RB * KM);
+      unsigned pm = sPiv[b & 1];
       for (int rr = b0r; rr < b1r; rr += B) {
-        const int bi = rr / B;
-        issue_batch(bi + PDB);
-        cp_async_wait<PDB>();  // everything but the PDB most recent groups has landed: batch bi is in the ring
+        issue_batch();
+        cp_async_wait<PDB>();  // everything but the PDB most recent groups has landed: this batch is in the ring
         double2 x[B];
 #pragma unroll
-        for (int k = 0; k < B; k++) x[k] = ring[(size_t)((rr + k) % NSTG) * kSweepThreads + tid];
+        for (int k = 0; k < B; k++) {
+          x[k] = *cs_cell;
+          cs_cell = ring + tid + (((cs_cell - (ring + tid)) + kSweepThreads) & (NSTG * kSweepThreads - 1));
+        }
 #pragma unroll
         for (int k = 0; k < B; k += 2) {
-          const int q = rr + k;
-          const double2* fra = reinterpret_cast<const double2*>(sf + (size_t)(q - b0r) * KM);
           const double2* frb = fra + KM / 2;
-          const unsigned two = (pm >> (q - b0r)) & 3u;  // CTA-uniform: pivot-row flags of rows q, q+1
-          if (q + 1 < b1r && two == 0u) {
+          const unsigned two = pm & 3u;  // CTA-uniform: pivot-row flags of rows q, q+1
+          if (rr + k + 1 < b1r && two == 0u) {
             blk_apply_fast2<KM>(x[k], x[k + 1], pr, fra, frb);
             if (active) {
-              dp[(size_t)(r_lo + q) * ldv] = x[k];
-              dp[(size_t)(r_lo + q + 1) * ldv] = x[k + 1];
+              gdst[0] = x[k];
+              gdst[ldv] = x[k + 1];
             }
           } else {
 #pragma unroll
             for (int kk = 0; kk < 2; kk++) {
-              const int qq = q + kk;
+              const int qq = rr + k + kk;
               if (qq < b1r) {
                 const double2* fr = kk ? frb : fra;
-                const bool slow = (pm >> (qq - b0r)) & 1u;
+                const bool slow = (pm >> kk) & 1u;
                 const double2 y = slow ? blk_apply_gen<KM>(x[k + kk], pr, fr, r_lo + qq, s, pu)
                                        : blk_apply_fast<KM>(x[k + kk], pr, fr);
-                if (active) dp[(size_t)(r_lo + qq) * ldv] = y;
+                if (active) gdst[(size_t)kk * ldv] = y;
               }
             }
           }
+          fra += KM;  // two rows of KM factors = KM double2
+          pm >>= 2;
+          gdst += 2 * (size_t)ldv;
         }
       }
       if (b + 1 < nblk) stage_store(b + 1, stg);
@@ -851,12 +868,13 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
   if (!resident) {
     cudaFuncSetAttribute(k_pipe_sweep_ca<PK, 4, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ca_smem_bytes(16));
     cudaFuncSetAttribute(k_pipe_sweep_ca<PK, 2, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ca_smem_bytes(16));
-    cudaFuncSetAttribute(k_pipe_sweep_ca<PK, 4, 12, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ca_smem_bytes(12));
+    cudaFuncSetAttribute(k_pipe_sweep_ca<PK, 4, 8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ca_smem_bytes(8));
+    cudaFuncSetAttribute(k_pipe_sweep_ca<PK, 2, 8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ca_smem_bytes(8));
     int r = 0;
     if (sweep_kind == 1)
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep_ca<PK, 4, 16, 32>, kSweepThreads, ca_smem_bytes(16));
     else if (sweep_kind >= 3)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep_ca<PK, 4, 12, 32>, kSweepThreads, ca_smem_bytes(12));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep_ca<PK, 4, 8, 32>, kSweepThreads, ca_smem_bytes(8));
     else
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_pipe_sweep_ca<PK, 2, 16, 32>, kSweepThreads, ca_smem_bytes(16));
     resident = std::max(1, r);
@@ -935,8 +953,6 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
     w.tl = (d_tl && g < TLG) ? d_tl + 4 * g : nullptr;
     if (sweep_kind == 1)
       k_pipe_sweep_ca<PK, 4, 16, 32><<<gs, kSweepThreads, ca_smem_bytes(16), P.s_sw>>>(w, ncg, nsplit);
-    else if (sweep_kind == 3)
-      k_pipe_sweep_ca<PK, 4, 12, 32><<<gs, kSweepThreads, ca_smem_bytes(12), P.s_sw>>>(w, ncg, nsplit);
     else if (sweep_kind == 4)
       k_pipe_sweep_ca<PK, 4, 8, 32><<<gs, kSweepThreads, ca_smem_bytes(8), P.s_sw>>>(w, ncg, nsplit);
     else if (sweep_kind == 5)
