@@ -682,12 +682,87 @@ static bool cache_give(int device, size_t bytes, double* ptr) {
   return true;
 }
 
+// Whole-handle cache: a destroyed big handle keeps its tableau buffers, scratch, streams, events and pinned
+// state mirror and is handed to the next tab_alloc of the same shape.  The host API creates one solver object
+// per Solve(); cudaFreeHost / cudaMallocHost / a dozen cudaFree alone cost 8 ms and sometimes hundreds.
+static std::vector<lpr_tab*> g_tab_cache;
+static size_t tab_bytes(const lpr_tab* h) {
+  return (size_t)h->Rcap * h->ld * sizeof(double) * (h->T2 ? 2 : 1);
+}
+static lpr_tab* tab_cache_take(int device, int rows, int cols, int rcap, int ccap) {
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  for (size_t i = 0; i < g_tab_cache.size(); i++) {
+    lpr_tab* c = g_tab_cache[i];
+    if (c->device == device && c->R == rows && c->C == cols && c->Rcap == rcap && c->Ccap == ccap) {
+      g_tab_cache.erase(g_tab_cache.begin() + i);
+      return c;
+    }
+  }
+  return nullptr;
+}
+static bool tab_cache_give(lpr_tab* h) {
+  if (tab_bytes(h) < (8u << 20)) return false;
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  size_t held = 0;
+  for (auto& c : g_buf_cache) held += c.bytes;
+  for (auto* c : g_tab_cache) held += tab_bytes(c);
+  if (held + tab_bytes(h) > cache_limit_bytes()) return false;
+  g_tab_cache.push_back(h);
+  return true;
+}
+int tab_destroy_now(lpr_tab* h);
+// out of device memory: give everything cached back to the driver (the caller retries once)
+static void cache_flush(int device) {
+  std::vector<lpr_tab*> tabs;
+  std::vector<CachedBuf> bufs;
+  {
+    std::lock_guard<std::mutex> lk(g_buf_mu);
+    for (size_t i = 0; i < g_tab_cache.size();)
+      if (g_tab_cache[i]->device == device) { tabs.push_back(g_tab_cache[i]); g_tab_cache.erase(g_tab_cache.begin() + i); } else i++;
+    for (size_t i = 0; i < g_buf_cache.size();)
+      if (g_buf_cache[i].device == device) { bufs.push_back(g_buf_cache[i]); g_buf_cache.erase(g_buf_cache.begin() + i); } else i++;
+  }
+  for (auto& b : bufs) cudaFree(b.ptr);
+  for (auto* t : tabs) {
+    double* T = t->T; double* T2 = t->T2;
+    t->T = t->T2 = nullptr;  // not back into the buffer cache
+    cudaFree(T);
+    cudaFree(T2);
+    tab_destroy_now(t);
+  }
+}
+
+static int tab_alloc_fresh(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab** out);
 int tab_alloc(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab** out) {
   if (!out) return fail(LPR_E_BADARG, "out is null");
   *out = nullptr;
   if (rows < 1 || cols < 2) return fail(LPR_E_BADARG, "tableau needs rows >= 1 and cols >= 2 (got %d x %d)", rows, cols);
   int rc = select_device(device);
   if (rc) return rc;
+  if (lpr_tab* c = tab_cache_take(device, rows, cols, std::max(rows, row_cap), std::max(cols, col_cap))) {
+    // same shape as a destroyed handle: reuse everything, reset what a fresh handle guarantees
+    cudaError_t e = cudaMemsetAsync(c->basis, 0xff, sizeof(int) * c->Rcap, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->st, 0, sizeof(TabState), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->ticket, 0, sizeof(unsigned), c->stream);
+    if (e != cudaSuccess) {
+      tab_destroy_now(c);
+      return fail(LPR_E_CUDA, "handle reuse failed: %s", cudaGetErrorString(e));
+    }
+    c->last_ms = 0.f;
+    c->last_sweep_us = 0.f;
+    *out = c;
+    return LPR_OK;
+  }
+  rc = tab_alloc_fresh(device, rows, cols, row_cap, col_cap, out);
+  if (rc == LPR_E_NOMEM) {
+    cache_flush(device);
+    rc = tab_alloc_fresh(device, rows, cols, row_cap, col_cap, out);
+  }
+  return rc;
+}
+
+static int tab_alloc_fresh(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab** out) {
+  *out = nullptr;
   lpr_tab* h = new (std::nothrow) lpr_tab();
   if (!h) return fail(LPR_E_NOMEM, "host allocation failed");
   h->device = device;
@@ -701,7 +776,7 @@ int tab_alloc(int device, int rows, int cols, int row_cap, int col_cap, lpr_tab*
   cudaError_t e;
 #define TRY(x)                                                                                   \
   if ((e = (x)) != cudaSuccess) {                                                                \
-    lpr_tab_destroy(h);                                                                          \
+    tab_destroy_now(h);                                                                          \
     return fail(e == cudaErrorMemoryAllocation ? LPR_E_NOMEM : LPR_E_CUDA, "%s failed: %s", #x, \
                 cudaGetErrorString(e));                                                          \
   }
@@ -968,31 +1043,7 @@ int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int*
   return LPR_OK;
 }
 
-}  // namespace lpr
-
-using namespace lpr;
-
-// =============================================================================================
-// C ABI
-// =============================================================================================
-extern "C" {
-
-int lpr_version(void) { return LPR_VERSION; }
-const char* lpr_last_error(void) { return last_error().c_str(); }
-int lpr_device_count(int* count) {
-  if (!count) return fail(LPR_E_BADARG, "count is null");
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess) {
-    *count = 0;
-    return fail(LPR_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
-  }
-  *count = n;
-  return LPR_OK;
-}
-int64_t lpr_launch_count(void) { return g_launches.load(); }
-
-int lpr_tab_destroy(lpr_tab* h) {
+int tab_destroy_now(lpr_tab* h) {
   if (!h) return LPR_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1023,6 +1074,39 @@ int lpr_tab_destroy(lpr_tab* h) {
   delete h;
   return LPR_OK;
 }
+
+}  // namespace lpr
+
+using namespace lpr;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int lpr_version(void) { return LPR_VERSION; }
+const char* lpr_last_error(void) { return last_error().c_str(); }
+int lpr_device_count(int* count) {
+  if (!count) return fail(LPR_E_BADARG, "count is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(LPR_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return LPR_OK;
+}
+int64_t lpr_launch_count(void) { return g_launches.load(); }
+
+int lpr_tab_destroy(lpr_tab* h) {
+  if (!h) return LPR_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->T && h->stream && h->st_host && tab_cache_give(h)) return LPR_OK;
+  return tab_destroy_now(h);
+}
+
 
 int lpr_tab_upload(lpr_tab* h, const double* host) {
   if (!h || !host) return fail(LPR_E_BADARG, "null argument");
