@@ -34,6 +34,11 @@ namespace LPR_381_Group_V22.Native
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_objective(IntPtr h, out double z);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_cutting_plane(IntPtr h, int maxCuts, out int status, out int nCuts, [Out] int[] cutLog, int cutLogCap);
 
+        // ---- SensitivityAnalyzer on a device-resident tableau (SensitivityAnalyzer.cs:609-723) ----------
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_sens_rebuild_basis(IntPtr h);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_sens_solution(IntPtr h, [Out] double[] x);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_sens_add_constraint(IntPtr h, double[] tech, double rhsMinusAx);
+
         // ---- revised simplex ---------------------------------------------------------------------
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
         public static extern int lpr_rev_create(int device, int m, int n, double[,] A, double[] b, double[] c, int isMin, out IntPtr h);

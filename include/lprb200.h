@@ -122,6 +122,16 @@ int lpr_tab_last_solve_ms(const lpr_tab* h, float* ms);
 /* average duration of the sweep kernel in the last lpr_tab_solve run with flags bit3 set (each sweep
  * launch bracketed by a CUDA event pair on the handle's stream; roofline measurement aid) */
 int lpr_tab_last_sweep_us(const lpr_tab* h, float* us);
+/* SensitivityAnalysis/SensitivityAnalyzer.cs on a device-resident final tableau:
+ * RebuildBasicsFromTableau :706-723 (basis[i-1] = first column that is a unit column with its 1 in row i,
+ * else -1); the solution rebuild of ReOptimize :158-164 (x has cols-1 entries, slacks included);
+ * AddNewConstraintNonInteractive :609-659 up to ResolveAll: tech has cols-1 entries, rhs_minus_ax =
+ * rhs - sum_j tech[j]*solution[j] as the caller computes it (:643-647); the handle needs one row and one
+ * column of headroom (row_cap / col_cap of lpr_tab_create), rows and cols grow by one, the RHS stays the
+ * last column.  ResolveAll = lpr_tab_sens_rebuild_basis + lpr_tab_solve(rule = LPR_RULE_SENS). */
+int lpr_tab_sens_rebuild_basis(lpr_tab* h);
+int lpr_tab_sens_solution(lpr_tab* h, double* x);
+int lpr_tab_sens_add_constraint(lpr_tab* h, const double* tech, double rhs_minus_ax);
 /* append one row (Gomory cut, CuttingPlaneSolver.cs:110) -- needs row headroom */
 int lpr_tab_append_row(lpr_tab* h, const double* row);
 /* Gomory fractional cut rows 1-4 of CuttingPlaneSolver.cs:76-107 generated on the device:

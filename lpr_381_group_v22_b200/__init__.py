@@ -9,6 +9,7 @@ from .io import Constraint, InputFileParser, add_cli_bound_rows, add_upper_bound
 from .simplex import (DualSimplexSolver, InvalidOperationException, PrimalSimplexSolver, PrimalSimplexSolver2,
                       RevisedPrimalSimplexSolver)
 from .tableau import DeviceTableau
+from .sensitivity_analysis import SensitivityAnalyzer
 from .integer_programming import (BranchAndBoundAdapter, BranchBoundSimplexSolver, CuttingPlaneSolver,
                                   KnapsackBranchBoundSimplex, KnapsackBranchBoundSolver)
 
@@ -16,5 +17,5 @@ __all__ = [
     "Constraint", "InputFileParser", "add_cli_bound_rows", "add_upper_bound_constraints", "DeviceTableau",
     "PrimalSimplexSolver", "PrimalSimplexSolver2", "DualSimplexSolver", "RevisedPrimalSimplexSolver",
     "BranchAndBoundAdapter", "BranchBoundSimplexSolver", "CuttingPlaneSolver", "KnapsackBranchBoundSimplex",
-    "KnapsackBranchBoundSolver", "InvalidOperationException", "LprError", "device_count", "launch_count",
+    "KnapsackBranchBoundSolver", "SensitivityAnalyzer", "InvalidOperationException", "LprError", "device_count", "launch_count",
 ]

@@ -61,6 +61,9 @@ SIGNATURES = {
     "lpr_tab_objective": (C.c_int, [vp, dp]),
     "lpr_tab_last_solve_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "lpr_tab_last_sweep_us": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "lpr_tab_sens_rebuild_basis": (C.c_int, [vp]),
+    "lpr_tab_sens_solution": (C.c_int, [vp, dp]),
+    "lpr_tab_sens_add_constraint": (C.c_int, [vp, dp, C.c_double]),
     "lpr_tab_append_row": (C.c_int, [vp, dp]),
     "lpr_tab_gomory_cut": (C.c_int, [vp, ip, dp, C.c_int]),
     "lpr_tab_cutting_plane": (C.c_int, [vp, C.c_int, ip, ip, ip, C.c_int]),

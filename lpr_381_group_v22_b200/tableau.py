@@ -162,6 +162,21 @@ class DeviceTableau:
         N.check(N.lib().lpr_tab_last_sweep_us(self._h, C.byref(us)))
         return us.value
 
+    # ---- SensitivityAnalyzer building blocks (SensitivityAnalyzer.cs:609-723) ----------------------------
+    def sens_rebuild_basis(self):
+        N.check(N.lib().lpr_tab_sens_rebuild_basis(self._h))
+
+    def sens_solution(self):
+        x = np.zeros(max(1, self.shape[1] - 1))
+        N.check(N.lib().lpr_tab_sens_solution(self._h, N.pd(x)))
+        return x[:self.shape[1] - 1]
+
+    def sens_add_constraint(self, tech, rhs_minus_ax):
+        tech = N.f64(tech)
+        if tech.shape != (self.shape[1] - 1,):
+            raise ValueError("tech must have cols-1 entries")
+        N.check(N.lib().lpr_tab_sens_add_constraint(self._h, N.pd(tech), float(rhs_minus_ax)))
+
     # ---- cutting plane / B&B building blocks ------------------------------------------------------
     def append_row(self, row):
         row = N.f64(row)

@@ -379,6 +379,66 @@ int orc_dual_solve(int R, int C, double* T, int max_iters, int print_steps, int*
 }
 
 /* ======================= SensitivityAnalyzer re-solve ===================================== */
+/* SensitivityAnalyzer.cs:64-83: GetBasicRow / IsPivotColumn */
+static int sens_basic_row(int R, int C, const double* T, int col) {
+  const double EPS = 1e-9;
+  for (int i = 1; i < R; i++) {
+    if (std::fabs(at(T, C, i, col) - 1.0) < EPS) {
+      bool pivot_col = true;
+      for (int k = 1; k < R; k++)
+        if (k != i && std::fabs(at(T, C, k, col)) > EPS) { pivot_col = false; break; }
+      if (pivot_col) return i;
+    }
+  }
+  return -1;
+}
+/* SensitivityAnalyzer.cs:706-723 */
+void orc_sens_rebuild_basis(int R, int C, const double* T, int* basis) {
+  const double EPS = 1e-9;
+  for (int i = 1; i < R; i++) {
+    basis[i - 1] = -1;
+    for (int j = 0; j < C - 1; j++) {
+      if (std::fabs(at(T, C, i, j) - 1.0) < EPS) {
+        bool pivot_col = true;
+        for (int k = 1; k < R; k++)
+          if (k != i && std::fabs(at(T, C, k, j)) > EPS) { pivot_col = false; break; }
+        if (pivot_col) { basis[i - 1] = j; break; }
+      }
+    }
+  }
+}
+/* SensitivityAnalyzer.cs:158-164 */
+void orc_sens_solution(int R, int C, const double* T, double* x) {
+  for (int j = 0; j < C - 1; j++) {
+    int r = sens_basic_row(R, C, T, j);
+    x[j] = (r == -1) ? 0.0 : at(T, C, r, C - 1);
+  }
+}
+/* SensitivityAnalyzer.cs:609-659 (the part before ResolveAll) */
+void orc_sens_add_constraint(int R, int C, const double* T, int* basis, const double* tech,
+                             double rhs_minus_ax, double* Tout) {
+  const int C2 = C + 1;
+  const int oldM = R - 1, oldNPlusM = C - 1;
+  for (int i = 0; i < (R + 1) * C2; i++) Tout[i] = 0.0;
+  for (int i = 0; i < R; i++) {
+    for (int j = 0; j < C - 1; j++) Tout[i * C2 + j] = at(T, C, i, j);
+    Tout[i * C2 + C] = at(T, C, i, C - 1);  // RHS moves one column to the right
+  }
+  const int newSlackCol = C - 1;
+  for (int i = 0; i < R + 1; i++) Tout[i * C2 + newSlackCol] = (i == R) ? 1.0 : 0.0;
+  for (int j = 0; j < oldNPlusM; j++) {
+    double coeff = -tech[j];
+    for (int pos = 0; pos < oldM; pos++) {
+      int basicCol = basis[pos];
+      coeff += tech[basicCol] * at(T, C, pos + 1, j);
+    }
+    Tout[R * C2 + j] = coeff;
+  }
+  Tout[R * C2 + C] = rhs_minus_ax;
+  Tout[0 * C2 + newSlackCol] = 0.0;
+  basis[R - 1] = newSlackCol;
+}
+
 /* SensitivityAnalysis/SensitivityAnalyzer.cs:168-201 (DualSimplexIfNeeded) then :121-166
  * (ReOptimize loop; the solution rebuild is done by the caller). */
 int orc_sens_resolve(int R, int C, double* T, int* basis, int max_iter, int* status,

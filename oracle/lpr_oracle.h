@@ -91,6 +91,18 @@ int orc_dual_solve(int R, int C, double* T, int max_iters, int print_steps, int*
 int orc_sens_resolve(int R, int C, double* T, int* basis, int max_iter, int* status,
                      int64_t* n_pivots, int* pivot_log, int64_t log_cap);
 
+/* RebuildBasicsFromTableau (SensitivityAnalyzer.cs:706-723) with GetBasicRow/IsPivotColumn (:64-83):
+ * basis[i-1] = first column j < C-1 with |T[i,j]-1| < 1e-9 whose other constraint rows are all
+ * within 1e-9 of 0, else -1 */
+void orc_sens_rebuild_basis(int R, int C, const double* T, int* basis);
+/* solution rebuild of ReOptimize (:158-164): x[j] = RHS of GetBasicRow(j) or 0, j < C-1 */
+void orc_sens_solution(int R, int C, const double* T, double* x);
+/* AddNewConstraintNonInteractive (:609-659) up to, not including, ResolveAll: Tout is (R+1) x (C+1);
+ * tech has C-1 entries; rhs_minus_ax = rhs - sum_j tech[j]*solution[j] (computed by the caller as
+ * the reference does, :643-647); basis gets the new slack column appended (R entries on return) */
+void orc_sens_add_constraint(int R, int C, const double* T, int* basis, const double* tech,
+                             double rhs_minus_ax, double* Tout);
+
 /* ---- CuttingPlaneSolver (IntegerProgramming/CuttingPlaneSolver.cs:64-229) --------------- */
 /* T has capacity row_cap x C; *R in/out (row 0 = objective).  max_cuts<0 = unlimited
  * (reference recursion is unbounded).  cut_log: per cut (chosen_row, pivot_col, n_dual, n_primal). */

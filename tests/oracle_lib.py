@@ -142,6 +142,29 @@ def sens_resolve(T, basis, max_iter=10000, log_cap=1 << 14):
     return dict(T=T, basis=basis, status=st.value, n_pivots=npv.value, log=log[:npv.value].copy())
 
 
+def sens_rebuild_basis(T):
+    T = f64(T); R, Cc = T.shape
+    basis = np.zeros(max(1, R - 1), dtype=np.int32)
+    lib().orc_sens_rebuild_basis(R, Cc, _d(T), _i(basis))
+    return basis[:R - 1]
+
+
+def sens_solution(T):
+    T = f64(T); R, Cc = T.shape
+    x = np.zeros(max(1, Cc - 1))
+    lib().orc_sens_solution(R, Cc, _d(T), _d(x))
+    return x[:Cc - 1]
+
+
+def sens_add_constraint(T, basis, tech, rhs_minus_ax):
+    T = f64(T); R, Cc = T.shape
+    b = np.zeros(R, dtype=np.int32); b[:R - 1] = basis
+    tech = f64(tech)
+    out = np.zeros((R + 1, Cc + 1))
+    lib().orc_sens_add_constraint(R, Cc, _d(T), _i(b), _d(tech), C.c_double(rhs_minus_ax), _d(out))
+    return out, b
+
+
 # ---------------------------------------------------------------- cutting plane
 def gomory_cut(T):
     T = f64(T); R, Cc = T.shape; cut = np.zeros(Cc)

@@ -203,3 +203,49 @@ def test_package_generators_match_oracle():
     w, v, cap = gen_knapsack(384, 100)
     w2, v2, cap2 = O.gen_knapsack(384, 100)
     assert np.array_equal(w, w2) and np.array_equal(v, v2) and cap == cap2
+
+
+@pytest.mark.parametrize("m,n,seed", [(5, 7, 1), (9, 6, 2), (12, 20, 3)])
+def test_sensitivity_add_constraint_against_highs(m, n, seed):
+    """AddNewConstraintNonInteractive + ResolveAll (SensitivityAnalyzer.cs:609-659, :98-209, :706-723) restated.
+    Reference quirk: the new row is built as -tech_j + sum_B tech_B * T[B, j] with slack +1 and
+    RHS rhs - a.x, i.e. its technical coefficients carry the opposite sign of the textbook row; the restatement
+    keeps that.  Fed with -tech the same code yields the textbook row, and then the re-solved tableau must be
+    optimal for the LP with the extra row (HiGHS objective, 1e-9 relative) -- which pins everything else."""
+    from scipy.optimize import linprog
+    A, b, c = O.gen_dense_lp(100 + seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    opt = O.primal_solve(T0, b0)
+    assert opt["status"] == O.OPTIMAL
+    T = opt["T"]
+    basis = O.sens_rebuild_basis(T)
+    assert sorted(basis.tolist()) == sorted(opt["basis"].tolist())
+    x = O.sens_solution(T)
+    tech = np.zeros(n + m)
+    tech[:n] = 1.0 + np.arange(n) % 3
+    rhs = 0.6 * float(tech @ x)          # cuts the current optimum off
+    ax = 0.0
+    for j in range(n + m):
+        ax += tech[j] * x[j]
+    for sign in (+1.0, -1.0):
+        T1, b1 = O.sens_add_constraint(T, basis, sign * tech, rhs - ax)
+        assert T1.shape == (m + 2, n + m + 2) and T1[-1, -1] < 0      # new row infeasible => dual simplex runs
+        assert T1[-1, n + m] == 1.0 and np.array_equal(T1[:-1, -1], T[:, -1])
+        b1 = O.sens_rebuild_basis(T1)
+        assert b1[-1] == n + m                                          # the new slack is basic in the new row
+        res = O.sens_resolve(T1, b1)
+        if sign > 0:
+            # the reference's own row: whatever it converges to satisfies its stopping rules (:85-96, :173-181)
+            if res["status"] == O.OPTIMAL:
+                Tr = res["T"]
+                nb = [j for j in range(Tr.shape[1] - 1) if j not in res["basis"].tolist()]
+                assert np.all(Tr[1:, -1] >= -1e-9) and np.all(Tr[0, nb] >= -1e-9)
+            continue
+        assert res["status"] == O.OPTIMAL and res["n_pivots"] >= 1
+        A2 = np.vstack([A, tech[:n]])
+        b2 = np.concatenate([b, [rhs]])
+        hs = linprog(-c, A_ub=A2, b_ub=b2, bounds=[(0, None)] * n, method="highs")
+        assert hs.status == 0
+        assert res["T"][0, -1] == pytest.approx(-hs.fun, rel=1e-9)
+        x2 = O.sens_solution(res["T"])
+        assert float(tech[:n] @ x2[:n]) == pytest.approx(rhs, rel=1e-9)  # the new row is tight

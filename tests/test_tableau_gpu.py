@@ -311,6 +311,54 @@ def test_sensitivity_resolve_rule(seed):
         assert_bit_equal(t.read(), ref["T"])
 
 
+@pytest.mark.parametrize("m,n,seed", [(5, 7, 1), (9, 6, 2), (12, 20, 3), (40, 90, 4), (130, 70, 5)])
+def test_sensitivity_add_constraint_on_device(m, n, seed):
+    """SensitivityAnalyzer(finalTableau, ...).AddNewConstraintNonInteractive(tech, rhs) with the tableau kept in
+    HBM (SensitivityAnalyzer.cs:22-41, :609-659, :706-723, ResolveAll :203-209) == the oracle, bit for bit,
+    twice in a row (the second constraint is added to the re-solved tableau)."""
+    A, b, c = O.gen_dense_lp(100 + seed, m, n)
+    s = L.PrimalSimplexSolver(list(c), [L.Constraint(A[i], "<=", b[i]) for i in range(m)], trace=False)
+    s.Solve()
+    T = s.GetFinalTableau()
+    with L.SensitivityAnalyzer(T, s.SolutionVector, s.FinalZ, s.BasicVariables) as sa:
+        Tref = np.array(T, dtype=np.float64)
+        Tref[0, -1] = s.FinalZ
+        bref = O.sens_rebuild_basis(Tref)
+        assert sa.BasicVariables == bref.tolist()
+        sol = list(s.SolutionVector)
+        for k in range(2):
+            cols = Tref.shape[1]
+            tech = np.zeros(cols - 1)
+            tech[:n] = 1.0 + (np.arange(n) + k) % 3
+            xfull = O.sens_solution(Tref)
+            rhs = (0.6 - 0.2 * k) * float(tech @ xfull)
+            ax = 0.0
+            for j in range(min(len(tech), len(sol))):
+                ax += tech[j] * sol[j]
+            T1, _ = O.sens_add_constraint(Tref, bref, tech, rhs - ax)
+            b1 = O.sens_rebuild_basis(T1)
+            ref = O.sens_resolve(T1, b1)
+            if ref["status"] != O.OPTIMAL:   # the reference throws (:151 / :194): so does the mirror
+                with pytest.raises(L.InvalidOperationException):
+                    sa.AddNewConstraintNonInteractive(tech, rhs)
+                assert sa.LastPivotLog == [tuple(p) for p in ref["log"].tolist()]
+                assert_bit_equal(sa.CurrentTableau, ref["T"])
+                break
+            r = sa.AddNewConstraintNonInteractive(tech, rhs)
+            assert r["status"] == ref["status"] == O.OPTIMAL
+            assert r["log"].tolist() == ref["log"].tolist()
+            assert sa.BasicVariables == ref["basis"].tolist()
+            assert_bit_equal(sa.CurrentTableau, ref["T"])
+            assert sa.CurrentZ == ref["T"][0, -1]
+            assert_bit_equal(np.array(sa.solutionVector), O.sens_solution(ref["T"]))
+            mm = ref["T"].shape[0] - 1
+            assert sa.ShadowPrices() == ref["T"][0, ref["T"].shape[1] - 1 - mm:-1].tolist()
+            Tref, bref, sol = ref["T"], O.sens_rebuild_basis(ref["T"]), O.sens_solution(ref["T"]).tolist()
+        with pytest.raises(L.LprError):   # headroom exhausted after 16 additions is an error, not a crash
+            for _ in range(20):
+                sa._tab.sens_add_constraint(np.zeros(sa._tab.shape[1] - 1), 1.0)
+
+
 def test_edge_shapes_and_errors():
     # smallest legal tableau, single constraint / single variable
     T = np.array([[-1.0, 0.0, 0.0], [2.0, 1.0, 4.0]])
