@@ -34,6 +34,12 @@ namespace LPR_381_Group_V22.Native
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_objective(IntPtr h, out double z);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_cutting_plane(IntPtr h, int maxCuts, out int status, out int nCuts, [Out] int[] cutLog, int cutLogCap);
 
+        // ---- RunBranchAndBound entry (BranchBoundSimplexSolver.cs:28-113, :281-468) -------------------------
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern int lpr_tab_create_bb(int device, int n, int m, double[] objective, double[,] consPadded, int stride, int[] len, int rowCap, int colCap, out IntPtr h);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern int lpr_tab_bb_node_solve_ex(IntPtr h, int isMinimization, long maxPivots, out int status, out long nPivots, [Out] int[] pivotLog, long logCap);
+
         // ---- SensitivityAnalyzer on a device-resident tableau (SensitivityAnalyzer.cs:609-723) ----------
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_sens_rebuild_basis(IntPtr h);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_sens_solution(IntPtr h, [Out] double[] x);

@@ -172,6 +172,16 @@ int lpr_rev_last_refactor_info(const lpr_rev* h, double* residual, double* flops
 int lpr_tab_round4(lpr_tab* h);                                  /* RoundTableau :552-567      */
 int lpr_tab_bb_node_solve(lpr_tab* h, int64_t max_pivots, int* status, int64_t* n_pivots,
                           int* pivot_log, int64_t log_cap);     /* DoDualSimplex :289-468     */
+/* the same with DoDualSimplex's isMinimization argument (optimal when the objective row is <= 0, entering =
+ * smallest positive entry :209-213, :346-348); only RunBranchAndBound's initial solve :1271 passes true */
+int lpr_tab_bb_node_solve_ex(lpr_tab* h, int is_minimization, int64_t max_pivots, int* status,
+                             int64_t* n_pivots, int* pivot_log, int64_t log_cap);
+/* DualSimplexSolverBB.FormulateTableau / PrepareInput (:28-113, :281-287) built on the device: cons is m rows
+ * of `stride` doubles, row i holds len[i] entries [coefficients..., rhs, type flag] (flag 1 = ">=": the row is
+ * negated; rows longer than n+2, like the ones ConfigureProblem :1233-1251 appends, spill into the slack
+ * columns exactly as in the reference).  The tableau is (m+1) x (n+m+1). */
+int lpr_tab_create_bb(int device, int n, int m, const double* objective, const double* cons, int stride,
+                      const int* len, int row_cap, int col_cap, lpr_tab** out);
 int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound, int type,
                               lpr_tab** child);                  /* AddConstraint :694-803     */
 int lpr_tab_bb_branch_var(lpr_tab* h, int n_vars, int* var, double* value,

@@ -83,6 +83,8 @@ SIGNATURES = {
     "lpr_rev_last_refactor_info": (C.c_int, [vp, dp, dp]),
     "lpr_tab_round4": (C.c_int, [vp]),
     "lpr_tab_bb_node_solve": (C.c_int, [vp, C.c_int64, ip, lp, ip, C.c_int64]),
+    "lpr_tab_bb_node_solve_ex": (C.c_int, [vp, C.c_int, C.c_int64, ip, lp, ip, C.c_int64]),
+    "lpr_tab_create_bb": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, ip, C.c_int, C.c_int, C.POINTER(vp)]),
     "lpr_tab_bb_add_constraint": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(vp)]),
     "lpr_tab_bb_branch_var": (C.c_int, [vp, C.c_int, ip, dp, dp]),
     "lpr_bb_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int64, dp, dp, ip, lp, lp,

@@ -34,6 +34,7 @@ struct BBLp {
   // state
   int status, src, phase, do_sweep, leave, enter, dropped, entered_primal;
   long long npiv, max_piv;
+  int is_min;  // DoDualSimplex's isMinimization (only the initial solve of RunBranchAndBound :1271 passes true)
 };
 
 struct BBEval {  // per node outputs of k_bb_eval
@@ -57,6 +58,31 @@ struct BBAddc {  // one AddConstraint job
 constexpr int kBBT = 1024;
 
 // ---- elementwise helpers --------------------------------------------------------------------
+// FormulateTableau :28-113 on the device: row 0 = -objective; constraint row i (ragged: [coefficients..., rhs,
+// type flag], len[i] entries) is negated entirely when its flag == 1 (-1 * x, so zeros become -0.0 as in the
+// reference), every entry but rhs/flag goes to columns 0.., the rhs to the last column, and row i gets a 1 at
+// column i+n-1 whatever its type (:103-109).
+__global__ void k_bb_formulate(double* T, int ld, int n, int m, const double* obj, const double* cons, int stride,
+                               const int* len) {
+  const int W = n + m + 1;
+  const size_t total = (size_t)(m + 1) * ld;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(q / ld), j = (int)(q - (size_t)i * ld);
+    double v = 0.0;
+    if (i == 0) {
+      if (j < n) v = -obj[j];
+    } else if (j < W) {
+      const double* row = cons + (size_t)(i - 1) * stride;
+      const int L = len[i - 1];
+      const bool neg = row[L - 1] == 1.0;
+      if (j < L - 2) v = neg ? __dmul_rn(-1.0, row[j]) : row[j];
+      if (j == W - 1) v = neg ? __dmul_rn(-1.0, row[L - 2]) : row[L - 2];
+      if (j == i + n - 1 && j < W - 1) v = 1.0;
+    }
+    T[q] = v;
+  }
+}
+
 __global__ void k_bb_negzero(BBLp* lps) {
   BBLp& lp = lps[blockIdx.y];
   double* T = lp.buf[lp.src];
@@ -144,7 +170,7 @@ __global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps) {
     } else {
       int notopt = 0;  // :345-348
       for (int j = tid; j < C - 1; j += blockDim.x)
-        if (!(T[j] >= 0.0)) notopt++;
+        if (lp.is_min ? !(T[j] <= 0.0) : !(T[j] >= 0.0)) notopt++;
       notopt = block_sum_int(notopt, smi);
       if (!notopt) { finish(LPR_OPTIMAL, src, npiv, 0); return; }
       phase = 1;
@@ -153,7 +179,7 @@ __global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps) {
   if (phase == 1 && r < 0) {
     int notopt = 0;  // :367-373
     for (int j = tid; j < C - 1; j += blockDim.x)
-      if (!(T[j] >= 0.0)) notopt++;
+      if (lp.is_min ? !(T[j] <= 0.0) : !(T[j] >= 0.0)) notopt++;
     notopt = block_sum_int(notopt, smi);
     if (!notopt) {
       go_final = true;
@@ -161,8 +187,9 @@ __global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps) {
       finish(LPR_ITER_LIMIT, src, npiv, 0);
       return;
     } else {
-      // PerformPrimalPivot :203-279 (isMinimization == false)
-      c = block_first_min(C - 1, [&](int j, double& val) { val = T[j]; return val < 0.0; }, sm);
+      // PerformPrimalPivot :203-279: Min() of the negative entries (max) / of the positive entries (min)
+      const int is_min = lp.is_min;
+      c = block_first_min(C - 1, [&](int j, double& val) { val = T[j]; return is_min ? val > 0.0 : val < 0.0; }, sm);
       if (c < 0 || R <= 1) {
         go_final = true;
       } else {
@@ -1030,8 +1057,53 @@ int lpr_tab_round4(lpr_tab* h) {
   return LPR_OK;
 }
 
+int lpr_tab_create_bb(int device, int n, int m, const double* objective, const double* cons, int stride,
+                      const int* len, int row_cap, int col_cap, lpr_tab** out) {
+  if (!out) return fail(LPR_E_BADARG, "out is null");
+  *out = nullptr;
+  if (n < 1 || m < 0 || !objective || (m > 0 && (!cons || !len)) || stride < 2)
+    return fail(LPR_E_BADARG, "bad model (n=%d m=%d)", n, m);
+  for (int i = 0; i < m; i++)
+    if (len[i] < 2 || len[i] > stride || len[i] - 2 > n + m)
+      return fail(LPR_E_BADARG, "constraint row %d has %d entries (need coefficients, rhs, type; at most %d)", i, len[i],
+                  std::min(stride, n + m + 2));
+  lpr_tab* h = nullptr;
+  int rc = tab_alloc(device, m + 1, n + m + 1, row_cap, col_cap, &h);
+  if (rc) return rc;
+  double *d_obj = nullptr, *d_cons = nullptr;
+  int* d_len = nullptr;
+  cudaError_t e = cudaMalloc(&d_obj, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_cons, sizeof(double) * std::max<size_t>(1, (size_t)m * stride));
+  if (e == cudaSuccess) e = cudaMalloc(&d_len, sizeof(int) * std::max(1, m));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_obj, objective, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && m > 0)
+    e = cudaMemcpyAsync(d_cons, cons, sizeof(double) * (size_t)m * stride, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && m > 0) e = cudaMemcpyAsync(d_len, len, sizeof(int) * m, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    const size_t total = (size_t)(m + 1) * h->ld;
+    k_bb_formulate<<<(int)std::max<size_t>(1, std::min<size_t>((size_t)h->sms * 8, (total + 255) / 256)), 256, 0,
+                     h->stream>>>(h->T, h->ld, n, m, d_obj, d_cons, stride, d_len);
+    count_launch();
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d_obj);
+  cudaFree(d_cons);
+  cudaFree(d_len);
+  if (e != cudaSuccess) {
+    lpr_tab_destroy(h);
+    return fail(LPR_E_CUDA, "create_bb: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return LPR_OK;
+}
+
 int lpr_tab_bb_node_solve(lpr_tab* h, int64_t max_pivots, int* status, int64_t* n_pivots, int* pivot_log,
                           int64_t log_cap) {
+  return lpr_tab_bb_node_solve_ex(h, 0, max_pivots, status, n_pivots, pivot_log, log_cap);
+}
+
+int lpr_tab_bb_node_solve_ex(lpr_tab* h, int is_minimization, int64_t max_pivots, int* status, int64_t* n_pivots,
+                             int* pivot_log, int64_t log_cap) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
   int rc = select_device(h->device);
   if (rc) return rc;
@@ -1056,6 +1128,7 @@ int lpr_tab_bb_node_solve(lpr_tab* h, int64_t max_pivots, int* status, int64_t* 
   h_lp->ld = h->ld;
   h_lp->status = LPR_RUNNING;
   h_lp->max_piv = max_pivots;
+  h_lp->is_min = is_minimization ? 1 : 0;
   // note: the building block returns the un-rounded final tableau (rounding is the caller's step :1124)
   LPR_CUDA(cudaMemcpyAsync(d_lp, h_lp, sizeof(BBLp), cudaMemcpyHostToDevice, h->stream));
   {

@@ -58,13 +58,41 @@ class BranchBoundSimplexSolver:
         def __init__(self, device=0):
             self._device = device
 
+        @staticmethod
+        def _strip_flags(constraints):
+            """what FormulateTableau does to the CALLER's rows (:42-56): negate the '>=' rows, drop the flags"""
+            for row in constraints:
+                if row[-1] == 1:
+                    for j in range(len(row)):
+                        row[j] = -1 * row[j]
+            for row in constraints:
+                del row[-1]
+
+        def FormulateTableau(self, objectiveFunction, constraints):  # :28-113
+            """Builds the tableau on the device and, like the reference, mutates `constraints` in place."""
+            with DeviceTableau.from_bb_model(objectiveFunction, constraints, device=self._device) as t:
+                T = t.read()
+            self._strip_flags(constraints)
+            return T
+
+        def PrepareInput(self, objectiveFunction, constraints, isMinimization):  # :281-287
+            surplusCount = sum(1 for c in constraints if c[-1] == 1 or c[-1] == 2)
+            slackCount = sum(1 for c in constraints if c[-1] != 1 and c[-1] != 2)
+            tableau = self.FormulateTableau(objectiveFunction, constraints)
+            return tableau, isMinimization, surplusCount, slackCount, len(objectiveFunction)
+
         def DoDualSimplex(self, objectiveFunction, constraints, isMinimization, tableauOverride=None):
-            """Only the tableauOverride form (the one B&B uses, :1107/:1174) is supported.  Returns
-            (final_tableau, optimalValue or None, pivot_rows, pivot_cols)."""
+            """:289-468.  Returns (final_tableau, optimalValue or None, pivot_rows, pivot_cols).  Without
+            tableauOverride the tableau comes from FormulateTableau (built on the device, never read back) and
+            isMinimization selects the optimality test / entering rule; with it (the form B&B uses, :1107/:1174)
+            the given tableau is solved."""
             if tableauOverride is None:
-                raise NotImplementedError("FormulateTableau path (RunBranchAndBound) is out of scope: SURVEY 8(f) row 4")
-            with DeviceTableau.from_host(tableauOverride, device=self._device) as t:
-                r = t.bb_node_solve()
+                t = DeviceTableau.from_bb_model(objectiveFunction, constraints, device=self._device)
+                self._strip_flags(constraints)
+            else:
+                t = DeviceTableau.from_host(tableauOverride, device=self._device)
+            with t:
+                r = t.bb_node_solve(is_min=bool(isMinimization))
                 T = t.read()
             if r["status"] != N.OPTIMAL:
                 return T, None, None, None
@@ -98,6 +126,29 @@ class BranchBoundSimplexSolver:
             with DeviceTableau.from_host(baseTableau, device=self._device) as t:
                 with t.bb_add_constraint(len(self.objectiveCoefficients), var, bound, typ) as ch:
                     return ch.read(), None
+
+        @staticmethod
+        def ConfigureProblem(objective, constraints):  # :1233-1251 (appends to the caller's list)
+            n = len(objective)
+            for i in range(n):
+                row = [0.0] * (n + 3)   # one entry longer than a normal row: the reference's own quirk
+                row[i] = 1.0
+                row[n + 1] = 1.0
+                constraints.append(row)
+            return objective, constraints
+
+        def RunBranchAndBound(self, objectivePassed, constraintsPassed, isMin, max_nodes=20):  # :1253-1298
+            """LP relaxation from the model rows (x_i <= 1 rows appended), 4-d.p. rounding, then the DFS.
+            Returns (bestSolution or None, bestValue) like ExecuteBranchAndBound."""
+            self.objectiveCoefficients = list(objectivePassed)
+            constraintMatrix = [list(r) for r in constraintsPassed]
+            self.objectiveCoefficients, constraintMatrix = self.ConfigureProblem(self.objectiveCoefficients, constraintMatrix)
+            solver = BranchBoundSimplexSolver.DualSimplexSolverBB(self._device)
+            T, opt, _, _ = solver.DoDualSimplex(list(self.objectiveCoefficients), [list(r) for r in constraintMatrix], isMin)
+            if opt is None:
+                raise InvalidOperationException("initial LP relaxation failed")  # RoundAllTableaux(null) throws :1273
+            self.simplexTableaux = [self.RoundTableau(T)]
+            return self.ExecuteBranchAndBound(self.simplexTableaux, False, max_nodes)
 
         def ExecuteBranchAndBound(self, initialTableaux, enablePruning=False, max_nodes=20):  # :1006-1233
             r = _solve_bb(initialTableaux[-1], len(self.objectiveCoefficients), enablePruning, max_nodes, self._device)

@@ -26,6 +26,23 @@ class DeviceTableau:
         return cls(h)
 
     @classmethod
+    def from_bb_model(cls, objective, constraints, device=0, row_cap=0, col_cap=0):
+        """DualSimplexSolverBB.FormulateTableau (BranchBoundSimplexSolver.cs:28-113) executed on the device;
+        constraints are the reference's ragged rows [coefficients..., rhs, type flag]."""
+        obj = N.f64(objective)
+        m = len(constraints)
+        stride = max([len(c) for c in constraints] + [2])
+        cons = np.zeros((max(1, m), stride))
+        ln = np.zeros(max(1, m), dtype=np.int32)
+        for i, c in enumerate(constraints):
+            cons[i, :len(c)] = c
+            ln[i] = len(c)
+        h = N.vp()
+        N.check(N.lib().lpr_tab_create_bb(device, len(obj), m, N.pd(obj), N.pd(cons), stride, N.pi(ln), row_cap, col_cap,
+                                          C.byref(h)))
+        return cls(h)
+
+    @classmethod
     def from_model(cls, objective, constraints, is_maximization=True, device=0):
         """PrimalSimplexSolver..ctor (PrimalSimplexSolver.cs:27-87) executed on the device."""
         n = len(objective)
@@ -197,11 +214,12 @@ class DeviceTableau:
     def round4(self):
         N.check(N.lib().lpr_tab_round4(self._h))
 
-    def bb_node_solve(self, max_pivots=-1, log_cap=4096):
+    def bb_node_solve(self, max_pivots=-1, log_cap=4096, is_min=False):
         st = C.c_int()
         npv = C.c_int64()
         log = np.zeros((log_cap, 2), dtype=np.int32)
-        N.check(N.lib().lpr_tab_bb_node_solve(self._h, max_pivots, C.byref(st), C.byref(npv), N.pi(log), log_cap))
+        N.check(N.lib().lpr_tab_bb_node_solve_ex(self._h, int(bool(is_min)), max_pivots, C.byref(st), C.byref(npv),
+                                                 N.pi(log), log_cap))
         return dict(status=st.value, n_pivots=npv.value, log=log[:min(npv.value, log_cap)].copy())
 
     def bb_add_constraint(self, n_vars, var, bound, typ):

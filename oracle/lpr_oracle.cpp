@@ -755,13 +755,17 @@ int orc_bb_dual_pivot(int R, int C, const double* T, double* out, int* prow, int
   if (pcol) *pcol = c;
   return 1;
 }
-/* PerformPrimalPivot :203-279, isMinimization == false */
+/* PerformPrimalPivot :203-279 */
+static int bb_primal_pivot_ex(int R, int C, const double* T, double* out, int* prow, int* pcol, int is_min);
 int orc_bb_primal_pivot(int R, int C, const double* T, double* out, int* prow, int* pcol) {
+  return bb_primal_pivot_ex(R, C, T, out, prow, pcol, 0);
+}
+static int bb_primal_pivot_ex(int R, int C, const double* T, double* out, int* prow, int* pcol, int is_min) {
   int c = -1;
   double pv = 0.0;
-  for (int j = 0; j < C - 1; j++) {  // :211-213 min of the negatives; IndexOf => first
+  for (int j = 0; j < C - 1; j++) {  // :209-213 Min() of the negatives (max) / of the positives (min); IndexOf => first
     double v = T[j];
-    if (v < 0 && (c == -1 || v < pv)) {
+    if ((is_min ? v > 0 : v < 0) && (c == -1 || v < pv)) {
       pv = v;
       c = j;
     }
@@ -805,6 +809,11 @@ int orc_bb_primal_pivot(int R, int C, const double* T, double* out, int* prow, i
 /* DoDualSimplex with tableauOverride :289-468 */
 int orc_bb_node_solve(int R, int C, double* T, int64_t max_pivots, int64_t* n_pivots,
                       int* pivot_log, int64_t log_cap) {
+  return orc_bb_node_solve_ex(R, C, T, 0, max_pivots, n_pivots, pivot_log, log_cap);
+}
+/* DoDualSimplex :289-468 with its isMinimization argument (only RunBranchAndBound :1271 passes true) */
+int orc_bb_node_solve_ex(int R, int C, double* T, int is_min, int64_t max_pivots, int64_t* n_pivots,
+                         int* pivot_log, int64_t log_cap) {
   const size_t N = (size_t)R * C;
   std::vector<double> a(T, T + N), b(N), prev;
   double* cur = a.data();
@@ -816,9 +825,9 @@ int orc_bb_node_solve(int R, int C, double* T, int64_t max_pivots, int64_t* n_pi
       if (!(at(X, C, i, C - 1) >= lim)) return false;
     return true;
   };
-  auto obj_opt = [&](const double* X) {
+  auto obj_opt = [&](const double* X) {  // :346-348
     for (int j = 0; j < C - 1; j++)
-      if (!(X[j] >= 0)) return false;
+      if (is_min ? !(X[j] <= 0) : !(X[j] >= 0)) return false;
     return true;
   };
   int result = ORC_OPTIMAL;
@@ -849,7 +858,7 @@ int orc_bb_node_solve(int R, int C, double* T, int64_t max_pivots, int64_t* n_pi
         break;
       }
       int pr, pc;
-      if (!orc_bb_primal_pivot(R, C, cur, nxt, &pr, &pc)) break;  // :375-387
+      if (!bb_primal_pivot_ex(R, C, cur, nxt, &pr, &pc, is_min)) break;  // :375-387
       log_pivot(pivot_log, log_cap, npiv, pr, pc);
       std::swap(cur, nxt);
       have_prev = true;
@@ -867,6 +876,25 @@ int orc_bb_node_solve(int R, int C, double* T, int64_t max_pivots, int64_t* n_pi
   if (result == ORC_OPTIMAL || result == ORC_ITER_LIMIT) std::memcpy(T, cur, N * sizeof(double));
   if (n_pivots) *n_pivots = npiv;
   return result;
+}
+/* FormulateTableau :28-113.  cons is m rows of `stride` doubles, row i has len[i] entries
+ * [coefficients..., rhs, type flag]; rows whose flag == 1 are negated entirely (:42-51), the flag is dropped,
+ * every entry but the last is copied into columns 0.. (:96-99: a row longer than n+2, like the ones
+ * ConfigureProblem :1233-1251 appends, spills its extra 0 into the first slack column), the last entry is
+ * the RHS, and row i gets a 1 at column i+n-1 (:103-109) whatever its type.  T is (m+1) x (n+m+1). */
+void orc_bb_formulate(int n, int m, const double* objective, const double* cons, int stride, const int* len, double* T) {
+  const int W = n + m + 1;
+  for (int i = 0; i < (m + 1) * W; i++) T[i] = 0.0;
+  for (int j = 0; j < n; j++) T[j] = -objective[j];
+  for (int i = 0; i < m; i++) {
+    const double* row = cons + (size_t)i * stride;
+    const int L = len[i];
+    const double sgn = (row[L - 1] == 1) ? -1.0 : 1.0;
+    for (int j = 0; j < L - 2; j++) T[(i + 1) * W + j] = (sgn < 0) ? -1 * row[j] : row[j];
+    T[(i + 1) * W + W - 1] = (sgn < 0) ? -1 * row[L - 2] : row[L - 2];
+  }
+  for (int i = 1; i <= m; i++)
+    if (n < W - 1) T[i * W + i + n - 1] = 1;
 }
 /* IdentifyBasicVariables :642-692 */
 int orc_bb_identify_basic(int R, int C, const double* T, int* basic) {

@@ -122,6 +122,10 @@ int orc_bb_primal_pivot(int R, int C, const double* T, double* out, int* prow, i
  * returns ORC_OPTIMAL (optimalValue != null) / ORC_INFEASIBLE (null or exception). */
 int orc_bb_node_solve(int R, int C, double* T, int64_t max_pivots, int64_t* n_pivots,
                       int* pivot_log, int64_t log_cap);
+int orc_bb_node_solve_ex(int R, int C, double* T, int is_min, int64_t max_pivots, int64_t* n_pivots,
+                         int* pivot_log, int64_t log_cap);
+/* FormulateTableau :28-113 (ragged rows [coefficients..., rhs, type flag]); T is (m+1) x (n+m+1) */
+void orc_bb_formulate(int n, int m, const double* objective, const double* cons, int stride, const int* len, double* T);
 /* IdentifyBasicVariables :642-692 (on an already rounded tableau). returns count */
 int orc_bb_identify_basic(int R, int C, const double* T, int* basic);
 /* AddConstraint :694-803 with one new constraint e_var (<= if type==0, >= if type==1).

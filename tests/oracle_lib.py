@@ -207,6 +207,38 @@ def bb_node_solve(T, max_pivots=-1, log_cap=4096):
     return dict(status=res, T=T, n_pivots=npv.value, log=log[:min(npv.value, log_cap)].copy())
 
 
+def bb_node_solve_ex(T, is_min, max_pivots=-1, log_cap=4096):
+    T = f64(T).copy(); R, Cc = T.shape
+    npv = C.c_int64(); log = np.zeros((log_cap, 2), dtype=np.int32)
+    st = lib().orc_bb_node_solve_ex(R, Cc, _d(T), int(bool(is_min)), C.c_int64(max_pivots), C.byref(npv), _i(log),
+                                    C.c_int64(log_cap))
+    return dict(T=T, status=st, n_pivots=npv.value, log=log[:min(npv.value, log_cap)].copy())
+
+
+def bb_formulate(objective, constraints):
+    """FormulateTableau :28-113 on the reference's ragged rows [coefficients..., rhs, type flag]"""
+    obj = f64(objective); n = len(obj); m = len(constraints)
+    stride = max([len(c) for c in constraints] + [2])
+    cons = np.zeros((max(1, m), stride)); ln = np.zeros(max(1, m), dtype=np.int32)
+    for i, c in enumerate(constraints):
+        cons[i, :len(c)] = c; ln[i] = len(c)
+    T = np.zeros((m + 1, n + m + 1))
+    lib().orc_bb_formulate(n, m, _d(obj), _d(cons), stride, _i(ln), _d(T))
+    return T
+
+
+def bb_configure_problem(objective, constraints):
+    """ConfigureProblem :1233-1251: one row x_i <= 1 per variable, each ONE ENTRY LONGER than a normal row"""
+    n = len(objective)
+    cons = [list(c) for c in constraints]
+    for i in range(n):
+        row = [0.0] * (n + 3)
+        row[i] = 1.0
+        row[n + 1] = 1.0
+        cons.append(row)
+    return list(objective), cons
+
+
 def bb_identify_basic(T):
     T = f64(T); basic = np.zeros(T.shape[1], dtype=np.int32)
     k = lib().orc_bb_identify_basic(T.shape[0], T.shape[1], _d(T), _i(basic))

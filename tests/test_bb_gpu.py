@@ -146,3 +146,55 @@ def test_bb_pool_batched_equals_sequential(seed, m, n):
         assert z.value == ref["z"]
         assert_bit_equal(x, ref["x"], "incumbent")
     assert total >= 1
+
+
+@pytest.mark.parametrize("m,n,seed", [(1, 6, 0), (5, 8, 1), (12, 9, 2), (30, 40, 3)])
+def test_formulate_and_run_branch_and_bound(m, n, seed):
+    """DualSimplexSolverBB.FormulateTableau / PrepareInput / DoDualSimplex(isMin) and
+    BranchAndBound.ConfigureProblem / RunBranchAndBound (BranchBoundSimplexSolver.cs:28-113, :281-468,
+    :1233-1298) on the device == the oracle, bit for bit."""
+    rng = np.random.default_rng(seed)
+    if m == 1:
+        obj = [2.0, 3.0, 3.0, 5.0, 2.0, 4.0]
+        cons = [[11.0, 8.0, 6.0, 14.0, 10.0, 10.0, 40.0, 0.0]]
+    else:
+        A, b, c = O.gen_dense_ip(200 + seed, m, n)
+        obj = list(c)
+        cons = [list(A[i]) + [float(b[i]), 0.0] for i in range(m)]
+        cons[1] = [1.0] * n + [1.0, 1.0]          # a '>=' row (flag 1): sum x >= 1
+    ref_o, ref_c = O.bb_configure_problem(obj, cons)
+    Tref = O.bb_formulate(ref_o, ref_c)
+    solver = L.BranchBoundSimplexSolver.DualSimplexSolverBB()
+    mine = [list(r) for r in ref_c]
+    T = solver.FormulateTableau(list(ref_o), mine)
+    assert_bit_equal(T, Tref, "FormulateTableau")
+    assert all(len(a) == len(r) - 1 for a, r in zip(mine, ref_c))      # the caller's rows lost their flags (:54-56)
+    if m > 1:
+        assert mine[1][0] == -1.0                                        # and the '>=' row was negated in place
+    _, is_min, sur, slk, nobj = solver.PrepareInput(list(ref_o), [list(r) for r in ref_c], False)
+    assert (is_min, sur, slk, nobj) == (False, 0 if m == 1 else 1, len(ref_c) - (0 if m == 1 else 1), len(obj))
+    for is_min in (False, True):
+        ref = O.bb_node_solve_ex(Tref, is_min)
+        Td, opt, prow, pcol = solver.DoDualSimplex(list(ref_o), [list(r) for r in ref_c], is_min)
+        if ref["status"] == O.OPTIMAL:
+            assert_bit_equal(Td, ref["T"], f"DoDualSimplex isMin={is_min}")
+            assert opt == ref["T"][0, -1] and list(zip(prow, pcol)) == [tuple(p) for p in ref["log"].tolist()]
+        else:
+            assert opt is None
+    # the whole entry point
+    ref = O.bb_node_solve_ex(Tref, False)
+    bb = L.BranchBoundSimplexSolver.BranchAndBound()
+    if ref["status"] != O.OPTIMAL:
+        with pytest.raises(L.InvalidOperationException):
+            bb.RunBranchAndBound(obj, cons, False)
+        return
+    rbb = O.bb_solve(O.bb_round(ref["T"]), len(obj), prune=False, max_nodes=20)
+    x, z = bb.RunBranchAndBound(obj, cons, False)
+    assert bb.LastRun["nodes"] == rbb["nodes"]
+    assert bb.LastRun["node_log"].tolist() == rbb["node_log"].tolist()
+    if rbb["has_solution"]:
+        assert x == rbb["x"].tolist() and z == rbb["z"]
+    else:
+        assert x is None
+    if m == 1:
+        assert x == [0, 1, 1, 1, 0, 1] and z == 15.0

@@ -249,3 +249,33 @@ def test_sensitivity_add_constraint_against_highs(m, n, seed):
         assert res["T"][0, -1] == pytest.approx(-hs.fun, rel=1e-9)
         x2 = O.sens_solution(res["T"])
         assert float(tech[:n] @ x2[:n]) == pytest.approx(rhs, rel=1e-9)  # the new row is tight
+
+
+def test_run_branch_and_bound_entry_restated():
+    """RunBranchAndBound (BranchBoundSimplexSolver.cs:1253-1298): ConfigureProblem :1233-1251 appends x_i <= 1 rows
+    that are one entry longer than a model row, FormulateTableau :28-113 negates '>=' rows (flag 1) and puts the
+    identity at column i+n-1, DoDualSimplex :289-468 solves (isMin picks the optimality test / entering rule)."""
+    from scipy.optimize import linprog
+    obj = [2.0, 3.0, 3.0, 5.0, 2.0, 4.0]                       # model A (data/TextFile.txt)
+    cons = [[11.0, 8.0, 6.0, 14.0, 10.0, 10.0, 40.0, 0.0]]
+    o2, c2 = O.bb_configure_problem(obj, cons)
+    assert len(c2) == 7 and len(c2[1]) == 9 and c2[3][2] == 1.0 and c2[3][7] == 1.0 and c2[3][8] == 0.0
+    T = O.bb_formulate(o2, c2)
+    assert T.shape == (8, 14) and T[0, :6].tolist() == [-2, -3, -3, -5, -2, -4]
+    assert T[1, :6].tolist() == [11, 8, 6, 14, 10, 10] and T[1, -1] == 40 and T[1, 6] == 1
+    assert np.array_equal(T[2:, 6:13], np.eye(7)[1:]) and np.all(T[2:, -1] == 1)   # the spilled 0 lands on column 6
+    r = O.bb_node_solve_ex(T, False)
+    hs = linprog(-np.array(obj), A_ub=[cons[0][:6]], b_ub=[40.0], bounds=[(0, 1)] * 6, method="highs")
+    assert r["status"] == O.OPTIMAL and r["T"][0, -1] == pytest.approx(-hs.fun, rel=1e-12)
+    bb = O.bb_solve(O.bb_round(r["T"]), 6, prune=False, max_nodes=20)
+    assert bb["x"].tolist() == [0, 1, 1, 1, 0, 1] and bb["z"] == 15.0          # Appendix C3's incumbent
+    # a '>=' row (flag 1) is negated entirely, zeros become -0.0 like `-1 * x` in C#
+    Tg = O.bb_formulate([1.0, 2.0], [[1.0, 0.0, 3.0, 1.0], [1.0, 1.0, 10.0, 0.0]])
+    assert Tg[1].tolist() == [-1.0, -0.0, 1.0, 0.0, -3.0] and np.signbit(Tg[1, 1])
+    assert Tg[2].tolist() == [1.0, 1.0, 0.0, 1.0, 10.0]
+    # isMin: optimal iff the objective row is <= 0; entering = smallest positive entry (:209-213, :346-348)
+    Tm = np.array([[3.0, 1.0, 0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 0.0, 4.0], [1.0, 3.0, 0.0, 1.0, 6.0]])
+    rm = O.bb_node_solve_ex(Tm, True)
+    assert rm["log"][0].tolist()[1] == 1 and rm["status"] == O.OPTIMAL   # column 1 (value 1) before column 0 (value 3)
+    r0 = O.bb_node_solve_ex(np.array([[-3.0, -1.0, 0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 0.0, 4.0], [1.0, 3.0, 0.0, 1.0, 6.0]]), True)
+    assert r0["n_pivots"] == 0 and r0["status"] == O.OPTIMAL             # all <= 0: already "optimal" for a min
