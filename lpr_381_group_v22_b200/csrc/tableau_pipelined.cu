@@ -133,6 +133,8 @@ constexpr int PRT = 256;  // rows owned per CTA (threads 0 .. PRT-1)
 template <int NT, int NC>
 __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
   constexpr int NW = NT / 32;
+  constexpr int PPR = (NT > 512) ? 8 : PK;  // previous-group pivot-row entries kept in registers (80-register
+                                            // budget at 768 threads); the other PK - PPR live in shared memory
   cg::cluster_group cluster = cg::this_cluster();
   const int ncta = (int)cluster.num_blocks();
   const int crank = (int)cluster.block_rank();
@@ -143,13 +145,15 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
   double* sPR = reinterpret_cast<double*>(smem_raw);   // [NC][PK][NT]  this group's pivot-row slices
   double* sFp = sPR + (size_t)NC * PK * NT;            // [PK][PRT]     previous group's factors of my row
   double* sFc = sFp + (size_t)PK * PRT;                // [PK][PRT]     this group's factors of my row
-  CandA* slotA = reinterpret_cast<CandA*>(sFc + (size_t)PK * PRT);  // [PMAXCTA]  one candidate per CTA
+  double* sPP = sFc + (size_t)PK * PRT;                // [NC][PK - PPR][NT] previous group's pivot-row slices
+  CandA* slotA = reinterpret_cast<CandA*>(sPP + (size_t)NC * (PK - PPR) * NT);  // [PMAXCTA]  one candidate per CTA
   CandB* slotB = reinterpret_cast<CandB*>(slotA + PMAXCTA);         // [PMAXCTA]
   CandA* wA = reinterpret_cast<CandA*>(slotB + PMAXCTA);            // [PRT / 32] per-warp candidates of this CTA
   CandB* wB = reinterpret_cast<CandB*>(wA + PRT / 32);              // [32]
   __shared__ double s_pe[2 * PK], s_fp[2 * PK], s_f0[PK], s_prc[PK];
   __shared__ int s_pu[2 * PK], s_el[PK];
   __shared__ unsigned s_hit;
+  __shared__ double s_zobj, s_lastpiv;  // uniform scalars only thread 0 needs: kept out of the register file
   TabState* st = a.st;
   const int R = a.R, C = a.C, ld = a.ld;
   const int CW = C - 1;
@@ -190,16 +194,22 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
     }
   }
   double r0[NC];
-  double ppv[NC][PK];
+  double ppv[NC][PPR];
 #pragma unroll
   for (int c = 0; c < NC; c++) {
     const int j = gid + c * nthr;
     r0[c] = (j < CW) ? a.row0[j] : 0.0;
 #pragma unroll
-    for (int u = 0; u < PK; u++) ppv[c][u] = (j < CW && u < sp) ? __ldg(a.PRp + (size_t)u * ld + j) : 0.0;
+    for (int u = 0; u < PK; u++) {
+      const double v = (j < CW && u < sp) ? __ldg(a.PRp + (size_t)u * ld + j) : 0.0;
+      if (u < PPR) ppv[c][u] = v;
+      else sPP[((size_t)c * (PK - PPR) + (u - PPR)) * NT + tid] = v;
+    }
   }
-  double zobj = (gid == 0) ? a.row0[CW] : 0.0;
-  double last_piv = 0.0;
+  if (tid == 0) {
+    s_zobj = a.row0[CW];  // objective value T[0, C-1] (only CTA 0's copy is written back)
+    s_lastpiv = 0.0;
+  }
   __syncthreads();
   int term = LPR_RUNNING;
   int s = 0;
@@ -323,21 +333,23 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
       if (j < CW) {
         double xx = x[c];
         double* prv = sPR + (size_t)c * PK * NT + tid;
+        const double* ppm = sPP + (size_t)c * (PK - PPR) * NT + tid;
+        auto prev_entry = [&](int u) { return (u < PPR) ? ppv[c][u < PPR ? u : 0] : ppm[(u - PPR) * NT]; };
         if (!hit_p) {
           if (sp == PK) {
 #pragma unroll
-            for (int u = 0; u < PK; u++) xx = __dsub_rn(xx, __dmul_rn(s_fp[u], ppv[c][u]));
+            for (int u = 0; u < PK; u++) xx = __dsub_rn(xx, __dmul_rn(s_fp[u], prev_entry(u)));
           } else {
 #pragma unroll
             for (int u = 0; u < PK; u++)
-              if (u < sp) xx = __dsub_rn(xx, __dmul_rn(s_fp[u], ppv[c][u]));
+              if (u < sp) xx = __dsub_rn(xx, __dmul_rn(s_fp[u], prev_entry(u)));
           }
 #pragma unroll 4
           for (int u = 0; u < s; u++) xx = __dsub_rn(xx, __dmul_rn(s_fp[PK + u], prv[u * NT]));
         } else {
 #pragma unroll
           for (int u = 0; u < PK; u++)
-            if (u < sp) xx = (p == s_pu[u]) ? ppv[c][u] : __dsub_rn(xx, __dmul_rn(s_fp[u], ppv[c][u]));
+            if (u < sp) xx = (p == s_pu[u]) ? prev_entry(u) : __dsub_rn(xx, __dmul_rn(s_fp[u], prev_entry(u)));
           for (int u = 0; u < s; u++) {
             const double pv = prv[u * NT];
             xx = (p == s_pu[PK + u]) ? pv : __dsub_rn(xx, __dmul_rn(s_fp[PK + u], pv));
@@ -361,11 +373,11 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
       rv = (i == p) ? prc : __dsub_rn(rv, __dmul_rn(col, prc));
       hit_row |= (i == p);
     }
-    zobj = __dsub_rn(zobj, __dmul_rn(f0, prc));
-    last_piv = piv;
     if (tid == 0) {
       s_pu[PK + s] = p;
       s_prc[s] = prc;
+      s_zobj = __dsub_rn(s_zobj, __dmul_rn(f0, prc));
+      s_lastpiv = piv;
     }
     {
       int src;
@@ -426,14 +438,14 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
       }
       if (a.basis) a.basis[pu - 1] = eu;  // :142
     }
-    a.row0[CW] = zobj;
+    a.row0[CW] = s_zobj;
     *a.count = s;
     st->group_base = npiv0;
     st->npiv = npiv;
     st->enter = e;
     st->enter_val = f0;
     if (s > 0) {
-      st->pivot = last_piv;
+      st->pivot = s_lastpiv;
       st->leave = s_pu[PK + s - 1];
     }
     if (term != LPR_RUNNING) st->status = term;
@@ -781,8 +793,9 @@ static void pipe_geometry3(const lpr_tab* h, int* ncta, int* nt, int* nc) {
   }
 }
 static size_t pipe_select3_smem(int nt, int nc) {
-  return sizeof(double) * ((size_t)nc * PK * nt + 2 * (size_t)PK * PRT) + sizeof(CandA) * (PMAXCTA + PRT / 32) +
-         sizeof(CandB) * (PMAXCTA + 32);
+  const int ppr = nt > 512 ? 8 : PK;  // as in the kernel
+  return sizeof(double) * ((size_t)nc * PK * nt + 2 * (size_t)PK * PRT + (size_t)nc * (PK - ppr) * nt) +
+         sizeof(CandA) * (PMAXCTA + PRT / 32) + sizeof(CandB) * (PMAXCTA + 32);
 }
 
 using SelectFn = void (*)(PipeArgs);
