@@ -439,6 +439,8 @@ for cap in (-1, 7, 17, 40):
 print(json.dumps(out))
 """
     env = dict(os.environ, LPR_TAB_BLOCK=str(block))
+    if block == 3:   # also cover the fallback without the green-context SM partition (two priority streams)
+        env["LPR_PIPE_GREEN"] = "0"
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
     out = json.loads(res.stdout.strip().splitlines()[-1])
