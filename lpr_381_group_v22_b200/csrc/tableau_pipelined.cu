@@ -71,6 +71,7 @@ struct PipeArgs {
   int K;               // pivots to select in this launch
   long long* dbg;      // optional: per-phase clock64 stamps of the last launch
   long long* tl;       // optional: [select start, select end, sweep start, sweep end] globaltimer of this group
+  int prefetch;        // bulk L2 prefetch of the CTA-local best row while the candidates cross the cluster
 };
 
 struct CandA {
@@ -286,6 +287,18 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
       c.piv = __shfl_sync(FULLM, c.piv, src);
       c.rhs = __shfl_sync(FULLM, c.rhs, src);
       if (lane < ncta) cluster.map_shared_rank(slotA, lane)[crank] = c;
+      if (a.prefetch && c.idx != INT_MAX && lane < 8) {
+        // head start for the pivot-row read: the leaving row is one of the <= 16 CTA-local best rows; pull
+        // mine towards L2 with the TMA unit (asynchronous proxy: no load/store the barrier would wait for)
+        const unsigned bytes = (unsigned)(((size_t)CW * sizeof(double) + 15) & ~(size_t)15);
+        const unsigned per = ((bytes / 8) + 15) & ~15u;
+        const unsigned off = lane * per;
+        if (off < bytes) {
+          const char* rp = reinterpret_cast<const char*>(T + (size_t)(c.idx + 1) * ld) + off;
+          const unsigned n = min(per, bytes - off);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rp), "r"(n) : "memory");
+        }
+      }
     }
     cluster.sync();
     stamp(q, 3);
@@ -867,6 +880,7 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
     LPR_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 8 * PK));
     LPR_CUDA(cudaMemset(d_dbg, 0, sizeof(long long) * 8 * PK));
   }
+  static const int prefetch_on = getenv("LPR_PIPE_PREFETCH") ? atoi(getenv("LPR_PIPE_PREFETCH")) : 0;
   long long* d_tl = nullptr;
   const int TLG = 24;
   if (getenv("LPR_PIPE_TIMELINE")) {
@@ -930,6 +944,7 @@ int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int6
     a.K = K;
     a.dbg = d_dbg;
     a.tl = (d_tl && g < TLG) ? d_tl + 4 * g : nullptr;
+    a.prefetch = prefetch_on;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta);
     cfg.blockDim = dim3(nt);
