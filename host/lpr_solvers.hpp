@@ -3,8 +3,10 @@
 // The reference is compiled C# (no .NET toolchain in this image), so the host layer above liblprb200 is
 // also provided in C++: same class names, member names, argument meaning and error behaviour as
 //   Simplex/PrimalSimplexSolver.cs, Simplex/RevisedPrimalSimplexSolver.cs, Simplex/PrimalSimplexSolver2.cs,
-//   Simplex/DualSimplex.cs, IntegerProgramming/CuttingPlaneSolver.cs, IntegerProgramming/BranchAndBoundAdapter.cs
-//   and the knapsack classes of Program.cs:430-471.
+//   Simplex/DualSimplex.cs, IntegerProgramming/CuttingPlaneSolver.cs, IntegerProgramming/BranchAndBoundAdapter.cs,
+//   BranchBoundSimplexSolver.{DualSimplexSolverBB, BranchAndBound} (RunBranchAndBound entry),
+//   SensitivityAnalysis/SensitivityAnalyzer.cs (re-optimisation members) and the knapsack classes of
+//   Program.cs:430-471.
 // Header only; link with -llprb200.  No arithmetic happens here: every pivot runs on the GPU.
 #pragma once
 #include <cmath>
@@ -271,6 +273,111 @@ struct BranchAndBoundAdapter {
   }
 };
 
+// IntegerProgramming/BranchBoundSimplexSolver.cs: the RunBranchAndBound entry (:28-113, :281-468, :1233-1298).
+// Model rows are the reference's ragged [coefficients..., rhs, type flag] lists.
+struct BranchBoundSimplexSolver {
+  class DualSimplexSolverBB {
+   public:
+    // FormulateTableau :28-113 built on the device; returns the (m+1) x (n+m+1) tableau row-major and, like the
+    // reference, negates the '>=' rows of the caller's list and drops the flags
+    std::vector<double> FormulateTableau(const std::vector<double>& objectiveFunction,
+                                         std::vector<std::vector<double>>& constraints, int* rows = nullptr,
+                                         int* cols = nullptr) {
+      lpr_tab* h = Create(objectiveFunction, constraints);
+      int R = 0, C = 0, ld = 0;
+      lpr_tab_dims(h, &R, &C, &ld);
+      std::vector<double> T((size_t)R * C);
+      int rc = lpr_tab_read(h, T.data());
+      lpr_tab_destroy(h);
+      Check(rc);
+      StripFlags(constraints);
+      if (rows) *rows = R;
+      if (cols) *cols = C;
+      return T;
+    }
+    // DoDualSimplex :289-468 without tableauOverride; returns false when the reference returns optimalValue = null
+    bool DoDualSimplex(const std::vector<double>& objectiveFunction, std::vector<std::vector<double>>& constraints,
+                       bool isMinimization, std::vector<double>& finalTableau, int& rows, int& cols,
+                       double& optimalValue, bool round4 = false) {
+      lpr_tab* h = Create(objectiveFunction, constraints);
+      StripFlags(constraints);
+      int st = 0, ld = 0;
+      int64_t npiv = 0;
+      int rc = lpr_tab_bb_node_solve_ex(h, isMinimization ? 1 : 0, -1, &st, &npiv, nullptr, 0);
+      if (rc == LPR_OK && round4) rc = lpr_tab_round4(h);  // RoundAllTableaux :540-593
+      if (rc == LPR_OK) rc = lpr_tab_dims(h, &rows, &cols, &ld);
+      if (rc == LPR_OK) {
+        finalTableau.assign((size_t)rows * cols, 0.0);
+        rc = lpr_tab_read(h, finalTableau.data());
+      }
+      lpr_tab_destroy(h);
+      Check(rc);
+      if (st != LPR_OPTIMAL) return false;
+      optimalValue = finalTableau[(size_t)cols - 1];
+      return true;
+    }
+
+   private:
+    static lpr_tab* Create(const std::vector<double>& obj, const std::vector<std::vector<double>>& cons) {
+      const int n = (int)obj.size(), m = (int)cons.size();
+      int stride = 2;
+      for (auto& c : cons) stride = std::max<int>(stride, (int)c.size());
+      std::vector<double> flat((size_t)std::max(1, m) * stride, 0.0);
+      std::vector<int> len(std::max(1, m), 0);
+      for (int i = 0; i < m; i++) {
+        std::copy(cons[i].begin(), cons[i].end(), flat.begin() + (size_t)i * stride);
+        len[i] = (int)cons[i].size();
+      }
+      lpr_tab* h = nullptr;
+      Check(lpr_tab_create_bb(0, n, m, obj.data(), flat.data(), stride, len.data(), 0, 0, &h));
+      return h;
+    }
+    static void StripFlags(std::vector<std::vector<double>>& cons) {  // :42-56
+      for (auto& row : cons)
+        if (!row.empty() && row.back() == 1)
+          for (auto& v : row) v = -1 * v;
+      for (auto& row : cons)
+        if (!row.empty()) row.pop_back();
+    }
+  };
+
+  class BranchAndBound {
+   public:
+    std::vector<double> objectiveCoefficients;
+    static void ConfigureProblem(const std::vector<double>& objective, std::vector<std::vector<double>>& constraints) {
+      const int n = (int)objective.size();  // :1233-1251: rows one entry longer than a model row
+      for (int i = 0; i < n; i++) {
+        std::vector<double> row(n + 3, 0.0);
+        row[i] = 1;
+        row[n + 1] = 1;
+        constraints.push_back(row);
+      }
+    }
+    // :1253-1298; returns (bestSolution, bestValue); an empty solution == the reference's null
+    std::pair<std::vector<double>, double> RunBranchAndBound(const std::vector<double>& objectivePassed,
+                                                             const std::vector<std::vector<double>>& constraintsPassed,
+                                                             bool isMin, int64_t maxNodes = 20) {
+      objectiveCoefficients = objectivePassed;
+      auto cons = constraintsPassed;
+      ConfigureProblem(objectiveCoefficients, cons);
+      DualSimplexSolverBB solver;
+      std::vector<double> T;
+      int R = 0, C = 0;
+      double opt = 0;
+      if (!solver.DoDualSimplex(objectiveCoefficients, cons, isMin, T, R, C, opt, /*round4=*/true))
+        throw InvalidOperationException("initial LP relaxation failed");
+      const int n = (int)objectiveCoefficients.size();
+      std::vector<double> x(n);
+      double z = 0;
+      int has = 0, st = 0;
+      int64_t nodes = 0, piv = 0;
+      Check(lpr_bb_solve(0, R, C, T.data(), n, 0, maxNodes, x.data(), &z, &has, &nodes, &piv, nullptr, nullptr, 0, &st));
+      if (!has) return {std::vector<double>(), -std::numeric_limits<double>::infinity()};
+      return {x, z};
+    }
+  };
+};
+
 // Program.cs:444-463 (the class is missing from the reference; contract from the call site)
 struct KnapsackItem {
   int Id;
@@ -310,4 +417,83 @@ struct KnapsackBranchBoundSolver {  // Program.cs:468 DP arbiter
 };
 
 }  // namespace IntegerProgramming
+
+namespace SensitivityAnalysis {
+
+// SensitivityAnalysis/SensitivityAnalyzer.cs: ctor :22-41, ResolveAll :203-209 (RebuildBasicsFromTableau :706-723,
+// DualSimplexIfNeeded :168-201, ReOptimize :121-166), AddNewConstraintNonInteractive :609-659, ShadowPrices
+// :212-222.  The tableau stays on the device between calls.
+class SensitivityAnalyzer {
+ public:
+  SensitivityAnalyzer(const std::vector<double>& finalTableau, int rows, int cols, const std::vector<double>& solution,
+                      double zValue, const std::vector<int>& basicVariables, int headroom = 16)
+      : solutionVector_(solution), finalZ_(zValue) {
+    std::vector<double> T(finalTableau);
+    T[(size_t)cols - 1] = zValue;  // :33
+    Check(lpr_tab_create(0, rows, cols, rows + headroom, cols + headroom, T.data(), &h_));
+    if (!basicVariables.empty()) lpr_tab_set_basis(h_, basicVariables.data());
+    Check(lpr_tab_sens_rebuild_basis(h_));  // :36
+  }
+  ~SensitivityAnalyzer() { lpr_tab_destroy(h_); }
+  SensitivityAnalyzer(const SensitivityAnalyzer&) = delete;
+  SensitivityAnalyzer& operator=(const SensitivityAnalyzer&) = delete;
+
+  double CurrentZ() const { return finalZ_; }
+  const std::vector<double>& SolutionVector() const { return solutionVector_; }
+  std::vector<double> CurrentTableau(int* rows = nullptr, int* cols = nullptr) const {
+    int R = 0, C = 0, ld = 0;
+    Check(lpr_tab_dims(h_, &R, &C, &ld));
+    std::vector<double> T((size_t)R * C);
+    Check(lpr_tab_read(h_, T.data()));
+    if (rows) *rows = R;
+    if (cols) *cols = C;
+    return T;
+  }
+  std::vector<int> BasicVariables() const {
+    int R = 0, C = 0, ld = 0;
+    Check(lpr_tab_dims(h_, &R, &C, &ld));
+    std::vector<int> b(std::max(1, R - 1));
+    Check(lpr_tab_get_basis(h_, b.data()));
+    b.resize(R - 1);
+    return b;
+  }
+  std::vector<double> ShadowPrices() const {  // :212-222
+    int R = 0, C = 0, ld = 0;
+    Check(lpr_tab_dims(h_, &R, &C, &ld));
+    std::vector<double> row0(C);
+    Check(lpr_tab_read_row(h_, 0, row0.data()));
+    const int m = R - 1, n = C - m - 1;
+    return std::vector<double>(row0.begin() + n, row0.begin() + n + m);
+  }
+  void ResolveAll(int maxIter = 10000) {  // :203-209
+    Check(lpr_tab_sens_rebuild_basis(h_));
+    int st = 0;
+    int64_t npiv = 0;
+    Check(lpr_tab_solve(h_, LPR_RULE_SENS, maxIter, 0, &st, &npiv, nullptr, 0));
+    if (st == LPR_INFEASIBLE) throw InvalidOperationException("Infeasible after RHS change (dual simplex).");
+    if (st == LPR_UNBOUNDED) throw InvalidOperationException("Unbounded during re-optimization.");
+    if (st == LPR_ITER_LIMIT) throw InvalidOperationException("Re-optimization exceeded iteration limit.");
+    Check(lpr_tab_objective(h_, &finalZ_));
+    int R = 0, C = 0, ld = 0;
+    Check(lpr_tab_dims(h_, &R, &C, &ld));
+    solutionVector_.assign(C - 1, 0.0);
+    Check(lpr_tab_sens_solution(h_, solutionVector_.data()));
+  }
+  void AddNewConstraintNonInteractive(const std::vector<double>& tech, double rhs) {  // :609-659
+    int R = 0, C = 0, ld = 0;
+    Check(lpr_tab_dims(h_, &R, &C, &ld));
+    if ((int)tech.size() < C - 1) throw ArgumentException("tech needs one coefficient per tableau column");
+    double aX = 0.0;
+    for (size_t j = 0; j < std::min(tech.size(), solutionVector_.size()); j++) aX += tech[j] * solutionVector_[j];
+    Check(lpr_tab_sens_add_constraint(h_, tech.data(), rhs - aX));
+    ResolveAll();
+  }
+
+ private:
+  lpr_tab* h_ = nullptr;
+  std::vector<double> solutionVector_;
+  double finalZ_;
+};
+
+}  // namespace SensitivityAnalysis
 }  // namespace LPR_381_Group_V22

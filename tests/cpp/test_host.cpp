@@ -41,6 +41,31 @@ int main() {
   REQUIRE((primal.BasicVariables() == std::vector<int>{4, 7, 1, 2, 3, 11, 5}));
   auto bb = IntegerProgramming::BranchAndBoundAdapter::SolveFromPrimal(primal, false, false);
   REQUIRE(bb.second == 15.0 && (bb.first == std::vector<double>{0, 1, 1, 1, 0, 1}));
+  // RunBranchAndBound entry (BranchBoundSimplexSolver.cs:1253-1298): same incumbent from the model rows
+  {
+    IntegerProgramming::BranchBoundSimplexSolver::BranchAndBound rb;
+    auto r = rb.RunBranchAndBound(obj, {{11, 8, 6, 14, 10, 10, 40, 0}}, false);
+    REQUIRE(r.second == 15.0 && (r.first == std::vector<double>{0, 1, 1, 1, 0, 1}));
+    IntegerProgramming::BranchBoundSimplexSolver::DualSimplexSolverBB ds;
+    std::vector<std::vector<double>> ge = {{1, 0, 3, 1}, {1, 1, 10, 0}};
+    int R = 0, C = 0;
+    auto T = ds.FormulateTableau({1, 2}, ge, &R, &C);
+    REQUIRE(R == 3 && C == 5 && T[5] == -1.0 && std::signbit(T[6]) && T[9] == -3.0 && T[13] == 1.0);
+    REQUIRE(ge[0].size() == 3 && ge[0][0] == -1.0 && ge[1].size() == 3);
+  }
+  // SensitivityAnalyzer on the device-resident final tableau: add x5 <= 0 (reference sign quirk included)
+  {
+    SensitivityAnalysis::SensitivityAnalyzer sa(primal.FinalTableau, primal.Rows, primal.Cols, primal.SolutionVector,
+                                                primal.FinalZ, primal.BasicVariables());
+    REQUIRE((sa.BasicVariables() == std::vector<int>{4, 7, 1, 2, 3, 11, 5}));
+    std::vector<double> tech(primal.Cols - 1, 0.0);
+    tech[4] = 1.0;
+    sa.AddNewConstraintNonInteractive(tech, 0.0);
+    REQUIRE(sa.CurrentZ() == 0x1.e2be2be2be2bep+3);
+    REQUIRE(sa.SolutionVector()[3] == 0x1.b6db6db6db6dcp-1 && sa.SolutionVector()[4] == 0x1.999999999999ap-2);
+    REQUIRE((sa.BasicVariables() == std::vector<int>{4, 7, 1, 2, 3, 11, 5, 10}));
+    REQUIRE(sa.ShadowPrices().size() == 8);
+  }
   // cutting plane on the final tableau (Appendix C4)
   {
     std::vector<double> o(primal.FinalTableau.begin(), primal.FinalTableau.begin() + primal.Cols);
