@@ -802,7 +802,7 @@ static void pipe_geometry3(const lpr_tab* h, int* ncta, int* nt, int* nc) {
     if (rows > c * PRT) continue;
     if (cw <= c * 256) { *ncta = c; *nt = 256; *nc = 1; return; }
     if (cw <= c * 768) { *ncta = c; *nt = 768; *nc = 1; return; }
-    if (cw <= c * 256 * 4) { *ncta = c; *nt = 256; *nc = (cw + c * 256 - 1) / (c * 256); return; }
+    if (cw <= c * 256 * 4) { *ncta = c; *nt = 256; *nc = 4; return; }  // (3 c 256, 4 c 256]: four columns per thread
   }
 }
 static size_t pipe_select3_smem(int nt, int nc) {
@@ -814,8 +814,7 @@ static size_t pipe_select3_smem(int nt, int nc) {
 using SelectFn = void (*)(PipeArgs);
 static SelectFn pipe_select3_fn(int nt, int nc) {
   if (nt == 768) return k_pipe_select3<768, 1>;
-  return nc == 1 ? k_pipe_select3<256, 1>
-                 : (nc == 2 ? k_pipe_select3<256, 2> : (nc == 3 ? k_pipe_select3<256, 3> : k_pipe_select3<256, 4>));
+  return nc == 1 ? k_pipe_select3<256, 1> : k_pipe_select3<256, 4>;  // the geometry only yields 1 or 4
 }
 static bool pipe_prepare3(int ncta, int nt, int nc) {
   static int ok[2][5][PMAXCTA + 1] = {};

@@ -406,7 +406,7 @@ def test_nan_and_inf_do_not_hang():
 
 
 @pytest.mark.parametrize("m,n,seed", [(8, 16, 1), (33, 70, 2), (100, 37, 4), (255, 513, 5), (300, 300, 6),
-                                      (21, 2500, 7), (700, 90, 8)])
+                                      (21, 2500, 7), (700, 90, 8), (50, 850, 9)])
 @pytest.mark.parametrize("block", [2, 3, 8, 16])
 def test_blocked_delayed_update_is_bit_identical(m, n, seed, block, monkeypatch):
     """K pending pivots applied by one sweep == one sweep per pivot == the oracle, for the overlapped
