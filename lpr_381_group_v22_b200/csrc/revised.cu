@@ -612,9 +612,14 @@ static int rev_alloc(int device, int m, int n, lpr_rev** out) {
   h->ldA = round_up(n, 16);
   h->ldB = round_up(m, 16);
   // row splits so that (column tiles x splits) is about 4 CTAs per SM
+  // ... and, when a nearby split count exists, so that the CTA count is a whole multiple of the SM count: 32
+  // column tiles x 19 splits = 608 CTAs on 148 SMs x 4 resident leaves 16 CTAs for a second, nearly empty
+  // wave (k_price ran at 4.8 TB/s); 32 x 37 = 1184 = 2 full waves
   auto splits = [&](int ld) {
     int tiles = (ld / 2 + kT - 1) / kT;
     int s = std::max(1, (h->sms * 4 + tiles - 1) / tiles);
+    for (int t = s; t <= 2 * s + 1; t++)
+      if (((long long)tiles * t) % h->sms == 0) { s = t; break; }
     return std::min(s, std::max(1, m / 8));
   };
   h->PS = splits(h->ldA);
