@@ -49,11 +49,18 @@ struct BBAddc {  // one AddConstraint job
   double* child;
   int* key;     // C ints: first-"1" row of basic columns, -1 for non-basic
   int* order;   // C ints: basic columns in elimination order
+  int* big;     // optional: set to 1 when the child holds an entry outside net_round4's idempotent range
   int R, C;     // parent dims
   int ldp, ldc;
   int n_vars, var, type;
+  int negzero;  // 1: write the child with -0.0 -> 0.0 already applied (the first step of DoDualSimplex :307-313)
   double bound;
 };
+
+// Control words of a batched DoDualSimplex run (device ints): the LPs that staged a pivot in round r are appended
+// to list[r & 1] by k_bb_select and swept by k_bb_sweep(r); count[r & 3] is their number (k_bb_sweep(r) clears
+// count[(r + 2) & 3] for the select after next).
+constexpr int kCtlRunning = 4, kCtlLists = 8;
 
 constexpr int kBBT = 1024;
 
@@ -90,9 +97,12 @@ __global__ void k_bb_negzero(BBLp* lps) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     if (T[i] == 0.0) T[i] = 0.0;  // :307-313
 }
-__global__ void k_bb_round(BBLp* lps) {
+// `dirty` (optional, one int per LP, written by k_bb_addc_*): 0 = the LP's start tableau was 4-d.p. rounded, free of
+// -0.0 and inside net_round4's idempotent range, so an LP that ended without a pivot is already its own rounding
+__global__ void k_bb_round(BBLp* lps, const int* dirty) {
   BBLp& lp = lps[blockIdx.y];
   if (lp.status != LPR_OPTIMAL) return;
+  if (dirty && !dirty[blockIdx.y] && lp.npiv == 0) return;
   double* T = lp.buf[lp.src];
   const size_t n = (size_t)lp.R * lp.ld;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -104,7 +114,7 @@ __global__ void k_round4(double* T, size_t n) {
 }
 
 // ---- DoDualSimplex state machine (:289-468), one CTA per LP --------------------------------------
-__global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps) {
+__global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps, int* ctl, int round, int cap) {
   __shared__ MinIdx sm[32];
   __shared__ int smi[32];
   BBLp& lp = lps[blockIdx.x];
@@ -267,59 +277,90 @@ __global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps) {
     lp.leave = r;
     lp.enter = c;
     lp.do_sweep = 1;
+    ctl[kCtlLists + (round & 1) * cap + atomicAdd(&ctl[round & 3], 1)] = blockIdx.x;
   }
 }
 
-__global__ void __launch_bounds__(kSweepThreads) k_bb_sweep(BBLp* lps) {
-  const BBLp& lp = lps[blockIdx.y];
-  if (!lp.do_sweep || lp.status != LPR_RUNNING) return;
-  sweep_body<0, true, false, 8>(reinterpret_cast<const double2*>(lp.buf[lp.src]),
-                                reinterpret_cast<double2*>(lp.buf[lp.src ^ 1]), lp.col,
-                                reinterpret_cast<const double2*>(lp.prow), nullptr, nullptr, lp.R, lp.C, lp.ld,
-                                lp.leave, -1, 0.0, 0);
+// Sweeps of the LPs that staged a pivot this round.  The (LP, tile) pairs are dealt round-robin to a grid sized for
+// the machine, not for the batch: late rounds, in which one or two long chains are still pivoting, get every SM.
+__global__ void __launch_bounds__(kSweepThreads) k_bb_sweep(const BBLp* lps, int* ctl, int round, int cap,
+                                                            int tiles_max) {
+  const int na = ctl[round & 3];
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl[(round + 2) & 3] = 0;
+  const int* list = ctl + kCtlLists + (round & 1) * cap;
+  constexpr unsigned TILE = kSweepThreads * 8;
+  const long long total = (long long)na * tiles_max;
+  for (long long g = blockIdx.x; g < total; g += gridDim.x) {
+    const BBLp& lp = lps[list[g / tiles_max]];
+    const unsigned long long t = (unsigned long long)(g % tiles_max);
+    const unsigned ldv = (unsigned)(lp.ld >> 1);
+    const unsigned long long n = (unsigned long long)lp.R * ldv;
+    if (t * TILE >= n) continue;
+    sweep_tile<0, true, false, 8>(reinterpret_cast<const double2*>(lp.buf[lp.src]),
+                                  reinterpret_cast<double2*>(lp.buf[lp.src ^ 1]), lp.col,
+                                  reinterpret_cast<const double2*>(lp.prow), nullptr, nullptr, n, ldv, lp.leave, t,
+                                  0.0, 0u, 0, 0xffffffffu, 0);
+  }
 }
 // number of LPs of the batch still running (host polls it)
-__global__ void k_bb_count_running(const BBLp* lps, int n, int* out) {
+__global__ void k_bb_count_running(const BBLp* lps, int n, int* ctl) {
   int c = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) c += (lps[i].status == LPR_RUNNING);
   __shared__ int smi[32];
   c = block_sum_int(c, smi);
-  if (threadIdx.x == 0) *out = c;
+  if (threadIdx.x == 0) ctl[kCtlRunning] = c;
 }
 
-// ---- node evaluation (:805-857, :892-921), one CTA per node -------------------------------------
-__global__ void __launch_bounds__(kBBT) k_bb_eval(const double* const* tabs, const int* dims /* R,C,ld */, int n_vars,
-                                                  BBEval* out, double* xout) {
+// ---- node evaluation (:805-857, :892-921) ------------------------------------------------------
+// k_bb_eval_x: x_i = Round(RHS of the first row, objective row included, holding a rounded 1 in column i).  Grid
+// (column blocks, nodes), CTA = kEvalCols columns x kEvalSegs row segments: a column's rows are scanned by kEvalSegs
+// threads (16 independent loads in flight each) and the first hit is the minimum over the segments, so a node costs a
+// handful of memory round trips instead of R / 8.
+constexpr int kEvalCols = 64, kEvalSegs = 8;
+__global__ void __launch_bounds__(kEvalCols* kEvalSegs) k_bb_eval_x(const double* const* tabs, const int* dims,
+                                                                    int n_vars, double* xout) {
+  __shared__ int first[kEvalSegs][kEvalCols];
+  const int node = blockIdx.y;
+  const double* T = tabs[node];
+  const int R = dims[3 * node], C = dims[3 * node + 1], ld = dims[3 * node + 2];
+  const int lc = threadIdx.x % kEvalCols, seg = threadIdx.x / kEvalCols;
+  const int i = blockIdx.x * kEvalCols + lc;
+  const int per = (R + kEvalSegs - 1) / kEvalSegs;
+  const int r0 = seg * per, r1 = min(R, r0 + per);
+  int hit = INT_MAX;
+  if (i < n_vars) {
+    for (int j0 = r0; j0 < r1 && hit == INT_MAX; j0 += 16) {
+      double t[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) t[q] = (j0 + q < r1) ? TAT(T, ld, j0 + q, i) : 0.0;
+#pragma unroll
+      for (int q = 15; q >= 0; q--)
+        if (j0 + q < r1 && net_round4_is_one(t[q])) hit = j0 + q;
+    }
+  }
+  first[seg][lc] = hit;
+  __syncthreads();
+  if (seg == 0 && i < n_vars) {
+#pragma unroll
+    for (int q = 1; q < kEvalSegs; q++) hit = min(hit, first[q][lc]);
+    xout[(size_t)node * n_vars + i] = (hit == INT_MAX) ? 0.0 : net_round4(TAT(T, ld, hit, C - 1));
+  }
+}
+// k_bb_eval_pick: integrality count, branching variable (fractional part closest to 0.5, first index), objective
+__global__ void __launch_bounds__(kBBT) k_bb_eval_pick(const double* const* tabs, const int* dims, int n_vars,
+                                                       BBEval* out, const double* xout) {
   __shared__ MinIdx sm[32];
   __shared__ int smi[32];
   const int node = blockIdx.x;
   const double* T = tabs[node];
-  const int R = dims[3 * node], C = dims[3 * node + 1], ld = dims[3 * node + 2];
-  double* x = xout + (size_t)node * n_vars;
+  const int C = dims[3 * node + 1], ld = dims[3 * node + 2];
+  const double* x = xout + (size_t)node * n_vars;
   int nonint = 0;
   for (int i = threadIdx.x; i < n_vars; i += blockDim.x) {
-    double xi = 0.0;
-    // first row (objective row included) holding a rounded 1; rows are fetched 8 at a time so the
-    // scan costs one memory round trip per 8 rows instead of one per row
-    bool found = false;
-    for (int j0 = 0; j0 < R && !found; j0 += 8) {
-      double t[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) t[q] = (j0 + q < R) ? TAT(T, ld, j0 + q, i) : 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        if (!found && j0 + q < R && fabs(net_round4(t[q]) - 1.0) <= 1e-6) {
-          xi = net_round4(TAT(T, ld, j0 + q, C - 1));
-          found = true;
-        }
-      }
-    }
-    x[i] = xi;
-    double rr = net_round4(xi);  // IsInteger :595-599
+    double rr = net_round4(x[i]);  // IsInteger :595-599
     if (!(fabs(rr - rint(rr)) <= 1e-6)) nonint++;
   }
   nonint = block_sum_int(nonint, smi);
-  __syncthreads();
   int var = block_first_min(n_vars, [&](int i, double& val) {
     double xi = x[i];
     double rr = net_round4(xi);
@@ -337,53 +378,91 @@ __global__ void __launch_bounds__(kBBT) k_bb_eval(const double* const* tabs, con
 }
 
 // ---- AddConstraint (:694-803) -------------------------------------------------------------------
-// child rows 0..R-1 = Round(parent) with a zero column inserted before the RHS; row R = the bound row
-__global__ void k_bb_addc_copy(const BBAddc* jobs) {
-  const BBAddc& jb = jobs[blockIdx.y];
-  const int R = jb.R, C = jb.C, C2 = C + 1;
-  // rows are dealt to the CTAs of this job, columns to the threads: no integer division per element
-  for (int i = blockIdx.x; i <= R; i += gridDim.x) {
-    const double* prow = jb.parent + (size_t)i * jb.ldp;
-    double* crow = jb.child + (size_t)i * jb.ldc;
-    for (int j = threadIdx.x; j < jb.ldc; j += blockDim.x) {
-      double v = 0.0;
-      if (i < R) {
-        if (j < C - 1)
-          v = net_round4(net_round4(prow[j]));
-        else if (j == C)
-          v = net_round4(net_round4(prow[C - 1]));
-      } else if (j < C2) {
-        if (j < jb.n_vars && j == jb.var) v = net_round4(1.0);  // :727-730
-        if (j == C2 - 1) v = net_round4(jb.bound);              // :732
-        if (j == C - 1) v = (jb.type == 1) ? -1.0 : 1.0;        // :734-742 (overrides a coefficient there)
-        v = net_round4(v);                                      // :747
-      }
-      crow[j] = v;
-    }
+// k_bb_addc_build: one pass over the parent does both halves of the preparation.  A thread owns two adjacent columns
+// and walks the rows (8 x 128-bit loads in flight):
+//   * child rows 0..R-1 = Round(Round(parent)) with a zero column inserted before the RHS, row R = the bound row;
+//   * IdentifyBasicVariables :642-662: column sums over ALL rows (objective row and RHS column included), added in
+//     row order like the reference, and the first row holding an exact 1.
+constexpr int kAddcThreads = 64;
+__device__ __forceinline__ double addc_bound_row(const BBAddc& jb, int j) {  // :727-747
+  const int C = jb.C, C2 = C + 1;
+  double v = 0.0;
+  if (j < C2) {
+    if (j < jb.n_vars && j == jb.var) v = net_round4(1.0);
+    if (j == C2 - 1) v = net_round4(jb.bound);
+    if (j == C - 1) v = (jb.type == 1) ? -1.0 : 1.0;  // overrides a coefficient there
+    v = net_round4(v);
   }
+  return v;
 }
-// IdentifyBasicVariables :642-662: column sums over ALL rows (objective row and RHS column included)
-__global__ void k_bb_colsum(const BBAddc* jobs) {
+__global__ void __launch_bounds__(kAddcThreads) k_bb_addc_build(const BBAddc* jobs) {
   const BBAddc& jb = jobs[blockIdx.y];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= jb.C) return;
-  double sum = 0.0;
-  int first1 = jb.R;
-  for (int i0 = 0; i0 < jb.R; i0 += 8) {  // loads batched 8 rows at a time, sum kept in row order
-    double t[8];
+  const int R = jb.R, C = jb.C, ldc = jb.ldc;
+  const int c0 = 2 * (blockIdx.x * kAddcThreads + threadIdx.x);
+  if (c0 >= ldc) return;
+  const bool nz = jb.negzero != 0;
+  const bool in0 = c0 < C, in1 = c0 + 1 < C;
+  const bool interior = c0 + 1 < C - 1;  // both columns keep their place in the child
+  const double2* src = reinterpret_cast<const double2*>(jb.parent + c0);
+  const size_t sp = (size_t)(jb.ldp >> 1);
+  double s0 = 0.0, s1 = 0.0;
+  int f0 = R, f1 = R;
+  bool big = false;
+  for (int i0 = 0; i0 < R; i0 += 8) {
+    double2 t[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) t[q] = (i0 + q < jb.R) ? jb.parent[(size_t)(i0 + q) * jb.ldp + k] : 0.0;
+    for (int q = 0; q < 8; q++)
+      if (i0 + q < R && in0) t[q] = ld_stream(src + (size_t)(i0 + q) * sp);
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-      if (i0 + q < jb.R) {
-        const double v = net_round4(net_round4(t[q]));
-        sum = __dadd_rn(sum, v);
-        if (first1 == jb.R && v == 1.0) first1 = i0 + q;
+      const int i = i0 + q;
+      if (i >= R) continue;
+      double v0 = 0.0, v1 = 0.0;
+      if (in0) {
+        big |= !(fabs(t[q].x) < 2e5);
+        v0 = net_round4_twice(t[q].x);
+        s0 = __dadd_rn(s0, v0);
+        if (f0 == R && v0 == 1.0) f0 = i;
+      }
+      if (in1) {
+        big |= !(fabs(t[q].y) < 2e5);
+        v1 = net_round4_twice(t[q].y);
+        s1 = __dadd_rn(s1, v1);
+        if (f1 == R && v1 == 1.0) f1 = i;
+      }
+      if (nz) {
+        if (v0 == 0.0) v0 = 0.0;
+        if (v1 == 0.0) v1 = 0.0;
+      }
+      double* crow = jb.child + (size_t)i * ldc;
+      if (interior) {
+        *reinterpret_cast<double2*>(crow + c0) = make_double2(v0, v1);
+      } else {  // the pair straddles the inserted column or lies in the padding
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int c = c0 + h;
+          const double v = h ? v1 : v0;
+          if (c < C - 1) {
+            crow[c] = v;
+          } else if (c == C - 1) {
+            crow[C - 1] = 0.0;
+            crow[C] = v;
+          } else if (c > C && c < ldc) {
+            crow[c] = 0.0;
+          }
+        }
       }
     }
   }
-  sum = net_round4(sum);
-  jb.key[k] = (fabs(sum - 1.0) <= 1e-6) ? first1 : -1;
+  {
+    double* crow = jb.child + (size_t)R * ldc;
+    crow[c0] = addc_bound_row(jb, c0);
+    if (c0 + 1 < ldc) crow[c0 + 1] = addc_bound_row(jb, c0 + 1);
+    if (c0 <= C && C <= c0 + 1) big |= !(fabs(jb.bound) < 2e5);
+  }
+  if (in0) jb.key[c0] = (fabs(net_round4(s0) - 1.0) <= 1e-6) ? f0 : -1;
+  if (in1) jb.key[c0 + 1] = (fabs(net_round4(s1) - 1.0) <= 1e-6) ? f1 : -1;
+  if (big && jb.big) *jb.big = 1;
 }
 // ordering (:664-685, stable by first-"1" row) and the elimination loop (:752-797); one CTA per job
 __global__ void __launch_bounds__(kBBT) k_bb_addc_elim(const BBAddc* jobs) {
@@ -467,7 +546,14 @@ __global__ void __launch_bounds__(kBBT) k_bb_addc_elim(const BBAddc* jobs) {
     __syncthreads();
     pos = q + 1;
   }
-  for (int cc = tid; cc < C2; cc += blockDim.x) v[cc] = net_round4(v[cc]);  // :799
+  bool big = false;
+  for (int cc = tid; cc < C2; cc += blockDim.x) {
+    double x = net_round4(v[cc]);  // :799
+    if (jb.negzero && x == 0.0) x = 0.0;
+    big |= !(fabs(x) < 2e5);
+    v[cc] = x;
+  }
+  if (big && jb.big) *jb.big = 1;
 }
 
 }  // namespace lpr
@@ -525,7 +611,8 @@ struct lpr_bb {
   double* d_prow = nullptr;  // 2*cap x ldmax
   int* d_key = nullptr;      // 2*cap x ldmax
   int* d_order = nullptr;    // 2*cap x ldmax
-  int* d_running = nullptr;
+  int* d_ctl = nullptr;    // kCtlLists + 2 * (2*cap) control words of the batched solve
+  int* d_dirty = nullptr;  // 2*cap
   int* h_running = nullptr;
   // optional node log (sequential mode)
   int* node_log = nullptr;
@@ -578,59 +665,76 @@ static int bb_alloc_scratch(lpr_bb* h, int cap) {
   A_DEV(d_prow, double, (size_t)nlp * h->ldmax);
   A_DEV(d_key, int, (size_t)nlp * h->ldmax);
   A_DEV(d_order, int, (size_t)nlp * 2 * h->ldmax);
-  A_DEV(d_running, int, 1);
+  A_DEV(d_ctl, int, kCtlLists + 2 * nlp);
+  A_DEV(d_dirty, int, nlp);
   A_HOST(h_running, int, 1);
 #undef A_DEV
 #undef A_HOST
   return LPR_OK;
 }
 
-// run the DoDualSimplex loop for nlp LPs whose descriptors are in h_lps[0..nlp)
-static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps, int nlp, int* d_running,
-                          int* h_running, int max_elems) {
+// run the DoDualSimplex loop for nlp LPs whose descriptors are in h_lps[0..nlp).  d_ctl: kCtlLists + 2 * cap device
+// ints (cap >= nlp).  skip_negzero: the start tableaux already have -0.0 -> 0.0 applied (BBAddc::negzero);
+// round_result: RoundAllTableaux on the finished LPs, skipping those d_dirty (optional) marks as already rounded.
+static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps, int nlp, int* d_ctl, int cap,
+                          int* h_running, size_t max_elems, bool skip_negzero, bool round_result, const int* d_dirty) {
   LPR_CUDA(cudaMemcpyAsync(d_lps, h_lps, sizeof(BBLp) * nlp, cudaMemcpyHostToDevice, stream));
-  const long long tiles = ((long long)max_elems / 2 + kSweepThreads * 8 - 1) / (kSweepThreads * 8);
-  const int gx = (int)std::max<long long>(1, std::min<long long>(tiles, std::max(1, sms * 6 / std::max(1, nlp))));
-  dim3 gs(gx, nlp);
-  dim3 ge(std::max(1, std::min(sms, (int)(((long long)max_elems + 8191) / 8192))), nlp);
-  k_bb_negzero<<<ge, 256, 0, stream>>>(d_lps);
-  LPR_LAUNCH_CHECK();
-  int chunk = 2;
-  while (true) {
-    for (int q = 0; q < chunk; q++) {
-      k_bb_select<<<nlp, kBBT, 0, stream>>>(d_lps);
+  LPR_CUDA(cudaMemsetAsync(d_ctl, 0, sizeof(int) * kCtlLists, stream));
+  const int tiles_max = (int)((max_elems / 2 + kSweepThreads * 8 - 1) / (kSweepThreads * 8));
+  const int gs = (int)std::max<long long>(1, std::min<long long>((long long)tiles_max * nlp, (long long)sms * 8));
+  dim3 ge(std::max(1, std::min(sms, (int)((max_elems + 8191) / 8192))), nlp);
+  if (!skip_negzero) {
+    k_bb_negzero<<<ge, 256, 0, stream>>>(d_lps);
+    LPR_LAUNCH_CHECK();
+  }
+  int round = 0, chunk = 2;
+  auto pivot_round = [&](bool count) -> int {
+    k_bb_select<<<nlp, kBBT, 0, stream>>>(d_lps, d_ctl, round, cap);
+    LPR_LAUNCH_CHECK();
+    if (count) {  // the select commits the previous sweep, so the count is exact; it may have staged the next pivot
+      k_bb_count_running<<<1, 256, 0, stream>>>(d_lps, nlp, d_ctl);
       LPR_LAUNCH_CHECK();
-      k_bb_sweep<<<gs, kSweepThreads, 0, stream>>>(d_lps);
-      LPR_LAUNCH_CHECK();
+      LPR_CUDA(cudaMemcpyAsync(h_running, d_ctl + kCtlRunning, sizeof(int), cudaMemcpyDeviceToHost, stream));
     }
-    k_bb_select<<<nlp, kBBT, 0, stream>>>(d_lps);  // commits the last sweep; may stage the next pivot
+    k_bb_sweep<<<gs, kSweepThreads, 0, stream>>>(d_lps, d_ctl, round, cap, tiles_max);
     LPR_LAUNCH_CHECK();
-    k_bb_count_running<<<1, 256, 0, stream>>>(d_lps, nlp, d_running);
-    LPR_LAUNCH_CHECK();
-    LPR_CUDA(cudaMemcpyAsync(h_running, d_running, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    k_bb_sweep<<<gs, kSweepThreads, 0, stream>>>(d_lps);
-    LPR_LAUNCH_CHECK();
+    round++;
+    return LPR_OK;
+  };
+  while (true) {
+    int rc;
+    for (int q = 0; q < chunk; q++)
+      if ((rc = pivot_round(false))) return rc;
+    if ((rc = pivot_round(true))) return rc;
     LPR_CUDA(cudaStreamSynchronize(stream));
     if (*h_running == 0) break;
     chunk = std::min(16, chunk * 2);
   }
-  k_bb_round<<<ge, 256, 0, stream>>>(d_lps);  // children are stored rounded (:1124, :1187)
-  LPR_LAUNCH_CHECK();
+  if (round_result) {
+    k_bb_round<<<ge, 256, 0, stream>>>(d_lps, d_dirty);  // children are stored rounded (:1124, :1187)
+    LPR_LAUNCH_CHECK();
+  }
   LPR_CUDA(cudaMemcpyAsync(h_lps, d_lps, sizeof(BBLp) * nlp, cudaMemcpyDeviceToHost, stream));
   LPR_CUDA(cudaStreamSynchronize(stream));
   return LPR_OK;
 }
 
-static int bb_run_addc(cudaStream_t stream, int sms, BBAddc* h_jobs, BBAddc* d_jobs, int njobs, int maxC,
-                       size_t max_child_elems) {
+static int bb_run_addc(cudaStream_t stream, BBAddc* h_jobs, BBAddc* d_jobs, int njobs, int max_ldc) {
   LPR_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(BBAddc) * njobs, cudaMemcpyHostToDevice, stream));
-  dim3 gc(std::max(1, std::min(64, (sms * 8 + njobs - 1) / njobs)), njobs);
-  k_bb_addc_copy<<<gc, 256, 0, stream>>>(d_jobs);
-  LPR_LAUNCH_CHECK();
-  dim3 gs((maxC + 127) / 128, njobs);
-  k_bb_colsum<<<gs, 128, 0, stream>>>(d_jobs);
+  dim3 gb((max_ldc / 2 + kAddcThreads - 1) / kAddcThreads, njobs);
+  k_bb_addc_build<<<gb, kAddcThreads, 0, stream>>>(d_jobs);
   LPR_LAUNCH_CHECK();
   k_bb_addc_elim<<<njobs, kBBT, 0, stream>>>(d_jobs);
+  LPR_LAUNCH_CHECK();
+  return LPR_OK;
+}
+
+static int bb_run_eval(cudaStream_t stream, const double** d_tabs, const int* d_dims, int nb, int n_vars, BBEval* d_eval,
+                       double* d_x) {
+  dim3 gx((n_vars + kEvalCols - 1) / kEvalCols, nb);
+  k_bb_eval_x<<<gx, kEvalCols * kEvalSegs, 0, stream>>>(d_tabs, d_dims, n_vars, d_x);
+  LPR_LAUNCH_CHECK();
+  k_bb_eval_pick<<<nb, kBBT, 0, stream>>>(d_tabs, d_dims, n_vars, d_eval, d_x);
   LPR_LAUNCH_CHECK();
   return LPR_OK;
 }
@@ -667,8 +771,7 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
     }
     LPR_CUDA(cudaMemcpyAsync(h->d_tabs, h->h_tabs, sizeof(double*) * nb, cudaMemcpyHostToDevice, h->stream));
     LPR_CUDA(cudaMemcpyAsync(h->d_dims, h->h_dims, sizeof(int) * 3 * nb, cudaMemcpyHostToDevice, h->stream));
-    k_bb_eval<<<nb, kBBT, 0, h->stream>>>(h->d_tabs, h->d_dims, h->n_vars, h->d_eval, h->d_x);
-    LPR_LAUNCH_CHECK();
+    if ((rc = bb_run_eval(h->stream, h->d_tabs, h->d_dims, nb, h->n_vars, h->d_eval, h->d_x))) return rc;
     LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(BBEval) * nb, cudaMemcpyDeviceToHost, h->stream));
     LPR_CUDA(cudaMemcpyAsync(h->h_x, h->d_x, sizeof(double) * (size_t)nb * h->n_vars, cudaMemcpyDeviceToHost, h->stream));
     LPR_CUDA(cudaStreamSynchronize(h->stream));
@@ -713,7 +816,6 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
     const int nj = (int)jobs.size();
     std::vector<double*> slabA(nj, nullptr), slabB(nj, nullptr);
     if (nj > 0) {
-      int maxC = 0;
       size_t max_elems = 0;
       for (int j = 0; j < nj; j++) {
         if ((rc = bb_take_slab(h, &slabA[j]))) return rc;
@@ -725,6 +827,8 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
         jb.child = slabA[j];
         jb.key = h->d_key + (size_t)j * h->ldmax;
         jb.order = h->d_order + (size_t)j * 2 * h->ldmax;
+        jb.big = h->d_dirty + j;
+        jb.negzero = 1;
         jb.R = nd.R;
         jb.C = nd.C;
         jb.ldp = h->ldmax;
@@ -734,7 +838,6 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
         jb.type = jobs[j].side;
         // (int)Math.Floor / (int)Math.Ceiling :870-871
         jb.bound = jobs[j].side == 0 ? (double)(int)std::floor(ev.branch_val) : (double)(int)std::ceil(ev.branch_val);
-        maxC = std::max(maxC, nd.C);
         max_elems = std::max(max_elems, (size_t)(nd.R + 1) * h->ldmax);
         BBLp& lp = h->h_lps[j];
         memset(&lp, 0, sizeof lp);
@@ -752,11 +855,13 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
       }
       double tp2 = now_s();
       h->t_host += tp2 - tp1;
-      if ((rc = bb_run_addc(h->stream, h->sms, h->h_jobs, h->d_jobs, nj, maxC, max_elems))) return rc;
+      LPR_CUDA(cudaMemsetAsync(h->d_dirty, 0, sizeof(int) * nj, h->stream));
+      if ((rc = bb_run_addc(h->stream, h->h_jobs, h->d_jobs, nj, h->ldmax))) return rc;
       if (getenv("LPR_BB_PROFILE")) cudaStreamSynchronize(h->stream);
       double tp3 = now_s();
       h->t_addc += tp3 - tp2;
-      if ((rc = bb_solve_batch(h->stream, h->sms, h->h_lps, h->d_lps, nj, h->d_running, h->h_running, (int)max_elems)))
+      if ((rc = bb_solve_batch(h->stream, h->sms, h->h_lps, h->d_lps, nj, h->d_ctl, 2 * h->cap, h->h_running, max_elems,
+                               true, true, h->d_dirty)))
         return rc;
       h->t_solve += now_s() - tp3;
       h->n_children += nj;
@@ -809,7 +914,7 @@ int lpr_bb_destroy(lpr_bb* h) {
   for (double* c : h->chunks) cudaFree(c);
   cudaFree(h->d_lps); cudaFree(h->d_jobs); cudaFree(h->d_eval); cudaFree(h->d_x); cudaFree(h->d_tabs);
   cudaFree(h->d_dims); cudaFree(h->d_col); cudaFree(h->d_prow); cudaFree(h->d_key); cudaFree(h->d_order);
-  cudaFree(h->d_running);
+  cudaFree(h->d_ctl); cudaFree(h->d_dirty);
   if (h->h_lps) cudaFreeHost(h->h_lps);
   if (h->h_jobs) cudaFreeHost(h->h_jobs);
   if (h->h_eval) cudaFreeHost(h->h_eval);
@@ -1111,10 +1216,10 @@ int lpr_tab_bb_node_solve_ex(lpr_tab* h, int is_minimization, int64_t max_pivots
   if (pivot_log && log_cap > 0 && (rc = tab_ensure_log(h, std::min<long long>(log_cap, 1 << 22)))) return rc;
   BBLp* d_lp = nullptr;
   BBLp* h_lp = nullptr;
-  int *d_run = nullptr, *h_run = nullptr;
+  int *d_ctl = nullptr, *h_run = nullptr;
   LPR_CUDA(cudaMalloc(&d_lp, sizeof(BBLp)));
   LPR_CUDA(cudaMallocHost(&h_lp, sizeof(BBLp)));
-  LPR_CUDA(cudaMalloc(&d_run, sizeof(int)));
+  LPR_CUDA(cudaMalloc(&d_ctl, sizeof(int) * (kCtlLists + 2)));
   LPR_CUDA(cudaMallocHost(&h_run, sizeof(int)));
   memset(h_lp, 0, sizeof(BBLp));
   h_lp->buf[0] = h->T;
@@ -1130,35 +1235,11 @@ int lpr_tab_bb_node_solve_ex(lpr_tab* h, int is_minimization, int64_t max_pivots
   h_lp->max_piv = max_pivots;
   h_lp->is_min = is_minimization ? 1 : 0;
   // note: the building block returns the un-rounded final tableau (rounding is the caller's step :1124)
-  LPR_CUDA(cudaMemcpyAsync(d_lp, h_lp, sizeof(BBLp), cudaMemcpyHostToDevice, h->stream));
-  {
-    const size_t elems = (size_t)h->R * h->ld;
-    dim3 ge(std::max(1, std::min(h->sms, (int)((elems + 8191) / 8192))), 1);
-    const long long tiles = ((long long)elems / 2 + kSweepThreads * 8 - 1) / (kSweepThreads * 8);
-    dim3 gs((int)std::max<long long>(1, std::min<long long>(tiles, h->sms * 6)), 1);
-    k_bb_negzero<<<ge, 256, 0, h->stream>>>(d_lp);
-    LPR_LAUNCH_CHECK();
-    int chunk = 2;
-    while (true) {
-      for (int q = 0; q < chunk; q++) {
-        k_bb_select<<<1, kBBT, 0, h->stream>>>(d_lp);
-        LPR_LAUNCH_CHECK();
-        k_bb_sweep<<<gs, kSweepThreads, 0, h->stream>>>(d_lp);
-        LPR_LAUNCH_CHECK();
-      }
-      k_bb_select<<<1, kBBT, 0, h->stream>>>(d_lp);
-      LPR_LAUNCH_CHECK();
-      k_bb_count_running<<<1, 256, 0, h->stream>>>(d_lp, 1, d_run);
-      LPR_LAUNCH_CHECK();
-      LPR_CUDA(cudaMemcpyAsync(h_run, d_run, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      k_bb_sweep<<<gs, kSweepThreads, 0, h->stream>>>(d_lp);
-      LPR_LAUNCH_CHECK();
-      LPR_CUDA(cudaStreamSynchronize(h->stream));
-      if (*h_run == 0) break;
-      chunk = std::min(16, chunk * 2);
-    }
+  rc = bb_solve_batch(h->stream, h->sms, h_lp, d_lp, 1, d_ctl, 1, h_run, (size_t)h->R * h->ld, false, false, nullptr);
+  if (rc) {
+    cudaFree(d_lp); cudaFreeHost(h_lp); cudaFree(d_ctl); cudaFreeHost(h_run);
+    return rc;
   }
-  LPR_CUDA(cudaMemcpy(h_lp, d_lp, sizeof(BBLp), cudaMemcpyDeviceToHost));
   if (h_lp->src == 1) std::swap(h->T, h->T2);  // the result lives in the other ping-pong buffer
   if (status) *status = h_lp->status;
   if (n_pivots) *n_pivots = h_lp->npiv;
@@ -1169,7 +1250,7 @@ int lpr_tab_bb_node_solve_ex(lpr_tab* h, int is_minimization, int64_t max_pivots
   }
   cudaFree(d_lp);
   cudaFreeHost(h_lp);
-  cudaFree(d_run);
+  cudaFree(d_ctl);
   cudaFreeHost(h_run);
   return LPR_OK;
 }
@@ -1197,6 +1278,8 @@ int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound
   jb.child = ch->T;
   jb.key = d_key;
   jb.order = d_order;
+  jb.big = nullptr;
+  jb.negzero = 0;  // AddConstraint proper: the -0.0 clean-up belongs to DoDualSimplex
   jb.R = parent->R;
   jb.C = parent->C;
   jb.ldp = parent->ld;
@@ -1206,7 +1289,7 @@ int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound
   jb.type = type;
   jb.bound = bound;
   cudaStreamSynchronize(parent->stream);
-  rc = bb_run_addc(ch->stream, ch->sms, &jb, d_jb, 1, parent->C, (size_t)(parent->R + 1) * ch->ld);
+  rc = bb_run_addc(ch->stream, &jb, d_jb, 1, ch->ld);
   if (rc == LPR_OK && cudaStreamSynchronize(ch->stream) != cudaSuccess) rc = fail(LPR_E_CUDA, "AddConstraint failed");
   cudaFree(d_key); cudaFree(d_order); cudaFree(d_jb);
   if (rc) {
@@ -1235,9 +1318,8 @@ int lpr_tab_bb_branch_var(lpr_tab* h, int n_vars, int* var, double* value, doubl
   cudaError_t e = cudaMemcpyAsync(d_tabs, &tp, sizeof(double*), cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_dims, dims, sizeof dims, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) {
-    k_bb_eval<<<1, kBBT, 0, h->stream>>>(d_tabs, d_dims, n_vars, d_ev, d_x);
-    count_launch();
-    e = cudaMemcpyAsync(&ev, d_ev, sizeof ev, cudaMemcpyDeviceToHost, h->stream);
+    if (bb_run_eval(h->stream, d_tabs, d_dims, 1, n_vars, d_ev, d_x) != LPR_OK) e = cudaErrorLaunchFailure;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&ev, d_ev, sizeof ev, cudaMemcpyDeviceToHost, h->stream);
   }
   if (e == cudaSuccess && x) e = cudaMemcpyAsync(x, d_x, sizeof(double) * n_vars, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

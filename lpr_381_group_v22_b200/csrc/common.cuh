@@ -104,7 +104,7 @@ __device__ __forceinline__ int block_sum_int(int x, int* smem) {
 // round, /1e4 when |x| < 1e16.  rint() in the default rounding mode is value identical to
 // COMDouble::Round for every finite double (tests/test_oracle_golden.py checks the oracle's
 // literal floor(x+0.5) form against rint on the edge cases).
-__device__ __forceinline__ double net_round4(double x) {
+__device__ __forceinline__ double net_round4_div(double x) {  // the literal form
   if (fabs(x) < 1e16) {
     x = __dmul_rn(x, 1e4);
     x = rint(x);
@@ -112,6 +112,28 @@ __device__ __forceinline__ double net_round4(double x) {
   }
   return x;
 }
+// Same value without the IEEE division: for an integer-valued k with |k| <= 2^31 the quotient k / 1e4 is
+// q1 = fma(r, RN(1e-4), q0) with q0 = k * RN(1e-4), r = fma(-1e4, q0, k) (Markstein's correction step;
+// tools/div1e4_check.c compares it with k / 1e4 for every such k, both signs: 0 mismatches).  |x| < 2e5 keeps
+// |k| below 2^31; anything larger (and NaN) takes the literal form.  k == 0 returns k so -0.0 stays -0.0.
+__device__ __forceinline__ double net_round4(double x) {
+  if (fabs(x) < 2e5) {
+    const double k = rint(__dmul_rn(x, 1e4));
+    if (k == 0.0) return k;
+    const double q0 = __dmul_rn(k, 1e-4);
+    const double r = __fma_rn(-1e4, q0, k);
+    return __fma_rn(r, 1e-4, q0);
+  }
+  return net_round4_div(x);
+}
+// Round(Round(x, 4), 4): on |x| < 2e5 the second rounding is the identity (rint((k / 1e4) * 1e4) == k for every
+// |k| <= 2^31, same exhaustive check), elsewhere it is applied literally.
+__device__ __forceinline__ double net_round4_twice(double x) {
+  return fabs(x) < 2e5 ? net_round4(x) : net_round4_div(net_round4_div(x));
+}
+// |Round(x, 4) - 1| <= 1e-6  <=>  rint(x * 1e4) == 1e4 (neighbouring quotients are 1e-4 away; |x| >= 1e16 and NaN
+// are never near 1): the "is a rounded 1" test of the basic-variable scans without the quotient.
+__device__ __forceinline__ bool net_round4_is_one(double x) { return rint(__dmul_rn(x, 1e4)) == 1e4; }
 // CuttingPlaneSolver.cs:12-17
 __device__ __forceinline__ double net_frac(double a) {
   double f = __dsub_rn(a, floor(a));

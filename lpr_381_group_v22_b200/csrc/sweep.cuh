@@ -20,6 +20,68 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
   return r;
 }
 
+// one TILE = kSweepThreads * UNROLL 16-byte chunks of the flat R x ld/2 array, tile index t
+template <int SKIP, bool OOP, bool EMIT, int UNROLL>
+__device__ __forceinline__ void sweep_tile(const double2* __restrict__ src, double2* __restrict__ dst,
+                                           const double* __restrict__ f, const double2* __restrict__ prow2,
+                                           double* __restrict__ cn, double* __restrict__ rhsb,
+                                           unsigned long long n, unsigned ldv, int p, unsigned long long t,
+                                           double eps, unsigned rhs_chunk, int rhs_odd, unsigned e_chunk, int e_odd) {
+  constexpr unsigned TILE = kSweepThreads * UNROLL;
+  const unsigned long long q0 = t * TILE + threadIdx.x;
+  unsigned row = (unsigned)(q0 / ldv);
+  unsigned c = (unsigned)(q0 - (unsigned long long)row * ldv);
+  double2 x[UNROLL];
+  double fv[UNROLL];
+  unsigned rw[UNROLL], cc[UNROLL];
+  bool act[UNROLL];
+#pragma unroll
+  for (int k = 0; k < UNROLL; k++) {
+    const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
+    rw[k] = row;
+    cc[k] = c;
+    act[k] = q < n;
+    if (act[k]) {
+      if (SKIP != 0) {  // the skip decision needs f before the load is issued
+        fv[k] = __ldg(f + row);
+        bool sk = ((int)row != p) && ((SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps));
+        if (sk && !OOP) act[k] = false;
+      }
+      if (act[k]) x[k] = ld_stream(src + q);
+    }
+    c += kSweepThreads;  // ldv may be < 256: wrap as often as needed
+    while (c >= ldv) { c -= ldv; row++; }
+  }
+#pragma unroll
+  for (int k = 0; k < UNROLL; k++) {
+    if (!act[k]) continue;
+    const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
+    if (SKIP == 0) fv[k] = __ldg(f + rw[k]);  // L1-resident: loaded late to keep registers low
+    const double2 pr = __ldg(prow2 + cc[k]);
+    double2 y;
+    bool sk = false;
+    if (SKIP != 0 && OOP && (int)rw[k] != p) sk = (SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps);
+    if ((int)rw[k] == p) {
+      y = pr;
+    } else if (sk) {
+      y = x[k];
+    } else {
+      y.x = __dsub_rn(x[k].x, __dmul_rn(fv[k], pr.x));
+      y.y = __dsub_rn(x[k].y, __dmul_rn(fv[k], pr.y));
+      if (OOP) {
+        if (y.x == 0.0) y.x = 0.0;
+        if (y.y == 0.0) y.y = 0.0;
+      }
+    }
+    dst[q] = y;
+    if (EMIT) {
+      if (cc[k] == e_chunk) cn[rw[k]] = e_odd ? y.y : y.x;
+      if (cc[k] == rhs_chunk) rhsb[rw[k]] = rhs_odd ? y.y : y.x;
+    }
+  }
+}
+
+// the tiles of one tableau dealt to the CTAs of the grid in contiguous spans
 template <int SKIP, bool OOP, bool EMIT, int UNROLL>
 __device__ __forceinline__ void sweep_body(const double2* __restrict__ src, double2* __restrict__ dst,
                                            const double* __restrict__ f, const double2* __restrict__ prow2,
@@ -36,57 +98,8 @@ __device__ __forceinline__ void sweep_body(const double2* __restrict__ src, doub
   const int e_odd = e_next & 1;
   for (unsigned long long tt = t0; tt < t1; tt++) {
     const unsigned long long t = reverse ? (ntiles - 1 - tt) : tt;  // full mirror: last tiles first
-    const unsigned long long q0 = t * TILE + threadIdx.x;
-    unsigned row = (unsigned)(q0 / ldv);
-    unsigned c = (unsigned)(q0 - (unsigned long long)row * ldv);
-    double2 x[UNROLL];
-    double fv[UNROLL];
-    unsigned rw[UNROLL], cc[UNROLL];
-    bool act[UNROLL];
-#pragma unroll
-    for (int k = 0; k < UNROLL; k++) {
-      const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
-      rw[k] = row;
-      cc[k] = c;
-      act[k] = q < n;
-      if (act[k]) {
-        if (SKIP != 0) {  // the skip decision needs f before the load is issued
-          fv[k] = __ldg(f + row);
-          bool sk = ((int)row != p) && ((SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps));
-          if (sk && !OOP) act[k] = false;
-        }
-        if (act[k]) x[k] = ld_stream(src + q);
-      }
-      c += kSweepThreads;  // ldv may be < 256: wrap as often as needed
-      while (c >= ldv) { c -= ldv; row++; }
-    }
-#pragma unroll
-    for (int k = 0; k < UNROLL; k++) {
-      if (!act[k]) continue;
-      const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
-      if (SKIP == 0) fv[k] = __ldg(f + rw[k]);  // L1-resident: loaded late to keep registers low
-      const double2 pr = __ldg(prow2 + cc[k]);
-      double2 y;
-      bool sk = false;
-      if (SKIP != 0 && OOP && (int)rw[k] != p) sk = (SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps);
-      if ((int)rw[k] == p) {
-        y = pr;
-      } else if (sk) {
-        y = x[k];
-      } else {
-        y.x = __dsub_rn(x[k].x, __dmul_rn(fv[k], pr.x));
-        y.y = __dsub_rn(x[k].y, __dmul_rn(fv[k], pr.y));
-        if (OOP) {
-          if (y.x == 0.0) y.x = 0.0;
-          if (y.y == 0.0) y.y = 0.0;
-        }
-      }
-      dst[q] = y;
-      if (EMIT) {
-        if (cc[k] == e_chunk) cn[rw[k]] = e_odd ? y.y : y.x;
-        if (cc[k] == rhs_chunk) rhsb[rw[k]] = rhs_odd ? y.y : y.x;
-      }
-    }
+    sweep_tile<SKIP, OOP, EMIT, UNROLL>(src, dst, f, prow2, cn, rhsb, n, ldv, p, t, eps, rhs_chunk, rhs_odd,
+                                        e_chunk, e_odd);
   }
 }
 
