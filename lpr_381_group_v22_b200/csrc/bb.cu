@@ -47,9 +47,10 @@ struct BBEval {  // per node outputs of k_bb_eval
 struct BBAddc {  // one AddConstraint job
   const double* parent;
   double* child;
-  int* key;     // C ints: first-"1" row of basic columns, -1 for non-basic
+  int* key;     // C ints, preset to kAddcNoRow: first-"1" row of basic columns, -1 for non-basic
   int* order;   // C ints: basic columns in elimination order
-  int* big;     // optional: set to 1 when the child holds an entry outside net_round4's idempotent range
+  double* ksum; // C doubles, zeroed: exact integer column sums of the 1e4-scaled entries
+  int* big;     // set to 1 when the job leaves the division-free / order-free range (see k_bb_addc_build)
   int R, C;     // parent dims
   int ldp, ldc;
   int n_vars, var, type;
@@ -378,12 +379,18 @@ __global__ void __launch_bounds__(kBBT) k_bb_eval_pick(const double* const* tabs
 }
 
 // ---- AddConstraint (:694-803) -------------------------------------------------------------------
-// k_bb_addc_build: one pass over the parent does both halves of the preparation.  A thread owns two adjacent columns
-// and walks the rows (8 x 128-bit loads in flight):
+// k_bb_addc_build: one pass over the parent does both halves of the preparation.  Grid (column blocks, row
+// segments, jobs); a thread owns two adjacent columns of one row segment (8 x 128-bit loads in flight):
 //   * child rows 0..R-1 = Round(Round(parent)) with a zero column inserted before the RHS, row R = the bound row;
-//   * IdentifyBasicVariables :642-662: column sums over ALL rows (objective row and RHS column included), added in
-//     row order like the reference, and the first row holding an exact 1.
-constexpr int kAddcThreads = 64;
+//   * IdentifyBasicVariables :642-662: the reference adds the rounded entries v_i = k_i / 1e4 of a column (ALL rows,
+//     objective row and RHS column included) in row order, rounds the sum and tests |Round(sum, 4) - 1| <= 1e-6.
+//     With every |entry| < 2e5 and R <= kAddcExactRows the floating-point sum is within (R+1) 2^-53 sum|v_i| < 2.4e-5
+//     of K / 1e4, K = sum k_i, so Round recovers K whatever the order of the additions and the test is K == 10000.
+//     K is a sum of integers below 2^53: exact and order independent, so the segments combine with atomicAdd (and
+//     atomicMin for the first row holding an exact 1).  A job outside those bounds raises its `big` flag and
+//     k_bb_addc_elim recomputes its keys with the literal row-order sums (addc_keys_literal).
+constexpr int kAddcThreads = 64, kAddcSegs = 4, kAddcExactRows = 1024;
+constexpr int kAddcNoRow = 0x7f7f7f7f;  // cudaMemset(0x7f) pattern of the key array: no row holds an exact 1
 __device__ __forceinline__ double addc_bound_row(const BBAddc& jb, int j) {  // :727-747
   const int C = jb.C, C2 = C + 1;
   double v = 0.0;
@@ -395,40 +402,52 @@ __device__ __forceinline__ double addc_bound_row(const BBAddc& jb, int j) {  // 
   }
   return v;
 }
+// Round(Round(x, 4), 4) and the integer k = x * 1e4 rounded (0 outside the division-free range)
+__device__ __forceinline__ double addc_round(double x, double& k, bool& big) {
+  if (fabs(x) < 2e5) {
+    k = rint(__dmul_rn(x, 1e4));
+    if (k == 0.0) return k;
+    const double q0 = __dmul_rn(k, 1e-4);
+    return __fma_rn(__fma_rn(-1e4, q0, k), 1e-4, q0);
+  }
+  big = true;
+  k = 0.0;
+  return net_round4_div(net_round4_div(x));
+}
 __global__ void __launch_bounds__(kAddcThreads) k_bb_addc_build(const BBAddc* jobs) {
-  const BBAddc& jb = jobs[blockIdx.y];
+  const BBAddc& jb = jobs[blockIdx.z];
   const int R = jb.R, C = jb.C, ldc = jb.ldc;
   const int c0 = 2 * (blockIdx.x * kAddcThreads + threadIdx.x);
   if (c0 >= ldc) return;
+  const int per = (R + kAddcSegs - 1) / kAddcSegs;
+  const int r0 = blockIdx.y * per, r1 = min(R, r0 + per);
   const bool nz = jb.negzero != 0;
   const bool in0 = c0 < C, in1 = c0 + 1 < C;
   const bool interior = c0 + 1 < C - 1;  // both columns keep their place in the child
   const double2* src = reinterpret_cast<const double2*>(jb.parent + c0);
   const size_t sp = (size_t)(jb.ldp >> 1);
   double s0 = 0.0, s1 = 0.0;
-  int f0 = R, f1 = R;
-  bool big = false;
-  for (int i0 = 0; i0 < R; i0 += 8) {
+  int f0 = INT_MAX, f1 = INT_MAX;
+  bool big = R > kAddcExactRows;
+  for (int i0 = r0; i0 < r1; i0 += 8) {
     double2 t[8];
 #pragma unroll
     for (int q = 0; q < 8; q++)
-      if (i0 + q < R && in0) t[q] = ld_stream(src + (size_t)(i0 + q) * sp);
+      if (i0 + q < r1 && in0) t[q] = ld_stream(src + (size_t)(i0 + q) * sp);
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int i = i0 + q;
-      if (i >= R) continue;
-      double v0 = 0.0, v1 = 0.0;
+      if (i >= r1) continue;
+      double v0 = 0.0, v1 = 0.0, k0 = 0.0, k1 = 0.0;
       if (in0) {
-        big |= !(fabs(t[q].x) < 2e5);
-        v0 = net_round4_twice(t[q].x);
-        s0 = __dadd_rn(s0, v0);
-        if (f0 == R && v0 == 1.0) f0 = i;
+        v0 = addc_round(t[q].x, k0, big);
+        s0 += k0;
+        if (f0 == INT_MAX && v0 == 1.0) f0 = i;
       }
       if (in1) {
-        big |= !(fabs(t[q].y) < 2e5);
-        v1 = net_round4_twice(t[q].y);
-        s1 = __dadd_rn(s1, v1);
-        if (f1 == R && v1 == 1.0) f1 = i;
+        v1 = addc_round(t[q].y, k1, big);
+        s1 += k1;
+        if (f1 == INT_MAX && v1 == 1.0) f1 = i;
       }
       if (nz) {
         if (v0 == 0.0) v0 = 0.0;
@@ -454,15 +473,33 @@ __global__ void __launch_bounds__(kAddcThreads) k_bb_addc_build(const BBAddc* jo
       }
     }
   }
-  {
+  if (blockIdx.y == 0) {
     double* crow = jb.child + (size_t)R * ldc;
     crow[c0] = addc_bound_row(jb, c0);
     if (c0 + 1 < ldc) crow[c0 + 1] = addc_bound_row(jb, c0 + 1);
     if (c0 <= C && C <= c0 + 1) big |= !(fabs(jb.bound) < 2e5);
   }
-  if (in0) jb.key[c0] = (fabs(net_round4(s0) - 1.0) <= 1e-6) ? f0 : -1;
-  if (in1) jb.key[c0 + 1] = (fabs(net_round4(s1) - 1.0) <= 1e-6) ? f1 : -1;
-  if (big && jb.big) *jb.big = 1;
+  if (in0) {
+    if (s0 != 0.0) atomicAdd(jb.ksum + c0, s0);
+    if (f0 != INT_MAX) atomicMin(jb.key + c0, f0);
+  }
+  if (in1) {
+    if (s1 != 0.0) atomicAdd(jb.ksum + c0 + 1, s1);
+    if (f1 != INT_MAX) atomicMin(jb.key + c0 + 1, f1);
+  }
+  if (big) *jb.big = 1;
+}
+// the literal IdentifyBasicVariables scan of one column (row-order floating-point sum), for jobs flagged `big`
+__device__ int addc_key_literal(const BBAddc& jb, int k) {
+  double sum = 0.0;
+  int first1 = jb.R;
+  for (int i = 0; i < jb.R; i++) {
+    const double v = net_round4_div(net_round4_div(jb.parent[(size_t)i * jb.ldp + k]));
+    sum = __dadd_rn(sum, v);
+    if (first1 == jb.R && v == 1.0) first1 = i;
+  }
+  sum = net_round4_div(sum);
+  return (fabs(sum - 1.0) <= 1e-6) ? first1 : -1;
 }
 // ordering (:664-685, stable by first-"1" row) and the elimination loop (:752-797); one CTA per job
 __global__ void __launch_bounds__(kBBT) k_bb_addc_elim(const BBAddc* jobs) {
@@ -482,6 +519,20 @@ __global__ void __launch_bounds__(kBBT) k_bb_addc_elim(const BBAddc* jobs) {
   if (tid == 0) {
     sh_nb = 0;
     sh_base = 0;
+  }
+  // keys: first-"1" row of the columns whose rounded sum is 1 (k_bb_addc_build left K and the first row there)
+  {
+    const bool literal = *jb.big != 0;
+    for (int k = tid; k < C; k += blockDim.x) {
+      int key;
+      if (literal) {
+        key = addc_key_literal(jb, k);
+      } else {
+        const int f = jb.key[k];
+        key = (jb.ksum[k] == 1e4) ? (f == kAddcNoRow ? R : f) : -1;
+      }
+      jb.key[k] = key;
+    }
   }
   __syncthreads();
   for (int k0 = 0; k0 < C; k0 += blockDim.x) {
@@ -553,7 +604,7 @@ __global__ void __launch_bounds__(kBBT) k_bb_addc_elim(const BBAddc* jobs) {
     big |= !(fabs(x) < 2e5);
     v[cc] = x;
   }
-  if (big && jb.big) *jb.big = 1;
+  if (big) *jb.big = 1;
 }
 
 }  // namespace lpr
@@ -610,6 +661,7 @@ struct lpr_bb {
   double* d_col = nullptr;   // 2*cap x Rmax
   double* d_prow = nullptr;  // 2*cap x ldmax
   int* d_key = nullptr;      // 2*cap x ldmax
+  double* d_ksum = nullptr;  // 2*cap x ldmax
   int* d_order = nullptr;    // 2*cap x ldmax
   int* d_ctl = nullptr;    // kCtlLists + 2 * (2*cap) control words of the batched solve
   int* d_dirty = nullptr;  // 2*cap
@@ -664,6 +716,7 @@ static int bb_alloc_scratch(lpr_bb* h, int cap) {
   A_DEV(d_col, double, (size_t)nlp * h->Rmax);
   A_DEV(d_prow, double, (size_t)nlp * h->ldmax);
   A_DEV(d_key, int, (size_t)nlp * h->ldmax);
+  A_DEV(d_ksum, double, (size_t)nlp * h->ldmax);
   A_DEV(d_order, int, (size_t)nlp * 2 * h->ldmax);
   A_DEV(d_ctl, int, kCtlLists + 2 * nlp);
   A_DEV(d_dirty, int, nlp);
@@ -721,7 +774,7 @@ static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps
 
 static int bb_run_addc(cudaStream_t stream, BBAddc* h_jobs, BBAddc* d_jobs, int njobs, int max_ldc) {
   LPR_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(BBAddc) * njobs, cudaMemcpyHostToDevice, stream));
-  dim3 gb((max_ldc / 2 + kAddcThreads - 1) / kAddcThreads, njobs);
+  dim3 gb((max_ldc / 2 + kAddcThreads - 1) / kAddcThreads, kAddcSegs, njobs);
   k_bb_addc_build<<<gb, kAddcThreads, 0, stream>>>(d_jobs);
   LPR_LAUNCH_CHECK();
   k_bb_addc_elim<<<njobs, kBBT, 0, stream>>>(d_jobs);
@@ -827,6 +880,7 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
         jb.child = slabA[j];
         jb.key = h->d_key + (size_t)j * h->ldmax;
         jb.order = h->d_order + (size_t)j * 2 * h->ldmax;
+        jb.ksum = h->d_ksum + (size_t)j * h->ldmax;
         jb.big = h->d_dirty + j;
         jb.negzero = 1;
         jb.R = nd.R;
@@ -856,6 +910,8 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
       double tp2 = now_s();
       h->t_host += tp2 - tp1;
       LPR_CUDA(cudaMemsetAsync(h->d_dirty, 0, sizeof(int) * nj, h->stream));
+      LPR_CUDA(cudaMemsetAsync(h->d_ksum, 0, sizeof(double) * (size_t)nj * h->ldmax, h->stream));
+      LPR_CUDA(cudaMemsetAsync(h->d_key, 0x7f, sizeof(int) * (size_t)nj * h->ldmax, h->stream));
       if ((rc = bb_run_addc(h->stream, h->h_jobs, h->d_jobs, nj, h->ldmax))) return rc;
       if (getenv("LPR_BB_PROFILE")) cudaStreamSynchronize(h->stream);
       double tp3 = now_s();
@@ -914,7 +970,7 @@ int lpr_bb_destroy(lpr_bb* h) {
   for (double* c : h->chunks) cudaFree(c);
   cudaFree(h->d_lps); cudaFree(h->d_jobs); cudaFree(h->d_eval); cudaFree(h->d_x); cudaFree(h->d_tabs);
   cudaFree(h->d_dims); cudaFree(h->d_col); cudaFree(h->d_prow); cudaFree(h->d_key); cudaFree(h->d_order);
-  cudaFree(h->d_ctl); cudaFree(h->d_dirty);
+  cudaFree(h->d_ctl); cudaFree(h->d_dirty); cudaFree(h->d_ksum);
   if (h->h_lps) cudaFreeHost(h->h_lps);
   if (h->h_jobs) cudaFreeHost(h->h_jobs);
   if (h->h_eval) cudaFreeHost(h->h_eval);
@@ -970,7 +1026,7 @@ static int bb_create_empty(int device, int rows, int cols, int n_vars, int enabl
     }
   }
   const char* bc = getenv("LPR_BB_BATCH");
-  rc = bb_alloc_scratch(h, bc ? std::max(1, atoi(bc)) : 32);
+  rc = bb_alloc_scratch(h, bc ? std::max(1, atoi(bc)) : 64);
   if (rc) {
     lpr_bb_destroy(h);
     return rc;
@@ -1264,21 +1320,22 @@ int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound
   rc = tab_alloc(parent->device, parent->R + 1, parent->C + 1, 0, 0, &ch);
   if (rc) return rc;
   BBAddc jb;
-  int *d_key = nullptr, *d_order = nullptr;
-  BBAddc* d_jb = nullptr;
-  cudaError_t e = cudaMalloc(&d_key, sizeof(int) * parent->C);
-  if (e == cudaSuccess) e = cudaMalloc(&d_order, sizeof(int) * 2 * (size_t)parent->C);
-  if (e == cudaSuccess) e = cudaMalloc(&d_jb, sizeof(BBAddc));
-  if (e != cudaSuccess) {
-    cudaFree(d_key); cudaFree(d_order); cudaFree(d_jb);
+  // scratch in one block: [ksum: C doubles | big: 2 ints | key: C ints | order: 2C ints | job descriptor]
+  const size_t Cp = (size_t)round_up(parent->C, 2);
+  const size_t off_big = sizeof(double) * Cp, off_key = off_big + 2 * sizeof(int), off_order = off_key + sizeof(int) * Cp,
+               off_job = (off_order + sizeof(int) * 2 * Cp + 15) / 16 * 16;
+  char* d_scr = nullptr;
+  if (cudaMalloc(&d_scr, off_job + sizeof(BBAddc)) != cudaSuccess) {
+    cudaGetLastError();
     lpr_tab_destroy(ch);
     return fail(LPR_E_NOMEM, "AddConstraint scratch allocation failed");
   }
   jb.parent = parent->T;
   jb.child = ch->T;
-  jb.key = d_key;
-  jb.order = d_order;
-  jb.big = nullptr;
+  jb.ksum = reinterpret_cast<double*>(d_scr);
+  jb.big = reinterpret_cast<int*>(d_scr + off_big);
+  jb.key = reinterpret_cast<int*>(d_scr + off_key);
+  jb.order = reinterpret_cast<int*>(d_scr + off_order);
   jb.negzero = 0;  // AddConstraint proper: the -0.0 clean-up belongs to DoDualSimplex
   jb.R = parent->R;
   jb.C = parent->C;
@@ -1289,9 +1346,12 @@ int lpr_tab_bb_add_constraint(lpr_tab* parent, int n_vars, int var, double bound
   jb.type = type;
   jb.bound = bound;
   cudaStreamSynchronize(parent->stream);
-  rc = bb_run_addc(ch->stream, &jb, d_jb, 1, ch->ld);
+  cudaError_t e = cudaMemsetAsync(d_scr, 0, off_key, ch->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_scr + off_key, 0x7f, sizeof(int) * Cp, ch->stream);
+  rc = e == cudaSuccess ? bb_run_addc(ch->stream, &jb, reinterpret_cast<BBAddc*>(d_scr + off_job), 1, ch->ld)
+                        : fail(LPR_E_CUDA, "AddConstraint: %s", cudaGetErrorString(e));
   if (rc == LPR_OK && cudaStreamSynchronize(ch->stream) != cudaSuccess) rc = fail(LPR_E_CUDA, "AddConstraint failed");
-  cudaFree(d_key); cudaFree(d_order); cudaFree(d_jb);
+  cudaFree(d_scr);
   if (rc) {
     lpr_tab_destroy(ch);
     return rc;

@@ -48,6 +48,49 @@ def test_round4_matches_oracle():
         assert_bit_equal(t.read(), O.bb_round(T))
 
 
+def test_round4_division_free_range_boundary():
+    """net_round4 computes k / 1e4 without a division for |x| < 2e5 (tools/div1e4_check.c) and literally above:
+    both sides of the boundary, halfway cases and signed zeros against the oracle's literal form."""
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([
+        rng.uniform(-2.2e5, 2.2e5, 4000), rng.uniform(-3, 3, 4000), rng.integers(-2_000_000, 2_000_000, 2000) / 1e4,
+        (rng.integers(-10**9, 10**9, 2000) + 0.5) / 1e4,
+        [199999.99995, 2e5, -2e5, 200000.00005, 214748.3648, 214748.36485, -0.0, 0.0, -4e-5, 4e-5, 1.00005, 0.99995,
+         np.nan, np.inf, -np.inf, 1e16, 9.99e15],
+    ])
+    T = np.zeros((41, 300))
+    T.flat[:xs.size] = xs
+    with L.DeviceTableau.from_host(T) as t:
+        t.round4()
+        assert_bit_equal(t.read(), O.bb_round(T))
+
+
+@pytest.mark.parametrize("poison", [3.1e5, -7e8, 1e17])
+def test_add_constraint_literal_path_for_large_entries(poison):
+    """One entry outside the division-free range sends the whole job through the literal row-order column sums."""
+    Tf = np.array(ip_final(31, 7, 9), copy=True)
+    Tf[3, 11] = poison
+    for var, typ in ((0, 0), (4, 1)):
+        ref = O.bb_add_constraint(Tf, 9, var, 2.0, typ)
+        with L.DeviceTableau.from_host(Tf) as t:
+            with t.bb_add_constraint(9, var, 2.0, typ) as ch:
+                assert_bit_equal(ch.read(), ref)
+
+
+@pytest.mark.parametrize("seed,m,n", [(41, 9, 14), (42, 20, 33), (43, 33, 64)])
+def test_add_constraint_random_ip(seed, m, n):
+    """Row-segment / column-pair geometry of k_bb_addc_build on shapes that straddle its tile edges."""
+    Tf = ip_final(seed, m, n)
+    x = O.bb_extract(O.bb_round(Tf), n)
+    for var in (0, n // 2, n - 1):
+        for typ in (0, 1):
+            bound = float(np.floor(x[var]) if typ == 0 else np.ceil(x[var]))
+            ref = O.bb_add_constraint(Tf, n, var, bound, typ)
+            with L.DeviceTableau.from_host(Tf) as t:
+                with t.bb_add_constraint(n, var, bound, typ) as ch:
+                    assert_bit_equal(ch.read(), ref)
+
+
 def test_net_round_equals_rint_on_edges():
     xs = [0.5, 1.5, 2.5, -0.5, -1.5, 0.49999999999999994, -0.49999999999999994, 1e15 + 0.5, 4503599627370497.0,
           0.0, -0.0, 2.4999999999999996, 1e300, -3.5, 7.5e-5 * 1e4]
