@@ -330,11 +330,13 @@ def main():
     # -------- branch & bound node pools (BASELINE configs[4] / configs[3]); partitioned across ranks ----
     bb = knap = None
     if not os.environ.get("LPR_BENCH_SKIP_BB"):
-        os.environ.setdefault("LPR_BB_PREALLOC_MB", "81920")  # node slabs carved before the timed region
-        os.environ.setdefault("LPR_BB_MAX_DEPTH", "192")       # deep enough for the node budget below
+        os.environ.setdefault("LPR_BB_PREALLOC_MB", "126976")  # node slabs carved before the timed region
+        os.environ.setdefault("LPR_BB_MAX_DEPTH", "192")        # deep enough for the node budget below
         from lpr_381_group_v22_b200.bench_workloads import run_bb_cfg5, run_knap_cfg4
         try:
-            bb = run_bb_cfg5(512, 1024, 385, dev, dist, int(os.environ.get("LPR_BENCH_BB_NODES", "4096")), 256)
+            # 12 time-sliced rounds of 10 ms (at most 1024 nodes each) per rank, whatever the rank count
+            bb = run_bb_cfg5(512, 1024, 385, dev, dist, int(os.environ.get("LPR_BENCH_BB_NODES", "12288")), 1024,
+                             float(os.environ.get("LPR_BENCH_BB_SLICE_MS", "10")))
             knap = run_knap_cfg4(10000, 384, dev, dist, 1 << 26, 32768)
         except Exception as ex:  # the headline line must still be printed
             bb = bb or {"error": repr(ex)}

@@ -201,6 +201,14 @@ int lpr_bb_destroy(lpr_bb* h);
 int lpr_bb_open_count(lpr_bb* h, int64_t* n);
 /* expand up to max_nodes open nodes (deepest first); returns nodes processed / pivots done */
 int lpr_bb_run(lpr_bb* h, int64_t max_nodes, int64_t* processed, int64_t* pivots);
+/* same with a time slice: stops after the batch during which max_seconds (> 0) of host time have elapsed.  The
+ * multi-GPU driver runs time-sliced rounds so that ranks whose subtrees need more pivots per node do not hold the
+ * others at the incumbent exchange (the result does not depend on where the rounds are cut). */
+int lpr_bb_run_timed(lpr_bb* h, int64_t max_nodes, double max_seconds, int64_t* processed, int64_t* pivots);
+/* keep the open nodes whose position in the stack is == offset (mod stride) and drop the others: after every rank
+ * has expanded the same root for a few batches (bit-identical pools), each keeps its own share -- a start-up
+ * partition without any transfer (lpr_381_group_v22_b200/distributed.py, replicated_root) */
+int lpr_bb_keep_stride(lpr_bb* h, int offset, int stride);
 /* totals since creation; depth_overflow counts nodes whose children were NOT generated because they would
  * exceed the slab depth headroom (LPR_BB_MAX_DEPTH, default 128) -- a non-zero value means the search was cut */
 int lpr_bb_stats(lpr_bb* h, int64_t* processed, int64_t* pivots, int64_t* depth_overflow, int* max_depth);

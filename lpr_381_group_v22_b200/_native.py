@@ -93,6 +93,8 @@ SIGNATURES = {
     "lpr_bb_destroy": (C.c_int, [vp]),
     "lpr_bb_open_count": (C.c_int, [vp, lp]),
     "lpr_bb_run": (C.c_int, [vp, C.c_int64, lp, lp]),
+    "lpr_bb_run_timed": (C.c_int, [vp, C.c_int64, C.c_double, lp, lp]),
+    "lpr_bb_keep_stride": (C.c_int, [vp, C.c_int, C.c_int]),
     "lpr_bb_stats": (C.c_int, [vp, lp, lp, lp, ip]),
     "lpr_bb_get_incumbent": (C.c_int, [vp, ip, dp, dp, ip, ip]),
     "lpr_bb_set_incumbent": (C.c_int, [vp, C.c_double, dp, ip, C.c_int]),

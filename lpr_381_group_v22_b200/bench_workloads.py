@@ -43,12 +43,13 @@ def _sync_time(comm, t):
     return comm.allreduce_max(t)
 
 
-def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk):
+def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk, slice_ms=0.0):
     """LP relaxation with the tableau solver, then branch & bound simplex with reference semantics
     (4-d.p. rounding, dual-then-primal node solves), node cap lifted to `max_nodes` per rank-round budget,
-    pruning on; the pool is partitioned across the ranks."""
+    pruning on; the pool is partitioned across the ranks.  `slice_ms` > 0: rounds are time slices of that
+    length (at most `chunk` nodes each), the number of rounds stays max_nodes / chunk."""
     import os
-    os.environ.setdefault("LPR_BB_PREALLOC_MB", "81920")  # node slabs carved before the timed region
+    os.environ.setdefault("LPR_BB_PREALLOC_MB", "126976")  # node slabs carved before the timed region
     os.environ.setdefault("LPR_BB_MAX_DEPTH", "192")       # deep enough for the node budgets used here
     comm = _Comm(dist, f"cuda:{device}")
     A, b, c = gen_dense_ip(seed, m, n)
@@ -61,12 +62,14 @@ def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk):
     lp_ms = tab.last_solve_ms
     final = tab.read()
     tab.close()
-    root = final if comm.rank == 0 else None
-    pool = BBPool(root, n, prune=True, device=device, rows=final.shape[0], cols=final.shape[1])
-    warmup_comm(dist, f"cuda:{device}")
+    # every rank solved the same relaxation to the same bits: all start from the root and split it without a
+    # transfer (run_distributed, replicated_root)
+    pool = BBPool(final, n, prune=True, device=device)
+    warmup_comm(dist, f"cuda:{device}", n)
     t1 = time.perf_counter()
     res = run_distributed(pool, dist, f"cuda:{device}", chunk_nodes=chunk, payload_len=n,
-                          max_rounds=max(1, max_nodes // max(1, chunk)))
+                          max_rounds=max(1, max_nodes // max(1, chunk)), chunk_seconds=slice_ms * 1e-3,
+                          replicated_root=True)
     dt = _sync_time(comm, time.perf_counter() - t1)
     piv = sum(v[0] for v in comm.allgather_ints([pool.pivots]))
     left = sum(v[0] for v in comm.allgather_ints([pool.open_count()]))
@@ -83,14 +86,15 @@ def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk):
                 node_pivots_per_s=piv / dt, lp_relaxation_pivots=lp["n_pivots"], lp_relaxation_ms=lp_ms,
                 incumbent_z=(inc[0] if inc else None), incumbent_nonzeros=(int(np.count_nonzero(inc[2])) if inc else None),
                 open_left=left, steals=res["steals"], nodes_moved=res["nodes_moved"], rounds=res["rounds"],
-                finished=(left == 0))
+                finished=(left == 0), phase_seconds_rank0=res["seconds_rank0"],
+                run_seconds_per_rank=res["run_seconds_per_rank"])
 
 
 def run_knap_cfg4(n_items, seed, device, dist, max_nodes, chunk):
     comm = _Comm(dist, f"cuda:{device}")
     w, v, cap = gen_knapsack(seed, n_items)
     pool = KnapPool(cap, w, v, device=device, with_root=(comm.rank == 0))
-    warmup_comm(dist, f"cuda:{device}")
+    warmup_comm(dist, f"cuda:{device}", n_items)
     t1 = time.perf_counter()
     res = run_distributed(pool, dist, f"cuda:{device}", chunk_nodes=chunk, payload_len=n_items,
                           max_rounds=max(1, max_nodes // max(1, chunk)), seed_nodes_per_rank=64, low_water=64)
@@ -105,4 +109,4 @@ def run_knap_cfg4(n_items, seed, device, dist, max_nodes, chunk):
                 best_value=(inc[0] if inc else None), items_chosen=(int(np.count_nonzero(inc[2])) if inc else None),
                 weight_used=(float(np.dot(inc[2], w)) if inc else None), open_left=left, steals=res["steals"],
                 nodes_moved=res["nodes_moved"], rounds=res["rounds"], finished=(left == 0),
-                phase_seconds_rank0=res["seconds_rank0"])
+                phase_seconds_rank0=res["seconds_rank0"], run_seconds_per_rank=res["run_seconds_per_rank"])

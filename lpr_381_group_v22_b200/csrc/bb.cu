@@ -797,16 +797,18 @@ static inline double now_s() {
 }
 
 static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processed_out, int64_t* pivots_out,
-                      bool* hit_limit) {
+                      bool* hit_limit, double max_seconds = 0.0) {
   int rc = select_device(h->device);
   if (rc) return rc;
   int64_t done = 0, piv = 0;
   if (hit_limit) *hit_limit = false;
+  const double t_start = now_s();
   while (!h->open.empty()) {
     if (max_nodes >= 0 && done >= max_nodes) {
       if (hit_limit) *hit_limit = true;
       break;
     }
+    if (max_seconds > 0.0 && done > 0 && now_s() - t_start >= max_seconds) break;
     int nb = (int)std::min<int64_t>(std::min<int64_t>(batch, h->cap), (int64_t)h->open.size());
     if (max_nodes >= 0) nb = (int)std::min<int64_t>(nb, max_nodes - done);
     double tp0 = now_s();
@@ -1011,7 +1013,7 @@ static int bb_create_empty(int device, int rows, int cols, int n_vars, int enabl
     const char* pm = getenv("LPR_BB_PREALLOC_MB");
     size_t want = (size_t)(pm ? std::max(0, atoi(pm)) : 1024) << 20;
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) want = std::min(want, free_b / 2);
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) want = std::min(want, free_b - free_b / 4);
     size_t nsl = want / (sizeof(double) * h->slab_doubles);
     while (nsl > 0) {
       const size_t take = std::min<size_t>(nsl, 512);
@@ -1093,6 +1095,22 @@ int lpr_bb_stats(lpr_bb* h, int64_t* processed, int64_t* pivots, int64_t* depth_
 int lpr_bb_run(lpr_bb* h, int64_t max_nodes, int64_t* processed, int64_t* pivots) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
   return bb_process(h, max_nodes, h->cap, processed, pivots, nullptr);
+}
+int lpr_bb_keep_stride(lpr_bb* h, int offset, int stride) {
+  if (!h || stride < 1 || offset < 0 || offset >= stride) return fail(LPR_E_BADARG, "bad keep_stride arguments");
+  std::vector<BBNode> kept;
+  for (size_t i = 0; i < h->open.size(); i++) {
+    if ((int)(i % (size_t)stride) == offset)
+      kept.push_back(std::move(h->open[i]));
+    else
+      bb_give_slab(h, h->open[i].slab);
+  }
+  h->open.swap(kept);
+  return LPR_OK;
+}
+int lpr_bb_run_timed(lpr_bb* h, int64_t max_nodes, double max_seconds, int64_t* processed, int64_t* pivots) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  return bb_process(h, max_nodes, h->cap, processed, pivots, nullptr, max_seconds);
 }
 
 int lpr_bb_get_incumbent(lpr_bb* h, int* has, double* z, double* x, int* key, int* key_len) {

@@ -7,7 +7,8 @@ pool in its GPU's HBM and expands it in batches; between batches the ranks
   1. all-reduce the incumbent value (NCCL all-reduce MAX over NVLink -- the north star's "allreduce-min"
      on the negated objective) and break ties on the DFS path key, so the incumbent -- and therefore
      the final answer -- is the same for every rank count,
-  2. all-gather the open-node counts (termination = all zero),
+  2. learn every rank's open-node count (termination = all zero) -- the counts ride in the same all-reduce
+     as the incumbent value (round_status), so a round without a new incumbent costs one collective,
   3. steal work: ranks that ran dry receive the shallowest nodes of the fullest ranks (peer
      send/recv of node records).
 
@@ -69,11 +70,14 @@ class BBPool:
         N.check(N.lib().lpr_bb_open_count(self._h, C.byref(n)))
         return n.value
 
-    def run(self, max_nodes):
+    def run(self, max_nodes, max_seconds=0.0):
         done, piv = C.c_int64(), C.c_int64()
-        N.check(N.lib().lpr_bb_run(self._h, max_nodes, C.byref(done), C.byref(piv)))
+        N.check(N.lib().lpr_bb_run_timed(self._h, max_nodes, float(max_seconds), C.byref(done), C.byref(piv)))
         self.pivots += piv.value
         return done.value
+
+    def keep_stride(self, offset, stride):
+        N.check(N.lib().lpr_bb_keep_stride(self._h, int(offset), int(stride)))
 
     def stats(self):
         done, piv, ovf, md = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
@@ -205,6 +209,14 @@ class _Comm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allreduce_max_vec(self, values):
+        """one all-reduce(MAX) over a short float64 vector (the per-round status word of run_distributed)"""
+        if self.dist is None:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
     def allgather_ints(self, values):
         if self.dist is None:
             return [list(values)]
@@ -240,11 +252,13 @@ class _Comm:
         return t.cpu().numpy()
 
 
-def exchange_incumbent(pool, comm, payload_len):
-    """all-reduce MAX of the value, then the DFS-first key among the ranks that hold that value; the
-    winner's payload (x or the chosen-item vector) is broadcast so every rank ends with the same incumbent."""
+def exchange_incumbent(pool, comm, payload_len, zmax=None):
+    """all-reduce MAX of the value (skipped when the caller already has it), then the DFS-first key among the
+    ranks that hold that value; the winner's payload (x or the chosen-item vector) is broadcast so every rank
+    ends with the same incumbent."""
     inc = pool.get_incumbent()
-    zmax = comm.allreduce_max(inc[0] if inc is not None else float("-inf"))
+    if zmax is None:
+        zmax = comm.allreduce_max(inc[0] if inc is not None else float("-inf"))
     if zmax == float("-inf"):
         return None
     mine = inc is not None and inc[0] == zmax
@@ -263,13 +277,35 @@ def exchange_incumbent(pool, comm, payload_len):
     return best
 
 
-def warmup_comm(dist, device):
-    """NCCL sets up its point-to-point channels lazily (tens of ms per pair): touch every pair once,
-    outside any timed region, so that the first steal does not pay for it."""
+def round_status(pool, comm, agreed):
+    """The per-round exchange, ONE all-reduce(MAX) over [z, changed, count_0 .. count_{world-1}]: the best
+    incumbent value of any rank, whether any rank's incumbent differs from the one agreed on last time (only
+    then are keys and the payload exchanged), and every rank's open-node count (each rank fills its own slot;
+    counts are >= 0, so MAX against the other ranks' zeros returns them unchanged)."""
+    inc = pool.get_incumbent()
+    mine = None if inc is None else (inc[0], tuple(inc[1]))
+    same = agreed is not None and mine == (agreed[0], tuple(agreed[1])) if mine is not None else agreed is None
+    vec = [float("-inf") if inc is None else float(inc[0]), 0.0 if same else 1.0] + [0.0] * comm.world
+    vec[2 + comm.rank] = float(pool.open_count())
+    out = comm.allreduce_max_vec(vec)
+    return out[0], out[1] != 0.0, [int(c) for c in out[2:]]
+
+
+def warmup_comm(dist, device, payload_len=1):
+    """NCCL sets up the channels of each collective kind and of each point-to-point pair lazily (tens to
+    hundreds of ms): run every one once, outside any timed region, so that the first incumbent exchange and the
+    first steal do not pay for it."""
     if dist is None:
         return
     comm = _Comm(dist, device)
-    comm.allreduce_max(0.0)
+    for _ in range(2):  # every collective run_distributed uses, at the sizes it uses them
+        comm.allreduce_max(0.0)
+        comm.allreduce_max_vec([0.0] * (2 + comm.world))
+        comm.allgather_ints([0])
+        comm.allgather_ints([0] * 64)
+        comm.allgather_ints([0, 0, 0, 0])
+        for src in range(comm.world):
+            comm.bcast_array(np.zeros(payload_len), src, np.float64)
     token = np.zeros(8, dtype=np.uint8)
     for a in range(comm.world):          # every unordered pair once, lower rank sends first
         for b in range(a + 1, comm.world):
@@ -300,9 +336,14 @@ def steal_plan(counts, min_keep=2, low_water=0):
 
 
 def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len=None, max_rounds=1 << 30,
-                    seed_nodes_per_rank=8, low_water=0):
+                    seed_nodes_per_rank=8, low_water=0, chunk_seconds=0.0, replicated_root=False):
     """Drive `pool` (rank-local) to completion together with the other ranks.  Returns a dict with the
-    incumbent (identical on every rank), node counts and exchange statistics."""
+    incumbent (identical on every rank), node counts and exchange statistics.  A round ends after
+    `chunk_nodes` nodes or, when `chunk_seconds` > 0 and the pool supports it, after that time slice --
+    whichever comes first: node costs differ between subtrees (pivots per node), so time-sliced rounds keep
+    every rank busy until the exchange instead of waiting for the rank with the most expensive nodes.
+    `replicated_root`: every rank was given the same root; all of them expand it identically (the kernels are
+    bit-reproducible) and keep every world-th open node, so the start-up partition needs no transfer."""
     import time
     comm = _Comm(dist, device)
     rank, world = comm.rank, comm.world
@@ -312,16 +353,23 @@ def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len
     if payload_len is None:
         payload_len = getattr(pool, "n_vars", None) or getattr(pool, "n")
     # seeding: rank 0 owns the root; expand it a little so that the first steal round has work to share
-    if world > 1 and rank == 0:
+    if world > 1 and (rank == 0 or replicated_root):
         guard = 0
         while 0 < pool.open_count() < seed_nodes_per_rank * world and guard < 64:
-            processed += pool.run(max(1, seed_nodes_per_rank))
+            n = pool.run(max(1, seed_nodes_per_rank))
+            processed += n if rank == 0 else 0  # the replicas' copies of the seed nodes are not counted
             guard += 1
+        if replicated_root:
+            pool.keep_stride(rank, world)
     t_seed = time.perf_counter() - t_a
+    agreed = None
     while rounds < max_rounds:
         rounds += 1
+        t_a = time.perf_counter()
+        zmax, changed, counts = round_status(pool, comm, agreed)
+        if changed:
+            agreed = exchange_incumbent(pool, comm, payload_len, zmax) if world > 1 else pool.get_incumbent()
         t_b = time.perf_counter()
-        counts = [v[0] for v in comm.allgather_ints([pool.open_count()])]
         if sum(counts) == 0:
             break
         for donor, recv, give in steal_plan(counts, low_water=low_water):
@@ -343,16 +391,14 @@ def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len
                     pool.import_nodes(comm.recv_bytes(nbytes, donor, keep_on_device=True))
         t_c = time.perf_counter()
         if pool.open_count() > 0:
-            processed += pool.run(chunk_nodes)
+            processed += pool.run(chunk_nodes, chunk_seconds) if chunk_seconds > 0 else pool.run(chunk_nodes)
         t_d = time.perf_counter()
-        exchange_incumbent(pool, comm, payload_len)
-        t_e = time.perf_counter()
+        t_inc += t_b - t_a
         t_steal += t_c - t_b
         t_run += t_d - t_c
-        t_inc += t_e - t_d
     best = exchange_incumbent(pool, comm, payload_len) if world > 1 else pool.get_incumbent()
-    totals = comm.allgather_ints([processed, steals, moved])
+    totals = comm.allgather_ints([processed, steals, moved, int(t_run * 1e6)])
     return dict(incumbent=best, nodes_local=processed, nodes_total=sum(t[0] for t in totals),
                 steals=sum(t[1] for t in totals), nodes_moved=sum(t[2] for t in totals), rounds=rounds,
-                world=world, rank=rank,
-                seconds_rank0=dict(seed=t_seed, steal_and_counts=t_steal, run=t_run, incumbent_exchange=t_inc))
+                world=world, rank=rank, run_seconds_per_rank=[t[3] * 1e-6 for t in totals],
+                seconds_rank0=dict(seed=t_seed, status_and_incumbent=t_inc, steal=t_steal, run=t_run))

@@ -77,6 +77,9 @@ class CpuKnapPool:
             self.open.append((tuple(zero), key + (0,)))
         return done
 
+    def keep_stride(self, offset, stride):
+        self.open = [nd for i, nd in enumerate(self.open) if i % stride == offset]
+
     def get_incumbent(self):
         return self.inc
 
@@ -109,15 +112,16 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, seed, n, chunk, q):
+def _worker(rank, world, port, seed, n, chunk, q, replicated=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle_lib as O
     from lpr_381_group_v22_b200.distributed import run_distributed
     w, v, cap = O.gen_knapsack(seed, n)
-    pool = CpuKnapPool(cap, w, v, with_root=(rank == 0))
-    res = run_distributed(pool, dist, "cpu", chunk_nodes=chunk, payload_len=n, seed_nodes_per_rank=2)
+    pool = CpuKnapPool(cap, w, v, with_root=(rank == 0 or replicated))
+    res = run_distributed(pool, dist, "cpu", chunk_nodes=chunk, payload_len=n, seed_nodes_per_rank=2,
+                          replicated_root=replicated)
     inc = res["incumbent"]
     q.put((rank, inc[0], tuple(inc[1]), inc[2].tolist(), res["nodes_total"], res["steals"], res["nodes_moved"]))
     dist.destroy_process_group()
@@ -145,6 +149,44 @@ def test_distributed_bb_same_answer_as_sequential(world, seed, n, chunk):
     assert len({o[2] for o in outs}) == 1  # same incumbent key everywhere
     assert outs[0][5] >= 1 and outs[0][6] >= 1  # work was actually stolen
     assert outs[0][4] >= ref["nodes"] // 4
+
+
+@pytest.mark.parametrize("world,seed,n,chunk", [(2, 4, 26, 6), (3, 8, 27, 5)])
+def test_distributed_bb_replicated_root(world, seed, n, chunk):
+    """every rank expands the same root and keeps every world-th node (no start-up transfer): same answer, and
+    the seed nodes are counted once"""
+    import oracle_lib as O
+    w, v, cap = O.gen_knapsack(seed, n)
+    ref = O.knap_bb(cap, w, v)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, seed, n, chunk, q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, best, key, chosen, total, steals, moved in outs:
+        assert best == ref["best"]
+        assert [int(c) for c in chosen] == ref["chosen"].tolist()
+    assert len({o[2] for o in outs}) == 1
+    assert len({o[4] for o in outs}) == 1 and outs[0][4] >= ref["nodes"] // 4
+
+
+def test_round_status_single_process():
+    """the fused status word: value, 'somebody's incumbent changed' flag, per-rank open counts"""
+    import oracle_lib as O
+    from lpr_381_group_v22_b200.distributed import _Comm, round_status
+    w, v, cap = O.gen_knapsack(9, 20)
+    pool = CpuKnapPool(cap, w, v)
+    comm = _Comm(None, "cpu")
+    assert round_status(pool, comm, None) == (float("-inf"), False, [1])
+    pool.run(10 ** 6)
+    z, changed, counts = round_status(pool, comm, None)
+    assert z == pool.get_incumbent()[0] and changed and counts == [0]
+    assert round_status(pool, comm, pool.get_incumbent())[1] is False
 
 
 def test_steal_plan_and_order():

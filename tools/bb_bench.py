@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--seed", type=int, default=385)
     ap.add_argument("--max-nodes", type=int, default=4000)
     ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--slice-ms", type=float, default=0.0, help="time-sliced rounds (B&B simplex pool)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -30,7 +31,7 @@ def main():
     import lpr_381_group_v22_b200 as L
     from lpr_381_group_v22_b200.bench_workloads import run_bb_cfg5, run_knap_cfg4
     if a.what == "bb":
-        r = run_bb_cfg5(a.m, a.n, a.seed, local, dist, a.max_nodes, a.chunk)
+        r = run_bb_cfg5(a.m, a.n, a.seed, local, dist, a.max_nodes, a.chunk, a.slice_ms)
     else:
         r = run_knap_cfg4(a.items, a.seed, local, dist, a.max_nodes, a.chunk)
     if rank == 0:
