@@ -71,6 +71,31 @@ namespace LPR_381_Group_V22.Native
         {
             if (rc != OK) throw new InvalidOperationException("liblprb200: " + Marshal.PtrToStringAnsi(lpr_last_error()));
         }
+
+        // ---- model input (IO/InputFileParser.cs:19-68, Program.cs:114-124, :511-535) ----------------------
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)] public static extern int lpr_model_parse_file(string path, out IntPtr model);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_parse_text(byte[] utf8, long len, out IntPtr model);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_from_dense(int n, int m, double[] objective, double[,] coef, int[] relation, double[] rhs, int isMax, out IntPtr model);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_destroy(IntPtr model);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_info(IntPtr model, out int loaded, out int n, out int nConstraints, out int nSigns);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_problem_type(IntPtr model, [Out] byte[] buf, int cap);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_message(IntPtr model, [Out] byte[] buf, int cap);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_objective(IntPtr model, [Out] double[] c);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_constraint(IntPtr model, int i, [Out] double[] coef, int cap, out int count, [Out] byte[] relation, int relCap, out double rhs);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_sign(IntPtr model, int j, [Out] byte[] buf, int cap);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_add_cli_bound_rows(IntPtr model);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_add_upper_bound_rows(IntPtr model);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_create_from_model(int device, IntPtr model, int isMax, out IntPtr h);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)] public static extern int lpr_model_save_binary(IntPtr model, string path);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)] public static extern int lpr_model_load_binary(string path, out IntPtr model);
+
+        // ---- snapshots (Utilities/TableIterationFormater.cs:22-48, NumFormat.N3) ------------------------------
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_fmt_f3(double x, [Out] byte[] buf, int cap);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_fmt_n3(double x, [Out] byte[] buf, int cap);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)]
+        public static extern int lpr_fmt_table(double[,] tab, int rows, int cols, long ld, int numOriginalVars, string title, string[] rowLabels, int nLabels, out IntPtr text, out long len);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)]
+        public static extern int lpr_tab_format(IntPtr h, int numOriginalVars, string title, string[] rowLabels, int nLabels, out IntPtr text, out long len);
     }
 
     /// <summary>Owns a native handle; Dispose/finalizer frees the device memory.</summary>
@@ -85,5 +110,11 @@ namespace LPR_381_Group_V22.Native
         public RevHandle(IntPtr h) : base(IntPtr.Zero, true) { SetHandle(h); }
         public override bool IsInvalid => handle == IntPtr.Zero;
         protected override bool ReleaseHandle() { return Lpr.lpr_rev_destroy(handle) == Lpr.OK; }
+    }
+    internal sealed class ModelHandle : SafeHandle
+    {
+        public ModelHandle(IntPtr h) : base(IntPtr.Zero, true) { SetHandle(h); }
+        public override bool IsInvalid => handle == IntPtr.Zero;
+        protected override bool ReleaseHandle() { return Lpr.lpr_model_destroy(handle) == Lpr.OK; }
     }
 }

@@ -40,7 +40,124 @@ struct Constraint {
   std::string Relation;
   double RHS;
 };
+
+// IO/InputFileParser.cs:10-68 over the native parser (lpr_model_*): same members, same two silent early returns
+// (missing file, fewer than three lines -> Message, members untouched); what throws FormatException /
+// IndexOutOfRangeException in the reference throws ArgumentException here, with that name in the text.
+class InputFileParser {
+ public:
+  std::string ProblemType;
+  std::vector<double> ObjectiveCoefficients;
+  std::vector<Constraint> Constraints;
+  std::vector<std::string> SignRestrictions;
+  std::string Message;  // the line ReadInputFile writes to the console
+
+  ~InputFileParser() { lpr_model_destroy(model_); }
+  InputFileParser() = default;
+  InputFileParser(const InputFileParser&) = delete;
+  InputFileParser& operator=(const InputFileParser&) = delete;
+
+  void ReadInputFile(const std::string& filePath) {
+    lpr_model* m = nullptr;
+    if (lpr_model_parse_file(filePath.c_str(), &m) != LPR_OK) throw ArgumentException(lpr_last_error());
+    Adopt(m);
+  }
+  void ReadInputText(const std::string& text) {  // the same on an in-memory buffer
+    lpr_model* m = nullptr;
+    if (lpr_model_parse_text(text.data(), (int64_t)text.size(), &m) != LPR_OK) throw ArgumentException(lpr_last_error());
+    Adopt(m);
+  }
+  // Program.cs:114-124 and :511-535 applied to the parsed model (Constraints is refreshed)
+  void AddCliBoundRows() { Check(lpr_model_add_cli_bound_rows(model_)); PullConstraints(); }
+  void AddUpperBoundConstraints() { Check(lpr_model_add_upper_bound_rows(model_)); PullConstraints(); }
+  // PrimalSimplexSolver..ctor on the parsed model, built on the device from the native arrays; caller owns it
+  lpr_tab* CreateDeviceTableau(bool isMaximization = true, int device = 0) const {
+    lpr_tab* t = nullptr;
+    Check(lpr_tab_create_from_model(device, model_, isMaximization ? 1 : 0, &t));
+    return t;
+  }
+  const lpr_model* Native() const { return model_; }
+
+ private:
+  static std::string Str(int (*fn)(const lpr_model*, char*, int), const lpr_model* m) {
+    std::vector<char> buf(1 << 12);
+    Check(fn(m, buf.data(), (int)buf.size()));
+    return std::string(buf.data());
+  }
+  void Adopt(lpr_model* m) {
+    int loaded = 0, n = 0, rows = 0, ns = 0;
+    Check(lpr_model_info(m, &loaded, &n, &rows, &ns));
+    Message = Str(lpr_model_message, m);
+    if (!loaded) {
+      lpr_model_destroy(m);
+      return;
+    }
+    lpr_model_destroy(model_);
+    model_ = m;
+    ProblemType = Str(lpr_model_problem_type, m);
+    std::vector<double> c(n);
+    Check(lpr_model_objective(m, c.data()));
+    ObjectiveCoefficients.insert(ObjectiveCoefficients.end(), c.begin(), c.end());
+    PullConstraints();
+    for (int j = 0; j < ns; j++) {
+      char buf[1024];
+      Check(lpr_model_sign(m, j, buf, (int)sizeof buf));
+      SignRestrictions.emplace_back(buf);
+    }
+  }
+  void PullConstraints() {
+    int rows = 0;
+    Check(lpr_model_info(model_, nullptr, nullptr, &rows, nullptr));
+    Constraints.clear();
+    for (int i = 0; i < rows; i++) {
+      int cnt = 0;
+      Constraint c;
+      char rel[64];
+      Check(lpr_model_constraint(model_, i, nullptr, 0, &cnt, nullptr, 0, nullptr));
+      c.Coefficients.resize(cnt);
+      Check(lpr_model_constraint(model_, i, c.Coefficients.data(), cnt, nullptr, rel, (int)sizeof rel, &c.RHS));
+      c.Relation = rel;
+      Constraints.push_back(std::move(c));
+    }
+  }
+  lpr_model* model_ = nullptr;
+};
 }  // namespace IO
+
+namespace Utilities {
+// Utilities/TableIterationFormater.cs:22-48 and NumFormat.N3 (RevisedPrimalSimplexSolver.cs:455-465), native
+struct TableIterationFormater {
+  static std::string Format(const std::vector<double>& tab, int rows, int cols, int numOriginalVars,
+                            const std::string& title, const std::vector<std::string>* rowLabels = nullptr) {
+    std::vector<const char*> lab;
+    if (rowLabels)
+      for (auto& s : *rowLabels) lab.push_back(s.c_str());
+    const char* text = nullptr;
+    int64_t len = 0;
+    Check(lpr_fmt_table(tab.data(), rows, cols, cols, numOriginalVars, title.c_str(), rowLabels ? lab.data() : nullptr,
+                        (int)lab.size(), &text, &len));
+    return std::string(text, (size_t)len);
+  }
+  static std::string Format(lpr_tab* deviceTableau, int numOriginalVars, const std::string& title,
+                            const std::vector<std::string>* rowLabels = nullptr) {
+    std::vector<const char*> lab;
+    if (rowLabels)
+      for (auto& s : *rowLabels) lab.push_back(s.c_str());
+    const char* text = nullptr;
+    int64_t len = 0;
+    Check(lpr_tab_format(deviceTableau, numOriginalVars, title.c_str(), rowLabels ? lab.data() : nullptr, (int)lab.size(),
+                         &text, &len));
+    return std::string(text, (size_t)len);
+  }
+};
+struct NumFormat {
+  static std::string N3(double x) {
+    char buf[400];
+    Check(lpr_fmt_n3(x, buf, (int)sizeof buf));
+    return buf;
+  }
+};
+}  // namespace Utilities
 
 namespace Simplex {
 

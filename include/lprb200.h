@@ -243,6 +243,56 @@ int lpr_knap_solve(int device, double capacity, int n, const double* weights,
                    const double* values, int64_t max_nodes, double* best, uint8_t* chosen,
                    int64_t* nodes, int* status);
 
+/* ---- model input: IO/InputFileParser.cs:19-68 and the CLI's extra rows ---------------- */
+typedef struct lpr_model lpr_model;
+/* InputFileParser.ReadInputFile (:19-68).  A missing file or fewer than three lines is not an error: like the
+ * reference the parser prints a message (lpr_model_message) and stays empty (lpr_model_info: loaded = 0).  What
+ * throws in the reference -- double.Parse FormatException, a constraint line with fewer than n+2 tokens
+ * (IndexOutOfRangeException) -- returns LPR_E_BADARG with the exception's name at the start of the message. */
+int lpr_model_parse_file(const char* path, lpr_model** out);
+int lpr_model_parse_text(const char* text, int64_t len, lpr_model** out);
+/* dense model from arrays (coef m x n row-major; relation NULL = all <=): the synthetic configs */
+int lpr_model_from_dense(int n, int m, const double* objective, const double* coef, const int* relation,
+                         const double* rhs, int is_maximization, lpr_model** out);
+int lpr_model_destroy(lpr_model* m);
+/* ObjectiveCoefficients.Count, Constraints.Count, SignRestrictions.Count (:12-15) */
+int lpr_model_info(const lpr_model* m, int* loaded, int* n, int* n_constraints, int* n_signs);
+int lpr_model_problem_type(const lpr_model* m, char* out, int cap); /* ProblemType :12, lower-cased :36 */
+int lpr_model_message(const lpr_model* m, char* out, int cap);      /* the console line of :23,:32,:66 */
+int lpr_model_objective(const lpr_model* m, double* c);
+/* Constraints[i] (:70-82): Coefficients (count entries), Relation string, RHS */
+int lpr_model_constraint(const lpr_model* m, int i, double* coef, int cap, int* count, char* relation,
+                         int rel_cap, double* rhs);
+int lpr_model_sign(const lpr_model* m, int j, char* out, int cap); /* SignRestrictions[j] :63-64 */
+/* Program.cs:114-124 / :372-382: menu options 1 and 3 append `x_i <= 1` rows of length n+3 with a stray 1 */
+int lpr_model_add_cli_bound_rows(lpr_model* m);
+/* Program.cs:511-535 AddUpperBoundConstraints (menu option 2): `x_j <= 1` for "bin" / "<=1" restrictions */
+int lpr_model_add_upper_bound_rows(lpr_model* m);
+/* PrimalSimplexSolver..ctor on the parsed model: the tableau is built on the device from the model's arrays
+ * (no List<Constraint> -> double[,] -> upload detour) */
+int lpr_tab_create_from_model(int device, const lpr_model* m, int is_maximization, lpr_tab** out);
+/* dense binary model file (header + raw doubles), so the synthetic configs need no text round trip */
+int lpr_model_save_binary(const lpr_model* m, const char* path);
+int lpr_model_load_binary(const char* path, lpr_model** out);
+
+/* ---- snapshots: Utilities/TableIterationFormater.cs:22-48, NumFormat.N3 ------------------ */
+/* $"{x:F3}" and NumFormat.N3 (RevisedPrimalSimplexSolver.cs:455-465) with .NET Framework semantics: 15
+ * significant digits first, then half-away-from-zero on the digit string; a negative that rounds to zero loses
+ * its sign */
+int lpr_fmt_f3(double x, char* out, int cap);
+int lpr_fmt_n3(double x, char* out, int cap);
+/* TableIterationFormater.Format(tab, numOriginalVars, title, rowLabels) on a host array (ld doubles per row).
+ * *text points to a buffer owned by the library, valid until the calling thread's next lpr_fmt_table /
+ * lpr_tab_format call. */
+int lpr_fmt_table(const double* tab, int rows, int cols, int64_t ld, int num_original_vars,
+                  const char* title, const char* const* row_labels, int n_labels, const char** text,
+                  int64_t* len);
+/* the same for a device tableau: rows stream D2H in ~8 MB blocks through two pinned buffers while host threads
+ * format the previous block (replaces the IterationSnapshots.Add(Format(...)) calls of
+ * PrimalSimplexSolver.cs:86,:148,:122) */
+int lpr_tab_format(lpr_tab* h, int num_original_vars, const char* title, const char* const* row_labels,
+                   int n_labels, const char** text, int64_t* len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,26 @@ SIGNATURES = {
     "lpr_knap_export_nodes": (C.c_int, [vp, C.c_int, vp, C.c_int64, lp, ip]),
     "lpr_knap_import_nodes": (C.c_int, [vp, vp, C.c_int64]),
     "lpr_knap_solve": (C.c_int, [C.c_int, C.c_double, C.c_int, dp, dp, C.c_int64, dp, bp, lp, ip]),
+    "lpr_model_parse_file": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "lpr_model_parse_text": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(vp)]),
+    "lpr_model_from_dense": (C.c_int, [C.c_int, C.c_int, dp, dp, ip, dp, C.c_int, C.POINTER(vp)]),
+    "lpr_model_destroy": (C.c_int, [vp]),
+    "lpr_model_info": (C.c_int, [vp, ip, ip, ip, ip]),
+    "lpr_model_problem_type": (C.c_int, [vp, C.c_char_p, C.c_int]),
+    "lpr_model_message": (C.c_int, [vp, C.c_char_p, C.c_int]),
+    "lpr_model_objective": (C.c_int, [vp, dp]),
+    "lpr_model_constraint": (C.c_int, [vp, C.c_int, dp, C.c_int, ip, C.c_char_p, C.c_int, dp]),
+    "lpr_model_sign": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int]),
+    "lpr_model_add_cli_bound_rows": (C.c_int, [vp]),
+    "lpr_model_add_upper_bound_rows": (C.c_int, [vp]),
+    "lpr_tab_create_from_model": (C.c_int, [C.c_int, vp, C.c_int, C.POINTER(vp)]),
+    "lpr_model_save_binary": (C.c_int, [vp, C.c_char_p]),
+    "lpr_model_load_binary": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "lpr_fmt_f3": (C.c_int, [C.c_double, C.c_char_p, C.c_int]),
+    "lpr_fmt_n3": (C.c_int, [C.c_double, C.c_char_p, C.c_int]),
+    "lpr_fmt_table": (C.c_int, [dp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_char_p, C.POINTER(C.c_char_p),
+                                C.c_int, C.POINTER(vp), lp]),
+    "lpr_tab_format": (C.c_int, [vp, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(vp), lp]),
 }
 
 

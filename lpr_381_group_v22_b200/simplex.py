@@ -52,7 +52,8 @@ class PrimalSimplexSolver:
 
     # -- helpers ---------------------------------------------------------------------------------
     def _capture(self, title):
-        self.IterationSnapshots.append(TableIterationFormater.Format(self._tab.read(), self.numVariables, title))
+        # the tableau stays in HBM: rows stream through pinned buffers into the native formatter (lpr_tab_format)
+        self.IterationSnapshots.append(TableIterationFormater.FormatDevice(self._tab, self.numVariables, title))
 
     def _col_label(self, col):  # :253-254
         return f"x{col + 1}" if col < self.numVariables else f"t{col - self.numVariables + 1}"

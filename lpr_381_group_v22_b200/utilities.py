@@ -1,38 +1,51 @@
-"""Text formatting used by the snapshot path: Utilities/TableIterationFormater.cs:22-48 and
-NumFormat.N3 (Simplex/RevisedPrimalSimplexSolver.cs:451-465).  Host-side only (display)."""
-from decimal import ROUND_HALF_UP, Decimal
+"""Text formatting used by the snapshot path: Utilities/TableIterationFormater.cs:22-48 and NumFormat.N3
+(Simplex/RevisedPrimalSimplexSolver.cs:451-465).  The formatting is native (csrc/host_io.cu: lpr_fmt_f3 /
+lpr_fmt_n3 / lpr_fmt_table, and lpr_tab_format for a tableau that lives on the device)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
 
 
-def _net_fixed(x, digits):
-    """.NET Framework double.ToString("F<digits>"): the value is first rendered with 15
-    significant digits, then rounded half away from zero; a zero result carries no sign."""
-    if x != x:
-        return "NaN"
-    if x in (float("inf"), float("-inf")):
-        return "Infinity" if x > 0 else "-Infinity"
-    d = Decimal(f"{x:.15g}").quantize(Decimal(1).scaleb(-digits), rounding=ROUND_HALF_UP)
-    if d == 0:
-        d = abs(d)
-    return f"{d:.{digits}f}"
+def _fmt(fn, x):
+    buf = C.create_string_buffer(400)
+    N.check(fn(float(x), buf, 400))
+    return buf.value.decode("ascii")
 
 
 def F3(x):
-    return _net_fixed(x, 3)
+    """$"{x:F3}" of the .NET Framework"""
+    return _fmt(N.lib().lpr_fmt_f3, x)
+
+
+def _labels(rowLabels):
+    if rowLabels is None:
+        return None, 0
+    arr = (C.c_char_p * max(1, len(rowLabels)))(*[str(s).encode("utf-8") for s in rowLabels])
+    return arr, len(rowLabels)
 
 
 class TableIterationFormater:
     @staticmethod
     def Format(tab, numOriginalVars, title, rowLabels=None):
-        rows, cols = len(tab), len(tab[0])
-        out = [f"\n{title}:", "-" * 80]
-        hdr = "Table\t" + "".join(f"x{j + 1}\t" for j in range(numOriginalVars))
-        hdr += "".join(f"t{j - numOriginalVars + 1}\t" for j in range(numOriginalVars, cols - 1)) + "RHS"
-        out.append(hdr)
-        out.append("Z\t" + "".join(F3(tab[0][j]) + "\t" for j in range(cols)))
-        for i in range(1, rows):
-            label = rowLabels[i - 1] if (rowLabels is not None and len(rowLabels) >= i) else f"{i}"
-            out.append(label + "\t" + "".join(F3(tab[i][j]) + "\t" for j in range(cols)))
-        return "\r\n".join(out) + "\r\n"
+        T = np.ascontiguousarray(np.asarray(tab, dtype=np.float64))
+        if T.ndim != 2:
+            raise ValueError("tab must be a 2-D table")
+        arr, n = _labels(rowLabels)
+        text, ln = N.vp(), C.c_int64()
+        N.check(N.lib().lpr_fmt_table(N.pd(T), T.shape[0], T.shape[1], T.shape[1], int(numOriginalVars),
+                                      str(title).encode("utf-8"), arr, n, C.byref(text), C.byref(ln)))
+        return C.string_at(text.value, ln.value).decode("utf-8")
+
+    @staticmethod
+    def FormatDevice(device_tableau, numOriginalVars, title, rowLabels=None):
+        """the same text for a tableau resident in HBM (row blocks streamed through pinned buffers)"""
+        arr, n = _labels(rowLabels)
+        text, ln = N.vp(), C.c_int64()
+        N.check(N.lib().lpr_tab_format(device_tableau._h, int(numOriginalVars), str(title).encode("utf-8"), arr, n,
+                                       C.byref(text), C.byref(ln)))
+        return C.string_at(text.value, ln.value).decode("utf-8")
 
 
 class NumFormat:
@@ -40,12 +53,4 @@ class NumFormat:
 
     @staticmethod
     def N3(x):
-        if abs(x) < NumFormat.EPS:
-            x = 0.0
-        r = float(Decimal(f"{x:.15g}").quantize(Decimal("0.001"), rounding=ROUND_HALF_UP))
-        if abs(r - round(r)) < NumFormat.EPS:
-            return str(int(round(r)))
-        s = _net_fixed(r, 3).rstrip("0").rstrip(".")
-        if s.startswith("0."):
-            s = s  # "0.###" keeps the leading zero
-        return s
+        return _fmt(N.lib().lpr_fmt_n3, x)

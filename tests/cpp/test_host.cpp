@@ -109,6 +109,43 @@ int main() {
     REQUIRE(d.Solve(o, rows, 10000, true));
     REQUIRE(!Simplex::DualSimplexSolver::AnyNegativeRhs(rows));
   }
+  // model input and snapshot text: parse the fixture, build the tableau from the native model,
+  // solve, and format the final tableau on the device path and on the host path
+  {
+    IO::InputFileParser parser;
+    parser.ReadInputText("max +2 +3 +3 +5 +2 +4\n+11 +8 +6 +14 +10 +10 <= 40\nbin bin bin bin bin bin");
+    REQUIRE(parser.ProblemType == "max" && parser.ObjectiveCoefficients.size() == 6 && parser.Constraints.size() == 1);
+    REQUIRE(parser.SignRestrictions.size() == 6 && parser.SignRestrictions[5] == "bin");
+    parser.AddCliBoundRows();
+    REQUIRE(parser.Constraints.size() == 7 && parser.Constraints[2].Coefficients.size() == 9);
+    lpr_tab* t = parser.CreateDeviceTableau();
+    int status = 0;
+    int64_t np = 0;
+    Check(lpr_tab_solve(t, LPR_RULE_PRIMAL, -1, 0, &status, &np, nullptr, 0));
+    REQUIRE(status == LPR_OPTIMAL && np == 6);
+    double z = 0;
+    Check(lpr_tab_objective(t, &z));
+    REQUIRE(z == primal.FinalZ);
+    const std::string dev = Utilities::TableIterationFormater::Format(t, 6, "Final Tableau (Optimal)");
+    const std::string host = Utilities::TableIterationFormater::Format(primal.FinalTableau, primal.Rows, primal.Cols, 6,
+                                                                       "Final Tableau (Optimal)");
+    REQUIRE(dev == host);
+    REQUIRE(dev.find("\nFinal Tableau (Optimal):\r\n") == 0 && dev.find("\tRHS\r\nZ\t") != std::string::npos);
+    REQUIRE(dev.find("15.400\t\r\n") != std::string::npos);
+    REQUIRE(Utilities::NumFormat::N3(primal.FinalZ) == "15.4" && Utilities::NumFormat::N3(-0.0) == "0");
+    lpr_tab_destroy(t);
+    IO::InputFileParser missing;
+    missing.ReadInputFile("/nonexistent/model.txt");
+    REQUIRE(missing.Message.find("can't find your file") != std::string::npos && missing.ObjectiveCoefficients.empty());
+    bool threw = false;
+    try {
+      IO::InputFileParser bad;
+      bad.ReadInputText("max 1 2\n1 <= 2\n+ +");
+    } catch (const ArgumentException& ex) {
+      threw = std::string(ex.what()).find("IndexOutOfRangeException") != std::string::npos;
+    }
+    REQUIRE(threw);
+  }
   std::printf("cpp host mirror: all checks passed\n");
   return 0;
 }

@@ -1,0 +1,68 @@
+"""Independent pure-Python restatement of the .NET Framework text rules the native formatter implements
+(csrc/host_io.cu), used only as a checker by tests/test_host_io.py.
+
+  * double.ToString("F3"): the value is rendered with 15 significant digits first (the Framework's
+    DoubleToNumber precision), then rounded half away from zero on that decimal string; a zero result has no sign.
+  * NumFormat.N3 (Simplex/RevisedPrimalSimplexSolver.cs:455-465): |x| < 1e-12 -> 0; Math.Round(x, 3,
+    MidpointRounding.AwayFromZero) = scale by 1e3, split with modf, bump when |fraction| >= 0.5, divide by 1e3;
+    integral results print through double.ToString(), the rest through "0.###".
+  * TableIterationFormater.Format (Utilities/TableIterationFormater.cs:22-48).
+"""
+import math
+from decimal import ROUND_HALF_UP, Context, Decimal
+
+_CTX = Context(prec=700)  # 1.8e308 with three decimals needs 312 digits
+
+
+def net_fixed(x, digits):
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    d = Decimal(f"{x:.15g}").quantize(Decimal(1).scaleb(-digits), rounding=ROUND_HALF_UP, context=_CTX)
+    if d == 0:
+        d = abs(d)
+    return f"{d:.{digits}f}"
+
+
+def F3(x):
+    return net_fixed(x, 3)
+
+
+def round3_away(x):
+    if abs(x) < 1e16:
+        fr, ip = math.modf(x * 1e3)
+        if abs(fr) >= 0.5:
+            ip += 1.0 if fr > 0 else -1.0
+        x = ip / 1e3
+    return x
+
+
+def N3(x):
+    if abs(x) < 1e-12:
+        x = 0.0
+    r = round3_away(x)
+    ri = float(round(r)) if abs(r) < 2 ** 52 else r  # Math.Round(r): half to even
+    if abs(r - ri) < 1e-12:
+        if ri == 0:
+            return "0"
+        s = f"{ri:.15g}"
+        if "e" in s:  # double.ToString() switches to d.dddE+XX at 1e15
+            mant, ex = s.split("e")
+            return f"{mant}E{'+' if int(ex) >= 0 else '-'}{abs(int(ex)):02d}"
+        return s
+    s = net_fixed(r, 3).rstrip("0").rstrip(".")
+    return s
+
+
+def format_table(tab, num_original_vars, title, row_labels=None):
+    rows, cols = len(tab), len(tab[0])
+    out = [f"\n{title}:", "-" * 80]
+    hdr = "Table\t" + "".join(f"x{j + 1}\t" for j in range(num_original_vars))
+    hdr += "".join(f"t{j - num_original_vars + 1}\t" for j in range(num_original_vars, cols - 1)) + "RHS"
+    out.append(hdr)
+    out.append("Z\t" + "".join(F3(tab[0][j]) + "\t" for j in range(cols)))
+    for i in range(1, rows):
+        label = row_labels[i - 1] if (row_labels is not None and len(row_labels) >= i) else f"{i}"
+        out.append(label + "\t" + "".join(F3(tab[i][j]) + "\t" for j in range(cols)))
+    return "\r\n".join(out) + "\r\n"

@@ -464,3 +464,56 @@ def test_build_paths_full_rows_and_cache_reuse():
     for _ in range(3):
         with L.DeviceTableau.from_host(big) as t:
             assert_bit_equal(t.read(), big)
+
+
+# ---- SURVEY 8f rows 2-3 on the device: snapshot text and model input ---------------------------------------------
+def test_device_snapshot_equals_host_formatter():
+    """lpr_tab_format (row blocks streamed D2H + native formatting) == lpr_fmt_table on the downloaded tableau ==
+    the independent restatement, for a single-block and a multi-block (> 8 MB) tableau"""
+    import net_reference as R
+    from lpr_381_group_v22_b200.utilities import TableIterationFormater as F
+    rng = np.random.default_rng(21)
+    for rows, cols, nv in ((7, 12, 4), (1300, 1111, 600)):
+        T = rng.normal(size=(rows, cols)) * 10.0 ** rng.integers(-4, 5, (rows, cols))
+        labels = [f"x{i}" for i in range(1, 6)]
+        with L.DeviceTableau.from_host(T) as t:
+            dev = F.FormatDevice(t, nv, "Iteration 2 - After pivot", labels)
+        assert dev == F.Format(T, nv, "Iteration 2 - After pivot", labels)
+        if rows < 100:
+            assert dev == R.format_table(T.tolist(), nv, "Iteration 2 - After pivot", labels)
+
+
+def test_traced_solve_snapshots_are_the_reference_text():
+    """IterationSnapshots of a traced solve: initial tableau, one per pivot, final block -- each the formatter's
+    text of the oracle's tableau at that point"""
+    import net_reference as R
+    obj = [3.0, 2.0, 4.0]
+    rows = [([1.0, 1.0, 2.0], "<=", 4.0), ([2.0, 0.0, 3.0], "<=", 5.0), ([2.0, 1.0, 3.0], "<=", 7.0)]
+    s = L.PrimalSimplexSolver(obj, [L.Constraint(*r) for r in rows], trace=True)
+    s.Solve()
+    T0, b0 = O.primal_build(obj, rows)
+    assert s.IterationSnapshots[0] == R.format_table(T0.tolist(), 3, "Initial Tableau")
+    for k in range(1, len(s.PivotLog) + 1):
+        ref = O.primal_solve(T0.copy(), b0.copy(), max_pivots=k)
+        assert s.IterationSnapshots[k] == R.format_table(ref["T"].tolist(), 3, f"Iteration {k} - After pivot")
+
+
+def test_model_to_device_equals_list_constructor(tmp_path):
+    """lpr_tab_create_from_model (parsed text, CLI rows, binary round trip) builds the tableau the List<Constraint>
+    constructor builds"""
+    from lpr_381_group_v22_b200.io import Model
+    text = "max +2 +3 +3 +5 +2 +4\n+11 +8 +6 +14 +10 +10 <= 40\n1 0 2 0 1 0 >= 3\nbin bin bin bin bin bin"
+    m = Model.parse_text(text).add_cli_bound_rows()
+    cons = [L.Constraint([11, 8, 6, 14, 10, 10], "<=", 40), L.Constraint([1, 0, 2, 0, 1, 0], ">=", 3)]
+    L.add_cli_bound_rows(6, cons)
+    with L.DeviceTableau.from_model([2, 3, 3, 5, 2, 4], cons) as a, m.to_device() as b:
+        assert np.array_equal(a.read().view(np.uint64), b.read().view(np.uint64)) and a.basis.tolist() == b.basis.tolist()
+    path = str(tmp_path / "m.lprm")
+    m.save_binary(path)
+    with Model.load_binary(path).to_device(is_maximization=False) as c, \
+            L.DeviceTableau.from_model([2, 3, 3, 5, 2, 4], cons, False) as d:
+        assert np.array_equal(c.read().view(np.uint64), d.read().view(np.uint64))
+    A, bb, cc = O.gen_dense_lp(5, 40, 70)
+    with Model.from_dense(cc, A, bb).to_device() as e, \
+            L.DeviceTableau.from_model(list(cc), [L.Constraint(A[i], "<=", bb[i]) for i in range(40)]) as f:
+        assert np.array_equal(e.read().view(np.uint64), f.read().view(np.uint64))
