@@ -1,6 +1,6 @@
-// InputOutputShim.cs -- bodies of IO/InputFileParser.ReadInputFile (:19-68) and
-// Utilities/TableIterationFormater.Format (:22-48) over liblprb200 (SURVEY 8f rows 2-3).  Signatures and members
-// are the reference's; source only (no .NET toolchain in the build image) -- the same entry points are driven by
+// InputOutputShim.cs -- replacements for IO/InputFileParser.cs (ReadInputFile :19-68, Constraint :70-82) and
+// Utilities/TableIterationFormater.cs (Format :19-48) over liblprb200 (SURVEY 8f rows 2-3).  Same public members
+// and signatures as the reference's classes; source only (no .NET toolchain in the build image) -- the same entry points are driven by
 // lpr_381_group_v22_b200/io.py, utilities.py and host/lpr_solvers.hpp in the tests.
 using System;
 using System.Collections.Generic;
@@ -10,8 +10,21 @@ using LPR_381_Group_V22.Native;
 
 namespace LPR_381_Group_V22.IO
 {
-    public partial class InputFileParser
+    public class InputFileParser
     {
+        public string ProblemType { get; set; }
+        public List<double> ObjectiveCoefficients { get; set; } = new List<double>();
+        public List<Constraint> Constraints { get; set; } = new List<Constraint>();
+        public List<string> SignRestrictions { get; set; } = new List<string>();
+
+        public class Constraint
+        {
+            public List<double> Coefficients { get; }
+            public string Relation { get; }
+            public double RHS { get; }
+            public Constraint(List<double> coefficients, string relation, double rhs) { Coefficients = coefficients; Relation = relation; RHS = rhs; }
+        }
+
         internal ModelHandle NativeModel; // lpr_tab_create_from_model builds the device tableau straight from it
 
         private static string Str(Func<byte[], int, int> call)
@@ -56,8 +69,10 @@ namespace LPR_381_Group_V22.IO
 
 namespace LPR_381_Group_V22.Utilities
 {
-    public static partial class TableIterationFormater
+    public static class TableIterationFormater
     {
+        public static string Format(double[,] tab, int numOriginalVars, string title) => Format(tab, numOriginalVars, title, null);
+
         public static string Format(double[,] tab, int numOriginalVars, string title, IReadOnlyList<string> rowLabels)
         {
             string[] labels = rowLabels == null ? null : new List<string>(rowLabels).ToArray();
