@@ -417,6 +417,16 @@ def main():
         "bb": bb,
         "knapsack": knap,
     }
+    if bb and "nodes_per_s" in bb:
+        # per node 16*R*C for each of the two child copies (AddConstraint) + 16*R*C per pivot executed in
+        # the node; R, C taken at the shallowest children (root + one row / one column), i.e. a lower bound
+        rc_bytes = 16.0 * (512 + 2) * (1024 + 512 + 2)
+        per_node = rc_bytes * (2.0 + bb["pivots_per_node"])
+        ach = per_node * bb["nodes_per_s"] / 1e9
+        bb["roofline"] = {"bound": "hbm", "bytes_per_node": per_node, "achieved": ach, "peak": peak * world, "unit": "GB/s",
+                          "frac": ach / (peak * world),
+                          "note": "algorithmic bytes (two child copies + pivots/node sweeps) x nodes/s over the measured "
+                                  "copy bandwidth of the GPUs in use; node tableaux of a batch are partly L2 resident"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
