@@ -288,6 +288,37 @@ def test_full_size_window_cfg2():
             assert col[i + 1] == 1.0 and np.count_nonzero(col) == 1
 
 
+def test_full_size_solve_cfg2_plans_agree_and_certify_optimality():
+    """BASELINE cfg2 solved to optimality (14 866 pivots).  The oracle needs ~13 minutes for this, so the full-size
+    check is (1) the per-pivot plan -- the one pinned bit-exactly to the oracle on windows -- and the default
+    overlapped delayed-update plan give the same pivot log and the same final tableau, bit for bit, and (2) the
+    result certifies itself: primal feasible, dual feasible, complementary, z = c.x = y.b (the LP optimality
+    conditions, evaluated from the synthetic A, b, c on the host)."""
+    m, n, seed = 4096, 8192, 383
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    with L.DeviceTableau.dense_lp(seed, m, n) as t:
+        r = t.solve(L.RULE_PRIMAL, log_cap=1 << 15)
+        assert r["status"] == L.OPTIMAL and r["n_pivots"] == 14866
+        T = t.read()
+        z, x, basis = t.objective(), t.extract_solution(n), t.basis.copy()
+    with L.DeviceTableau.dense_lp(seed, m, n) as t:
+        r1 = t.solve(L.RULE_PRIMAL, log_cap=1 << 15, blocked=False)  # one sweep per pivot
+        assert r1["status"] == L.OPTIMAL and r1["log"].tolist() == r["log"].tolist()
+        assert_bit_equal(t.read(), T)
+        assert t.basis.tolist() == basis.tolist()
+    # optimality certificate
+    assert np.all(T[0, :-1] >= 0.0) and np.all(T[1:, -1] >= 0.0)          # reduced costs / basic values
+    y = T[0, n:n + m]                                                     # duals sit under the slack columns
+    assert z == T[0, -1] and abs(z - c @ x) <= 1e-9 * abs(z) and abs(z - y @ b) <= 1e-9 * abs(z)
+    assert np.all(A @ x <= b * (1 + 1e-9)) and np.all(x >= 0.0)
+    assert np.all(A.T @ y >= c * (1 - 1e-9)) and np.all(y >= 0.0)
+    slack = b - A @ x
+    assert np.all(np.abs(slack * y) <= 1e-6 * np.abs(z))                  # complementary slackness
+    for i in range(0, m, 257):                                            # basic columns are unit vectors
+        col = T[:, basis[i]]
+        assert col[i + 1] == 1.0 and np.count_nonzero(col) == 1
+
+
 @pytest.mark.parametrize("seed", range(5))
 def test_sensitivity_resolve_rule(seed):
     """SensitivityAnalyzer.ResolveAll (dual phase then primal re-optimisation, SensitivityAnalyzer.cs:121-201):
