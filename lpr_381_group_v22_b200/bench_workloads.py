@@ -102,7 +102,7 @@ def run_knap_cfg4(n_items, seed, device, dist, max_nodes, chunk):
     left = sum(x[0] for x in comm.allgather_ints([pool.open_count()]))
     pool.close()
     inc = res["incumbent"]
-    rec_bytes = 8 * (3 * ((n_items + 63) // 64) + 2)
+    rec_bytes = 8 * (3 * ((n_items + 63) // 64) + 4)
     return dict(workload=f"cfg4 knapsack n={n_items} weakly correlated, capacity {cap:.0f}", n_gpus=comm.world,
                 nodes=res["nodes_total"], seconds=dt, nodes_per_s=res["nodes_total"] / dt,
                 node_record_bytes=rec_bytes, record_gbs=3.0 * rec_bytes * res["nodes_total"] / dt / 1e9,

@@ -11,13 +11,23 @@
 //   * the answer is the DFS-first optimal candidate.  Nodes carry their DFS path as a bit string so
 //     that (value, path) selects the same incumbent for ANY exploration order / GPU count.
 // Device layout: the open-node pool is an array of fixed-size records in HBM
-//   [ fixmask : W words | fixval : W words | key : W words | depth, pad ]   W = ceil(n/64)
-// (3.8 KB at n = 10^4).  One warp evaluates one node with ballot/shuffle scans over the
-// ranked item arrays (L2 resident); a second kernel writes the two children of surviving nodes.
+//   [ fixmask : W words | fixval : W words | key : W words | depth | (k, side) | cap_k | val_k ]   W = ceil(n/64)
+// (3.8 KB at n = 10^4).  The last three words are the greedy state inherited from the parent, whose
+// critical item was k: cap_k / val_k = capacity left / value collected when the parent's fill stopped at k.  A
+// child differs from its parent in that one item, so its relaxation is a short walk from k instead of two passes
+// over all n items (k_knap_eval, one thread per node):
+//   * x_k = 0: the items before k stay as they were; the fill resumes at k+1 with (cap_k, val_k);
+//   * x_k = 1: k is forced in (cap_k - w_k < 0), so free items are given back from k-1 downwards until the
+//     rest fits; the last one given back is the new critical item.
+// Sums are therefore formed in a different order than a front-to-back scan; they are exact (and the result
+// identical) for integer-valued weights and values below 2^53, which is what the call site passes
+// (Program.cs:444-448) and what the specification above assumes.  A second kernel writes the two children of the
+// surviving nodes.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <numeric>
 #include <vector>
 
@@ -26,101 +36,124 @@
 namespace lpr {
 
 struct KnapEval {
-  double val;  // candidate value or bound
-  int crit;    // critical ranked position, -1 = none
-  int type;    // 0 infeasible, 1 candidate, 2 branch
+  double val;   // candidate value or bound
+  double cap;   // capacity left when the fill stopped (state handed to the children)
+  double base;  // value collected when the fill stopped
+  int crit;     // critical ranked position, -1 = none
+  int type;     // 0 infeasible, 1 candidate, 2 branch
+  int cmp;      // DFS order of the node's key against the incumbent's (-1 before, 0 same, 1 after) when val ties with
+                // the incumbent value the kernel was given; kCmpNone otherwise
+  int pad;
 };
+constexpr int kCmpNone = 3;
 
-__device__ __forceinline__ double warp_sum(double x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
-  return x;
-}
-__device__ __forceinline__ double warp_incl_scan(double x, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x = __dadd_rn(x, y);
-  }
-  return x;
-}
-
-// one warp per node
-__global__ void __launch_bounds__(128) k_knap_eval(const uint64_t* __restrict__ pool, size_t rec_words, int W,
-                                                   long long first, int count, int n, double capacity,
-                                                   const double* __restrict__ w, const double* __restrict__ v,
-                                                   KnapEval* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (node >= count) return;
-  const uint64_t* rec = pool + (size_t)(first + node) * rec_words;
-  const uint32_t* mask32 = reinterpret_cast<const uint32_t*>(rec);
-  const uint32_t* val32 = reinterpret_cast<const uint32_t*>(rec + W);
-  // pass 1: fixed-1 items
-  double cw = 0.0, cv = 0.0;
-  for (int base = 0; base < n; base += 32) {
-    const int p = base + lane;
-    const uint32_t m = mask32[base >> 5], f = val32[base >> 5];
-    if (p < n && ((m & f) >> lane) & 1u) {
-      cw = __dadd_rn(cw, w[p]);
-      cv = __dadd_rn(cv, v[p]);
+// DFS order of two path keys (bit strings): first differing bit decides, a prefix precedes its extensions
+__host__ __device__ inline int knap_key_order(const uint64_t* a, int abits, const uint64_t* b, int bbits) {
+  const int n = abits < bbits ? abits : bbits;
+  for (int w0 = 0; w0 * 64 < n; w0++) {
+    uint64_t x = a[w0] ^ b[w0];
+    const int left = n - w0 * 64;
+    if (left < 64) x &= (1ull << left) - 1ull;
+    if (x) {
+      const uint64_t low = x & (~x + 1ull);  // lowest differing bit = earliest branch
+      return (a[w0] & low) ? 1 : -1;
     }
   }
-  cw = warp_sum(cw);
-  cv = warp_sum(cv);
-  double cap = __dsub_rn(capacity, cw);
+  if (abits == bbits) return 0;
+  return abits < bbits ? -1 : 1;
+}
+
+constexpr int kRecTail = 4;  // depth | (k, side) | cap_k | val_k
+__host__ __device__ inline uint64_t knap_pack_state(int k, int side) {
+  return (uint64_t)(uint32_t)k | ((uint64_t)(uint32_t)side << 32);
+}
+
+// one thread per node: a walk from the parent's critical item (see the header)
+__global__ void __launch_bounds__(128) k_knap_eval(const uint64_t* __restrict__ pool, size_t rec_words, int W, int count,
+                                                   int n, const double* __restrict__ w, const double* __restrict__ v,
+                                                   int has_inc, double inc_val, const uint64_t* __restrict__ inc_key,
+                                                   int inc_bits, KnapEval* __restrict__ out) {
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= count) return;
+  const uint64_t* rec = pool + (size_t)node * rec_words;
+  const uint64_t st = rec[3 * (size_t)W + 1];
+  const int k = (int)(uint32_t)st, side = (int)(st >> 32);
+  double cap = __longlong_as_double((long long)rec[3 * (size_t)W + 2]);
+  double val = __longlong_as_double((long long)rec[3 * (size_t)W + 3]);
+  auto fixed = [&](int p) { return (rec[p >> 6] >> (p & 63)) & 1ull; };
+  int crit = -1;
+  bool infeasible = k < 0 && cap < 0.0;  // negative capacity at the root
+  if (infeasible) {
+  } else if (side == 1 && k >= 0) {
+    cap = __dsub_rn(cap, w[k]);  // < 0: k did not fit in the parent
+    val = __dadd_rn(val, v[k]);
+    int p = k - 1;
+    for (; p >= 0; p--) {
+      if (fixed(p)) continue;
+      cap = __dadd_rn(cap, w[p]);
+      val = __dsub_rn(val, v[p]);
+      if (cap >= 0.0) break;
+    }
+    if (p < 0) infeasible = true;  // the fixed-1 items alone exceed the capacity
+    crit = p;
+  } else {
+    for (int p = k + 1; p < n; p++) {  // k = -1 for the root
+      if (fixed(p)) continue;
+      const double wp = w[p];
+      if (wp <= cap) {
+        cap = __dsub_rn(cap, wp);
+        val = __dadd_rn(val, v[p]);
+      } else {
+        crit = p;
+        break;
+      }
+    }
+  }
   KnapEval ev;
-  if (cap < 0.0) {
+  ev.cap = cap;
+  ev.base = val;
+  ev.crit = crit;
+  if (infeasible) {
     ev.val = 0.0;
     ev.crit = -1;
     ev.type = 0;
-    if (lane == 0) out[node] = ev;
-    return;
-  }
-  // pass 2: greedy fill of the free items in rank order until the first that does not fit
-  double val = cv;
-  int crit = -1;
-  for (int base = 0; base < n && crit < 0; base += 32) {
-    const int p = base + lane;
-    const uint32_t m = mask32[base >> 5];
-    const bool free = p < n && !((m >> lane) & 1u);
-    const double wi = free ? w[p] : 0.0, vi = free ? v[p] : 0.0;
-    const double incl = warp_incl_scan(wi, lane);
-    const bool fits = !free || (incl <= cap);
-    const unsigned nofit = __ballot_sync(0xffffffffu, !fits);
-    if (nofit) {
-      const int l = __ffs(nofit) - 1;
-      crit = base + l;
-      // take the free items before the critical one
-      const double wpre = __shfl_sync(0xffffffffu, __dsub_rn(incl, wi), l);
-      double vpre = warp_sum(lane < l ? vi : 0.0);
-      cap = __dsub_rn(cap, wpre);
-      val = __dadd_rn(val, vpre);
-    } else {
-      cap = __dsub_rn(cap, __shfl_sync(0xffffffffu, incl, 31));
-      val = __dadd_rn(val, warp_sum(vi));
-    }
-  }
-  if (crit < 0 || cap == 0.0) {
+  } else if (crit < 0 || cap == 0.0) {
     ev.val = val;
-    ev.crit = crit;
     ev.type = 1;
   } else {
     ev.val = __dadd_rn(val, __dmul_rn(v[crit], __ddiv_rn(cap, w[crit])));
-    ev.crit = crit;
     ev.type = 2;
   }
-  if (lane == 0) out[node] = ev;
+  // ties with the incumbent are decided by the DFS keys: compare here so that the host never needs the record
+  ev.cmp = kCmpNone;
+  ev.pad = 0;
+  if (has_inc && ev.type != 0 && ev.val == inc_val)
+    ev.cmp = knap_key_order(rec + 2 * (size_t)W, (int)rec[3 * (size_t)W], inc_key, inc_bits);
+  out[node] = ev;
 }
 
-// children of surviving nodes: job = (parent record index, critical position); two records per job
-__global__ void k_knap_expand(uint64_t* pool, size_t rec_words, int W, const long long* parent, const int* crit,
+// the incumbent changed while the host was reading this batch: redo the tie test against the new one
+__global__ void k_knap_retie(const uint64_t* __restrict__ pool, size_t rec_words, int W, int count, double inc_val,
+                             const uint64_t* __restrict__ inc_key, int inc_bits, KnapEval* __restrict__ evals) {
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= count) return;
+  const uint64_t* rec = pool + (size_t)node * rec_words;
+  int cmp = kCmpNone;
+  if (evals[node].type != 0 && evals[node].val == inc_val)
+    cmp = knap_key_order(rec + 2 * (size_t)W, (int)rec[3 * (size_t)W], inc_key, inc_bits);
+  evals[node].cmp = cmp;
+}
+
+// children of surviving nodes: job = index of the parent in the staged batch; two records per job, each carrying
+// the parent's fill state at its critical item
+__global__ void k_knap_expand(uint64_t* pool, size_t rec_words, int W, const long long* parent, const KnapEval* evals,
                               int njobs, long long dst_first, const uint64_t* __restrict__ src_pool) {
   const int job = blockIdx.x;
   if (job >= njobs) return;
   const uint64_t* src = src_pool + (size_t)parent[job] * rec_words;
+  const KnapEval ev = evals[parent[job]];
   const int depth = (int)src[3 * (size_t)W];
-  const int k = crit[job];
+  const int k = ev.crit;
   // stack order: the x_k = 1 child below the x_k = 0 child (the zero child is DFS-first)
   uint64_t* one = pool + (size_t)(dst_first + 2 * (long long)job) * rec_words;
   uint64_t* zero = one + rec_words;
@@ -138,6 +171,13 @@ __global__ void k_knap_expand(uint64_t* pool, size_t rec_words, int W, const lon
       }
     } else if (t == 3 * W) {
       x0 = x1 = (uint64_t)(depth + 1);
+    } else if (t == 3 * W + 1) {
+      x0 = knap_pack_state(k, 0);
+      x1 = knap_pack_state(k, 1);
+    } else if (t == 3 * W + 2) {
+      x0 = x1 = (uint64_t)__double_as_longlong(ev.cap);
+    } else {
+      x0 = x1 = (uint64_t)__double_as_longlong(ev.base);
     }
     zero[t] = x0;
     one[t] = x1;
@@ -207,7 +247,6 @@ struct lpr_knap {
   long long pool_cap = 0, open = 0;
   KnapEval *d_eval = nullptr, *h_eval = nullptr;
   long long *d_parent = nullptr, *h_parent = nullptr;
-  int *d_crit = nullptr, *h_crit = nullptr;
   uint64_t* stage = nullptr;  // batch staging (the batch is moved off the stack before children are pushed)
   int batch = 0;
   // incumbent
@@ -216,17 +255,23 @@ struct lpr_knap {
   std::vector<uint64_t> inc_key;
   int inc_key_bits = 0;
   std::vector<uint8_t> inc_chosen;
+  uint64_t* d_inc_key = nullptr;  // device copy of inc_key for the tie test in k_knap_eval
+  bool inc_key_dirty = false;
+  int64_t inc_version = 0;        // bumped whenever the incumbent changes
   int64_t processed = 0;
+  // LPR_KNAP_PROFILE=1: host-clock split of lpr_knap_run, printed by lpr_knap_destroy
+  double t_eval = 0, t_host = 0, t_expand = 0;
+  int64_t n_batches = 0, n_fetch = 0, n_incumbents = 0;
 };
 
+static inline double knap_now() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
 static int knap_key_cmp(const uint64_t* a, int abits, const uint64_t* b, int bbits) {
-  const int n = std::min(abits, bbits);
-  for (int i = 0; i < n; i++) {
-    const int ba = (a[i >> 6] >> (i & 63)) & 1, bb = (b[i >> 6] >> (i & 63)) & 1;
-    if (ba != bb) return ba < bb ? -1 : 1;
-  }
-  if (abits == bbits) return 0;
-  return abits < bbits ? -1 : 1;
+  return knap_key_order(a, abits, b, bbits);
 }
 
 extern "C" {
@@ -234,12 +279,15 @@ extern "C" {
 int lpr_knap_destroy(lpr_knap* h) {
   if (!h) return LPR_OK;
   cudaSetDevice(h->device);
+  if (getenv("LPR_KNAP_PROFILE"))
+    fprintf(stderr, "[lpr_knap] nodes=%lld batches=%lld fetches=%lld incumbents=%lld | stage+eval %.4fs host %.4fs expand %.4fs\n",
+            (long long)h->processed, (long long)h->n_batches, (long long)h->n_fetch, (long long)h->n_incumbents, h->t_eval,
+            h->t_host, h->t_expand);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_w); cudaFree(h->d_v); cudaFree(h->d_rank); cudaFree(h->pool); cudaFree(h->d_eval);
-  cudaFree(h->d_parent); cudaFree(h->d_crit); cudaFree(h->stage);
+  cudaFree(h->d_parent); cudaFree(h->stage); cudaFree(h->d_inc_key);
   if (h->h_eval) cudaFreeHost(h->h_eval);
   if (h->h_parent) cudaFreeHost(h->h_parent);
-  if (h->h_crit) cudaFreeHost(h->h_crit);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return LPR_OK;
@@ -260,7 +308,7 @@ int lpr_knap_create(int device, double capacity, int n, const double* weights, c
   h->sms = sm_count(device);
   h->n = n;
   h->W = (n + 63) / 64;
-  h->rec_words = 3 * (size_t)h->W + 2;
+  h->rec_words = 3 * (size_t)h->W + kRecTail;
   h->capacity = capacity;
   // rank by value/weight descending, ties by lower original id (host side setup, O(n log n))
   h->rank.resize(n);
@@ -294,15 +342,19 @@ int lpr_knap_create(int device, double capacity, int n, const double* weights, c
   TRY(cudaMalloc(&h->d_eval, sizeof(KnapEval) * h->batch));
   TRY(cudaMallocHost(&h->h_eval, sizeof(KnapEval) * h->batch));
   TRY(cudaMalloc(&h->d_parent, sizeof(long long) * h->batch));
+  TRY(cudaMalloc(&h->d_inc_key, sizeof(uint64_t) * h->W));
   TRY(cudaMallocHost(&h->h_parent, sizeof(long long) * h->batch));
-  TRY(cudaMalloc(&h->d_crit, sizeof(int) * h->batch));
-  TRY(cudaMallocHost(&h->h_crit, sizeof(int) * h->batch));
   TRY(cudaMemcpyAsync(h->d_w, rw.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
   TRY(cudaMemcpyAsync(h->d_v, rv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
   TRY(cudaMemcpyAsync(h->d_rank, h->rank.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
-  // root node: nothing fixed, empty key
-  TRY(cudaMemsetAsync(h->pool, 0, sizeof(uint64_t) * h->rec_words, h->stream));
-  TRY(cudaStreamSynchronize(h->stream));
+  // root node: nothing fixed, empty key, fill state = (no parent item, whole capacity, no value)
+  {
+    std::vector<uint64_t> root(h->rec_words, 0);
+    root[3 * (size_t)h->W + 1] = knap_pack_state(-1, 0);
+    memcpy(&root[3 * (size_t)h->W + 2], &capacity, sizeof(double));
+    TRY(cudaMemcpyAsync(h->pool, root.data(), sizeof(uint64_t) * h->rec_words, cudaMemcpyHostToDevice, h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+  }
 #undef TRY
   h->open = 1;
   h->inc_chosen.assign(n, 0);
@@ -331,18 +383,29 @@ int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status
     }
     long long nb = std::min<long long>(h->batch, h->open);
     if (max_nodes >= 0) nb = std::min<long long>(nb, max_nodes - done);
+    const double tp0 = knap_now();
+    h->n_batches++;
     const long long first = h->open - nb;  // deepest nodes sit at the top of the stack
     // move the batch off the stack so that children can be written over it
     LPR_CUDA(cudaMemcpyAsync(h->stage, h->pool + (size_t)first * h->rec_words, rb * nb, cudaMemcpyDeviceToDevice, h->stream));
-    k_knap_eval<<<(int)((nb * 32 + 127) / 128), 128, 0, h->stream>>>(h->stage, h->rec_words, h->W, 0, (int)nb, h->n,
-                                                                      h->capacity, h->d_w, h->d_v, h->d_eval);
+    if (h->has_inc && h->inc_key_dirty) {
+      LPR_CUDA(cudaMemcpyAsync(h->d_inc_key, h->inc_key.data(), sizeof(uint64_t) * h->W, cudaMemcpyHostToDevice, h->stream));
+      h->inc_key_dirty = false;
+    }
+    const int64_t version0 = h->inc_version;
+    k_knap_eval<<<(int)((nb + 127) / 128), 128, 0, h->stream>>>(h->stage, h->rec_words, h->W, (int)nb, h->n, h->d_w,
+                                                                 h->d_v, h->has_inc ? 1 : 0, h->inc_val, h->d_inc_key,
+                                                                 h->inc_key_bits, h->d_eval);
     LPR_LAUNCH_CHECK();
     LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(KnapEval) * nb, cudaMemcpyDeviceToHost, h->stream));
     LPR_CUDA(cudaStreamSynchronize(h->stream));
     h->open = first;
     done += nb;
     h->processed += nb;
+    const double tp1 = knap_now();
+    h->t_eval += tp1 - tp0;
     auto fetch = [&](long long idx) -> int {
+      h->n_fetch++;
       LPR_CUDA(cudaMemcpy(rec.data(), h->stage + (size_t)idx * h->rec_words, rb, cudaMemcpyDeviceToHost));
       return LPR_OK;
     };
@@ -353,11 +416,16 @@ int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status
       bool better = !h->has_inc || ev.val > h->inc_val;
       bool tie = h->has_inc && ev.val == h->inc_val;
       if (!better && !tie) continue;
+      // the kernel already ordered tied keys against the incumbent it was launched with
+      if (tie && h->inc_version == version0 && ev.cmp != kCmpNone && ev.cmp >= 0) continue;
       if ((rc = fetch(i))) return rc;
       const int kbits = (int)rec[3 * (size_t)h->W];
       const uint64_t* key = rec.data() + 2 * (size_t)h->W;
       if (tie && knap_key_cmp(key, kbits, h->inc_key.data(), h->inc_key_bits) >= 0) continue;
       h->has_inc = true;
+      h->inc_version++;
+      h->inc_key_dirty = true;
+      h->n_incumbents++;
       h->inc_val = ev.val;
       h->inc_key.assign(key, key + h->W);
       h->inc_key_bits = kbits;
@@ -372,6 +440,15 @@ int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status
       if (e != cudaSuccess) return fail(LPR_E_CUDA, "selection readback failed: %s", cudaGetErrorString(e));
     }
     // 2) surviving branch nodes -> children
+    if (h->inc_version != version0) {  // order the batch against the incumbent it has just produced
+      LPR_CUDA(cudaMemcpyAsync(h->d_inc_key, h->inc_key.data(), sizeof(uint64_t) * h->W, cudaMemcpyHostToDevice, h->stream));
+      h->inc_key_dirty = false;
+      k_knap_retie<<<(int)((nb + 127) / 128), 128, 0, h->stream>>>(h->stage, h->rec_words, h->W, (int)nb, h->inc_val,
+                                                                    h->d_inc_key, h->inc_key_bits, h->d_eval);
+      LPR_LAUNCH_CHECK();
+      LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(KnapEval) * nb, cudaMemcpyDeviceToHost, h->stream));
+      LPR_CUDA(cudaStreamSynchronize(h->stream));
+    }
     int nj = 0;
     for (long long i = 0; i < nb; i++) {
       const KnapEval& ev = h->h_eval[i];
@@ -379,26 +456,31 @@ int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status
       if (h->has_inc) {
         if (ev.val < h->inc_val) continue;
         if (ev.val == h->inc_val) {  // keep only if the node precedes the incumbent in DFS order
-          if ((rc = fetch(i))) return rc;
-          const int kbits = (int)rec[3 * (size_t)h->W];
-          if (knap_key_cmp(rec.data() + 2 * (size_t)h->W, kbits, h->inc_key.data(), h->inc_key_bits) > 0) continue;
+          if (ev.cmp != kCmpNone) {
+            if (ev.cmp > 0) continue;
+          } else {  // not reached (the kernels order every tie); kept as the literal rule
+            if ((rc = fetch(i))) return rc;
+            const int kbits = (int)rec[3 * (size_t)h->W];
+            if (knap_key_cmp(rec.data() + 2 * (size_t)h->W, kbits, h->inc_key.data(), h->inc_key_bits) > 0) continue;
+          }
         }
       }
       h->h_parent[nj] = i;
-      h->h_crit[nj] = ev.crit;
       nj++;
     }
+    const double tp2 = knap_now();
+    h->t_host += tp2 - tp1;
     if (nj > 0) {
       if (h->open + 2LL * nj > h->pool_cap)
         return fail(LPR_E_CAPACITY, "knapsack node pool full (%lld records); raise LPR_KNAP_POOL_MB", h->pool_cap);
       // keep DFS order inside the batch: later batch entries (deeper / DFS-earlier) stay on top
       LPR_CUDA(cudaMemcpyAsync(h->d_parent, h->h_parent, sizeof(long long) * nj, cudaMemcpyHostToDevice, h->stream));
-      LPR_CUDA(cudaMemcpyAsync(h->d_crit, h->h_crit, sizeof(int) * nj, cudaMemcpyHostToDevice, h->stream));
-      k_knap_expand<<<nj, 128, 0, h->stream>>>(h->pool, h->rec_words, h->W, h->d_parent, h->d_crit, nj, h->open, h->stage);
+      k_knap_expand<<<nj, 128, 0, h->stream>>>(h->pool, h->rec_words, h->W, h->d_parent, h->d_eval, nj, h->open, h->stage);
       LPR_LAUNCH_CHECK();
       LPR_CUDA(cudaStreamSynchronize(h->stream));
       h->open += 2LL * nj;
     }
+    h->t_expand += knap_now() - tp2;
   }
   if (processed) *processed = done;
   if (status) *status = st;
@@ -421,6 +503,8 @@ int lpr_knap_set_incumbent(lpr_knap* h, double best, const uint8_t* chosen, cons
   if (!h->has_inc || best > h->inc_val ||
       (best == h->inc_val && knap_key_cmp(k.data(), key_bits, h->inc_key.data(), h->inc_key_bits) < 0)) {
     h->has_inc = true;
+    h->inc_version++;
+    h->inc_key_dirty = true;
     h->inc_val = best;
     h->inc_key = k;
     h->inc_key_bits = key_bits;

@@ -125,7 +125,7 @@ class KnapPool:
         h = N.vp()
         N.check(N.lib().lpr_knap_create(device, float(capacity), self.n, N.pd(self.w), N.pd(self.v), C.byref(h)))
         self._h = h
-        self.rec_bytes = 8 * (3 * ((self.n + 63) // 64) + 2)
+        self.rec_bytes = 8 * (3 * ((self.n + 63) // 64) + 4)
         if not with_root:
             self.export_nodes(1)
 
