@@ -477,11 +477,13 @@ int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status
       LPR_CUDA(cudaMemcpyAsync(h->d_parent, h->h_parent, sizeof(long long) * nj, cudaMemcpyHostToDevice, h->stream));
       k_knap_expand<<<nj, 128, 0, h->stream>>>(h->pool, h->rec_words, h->W, h->d_parent, h->d_eval, nj, h->open, h->stage);
       LPR_LAUNCH_CHECK();
-      LPR_CUDA(cudaStreamSynchronize(h->stream));
+      // no synchronisation here: the next batch's stage copy is ordered behind this launch on the same stream, and
+      // h_parent is not rewritten before that batch's evaluation has been waited for
       h->open += 2LL * nj;
     }
     h->t_expand += knap_now() - tp2;
   }
+  LPR_CUDA(cudaStreamSynchronize(h->stream));  // export / import use blocking copies outside this stream
   if (processed) *processed = done;
   if (status) *status = st;
   return LPR_OK;
