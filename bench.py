@@ -342,6 +342,15 @@ def main():
             bb = bb or {"error": repr(ex)}
             knap = knap or {"error": repr(ex)}
 
+    # -------- revised simplex (BASELINE configs[2]): replicas only, reported from rank 0 ----------------------------
+    rev = None
+    if rank == 0 and not os.environ.get("LPR_BENCH_SKIP_REV"):
+        from lpr_381_group_v22_b200.bench_workloads import run_rev_cfg3
+        try:
+            rev = run_rev_cfg3(8192, 16384, 384, dev)
+        except Exception as ex:
+            rev = {"error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -416,7 +425,13 @@ def main():
         "cpu_baseline": cpu,
         "bb": bb,
         "knapsack": knap,
+        "revised": rev,
     }
+    if rev and "dense_rows" in rev:
+        rev["roofline"] = {"bound": "hbm", "achieved": rev["dense_rows"]["gbs"], "peak": peak, "unit": "GB/s",
+                           "frac": rev["dense_rows"]["gbs"] / peak,
+                           "note": "24 m^2 + 8 m n bytes per iteration (A once, B^-1 read once for u and x_B, read+written "
+                                   "once by the update) with the zero-multiplier row skip disabled"}
     if bb and "nodes_per_s" in bb:
         # per node 16*R*C for each of the two child copies (AddConstraint) + 16*R*C per pivot executed in
         # the node; R, C taken at the shallowest children (root + one row / one column), i.e. a lower bound

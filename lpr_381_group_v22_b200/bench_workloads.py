@@ -110,3 +110,42 @@ def run_knap_cfg4(n_items, seed, device, dist, max_nodes, chunk):
                 weight_used=(float(np.dot(inc[2], w)) if inc else None), open_left=left, steals=res["steals"],
                 nodes_moved=res["nodes_moved"], rounds=res["rounds"], finished=(left == 0),
                 phase_seconds_rank0=res["seconds_rank0"], run_seconds_per_rank=res["run_seconds_per_rank"])
+
+
+def run_rev_cfg3(m, n, seed, device, iters=256):
+    """BASELINE configs[2]: revised primal simplex on a synthetic dense LP generated in HBM, `iters` iterations from
+    the slack basis (device-timed), once as shipped and once with the zero-multiplier row skip disabled (every
+    iteration then moves the full 24 m^2 + 8 m n bytes), plus one on-device refactorisation of B^-1."""
+    import os
+    lib = N.lib()
+    byts = 24.0 * m * m + 8.0 * m * n
+    out = dict(workload=f"cfg3 dense LP m={m} n={n} revised primal simplex, B^-1 {m}x{m} on device",
+               bytes_per_iteration=byts, iterations=iters)
+    for tag, dense in (("as_shipped", False), ("dense_rows", True)):
+        if dense:
+            os.environ["LPR_REV_DENSE"] = "1"
+        try:
+            h = N.vp()
+            N.check(lib.lpr_rev_create_dense_lp(device, seed, m, n, C.byref(h)))
+            st, nit, ms = C.c_int(), C.c_int64(), C.c_float()
+            N.check(lib.lpr_rev_solve(h, iters, 0, C.byref(st), C.byref(nit), None, 0))
+            N.check(lib.lpr_rev_last_solve_ms(h, C.byref(ms)))
+            out[tag] = dict(us_per_iteration=ms.value * 1e3 / max(1, nit.value), iterations_per_s=nit.value / ms.value * 1e3,
+                            gbs=byts * nit.value / ms.value / 1e6, status=STATUS(st.value))
+            if dense:
+                rms, res, fl = C.c_float(), C.c_double(), C.c_double()
+                N.check(lib.lpr_rev_refactor(h))
+                N.check(lib.lpr_rev_last_refactor_ms(h, C.byref(rms)))
+                N.check(lib.lpr_rev_last_refactor_info(h, C.byref(res), C.byref(fl)))
+                out["refactorisation"] = dict(ms=rms.value, fp64_tflops=fl.value / rms.value / 1e9,
+                                              residual_before=res.value,
+                                              what="Newton-Schulz refresh of B^-1, two m^3 FP64 DMMA GEMMs (mma.sync m8n8k4)")
+            lib.lpr_rev_destroy(h)
+        finally:
+            if dense:
+                os.environ.pop("LPR_REV_DENSE", None)
+    return out
+
+
+def STATUS(code):
+    return N.STATUS_NAMES[code] if 0 <= code < len(N.STATUS_NAMES) else str(code)

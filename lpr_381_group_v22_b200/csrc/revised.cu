@@ -591,8 +591,8 @@ struct lpr_rev {
     v.xB = xB; v.y = y; v.rc = rc; v.u = u; v.ekey = ekey; v.ab = ab; v.ecoef = ecoef; v.brow = brow; v.ppart = ppart;
     v.ypart = ypart; v.PS = PS; v.YS = YS; v.basis = basis; v.isbasic = isbasic; v.st = st; v.log = log;
     v.log_cap = log_cap;
-    static const int dense = getenv("LPR_REV_DENSE") ? atoi(getenv("LPR_REV_DENSE")) : 0;
-    v.dense = dense;
+    const char* de = getenv("LPR_REV_DENSE");  // read per call: bench.py measures both settings in one process
+    v.dense = de ? atoi(de) : 0;
     return v;
   }
 };
