@@ -2,9 +2,9 @@
 //
 // A node of the tree IS its final (4-d.p. rounded) tableau, exactly as in the reference, which warm
 // starts every child from the parent's final tableau (:1105-1108).  Per batch of open nodes:
-//   k_bb_eval        GetObjective / ExtractSolution / CheckIntegerBasicVar        (:805-857,:892-921)
-//   k_bb_addc_*      AddConstraint: round, basic-column detection, bound row,     (:642-803)
-//                    elimination with 4-d.p. rounding after every step
+//   k_bb_eval_x/pick GetObjective / ExtractSolution / CheckIntegerBasicVar        (:805-857,:892-921)
+//   k_bb_addc_build  AddConstraint: round, basic-column detection, bound row      (:642-747)
+//   k_bb_addc_elim   ... ordering and elimination with 4-d.p. rounding per step   (:664-685,:752-803)
 //   k_bb_select +    DoDualSimplex with tableauOverride: dual phase, primal phase, (:115-279,:289-468)
 //   k_bb_sweep       out-of-place Gauss-Jordan pivots, -0.0 -> 0.0, "drop last tableau" quirk
 //   k_bb_round       RoundAllTableaux on the children                               (:1124,:1187)

@@ -191,6 +191,46 @@ def test_bb_pool_batched_equals_sequential(seed, m, n):
     assert total >= 1
 
 
+@pytest.mark.parametrize("seed,m,n,world", [(21, 6, 9, 2), (23, 10, 14, 3)])
+def test_bb_pool_replicated_root_partition_and_time_slices(seed, m, n, world):
+    """The multi-GPU start-up without a transfer, on one device: `world` pools expand the same root identically
+    (lpr_bb_run), each keeps every world-th open node (lpr_bb_keep_stride), then runs in time slices
+    (lpr_bb_run_timed).  The best incumbent over the pools (value, then DFS key) is the sequential oracle's."""
+    from lpr_381_group_v22_b200.distributed import BBPool, better
+    Tf = ip_final(seed, m, n)
+    ref = O.bb_solve(Tf, n, prune=True, max_nodes=-1)
+    pools = [BBPool(Tf, n, prune=True) for _ in range(world)]
+    try:
+        for p in pools:
+            guard = 0
+            while 0 < p.open_count() < 3 * world and guard < 32:
+                p.run(2)
+                guard += 1
+        counts = [p.open_count() for p in pools]
+        assert len(set(counts)) == 1  # identical expansion
+        for r, p in enumerate(pools):
+            p.keep_stride(r, world)
+        assert sum(p.open_count() for p in pools) == counts[0]
+        best = None
+        for p in pools:
+            slices = 0
+            while p.open_count() > 0:
+                done = p.run(1 << 30, max_seconds=1e-4)  # a slice ends after the batch that crosses it
+                assert done > 0
+                slices += 1
+                assert slices < 10000
+            inc = p.get_incumbent()
+            if better(inc, best):
+                best = inc
+        assert (best is not None) == ref["has_solution"]
+        if best is not None:
+            assert best[0] == ref["z"]
+            assert_bit_equal(np.asarray(best[2]), ref["x"], "incumbent")
+    finally:
+        for p in pools:
+            p.close()
+
+
 @pytest.mark.parametrize("m,n,seed", [(1, 6, 0), (5, 8, 1), (12, 9, 2), (30, 40, 3)])
 def test_formulate_and_run_branch_and_bound(m, n, seed):
     """DualSimplexSolverBB.FormulateTableau / PrepareInput / DoDualSimplex(isMin) and
