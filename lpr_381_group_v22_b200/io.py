@@ -119,9 +119,9 @@ class Model:
             cnt, rhs = C.c_int(), C.c_double()
             N.check(N.lib().lpr_model_constraint(self._h, i, None, 0, C.byref(cnt), None, 0, C.byref(rhs)))
             co = np.zeros(max(1, cnt.value))
-            rel = C.create_string_buffer(64)
-            N.check(N.lib().lpr_model_constraint(self._h, i, N.pd(co), cnt.value, None, rel, 64, None))
-            out.append(Constraint(co[:cnt.value].tolist(), rel.value.decode("utf-8", "replace"), rhs.value))
+            N.check(N.lib().lpr_model_constraint(self._h, i, N.pd(co), cnt.value, None, None, 0, None))
+            rel = _string(lambda buf, cap: N.lib().lpr_model_constraint(self._h, i, None, 0, None, buf, cap, None))
+            out.append(Constraint(co[:cnt.value].tolist(), rel, rhs.value))
         return out
 
     def signs(self):

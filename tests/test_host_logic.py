@@ -41,3 +41,16 @@ def test_net_style_formatting():
     lines = txt.split("\r\n")
     assert lines[0] == "\nInitial Tableau:" or lines[0] == "" or "Initial Tableau:" in txt
     assert "Table\tx1\tt1\tRHS" in txt and "Z\t0.000\t-1.000\t2.000\t" in txt and "1\t1.000\t0.500\t3.000\t" in txt
+
+
+def test_division_free_round4_tail(tmp_path):
+    """tools/div1e4_check.c: the fma-based k / 1e4 of the B&B kernels (common.cuh net_round4) equals the IEEE quotient
+    and rounding twice equals rounding once.  The full claim (every |k| <= 2^31) takes ~40 core-seconds and was run
+    when the kernels were written; here the first 2^23 integers of both signs plus the top of the range."""
+    import subprocess
+    exe = str(tmp_path / "div1e4_check")
+    src = os.path.join(os.path.dirname(HERE), "tools", "div1e4_check.c")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", src, "-lm", "-o", exe])
+    for args in (["8388608"], ["2147483648", "2139095040"]):
+        res = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0 and "mismatches 0, idempotence mismatches 0" in res.stdout, res.stdout

@@ -10,10 +10,11 @@
 
 int main(int argc, char** argv) {
   const long long lim = argc > 1 ? atoll(argv[1]) : (1LL << 31);
+  const long long from = argc > 2 ? atoll(argv[2]) : 0; /* optional start of the range */
   const double inv = 1e-4;
   long long bad_div = 0, bad_idem = 0;
 #pragma omp parallel for reduction(+ : bad_div, bad_idem) schedule(static)
-  for (long long i = 0; i <= lim; i++) {
+  for (long long i = from; i <= lim; i++) {
     for (int s = 0; s < 2; s++) {
       const double k = s ? -(double)i : (double)i;
       const double ref = k / 1e4;
@@ -27,6 +28,6 @@ int main(int argc, char** argv) {
       if (rint(ref * 1e4) != k) bad_idem++;
     }
   }
-  printf("checked |k| <= %lld: division mismatches %lld, idempotence mismatches %lld\n", lim, bad_div, bad_idem);
+  printf("checked %lld <= |k| <= %lld: division mismatches %lld, idempotence mismatches %lld\n", from, lim, bad_div, bad_idem);
   return (bad_div || bad_idem) ? 1 : 0;
 }
