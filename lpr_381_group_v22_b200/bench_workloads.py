@@ -62,6 +62,22 @@ def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk, slice_ms=0.0):
     lp_ms = tab.last_solve_ms
     final = tab.read()
     tab.close()
+    # Gomory cuts at the root (the "cutting plane" half of BASELINE configs[4]): CuttingPlaneSolver.CuttingPlaneSolution
+    # on the relaxation's final tableau, cut rows generated on the device; reported beside the tree search, which like
+    # the reference's menu path starts from the relaxation itself.  Rank 0 only, outside the timed region.
+    cuts = None
+    if comm.rank == 0:
+        try:
+            with DeviceTableau.from_host(final, device=device, row_cap=final.shape[0] + 40) as tc:
+                tq = time.perf_counter()
+                rc = tc.cutting_plane(max_cuts=32)
+                dq = time.perf_counter() - tq
+                cuts = dict(n_cuts=rc["n_cuts"], status=N.STATUS_NAMES[rc["status"]], seconds=dq,
+                            dual_pivots=int(rc["log"][:, 2].sum()), primal_pivots=int(rc["log"][:, 3].sum()),
+                            cuts_per_s=rc["n_cuts"] / dq if dq > 0 else None,
+                            what="host clock around lpr_tab_cutting_plane(max_cuts=32) on the 513x1537 relaxation tableau")
+        except Exception as ex:
+            cuts = {"error": repr(ex)}
     # every rank solved the same relaxation to the same bits: all start from the root and split it without a
     # transfer (run_distributed, replicated_root)
     pool = BBPool(final, n, prune=True, device=device)
@@ -87,7 +103,7 @@ def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk, slice_ms=0.0):
                 incumbent_z=(inc[0] if inc else None), incumbent_nonzeros=(int(np.count_nonzero(inc[2])) if inc else None),
                 open_left=left, steals=res["steals"], nodes_moved=res["nodes_moved"], rounds=res["rounds"],
                 finished=(left == 0), phase_seconds_rank0=res["seconds_rank0"],
-                run_seconds_per_rank=res["run_seconds_per_rank"])
+                run_seconds_per_rank=res["run_seconds_per_rank"], root_cuts=cuts)
 
 
 def run_knap_cfg4(n_items, seed, device, dist, max_nodes, chunk):
