@@ -111,7 +111,11 @@ std::string to_lower_ascii(std::string s) {
 // double.Parse(s, CultureInfo.InvariantCulture): NumberStyles.Float | AllowThousands -- white space around, one
 // leading sign, digits with ',' group separators in the integer part, '.', exponent; or the NaN / Infinity symbols.
 bool parse_net_double(const std::string& tok, double* out) {
-  const std::string s = trim(tok);
+  // Number parsing only skips the ASCII white space 0x09-0x0D and 0x20 (not the Unicode set String.Trim() removes)
+  size_t a = 0, b = tok.size();
+  while (a < b && is_ws((unsigned char)tok[a])) a++;
+  while (b > a && is_ws((unsigned char)tok[b - 1])) b--;
+  const std::string s = tok.substr(a, b - a);
   if (s.empty()) return false;
   if (s == "NaN") { *out = NAN; return true; }
   if (s == "Infinity") { *out = INFINITY; return true; }
@@ -120,7 +124,7 @@ bool parse_net_double(const std::string& tok, double* out) {
   size_t i = 0;
   if (s[i] == '+' || s[i] == '-') clean.push_back(s[i++]);
   int digits = 0;
-  while (i < s.size() && ((s[i] >= '0' && s[i] <= '9') || s[i] == ',')) {
+  while (i < s.size() && ((s[i] >= '0' && s[i] <= '9') || (s[i] == ',' && digits > 0))) {  // a group separator needs a digit before it
     if (s[i] != ',') { clean.push_back(s[i]); digits++; }
     i++;
   }

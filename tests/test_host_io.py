@@ -53,6 +53,12 @@ def test_parse_failure_modes_match_the_reference():
         Model.parse_text("max 1 2\n1 1 <= 0x10\n+ +")  # strtod extensions are not .NET syntax
     with pytest.raises(ValueError):
         Model.parse_text("max 1 2\n1 1 <= 1e999\n+ +")  # OverflowException on the Framework
+    for bad in (",5", "1e", ".", "+", "1-", "(1)", "$1", "\u00a05", "0x1p3", "inf", "nan", "1_0"):
+        with pytest.raises((ValueError, IndexError)):
+            Model.parse_text(f"max 1 2\n1 1 <= {bad}\n+ +")
+    for ok, val in (("1,,0", 10.0), (".5", 0.5), ("5.", 5.0), ("-1E+2", -100.0), ("\t7\t", 7.0), ("-.25e1", -2.5), ("NaN", None)):
+        got = Model.parse_text(f"max 1 2\n1 1 <= {ok}\n+ +").constraints()[0].RHS
+        assert (got != got) if val is None else got == val, ok
     with pytest.raises(L.LprError):
         Model.parse_text("max 1\n+").to_device()  # not loaded
 
