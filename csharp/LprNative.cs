@@ -72,6 +72,18 @@ namespace LPR_381_Group_V22.Native
             if (rc != OK) throw new InvalidOperationException("liblprb200: " + Marshal.PtrToStringAnsi(lpr_last_error()));
         }
 
+        // ---- partitionable B&B node pool (one process per GPU; see INTEGRATION.md section 3) ---------------------
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_create(int device, int rows, int cols, double[,] rootTableau, int nVars, int enablePruning, out IntPtr pool);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_destroy(IntPtr pool);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_open_count(IntPtr pool, out long n);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_run(IntPtr pool, long maxNodes, out long processed, out long pivots);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_run_timed(IntPtr pool, long maxNodes, double maxSeconds, out long processed, out long pivots);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_keep_stride(IntPtr pool, int offset, int stride);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_get_incumbent(IntPtr pool, out int has, out double z, [Out] double[] x, [Out] int[] key, ref int keyLen);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_set_incumbent(IntPtr pool, double z, double[] x, int[] key, int keyLen);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_export_nodes(IntPtr pool, int maxNodes, IntPtr buf, long bufCap, out long bytes, out int nExported);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_bb_import_nodes(IntPtr pool, IntPtr buf, long bytes);
+
         // ---- model input (IO/InputFileParser.cs:19-68, Program.cs:114-124, :511-535) ----------------------
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)] public static extern int lpr_model_parse_file(string path, out IntPtr model);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_parse_text(byte[] utf8, long len, out IntPtr model);
