@@ -171,15 +171,22 @@ int parse_lines(const std::vector<std::string>& lines, lpr_model* m) {
   const size_t n = m->objective.size();
   for (size_t li = 1; li + 1 < lines.size(); li++) {
     const std::vector<std::string> parts = split_space(trim(lines[li]), true);
-    if (parts.size() < n + 2)
-      return fail(LPR_E_BADARG, "IndexOutOfRangeException: constraint line %zu has %zu tokens, needs %zu", li, parts.size(),
-                  n + 2);
+    // tokens are consumed left to right like the reference's loop (:50-57): a malformed coefficient throws
+    // FormatException before a missing one throws IndexOutOfRangeException
+    auto missing = [&](size_t idx) {
+      return fail(LPR_E_BADARG, "IndexOutOfRangeException: constraint line %zu has %zu tokens, token %zu is needed", li,
+                  parts.size(), idx + 1);
+    };
     lpr_model::Row row;
     row.coef.resize(n);
-    for (size_t j = 0; j < n; j++)
+    for (size_t j = 0; j < n; j++) {
+      if (j >= parts.size()) return missing(j);
       if (!parse_net_double(parts[j], &row.coef[j]))
         return fail(LPR_E_BADARG, "FormatException: constraint line %zu, coefficient %zu ('%s')", li, j + 1, parts[j].c_str());
+    }
+    if (n >= parts.size()) return missing(n);
     row.relation = parts[n];
+    if (n + 1 >= parts.size()) return missing(n + 1);
     if (!parse_net_double(parts[n + 1], &row.rhs))
       return fail(LPR_E_BADARG, "FormatException: constraint line %zu, right-hand side ('%s')", li, parts[n + 1].c_str());
     m->rows.push_back(std::move(row));

@@ -140,7 +140,7 @@ int main() {
     bool threw = false;
     try {
       IO::InputFileParser bad;
-      bad.ReadInputText("max 1 2\n1 <= 2\n+ +");
+      bad.ReadInputText("max 1 2\n1\n+ +");
     } catch (const ArgumentException& ex) {
       threw = std::string(ex.what()).find("IndexOutOfRangeException") != std::string::npos;
     }

@@ -66,3 +66,49 @@ def format_table(tab, num_original_vars, title, row_labels=None):
         label = row_labels[i - 1] if (row_labels is not None and len(row_labels) >= i) else f"{i}"
         out.append(label + "\t" + "".join(F3(tab[i][j]) + "\t" for j in range(cols)))
     return "\r\n".join(out) + "\r\n"
+
+
+# ---- IO/InputFileParser.cs:19-68, restated with regular expressions (independent of csrc/host_io.cu) ----------------
+import re
+
+_NUM = re.compile(r"^[\t\n\v\f\r ]*[+-]?(?:(?:\d[\d,]*)(?:\.\d*)?|\.\d+)(?:[eE][+-]?\d+)?[\t\n\v\f\r ]*$")
+
+
+def net_parse_double(tok):
+    """double.Parse(tok, InvariantCulture): NumberStyles.Float | AllowThousands"""
+    t = tok.strip("\t\n\v\f\r ")
+    if t in ("NaN", "Infinity", "-Infinity"):
+        return float(t.replace("Infinity", "inf").replace("NaN", "nan"))
+    if not _NUM.match(tok):
+        raise ValueError("FormatException")
+    v = float(t.replace(",", ""))
+    if v in (float("inf"), float("-inf")):
+        raise ValueError("OverflowException")
+    return v
+
+
+def parse_model(text):
+    """returns None when ReadInputFile takes its 'not formatted correctly' early return, else
+    (problem_type, objective, [(coefficients, relation, rhs)], signs); raises ValueError / IndexError where the
+    reference throws FormatException / IndexOutOfRangeException"""
+    if text.startswith("﻿"):
+        text = text[1:]
+    lines = re.split(r"\r\n|\r|\n", text)
+    if lines and lines[-1] == "":
+        lines.pop()  # File.ReadAllLines: a final line terminator does not start a new line
+    if len(lines) < 3:
+        return None
+    obj = lines[0].strip().split(" ")
+    ptype = obj[0].lower()
+    c = [net_parse_double(t) for t in obj[1:]]
+    rows = []
+    for ln in lines[1:-1]:
+        parts = [p for p in ln.strip().split(" ") if p != ""]
+        if len(parts) < len(c) + 2:
+            # coefficients are parsed left to right before the index runs out
+            for t in parts[:len(c)]:
+                net_parse_double(t)
+            raise IndexError("IndexOutOfRangeException")
+        co = [net_parse_double(parts[j]) for j in range(len(c))]
+        rows.append((co, parts[len(c)], net_parse_double(parts[len(c) + 1])))
+    return ptype, c, rows, lines[-1].strip().split(" ")

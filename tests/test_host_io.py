@@ -48,7 +48,11 @@ def test_parse_failure_modes_match_the_reference():
     with pytest.raises(ValueError, match="FormatException"):
         Model.parse_text("max 1 x\n1 1 <= 2\n+ +")
     with pytest.raises(IndexError, match="IndexOutOfRangeException"):
-        Model.parse_text("max 1 2\n1 <= 2\n+ +")
+        Model.parse_text("max 1 2\n1\n+ +")  # the line runs out of tokens
+    with pytest.raises(IndexError, match="IndexOutOfRangeException"):
+        Model.parse_text("max 1 2\n1 1 <=\n+ +")  # no right-hand side
+    with pytest.raises(ValueError, match="FormatException"):
+        Model.parse_text("max 1 2\n1 <= 2\n+ +")  # "<=" is read as the second coefficient first (:50-53)
     with pytest.raises(ValueError):
         Model.parse_text("max 1 2\n1 1 <= 0x10\n+ +")  # strtod extensions are not .NET syntax
     with pytest.raises(ValueError):
@@ -152,3 +156,47 @@ def test_table_format_threaded_path_equals_restatement():
     T = rng.normal(size=(301, 257)) * 10.0 ** rng.integers(-4, 6, (301, 257))  # > 16k cells: several formatter threads
     txt = TableIterationFormater.Format(T, 100, "Iteration 3 - After pivot")
     assert txt == R.format_table(T.tolist(), 100, "Iteration 3 - After pivot")
+
+
+# ---- parser fuzz against the independent restatement ------------------------------------------------------------
+def _outcome(fn):
+    try:
+        return ("ok", fn())
+    except ValueError:
+        return ("format", None)
+    except IndexError:
+        return ("index", None)
+
+
+def _native_parse(text):
+    m = Model.parse_text(text)
+    if not m.info()[0]:
+        return None
+    return m.problem_type, m.objective(), [(c.Coefficients, c.Relation, c.RHS) for c in m.constraints()], m.signs()
+
+
+def test_parser_fuzz_against_restatement():
+    from hypothesis import given, settings, strategies as st
+    tok = st.one_of(
+        st.sampled_from(["1", "-2", "+3.5", ".5", "5.", "1e3", "1E-2", "1,000", "1,,0", ",5", "", "x", "1e", "NaN", "Infinity",
+                         "-Infinity", "<=", ">=", "=", "\t7", "7\t", "0x10", "1_0", "--1", "1.2.3", "1e999", "-0", "00012"]),
+        st.from_regex(r"[+-]?[0-9]{1,4}(\.[0-9]{0,3})?", fullmatch=True))
+    line = st.lists(tok, min_size=0, max_size=6).map(" ".join)
+    eol = st.sampled_from(["\n", "\r\n", "\r"])
+
+    @settings(max_examples=600, deadline=None)
+    @given(st.sampled_from(["max", "MIN", "Max", ""]), st.lists(line, min_size=0, max_size=5), eol, st.booleans(), st.booleans())
+    def run(ptype, lines, nl, trailing, pad):
+        body = [(ptype + " " + lines[0]) if lines else ptype] + lines[1:]
+        if pad:
+            body = ["  " + b + " \t" for b in body]
+        text = nl.join(body) + (nl if trailing else "")
+        ref = _outcome(lambda: R.parse_model(text))
+        got = _outcome(lambda: _native_parse(text))
+        assert ref[0] == got[0], (text, ref, got)
+        if ref[0] == "ok" and ref[1] is not None:
+            assert repr(ref[1]) == repr(got[1]), (text, ref, got)  # repr: NaN-safe, keeps the sign of zero
+        else:
+            assert ref[1] == got[1], (text, ref, got)
+
+    run()
