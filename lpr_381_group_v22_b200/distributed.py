@@ -37,12 +37,13 @@ def _alloc_bytes(cap, torch_device):
 
 
 def _bytes_ptr(data):
+    """(owner, pointer, byte count): the caller holds `owner` until the native call that reads the pointer returns"""
     if hasattr(data, "data_ptr"):  # torch tensor (host or device)
         data = data.contiguous()
-        return C.c_void_p(data.data_ptr()), int(data.numel())
+        return data, C.c_void_p(data.data_ptr()), int(data.numel())
     a = np.ascontiguousarray(data, dtype=np.uint8)
-    _bytes_ptr.keep = a
-    return a.ctypes.data_as(N.vp), int(a.size)
+    return a, a.ctypes.data_as(N.vp), int(a.size)
+
 
 class BBPool:
     """Open-node pool of the branch & bound simplex solver (lpr_bb_*)."""
@@ -110,9 +111,10 @@ class BBPool:
         return buf[:nbytes.value], n.value
 
     def import_nodes(self, data):
-        ptr, size = _bytes_ptr(data)
+        owner, ptr, size = _bytes_ptr(data)
         if size:
             N.check(N.lib().lpr_bb_import_nodes(self._h, ptr, size))
+        del owner
 
 
 class KnapPool:
@@ -172,9 +174,10 @@ class KnapPool:
         return buf[:nbytes.value], n.value
 
     def import_nodes(self, data):
-        ptr, size = _bytes_ptr(data)
+        owner, ptr, size = _bytes_ptr(data)
         if size:
             N.check(N.lib().lpr_knap_import_nodes(self._h, ptr, size))
+        del owner
 
 
 # ------------------------------------------------------------------------------------------------
