@@ -163,6 +163,36 @@ def test_bb_random_ip_matches_oracle(seed, m, n, prune):
         assert_bit_equal(np.array(x), ref["x"], "incumbent")
 
 
+def test_bb_cfg5_size_first_nodes_match_oracle():
+    """BASELINE cfg5 shape (root 513 x 1537): the first 48 nodes of ExecuteBranchAndBound -- node log, node objective
+    values, pivot count -- against the oracle, so the node kernels (row-segmented AddConstraint build, segmented
+    evaluation, machine-wide sweep grid) are checked at the size the bench runs them, not only on toy tableaux."""
+    m, n, seed = 512, 1024, 385
+    A, b, c = O.gen_dense_ip(seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    lp = O.primal_solve(T0, b0, threads=8)
+    assert lp["status"] == O.OPTIMAL
+    Tf = lp["T"]
+    ref = O.bb_solve(Tf, n, prune=True, max_nodes=48)
+    bb = L.BranchBoundSimplexSolver.BranchAndBound()
+    bb.SetNumVars(n)
+    x, z = bb.ExecuteBranchAndBound([Tf], True, max_nodes=48)
+    run = bb.LastRun
+    assert run["nodes"] == ref["nodes"] == 48 and run["pivots"] == ref["pivots"]
+    assert run["node_log"].tolist() == ref["node_log"].tolist()
+    assert_bit_equal(run["node_z"], ref["node_z"], "node z")
+    assert run["has_solution"] == ref["has_solution"]
+    # one AddConstraint at this size, every element
+    Tr = O.bb_round(Tf)
+    val = O.bb_extract(Tr, n)
+    var, _ = O.bb_branch_var(Tr, n)
+    with L.DeviceTableau.from_host(Tr) as t:
+        for typ in (0, 1):
+            bound = float(np.floor(val[var]) if typ == 0 else np.ceil(val[var]))
+            with t.bb_add_constraint(n, var, bound, typ) as ch:
+                assert_bit_equal(ch.read(), O.bb_add_constraint(Tr, n, var, bound, typ))
+
+
 @pytest.mark.parametrize("seed,m,n", [(21, 6, 9), (22, 8, 10), (23, 10, 14)])
 def test_bb_pool_batched_equals_sequential(seed, m, n):
     """Throughput mode (batches of open nodes, pruning on): same incumbent as the sequential oracle."""
