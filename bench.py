@@ -350,6 +350,8 @@ def main():
             rev = run_rev_cfg3(8192, 16384, 384, dev)
         except Exception as ex:
             rev = {"error": repr(ex)}
+    if dist is not None:
+        dist.barrier()  # the other ranks stay in the group until rank 0 is done measuring
 
     if rank != 0:
         if dist is not None:
