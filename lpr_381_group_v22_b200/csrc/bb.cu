@@ -332,8 +332,14 @@ __global__ void __launch_bounds__(kEvalCols* kEvalSegs) k_bb_eval_x(const double
   if (i < n_vars) {
     for (int j0 = r0; j0 < r1 && hit == INT_MAX; j0 += 16) {
       double t[16];
+      const double* col = T + (size_t)j0 * ld + i;
+      if (j0 + 16 <= r1) {  // full block: 16 unpredicated loads issued back to back
 #pragma unroll
-      for (int q = 0; q < 16; q++) t[q] = (j0 + q < r1) ? TAT(T, ld, j0 + q, i) : 0.0;
+        for (int q = 0; q < 16; q++) t[q] = __ldg(col + (size_t)q * ld);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) t[q] = (j0 + q < r1) ? col[(size_t)q * ld] : 0.0;
+      }
 #pragma unroll
       for (int q = 15; q >= 0; q--)
         if (j0 + q < r1 && net_round4_is_one(t[q])) hit = j0 + q;
