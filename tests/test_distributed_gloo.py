@@ -53,9 +53,13 @@ class CpuKnapPool:
             return ("cand", val, sel, crit)
         return ("branch", val + self.v[crit] * (cap / self.w[crit]), sel, crit)
 
-    def run(self, max_nodes):
+    def run(self, max_nodes, max_seconds=0.0):
+        import time
         done = 0
+        t0 = time.perf_counter()
         while self.open and done < max_nodes:
+            if max_seconds > 0 and done > 0 and time.perf_counter() - t0 >= max_seconds:
+                break  # time slice over (lpr_bb_run_timed semantics: at least one node per call)
             fix, key = self.open.pop()
             done += 1
             kind, val, sel, crit = self._eval(fix)
@@ -112,7 +116,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, seed, n, chunk, q, replicated=False):
+def _worker(rank, world, port, seed, n, chunk, q, replicated=False, slice_s=0.0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -121,7 +125,7 @@ def _worker(rank, world, port, seed, n, chunk, q, replicated=False):
     w, v, cap = O.gen_knapsack(seed, n)
     pool = CpuKnapPool(cap, w, v, with_root=(rank == 0 or replicated))
     res = run_distributed(pool, dist, "cpu", chunk_nodes=chunk, payload_len=n, seed_nodes_per_rank=2,
-                          replicated_root=replicated)
+                          replicated_root=replicated, chunk_seconds=slice_s)
     inc = res["incumbent"]
     q.put((rank, inc[0], tuple(inc[1]), inc[2].tolist(), res["nodes_total"], res["steals"], res["nodes_moved"]))
     dist.destroy_process_group()
@@ -151,17 +155,17 @@ def test_distributed_bb_same_answer_as_sequential(world, seed, n, chunk):
     assert outs[0][4] >= ref["nodes"] // 4
 
 
-@pytest.mark.parametrize("world,seed,n,chunk", [(2, 4, 26, 6), (3, 8, 27, 5)])
-def test_distributed_bb_replicated_root(world, seed, n, chunk):
+@pytest.mark.parametrize("world,seed,n,chunk,slice_s", [(2, 4, 26, 6, 0.0), (3, 8, 27, 5, 0.0), (2, 6, 28, 10 ** 6, 2e-4)])
+def test_distributed_bb_replicated_root(world, seed, n, chunk, slice_s):
     """every rank expands the same root and keeps every world-th node (no start-up transfer): same answer, and
-    the seed nodes are counted once"""
+    the seed nodes are counted once; the last case cuts the rounds by time slices instead of node counts"""
     import oracle_lib as O
     w, v, cap = O.gen_knapsack(seed, n)
     ref = O.knap_bb(cap, w, v)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, seed, n, chunk, q, True)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, seed, n, chunk, q, True, slice_s)) for r in range(world)]
     for p in procs:
         p.start()
     outs = sorted(q.get(timeout=180) for _ in range(world))
