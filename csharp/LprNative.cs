@@ -106,6 +106,12 @@ namespace LPR_381_Group_V22.Native
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_fmt_n3(double x, [Out] byte[] buf, int cap);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)]
         public static extern int lpr_fmt_table(double[,] tab, int rows, int cols, long ld, int numOriginalVars, string title, string[] rowLabels, int nLabels, out IntPtr text, out long len);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_fmt_general(double x, [Out] byte[] buf, int cap);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_model_canonical_form(IntPtr model, out IntPtr text, out long len);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)]
+        public static extern int lpr_out_write_full_results(string path, string solverUsed, IntPtr model, string[] snapshots, int nSnapshots, double finalZ, double[] x, int nX, int append, string timestamp);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)]
+        public static extern int lpr_out_write_snapshots_only(string path, string solverUsed, string[] snapshots, int nSnapshots, double finalZ, double[] x, int nX, int append, string timestamp);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, CharSet = CharSet.Ansi)]
         public static extern int lpr_tab_format(IntPtr h, int numOriginalVars, string title, string[] rowLabels, int nLabels, out IntPtr text, out long len);
     }

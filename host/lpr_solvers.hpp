@@ -122,6 +122,33 @@ class InputFileParser {
   }
   lpr_model* model_ = nullptr;
 };
+
+// IO/OutputFileWrite.cs:16-137 over lpr_out_write_*; the parsed model stands in for the reference's four model lists.
+// `timestamp` empty = local time now.
+struct OutputFileWrite {
+  static void WriteFullResults(const std::string& filePath, const std::string& solverUsed, const InputFileParser& model,
+                               const std::vector<std::string>& iterationSnapshots, double finalZ,
+                               const std::vector<double>* solutionVector, bool append = false,
+                               const std::string& timestamp = "") {
+    std::vector<const char*> sn;
+    for (auto& s : iterationSnapshots) sn.push_back(s.c_str());
+    Check(lpr_out_write_full_results(filePath.c_str(), solverUsed.c_str(), model.Native(), sn.data(), (int)sn.size(), finalZ,
+                                     solutionVector ? solutionVector->data() : nullptr,
+                                     solutionVector ? (int)solutionVector->size() : 0, append ? 1 : 0,
+                                     timestamp.empty() ? nullptr : timestamp.c_str()));
+  }
+  static void WriteSnapshotsOnly(const std::string& filePath, const std::string& solverUsed,
+                                 const std::vector<std::string>& snapshots, double finalZ,
+                                 const std::vector<double>* solutionVector, bool append = true,
+                                 const std::string& timestamp = "") {
+    std::vector<const char*> sn;
+    for (auto& s : snapshots) sn.push_back(s.c_str());
+    Check(lpr_out_write_snapshots_only(filePath.c_str(), solverUsed.c_str(), sn.data(), (int)sn.size(), finalZ,
+                                       solutionVector ? solutionVector->data() : nullptr,
+                                       solutionVector ? (int)solutionVector->size() : 0, append ? 1 : 0,
+                                       timestamp.empty() ? nullptr : timestamp.c_str()));
+  }
+};
 }  // namespace IO
 
 namespace Utilities {

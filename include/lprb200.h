@@ -293,6 +293,21 @@ int lpr_fmt_table(const double* tab, int rows, int cols, int64_t ld, int num_ori
 int lpr_tab_format(lpr_tab* h, int num_original_vars, const char* title, const char* const* row_labels,
                    int n_labels, const char** text, int64_t* len);
 
+/* ---- result files: IO/OutputFileWrite.cs:16-137, CanonicalFormConverter.cs:57-98 ------------ */
+int lpr_fmt_general(double x, char* out, int cap); /* double.ToString(): 15 significant digits, "G" */
+/* CanonicalFormConverter.CanonicalFormForFile on the model; *text is library owned like lpr_fmt_table's */
+int lpr_model_canonical_form(const lpr_model* m, const char** text, int64_t* len);
+/* OutputFileWrite.WriteFullResults (:16-78): header, canonical form, snapshots, Z* and x (NumFormat.N3).  x may be
+ * NULL / n_x 0 (solutionVector == null).  timestamp NULL = local time now ("yyyy-MM-dd HH:mm:ss").  The file gets
+ * a UTF-8 byte-order mark when it starts empty, like File.WriteAllText(..., Encoding.UTF8). */
+int lpr_out_write_full_results(const char* path, const char* solver_used, const lpr_model* m,
+                               const char* const* snapshots, int n_snapshots, double final_z, const double* x,
+                               int n_x, int append, const char* timestamp);
+/* OutputFileWrite.WriteSnapshotsOnly (:83-119) */
+int lpr_out_write_snapshots_only(const char* path, const char* solver_used, const char* const* snapshots,
+                                 int n_snapshots, double final_z, const double* x, int n_x, int append,
+                                 const char* timestamp);
+
 #ifdef __cplusplus
 }
 #endif

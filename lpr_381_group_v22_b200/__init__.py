@@ -5,7 +5,8 @@ from . import _native
 from ._native import (CUT_STEP_DONE, INFEASIBLE, ITER_LIMIT, NO_CUT_NEEDED, NO_PIVOT_COL, NODE_LIMIT, OPTIMAL,
                       PIVOT_TOO_SMALL, RULE_DUAL, RULE_PRIMAL, RULE_PRIMAL2, RULE_SENS, RUNNING, STATUS_NAMES,
                       UNBOUNDED, LprError, device_count, launch_count)
-from .io import Constraint, InputFileParser, add_cli_bound_rows, add_upper_bound_constraints
+from .io import (Constraint, InputFileParser, Model, OutputFileWrite, add_cli_bound_rows,
+                 add_upper_bound_constraints)
 from .simplex import (DualSimplexSolver, InvalidOperationException, PrimalSimplexSolver, PrimalSimplexSolver2,
                       RevisedPrimalSimplexSolver)
 from .tableau import DeviceTableau
@@ -14,7 +15,7 @@ from .integer_programming import (BranchAndBoundAdapter, BranchBoundSimplexSolve
                                   KnapsackBranchBoundSimplex, KnapsackBranchBoundSolver)
 
 __all__ = [
-    "Constraint", "InputFileParser", "add_cli_bound_rows", "add_upper_bound_constraints", "DeviceTableau",
+    "Constraint", "InputFileParser", "Model", "OutputFileWrite", "add_cli_bound_rows", "add_upper_bound_constraints", "DeviceTableau",
     "PrimalSimplexSolver", "PrimalSimplexSolver2", "DualSimplexSolver", "RevisedPrimalSimplexSolver",
     "BranchAndBoundAdapter", "BranchBoundSimplexSolver", "CuttingPlaneSolver", "KnapsackBranchBoundSimplex",
     "KnapsackBranchBoundSolver", "SensitivityAnalyzer", "InvalidOperationException", "LprError", "device_count", "launch_count",

@@ -130,6 +130,12 @@ SIGNATURES = {
     "lpr_fmt_table": (C.c_int, [dp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_char_p, C.POINTER(C.c_char_p),
                                 C.c_int, C.POINTER(vp), lp]),
     "lpr_tab_format": (C.c_int, [vp, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(vp), lp]),
+    "lpr_fmt_general": (C.c_int, [C.c_double, C.c_char_p, C.c_int]),
+    "lpr_model_canonical_form": (C.c_int, [vp, C.POINTER(vp), lp]),
+    "lpr_out_write_full_results": (C.c_int, [C.c_char_p, C.c_char_p, vp, C.POINTER(C.c_char_p), C.c_int, C.c_double, dp,
+                                             C.c_int, C.c_int, C.c_char_p]),
+    "lpr_out_write_snapshots_only": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_double, dp,
+                                               C.c_int, C.c_int, C.c_char_p]),
 }
 
 

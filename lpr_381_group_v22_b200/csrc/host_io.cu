@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <sys/stat.h>
 #include <string>
 #include <thread>
 #include <vector>
@@ -269,14 +271,14 @@ void append_fixed(std::string& out, double x, int decimals) {
     }
   }
 }
-// double.ToString() ("G", 15 significant digits) -- only reached by NumFormat.N3 for integral values
+// double.ToString() ("G", 15 significant digits): NumFormat.N3's integral branch and CanonicalFormConverter
 void append_general(std::string& out, double x) {
   if (std::isnan(x)) { out += "NaN"; return; }
   if (std::isinf(x)) { out += x > 0 ? "Infinity" : "-Infinity"; return; }
   NetNumber nb = to_number15(x);
   if (nb.digits.empty()) { out.push_back('0'); return; }
   if (nb.neg) out.push_back('-');
-  if (nb.scale > 15 || nb.scale < -4) {  // scientific (exponent >= 15 or < -5): d.dddE+XX
+  if (nb.scale > 15 || nb.scale < -3) {  // scientific unless -5 < exponent < 15 (exponent = scale - 1): d.dddE+XX
     out.push_back(nb.digits[0]);
     if (nb.digits.size() > 1) {
       out.push_back('.');
@@ -404,7 +406,82 @@ void format_header(std::string& out, int cols, int num_original_vars, const char
   out += "RHS\r\n";
 }
 
-thread_local std::string g_text;  // result of the last lpr_fmt_table / lpr_tab_format call of this thread
+thread_local std::string g_text;
+
+// FormatCoeff :95-98
+void append_coeff(std::string& out, double c) {
+  if (c >= 0) out += "+ ";
+  append_general(out, c);
+}
+// CanonicalFormConverter.CanonicalFormForFile :57-93 (AppendLine = "\r\n", the literal "\n"s are the source's)
+void append_canonical_form(std::string& sb, const lpr_model* m) {
+  sb += "\n=== Canonical Form ===\r\n";
+  sb += "Z ";
+  for (size_t i = 0; i < m->objective.size(); i++) {
+    append_coeff(sb, m->objective[i] * -1);
+    sb += "x" + std::to_string(i + 1) + " ";
+  }
+  sb += "= 0\n";
+  for (size_t i = 0; i < m->rows.size(); i++) {
+    const auto& r = m->rows[i];
+    for (size_t j = 0; j < r.coef.size(); j++) {
+      append_coeff(sb, r.coef[j]);
+      sb += "x" + std::to_string(j + 1) + " ";
+    }
+    sb += "+ S" + std::to_string(i + 1) + " ";
+    sb += "= ";
+    append_general(sb, r.rhs);
+    sb += "\n";
+  }
+  sb += "\nSign Restrictions: ";
+  for (size_t i = 0; i < m->signs.size(); i++) sb += "x" + std::to_string(i + 1) + ": " + m->signs[i] + " ";
+  sb += "\n======================\n\r\n";
+}
+std::string timestamp_or_now(const char* ts) {  // DateTime.Now:yyyy-MM-dd HH:mm:ss
+  if (ts) return ts;
+  char buf[32];
+  const time_t t = time(nullptr);
+  tm lt;
+  localtime_r(&t, &lt);
+  strftime(buf, sizeof buf, "%Y-%m-%d %H:%M:%S", &lt);
+  return buf;
+}
+void append_final_results(std::string& sb, double final_z, const double* x, int n_x) {  // :66-73, :109-116
+  sb += "=== Final Results ===\r\n";
+  sb += "Z* = ";
+  append_n3(sb, final_z);
+  sb += "\r\n";
+  for (int i = 0; x && i < n_x; i++) {
+    sb += "x" + std::to_string(i + 1) + " = ";
+    append_n3(sb, x[i]);
+    sb += "\r\n";
+  }
+}
+// EnsureDirectory + WriteToFile :122-137: File.WriteAllText / AppendAllText with Encoding.UTF8 -- the byte-order mark
+// is written when the file starts empty, never when text is appended to existing content
+int write_text_file(const char* path, const std::string& content, int append) {
+  std::string p(path);
+  for (size_t i = 1; i < p.size(); i++) {  // Directory.CreateDirectory of the parent, recursively
+    if (p[i] == '/') {
+      const std::string dir = p.substr(0, i);
+      if (mkdir(dir.c_str(), 0777) != 0 && errno != EEXIST) return fail(LPR_E_BADARG, "cannot create directory '%s'", dir.c_str());
+    }
+  }
+  bool bom = true;
+  if (append) {
+    struct stat st;
+    if (stat(path, &st) == 0) bom = st.st_size == 0;
+    else append = 0;
+  }
+  FILE* f = fopen(path, append ? "ab" : "wb");
+  if (!f) return fail(LPR_E_BADARG, "cannot open '%s' for writing", path);
+  bool ok = true;
+  if (bom) ok = fwrite("\xEF\xBB\xBF", 1, 3, f) == 3;
+  ok = ok && (content.empty() || fwrite(content.data(), 1, content.size(), f) == content.size());
+  ok = (fclose(f) == 0) && ok;
+  return ok ? LPR_OK : fail(LPR_E_BADARG, "short write to '%s'", path);
+}
+  // result of the last lpr_fmt_table / lpr_tab_format call of this thread
 
 int model_to_arrays(const lpr_model* m, std::vector<double>& coef, std::vector<int>& cnt, std::vector<int>& rel,
                     std::vector<double>& rhs, int* stride) {
@@ -722,6 +799,63 @@ int lpr_tab_format(lpr_tab* h, int num_original_vars, const char* title, const c
   *text = g_text.c_str();
   if (len) *len = (int64_t)g_text.size();
   return LPR_OK;
+}
+
+
+// ---- result files (IO/OutputFileWrite.cs:16-137, Utilities/CanonicalFormConverter.cs:57-98) -------------------------
+int lpr_fmt_general(double x, char* out, int cap) {  // double.ToString()
+  std::string s;
+  append_general(s, x);
+  return copy_out(s, out, cap);
+}
+int lpr_model_canonical_form(const lpr_model* m, const char** text, int64_t* len) {
+  if (!m || !text) return fail(LPR_E_BADARG, "null argument");
+  g_text.clear();
+  append_canonical_form(g_text, m);
+  *text = g_text.c_str();
+  if (len) *len = (int64_t)g_text.size();
+  return LPR_OK;
+}
+int lpr_out_write_full_results(const char* path, const char* solver_used, const lpr_model* m, const char* const* snapshots,
+                               int n_snapshots, double final_z, const double* x, int n_x, int append, const char* timestamp) {
+  if (!path || !m || n_snapshots < 0 || (n_snapshots > 0 && !snapshots)) return fail(LPR_E_BADARG, "bad arguments");
+  std::string sb;
+  sb += "============================================================\r\n";
+  sb += std::string("Solver: ") + (solver_used ? solver_used : "") + "\r\n";
+  sb += "Problem type: " + m->problem_type + "\r\n";
+  sb += "Timestamp: " + timestamp_or_now(timestamp) + "\r\n";
+  sb += "============================================================\r\n";
+  append_canonical_form(sb, m);
+  if (n_snapshots > 0) {
+    sb += "=== Iteration Snapshots ===\r\n";
+    for (int i = 0; i < n_snapshots; i++) {
+      sb += "--- Iteration " + std::to_string(i + 1) + " ---\r\n";
+      sb += snapshots[i] ? snapshots[i] : "";
+      sb += "\r\n";
+    }
+    sb += "\r\n";
+  }
+  append_final_results(sb, final_z, x, n_x);
+  return write_text_file(path, sb, append);
+}
+int lpr_out_write_snapshots_only(const char* path, const char* solver_used, const char* const* snapshots, int n_snapshots,
+                                 double final_z, const double* x, int n_x, int append, const char* timestamp) {
+  if (!path || n_snapshots < 0 || (n_snapshots > 0 && !snapshots)) return fail(LPR_E_BADARG, "bad arguments");
+  std::string sb;
+  sb += "============================================================\r\n";
+  sb += std::string("Solver: ") + (solver_used ? solver_used : "") + "\r\n";
+  sb += "Timestamp: " + timestamp_or_now(timestamp) + "\r\n";
+  sb += "============================================================\r\n";
+  if (n_snapshots > 0) {
+    sb += "=== Solver Log ===\r\n";
+    for (int i = 0; i < n_snapshots; i++) {
+      const std::string s = snapshots[i] ? snapshots[i] : "";
+      sb += s + "\r\n";
+      if (s.empty() || s.back() != '\n') sb += "\r\n";
+    }
+  }
+  append_final_results(sb, final_z, x, n_x);
+  return write_text_file(path, sb, append);
 }
 
 }  // extern "C"

@@ -127,6 +127,12 @@ class Model:
     def signs(self):
         return [_string(N.lib().lpr_model_sign, self._h, j) for j in range(self.info()[3])]
 
+    def canonical_form(self):
+        """CanonicalFormConverter.CanonicalFormForFile (Utilities/CanonicalFormConverter.cs:57-93)"""
+        text, ln = N.vp(), C.c_int64()
+        N.check(N.lib().lpr_model_canonical_form(self._h, C.byref(text), C.byref(ln)))
+        return C.string_at(text.value, ln.value).decode("utf-8")
+
     def add_cli_bound_rows(self):
         N.check(N.lib().lpr_model_add_cli_bound_rows(self._h))
         return self
@@ -165,6 +171,36 @@ class InputFileParser:
         self.Constraints.extend(model.constraints())
         self.SignRestrictions.extend(model.signs())
         self.Model = model
+
+
+def _strings(items):
+    items = list(items or [])
+    arr = (C.c_char_p * max(1, len(items)))(*[str(s).encode("utf-8") for s in items])
+    return arr, len(items)
+
+
+class OutputFileWrite:
+    """IO/OutputFileWrite.cs:16-137 over lpr_out_write_* (the text is assembled and written natively).  The first
+    method takes the parsed model (InputFileParser.Model / io.Model) in place of the reference's four model lists."""
+
+    @staticmethod
+    def WriteFullResults(filePath, solverUsed, model, iterationSnapshots, finalZ, solutionVector, append=False,
+                         timestamp=None):
+        snaps, ns = _strings(iterationSnapshots)
+        x = N.f64(solutionVector) if solutionVector is not None and len(solutionVector) else None
+        N.check(N.lib().lpr_out_write_full_results(
+            os.fsencode(filePath), str(solverUsed).encode("utf-8"), model._h, snaps, ns, float(finalZ),
+            N.pd(x) if x is not None else None, len(x) if x is not None else 0, int(bool(append)),
+            timestamp.encode("utf-8") if timestamp else None))
+
+    @staticmethod
+    def WriteSnapshotsOnly(filePath, solverUsed, snapshots, finalZ, solutionVector, append=True, timestamp=None):
+        snaps, ns = _strings(snapshots)
+        x = N.f64(solutionVector) if solutionVector is not None and len(solutionVector) else None
+        N.check(N.lib().lpr_out_write_snapshots_only(
+            os.fsencode(filePath), str(solverUsed).encode("utf-8"), snaps, ns, float(finalZ),
+            N.pd(x) if x is not None else None, len(x) if x is not None else 0, int(bool(append)),
+            timestamp.encode("utf-8") if timestamp else None))
 
 
 def add_cli_bound_rows(n, constraints):

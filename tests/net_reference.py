@@ -112,3 +112,71 @@ def parse_model(text):
         co = [net_parse_double(parts[j]) for j in range(len(c))]
         rows.append((co, parts[len(c)], net_parse_double(parts[len(c) + 1])))
     return ptype, c, rows, lines[-1].strip().split(" ")
+
+
+# ---- double.ToString(), CanonicalFormConverter.CanonicalFormForFile (:57-98), OutputFileWrite (:16-137) -------------
+def net_general(x):
+    """double.ToString() of the .NET Framework: 15 significant digits, fixed notation when -5 < exponent < 15"""
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == 0:
+        return "0"
+    mant, ex = f"{abs(x):.14e}".split("e")
+    digits = mant.replace(".", "").rstrip("0")
+    ex = int(ex)
+    sign = "-" if x < 0 else ""
+    if -5 < ex < 15:
+        if ex >= 0:
+            ip = digits[:ex + 1].ljust(ex + 1, "0")
+            fp = digits[ex + 1:]
+            return sign + ip + ("." + fp if fp else "")
+        return sign + "0." + "0" * (-ex - 1) + digits
+    m = digits[0] + ("." + digits[1:] if len(digits) > 1 else "")
+    return f"{sign}{m}E{'+' if ex >= 0 else '-'}{abs(ex):02d}"
+
+
+def _coeff(c):
+    return ("+ " if c >= 0 else "") + net_general(c)
+
+
+def canonical_form(objective, constraints, signs):
+    s = "\n=== Canonical Form ===\r\n" + "Z "
+    for i, c in enumerate(objective):
+        s += f"{_coeff(c * -1)}x{i + 1} "
+    s += "= 0\n"
+    for i, (coef, _rel, rhs) in enumerate(constraints):
+        for j, a in enumerate(coef):
+            s += f"{_coeff(a)}x{j + 1} "
+        s += f"+ S{i + 1} " + f"= {net_general(rhs)}\n"
+    s += "\nSign Restrictions: " + "".join(f"x{i + 1}: {r} " for i, r in enumerate(signs)) + "\n======================\n\r\n"
+    return s
+
+
+def _final(final_z, x):
+    s = "=== Final Results ===\r\n" + f"Z* = {N3(final_z)}\r\n"
+    for i, v in enumerate(x or []):
+        s += f"x{i + 1} = {N3(v)}\r\n"
+    return s
+
+
+def full_results_text(solver, ptype, objective, constraints, signs, snapshots, final_z, x, ts):
+    bar = "=" * 60 + "\r\n"
+    s = bar + f"Solver: {solver}\r\nProblem type: {ptype}\r\nTimestamp: {ts}\r\n" + bar + canonical_form(objective, constraints, signs)
+    if snapshots:
+        s += "=== Iteration Snapshots ===\r\n"
+        for i, sn in enumerate(snapshots):
+            s += f"--- Iteration {i + 1} ---\r\n{sn}\r\n"
+        s += "\r\n"
+    return s + _final(final_z, x)
+
+
+def snapshots_only_text(solver, snapshots, final_z, x, ts):
+    bar = "=" * 60 + "\r\n"
+    s = bar + f"Solver: {solver}\r\nTimestamp: {ts}\r\n" + bar
+    if snapshots:
+        s += "=== Solver Log ===\r\n"
+        for sn in snapshots:
+            s += sn + "\r\n" + ("" if sn.endswith("\n") else "\r\n")
+    return s + _final(final_z, x)

@@ -200,3 +200,53 @@ def test_parser_fuzz_against_restatement():
             assert ref[1] == got[1], (text, ref, got)
 
     run()
+
+
+# ---- result files: OutputFileWrite / CanonicalFormForFile ------------------------------------------------------------
+def test_general_format_is_double_tostring():
+    import ctypes as C
+    from lpr_381_group_v22_b200 import _native as N
+
+    def G(x):
+        buf = C.create_string_buffer(64)
+        N.check(N.lib().lpr_fmt_general(float(x), buf, 64))
+        return buf.value.decode()
+
+    known = {0.0: "0", -0.0: "0", 40.0: "40", -11.0: "-11", 0.1: "0.1", 2.5: "2.5", 1e15: "1E+15", 123456789012345.0: "123456789012345",
+             0.0001: "0.0001", 0.00001: "1E-05", 1.5e-7: "1.5E-07", 1 / 3: "0.333333333333333", 2 / 3: "0.666666666666667",
+             1e300: "1E+300", 15.399999999999999: "15.4", -1234.5678: "-1234.5678", float("nan"): "NaN"}
+    for x, s in known.items():
+        assert G(x) == s == R.net_general(x), (x, G(x), s)
+    rng = np.random.default_rng(14)
+    for x in (rng.normal(size=3000) * 10.0 ** rng.integers(-9, 18, 3000)).tolist():
+        assert G(x) == R.net_general(x), x
+
+
+def test_canonical_form_and_result_files(tmp_path):
+    text = "max +2 +3 +3 +5 +2 +4\n+11 +8 +6 +14 +10 +10 <= 40\n1 0 -2.5 0 1 0 >= 3\nbin bin bin bin bin bin"
+    m = Model.parse_text(text)
+    obj = [2, 3, 3, 5, 2, 4]
+    cons = [([11, 8, 6, 14, 10, 10], "<=", 40.0), ([1, 0, -2.5, 0, 1, 0], ">=", 3.0)]
+    assert m.canonical_form() == R.canonical_form(obj, cons, ["bin"] * 6)
+    assert "Z -2x1 -3x2 -3x3 -5x4 -2x5 -4x6 = 0\n+ 11x1 + 8x2" in m.canonical_form()  # negated objective, "+ " prefix
+    snaps = ["\nInitial Tableau:\r\n...\r\n", "no newline at the end"]
+    x = [0.0, 1.0, 1.0, 1.0, 0.2, 1.0]
+    ts = "2025-08-29 10:11:12"
+    path = str(tmp_path / "sub" / "dir" / "output_results.txt")  # EnsureDirectory creates the parents
+    L.io.OutputFileWrite.WriteFullResults(path, "Primal Simplex Algorithm", m, snaps, 15.4, x, append=False, timestamp=ts)
+    want = R.full_results_text("Primal Simplex Algorithm", "max", obj, cons, ["bin"] * 6, snaps, 15.4, x, ts)
+    assert open(path, "rb").read() == b"\xef\xbb\xbf" + want.encode("utf-8")  # File.WriteAllText(..., Encoding.UTF8): BOM
+    assert "Z* = 15.4\r\nx1 = 0\r\nx2 = 1\r\n" in want and "x5 = 0.2\r\n" in want
+    # append to existing content: no second BOM; append to a missing file behaves like a fresh write
+    L.io.OutputFileWrite.WriteSnapshotsOnly(path, "Branch and Bound Simplex Algorithm", snaps, 15.0, None, append=True, timestamp=ts)
+    tail = R.snapshots_only_text("Branch and Bound Simplex Algorithm", snaps, 15.0, None, ts)
+    assert open(path, "rb").read() == b"\xef\xbb\xbf" + (want + tail).encode("utf-8")
+    assert "no newline at the end\r\n\r\n=== Final Results ===" in tail and "...\r\n\r\n=== Final" not in tail.replace("end\r\n\r\n", "")
+    fresh = str(tmp_path / "fresh.txt")
+    L.io.OutputFileWrite.WriteSnapshotsOnly(fresh, "s", [], 1.0, [2.0], append=True, timestamp=ts)
+    assert open(fresh, "rb").read() == b"\xef\xbb\xbf" + R.snapshots_only_text("s", [], 1.0, [2.0], ts).encode("utf-8")
+    L.io.OutputFileWrite.WriteFullResults(fresh, "s", m, [], 0.0, [], timestamp=ts)  # overwrite, no snapshots, empty x
+    assert open(fresh, "rb").read() == b"\xef\xbb\xbf" + R.full_results_text("s", "max", obj, cons, ["bin"] * 6, [], 0.0, [], ts).encode("utf-8")
+    L.io.OutputFileWrite.WriteSnapshotsOnly(str(tmp_path / "now.txt"), "s", ["a\n"], 1.0, None, append=False)
+    import re
+    assert re.search(rb"Timestamp: \d{4}-\d\d-\d\d \d\d:\d\d:\d\d\r\n", open(str(tmp_path / "now.txt"), "rb").read())
