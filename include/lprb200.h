@@ -36,6 +36,7 @@ extern "C" {
 #define LPR_E_NOMEM (-3)
 #define LPR_E_STATE (-4)
 #define LPR_E_CAPACITY (-5)
+#define LPR_E_NCCL (-6)
 
 /* solver status (written to *status) */
 #define LPR_RUNNING 0
@@ -48,6 +49,7 @@ extern "C" {
 #define LPR_NO_CUT_NEEDED 7
 #define LPR_NO_PIVOT_COL 8
 #define LPR_CUT_STEP_DONE 9
+#define LPR_DEPTH_LIMIT 10 /* B&B: some subtree was cut at the slab depth headroom (LPR_BB_MAX_DEPTH) */
 
 /* pivot rule ids: the exact selection / tolerance variant */
 #define LPR_RULE_PRIMAL 0  /* Simplex/PrimalSimplexSolver.cs:152-211                      */
@@ -156,6 +158,16 @@ int lpr_rev_destroy(lpr_rev* h);
 int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status, int64_t* n_iter,
                   int* log, int64_t log_cap);
 int lpr_rev_refactor(lpr_rev* h);
+/* One iteration at a time, for snapshot-accurate tracing (the C# shim / the Python mirror use this path below a size
+ * threshold, lpr_rev_solve above it): lpr_rev_begin resets to the slack basis; lpr_rev_step runs one pass of the loop
+ * of Solve() :86-250 -- *status RUNNING after a pivot, OPTIMAL when none is left (x and z are then ready), INFEASIBLE /
+ * UNBOUNDED / PIVOT_TOO_SMALL where the reference throws; lpr_rev_format_snapshot returns the text block
+ * CaptureSnapshot (:294-387) builds for that step ("Iteration k" / "Optimal": post-pivot duals, reduced costs and
+ * B^-1 A | B^-1 | RHS table beside the pre-pivot direction and ratio test).  B^-1 A (:360, O(m^2 n)) is only computed
+ * when this function is called.  *text is library owned, valid until the thread's next formatting call. */
+int lpr_rev_begin(lpr_rev* h);
+int lpr_rev_step(lpr_rev* h, int* status, int* enter, int* leave_row, int* leave_var);
+int lpr_rev_format_snapshot(lpr_rev* h, const char** text, int64_t* len);
 int lpr_rev_read_basis(lpr_rev* h, int* basis);   /* BasicVariables :39, m entries          */
 int lpr_rev_read_x(lpr_rev* h, double* x);        /* SolutionVector :277-287, n entries     */
 int lpr_rev_read_z(lpr_rev* h, double* z);        /* FinalZ :286                            */
@@ -228,8 +240,11 @@ int lpr_knap_dp(int device, int capacity, int n, const int* weights, const int* 
 int lpr_knap_create(int device, double capacity, int n, const double* weights,
                     const double* values, lpr_knap** out);
 int lpr_knap_destroy(lpr_knap* h);
-/* run rounds of best-bound frontier expansion until the pool is empty or max_nodes reached */
+/* expand the pool level by level (batches of the deepest nodes) until it is empty or max_nodes is reached; the
+ * levels run back to back on the device, the host only looks at a control block every few levels */
 int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status);
+/* same with a time slice: returns after the group of tree levels during which max_seconds (> 0) have elapsed */
+int lpr_knap_run_timed(lpr_knap* h, int64_t max_nodes, double max_seconds, int64_t* processed, int* status);
 int lpr_knap_open_count(lpr_knap* h, int64_t* n);
 int lpr_knap_get_incumbent(lpr_knap* h, double* best, uint8_t* chosen /* n, original ids */,
                            uint64_t* key /* key_words */, int* key_bits);
@@ -242,6 +257,35 @@ int lpr_knap_import_nodes(lpr_knap* h, const void* buf, int64_t bytes);
 int lpr_knap_solve(int device, double capacity, int n, const double* weights,
                    const double* values, int64_t max_nodes, double* best, uint8_t* chosen,
                    int64_t* nodes, int* status);
+
+/* ---- multi-GPU branch & bound inside the library ----------------------------------------
+ * The reference's callers are single-process (Program.cs:385-389 B&B simplex, :444-468 knapsack), so the node pool
+ * is partitioned over n_gpus devices of the box BY THE LIBRARY: one host thread per device, one NCCL communicator
+ * per device (ncclCommInitAll, cached), per round one ncclAllReduce(MAX) of [incumbent value, changed flag, counts],
+ * work stealing with ncclSend / ncclRecv of node records device to device, then one time slice of node work
+ * (csrc/multi_gpu.cu).  devices NULL = 0 .. n_gpus-1.  The incumbent (value, then DFS-first key) does not depend on
+ * n_gpus.  n_gpus = 1 needs no NCCL; with n_gpus > 1 a missing libnccl.so.2 is LPR_E_NCCL (no fallback). */
+typedef struct lpr_mgpu_stats {
+  int n_gpus, nccl_version;
+  int64_t rounds, steals, nodes_moved, open_left, depth_overflow;
+  double seconds;       /* seeding + rounds, max over the ranks */
+  double setup_seconds; /* pool creation, NCCL communicator and channel set-up */
+  double seed_seconds, exchange_seconds, steal_seconds; /* rank 0 */
+  int64_t nodes_per_gpu[16];
+  double run_seconds_per_gpu[16];
+} lpr_mgpu_stats;
+/* BranchAndBound.ExecuteBranchAndBound over n_gpus devices.  max_nodes: total node budget (< 0 none); max_rounds:
+ * number of rounds (< 0 until the pools are empty); slice_seconds > 0: a round is a time slice of that length.
+ * status: OPTIMAL (tree closed), NODE_LIMIT (budget / rounds spent, open nodes left), DEPTH_LIMIT. */
+int lpr_bb_solve_mgpu(int n_gpus, const int* devices, int rows, int cols, const double* final_tableau, int n_vars,
+                      int enable_pruning, int64_t max_nodes, int64_t max_rounds, double slice_seconds, double* x,
+                      double* z, int* has_solution, int64_t* nodes, int64_t* pivots, int* status,
+                      lpr_mgpu_stats* stats /* may be NULL */);
+/* KnapsackBranchBoundSimplex.Solve() over n_gpus devices (slice_seconds <= 0: 2 ms) */
+int lpr_knap_solve_mgpu(int n_gpus, const int* devices, double capacity, int n, const double* weights,
+                        const double* values, int64_t max_nodes, int64_t max_rounds, double slice_seconds, double* best,
+                        uint8_t* chosen, int64_t* nodes, int* status, lpr_mgpu_stats* stats /* may be NULL */);
+int lpr_nccl_version(int* version); /* the NCCL the library resolved (dlopen), e.g. 22809 */
 
 /* ---- model input: IO/InputFileParser.cs:19-68 and the CLI's extra rows ---------------- */
 typedef struct lpr_model lpr_model;
@@ -281,6 +325,8 @@ int lpr_model_load_binary(const char* path, lpr_model** out);
  * its sign */
 int lpr_fmt_f3(double x, char* out, int cap);
 int lpr_fmt_n3(double x, char* out, int cap);
+/* $"{x:F<decimals>}" with the same rules (e.g. the F6 of the "Final Tableau (Optimal)" summary) */
+int lpr_fmt_fixed(double x, int decimals, char* out, int cap);
 /* TableIterationFormater.Format(tab, numOriginalVars, title, rowLabels) on a host array (ld doubles per row).
  * *text points to a buffer owned by the library, valid until the calling thread's next lpr_fmt_table /
  * lpr_tab_format call. */

@@ -4,7 +4,7 @@ there is no CPU fallback."""
 from . import _native
 from ._native import (CUT_STEP_DONE, INFEASIBLE, ITER_LIMIT, NO_CUT_NEEDED, NO_PIVOT_COL, NODE_LIMIT, OPTIMAL,
                       PIVOT_TOO_SMALL, RULE_DUAL, RULE_PRIMAL, RULE_PRIMAL2, RULE_SENS, RUNNING, STATUS_NAMES,
-                      UNBOUNDED, LprError, device_count, launch_count)
+                      UNBOUNDED, DEPTH_LIMIT, LprError, device_count, launch_count)
 from .io import (Constraint, InputFileParser, Model, OutputFileWrite, add_cli_bound_rows,
                  add_upper_bound_constraints)
 from .simplex import (DualSimplexSolver, InvalidOperationException, PrimalSimplexSolver, PrimalSimplexSolver2,
@@ -12,11 +12,11 @@ from .simplex import (DualSimplexSolver, InvalidOperationException, PrimalSimple
 from .tableau import DeviceTableau
 from .sensitivity_analysis import SensitivityAnalyzer
 from .integer_programming import (BranchAndBoundAdapter, BranchBoundSimplexSolver, CuttingPlaneSolver,
-                                  KnapsackBranchBoundSimplex, KnapsackBranchBoundSolver)
+                                  KnapsackBranchBoundSimplex, KnapsackBranchBoundSolver, solve_bb_mgpu)
 
 __all__ = [
     "Constraint", "InputFileParser", "Model", "OutputFileWrite", "add_cli_bound_rows", "add_upper_bound_constraints", "DeviceTableau",
     "PrimalSimplexSolver", "PrimalSimplexSolver2", "DualSimplexSolver", "RevisedPrimalSimplexSolver",
     "BranchAndBoundAdapter", "BranchBoundSimplexSolver", "CuttingPlaneSolver", "KnapsackBranchBoundSimplex",
-    "KnapsackBranchBoundSolver", "SensitivityAnalyzer", "InvalidOperationException", "LprError", "device_count", "launch_count",
+    "KnapsackBranchBoundSolver", "solve_bb_mgpu", "SensitivityAnalyzer", "InvalidOperationException", "LprError", "device_count", "launch_count",
 ]

@@ -14,9 +14,9 @@ LIB_PATH = os.path.join(_PKG, "liblprb200.so")
 
 OK = 0
 RUNNING, OPTIMAL, UNBOUNDED, INFEASIBLE, ITER_LIMIT, NODE_LIMIT, PIVOT_TOO_SMALL, NO_CUT_NEEDED, \
-    NO_PIVOT_COL, CUT_STEP_DONE = range(10)
+    NO_PIVOT_COL, CUT_STEP_DONE, DEPTH_LIMIT = range(11)
 STATUS_NAMES = ["running", "optimal", "unbounded", "infeasible", "iter_limit", "node_limit",
-                "pivot_too_small", "no_cut_needed", "no_pivot_col", "cut_step_done"]
+                "pivot_too_small", "no_cut_needed", "no_pivot_col", "cut_step_done", "depth_limit"]
 RULE_PRIMAL, RULE_PRIMAL2, RULE_DUAL, RULE_SENS = range(4)
 REL = {"<=": 0, ">=": 1, "=": 2}
 
@@ -26,6 +26,23 @@ lp = C.POINTER(C.c_int64)
 bp = C.POINTER(C.c_uint8)
 u64p = C.POINTER(C.c_uint64)
 vp = C.c_void_p
+
+
+class MgpuStats(C.Structure):
+    """lpr_mgpu_stats of include/lprb200.h"""
+    _fields_ = [("n_gpus", C.c_int), ("nccl_version", C.c_int), ("rounds", C.c_int64), ("steals", C.c_int64),
+                ("nodes_moved", C.c_int64), ("open_left", C.c_int64), ("depth_overflow", C.c_int64),
+                ("seconds", C.c_double), ("setup_seconds", C.c_double), ("seed_seconds", C.c_double),
+                ("exchange_seconds", C.c_double), ("steal_seconds", C.c_double), ("nodes_per_gpu", C.c_int64 * 16),
+                ("run_seconds_per_gpu", C.c_double * 16)]
+
+    def as_dict(self):
+        n = self.n_gpus
+        return dict(n_gpus=n, nccl_version=self.nccl_version, rounds=self.rounds, steals=self.steals,
+                    nodes_moved=self.nodes_moved, open_left=self.open_left, depth_overflow=self.depth_overflow,
+                    seconds=self.seconds, setup_seconds=self.setup_seconds, seed_seconds=self.seed_seconds,
+                    exchange_seconds=self.exchange_seconds, steal_seconds=self.steal_seconds,
+                    nodes_per_gpu=list(self.nodes_per_gpu[:n]), run_seconds_per_gpu=list(self.run_seconds_per_gpu[:n]))
 
 
 class LprError(RuntimeError):
@@ -72,6 +89,10 @@ SIGNATURES = {
     "lpr_rev_destroy": (C.c_int, [vp]),
     "lpr_rev_solve": (C.c_int, [vp, C.c_int64, C.c_int, ip, lp, ip, C.c_int64]),
     "lpr_rev_refactor": (C.c_int, [vp]),
+    "lpr_rev_begin": (C.c_int, [vp]),
+    "lpr_rev_step": (C.c_int, [vp, ip, ip, ip, ip]),
+    "lpr_rev_format_snapshot": (C.c_int, [vp, C.POINTER(vp), lp]),
+    "lpr_fmt_fixed": (C.c_int, [C.c_double, C.c_int, C.c_char_p, C.c_int]),
     "lpr_rev_read_basis": (C.c_int, [vp, ip]),
     "lpr_rev_read_x": (C.c_int, [vp, dp]),
     "lpr_rev_read_z": (C.c_int, [vp, dp]),
@@ -104,6 +125,12 @@ SIGNATURES = {
     "lpr_knap_create": (C.c_int, [C.c_int, C.c_double, C.c_int, dp, dp, C.POINTER(vp)]),
     "lpr_knap_destroy": (C.c_int, [vp]),
     "lpr_knap_run": (C.c_int, [vp, C.c_int64, lp, ip]),
+    "lpr_knap_run_timed": (C.c_int, [vp, C.c_int64, C.c_double, lp, ip]),
+    "lpr_bb_solve_mgpu": (C.c_int, [C.c_int, ip, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_double,
+                                    dp, dp, ip, lp, lp, ip, C.POINTER(MgpuStats)]),
+    "lpr_knap_solve_mgpu": (C.c_int, [C.c_int, ip, C.c_double, C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_double, dp, bp,
+                                      lp, ip, C.POINTER(MgpuStats)]),
+    "lpr_nccl_version": (C.c_int, [ip]),
     "lpr_knap_open_count": (C.c_int, [vp, lp]),
     "lpr_knap_get_incumbent": (C.c_int, [vp, dp, bp, u64p, ip]),
     "lpr_knap_set_incumbent": (C.c_int, [vp, C.c_double, bp, u64p, C.c_int]),

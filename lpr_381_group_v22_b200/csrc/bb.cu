@@ -1225,7 +1225,8 @@ int lpr_bb_solve(int device, int rows, int cols, const double* final_tableau, in
       for (int i = 0; i < n_vars; i++) x[i] = h->has_inc ? h->inc_x[i] : 0.0;
     if (nodes) *nodes = done;
     if (pivots) *pivots = piv;
-    if (status) *status = limit ? LPR_NODE_LIMIT : LPR_OPTIMAL;
+    // a subtree cut at the slab depth headroom means the incumbent is not proven optimal: say so (LPR_DEPTH_LIMIT)
+    if (status) *status = h->depth_overflow > 0 ? LPR_DEPTH_LIMIT : (limit ? LPR_NODE_LIMIT : LPR_OPTIMAL);
   }
   lpr_bb_destroy(h);
   return rc;

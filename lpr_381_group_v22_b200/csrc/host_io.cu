@@ -727,6 +727,128 @@ int lpr_model_load_binary(const char* path, lpr_model** out) {
   return LPR_OK;
 }
 
+// ---- RevisedPrimalSimplexSolver.CaptureSnapshot (Simplex/RevisedPrimalSimplexSolver.cs:294-387) --------------------
+// Pure text: every number is already computed.  sb.AppendLine = "\r\n" (.NET Framework on Windows), VarLabel :289-292,
+// NumFormat.N3 :455-465.  rcS may be NULL (= -y, :100-102 / :224-227).
+}  // extern "C"
+namespace lpr {
+void format_revised_snapshot(std::string& sb, const char* title, bool is_min, int m, int n, const double* y,
+                             const double* rcX, const double* rcS, int entering, double rc_pre, const double* u_pre,
+                             const double* ratios_pre, const int* basis_pre, int leave_row, int leave_var_pre,
+                             double z_working, double z_original, const double* BinvA, int64_t ldBA,
+                             const double* Binv, int64_t ldB, const double* xB, const int* basis_post) {
+  const char* NL = "\r\n";
+  auto label = [&](int idx) {
+    return idx < n ? "x" + std::to_string(idx + 1) : "S" + std::to_string(idx - n + 1);
+  };
+  auto joined = [&](const double* v, int cnt, bool neg) {
+    for (int i = 0; i < cnt; i++) {
+      if (i) sb.push_back('\t');
+      append_n3(sb, neg ? -v[i] : v[i]);
+    }
+  };
+  sb += title ? title : "";
+  sb += NL;
+  sb += "Current Tableau (Revised Simplex)";
+  sb += NL;
+  sb += is_min ? "Problem type: MIN (solving by MAX of -c)" : "Problem type: MAX";
+  sb += NL;
+  sb += NL;
+  sb += "Dual prices (y = c_B^T B^{-1}):";
+  sb += NL;
+  joined(y, m, false);
+  sb += NL;
+  sb += NL;
+  sb += "Reduced costs:";
+  sb += NL;
+  sb += "  x: ";
+  joined(rcX, n, false);
+  sb += NL;
+  sb += "  s: ";
+  if (rcS) joined(rcS, m, false); else joined(y, m, true);
+  sb += NL;
+  sb += NL;
+  if (entering >= 0) {
+    const std::string el = label(entering);
+    sb += "Entering variable (chosen pre-pivot): " + el + "  (reduced cost pre = ";
+    append_n3(sb, rc_pre);
+    sb += ")";
+    sb += NL;
+    sb += "Direction u = B^{-1} a_enter (pre-pivot):";
+    sb += NL;
+    joined(u_pre, m, false);
+    sb += NL;
+    sb += NL;
+    sb += "Ratio test (xB_i / u_i; \xE2\x88\x9E if u_i \xE2\x89\xA4 0)  [labels = pre-pivot basis]:";
+    sb += NL;
+    for (int i = 0; i < m; i++) {
+      sb += label(basis_pre[i]) + ": ";
+      if (std::isinf(ratios_pre[i]) && ratios_pre[i] > 0) sb += "\xE2\x88\x9E"; else append_n3(sb, ratios_pre[i]);
+      sb += NL;
+    }
+    if (leave_row >= 0 && leave_var_pre >= 0) {
+      sb += "Pivot (pre\xE2\x86\x92post): " + label(leave_var_pre) + "  \xE2\x86\x92  " + el + "    (pivot = ";
+      append_n3(sb, u_pre[leave_row]);
+      sb += ")";
+      sb += NL;
+      sb += NL;
+    }
+  }
+  sb += "Working objective Z_working (maxified): ";
+  append_n3(sb, z_working);
+  sb += NL;
+  sb += is_min ? "Original objective Z_original (MIN): " : "Original objective Z_original (MAX): ";
+  append_n3(sb, z_original);
+  sb += NL;
+  sb += NL;
+  sb += "Table\t";
+  for (int j = 0; j < n; j++) sb += "x" + std::to_string(j + 1) + "\t";
+  for (int j = 0; j < m; j++) sb += "S" + std::to_string(j + 1) + "\t";
+  sb += "RHS";
+  sb += NL;
+  sb += "Z~\t";
+  for (int j = 0; j < n; j++) {
+    append_n3(sb, rcX[j]);
+    sb.push_back('\t');
+  }
+  for (int j = 0; j < m; j++) {
+    append_n3(sb, rcS ? rcS[j] : -y[j]);
+    sb.push_back('\t');
+  }
+  append_n3(sb, z_working);
+  sb += NL;
+  for (int i = 0; i < m; i++) {
+    sb += label(basis_post[i]) + "\t";
+    for (int j = 0; j < n; j++) {
+      append_n3(sb, BinvA[(size_t)i * ldBA + j]);
+      sb.push_back('\t');
+    }
+    for (int j = 0; j < m; j++) {
+      append_n3(sb, Binv[(size_t)i * ldB + j]);
+      sb.push_back('\t');
+    }
+    append_n3(sb, xB[i]);
+    sb += NL;
+  }
+  sb += "Basic Variables: ";
+  for (int i = 0; i < m; i++) {
+    if (i) sb += ", ";
+    sb += label(basis_post[i]);
+  }
+  sb += NL;
+}
+std::string& thread_text() { return g_text; }
+}  // namespace lpr
+extern "C" {
+
+/* $"{x:F6}" etc. with the .NET Framework rules (the "Final Tableau (Optimal)" summary must not use printf) */
+int lpr_fmt_fixed(double x, int decimals, char* out, int cap) {
+  if (decimals < 0 || decimals > 15) return fail(LPR_E_BADARG, "decimals out of range");
+  std::string s;
+  append_fixed(s, x, decimals);
+  return copy_out(s, out, cap);
+}
+
 // ---- formatting ---------------------------------------------------------------------------------------------
 int lpr_fmt_f3(double x, char* out, int cap) {
   std::string s;

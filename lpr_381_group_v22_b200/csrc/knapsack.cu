@@ -68,14 +68,31 @@ __host__ __device__ inline uint64_t knap_pack_state(int k, int side) {
   return (uint64_t)(uint32_t)k | ((uint64_t)(uint32_t)side << 32);
 }
 
+// Device-resident control block: the tree is walked level by level WITHOUT the host in the loop.  One level =
+// k_knap_eval (batch = top ev_nb records of the stack, evaluated in place) -> k_knap_plan (one CTA: incumbent from the
+// batch's candidates, pruning against it, stable compaction of the survivors, stack bookkeeping, next batch) ->
+// k_knap_gather (surviving parents -> staging, because children overwrite the batch's slots) -> k_knap_expand.  The
+// host enqueues several levels back to back and only then reads this block (lpr_knap_run).
+struct KnapCtl {
+  long long open;       // stack size (records)
+  long long processed;  // nodes evaluated since creation
+  long long max_nodes;  // absolute budget on `processed` for the current run, < 0 = none
+  long long pool_cap;
+  long long ev_first;   // batch of the next k_knap_eval: records [ev_first, ev_first + ev_nb)
+  long long ex_first;   // children of the current level are written from here (= first slot of its batch)
+  int ev_nb, ex_nj;
+  int has_inc, inc_bits, inc_crit, inc_version;
+  double inc_val;
+  int error, stop, levels, batch;
+};
+
 // one thread per node: a walk from the parent's critical item (see the header)
-__global__ void __launch_bounds__(128) k_knap_eval(const uint64_t* __restrict__ pool, size_t rec_words, int W, int count,
-                                                   int n, const double* __restrict__ w, const double* __restrict__ v,
-                                                   int has_inc, double inc_val, const uint64_t* __restrict__ inc_key,
-                                                   int inc_bits, KnapEval* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_knap_eval(const KnapCtl* __restrict__ ctl, const uint64_t* __restrict__ pool,
+                                                   size_t rec_words, int W, int n, const double* __restrict__ w,
+                                                   const double* __restrict__ v, KnapEval* __restrict__ out) {
   const int node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= count) return;
-  const uint64_t* rec = pool + (size_t)node * rec_words;
+  if (node >= ctl->ev_nb) return;
+  const uint64_t* rec = pool + (size_t)(ctl->ev_first + node) * rec_words;
   const uint64_t st = rec[3 * (size_t)W + 1];
   const int k = (int)(uint32_t)st, side = (int)(st >> 32);
   double cap = __longlong_as_double((long long)rec[3 * (size_t)W + 2]);
@@ -124,65 +141,218 @@ __global__ void __launch_bounds__(128) k_knap_eval(const uint64_t* __restrict__ 
     ev.val = __dadd_rn(val, __dmul_rn(v[crit], __ddiv_rn(cap, w[crit])));
     ev.type = 2;
   }
-  // ties with the incumbent are decided by the DFS keys: compare here so that the host never needs the record
   ev.cmp = kCmpNone;
   ev.pad = 0;
-  if (has_inc && ev.type != 0 && ev.val == inc_val)
-    ev.cmp = knap_key_order(rec + 2 * (size_t)W, (int)rec[3 * (size_t)W], inc_key, inc_bits);
   out[node] = ev;
 }
 
-// the incumbent changed while the host was reading this batch: redo the tie test against the new one
-__global__ void k_knap_retie(const uint64_t* __restrict__ pool, size_t rec_words, int W, int count, double inc_val,
-                             const uint64_t* __restrict__ inc_key, int inc_bits, KnapEval* __restrict__ evals) {
-  const int node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= count) return;
-  const uint64_t* rec = pool + (size_t)node * rec_words;
-  int cmp = kCmpNone;
-  if (evals[node].type != 0 && evals[node].val == inc_val)
-    cmp = knap_key_order(rec + 2 * (size_t)W, (int)rec[3 * (size_t)W], inc_key, inc_bits);
-  evals[node].cmp = cmp;
-}
-
-// children of surviving nodes: job = index of the parent in the staged batch; two records per job, each carrying
-// the parent's fill state at its critical item
-__global__ void k_knap_expand(uint64_t* pool, size_t rec_words, int W, const long long* parent, const KnapEval* evals,
-                              int njobs, long long dst_first, const uint64_t* __restrict__ src_pool) {
-  const int job = blockIdx.x;
-  if (job >= njobs) return;
-  const uint64_t* src = src_pool + (size_t)parent[job] * rec_words;
-  const KnapEval ev = evals[parent[job]];
-  const int depth = (int)src[3 * (size_t)W];
-  const int k = ev.crit;
-  // stack order: the x_k = 1 child below the x_k = 0 child (the zero child is DFS-first)
-  uint64_t* one = pool + (size_t)(dst_first + 2 * (long long)job) * rec_words;
-  uint64_t* zero = one + rec_words;
-  for (int t = threadIdx.x; t < (int)rec_words; t += blockDim.x) {
-    uint64_t x = src[t], x1 = x, x0 = x;
-    const int word = t % W, sect = t / W;
-    if (t < 3 * W) {
-      if (sect == 0 && word == (k >> 6)) {  // fixmask: mark k fixed
-        x0 |= 1ull << (k & 63);
-        x1 |= 1ull << (k & 63);
-      } else if (sect == 1 && word == (k >> 6)) {  // fixval
-        x1 |= 1ull << (k & 63);
-      } else if (sect == 2 && word == (depth >> 6)) {  // key: append the branch bit
-        x1 |= 1ull << (depth & 63);
-      }
-    } else if (t == 3 * W) {
-      x0 = x1 = (uint64_t)(depth + 1);
-    } else if (t == 3 * W + 1) {
-      x0 = knap_pack_state(k, 0);
-      x1 = knap_pack_state(k, 1);
-    } else if (t == 3 * W + 2) {
-      x0 = x1 = (uint64_t)__double_as_longlong(ev.cap);
-    } else {
-      x0 = x1 = (uint64_t)__double_as_longlong(ev.base);
+// One CTA per level.  (1) best candidate of the batch: largest value, ties -> DFS-first key (a total order, so the
+// tree reduction is order independent); (2) it replaces the incumbent on strict improvement or on a tie with an
+// earlier key; (3) a branch node survives when its bound beats the incumbent, or ties with it while preceding it
+// in DFS order; (4) survivors are compacted in batch order (stable), so the stack order -- and with it the node
+// count -- does not depend on how the work was scheduled; (5) stack bookkeeping and the next batch.
+constexpr int kPlanT = 1024;
+__global__ void __launch_bounds__(kPlanT) k_knap_plan(KnapCtl* ctl, const uint64_t* __restrict__ pool, size_t rec_words,
+                                                      int W, KnapEval* __restrict__ evals, long long* __restrict__ parent,
+                                                      uint64_t* inc_key, uint64_t* inc_rec) {
+  __shared__ int s_idx[kPlanT];
+  __shared__ int s_cnt[kPlanT];
+  __shared__ int s_upd, s_total;
+  const int tid = threadIdx.x;
+  const int nb = ctl->ev_nb;
+  if (nb <= 0 || ctl->stop) {
+    if (tid == 0) {
+      ctl->ex_nj = 0;
+      ctl->ev_nb = 0;
+      ctl->stop = 1;
     }
-    zero[t] = x0;
-    one[t] = x1;
+    return;
+  }
+  const long long first = ctl->ev_first;
+  auto rec_of = [&](int i) { return pool + (size_t)(first + i) * rec_words; };
+  auto key_of = [&](int i) { return rec_of(i) + 2 * (size_t)W; };
+  auto bits_of = [&](int i) { return (int)rec_of(i)[3 * (size_t)W]; };
+  auto cand_better = [&](int a, int b) {  // is candidate a ahead of candidate b?
+    if (b < 0) return a >= 0;
+    if (a < 0) return false;
+    const double va = evals[a].val, vb = evals[b].val;
+    if (va != vb) return va > vb;
+    return knap_key_order(key_of(a), bits_of(a), key_of(b), bits_of(b)) < 0;
+  };
+  int best = -1;
+  for (int i = tid; i < nb; i += kPlanT)
+    if (evals[i].type == 1 && cand_better(i, best)) best = i;
+  s_idx[tid] = best;
+  __syncthreads();
+  for (int o = kPlanT / 2; o > 0; o >>= 1) {
+    if (tid < o && cand_better(s_idx[tid + o], s_idx[tid])) s_idx[tid] = s_idx[tid + o];
+    __syncthreads();
+  }
+  best = s_idx[0];
+  if (tid == 0) {
+    int upd = 0;
+    if (best >= 0) {
+      const double bv = evals[best].val;
+      if (!ctl->has_inc || bv > ctl->inc_val ||
+          (bv == ctl->inc_val && knap_key_order(key_of(best), bits_of(best), inc_key, ctl->inc_bits) < 0))
+        upd = 1;
+    }
+    s_upd = upd;
+  }
+  __syncthreads();
+  if (s_upd) {  // the incumbent's record stays on the device; the host fetches it when asked (lpr_knap_get_incumbent)
+    const uint64_t* src = rec_of(best);
+    for (int t = tid; t < (int)rec_words; t += kPlanT) inc_rec[t] = src[t];
+    for (int t = tid; t < W; t += kPlanT) inc_key[t] = src[2 * (size_t)W + t];
+    __syncthreads();
+    if (tid == 0) {
+      ctl->has_inc = 1;
+      ctl->inc_val = evals[best].val;
+      ctl->inc_bits = bits_of(best);
+      ctl->inc_crit = evals[best].crit;
+      ctl->inc_version++;
+    }
+    __syncthreads();
+  }
+  const int has_inc = ctl->has_inc;
+  const double inc_val = ctl->inc_val;
+  const int inc_bits = ctl->inc_bits;
+  const int per = (nb + kPlanT - 1) / kPlanT;
+  const int i0 = tid * per, i1 = min(nb, i0 + per);
+  int cnt = 0;
+  for (int i = i0; i < i1; i++) {
+    int keep = 0;
+    if (evals[i].type == 2) {
+      const double bv = evals[i].val;
+      keep = !has_inc || bv > inc_val ||
+             (bv == inc_val && knap_key_order(key_of(i), bits_of(i), inc_key, inc_bits) <= 0);
+    }
+    evals[i].pad = keep;
+    cnt += keep;
+  }
+  s_cnt[tid] = cnt;
+  __syncthreads();
+  for (int o = 1; o < kPlanT; o <<= 1) {  // inclusive scan
+    const int add = tid >= o ? s_cnt[tid - o] : 0;
+    __syncthreads();
+    s_cnt[tid] += add;
+    __syncthreads();
+  }
+  if (tid == kPlanT - 1) s_total = s_cnt[tid];
+  int off = s_cnt[tid] - cnt;
+  __syncthreads();
+  const int nj = s_total;
+  const bool full = first + 2LL * nj > ctl->pool_cap;
+  if (!full)
+    for (int i = i0; i < i1; i++)
+      if (evals[i].pad) parent[off++] = i;
+  __syncthreads();
+  if (tid == 0) {
+    if (full) {  // the batch cannot be expanded: report, keep the nodes where they are
+      ctl->error = 1;
+      ctl->stop = 1;
+      ctl->ex_nj = 0;
+      ctl->ev_nb = 0;
+    } else {
+      ctl->processed += nb;
+      ctl->levels++;
+      const long long open = first + 2LL * nj;
+      ctl->open = open;
+      ctl->ex_first = first;
+      ctl->ex_nj = nj;
+      long long next = open < (long long)ctl->batch ? open : (long long)ctl->batch;
+      if (ctl->max_nodes >= 0) {
+        const long long left = ctl->max_nodes - ctl->processed;
+        if (left < next) next = left < 0 ? 0 : left;
+      }
+      ctl->ev_nb = (int)next;
+      ctl->ev_first = open - next;
+      if (next == 0) ctl->stop = 1;
+    }
   }
 }
+
+// surviving parents -> staging (their slots are about to be overwritten by children of other parents)
+__global__ void __launch_bounds__(128) k_knap_gather(const KnapCtl* __restrict__ ctl, const uint64_t* __restrict__ pool,
+                                                     size_t rec_words, const long long* __restrict__ parent,
+                                                     uint64_t* __restrict__ stage) {
+  const int nj = ctl->ex_nj;
+  const long long first = ctl->ex_first;
+  for (int job = blockIdx.x; job < nj; job += gridDim.x) {
+    const uint64_t* src = pool + (size_t)(first + parent[job]) * rec_words;
+    uint64_t* dst = stage + (size_t)job * rec_words;
+    for (int t = threadIdx.x; t < (int)rec_words; t += blockDim.x) dst[t] = src[t];
+  }
+}
+
+// children of surviving nodes: job = index among the survivors (its parent record sits in stage[job]); two records
+// per job, each carrying the parent's fill state at its critical item
+__global__ void __launch_bounds__(128) k_knap_expand(const KnapCtl* __restrict__ ctl, uint64_t* pool, size_t rec_words,
+                                                     int W, const long long* __restrict__ parent,
+                                                     const KnapEval* __restrict__ evals,
+                                                     const uint64_t* __restrict__ stage) {
+  const int nj = ctl->ex_nj;
+  const long long dst_first = ctl->ex_first;
+  for (int job = blockIdx.x; job < nj; job += gridDim.x) {
+    const uint64_t* src = stage + (size_t)job * rec_words;
+    const KnapEval ev = evals[parent[job]];
+    const int depth = (int)src[3 * (size_t)W];
+    const int k = ev.crit;
+    // stack order: the x_k = 1 child below the x_k = 0 child (the zero child is DFS-first)
+    uint64_t* one = pool + (size_t)(dst_first + 2 * (long long)job) * rec_words;
+    uint64_t* zero = one + rec_words;
+    for (int t = threadIdx.x; t < (int)rec_words; t += blockDim.x) {
+      uint64_t x = src[t], x1 = x, x0 = x;
+      const int word = t % W, sect = t / W;
+      if (t < 3 * W) {
+        if (sect == 0 && word == (k >> 6)) {  // fixmask: mark k fixed
+          x0 |= 1ull << (k & 63);
+          x1 |= 1ull << (k & 63);
+        } else if (sect == 1 && word == (k >> 6)) {  // fixval
+          x1 |= 1ull << (k & 63);
+        } else if (sect == 2 && word == (depth >> 6)) {  // key: append the branch bit
+          x1 |= 1ull << (depth & 63);
+        }
+      } else if (t == 3 * W) {
+        x0 = x1 = (uint64_t)(depth + 1);
+      } else if (t == 3 * W + 1) {
+        x0 = knap_pack_state(k, 0);
+        x1 = knap_pack_state(k, 1);
+      } else if (t == 3 * W + 2) {
+        x0 = x1 = (uint64_t)__double_as_longlong(ev.cap);
+      } else {
+        x0 = x1 = (uint64_t)__double_as_longlong(ev.base);
+      }
+      zero[t] = x0;
+      one[t] = x1;
+    }
+  }
+}
+
+// start of a run: the host's view of the stack (it may have exported / imported records) and the node budget
+__global__ void k_knap_start(KnapCtl* ctl, long long open, long long budget, int batch) {
+  ctl->open = open;
+  ctl->batch = batch;
+  ctl->max_nodes = budget < 0 ? -1 : ctl->processed + budget;
+  long long next = open < (long long)batch ? open : (long long)batch;
+  if (budget >= 0 && budget < next) next = budget;
+  ctl->ev_nb = (int)next;
+  ctl->ev_first = open - next;
+  ctl->ex_nj = 0;
+  ctl->ex_first = open;
+  ctl->stop = next == 0 ? 1 : 0;
+  ctl->error = 0;
+}
+
+// incumbent handed in by the host (another GPU found it): its key is already in inc_key, its payload stays on the host
+__global__ void k_knap_set_inc(KnapCtl* ctl, double val, int bits) {
+  ctl->has_inc = 1;
+  ctl->inc_val = val;
+  ctl->inc_bits = bits;
+  ctl->inc_crit = -2;
+  ctl->inc_version++;
+}
+
 
 // selection of a candidate node, in ORIGINAL item ids (warp per call)
 __global__ void k_knap_selection(const uint64_t* rec, int W, int n, double capacity, const double* w, int crit,
@@ -244,24 +414,27 @@ struct lpr_knap {
   double *d_w = nullptr, *d_v = nullptr;
   int* d_rank = nullptr;
   uint64_t* pool = nullptr;
-  long long pool_cap = 0, open = 0;
-  KnapEval *d_eval = nullptr, *h_eval = nullptr;
-  long long *d_parent = nullptr, *h_parent = nullptr;
-  uint64_t* stage = nullptr;  // batch staging (the batch is moved off the stack before children are pushed)
+  long long pool_cap = 0, open = 0;  // `open` mirrors ctl->open between runs (export / import work on it)
+  KnapEval* d_eval = nullptr;
+  long long* d_parent = nullptr;
+  uint64_t* stage = nullptr;  // surviving parents of a level (children are written over the batch's slots)
   int batch = 0;
-  // incumbent
+  KnapCtl* d_ctl = nullptr;
+  KnapCtl* h_ctl = nullptr;       // pinned copy, refreshed at every host synchronisation of lpr_knap_run
+  uint64_t* d_inc_key = nullptr;  // incumbent key (device copy, read by k_knap_plan)
+  uint64_t* d_inc_rec = nullptr;  // incumbent node record (selection is extracted from it on demand)
+  uint8_t* d_chosen = nullptr;
+  // host mirror of the incumbent, valid when seen_version == h_ctl->inc_version
   bool has_inc = false;
   double inc_val = -INFINITY;
   std::vector<uint64_t> inc_key;
   int inc_key_bits = 0;
   std::vector<uint8_t> inc_chosen;
-  uint64_t* d_inc_key = nullptr;  // device copy of inc_key for the tie test in k_knap_eval
-  bool inc_key_dirty = false;
-  int64_t inc_version = 0;        // bumped whenever the incumbent changes
+  int seen_version = 0;
   int64_t processed = 0;
-  // LPR_KNAP_PROFILE=1: host-clock split of lpr_knap_run, printed by lpr_knap_destroy
-  double t_eval = 0, t_host = 0, t_expand = 0;
-  int64_t n_batches = 0, n_fetch = 0, n_incumbents = 0;
+  // LPR_KNAP_PROFILE=1: printed by lpr_knap_destroy
+  double t_run = 0;
+  int64_t n_syncs = 0, n_levels = 0, n_incumbents = 0;
 };
 
 static inline double knap_now() {
@@ -274,20 +447,37 @@ static int knap_key_cmp(const uint64_t* a, int abits, const uint64_t* b, int bbi
   return knap_key_order(a, abits, b, bbits);
 }
 
+// bring the host mirror of the incumbent up to date with the device (the device finds incumbents on its own)
+static int knap_refresh_incumbent(lpr_knap* h) {
+  if (h->seen_version == h->h_ctl->inc_version) return LPR_OK;
+  const KnapCtl& c = *h->h_ctl;
+  h->inc_key.assign(h->W, 0);
+  LPR_CUDA(cudaMemcpyAsync(h->inc_key.data(), h->d_inc_key, sizeof(uint64_t) * h->W, cudaMemcpyDeviceToHost, h->stream));
+  k_knap_selection<<<1, 256, 0, h->stream>>>(h->d_inc_rec, h->W, h->n, h->capacity, h->d_w, c.inc_crit, h->d_rank, h->d_chosen);
+  LPR_LAUNCH_CHECK();
+  LPR_CUDA(cudaMemcpyAsync(h->inc_chosen.data(), h->d_chosen, h->n, cudaMemcpyDeviceToHost, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  h->has_inc = c.has_inc != 0;
+  h->inc_val = c.inc_val;
+  h->inc_key_bits = c.inc_bits;
+  h->n_incumbents += c.inc_version - h->seen_version;
+  h->seen_version = c.inc_version;
+  return LPR_OK;
+}
+
 extern "C" {
 
 int lpr_knap_destroy(lpr_knap* h) {
   if (!h) return LPR_OK;
   cudaSetDevice(h->device);
   if (getenv("LPR_KNAP_PROFILE"))
-    fprintf(stderr, "[lpr_knap] nodes=%lld batches=%lld fetches=%lld incumbents=%lld | stage+eval %.4fs host %.4fs expand %.4fs\n",
-            (long long)h->processed, (long long)h->n_batches, (long long)h->n_fetch, (long long)h->n_incumbents, h->t_eval,
-            h->t_host, h->t_expand);
+    fprintf(stderr, "[lpr_knap] nodes=%lld levels=%lld host syncs=%lld incumbents=%lld | run %.4fs\n",
+            (long long)h->processed, (long long)h->n_levels, (long long)h->n_syncs, (long long)h->n_incumbents, h->t_run);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_w); cudaFree(h->d_v); cudaFree(h->d_rank); cudaFree(h->pool); cudaFree(h->d_eval);
-  cudaFree(h->d_parent); cudaFree(h->stage); cudaFree(h->d_inc_key);
-  if (h->h_eval) cudaFreeHost(h->h_eval);
-  if (h->h_parent) cudaFreeHost(h->h_parent);
+  cudaFree(h->d_parent); cudaFree(h->stage); cudaFree(h->d_inc_key); cudaFree(h->d_inc_rec); cudaFree(h->d_chosen);
+  cudaFree(h->d_ctl);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return LPR_OK;
@@ -340,13 +530,24 @@ int lpr_knap_create(int device, double capacity, int n, const double* weights, c
   TRY(cudaMalloc(&h->pool, sizeof(uint64_t) * h->rec_words * (size_t)h->pool_cap));
   TRY(cudaMalloc(&h->stage, sizeof(uint64_t) * h->rec_words * (size_t)h->batch));
   TRY(cudaMalloc(&h->d_eval, sizeof(KnapEval) * h->batch));
-  TRY(cudaMallocHost(&h->h_eval, sizeof(KnapEval) * h->batch));
   TRY(cudaMalloc(&h->d_parent, sizeof(long long) * h->batch));
   TRY(cudaMalloc(&h->d_inc_key, sizeof(uint64_t) * h->W));
-  TRY(cudaMallocHost(&h->h_parent, sizeof(long long) * h->batch));
+  TRY(cudaMalloc(&h->d_inc_rec, sizeof(uint64_t) * h->rec_words));
+  TRY(cudaMalloc(&h->d_chosen, n));
+  TRY(cudaMalloc(&h->d_ctl, sizeof(KnapCtl)));
+  TRY(cudaMallocHost(&h->h_ctl, sizeof(KnapCtl)));
+  TRY(cudaMemsetAsync(h->d_inc_key, 0, sizeof(uint64_t) * h->W, h->stream));
+  TRY(cudaMemsetAsync(h->d_inc_rec, 0, sizeof(uint64_t) * h->rec_words, h->stream));
   TRY(cudaMemcpyAsync(h->d_w, rw.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
   TRY(cudaMemcpyAsync(h->d_v, rv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
   TRY(cudaMemcpyAsync(h->d_rank, h->rank.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+  memset(h->h_ctl, 0, sizeof(KnapCtl));
+  h->h_ctl->pool_cap = h->pool_cap;
+  h->h_ctl->max_nodes = -1;
+  h->h_ctl->batch = h->batch;
+  h->h_ctl->inc_crit = -1;
+  h->h_ctl->inc_val = -INFINITY;
+  TRY(cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(KnapCtl), cudaMemcpyHostToDevice, h->stream));
   // root node: nothing fixed, empty key, fill state = (no parent item, whole capacity, no value)
   {
     std::vector<uint64_t> root(h->rec_words, 0);
@@ -358,6 +559,7 @@ int lpr_knap_create(int device, double capacity, int n, const double* weights, c
 #undef TRY
   h->open = 1;
   h->inc_chosen.assign(n, 0);
+  h->inc_key.assign(h->W, 0);
   *out = h;
   return LPR_OK;
 }
@@ -368,129 +570,62 @@ int lpr_knap_open_count(lpr_knap* h, int64_t* n) {
   return LPR_OK;
 }
 
-int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status) {
+// Levels are enqueued several at a time; the host only reads the control block between such groups (4, 8, ... 32
+// levels), so a level costs four back-to-back launches and no round trip.  A group enqueued after the device has
+// stopped (pool empty, budget reached) falls through: every kernel returns on ctl->stop / empty counts.
+int lpr_knap_run_timed(lpr_knap* h, int64_t max_nodes, double max_seconds, int64_t* processed, int* status) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
   int rc = select_device(h->device);
   if (rc) return rc;
-  int64_t done = 0;
-  int st = LPR_OPTIMAL;
-  const size_t rb = sizeof(uint64_t) * h->rec_words;
-  std::vector<uint64_t> rec(h->rec_words);
-  while (h->open > 0) {
-    if (max_nodes >= 0 && done >= max_nodes) {
-      st = LPR_NODE_LIMIT;
-      break;
+  const double t0 = knap_now();
+  const long long before = h->h_ctl->processed;
+  const int g_eval = (h->batch + 127) / 128;
+  const int g_exp = std::max(1, std::min(h->batch, h->sms * 8));
+  k_knap_start<<<1, 1, 0, h->stream>>>(h->d_ctl, h->open, (long long)max_nodes, h->batch);
+  LPR_LAUNCH_CHECK();
+  int group = 4;
+  while (true) {
+    for (int l = 0; l < group; l++) {
+      k_knap_eval<<<g_eval, 128, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->n, h->d_w, h->d_v, h->d_eval);
+      LPR_LAUNCH_CHECK();
+      k_knap_plan<<<1, kPlanT, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->d_eval, h->d_parent,
+                                               h->d_inc_key, h->d_inc_rec);
+      LPR_LAUNCH_CHECK();
+      k_knap_gather<<<g_exp, 128, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->d_parent, h->stage);
+      LPR_LAUNCH_CHECK();
+      k_knap_expand<<<g_exp, 128, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->d_parent, h->d_eval, h->stage);
+      LPR_LAUNCH_CHECK();
     }
-    long long nb = std::min<long long>(h->batch, h->open);
-    if (max_nodes >= 0) nb = std::min<long long>(nb, max_nodes - done);
-    const double tp0 = knap_now();
-    h->n_batches++;
-    const long long first = h->open - nb;  // deepest nodes sit at the top of the stack
-    // move the batch off the stack so that children can be written over it
-    LPR_CUDA(cudaMemcpyAsync(h->stage, h->pool + (size_t)first * h->rec_words, rb * nb, cudaMemcpyDeviceToDevice, h->stream));
-    if (h->has_inc && h->inc_key_dirty) {
-      LPR_CUDA(cudaMemcpyAsync(h->d_inc_key, h->inc_key.data(), sizeof(uint64_t) * h->W, cudaMemcpyHostToDevice, h->stream));
-      h->inc_key_dirty = false;
-    }
-    const int64_t version0 = h->inc_version;
-    k_knap_eval<<<(int)((nb + 127) / 128), 128, 0, h->stream>>>(h->stage, h->rec_words, h->W, (int)nb, h->n, h->d_w,
-                                                                 h->d_v, h->has_inc ? 1 : 0, h->inc_val, h->d_inc_key,
-                                                                 h->inc_key_bits, h->d_eval);
-    LPR_LAUNCH_CHECK();
-    LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(KnapEval) * nb, cudaMemcpyDeviceToHost, h->stream));
+    LPR_CUDA(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(KnapCtl), cudaMemcpyDeviceToHost, h->stream));
     LPR_CUDA(cudaStreamSynchronize(h->stream));
-    h->open = first;
-    done += nb;
-    h->processed += nb;
-    const double tp1 = knap_now();
-    h->t_eval += tp1 - tp0;
-    auto fetch = [&](long long idx) -> int {
-      h->n_fetch++;
-      LPR_CUDA(cudaMemcpy(rec.data(), h->stage + (size_t)idx * h->rec_words, rb, cudaMemcpyDeviceToHost));
-      return LPR_OK;
-    };
-    // 1) incumbent from the candidates of this batch: max value, ties -> DFS-first key
-    for (long long i = 0; i < nb; i++) {
-      const KnapEval& ev = h->h_eval[i];
-      if (ev.type != 1) continue;
-      bool better = !h->has_inc || ev.val > h->inc_val;
-      bool tie = h->has_inc && ev.val == h->inc_val;
-      if (!better && !tie) continue;
-      // the kernel already ordered tied keys against the incumbent it was launched with
-      if (tie && h->inc_version == version0 && ev.cmp != kCmpNone && ev.cmp >= 0) continue;
-      if ((rc = fetch(i))) return rc;
-      const int kbits = (int)rec[3 * (size_t)h->W];
-      const uint64_t* key = rec.data() + 2 * (size_t)h->W;
-      if (tie && knap_key_cmp(key, kbits, h->inc_key.data(), h->inc_key_bits) >= 0) continue;
-      h->has_inc = true;
-      h->inc_version++;
-      h->inc_key_dirty = true;
-      h->n_incumbents++;
-      h->inc_val = ev.val;
-      h->inc_key.assign(key, key + h->W);
-      h->inc_key_bits = kbits;
-      uint8_t* d_ch = nullptr;
-      LPR_CUDA(cudaMalloc(&d_ch, h->n));
-      k_knap_selection<<<1, 256, 0, h->stream>>>(h->stage + (size_t)i * h->rec_words, h->W, h->n, h->capacity, h->d_w,
-                                                 ev.crit, h->d_rank, d_ch);
-      count_launch();
-      cudaError_t e = cudaMemcpyAsync(h->inc_chosen.data(), d_ch, h->n, cudaMemcpyDeviceToHost, h->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-      cudaFree(d_ch);
-      if (e != cudaSuccess) return fail(LPR_E_CUDA, "selection readback failed: %s", cudaGetErrorString(e));
+    h->n_syncs++;
+    if (h->h_ctl->error) {
+      h->open = h->h_ctl->open;
+      return fail(LPR_E_CAPACITY, "knapsack node pool full (%lld records); raise LPR_KNAP_POOL_MB", h->pool_cap);
     }
-    // 2) surviving branch nodes -> children
-    if (h->inc_version != version0) {  // order the batch against the incumbent it has just produced
-      LPR_CUDA(cudaMemcpyAsync(h->d_inc_key, h->inc_key.data(), sizeof(uint64_t) * h->W, cudaMemcpyHostToDevice, h->stream));
-      h->inc_key_dirty = false;
-      k_knap_retie<<<(int)((nb + 127) / 128), 128, 0, h->stream>>>(h->stage, h->rec_words, h->W, (int)nb, h->inc_val,
-                                                                    h->d_inc_key, h->inc_key_bits, h->d_eval);
-      LPR_LAUNCH_CHECK();
-      LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(KnapEval) * nb, cudaMemcpyDeviceToHost, h->stream));
-      LPR_CUDA(cudaStreamSynchronize(h->stream));
-    }
-    int nj = 0;
-    for (long long i = 0; i < nb; i++) {
-      const KnapEval& ev = h->h_eval[i];
-      if (ev.type != 2) continue;
-      if (h->has_inc) {
-        if (ev.val < h->inc_val) continue;
-        if (ev.val == h->inc_val) {  // keep only if the node precedes the incumbent in DFS order
-          if (ev.cmp != kCmpNone) {
-            if (ev.cmp > 0) continue;
-          } else {  // not reached (the kernels order every tie); kept as the literal rule
-            if ((rc = fetch(i))) return rc;
-            const int kbits = (int)rec[3 * (size_t)h->W];
-            if (knap_key_cmp(rec.data() + 2 * (size_t)h->W, kbits, h->inc_key.data(), h->inc_key_bits) > 0) continue;
-          }
-        }
-      }
-      h->h_parent[nj] = i;
-      nj++;
-    }
-    const double tp2 = knap_now();
-    h->t_host += tp2 - tp1;
-    if (nj > 0) {
-      if (h->open + 2LL * nj > h->pool_cap)
-        return fail(LPR_E_CAPACITY, "knapsack node pool full (%lld records); raise LPR_KNAP_POOL_MB", h->pool_cap);
-      // keep DFS order inside the batch: later batch entries (deeper / DFS-earlier) stay on top
-      LPR_CUDA(cudaMemcpyAsync(h->d_parent, h->h_parent, sizeof(long long) * nj, cudaMemcpyHostToDevice, h->stream));
-      k_knap_expand<<<nj, 128, 0, h->stream>>>(h->pool, h->rec_words, h->W, h->d_parent, h->d_eval, nj, h->open, h->stage);
-      LPR_LAUNCH_CHECK();
-      // no synchronisation here: the next batch's stage copy is ordered behind this launch on the same stream, and
-      // h_parent is not rewritten before that batch's evaluation has been waited for
-      h->open += 2LL * nj;
-    }
-    h->t_expand += knap_now() - tp2;
+    if (h->h_ctl->stop) break;
+    if (max_seconds > 0.0 && knap_now() - t0 >= max_seconds) break;
+    group = std::min(32, group * 2);
   }
-  LPR_CUDA(cudaStreamSynchronize(h->stream));  // export / import use blocking copies outside this stream
+  h->open = h->h_ctl->open;
+  const int64_t done = h->h_ctl->processed - before;
+  h->processed = h->h_ctl->processed;
+  h->n_levels = h->h_ctl->levels;
+  h->t_run += knap_now() - t0;
   if (processed) *processed = done;
-  if (status) *status = st;
+  if (status) *status = (h->open > 0 && max_nodes >= 0 && done >= max_nodes) ? LPR_NODE_LIMIT : LPR_OPTIMAL;
   return LPR_OK;
+}
+
+int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status) {
+  return lpr_knap_run_timed(h, max_nodes, 0.0, processed, status);
 }
 
 int lpr_knap_get_incumbent(lpr_knap* h, double* best, uint8_t* chosen, uint64_t* key, int* key_bits) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  if ((rc = knap_refresh_incumbent(h))) return rc;
   if (best) *best = h->has_inc ? h->inc_val : -INFINITY;
   if (chosen) memcpy(chosen, h->inc_chosen.data(), h->n);
   if (key && h->has_inc) memcpy(key, h->inc_key.data(), sizeof(uint64_t) * h->W);
@@ -500,17 +635,28 @@ int lpr_knap_get_incumbent(lpr_knap* h, double* best, uint8_t* chosen, uint64_t*
 
 int lpr_knap_set_incumbent(lpr_knap* h, double best, const uint8_t* chosen, const uint64_t* key, int key_bits) {
   if (!h || !chosen || key_bits < 0 || (key_bits > 0 && !key)) return fail(LPR_E_BADARG, "bad incumbent");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  if ((rc = knap_refresh_incumbent(h))) return rc;
   std::vector<uint64_t> k(h->W, 0);
   if (key) memcpy(k.data(), key, sizeof(uint64_t) * h->W);
   if (!h->has_inc || best > h->inc_val ||
       (best == h->inc_val && knap_key_cmp(k.data(), key_bits, h->inc_key.data(), h->inc_key_bits) < 0)) {
     h->has_inc = true;
-    h->inc_version++;
-    h->inc_key_dirty = true;
     h->inc_val = best;
     h->inc_key = k;
     h->inc_key_bits = key_bits;
     h->inc_chosen.assign(chosen, chosen + h->n);
+    LPR_CUDA(cudaMemcpyAsync(h->d_inc_key, h->inc_key.data(), sizeof(uint64_t) * h->W, cudaMemcpyHostToDevice, h->stream));
+    k_knap_set_inc<<<1, 1, 0, h->stream>>>(h->d_ctl, best, key_bits);
+    LPR_LAUNCH_CHECK();
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
+    h->h_ctl->has_inc = 1;
+    h->h_ctl->inc_val = best;
+    h->h_ctl->inc_bits = key_bits;
+    h->h_ctl->inc_crit = -2;
+    h->h_ctl->inc_version++;
+    h->seen_version = h->h_ctl->inc_version;
   }
   return LPR_OK;
 }
@@ -559,6 +705,7 @@ int lpr_knap_solve(int device, double capacity, int n, const double* weights, co
   int64_t done = 0;
   int st = LPR_OPTIMAL;
   rc = lpr_knap_run(h, max_nodes, &done, &st);
+  if (rc == LPR_OK) rc = knap_refresh_incumbent(h);
   if (rc == LPR_OK) {
     if (best) *best = h->has_inc ? h->inc_val : 0.0;
     if (chosen) memcpy(chosen, h->inc_chosen.data(), n);

@@ -13,6 +13,7 @@
 // sequential sums, which is why this path is held to 1e-9 relative, not bit equality.
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -541,6 +542,49 @@ __global__ void k_rev_gen(double* A, int ldA, double* b, double* c, double* c_or
   if (blockIdx.x == 0 && threadIdx.x == 0) b[row] = ((double)n / 4.0) * (1.0 + u01(seed, 1, (uint64_t)row));
 }
 
+// x_B = B^-1 b alone (same warp-per-row tree as k_dir, so the value is the one the next k_dir will produce): the
+// POST-pivot basic solution of the per-iteration snapshot (:218)
+__global__ void __launch_bounds__(kT) k_xb_only(RevView v) {
+  const int m = v.m;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kT + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * kT) >> 5;
+  const int ldv = v.ldB >> 1;
+  const double2* __restrict__ B2 = reinterpret_cast<const double2*>(v.Binv);
+  const double4* __restrict__ ab4 = reinterpret_cast<const double4*>(v.ab);
+  const int mv = (m + 1) >> 1;
+  for (int i = warp; i < m; i += nwarps) {
+    double sx = 0.0;
+    const double2* row = B2 + (size_t)i * ldv;
+    for (int c = lane; c < mv; c += 32) {
+      double2 bv = row[c];
+      double4 w = ab4[c];
+      sx = __dadd_rn(sx, __dmul_rn(bv.x, w.y));
+      if (2 * c + 1 < m) sx = __dadd_rn(sx, __dmul_rn(bv.y, w.w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sx = __dadd_rn(sx, __shfl_xor_sync(0xffffffffu, sx, o));
+    if (lane == 0) v.xB[i] = sx;
+  }
+}
+
+// MultiplyMatrices(BInverse, A) of CaptureSnapshot (:360, :426-441), literally: k ascending, |B^-1[i,k]| < 1e-9 skipped,
+// multiply then add into a zero -- one thread per output element, so the printed tableau is the reference's bit for bit
+// given the same B^-1.  O(m^2 n): only ever launched for a snapshot (lazy), never inside Solve().
+__global__ void __launch_bounds__(256) k_binv_a(RevView v, double* __restrict__ out, int ldo) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= v.n) return;
+  const double* __restrict__ brow = v.Binv + (size_t)i * v.ldB;
+  double s = 0.0;
+  for (int k = 0; k < v.m; k++) {
+    const double aik = brow[k];
+    if (fabs(aik) < 1e-9) continue;
+    s = __dadd_rn(s, __dmul_rn(aik, v.A[(size_t)k * v.ldA + j]));
+  }
+  out[(size_t)i * ldo + j] = s;
+}
+
 // SolutionVector / FinalZ :277-287 (x = max(0, x_B) for basic structurals; z = c_orig . x sequential)
 __global__ void k_rev_solution(RevView v, const double* c_orig, double* x, double* z) {
   const int n = v.n, m = v.m;
@@ -585,6 +629,16 @@ struct lpr_rev {
   float last_ms = 0.f, last_refactor_ms = 0.f;
   double last_refactor_residual = 0.0, last_refactor_flops = 0.0;
   bool solved = false;
+  // lpr_rev_begin / lpr_rev_step: host copies of the PRE-pivot quantities of the last step, which CaptureSnapshot
+  // (:294-387) prints beside the post-pivot tableau
+  struct Trace {
+    bool valid = false, optimal = false;
+    long long iteration = 0;
+    int enter = -1, leave_row = -1, leave_var = -1;
+    double rc_enter_pre = 0.0;
+    std::vector<double> u_pre, xb_pre;
+  } trace;
+  bool stepping = false, is_min = false;
   RevView view() const {
     RevView v;
     v.m = m; v.n = n; v.ldA = ldA; v.ldB = ldB; v.A = A; v.Binv = Binv; v.b = b; v.c = c; v.cB = cB;
@@ -747,6 +801,7 @@ int lpr_rev_create(int device, int m, int n, const double* A, const double* b, c
     lpr_rev_destroy(h);
     return rc;
   }
+  h->is_min = is_minimization != 0;
   *out = h;
   return LPR_OK;
 }
@@ -843,6 +898,157 @@ int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status,
     LPR_CUDA(cudaMemcpy(log, h->log, sizeof(int) * 3 * (size_t)cnt, cudaMemcpyDeviceToHost));
   }
   h->solved = true;
+  return LPR_OK;
+}
+
+// ---- one iteration at a time, for snapshot-accurate tracing (SURVEY 8b "Snapshots", row b9) ----------------------------
+int lpr_rev_begin(lpr_rev* h) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  if ((rc = rev_init_basis(h))) return rc;  // Solve() always starts from the slack basis (:63-79)
+  k_rev_reset<<<1, 1, 0, h->stream>>>(h->st, -1LL);
+  LPR_LAUNCH_CHECK();
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  h->stepping = true;
+  h->trace = lpr_rev::Trace();
+  return LPR_OK;
+}
+
+// One pass of the while loop of Solve() (:86-250).  *status: RUNNING after a pivot ("Iteration k" snapshot available),
+// OPTIMAL when no entering variable exists ("Optimal" snapshot available, x and z ready), INFEASIBLE / UNBOUNDED /
+// PIVOT_TOO_SMALL where the reference throws (:91, :179, :267).
+int lpr_rev_step(lpr_rev* h, int* status, int* enter, int* leave_row, int* leave_var) {
+  if (!h) return fail(LPR_E_BADARG, "null handle");
+  if (!h->stepping) return fail(LPR_E_STATE, "lpr_rev_step needs lpr_rev_begin first");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  lpr_rev hv = *h;
+  hv.log = nullptr;
+  hv.log_cap = 0;
+  RevView v = hv.view();
+  const int m = h->m, n = h->n;
+  dim3 gp((h->ldA / 2 + kT - 1) / kT, h->PS), gu((h->ldB / 2 + kT - 1) / kT, h->YS);
+  if (rev_launch(k_price, gp, kT, h->stream, v) || rev_launch(k_rc, dim3((n + kT - 1) / kT), kT, h->stream, v) ||
+      rev_launch(k_enter, dim3(1), 1024, h->stream, v) || rev_launch(k_dir, dim3(h->sms * 8), kT, h->stream, v))
+    return fail(LPR_E_CUDA, "revised simplex kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  // pre-pivot x_B (k_ratio does not change it, but the snapshot pass overwrites it with the post-pivot one)
+  lpr_rev::Trace& tr = h->trace;
+  tr.valid = false;
+  tr.u_pre.assign(m, 0.0);
+  tr.xb_pre.assign(m, 0.0);
+  LPR_CUDA(cudaMemcpyAsync(tr.xb_pre.data(), h->xB, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+  if (rev_launch(k_ratio, dim3(1), 1024, h->stream, v))
+    return fail(LPR_E_CUDA, "revised simplex kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  LPR_CUDA(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(RevState), cudaMemcpyDeviceToHost, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  const RevState st = h->st_host[0];
+  if (status) *status = st.status;
+  if (enter) *enter = st.enter;
+  if (leave_row) *leave_row = st.status == LPR_RUNNING ? st.leave_row : -1;
+  if (leave_var) *leave_var = st.status == LPR_RUNNING ? st.leave_var : -1;
+  if (st.status == LPR_RUNNING && st.do_update) {
+    const int e = st.enter;
+    LPR_CUDA(cudaMemcpyAsync(tr.u_pre.data(), h->u, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    double t = 0.0;  // reduced cost of the entering variable BEFORE the pivot: rc_e, or -y_k for slack k (:185-187)
+    LPR_CUDA(cudaMemcpyAsync(&t, e < n ? h->rc + e : h->y + (e - n), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
+    tr.rc_enter_pre = e < n ? t : -t;
+    if (rev_launch(k_update, gu, kT, h->stream, v) || rev_launch(k_y, dim3((m + kT - 1) / kT), kT, h->stream, v))
+      return fail(LPR_E_CUDA, "revised simplex kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
+    tr.valid = true;
+    tr.optimal = false;
+    tr.iteration = st.iter;  // already advanced: "Iteration {iteration + 1}" (:231)
+    tr.enter = e;
+    tr.leave_row = st.leave_row;
+    tr.leave_var = st.leave_var;
+  } else if (st.status == LPR_OPTIMAL) {
+    k_rev_solution<<<1, 1024, 0, h->stream>>>(v, h->c_orig, h->x, h->z);
+    LPR_LAUNCH_CHECK();
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
+    tr.valid = true;
+    tr.optimal = true;
+    tr.iteration = st.iter;
+    tr.enter = tr.leave_row = tr.leave_var = -1;
+    h->solved = true;
+    h->stepping = false;
+  } else {
+    h->stepping = false;
+  }
+  return LPR_OK;
+}
+
+}  // extern "C"
+namespace lpr {
+void format_revised_snapshot(std::string& sb, const char* title, bool is_min, int m, int n, const double* y,
+                             const double* rcX, const double* rcS, int entering, double rc_pre, const double* u_pre,
+                             const double* ratios_pre, const int* basis_pre, int leave_row, int leave_var_pre,
+                             double z_working, double z_original, const double* BinvA, int64_t ldBA,
+                             const double* Binv, int64_t ldB, const double* xB, const int* basis_post);
+std::string& thread_text();
+}
+extern "C" {
+
+// CaptureSnapshot (:294-387) for the step lpr_rev_step has just made: post-pivot duals / reduced costs / B^-1 A | B^-1 |
+// RHS table beside the pre-pivot direction and ratio test.  Everything O(m n) and larger is computed HERE, on demand
+// (the reference pays MultiplyMatrices(B^-1, A) = O(m^2 n) on every iteration whether or not anybody reads the text).
+int lpr_rev_format_snapshot(lpr_rev* h, const char** text, int64_t* len) {
+  if (!h || !text) return fail(LPR_E_BADARG, "null argument");
+  lpr_rev::Trace& tr = h->trace;
+  if (!tr.valid) return fail(LPR_E_STATE, "no step to describe: call lpr_rev_step first");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  const int m = h->m, n = h->n;
+  if ((double)m * ((double)n + m) > 2.7e8) return fail(LPR_E_CAPACITY, "snapshot of a %d x %d model is too large to print", m, n);
+  RevView v = h->view();
+  dim3 gp((h->ldA / 2 + kT - 1) / kT, h->PS);
+  if (!tr.optimal) {  // post-pivot x_B and reduced costs (:218-227); at the optimum the current ones are the post ones
+    k_xb_only<<<h->sms * 8, kT, 0, h->stream>>>(v);
+    LPR_LAUNCH_CHECK();
+    if (rev_launch(k_price, gp, kT, h->stream, v) || rev_launch(k_rc, dim3((n + kT - 1) / kT), kT, h->stream, v))
+      return fail(LPR_E_CUDA, "snapshot kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  double* d_ba = nullptr;
+  LPR_CUDA(cudaMalloc(&d_ba, sizeof(double) * (size_t)m * n));
+  k_binv_a<<<dim3((n + 255) / 256, m), 256, 0, h->stream>>>(v, d_ba, n);
+  count_launch();
+  std::vector<double> y(m), rcx(n), xb(m), cb(m), corig(n), ba((size_t)m * n), binv((size_t)m * m), ratios(m);
+  std::vector<int> basis(m), basis_pre(m);
+  cudaError_t e = cudaMemcpyAsync(ba.data(), d_ba, sizeof(double) * (size_t)m * n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(y.data(), h->y, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rcx.data(), h->rc, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(xb.data(), h->xB, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cb.data(), h->cB, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(corig.data(), h->c_orig, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(basis.data(), h->basis, sizeof(int) * m, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(binv.data(), sizeof(double) * m, h->Binv, sizeof(double) * h->ldB, sizeof(double) * m, m,
+                          cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_ba);
+  if (e != cudaSuccess) return fail(LPR_E_CUDA, "snapshot readback failed: %s", cudaGetErrorString(e));
+  double zw = 0.0;  // Dot(cB, xB) :247 / :143, sequential like :443-448
+  for (int i = 0; i < m; i++) zw += cb[i] * xb[i];
+  std::vector<double> x(n, 0.0);  // ComputeOriginalZFromCurrentBasis :253-262
+  for (int i = 0; i < m; i++)
+    if (basis[i] < n) x[basis[i]] = (0.0 > xb[i]) ? 0.0 : xb[i];
+  double zo = 0.0;
+  for (int j = 0; j < n; j++) zo += corig[j] * x[j];
+  basis_pre = basis;
+  if (!tr.optimal) {
+    basis_pre[tr.leave_row] = tr.leave_var;
+    for (int i = 0; i < m; i++)  // :159-175
+      ratios[i] = tr.u_pre[i] > 1e-9 ? tr.xb_pre[i] / tr.u_pre[i] : __builtin_huge_val();
+  }
+  std::string& sb = thread_text();
+  sb.clear();
+  const std::string title = tr.optimal ? std::string("Optimal") : "Iteration " + std::to_string(tr.iteration);
+  format_revised_snapshot(sb, title.c_str(), h->is_min, m, n, y.data(), rcx.data(), nullptr, tr.optimal ? -1 : tr.enter,
+                          tr.rc_enter_pre, tr.u_pre.data(), ratios.data(), basis_pre.data(), tr.leave_row, tr.leave_var,
+                          zw, zo, ba.data(), n, binv.data(), m, xb.data(), basis.data());
+  *text = sb.c_str();
+  if (len) *len = (int64_t)sb.size();
   return LPR_OK;
 }
 

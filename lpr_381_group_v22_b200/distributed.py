@@ -141,9 +141,9 @@ class KnapPool:
         N.check(N.lib().lpr_knap_open_count(self._h, C.byref(n)))
         return n.value
 
-    def run(self, max_nodes):
+    def run(self, max_nodes, max_seconds=0.0):
         done, st = C.c_int64(), C.c_int()
-        N.check(N.lib().lpr_knap_run(self._h, max_nodes, C.byref(done), C.byref(st)))
+        N.check(N.lib().lpr_knap_run_timed(self._h, max_nodes, float(max_seconds), C.byref(done), C.byref(st)))
         return done.value
 
     def get_incumbent(self):

@@ -35,16 +35,36 @@ def _solve_bb(tableau, n_vars, enable_pruning, max_nodes, device=0, log_cap=4096
                 node_log=nlog[:k].copy(), node_z=nz[:k].copy())
 
 
+def solve_bb_mgpu(tableau, n_vars, enable_pruning=True, n_gpus=1, max_nodes=-1, max_rounds=-1, slice_seconds=0.0,
+                  devices=None):
+    """lpr_bb_solve_mgpu: the open-node pool partitioned over `n_gpus` devices INSIDE the library (host threads +
+    NCCL, csrc/multi_gpu.cu); this is what a single-process caller like the reference's Program.cs can reach."""
+    T = N.f64(tableau)
+    R, Cc = T.shape
+    x = np.zeros(n_vars)
+    z, has, nodes, piv, st = C.c_double(), C.c_int(), C.c_int64(), C.c_int64(), C.c_int()
+    stats = N.MgpuStats()
+    dev = N.i32(devices) if devices is not None else None
+    N.check(N.lib().lpr_bb_solve_mgpu(n_gpus, N.pi(dev), R, Cc, N.pd(T), n_vars, int(bool(enable_pruning)), max_nodes,
+                                      max_rounds, float(slice_seconds), N.pd(x), C.byref(z), C.byref(has),
+                                      C.byref(nodes), C.byref(piv), C.byref(st), C.byref(stats)))
+    return dict(x=x, z=z.value, has_solution=bool(has.value), nodes=nodes.value, pivots=piv.value, status=st.value,
+                stats=stats.as_dict())
+
+
 class BranchAndBoundAdapter:
     """BranchAndBoundAdapter.SolveFromPrimal (BranchAndBoundAdapter.cs:9-24)."""
 
     @staticmethod
-    def SolveFromPrimal(primal, enablePruning=False, isMin=False, max_nodes=20, device=0):
+    def SolveFromPrimal(primal, enablePruning=False, isMin=False, max_nodes=20, device=0, n_gpus=1):
         if primal.FinalTableau is None:
             raise InvalidOperationException("Primal simplex has not been solved yet.")
         final = primal.FinalTableau
         n = len(primal.SolutionVector) if primal.SolutionVector is not None else max(1, final.shape[1] - 1)
-        r = _solve_bb(final, n, enablePruning, max_nodes, device)  # isMin is ignored by the reference (Q9)
+        if n_gpus > 1:  # throughput mode: the pool partitioned over the box's GPUs (not the reference's 20-node order)
+            r = solve_bb_mgpu(final, n, enablePruning, n_gpus, max_nodes)
+        else:
+            r = _solve_bb(final, n, enablePruning, max_nodes, device)  # isMin is ignored by the reference (Q9)
         x = list(r["x"]) if r["has_solution"] else []
         z = r["z"] if r["has_solution"] else float("-inf")
         BranchAndBoundAdapter.LastRun = r
@@ -198,12 +218,14 @@ class KnapsackBranchBoundSimplex:
     """Contract from Program.cs:444-463: ctor(capacity, double[] weights, double[] values), Solve() -> best
     value, PrintIterations(), GetSelectedItemsOriginal() -> items with Id (0-based), Value, Weight."""
 
-    def __init__(self, capacity, weights, values, device=0, max_nodes=-1):
+    def __init__(self, capacity, weights, values, device=0, max_nodes=-1, n_gpus=1):
         self.capacity = float(capacity)
         self.weights = N.f64(weights)
         self.values = N.f64(values)
         self._device = device
         self._max_nodes = max_nodes
+        self._n_gpus = n_gpus
+        self.mgpu_stats = None
         self.chosen = None
         self.best = None
         self.nodes = 0
@@ -215,9 +237,17 @@ class KnapsackBranchBoundSimplex:
         chosen = np.zeros(n, dtype=np.uint8)
         nodes = C.c_int64()
         st = C.c_int()
-        N.check(N.lib().lpr_knap_solve(self._device, self.capacity, n, N.pd(self.weights), N.pd(self.values),
-                                       self._max_nodes, C.byref(best), chosen.ctypes.data_as(N.bp), C.byref(nodes),
-                                       C.byref(st)))
+        if self._n_gpus > 1:  # node pool partitioned over the box's GPUs inside the library (csrc/multi_gpu.cu)
+            stats = N.MgpuStats()
+            N.check(N.lib().lpr_knap_solve_mgpu(self._n_gpus, None, self.capacity, n, N.pd(self.weights),
+                                                N.pd(self.values), self._max_nodes, -1, 0.0, C.byref(best),
+                                                chosen.ctypes.data_as(N.bp), C.byref(nodes), C.byref(st),
+                                                C.byref(stats)))
+            self.mgpu_stats = stats.as_dict()
+        else:
+            N.check(N.lib().lpr_knap_solve(self._device, self.capacity, n, N.pd(self.weights), N.pd(self.values),
+                                           self._max_nodes, C.byref(best), chosen.ctypes.data_as(N.bp),
+                                           C.byref(nodes), C.byref(st)))
         self.best, self.chosen, self.nodes, self.status = best.value, chosen, nodes.value, st.value
         return self.best
 

@@ -59,9 +59,10 @@ class PrimalSimplexSolver:
         return f"x{col + 1}" if col < self.numVariables else f"t{col - self.numVariables + 1}"
 
     def _solution_summary(self, title="Optimal solution"):  # :256-267
-        lines = [title + ":", f"Z = {self.FinalZ:.6f}"]
+        # {v:F6} with the .NET Framework rules (15 significant digits, half away from zero, no "-0.000000"): native
+        lines = [title + ":", "Z = " + NumFormat.Fixed(self.FinalZ, 6)]
         if self.SolutionVector is not None:
-            lines += [f"x{i + 1} = {self.SolutionVector[i]:.6f}" for i in range(self.numVariables)]
+            lines += [f"x{i + 1} = " + NumFormat.Fixed(self.SolutionVector[i], 6) for i in range(self.numVariables)]
         return "\r\n".join(lines) + "\r\n"
 
     # -- Solve :102-150 ---------------------------------------------------------------------------
@@ -220,7 +221,7 @@ class RevisedPrimalSimplexSolver:
     Relation is ignored (every row is <=, :55-61).  Infeasible / unbounded / tiny pivot raise the
     reference's Exception messages (:91, :179, :267)."""
 
-    def __init__(self, objective, constraints, isMinimization, device=0, refactor_every=0, max_iter=-1):
+    def __init__(self, objective, constraints, isMinimization, device=0, refactor_every=0, max_iter=-1, trace=None):
         if objective is None or len(objective) == 0:
             raise ValueError("Objective cannot be null or empty.")
         if constraints is None or len(constraints) == 0:
@@ -240,6 +241,9 @@ class RevisedPrimalSimplexSolver:
         self._h = h
         self._refactor_every = refactor_every
         self._max_iter = max_iter
+        # one CaptureSnapshot text block per iteration like the reference (:226-246), below the size threshold of
+        # SURVEY 8b "Snapshots" unless forced; above it Solve() runs entirely on the device and records no text
+        self._trace = (m * (n + m + 1) <= TRACE_MAX_ELEMENTS) if trace is None else bool(trace)
         self.IterationSnapshots = []
         self.FinalZ = 0.0
         self.SolutionVector = []
@@ -257,32 +261,58 @@ class RevisedPrimalSimplexSolver:
         except Exception:
             pass
 
+    def _raise_for(self, status):
+        if status == N.INFEASIBLE:
+            raise Exception("Infeasible basis (negative basic value).")  # :91
+        if status == N.UNBOUNDED:
+            raise Exception("Unbounded problem (no positive component in direction).")  # :179
+        if status == N.PIVOT_TOO_SMALL:
+            raise Exception("Pivot too small.")  # :267
+
+    def _snapshot(self):
+        text, ln = N.vp(), C.c_int64()
+        N.check(N.lib().lpr_rev_format_snapshot(self._h, C.byref(text), C.byref(ln)))
+        return C.string_at(text.value, ln.value).decode("utf-8")
+
     def Solve(self):
-        st = C.c_int()
-        nit = C.c_int64()
-        cap = 1 << 16
-        log = np.zeros((cap, 3), dtype=np.int32)
-        N.check(N.lib().lpr_rev_solve(self._h, self._max_iter, self._refactor_every, C.byref(st), C.byref(nit),
+        lib = N.lib()
+        if self._trace:  # one iteration per call, one CaptureSnapshot text per iteration plus the "Optimal" block
+            N.check(lib.lpr_rev_begin(self._h))
+            self.PivotLog = []
+            st, e, lr, lv = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            while True:
+                if 0 <= self._max_iter <= len(self.PivotLog):
+                    st.value = N.ITER_LIMIT
+                    break
+                N.check(lib.lpr_rev_step(self._h, C.byref(st), C.byref(e), C.byref(lr), C.byref(lv)))
+                if st.value != N.RUNNING:
+                    break
+                self.PivotLog.append((lr.value, e.value, lv.value))
+                self.IterationSnapshots.append(self._snapshot())
+                if self._refactor_every > 0 and len(self.PivotLog) % self._refactor_every == 0:
+                    N.check(lib.lpr_rev_refactor(self._h))
+            self.Status = st.value
+            self.Iterations = len(self.PivotLog)
+            self._raise_for(st.value)
+            if st.value == N.OPTIMAL:
+                self.IterationSnapshots.append(self._snapshot())
+        else:
+            st = C.c_int()
+            nit = C.c_int64()
+            cap = 1 << 16
+            log = np.zeros((cap, 3), dtype=np.int32)
+            N.check(lib.lpr_rev_solve(self._h, self._max_iter, self._refactor_every, C.byref(st), C.byref(nit),
                                       N.pi(log), cap))
-        self.Status = st.value
-        self.Iterations = nit.value
-        self.PivotLog = [tuple(x) for x in log[:min(nit.value, cap)].tolist()]
-        if st.value == N.INFEASIBLE:
-            raise Exception("Infeasible basis (negative basic value).")
-        if st.value == N.UNBOUNDED:
-            raise Exception("Unbounded problem (no positive component in direction).")
-        if st.value == N.PIVOT_TOO_SMALL:
-            raise Exception("Pivot too small.")
+            self.Status = st.value
+            self.Iterations = nit.value
+            self.PivotLog = [tuple(x) for x in log[:min(nit.value, cap)].tolist()]
+            self._raise_for(st.value)
         x = np.zeros(self.numVariables)
         z = C.c_double()
-        N.check(N.lib().lpr_rev_read_x(self._h, N.pd(x)))
-        N.check(N.lib().lpr_rev_read_z(self._h, C.byref(z)))
+        N.check(lib.lpr_rev_read_x(self._h, N.pd(x)))
+        N.check(lib.lpr_rev_read_z(self._h, C.byref(z)))
         self.SolutionVector = list(x)
         self.FinalZ = z.value
-        self.IterationSnapshots.append(
-            "Optimal\r\nDual prices (y = c_B^T B^{-1}):\r\n" + "\t".join(NumFormat.N3(v) for v in self.DualPrices)
-            + f"\r\nOriginal objective Z_original ({'MIN' if self.isMinimization else 'MAX'}): "
-            + NumFormat.N3(self.FinalZ) + "\r\n")
 
     @property
     def BasicVariables(self):

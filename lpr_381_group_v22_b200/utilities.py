@@ -54,3 +54,10 @@ class NumFormat:
     @staticmethod
     def N3(x):
         return _fmt(N.lib().lpr_fmt_n3, x)
+
+    @staticmethod
+    def Fixed(x, decimals):
+        """$"{x:F<decimals>}" of the .NET Framework (lpr_fmt_fixed)"""
+        buf = C.create_string_buffer(400)
+        N.check(N.lib().lpr_fmt_fixed(float(x), int(decimals), buf, 400))
+        return buf.value.decode("ascii")

@@ -1282,6 +1282,27 @@ double orc_knap_dp(int capacity, int n, const int* w, const int* v, uint8_t* cho
   return (double)D(n, capacity);
 }
 
+/* The same DP, value only, two rolling rows: O(capacity) memory, so that the arbiter of Program.cs:467-470 can
+ * also be run at BASELINE cfg4's size (n = 10^4, capacity ~ 2.5e6: the full table above would need 200 GB). */
+double orc_knap_dp_value(int capacity, int n, const int* w, const int* v) {
+  if (capacity < 0) capacity = 0;
+  std::vector<int64_t> prev((size_t)capacity + 1, 0), next((size_t)capacity + 1, 0);
+  for (int i = 0; i < n; i++) {
+    const int wi = w[i];
+    const int64_t vi = v[i];
+    const int64_t* p = prev.data();
+    int64_t* q = next.data();
+    const int lim = wi <= capacity ? wi : capacity + 1;
+    for (int cc = 0; cc < lim; cc++) q[cc] = p[cc];
+    for (int cc = wi; cc <= capacity; cc++) {
+      const int64_t a = p[cc], t = p[cc - wi] + vi;
+      q[cc] = t > a ? t : a;
+    }
+    prev.swap(next);
+  }
+  return (double)prev[capacity];
+}
+
 /* KnapsackBranchBoundSimplex (Program.cs:444-463 is the only contract).  Specification used
  * by this build (DESIGN.md "Knapsack B&B"): rank items by value/weight descending (ties:
  * lower original id); a node fixes some items to 0/1; its relaxation fills the free items

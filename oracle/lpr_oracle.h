@@ -155,6 +155,8 @@ int orc_rev_solve(int m, int n, const double* A, const double* b, const double* 
 /* ---- Knapsack (Program.cs:430-471; bodies missing in the reference => spec in DESIGN.md) - */
 /* DP arbiter: KnapsackBranchBoundSolver.Solve(int,int[],int[]) */
 double orc_knap_dp(int capacity, int n, const int* weights, const int* values, uint8_t* chosen);
+/* value only, O(capacity) memory (cfg4 size) */
+double orc_knap_dp_value(int capacity, int n, const int* weights, const int* values);
 /* B&B: ratio-ranked fractional bound, branch on the fractional item x=0 then x=1, DFS,
  * strict-improvement incumbent.  chosen[i] over ORIGINAL ids. */
 double orc_knap_bb(double capacity, int n, const double* weights, const double* values,

@@ -180,3 +180,134 @@ def snapshots_only_text(solver, snapshots, final_z, x, ts):
         for sn in snapshots:
             s += sn + "\r\n" + ("" if sn.endswith("\n") else "\r\n")
     return s + _final(final_z, x)
+
+
+# ---- RevisedPrimalSimplexSolver.Solve + CaptureSnapshot (Simplex/RevisedPrimalSimplexSolver.cs:82-387), restated loop
+# for loop in plain Python (sequential sums like :398-448) -- the checker of lpr_rev_step / lpr_rev_format_snapshot.
+def revised_solve_with_snapshots(objective, A, b, is_min=False, max_iter=10_000):
+    """returns (snapshots, pivot_log[(leaveRow, enter, leaveVar)], x, finalZ, basis); raises Exception with the
+    reference's messages"""
+    EPS = 1e-9
+    n, m = len(objective), len(A)
+    c_orig = [float(v) for v in objective]
+    c = [-v if is_min else v for v in c_orig]                                    # :51
+    A = [[float(v) for v in row[:n]] for row in A]
+    b = [float(v) for v in b]
+    Binv = [[1.0 if i == j else 0.0 for j in range(m)] for i in range(m)]
+    basis = [n + i for i in range(m)]
+    nonbasic = list(range(n))
+    cB = [0.0] * m
+
+    def dot(u, v):
+        s = 0.0
+        for x, y in zip(u, v):
+            s += x * y
+        return s
+
+    def matvec(M, v):
+        return [dot(row, v) for row in M]
+
+    def vecmat(v, M):
+        return [dot(v, [M[i][j] for i in range(len(M))]) for j in range(len(M[0]))]
+
+    def matmul(X, Y):                                                            # :426-441
+        R = [[0.0] * len(Y[0]) for _ in X]
+        for i in range(len(X)):
+            for k in range(len(Y)):
+                a = X[i][k]
+                if abs(a) < EPS:
+                    continue
+                for j in range(len(Y[0])):
+                    R[i][j] += a * Y[k][j]
+        return R
+
+    def label(idx):
+        return f"x{idx + 1}" if idx < n else f"S{idx - n + 1}"
+
+    def z_original(xB):
+        x = [0.0] * n
+        for i in range(m):
+            if basis[i] < n:
+                x[basis[i]] = max(0.0, xB[i])
+        return dot(c_orig, x), x
+
+    def capture(title, xB, y, rcX, rcS, enter, rc_pre, u_pre, ratios, basis_pre, leave_row, leave_var_pre, zw, zo):
+        L = [title, "Current Tableau (Revised Simplex)",
+             "Problem type: " + ("MIN (solving by MAX of -c)" if is_min else "MAX"), "",
+             "Dual prices (y = c_B^T B^{-1}):", "\t".join(N3(v) for v in y), "",
+             "Reduced costs:", "  x: " + "\t".join(N3(v) for v in rcX), "  s: " + "\t".join(N3(v) for v in rcS), ""]
+        if enter >= 0:
+            L += [f"Entering variable (chosen pre-pivot): {label(enter)}  (reduced cost pre = {N3(rc_pre)})",
+                  "Direction u = B^{-1} a_enter (pre-pivot):", "\t".join(N3(v) for v in u_pre), "",
+                  "Ratio test (xB_i / u_i; ∞ if u_i ≤ 0)  [labels = pre-pivot basis]:"]
+            for i in range(m):
+                L.append(f"{label(basis_pre[i])}: " + ("∞" if ratios[i] == float("inf") else N3(ratios[i])))
+            if leave_row >= 0 and leave_var_pre >= 0:
+                L += [f"Pivot (pre→post): {label(leave_var_pre)}  →  {label(enter)}    (pivot = {N3(u_pre[leave_row])})", ""]
+        L += [f"Working objective Z_working (maxified): {N3(zw)}",
+              f"Original objective Z_original ({'MIN' if is_min else 'MAX'}): {N3(zo)}", ""]
+        BA = matmul(Binv, A)
+        L.append("Table\t" + "".join(f"x{j + 1}\t" for j in range(n)) + "".join(f"S{j + 1}\t" for j in range(m)) + "RHS")
+        L.append("Z~\t" + "".join(N3(v) + "\t" for v in rcX) + "".join(N3(v) + "\t" for v in rcS) + N3(zw))
+        for i in range(m):
+            L.append(label(basis[i]) + "\t" + "".join(N3(v) + "\t" for v in BA[i]) + "".join(N3(v) + "\t" for v in Binv[i])
+                     + N3(xB[i]))
+        L.append("Basic Variables: " + ", ".join(label(v) for v in basis))
+        return "\r\n".join(L) + "\r\n"
+
+    snaps, log = [], []
+    it = 0
+    while True:
+        xB = matvec(Binv, b)
+        if any(v < -EPS for v in xB):
+            raise Exception("Infeasible basis (negative basic value).")
+        y = vecmat(cB, Binv)
+        rcX = [c[j] - dot(y, [A[i][j] for i in range(m)]) for j in range(n)]
+        rcS = [-y[k] for k in range(m)]
+        enter, best = -1, float("-inf")
+        for v in sorted(nonbasic):
+            rc = rcX[v] if v < n else rcS[v - n]
+            if rc > EPS and (enter == -1 or rc > best + EPS or (abs(rc - best) <= EPS and v < enter)):
+                best, enter = rc, v
+        if enter == -1:
+            zo, x = z_original(xB)
+            snaps.append(capture("Optimal", xB, y, rcX, rcS, -1, 0.0, [0.0] * m, [float("inf")] * m, list(basis), -1, -1,
+                                 dot(cB, xB), zo))
+            return snaps, log, x, zo, list(basis)
+        if it >= max_iter:
+            raise RuntimeError("iteration cap of the restatement")
+        u = matvec(Binv, [A[i][enter] for i in range(m)]) if enter < n else [Binv[i][enter - n] for i in range(m)]
+        leave, best_ratio, ratios = -1, 1.7976931348623157e308, [0.0] * m
+        for i in range(m):
+            if u[i] > EPS:
+                ratios[i] = xB[i] / u[i]
+                if ratios[i] < best_ratio - EPS or (abs(ratios[i] - best_ratio) <= EPS and
+                                                    (leave == -1 or basis[i] < basis[leave])):
+                    best_ratio, leave = ratios[i], i
+            else:
+                ratios[i] = float("inf")
+        if leave == -1:
+            raise Exception("Unbounded problem (no positive component in direction).")
+        leave_var = basis[leave]
+        basis_pre = list(basis)
+        rc_pre = rcX[enter] if enter < n else rcS[enter - n]
+        basis[leave] = enter
+        nonbasic.remove(enter)
+        if leave_var not in nonbasic:
+            nonbasic.append(leave_var)
+        cB[leave] = c[enter] if enter < n else 0.0
+        pivot = u[leave]
+        if abs(pivot) < EPS:
+            raise Exception("Pivot too small.")
+        E = [[1.0 if i == j else 0.0 for j in range(m)] for i in range(m)]
+        for i in range(m):
+            E[i][leave] = 1.0 / pivot if i == leave else -u[i] / pivot
+        Binv = matmul(E, Binv)
+        xB = matvec(Binv, b)
+        y2 = vecmat(cB, Binv)
+        rcX2 = [c[j] - dot(y2, [A[i][j] for i in range(m)]) for j in range(n)]
+        rcS2 = [-v for v in y2]
+        log.append((leave, enter, leave_var))
+        snaps.append(capture(f"Iteration {it + 1}", xB, y2, rcX2, rcS2, enter, rc_pre, u, ratios, basis_pre, leave,
+                             leave_var, dot(cB, xB), z_original(xB)[0]))
+        it += 1

@@ -45,6 +45,7 @@ def lib():
             getattr(_lib, f).restype = C.c_double
             getattr(_lib, f).argtypes = [C.c_double]
         _lib.orc_knap_dp.restype = C.c_double
+        _lib.orc_knap_dp_value.restype = C.c_double
         _lib.orc_knap_bb.restype = C.c_double
         _lib.orc_knap_bb.argtypes = [C.c_double, C.c_int, _dp, _dp, C.c_int64, _bp, _lp, _ip]
         _lib.orc_gen_dense_lp.argtypes = [C.c_uint64, C.c_int, C.c_int, _dp, _dp, _dp]
@@ -293,6 +294,12 @@ def knap_dp(capacity, weights, values):
     ch = np.zeros(len(w), dtype=np.uint8)
     best = lib().orc_knap_dp(int(capacity), len(w), _i(w), _i(v), ch.ctypes.data_as(_bp))
     return best, ch
+
+
+def knap_dp_value(capacity, weights, values):
+    """value-only DP with O(capacity) memory: the arbiter at BASELINE cfg4's size"""
+    w = np.ascontiguousarray(weights, dtype=np.int32); v = np.ascontiguousarray(values, dtype=np.int32)
+    return lib().orc_knap_dp_value(int(capacity), len(w), _i(w), _i(v))
 
 
 def knap_bb(capacity, weights, values, max_nodes=-1):

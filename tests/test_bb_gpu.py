@@ -311,3 +311,74 @@ def test_formulate_and_run_branch_and_bound(m, n, seed):
         assert x is None
     if m == 1:
         assert x == [0, 1, 1, 1, 0, 1] and z == 15.0
+
+
+def binary_ip_final(seed, m, n, div):
+    """cfg5-family instance that terminates under the reference's semantics: the cfg5 generator's A and c, b = floor(row
+    sum / div), plus one `x_j <= 1` row per variable (what menu option 3 appends, Program.cs:372-382)."""
+    A, b, c = O.gen_dense_ip(seed, m, n)
+    b = np.floor(A.sum(axis=1) / div)
+    cons = [(A[i], "<=", b[i]) for i in range(m)] + [(np.eye(n)[j], "<=", 1.0) for j in range(n)]
+    T0, b0 = O.primal_build(list(c), cons)
+    lp = O.primal_solve(T0, b0)
+    assert lp["status"] == O.OPTIMAL
+    return lp["T"]
+
+
+MID = [(31, 8, 24, 3.0), (32, 8, 26, 3.0), (42, 6, 32, 2.0), (43, 6, 30, 3.0)]  # 33..39 rows, 279 .. 1665 oracle nodes
+
+
+@pytest.mark.parametrize("seed,m,n,div", MID)
+def test_bb_pool_batch64_equals_sequential_oracle_mid_size(seed, m, n, div):
+    """The batched pool the bench runs (64 nodes = 128 children per batch, pruning on) against the sequential oracle
+    on mid-size instances whose trees close (hundreds to thousands of nodes, depth ~ 25): same incumbent, bit for bit."""
+    import ctypes as C
+    from lpr_381_group_v22_b200 import _native as N
+    Tf = binary_ip_final(seed, m, n, div)
+    ref = O.bb_solve(Tf, n, prune=True, max_nodes=-1, log_cap=1 << 16)
+    assert ref["status"] == O.OPTIMAL and ref["has_solution"]
+    h = N.vp()
+    N.check(N.lib().lpr_bb_create(0, Tf.shape[0], Tf.shape[1], N.pd(N.f64(Tf)), n, 1, C.byref(h)))
+    done, piv, left, ovf = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    total = 0
+    while True:
+        N.check(N.lib().lpr_bb_run(h, 1 << 20, C.byref(done), C.byref(piv)))
+        total += done.value
+        N.check(N.lib().lpr_bb_open_count(h, C.byref(left)))
+        if left.value == 0:
+            break
+    N.check(N.lib().lpr_bb_stats(h, None, None, C.byref(ovf), None))
+    has, z, klen = C.c_int(), C.c_double(), C.c_int(0)
+    x = np.zeros(n)
+    N.check(N.lib().lpr_bb_get_incumbent(h, C.byref(has), C.byref(z), N.pd(x), None, C.byref(klen)))
+    N.lib().lpr_bb_destroy(h)
+    assert ovf.value == 0 and has.value == 1
+    assert z.value == ref["z"]
+    assert_bit_equal(x, ref["x"], "incumbent")
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 3])
+def test_bb_solve_mgpu_in_library_matches_oracle(n_gpus):
+    """lpr_bb_solve_mgpu: host threads + NCCL inside the library.  With fewer physical GPUs than ranks the ranks
+    share devices only when NCCL allows it, so on a 1-GPU box the N > 1 cases are skipped."""
+    if n_gpus > L.device_count():
+        pytest.skip("needs %d GPUs" % n_gpus)
+    seed, m, n, div = MID[2]
+    Tf = binary_ip_final(seed, m, n, div)
+    ref = O.bb_solve(Tf, n, prune=True, max_nodes=-1, log_cap=1 << 16)
+    r = L.solve_bb_mgpu(Tf, n, True, n_gpus=n_gpus, slice_seconds=2e-3)
+    assert r["status"] == L.OPTIMAL and r["has_solution"] and r["stats"]["open_left"] == 0
+    assert r["z"] == ref["z"]
+    assert_bit_equal(r["x"], ref["x"], "incumbent")
+    assert r["stats"]["n_gpus"] == n_gpus and (n_gpus == 1 or r["stats"]["nccl_version"] > 0)
+
+
+def test_bb_depth_overflow_is_reported(monkeypatch):
+    """A subtree cut at the slab depth headroom must not come back as OPTIMAL."""
+    monkeypatch.setenv("LPR_BB_MAX_DEPTH", "3")
+    seed, m, n, div = MID[0]
+    Tf = binary_ip_final(seed, m, n, div)
+    bb = L.BranchBoundSimplexSolver.BranchAndBound()
+    bb.SetNumVars(n)
+    bb.ExecuteBranchAndBound([Tf], True, max_nodes=-1)
+    assert bb.LastRun["status"] == L.DEPTH_LIMIT

@@ -127,6 +127,21 @@ def test_f3_against_independent_restatement():
         assert F3(x) == R.F3(x), x
 
 
+def test_fixed_f6_of_the_optimal_summary():
+    """{v:F6} of PrimalSimplexSolver.cs:256-267 through lpr_fmt_fixed (Python's :.6f prints "-0.000000" for
+    a negative that rounds to zero and rounds half to even on the binary value)."""
+    from lpr_381_group_v22_b200.utilities import NumFormat
+    known = {-1e-17: "0.000000", -0.0: "0.000000", 0.0000005: "0.000001", -0.0000005: "-0.000001", 15.4: "15.400000",
+             2.0000005: "2.000001", 1.0000015: "1.000002", 0.1234565: "0.123457", 9.0: "9.000000", -4.9e-7: "0.000000"}
+    for x, t in known.items():
+        assert NumFormat.Fixed(x, 6) == t, (x, NumFormat.Fixed(x, 6), t)
+    rng = np.random.default_rng(12)
+    xs = np.concatenate([rng.normal(size=2000) * 10.0 ** rng.integers(-8, 12, 2000), (rng.integers(-10**8, 10**8, 2000) + 0.5) / 1e6])
+    for x in xs.tolist():
+        assert NumFormat.Fixed(x, 6) == R.net_fixed(x, 6), x
+        assert NumFormat.Fixed(x, 3) == R.F3(x)
+
+
 def test_n3_literal_framework_rounding():
     known = {1e-13: "0", 2.0: "2", 0.125: "0.125", 0.2000000000000001: "0.2", -1.9999999: "-2", 0.0005: "0.001",
              -0.0: "0", 1234.5678: "1234.568", -0.25: "-0.25", 1e15: "1E+15", 123456789012345678.0: "1.23456789012346E+17",

@@ -96,3 +96,65 @@ def test_export_import_roundtrip_keeps_answer():
     # reduce like the multi-GPU driver does: max value, then DFS-first key
     best = max(r[0] for r in results)
     assert best == ref["best"]
+
+
+def test_cfg4_size_matches_oracle_and_dp():
+    """BASELINE cfg4 (n = 10^4 weakly correlated items, seed 384): the reference's own check (Program.cs:467-470,
+    B&B value == DP value within 1e-6) at the benchmark size, with the device DP, the oracle's DP and the oracle's
+    depth-first B&B as arbiters; the selection must be the oracle's, bit for bit."""
+    n, seed = 10000, 384
+    w, v, cap = O.gen_knapsack(seed, n)
+    ref = O.knap_bb(cap, w, v)                                   # ~10 s single thread
+    odp = O.knap_dp_value(int(cap), w.astype(int), v.astype(int))  # ~20 s, O(capacity) memory
+    s = L.KnapsackBranchBoundSimplex(cap, w, v)
+    best = s.Solve()
+    dp, ch = L.KnapsackBranchBoundSolver.Solve(int(cap), w.astype(int), v.astype(int), return_chosen=True)
+    assert abs(best - dp) < 1e-6 and best == ref["best"] == odp == dp
+    assert s.chosen.tolist() == ref["chosen"].tolist()
+    assert float(np.dot(s.chosen, v)) == best and float(np.dot(s.chosen, w)) <= cap
+    assert float(np.dot(ch, v)) == dp and float(np.dot(ch, w)) <= cap
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 4])
+def test_knap_solve_mgpu_in_library(n_gpus):
+    """lpr_knap_solve_mgpu (host threads + NCCL inside the library): value and selection are the oracle's for any
+    GPU count."""
+    if n_gpus > L.device_count():
+        pytest.skip("needs %d GPUs" % n_gpus)
+    w, v, cap = O.gen_knapsack(13, 400)
+    ref = O.knap_bb(cap, w, v)
+    s = L.KnapsackBranchBoundSimplex(cap, w, v, n_gpus=n_gpus)
+    # n_gpus = 1 also goes through the multi-GPU driver here (no NCCL needed)
+    import ctypes as C
+    best, nodes, st = C.c_double(), C.c_int64(), C.c_int()
+    ch = np.zeros(len(w), dtype=np.uint8)
+    stats = N.MgpuStats()
+    N.check(N.lib().lpr_knap_solve_mgpu(n_gpus, None, cap, len(w), N.pd(N.f64(w)), N.pd(N.f64(v)), -1, -1, 1e-3,
+                                        C.byref(best), ch.ctypes.data_as(N.bp), C.byref(nodes), C.byref(st),
+                                        C.byref(stats)))
+    assert st.value == L.OPTIMAL and stats.open_left == 0
+    assert best.value == ref["best"] and ch.tolist() == ref["chosen"].tolist()
+    assert s.Solve() == ref["best"] and s.chosen.tolist() == ref["chosen"].tolist()
+
+
+@pytest.mark.parametrize("batch", [64, 4096])
+def test_node_budget_and_time_slices(batch, monkeypatch):
+    """lpr_knap_run with a node budget stops on the budget (device-side accounting) and continues where it stopped;
+    lpr_knap_run_timed returns between groups of levels; the answer does not depend on where the runs are cut."""
+    monkeypatch.setenv("LPR_KNAP_BATCH", str(batch))
+    w, v, cap = O.gen_knapsack(17, 300)
+    ref = O.knap_bb(cap, w, v)
+    from lpr_381_group_v22_b200.distributed import KnapPool
+    p = KnapPool(cap, w, v)
+    try:
+        assert p.run(100) == 100  # exactly the budget while nodes are left
+        total = 100
+        guard = 0
+        while p.open_count() > 0:
+            total += p.run(1 << 40, max_seconds=1e-4)
+            guard += 1
+            assert guard < 100000
+        inc = p.get_incumbent()
+        assert inc[0] == ref["best"] and inc[2].astype(np.uint8).tolist() == ref["chosen"].tolist()
+    finally:
+        p.close()

@@ -121,3 +121,84 @@ def test_refactorisation_fp64_dmma():
     Bm = np.column_stack([A[:, v] if v < n else np.eye(m)[:, v - n] for v in basis])
     assert np.max(np.abs(Bm @ after - np.eye(m))) <= np.max(np.abs(Bm @ before - np.eye(m))) + 1e-13
     close(s.DualPrices, ref["y"], "y after refresh")
+
+
+@pytest.mark.parametrize("refactor_every", [0, 12])
+def test_cfg3_size_window_matches_oracle(refactor_every):
+    """BASELINE cfg3 shape (m = 8192, n = 16384, seed 384, generated in HBM): the first 32 iterations against the
+    oracle run on the same input -- pivot log exact, z / x / y / x_B within 1e-9 relative -- as shipped and with a
+    refactorisation of B^-1 every 12 iterations (which must not move anything beyond the tolerance)."""
+    import ctypes as C
+    from lpr_381_group_v22_b200 import _native as N
+    m, n, seed, K = 8192, 16384, 384, 32
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    ref = O.rev_solve(A, b, c, False, max_iter=K, log_cap=K)
+    del A
+    assert ref["status"] == O.ITER_LIMIT and ref["n_iter"] == K
+    lib = N.lib()
+    h = N.vp()
+    N.check(lib.lpr_rev_create_dense_lp(0, seed, m, n, C.byref(h)))
+    try:
+        st, nit = C.c_int(), C.c_int64()
+        log = np.zeros((K, 3), dtype=np.int32)
+        N.check(lib.lpr_rev_solve(h, K, refactor_every, C.byref(st), C.byref(nit), N.pi(log), K))
+        assert st.value == L.ITER_LIMIT and nit.value == K
+        assert log.tolist() == ref["log"].tolist()
+        basis = np.zeros(m, dtype=np.int32); x = np.zeros(n); y = np.zeros(m); xb = np.zeros(m); z = C.c_double()
+        N.check(lib.lpr_rev_read_basis(h, N.pi(basis)))
+        N.check(lib.lpr_rev_read_x(h, N.pd(x)))
+        N.check(lib.lpr_rev_read_y(h, N.pd(y)))
+        N.check(lib.lpr_rev_read_xb(h, N.pd(xb)))
+        N.check(lib.lpr_rev_read_z(h, C.byref(z)))
+        assert basis.tolist() == ref["basis"].tolist()
+        close(z.value, ref["z"], "z")
+        close(x, ref["x"], "x")
+        close(y, ref["y"], "y")
+        close(xb, ref["xB"], "xB")
+        if refactor_every:
+            res, fl = C.c_double(), C.c_double()
+            N.check(lib.lpr_rev_last_refactor_info(h, C.byref(res), C.byref(fl)))
+            assert res.value < 1e-9
+    finally:
+        lib.lpr_rev_destroy(h)
+
+
+def _models_for_snapshots():
+    yield "README", [2, 3, 4], [[1, 2, 3], [3, 2, 1.0]], [10, 15], False
+    yield "TextFile", [2, 3, 3, 5, 2, 4], np.vstack([[11, 8, 6, 14, 10, 10], np.eye(6)]).tolist(), [40] + [1] * 6, False
+    A, b, c = O.gen_dense_lp(5, 7, 9)
+    yield "random max", list(c), A.tolist(), list(b), False
+    A, b, c = O.gen_dense_lp(6, 5, 8)
+    yield "random min", list(-c), A.tolist(), list(b), True
+
+
+@pytest.mark.parametrize("case", list(_models_for_snapshots()), ids=lambda c: c[0])
+def test_iteration_snapshots_match_capture_snapshot_restatement(case):
+    """one CaptureSnapshot text block per iteration plus the "Optimal" block
+    (RevisedPrimalSimplexSolver.cs:124-146, :226-246, :294-387) through lpr_rev_begin / lpr_rev_step /
+    lpr_rev_format_snapshot, against the loop-for-loop Python restatement in tests/net_reference.py."""
+    import net_reference as R
+    _, obj, A, b, is_min = case
+    snaps, log, x, z, basis = R.revised_solve_with_snapshots(obj, A, b, is_min)
+    s = L.RevisedPrimalSimplexSolver(list(obj), [L.Constraint(A[i], "<=", b[i]) for i in range(len(A))], is_min, trace=True)
+    s.Solve()
+    assert s.PivotLog == log and s.BasicVariables == basis
+    assert len(s.IterationSnapshots) == len(snaps) == len(log) + 1
+    for k, (mine, ref) in enumerate(zip(s.IterationSnapshots, snaps)):
+        assert mine == ref, f"snapshot {k} differs:\n{mine}\n---\n{ref}"
+    close(s.FinalZ, z, "z")
+    close(s.SolutionVector, x, "x")
+    # the untraced path gives the same numbers and records no text
+    q = L.RevisedPrimalSimplexSolver(list(obj), [L.Constraint(A[i], "<=", b[i]) for i in range(len(A))], is_min, trace=False)
+    q.Solve()
+    assert q.PivotLog == log and q.IterationSnapshots == [] and q.FinalZ == s.FinalZ
+
+
+def test_result_file_of_a_revised_run_matches_restatement(tmp_path):
+    """Program.cs:329-347 -> OutputFileWrite.WriteFullResults with the revised solver's IterationSnapshots."""
+    import net_reference as R
+    obj, A, b = [2, 3, 4], [[1, 2, 3], [3, 2, 1.0]], [10, 15]
+    s = L.RevisedPrimalSimplexSolver(obj, [L.Constraint(A[i], "<=", b[i]) for i in range(2)], False)
+    s.Solve()
+    snaps, _, x, z, _ = R.revised_solve_with_snapshots(obj, A, b, False)
+    assert s.IterationSnapshots == snaps

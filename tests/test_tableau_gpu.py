@@ -319,6 +319,28 @@ def test_full_size_solve_cfg2_plans_agree_and_certify_optimality():
         assert col[i + 1] == 1.0 and np.count_nonzero(col) == 1
 
 
+def test_full_size_solve_cfg2_matches_oracle_digest():
+    """The WHOLE 14 866-pivot cfg2 solve against the oracle: SHA-256 of the pivot log, of the basis and of the final
+    tableau, compared with the digests the threaded CPU oracle produced once (tests/golden/make_cfg2_full_hash.py,
+    ~4 minutes on 8 cores; committed as tests/golden/cfg2_full_solve.json).  Default plan (overlapped delayed updates)."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "cfg2_full_solve.json")) as f:
+        gold = json.load(f)
+    m, n, seed = gold["m"], gold["n"], gold["seed"]
+    with L.DeviceTableau.dense_lp(seed, m, n) as t:
+        r = t.solve(L.RULE_PRIMAL, log_cap=1 << 15)
+        assert r["status"] == L.OPTIMAL and r["n_pivots"] == gold["n_pivots"]
+        log = np.ascontiguousarray(r["log"], dtype=np.int32)
+        assert log[:8].tolist() == gold["first_pivots"] and log[-8:].tolist() == gold["last_pivots"]
+        assert hashlib.sha256(log.tobytes()).hexdigest() == gold["pivot_log_sha256"]
+        assert hashlib.sha256(np.ascontiguousarray(t.basis, dtype=np.int32).tobytes()).hexdigest() == gold["basis_sha256"]
+        T = np.ascontiguousarray(t.read(), dtype=np.float64)
+        assert float(T[0, -1]).hex() == gold["z_hex"]
+        assert hashlib.sha256(T.tobytes()).hexdigest() == gold["final_tableau_sha256"]
+
+
 @pytest.mark.parametrize("seed", range(5))
 def test_sensitivity_resolve_rule(seed):
     """SensitivityAnalyzer.ResolveAll (dual phase then primal re-optimisation, SensitivityAnalyzer.cs:121-201):

@@ -1,0 +1,60 @@
+"""Probe knapsack instance families on the GPU (node counts, nodes/s) -- used to choose the 'cfg4-hard' family of
+bench.py: python tools/knap_probe.py [n_gpus]"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lpr_381_group_v22_b200 import _native as N  # noqa: E402
+from lpr_381_group_v22_b200.bench_workloads import u01  # noqa: E402
+
+
+def family(kind, seed, n, R=1000):
+    idx = np.arange(n, dtype=np.uint64)
+    w = 1.0 + np.floor(R * u01(seed, 0, idx))
+    if kind == "weak":
+        v = np.maximum(1.0, w + np.floor(R / 5 * u01(seed, 1, idx)) - R / 10)
+    elif kind == "strong":
+        v = w + R / 10
+    elif kind == "almost_strong":
+        v = w + R / 10 + np.floor(R / 250 * u01(seed, 1, idx)) - R / 500
+    elif kind == "uncorr":
+        v = 1.0 + np.floor(R * u01(seed, 1, idx))
+    elif kind == "subset":
+        v = w.copy()
+    else:
+        raise ValueError(kind)
+    return w, v, float(np.floor(w.sum() / 2.0))
+
+
+def run(kind, seed, n, n_gpus=1, cap_nodes=200_000_000, R=1000):
+    w, v, cap = family(kind, seed, n, R)
+    best, nodes, st = C.c_double(), C.c_int64(), C.c_int()
+    ch = np.zeros(n, dtype=np.uint8)
+    stats = N.MgpuStats()
+    t = time.perf_counter()
+    N.check(N.lib().lpr_knap_solve_mgpu(n_gpus, None, cap, n, N.pd(w), N.pd(v), cap_nodes, -1, 2e-3, C.byref(best),
+                                        ch.ctypes.data_as(N.bp), C.byref(nodes), C.byref(st), C.byref(stats)))
+    dt = time.perf_counter() - t
+    d = stats.as_dict()
+    print(dict(kind=kind, seed=seed, n=n, R=R, n_gpus=n_gpus, best=best.value, nodes=nodes.value, status=st.value,
+               wall=round(dt, 3), loop_s=round(d["seconds"], 4), mnodes_per_s=round(nodes.value / max(d["seconds"], 1e-9) / 1e6, 2),
+               rounds=d["rounds"], steals=d["steals"], moved=d["nodes_moved"], open_left=d["open_left"],
+               per_gpu=d["nodes_per_gpu"]), flush=True)
+
+
+if __name__ == "__main__":
+    ng = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    os.environ.setdefault("LPR_KNAP_POOL_MB", "16384")
+    for kind, seed, n, R in [("weak", 384, 10000, 1000), ("weak", 384, 10000, 1000), ("weak", 385, 100000, 1000),
+                             ("weak", 386, 10000, 100000), ("uncorr", 387, 10000, 1000), ("almost_strong", 388, 2000, 1000),
+                             ("almost_strong", 388, 10000, 1000), ("strong", 389, 200, 1000), ("strong", 389, 1000, 1000),
+                             ("subset", 390, 1000, 100000)]:
+        try:
+            run(kind, seed, n, ng, R=R)
+        except Exception as ex:
+            print("FAIL", kind, seed, n, repr(ex), flush=True)
