@@ -268,11 +268,10 @@ def main():
         sys.stderr.write(f"[bench] per-kernel timing pass failed: {ex!r}\n")
 
     # -------- e2e: host buffers through the C ABI (rank-local replica) --------------------------
-    import oracle_lib as O  # only to GENERATE the host-side model arrays (same generator as the device one)
-    A, b, c = O.gen_dense_lp(SEED, M, NV)
+    from lpr_381_group_v22_b200 import bench_workloads as W
     Ah, bh, ch = pinned((M, NV)), pinned((M,)), pinned((NV,))
-    Ah[:] = A; bh[:] = b; ch[:] = c
-    del A
+    _, b, c = W.gen_dense_lp(SEED, M, NV, out=Ah)  # the package's own generator, bit identical to the device one
+    bh[:] = b; ch[:] = c
     outT, outx = pinned((R, CC)), pinned((NV,))
     outb = np.zeros(M, dtype=np.int32)
     h2d = 8 * (M * NV + M + NV)
@@ -314,49 +313,54 @@ def main():
     e2e_value = world * e2e_piv / te_max
     assert ze == zval, "e2e and resident solves disagree"
 
-    # -------- cpu baseline: oracle, single thread like the reference, bounded sample (rank 0) ----
+    # -------- from here on rank 0 works alone; the other ranks wait on the rendezvous store (a CPU wait: a NCCL barrier
+    # would park a spinning kernel on their GPUs, which rank 0's in-library multi-GPU legs are about to use) ------------
+    barrier(dist, local)
+    if rank != 0:
+        wait_for_rank0(dist, rank)
+        dist.destroy_process_group()
+        return
+
+    # -------- cpu baseline: oracle, single thread like the reference, bounded sample ------------------------------------
+    import oracle_lib as O  # the checker: cpu_baseline legs only
     cpu = None
-    if rank == 0 and world == 1:
+    if world == 1:
         sample = int(os.environ.get("LPR_CPU_SAMPLE_PIVOTS", "96"))
         T0, b0 = O.primal_build(list(ch), [(Ah[i], "<=", bh[i]) for i in range(M)])
         tc = time.perf_counter()
         r = O.primal_solve(T0, b0, max_pivots=sample, threads=1, log_cap=0)
         dtc = time.perf_counter() - tc
+        del T0, r
         cpu = {"value": sample / dtc, "unit": "pivots/s", "cores": 1, "kind": "port",
                "sample": f"first {sample} pivots of the same cfg2 solve ({dtc:.1f} s); C++ restatement of "
                          "PrimalSimplexSolver.cs:152-211 (no .NET toolchain in the image), single thread like "
                          f"the reference; host has {os.cpu_count()} cores"}
+    del Ah, outT
 
-    # -------- branch & bound node pools (BASELINE configs[4] / configs[3]); partitioned across ranks ----
+    # -------- branch & bound node pools (BASELINE configs[4] / configs[3]) partitioned over the box's GPUs INSIDE the
+    # library: rank 0 calls lpr_bb_solve_mgpu / lpr_knap_solve_mgpu with n_gpus = world (host threads + NCCL) ---------
     bb = knap = None
     if not os.environ.get("LPR_BENCH_SKIP_BB"):
         os.environ.setdefault("LPR_BB_PREALLOC_MB", "126976")  # node slabs carved before the timed region
         os.environ.setdefault("LPR_BB_MAX_DEPTH", "192")        # deep enough for the node budget below
-        from lpr_381_group_v22_b200.bench_workloads import run_bb_cfg5, run_knap_cfg4
         try:
-            # 12 time-sliced rounds of 10 ms (at most 1024 nodes each) per rank, whatever the rank count
-            bb = run_bb_cfg5(512, 1024, 385, dev, dist, int(os.environ.get("LPR_BENCH_BB_NODES", "12288")), 1024,
-                             float(os.environ.get("LPR_BENCH_BB_SLICE_MS", "10")))
-            knap = run_knap_cfg4(10000, 384, dev, dist, 1 << 26, 32768)
+            bb = run_bb_legs(W, O, world, dev)
         except Exception as ex:  # the headline line must still be printed
-            bb = bb or {"error": repr(ex)}
-            knap = knap or {"error": repr(ex)}
-
-    # -------- revised simplex (BASELINE configs[2]): replicas only, reported from rank 0 ----------------------------
-    rev = None
-    if rank == 0 and not os.environ.get("LPR_BENCH_SKIP_REV"):
-        from lpr_381_group_v22_b200.bench_workloads import run_rev_cfg3
+            bb = {"error": repr(ex)}
         try:
-            rev = run_rev_cfg3(8192, 16384, 384, dev)
+            knap = run_knap_legs(W, O, world, dev)
         except Exception as ex:
-            rev = {"error": repr(ex)}
-    if dist is not None:
-        dist.barrier()  # the other ranks stay in the group until rank 0 is done measuring
+            knap = {"error": repr(ex)}
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    # -------- revised simplex (BASELINE configs[2]): replicas only, measured on rank 0 ------------------------------------
+    rev = None
+    if not os.environ.get("LPR_BENCH_SKIP_REV"):
+        try:
+            rev = W.run_rev_cfg3(8192, 16384, 384, dev)
+            rev.update(run_rev_host_legs(W, O, lib, N, C, dev, world))
+        except Exception as ex:
+            rev = dict(rev or {}, error=repr(ex))
+    wait_for_rank0(dist, rank)
 
     per_pivot_us = ms_max * 1e3 / piv_total
     traffic = None
@@ -418,6 +422,8 @@ def main():
                                       "select cluster of the next group running concurrently",
                      "group_period_us": per_pivot_us * KBLK,
                      "traffic": (traffic or {}).get("blocked_dram_bytes_per_launch"),
+                     "traffic_how": "from profile: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture "
+                                    "of this kernel (profiles/sweep_dram_traffic.json), not measured in this run",
                      "note": "bit-identical delayed-update path: every element still goes through the same "
                              "multiply/subtract roundings in the same order, but the tableau is swept once per "
                              f"{KBLK} pivots; pivot_equivalent = 16RC-per-pivot bytes x pivots/s",
@@ -444,9 +450,163 @@ def main():
                           "frac": ach / (peak * world),
                           "note": "algorithmic bytes (two child copies + pivots/node sweeps) x nodes/s over the measured "
                                   "copy bandwidth of the GPUs in use; node tableaux of a batch are partly L2 resident"}
+    # compact multi-GPU record as the LAST key, so that it survives a truncated tail of the line
+    mg = {"n_gpus": world, "how": "node pool partitioned inside the library (lpr_*_solve_mgpu: host threads + NCCL)"}
+    if bb and "nodes_per_s" in bb:
+        mg.update(bb_nodes_per_s=bb["nodes_per_s"], bb_gbs=bb["roofline"]["achieved"], bb_frac=bb["roofline"]["frac"],
+                  bb_bytes_per_node=bb["roofline"]["bytes_per_node"], bb_pivots_per_node=bb["pivots_per_node"])
+        if isinstance(bb.get("closed_instance"), dict):
+            mg.update(bb_closed_nodes=bb["closed_instance"].get("nodes"), bb_closed_z=bb["closed_instance"].get("incumbent_z"),
+                      bb_incumbent_sha=bb["closed_instance"].get("incumbent_sha"),
+                      bb_closed_matches_oracle=bb["closed_instance"].get("matches_oracle"))
+    if knap and "nodes_per_s" in knap:
+        mg.update(knap_nodes_per_s=knap["nodes_per_s"], knap_best=knap["best_value"], knap_selection_sha=knap["selection_sha"],
+                  knap_equals_dp=knap.get("equals_dp"))
+        if isinstance(knap.get("hard"), dict) and "nodes_per_s" in knap["hard"]:
+            mg.update(knap_hard_nodes_per_s=knap["hard"]["nodes_per_s"], knap_hard_nodes=knap["hard"]["nodes"],
+                      knap_hard_best=knap["hard"]["best_value"], knap_hard_selection_sha=knap["hard"]["selection_sha"])
+    line["multi_gpu"] = mg
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def wait_for_rank0(dist, rank):
+    """ranks != 0 block (on the CPU) until rank 0 has finished the legs it runs alone"""
+    if dist is None:
+        return
+    from datetime import timedelta
+    store = dist.distributed_c10d._get_default_store()
+    if rank == 0:
+        store.set("lpr_rank0_done", "1")
+    else:
+        store.wait(["lpr_rank0_done"], timedelta(minutes=60))
+
+
+def run_bb_legs(W, O, world, dev):
+    """cfg5 (m=512, n=1024 dense IP): LP relaxation on the tableau path, Gomory cuts at the root, then branch & bound
+    simplex with reference semantics, pruning on, 12 time slices of 10 ms per GPU whatever the GPU count (weak scaling);
+    plus a cfg5-family instance whose tree CLOSES, for a GPU-count independent incumbent hash checked against the
+    sequential oracle; plus the oracle's nodes/s on the cfg5 root as cpu_baseline."""
+    import numpy as np
+    import lpr_381_group_v22_b200 as L
+    m, n, seed = 512, 1024, 385
+    A, b, c = W.gen_dense_ip(seed, m, n)
+    final, lp, lp_ms = W.lp_relaxation(A, b, c, dev)
+    cuts = None
+    try:
+        with L.DeviceTableau.from_host(final, device=dev, row_cap=final.shape[0] + 40) as tc:
+            tq = time.perf_counter()
+            rc = tc.cutting_plane(max_cuts=32)
+            dq = time.perf_counter() - tq
+            piv = int(rc["log"][:, 2].sum() + rc["log"][:, 3].sum()) + int(rc["n_cuts"])
+            cuts = dict(n_cuts=rc["n_cuts"], status=L.STATUS_NAMES[rc["status"]], seconds=dq,
+                        dual_pivots=int(rc["log"][:, 2].sum()), primal_pivots=int(rc["log"][:, 3].sum()),
+                        us_per_pivot=dq * 1e6 / max(1, piv),
+                        what="host clock around lpr_tab_cutting_plane(max_cuts=32) on the 513x1537 relaxation tableau")
+    except Exception as ex:
+        cuts = {"error": repr(ex)}
+    slices = int(os.environ.get("LPR_BENCH_BB_SLICES", "12"))
+    slice_ms = float(os.environ.get("LPR_BENCH_BB_SLICE_MS", "10"))
+    out = W.bb_mgpu(final, n, world, max_rounds=slices, slice_seconds=slice_ms * 1e-3)
+    out.update(workload=f"cfg5 dense IP m={m} n={n} B&B simplex (root {final.shape[0]}x{final.shape[1]}), "
+                        f"{slices} slices of {slice_ms:g} ms per GPU",
+               lp_relaxation_pivots=lp["n_pivots"], lp_relaxation_ms=lp_ms, root_cuts=cuts,
+               note="reference semantics (4-d.p. rounding, first-row-with-a-1 extraction, SURVEY Q8/Q10): this tree never "
+                    "closes (the rounding keeps re-branching), so throughput is measured on time slices and the "
+                    "GPU-count independent incumbent is demonstrated on closed_instance")
+    # oracle on the same root: sequential ExecuteBranchAndBound, bounded sample
+    k = int(os.environ.get("LPR_CPU_SAMPLE_BB_NODES", "32"))
+    tq = time.perf_counter()
+    ref = O.bb_solve(final, n, prune=True, max_nodes=k)
+    dq = time.perf_counter() - tq
+    out["cpu_baseline"] = {"value": ref["nodes"] / dq, "unit": "nodes/s", "cores": 1, "kind": "port",
+                           "sample": f"first {ref['nodes']} nodes of ExecuteBranchAndBound on the same cfg5 root ({dq:.1f} s); "
+                                     "C++ restatement of BranchBoundSimplexSolver.cs:1006-1233, single thread"}
+    # a cfg5-family instance that terminates: incumbent hash at this GPU count == the sequential oracle's
+    try:
+        cm, cn, cseed, cdiv = 6, 32, 42, 2.0
+        A2, b2, c2 = W.gen_binary_ip(cseed, cm, cn, cdiv)
+        f2, _, _ = W.lp_relaxation(A2, b2, c2, dev)
+        os.environ["LPR_BB_PREALLOC_MB"] = "256"
+        closed = W.bb_mgpu(f2, cn, world, slice_seconds=1e-3)
+        refc = O.bb_solve(f2, cn, prune=True, max_nodes=-1, log_cap=1 << 16)
+        closed["oracle_nodes"] = int(refc["nodes"])
+        closed["matches_oracle"] = bool(refc["has_solution"] and closed["incumbent_z"] == refc["z"]
+                                        and closed["incumbent_sha"] == W.sha16(refc["x"]))
+        closed["workload"] = f"cfg5 family m={cm} n={cn} + {cn} bound rows, b = rowsum/{cdiv:g}, seed {cseed}: tree closes"
+        out["closed_instance"] = closed
+    except Exception as ex:
+        out["closed_instance"] = {"error": repr(ex)}
+    finally:
+        os.environ["LPR_BB_PREALLOC_MB"] = "126976"
+    return out
+
+
+def run_knap_legs(W, O, world, dev):
+    """cfg4 (n = 10^4 weakly correlated, seed 384) to proven optimality with the reference's own check (B&B == DP,
+    Program.cs:467-470) asserted in the run; 'hard' = an almost strongly correlated instance with seconds of work, which
+    is what the scaling figure is quoted on; cpu_baseline = the oracle's depth-first B&B on cfg4."""
+    w, v, cap = W.gen_knapsack(384, 10000)
+    out, ch = W.knap_mgpu(w, v, cap, world)
+    out["workload"] = f"cfg4 knapsack n=10000 weakly correlated, capacity {cap:.0f}, to proven optimality"
+    dp, dp_s = W.knap_dp_check(w, v, cap, dev)
+    out["dp_value"], out["dp_seconds"] = dp, dp_s
+    out["equals_dp"] = bool(abs(out["best_value"] - dp) < 1e-6)
+    assert out["equals_dp"], f"knapsack B&B {out['best_value']} != DP {dp}"
+    k = int(os.environ.get("LPR_CPU_SAMPLE_KNAP_NODES", "150000"))
+    tq = time.perf_counter()
+    ref = O.knap_bb(cap, w, v, max_nodes=k)
+    dq = time.perf_counter() - tq
+    out["cpu_baseline"] = {"value": ref["nodes"] / dq, "unit": "nodes/s", "cores": 1, "kind": "port",
+                           "sample": f"first {ref['nodes']} nodes of the oracle's depth-first B&B on cfg4 ({dq:.1f} s), single thread"}
+    try:
+        hn, hseed = int(os.environ.get("LPR_BENCH_KNAP_HARD_N", "2000")), 388
+        w2, v2, cap2 = W.gen_knapsack_hard(hseed, hn)
+        hard, _ = W.knap_mgpu(w2, v2, cap2, world, max_nodes=int(os.environ.get("LPR_BENCH_KNAP_HARD_NODES", "-1")))
+        hard["workload"] = f"cfg4-hard: almost strongly correlated n={hn}, seed {hseed}, capacity {cap2:.0f}"
+        out["hard"] = hard
+    except Exception as ex:
+        out["hard"] = {"error": repr(ex)}
+    return out
+
+
+def run_rev_host_legs(W, O, lib, N, C, dev, world):
+    """cfg3 through the C ABI with HOST arrays (A, b, c pinned -> lpr_rev_create -> 256 iterations -> x, z, y, basis
+    back), and the oracle's iterations/s on the same model as cpu_baseline."""
+    import numpy as np
+    m, n, seed, iters = 8192, 16384, 384, 256
+    A = pinned((m, n))
+    _, b, c = W.gen_dense_lp(seed, m, n, out=A)
+    out = {}
+    t0 = time.perf_counter()
+    h = N.vp()
+    N.check(lib.lpr_rev_create(dev, m, n, N.pd(A), N.pd(N.f64(b)), N.pd(N.f64(c)), 0, C.byref(h)))
+    t1 = time.perf_counter()
+    st, nit, z = C.c_int(), C.c_int64(), C.c_double()
+    N.check(lib.lpr_rev_solve(h, iters, 0, C.byref(st), C.byref(nit), None, 0))
+    t2 = time.perf_counter()
+    x, y, basis = np.zeros(n), np.zeros(m), np.zeros(m, dtype=np.int32)
+    N.check(lib.lpr_rev_read_x(h, N.pd(x)))
+    N.check(lib.lpr_rev_read_z(h, C.byref(z)))
+    N.check(lib.lpr_rev_read_y(h, N.pd(y)))
+    N.check(lib.lpr_rev_read_basis(h, N.pi(basis)))
+    t3 = time.perf_counter()
+    lib.lpr_rev_destroy(h)
+    out["e2e"] = {"value": nit.value / (t3 - t0), "unit": "iterations/s", "iterations": nit.value,
+                  "h2d_bytes_per_step": 8 * (m * n + m + n), "d2h_bytes_per_step": 8 * (n + m + 1) + 4 * m,
+                  "phase_ms": {"create_h2d": (t1 - t0) * 1e3, "solve": (t2 - t1) * 1e3, "read_back": (t3 - t2) * 1e3},
+                  "what": "lpr_rev_create(host A, b, c pinned) + lpr_rev_solve(256 iterations) + x, z, y, basis back"}
+    if world == 1:
+        k1, k2 = 1, int(os.environ.get("LPR_CPU_SAMPLE_REV_ITERS", "5"))
+        tq = time.perf_counter(); O.rev_solve(A, b, c, False, max_iter=k1, log_cap=8); d1 = time.perf_counter() - tq
+        tq = time.perf_counter(); O.rev_solve(A, b, c, False, max_iter=k2, log_cap=8); d2 = time.perf_counter() - tq
+        per = max(1e-9, (d2 - d1) / (k2 - k1))
+        out["cpu_baseline"] = {"value": 1.0 / per, "unit": "iterations/s", "cores": 1, "kind": "port",
+                               "sample": f"iterations {k1 + 1}..{k2} of the same cfg3 solve ({d2:.1f} s incl. set-up); C++ "
+                                         "restatement of RevisedPrimalSimplexSolver.cs:82-251 without the O(m^2 n) snapshot "
+                                         "product, single thread"}
+    return out
 
 
 if __name__ == "__main__":

@@ -27,10 +27,15 @@ namespace LPR_381_Group_V22.IntegerProgramming
     {
         private readonly double capacity; private readonly double[] weights, values; private byte[] chosen; private long nodes; private double best;
         public KnapsackBranchBoundSimplex(int capacity, double[] weights, double[] values) { this.capacity = capacity; this.weights = weights; this.values = values; }
+        /// <summary>GPUs the open-node pool is partitioned over (inside the library: host threads + NCCL)</summary>
+        public int Gpus { get; set; } = 1;
         public double Solve()
         {
             chosen = new byte[weights.Length];
-            Lpr.Check(Lpr.lpr_knap_solve(0, capacity, weights.Length, weights, values, -1, out best, chosen, out nodes, out int _));
+            if (Gpus > 1)
+                Lpr.Check(Lpr.lpr_knap_solve_mgpu(Gpus, null, capacity, weights.Length, weights, values, -1, -1, 0.0, out best, chosen, out nodes, out int _, IntPtr.Zero));
+            else
+                Lpr.Check(Lpr.lpr_knap_solve(0, capacity, weights.Length, weights, values, -1, out best, chosen, out nodes, out int _));
             return best;
         }
         public void PrintIterations() { Console.WriteLine($"Knapsack B&B: {nodes} nodes processed, best value {best}"); }

@@ -11,7 +11,7 @@ namespace LPR_381_Group_V22.Native
 
         public const int OK = 0;
         public const int RUNNING = 0, OPTIMAL = 1, UNBOUNDED = 2, INFEASIBLE = 3, ITER_LIMIT = 4, NODE_LIMIT = 5,
-                         PIVOT_TOO_SMALL = 6, NO_CUT_NEEDED = 7, NO_PIVOT_COL = 8, CUT_STEP_DONE = 9;
+                         PIVOT_TOO_SMALL = 6, NO_CUT_NEEDED = 7, NO_PIVOT_COL = 8, CUT_STEP_DONE = 9, DEPTH_LIMIT = 10;
         public const int RULE_PRIMAL = 0, RULE_PRIMAL2 = 1, RULE_DUAL = 2, RULE_SENS = 3;
 
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_version();
@@ -55,6 +55,11 @@ namespace LPR_381_Group_V22.Native
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_rev_read_x(IntPtr h, [Out] double[] x);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_rev_read_z(IntPtr h, out double z);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_rev_read_y(IntPtr h, [Out] double[] y);
+        // one iteration at a time + the CaptureSnapshot text of that iteration (RevisedPrimalSimplexSolver.cs:82-250, :294-387)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_rev_begin(IntPtr h);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_rev_step(IntPtr h, out int status, out int enter, out int leaveRow, out int leaveVar);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_rev_format_snapshot(IntPtr h, out IntPtr utf8Text, out long len);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_rev_refactor(IntPtr h);
 
         // ---- integer programming -------------------------------------------------------------------
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
@@ -66,6 +71,26 @@ namespace LPR_381_Group_V22.Native
                                                 out double best, [Out] byte[] chosen, out long nodes, out int status);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
         public static extern int lpr_knap_dp(int device, int capacity, int n, int[] weights, int[] values, out double best, [Out] byte[] chosen);
+
+        // ---- multi-GPU branch & bound inside the library (host threads + NCCL; stats may be IntPtr.Zero) ----------------
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern int lpr_bb_solve_mgpu(int nGpus, int[] devices, int rows, int cols, double[,] finalTableau, int nVars, int enablePruning,
+                                                   long maxNodes, long maxRounds, double sliceSeconds, [Out] double[] x, out double z, out int hasSolution,
+                                                   out long nodes, out long pivots, out int status, IntPtr stats);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern int lpr_knap_solve_mgpu(int nGpus, int[] devices, double capacity, int n, double[] weights, double[] values, long maxNodes,
+                                                     long maxRounds, double sliceSeconds, out double best, [Out] byte[] chosen, out long nodes, out int status, IntPtr stats);
+        // ---- B&B building blocks on one device tableau (BranchBoundSimplexSolver.cs:552-567, :694-803) -----------------
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_round4(IntPtr h);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_tab_bb_add_constraint(IntPtr parent, int nVars, int var, double bound, int type, out IntPtr child);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int lpr_fmt_fixed(double x, int decimals, [Out] byte[] buf, int cap);
+
+        public static string Utf8(IntPtr p, long len)
+        {
+            var bytes = new byte[len];
+            Marshal.Copy(p, bytes, 0, (int)len);
+            return System.Text.Encoding.UTF8.GetString(bytes);
+        }
 
         public static void Check(int rc)
         {

@@ -43,18 +43,39 @@ namespace LPR_381_Group_V22.Simplex
             rev = new RevHandle(h);
         }
 
+        /// <summary>Tracing threshold (SURVEY 8b "Snapshots"): below it Solve() steps iteration by iteration and records the
+        /// reference's CaptureSnapshot text for each one; above it the whole loop runs on the device and no text is built
+        /// (one snapshot of BASELINE cfg3 would be gigabytes).</summary>
+        public static long TraceMaxElements = 4096;
+
         public void Solve()
         {
-            Lpr.Check(Lpr.lpr_rev_solve(rev.DangerousGetHandle(), -1, 0, out int status, out long _, null, 0));
+            IntPtr h = rev.DangerousGetHandle();
+            int status;
+            if ((long)numConstraints * (numVariables + numConstraints + 1) <= TraceMaxElements)
+            {
+                Lpr.Check(Lpr.lpr_rev_begin(h));
+                while (true)
+                {
+                    Lpr.Check(Lpr.lpr_rev_step(h, out status, out int _, out int _, out int _));
+                    if (status != Lpr.RUNNING && status != Lpr.OPTIMAL) break;
+                    Lpr.Check(Lpr.lpr_rev_format_snapshot(h, out IntPtr text, out long len));   // "Iteration k" / "Optimal" (:226-246, :124-146)
+                    IterationSnapshots.Add(Lpr.Utf8(text, len));
+                    if (status == Lpr.OPTIMAL) break;
+                }
+            }
+            else
+            {
+                Lpr.Check(Lpr.lpr_rev_solve(h, -1, 0, out status, out long _, null, 0));
+            }
             if (status == Lpr.INFEASIBLE) throw new Exception("Infeasible basis (negative basic value).");
             if (status == Lpr.UNBOUNDED) throw new Exception("Unbounded problem (no positive component in direction).");
             if (status == Lpr.PIVOT_TOO_SMALL) throw new Exception("Pivot too small.");
             var x = new double[numVariables];
-            Lpr.Check(Lpr.lpr_rev_read_x(rev.DangerousGetHandle(), x));
-            Lpr.Check(Lpr.lpr_rev_read_z(rev.DangerousGetHandle(), out double z));
+            Lpr.Check(Lpr.lpr_rev_read_x(h, x));
+            Lpr.Check(Lpr.lpr_rev_read_z(h, out double z));
             SolutionVector = x.ToList();
             FinalZ = z;
-            IterationSnapshots.Add("Optimal\nDual prices (y = c_B^T B^{-1}):\n" + string.Join("\t", DualPrices.Select(NumFormat.N3)));
         }
         public void Dispose() { rev.Dispose(); }
     }

@@ -26,6 +26,18 @@ def u01(seed, stream, idx):
         return (_splitmix64(k) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
 
 
+def gen_dense_lp(seed, m, n, out=None):
+    """SURVEY 8(d) cfg2 / cfg3 model: A = 0.1 + u, b = (n/4)(1 + u), c = 1 + u (bit identical to the CUDA generator)"""
+    A = out if out is not None else np.empty((m, n))
+    step = max(1, (1 << 24) // n)
+    for r0 in range(0, m, step):  # row blocks: the index array of the whole matrix would be another gigabyte
+        r1 = min(m, r0 + step)
+        A[r0:r1] = 0.1 + u01(seed, 0, np.arange(r0 * n, r1 * n, dtype=np.uint64)).reshape(r1 - r0, n)
+    b = (n / 4.0) * (1.0 + u01(seed, 1, np.arange(m, dtype=np.uint64)))
+    c = 1.0 + u01(seed, 2, np.arange(n, dtype=np.uint64))
+    return A, b, c
+
+
 def gen_dense_ip(seed, m, n):
     A = 1.0 + np.floor(20.0 * u01(seed, 0, np.arange(m * n, dtype=np.uint64))).reshape(m, n)
     b = np.floor(A.sum(axis=1) / 4.0)
@@ -36,6 +48,92 @@ def gen_dense_ip(seed, m, n):
 def gen_knapsack(seed, n):
     w = 1.0 + np.floor(1000.0 * u01(seed, 0, np.arange(n, dtype=np.uint64)))
     v = np.maximum(1.0, w + np.floor(200.0 * u01(seed, 1, np.arange(n, dtype=np.uint64))) - 100.0)
+    return w, v, float(np.floor(w.sum() / 2.0))
+
+
+def gen_binary_ip(seed, m, n, div):
+    """cfg5-family instance whose tree closes under the reference's semantics: the cfg5 generator's A and c,
+    b = floor(row sum / div), plus one `x_j <= 1` row per variable (what menu option 3 appends, Program.cs:372-382)"""
+    A, _, c = gen_dense_ip(seed, m, n)
+    b = np.floor(A.sum(axis=1) / div)
+    return np.vstack([A, np.eye(n)]), np.concatenate([b, np.ones(n)]), c
+
+
+def sha16(arr):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()[:16]
+
+
+def lp_relaxation(A, b, c, device):
+    """final tableau of the LP relaxation, solved by the tableau path on `device`"""
+    m, n = A.shape
+    coef = N.f64(A); rhs = N.f64(b); obj = N.f64(c)
+    h = N.vp()
+    N.check(N.lib().lpr_tab_create_primal(device, n, m, N.pd(obj), N.pd(coef), n, None, None, N.pd(rhs), 1, C.byref(h)))
+    tab = DeviceTableau(h)
+    lp = tab.solve(log_cap=0)
+    ms = tab.last_solve_ms
+    final = tab.read()
+    tab.close()
+    return final, lp, ms
+
+
+def bb_mgpu(final, n_vars, n_gpus, max_rounds=-1, slice_seconds=0.0, max_nodes=-1):
+    """lpr_bb_solve_mgpu: the node pool partitioned over n_gpus devices INSIDE the library (host threads + NCCL)"""
+    from .integer_programming import solve_bb_mgpu
+    r = solve_bb_mgpu(final, n_vars, True, n_gpus=n_gpus, max_nodes=max_nodes, max_rounds=max_rounds,
+                      slice_seconds=slice_seconds)
+    st = r["stats"]
+    dt = max(st["seconds"], 1e-9)
+    return dict(n_gpus=n_gpus, nodes=r["nodes"], seconds=dt, nodes_per_s=r["nodes"] / dt, pivots_in_nodes=r["pivots"],
+                pivots_per_node=r["pivots"] / max(1, r["nodes"]), status=STATUS(r["status"]),
+                incumbent_z=(r["z"] if r["has_solution"] else None),
+                incumbent_sha=(sha16(r["x"]) if r["has_solution"] else None), open_left=st["open_left"],
+                depth_overflow=st["depth_overflow"], rounds=st["rounds"], steals=st["steals"],
+                nodes_moved=st["nodes_moved"], nodes_per_gpu=st["nodes_per_gpu"],
+                run_seconds_per_gpu=[round(v, 4) for v in st["run_seconds_per_gpu"]],
+                phase_seconds_rank0=dict(seed=st["seed_seconds"], exchange=st["exchange_seconds"], steal=st["steal_seconds"]),
+                setup_seconds=st["setup_seconds"], nccl_version=st["nccl_version"])
+
+
+def knap_mgpu(w, v, cap, n_gpus, max_nodes=-1, slice_seconds=2e-3):
+    """lpr_knap_solve_mgpu: same, for the knapsack pool"""
+    n = len(w)
+    best, nodes, st = C.c_double(), C.c_int64(), C.c_int()
+    ch = np.zeros(n, dtype=np.uint8)
+    stats = N.MgpuStats()
+    N.check(N.lib().lpr_knap_solve_mgpu(n_gpus, None, float(cap), n, N.pd(N.f64(w)), N.pd(N.f64(v)), max_nodes, -1,
+                                        float(slice_seconds), C.byref(best), ch.ctypes.data_as(N.bp), C.byref(nodes),
+                                        C.byref(st), C.byref(stats)))
+    d = stats.as_dict()
+    dt = max(d["seconds"], 1e-9)
+    rec_bytes = 8 * (3 * ((n + 63) // 64) + 4)
+    return dict(n_gpus=n_gpus, nodes=nodes.value, seconds=dt, nodes_per_s=nodes.value / dt, status=STATUS(st.value),
+                best_value=best.value, selection_sha=sha16(ch), items_chosen=int(ch.sum()),
+                weight_used=float(np.dot(ch, w)), node_record_bytes=rec_bytes,
+                record_gbs=4.0 * rec_bytes * nodes.value / dt / 1e9, open_left=d["open_left"], rounds=d["rounds"],
+                steals=d["steals"], nodes_moved=d["nodes_moved"], nodes_per_gpu=d["nodes_per_gpu"],
+                run_seconds_per_gpu=[round(x, 4) for x in d["run_seconds_per_gpu"]],
+                phase_seconds_rank0=dict(seed=d["seed_seconds"], exchange=d["exchange_seconds"], steal=d["steal_seconds"]),
+                setup_seconds=d["setup_seconds"], nccl_version=d["nccl_version"]), ch
+
+
+def knap_dp_check(w, v, cap, device=0):
+    """KnapsackBranchBoundSolver.Solve(int, int[], int[]) on the device: the arbiter of Program.cs:467-470"""
+    wi = N.i32(w.astype(np.int64)); vi = N.i32(v.astype(np.int64))
+    best = C.c_double()
+    ch = np.zeros(len(wi), dtype=np.uint8)
+    t = time.perf_counter()
+    N.check(N.lib().lpr_knap_dp(device, int(cap), len(wi), N.pi(wi), N.pi(vi), C.byref(best), ch.ctypes.data_as(N.bp)))
+    return best.value, time.perf_counter() - t
+
+
+def gen_knapsack_hard(seed, n, R=1000):
+    """'cfg4-hard': Pisinger's almost strongly correlated family, v = w + R/10 + U[-R/500, R/500] -- bounds of
+    neighbouring nodes differ little, so the LP bound prunes late and the tree has seconds of GPU work"""
+    idx = np.arange(n, dtype=np.uint64)
+    w = 1.0 + np.floor(R * u01(seed, 0, idx))
+    v = w + R / 10 + np.floor(R / 250 * u01(seed, 1, idx)) - R / 500
     return w, v, float(np.floor(w.sum() / 2.0))
 
 

@@ -689,7 +689,12 @@ static bool drv_entry(const char* name, F* fn) {
 }
 
 static GreenDev* green_get(int device) {
-  static const int on = getenv("LPR_PIPE_GREEN") ? atoi(getenv("LPR_PIPE_GREEN")) : 1;
+  // Green-context streams break Nsight Compute's replay (ncu dies at the first launch on them): under a profiler --
+  // recognised by the injection variables its launcher exports -- the two priority streams are used instead, so a
+  // profiled run still lists k_pipe_select3 / k_pipe_sweep_ca (the partitioned run is the one that is timed).
+  static const bool profiled = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("CUDA_INJECTION64_PATH") ||
+                               getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") || getenv("NVTX_INJECTION64_PATH");
+  static const int on = getenv("LPR_PIPE_GREEN") ? atoi(getenv("LPR_PIPE_GREEN")) : (profiled ? 0 : 1);
   if (!on || device < 0 || device >= 64) return nullptr;
   std::lock_guard<std::mutex> lk(g_green_mu);
   GreenDev& G = g_green[device];

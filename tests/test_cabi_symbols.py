@@ -30,7 +30,7 @@ def test_ctypes_table_matches_header():
 
 def test_no_stub_left():
     assert not os.path.exists(os.path.join(ROOT, "lpr_381_group_v22_b200", "csrc", "stubs.cu")), \
-        "tools/gen_stubs.py left unimplemented entry points"
+        "a stub source was left in csrc/: every entry point of the header must be implemented"
 
 
 def test_version_and_error_plumbing_without_gpu():
