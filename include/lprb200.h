@@ -176,8 +176,16 @@ int lpr_rev_read_xb(lpr_rev* h, double* xb);      /* x_B = B^-1 b :89, m        
 int lpr_rev_read_binv(lpr_rev* h, double* binv);  /* m x m                                  */
 int lpr_rev_last_solve_ms(const lpr_rev* h, float* ms);
 int lpr_rev_last_refactor_ms(const lpr_rev* h, float* ms);
-/* max |I - B X| before the refresh and the GEMM flop count (4 m^3) of the last refactorisation */
+/* max |I - B X| before the refactorisation (of the new inverse when mode 2 was asked for) and its FP64 flop count */
 int lpr_rev_last_refactor_info(const lpr_rev* h, double* residual, double* flops);
+/* Refactorisation with an explicit mode.  0 (what lpr_rev_refactor and refactor_every use): Newton-Schulz refresh
+ * X <- X + X (I - B X) while the current inverse is usable (max |I - B X| < 0.5), otherwise the full path; 1: refresh
+ * only; 2: full refactorisation from the basis columns alone -- blocked Gauss-Jordan inversion with partial pivoting,
+ * rank-64 trailing updates on the FP64 tensor cores, residual check and one polishing step.  lpr_rev_last_refactor_path:
+ * which path ran (1 refresh, 2 full) and max |I - B X| of the result of the full path. */
+int lpr_rev_refactor_ex(lpr_rev* h, int mode);
+int lpr_rev_last_refactor_path(const lpr_rev* h, int* path, double* residual_after);
+int lpr_rev_write_binv(lpr_rev* h, const double* binv); /* overwrite B^-1 (m x m row major) */
 
 /* ---- BranchBoundSimplexSolver (IntegerProgramming/BranchBoundSimplexSolver.cs) ------------- */
 /* building blocks, each on a device tableau */

@@ -89,6 +89,9 @@ SIGNATURES = {
     "lpr_rev_destroy": (C.c_int, [vp]),
     "lpr_rev_solve": (C.c_int, [vp, C.c_int64, C.c_int, ip, lp, ip, C.c_int64]),
     "lpr_rev_refactor": (C.c_int, [vp]),
+    "lpr_rev_refactor_ex": (C.c_int, [vp, C.c_int]),
+    "lpr_rev_last_refactor_path": (C.c_int, [vp, ip, dp]),
+    "lpr_rev_write_binv": (C.c_int, [vp, dp]),
     "lpr_rev_begin": (C.c_int, [vp]),
     "lpr_rev_step": (C.c_int, [vp, ip, ip, ip, ip]),
     "lpr_rev_format_snapshot": (C.c_int, [vp, C.POINTER(vp), lp]),

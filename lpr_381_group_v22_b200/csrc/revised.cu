@@ -607,10 +607,7 @@ __global__ void k_rev_solution(RevView v, const double* c_orig, double* x, doubl
 
 }  // namespace lpr
 
-namespace lpr {
-int refactor_binv(cudaStream_t stream, int m, int n, const double* A, int ldA, double* Binv, int ldB,
-                  const int* basis, double* residual_out, double* flops_out);
-}
+#include "refactor.cuh"
 using namespace lpr;
 
 struct lpr_rev {
@@ -627,7 +624,9 @@ struct lpr_rev {
   RevState* st_host = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evb[2] = {nullptr, nullptr};
   float last_ms = 0.f, last_refactor_ms = 0.f;
-  double last_refactor_residual = 0.0, last_refactor_flops = 0.0;
+  double last_refactor_residual = 0.0, last_refactor_residual_after = 0.0, last_refactor_flops = 0.0;
+  int last_refactor_path = 0;  // 1 = Newton-Schulz refresh, 2 = full blocked Gauss-Jordan inversion
+  RefactorWs rws;              // refactorisation workspace, allocated by the first refactorisation
   bool solved = false;
   // lpr_rev_begin / lpr_rev_step: host copies of the PRE-pivot quantities of the last step, which CaptureSnapshot
   // (:294-387) prints beside the post-pivot tableau
@@ -756,6 +755,7 @@ int lpr_rev_destroy(lpr_rev* h) {
   if (!h) return LPR_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  refactor_ws_free(h->rws);
   double* d[] = {h->A, h->Binv, h->b, h->c, h->c_orig, h->cB, h->xB, h->y, h->rc, h->u, h->ab, h->ecoef,
                  h->brow, h->ppart, h->ypart, h->x, h->z};
   for (double* p : d) cudaFree(p);
@@ -1052,16 +1052,18 @@ int lpr_rev_format_snapshot(lpr_rev* h, const char** text, int64_t* len) {
   return LPR_OK;
 }
 
-int lpr_rev_refactor(lpr_rev* h) {
+// mode 0: Newton-Schulz refresh while max |I - B X| < 0.5, else the full refactorisation; 1: refresh only;
+// 2: full refactorisation from the basis columns alone (blocked Gauss-Jordan, refactor.cu)
+int lpr_rev_refactor_ex(lpr_rev* h, int mode) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
+  if (mode < 0 || mode > 2) return fail(LPR_E_BADARG, "refactorisation mode %d", mode);
   int rc = select_device(h->device);
   if (rc) return rc;
-  cudaEvent_t a, b;
-  LPR_CUDA(cudaEventCreate(&a));
-  LPR_CUDA(cudaEventCreate(&b));
-  LPR_CUDA(cudaEventRecord(a, h->stream));
-  double res = 0.0, flops = 0.0;
-  rc = refactor_binv(h->stream, h->m, h->n, h->A, h->ldA, h->Binv, h->ldB, h->basis, &res, &flops);
+  LPR_CUDA(cudaEventRecord(h->ev0, h->stream));
+  double res = 0.0, res_after = 0.0, flops = 0.0;
+  int path = 0;
+  rc = refactor_binv(h->stream, h->m, h->n, h->A, h->ldA, h->Binv, h->ldB, h->basis, h->rws, mode, &res, &res_after,
+                     &flops, &path);
   if (rc == LPR_OK) {
     // the dual vector of the next pricing pass must come from the refreshed inverse
     RevView v = h->view();
@@ -1071,17 +1073,21 @@ int lpr_rev_refactor(lpr_rev* h) {
     // k_y checks the status word: it is RUNNING or terminal; recompute unconditionally with a local copy
     k_y_force<<<(h->m + kT - 1) / kT, kT, 0, h->stream>>>(v);
     count_launch();
-    cudaEventRecord(b, h->stream);
+    cudaEventRecord(h->ev1, h->stream);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(LPR_E_CUDA, "refactor: y recompute failed");
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, a, b);
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->last_refactor_ms = ms;
     h->last_refactor_residual = res;
+    h->last_refactor_residual_after = res_after;
     h->last_refactor_flops = flops;
+    h->last_refactor_path = path;
   }
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
   return rc;
+}
+int lpr_rev_refactor(lpr_rev* h) {
+  static const int mode = getenv("LPR_REV_REFACTOR_MODE") ? atoi(getenv("LPR_REV_REFACTOR_MODE")) : 0;
+  return lpr_rev_refactor_ex(h, mode);
 }
 
 #define REV_READ(name, field, count, type)                                                        \
@@ -1123,6 +1129,22 @@ int lpr_rev_last_refactor_info(const lpr_rev* h, double* residual, double* flops
   if (!h) return fail(LPR_E_BADARG, "null argument");
   if (residual) *residual = h->last_refactor_residual;
   if (flops) *flops = h->last_refactor_flops;
+  return LPR_OK;
+}
+int lpr_rev_last_refactor_path(const lpr_rev* h, int* path, double* residual_after) {
+  if (!h) return fail(LPR_E_BADARG, "null argument");
+  if (path) *path = h->last_refactor_path;
+  if (residual_after) *residual_after = h->last_refactor_residual_after;
+  return LPR_OK;
+}
+// overwrite B^-1 (m x m, row major) -- warm starts, and the tests that damage the inverse to exercise the guard
+int lpr_rev_write_binv(lpr_rev* h, const double* binv) {
+  if (!h || !binv) return fail(LPR_E_BADARG, "null argument");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  LPR_CUDA(cudaMemcpy2DAsync(h->Binv, sizeof(double) * h->ldB, binv, sizeof(double) * h->m, sizeof(double) * h->m, h->m,
+                             cudaMemcpyHostToDevice, h->stream));
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
   return LPR_OK;
 }
 

@@ -911,6 +911,10 @@ bool tab_pipe_applicable(const lpr_tab* h);
 int tab_solve_pipelined(lpr_tab* h, int K, int64_t max_pivots, int* status, int64_t* n_pivots, int* pivot_log,
                         int64_t log_cap, bool time_sweeps);
 
+bool tab_persist_applicable(const lpr_tab* h);
+int tab_run_persistent(lpr_tab* h, int program, int64_t max_pivots, int print_steps, int max_cuts, int* status,
+                       int64_t* n_pivots, int* pivot_log, int64_t log_cap, int* n_cuts, int* cut_log, int cut_log_cap);
+
 int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int* status,
                        int64_t* n_pivots, int* pivot_log, int64_t log_cap) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
@@ -929,6 +933,11 @@ int tab_solve_internal(lpr_tab* h, int rule, int64_t max_pivots, int flags, int*
       return tab_solve_blocked(h, blk, max_pivots, status, n_pivots, pivot_log, log_cap, (flags & 8) != 0);
     }
   }
+  // PrimalSimplexSolver2 / DualSimplexSolver loops on an L2-resident tableau: one cooperative launch for the whole
+  // loop (tableau_persistent.cu); flags bit2 keeps the two-kernel path
+  if ((rule == LPR_RULE_DUAL || rule == LPR_RULE_PRIMAL2) && !(flags & 4) && tab_persist_applicable(h))
+    return tab_run_persistent(h, rule == LPR_RULE_DUAL ? 0 : 1, max_pivots, flags & F_PRINT, 0, status, n_pivots,
+                              pivot_log, log_cap, nullptr, nullptr, 0);
   static const int fused_default = env_int("LPR_TAB_FUSED", 1);
   static const int batch = std::max(1, env_int("LPR_TAB_BATCH", 32));
   static const int serp = env_int("LPR_TAB_SERPENTINE", 1);
@@ -1408,6 +1417,10 @@ int lpr_tab_cutting_plane(lpr_tab* h, int max_cuts, int* status, int* n_cuts, in
   if (!h) return fail(LPR_E_BADARG, "null handle");
   int rc = select_device(h->device);
   if (rc) return rc;
+  if (tab_persist_applicable(h)) {  // the whole recursion in one cooperative launch (tableau_persistent.cu)
+    int64_t piv = 0;
+    return tab_run_persistent(h, 2, 10000, 1, max_cuts, status, &piv, nullptr, 0, n_cuts, cut_log, cut_log_cap);
+  }
   int* dflags = nullptr;
   LPR_CUDA(cudaMalloc(&dflags, sizeof(int) * 4));
   int st = LPR_RUNNING, cuts = 0;

@@ -123,11 +123,11 @@ def test_refactorisation_fp64_dmma():
     close(s.DualPrices, ref["y"], "y after refresh")
 
 
-@pytest.mark.parametrize("refactor_every", [0, 12])
-def test_cfg3_size_window_matches_oracle(refactor_every):
+def test_cfg3_size_window_matches_oracle():
     """BASELINE cfg3 shape (m = 8192, n = 16384, seed 384, generated in HBM): the first 32 iterations against the
-    oracle run on the same input -- pivot log exact, z / x / y / x_B within 1e-9 relative -- as shipped and with a
-    refactorisation of B^-1 every 12 iterations (which must not move anything beyond the tolerance)."""
+    oracle run on the same input (one ~90 s single-thread oracle run serves both device runs) -- pivot log exact,
+    z / x / y / x_B within 1e-9 relative -- as shipped and with a refactorisation of B^-1 every 12 iterations (which
+    must not move anything beyond the tolerance)."""
     import ctypes as C
     from lpr_381_group_v22_b200 import _native as N
     m, n, seed, K = 8192, 16384, 384, 32
@@ -136,31 +136,32 @@ def test_cfg3_size_window_matches_oracle(refactor_every):
     del A
     assert ref["status"] == O.ITER_LIMIT and ref["n_iter"] == K
     lib = N.lib()
-    h = N.vp()
-    N.check(lib.lpr_rev_create_dense_lp(0, seed, m, n, C.byref(h)))
-    try:
-        st, nit = C.c_int(), C.c_int64()
-        log = np.zeros((K, 3), dtype=np.int32)
-        N.check(lib.lpr_rev_solve(h, K, refactor_every, C.byref(st), C.byref(nit), N.pi(log), K))
-        assert st.value == L.ITER_LIMIT and nit.value == K
-        assert log.tolist() == ref["log"].tolist()
-        basis = np.zeros(m, dtype=np.int32); x = np.zeros(n); y = np.zeros(m); xb = np.zeros(m); z = C.c_double()
-        N.check(lib.lpr_rev_read_basis(h, N.pi(basis)))
-        N.check(lib.lpr_rev_read_x(h, N.pd(x)))
-        N.check(lib.lpr_rev_read_y(h, N.pd(y)))
-        N.check(lib.lpr_rev_read_xb(h, N.pd(xb)))
-        N.check(lib.lpr_rev_read_z(h, C.byref(z)))
-        assert basis.tolist() == ref["basis"].tolist()
-        close(z.value, ref["z"], "z")
-        close(x, ref["x"], "x")
-        close(y, ref["y"], "y")
-        close(xb, ref["xB"], "xB")
-        if refactor_every:
-            res, fl = C.c_double(), C.c_double()
-            N.check(lib.lpr_rev_last_refactor_info(h, C.byref(res), C.byref(fl)))
-            assert res.value < 1e-9
-    finally:
-        lib.lpr_rev_destroy(h)
+    for refactor_every in (0, 12):
+        h = N.vp()
+        N.check(lib.lpr_rev_create_dense_lp(0, seed, m, n, C.byref(h)))
+        try:
+            st, nit = C.c_int(), C.c_int64()
+            log = np.zeros((K, 3), dtype=np.int32)
+            N.check(lib.lpr_rev_solve(h, K, refactor_every, C.byref(st), C.byref(nit), N.pi(log), K))
+            assert st.value == L.ITER_LIMIT and nit.value == K
+            assert log.tolist() == ref["log"].tolist()
+            basis = np.zeros(m, dtype=np.int32); x = np.zeros(n); y = np.zeros(m); xb = np.zeros(m); z = C.c_double()
+            N.check(lib.lpr_rev_read_basis(h, N.pi(basis)))
+            N.check(lib.lpr_rev_read_x(h, N.pd(x)))
+            N.check(lib.lpr_rev_read_y(h, N.pd(y)))
+            N.check(lib.lpr_rev_read_xb(h, N.pd(xb)))
+            N.check(lib.lpr_rev_read_z(h, C.byref(z)))
+            assert basis.tolist() == ref["basis"].tolist()
+            close(z.value, ref["z"], "z")
+            close(x, ref["x"], "x")
+            close(y, ref["y"], "y")
+            close(xb, ref["xB"], "xB")
+            if refactor_every:
+                res, fl = C.c_double(), C.c_double()
+                N.check(lib.lpr_rev_last_refactor_info(h, C.byref(res), C.byref(fl)))
+                assert res.value < 1e-9
+        finally:
+            lib.lpr_rev_destroy(h)
 
 
 def _models_for_snapshots():
@@ -202,3 +203,47 @@ def test_result_file_of_a_revised_run_matches_restatement(tmp_path):
     s.Solve()
     snaps, _, x, z, _ = R.revised_solve_with_snapshots(obj, A, b, False)
     assert s.IterationSnapshots == snaps
+
+
+@pytest.mark.parametrize("m,n,seed", [(40, 70, 31), (150, 260, 32), (333, 500, 33)])
+def test_full_refactorisation_from_the_basis_columns(m, n, seed):
+    """The full path (blocked Gauss-Jordan inversion with partial pivoting on the FP64 tensor cores) rebuilds B^-1 from
+    the basis columns ALONE: damage the inverse (noise, then garbage), refactorise, compare with numpy's inverse of the
+    gathered basis; the guard of the automatic mode must pick the full path when the refresh would diverge."""
+    import ctypes as C
+    from lpr_381_group_v22_b200 import _native as N
+    A, b, c = O.gen_dense_lp(seed, m, n)
+    ref = O.rev_solve(A, b, c, want_binv=True)
+    s = L.RevisedPrimalSimplexSolver(list(c), [L.Constraint(A[i], "<=", b[i]) for i in range(m)], False, trace=False)
+    s.Solve()
+    lib = N.lib()
+    basis = s.BasicVariables
+    Bm = np.column_stack([A[:, v] if v < n else np.eye(m)[:, v - n] for v in basis])
+    exact = np.linalg.inv(Bm)
+    good = s.BInverse
+    rng = np.random.default_rng(seed)
+    path, after = C.c_int(), C.c_double()
+
+    def err(X):
+        return float(np.max(np.abs(Bm @ X - np.eye(m))))
+
+    # (1) explicit full refactorisation of an intact inverse
+    N.check(lib.lpr_rev_refactor_ex(s._h, 2))
+    N.check(lib.lpr_rev_last_refactor_path(s._h, C.byref(path), C.byref(after)))
+    assert path.value == 2 and after.value < 1e-9
+    X = s.BInverse
+    assert err(X) < 1e-11 and np.max(np.abs(X - exact)) <= 1e-9 * max(1.0, np.max(np.abs(exact)))
+    # (2) multiplicative noise of 1e-3 on every entry: automatic mode; either path must land on the inverse
+    noisy = good * (1.0 + 1e-3 * rng.standard_normal(good.shape))
+    N.check(lib.lpr_rev_write_binv(s._h, N.pd(N.f64(noisy))))
+    N.check(lib.lpr_rev_refactor_ex(s._h, 0))
+    N.check(lib.lpr_rev_refactor_ex(s._h, 0))  # a refresh contracts quadratically: the second one finishes the job
+    assert err(s.BInverse) < 1e-11
+    # (3) garbage: the refresh would diverge (max |I - B X| >= 0.5), the guard must take the full path
+    N.check(lib.lpr_rev_write_binv(s._h, N.pd(N.f64(rng.standard_normal(good.shape)))))
+    N.check(lib.lpr_rev_refactor_ex(s._h, 0))
+    N.check(lib.lpr_rev_last_refactor_path(s._h, C.byref(path), C.byref(after)))
+    assert path.value == 2
+    X = s.BInverse
+    assert err(X) < 1e-11 and np.max(np.abs(X - exact)) <= 1e-9 * max(1.0, np.max(np.abs(exact)))
+    close(s.DualPrices, ref["y"], "y after the full refactorisation")

@@ -570,3 +570,58 @@ def test_model_to_device_equals_list_constructor(tmp_path):
     with Model.from_dense(cc, A, bb).to_device() as e, \
             L.DeviceTableau.from_model(list(cc), [L.Constraint(A[i], "<=", bb[i]) for i in range(40)]) as f:
         assert np.array_equal(e.read().view(np.uint64), f.read().view(np.uint64))
+
+
+@pytest.mark.parametrize("persist", ["0", "1"])
+def test_generic_rules_persistent_and_two_kernel_paths_agree_with_oracle(persist, monkeypatch):
+    """PrimalSimplexSolver2 / DualSimplexSolver / CuttingPlaneSolver loops run by default as ONE cooperative launch
+    (tableau_persistent.cu: redundant selection per CTA, out-of-place update, one grid barrier per pivot);
+    LPR_TAB_PERSIST=0 keeps the two-kernel path.  Both must match the oracle bit for bit on mid-size tableaux."""
+    monkeypatch.setenv("LPR_TAB_PERSIST", persist)
+    rng = np.random.default_rng(77)
+    for R, C in ((40, 100), (150, 333), (257, 700)):
+        T = _random_tableau(rng, R, C)
+        T[1:, :4] = np.abs(T[1:, :4]) + 1
+        for ps in (False, True):
+            ref = O.primal2_solve(T, 10000, ps)
+            with L.DeviceTableau.from_host(T) as t:
+                r = t.solve(L.RULE_PRIMAL2, max_pivots=10000, print_steps=ps)
+                assert r["status"] == ref["status"] and r["log"].tolist() == ref["log"].tolist()
+                assert_bit_equal(t.read(), ref["T"])
+        ref = O.primal2_solve(T, 3, True)
+        with L.DeviceTableau.from_host(T) as t:
+            r = t.solve(L.RULE_PRIMAL2, max_pivots=3, print_steps=True)
+            assert r["status"] == ref["status"] == O.ITER_LIMIT and r["n_pivots"] == ref["n_pivots"]
+            assert_bit_equal(t.read(), ref["T"])
+        T = _random_tableau(rng, R, C, neg_rhs=True)
+        ref = O.dual_solve(T, 10000, True)
+        with L.DeviceTableau.from_host(T) as t:
+            r = t.solve(L.RULE_DUAL, max_pivots=10000, print_steps=True)
+            assert r["status"] == ref["status"] and r["log"].tolist() == ref["log"].tolist()
+            assert_bit_equal(t.read(), ref["T"])
+    for seed in range(3):
+        m, n = 20 + 7 * seed, 30 + 9 * seed
+        A, b, c = O.gen_dense_ip(2000 + seed, m, n)
+        T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+        lp = O.primal_solve(T0, b0)
+        ref = O.cutting_plane(lp["T"], max_cuts=10)
+        with L.DeviceTableau.from_host(lp["T"], row_cap=lp["T"].shape[0] + 12) as t:
+            res = t.cutting_plane(max_cuts=10)
+            assert res["status"] == ref["status"] and res["log"].tolist() == ref["log"].tolist()
+            assert_bit_equal(t.read(), ref["T"])
+
+
+def test_cutting_plane_cfg5_size_matches_oracle():
+    """BASELINE cfg5's root (513 x 1537 relaxation tableau): 32 Gomory cuts with their dual / primal clean-up pivots
+    (what bench.py reports as bb.root_cuts) against orc_cutting_plane: cut log and final tableau bit for bit."""
+    m, n, seed = 512, 1024, 385
+    A, b, c = O.gen_dense_ip(seed, m, n)
+    T0, b0 = O.primal_build(list(c), [(A[i], "<=", b[i]) for i in range(m)])
+    lp = O.primal_solve(T0, b0, threads=8)
+    assert lp["status"] == O.OPTIMAL
+    ref = O.cutting_plane(lp["T"], max_cuts=32)
+    with L.DeviceTableau.from_host(lp["T"], row_cap=lp["T"].shape[0] + 40) as t:
+        res = t.cutting_plane(max_cuts=32)
+        assert res["n_cuts"] == ref["n_cuts"] == 32 and res["status"] == ref["status"]
+        assert res["log"].tolist() == ref["log"].tolist()
+        assert_bit_equal(t.read(), ref["T"])
