@@ -563,7 +563,7 @@ def run_knap_legs(W, O, world, dev):
     try:
         hn, hseed = int(os.environ.get("LPR_BENCH_KNAP_HARD_N", "2000")), 388
         w2, v2, cap2 = W.gen_knapsack_hard(hseed, hn)
-        hard, _ = W.knap_mgpu(w2, v2, cap2, world, max_nodes=int(os.environ.get("LPR_BENCH_KNAP_HARD_NODES", "-1")))
+        hard, _ = W.knap_mgpu(w2, v2, cap2, world, max_nodes=int(os.environ.get("LPR_BENCH_KNAP_HARD_NODES", "600000000")))
         hard["workload"] = f"cfg4-hard: almost strongly correlated n={hn}, seed {hseed}, capacity {cap2:.0f}"
         out["hard"] = hard
     except Exception as ex:

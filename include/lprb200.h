@@ -176,13 +176,14 @@ int lpr_rev_read_xb(lpr_rev* h, double* xb);      /* x_B = B^-1 b :89, m        
 int lpr_rev_read_binv(lpr_rev* h, double* binv);  /* m x m                                  */
 int lpr_rev_last_solve_ms(const lpr_rev* h, float* ms);
 int lpr_rev_last_refactor_ms(const lpr_rev* h, float* ms);
-/* max |I - B X| before the refactorisation (of the new inverse when mode 2 was asked for) and its FP64 flop count */
+/* ||I - B X||_inf before the refactorisation (of the new inverse when mode 2 was asked for) and its FP64 flop count */
 int lpr_rev_last_refactor_info(const lpr_rev* h, double* residual, double* flops);
 /* Refactorisation with an explicit mode.  0 (what lpr_rev_refactor and refactor_every use): Newton-Schulz refresh
- * X <- X + X (I - B X) while the current inverse is usable (max |I - B X| < 0.5), otherwise the full path; 1: refresh
+ * X <- X + X (I - B X) while the current inverse is good (||I - B X||_inf < 1e-5: one step then reaches working
+ * precision), otherwise the full path; 1: refresh
  * only; 2: full refactorisation from the basis columns alone -- blocked Gauss-Jordan inversion with partial pivoting,
  * rank-64 trailing updates on the FP64 tensor cores, residual check and one polishing step.  lpr_rev_last_refactor_path:
- * which path ran (1 refresh, 2 full) and max |I - B X| of the result of the full path. */
+ * which path ran (1 refresh, 2 full) and ||I - B X||_inf of the result of the full path (before its polishing step). */
 int lpr_rev_refactor_ex(lpr_rev* h, int mode);
 int lpr_rev_last_refactor_path(const lpr_rev* h, int* path, double* residual_after);
 int lpr_rev_write_binv(lpr_rev* h, const double* binv); /* overwrite B^-1 (m x m row major) */
@@ -275,6 +276,8 @@ int lpr_knap_solve(int device, double capacity, int n, const double* weights,
  * n_gpus.  n_gpus = 1 needs no NCCL; with n_gpus > 1 a missing libnccl.so.2 is LPR_E_NCCL (no fallback). */
 typedef struct lpr_mgpu_stats {
   int n_gpus, nccl_version;
+  int ranks_per_gpu, reserved; /* pools (host thread + stream each) per device: LPR_MG_RANKS_PER_GPU, default 2 for
+                                  B&B simplex (child construction of one pool overlaps the pivot chains of the other) */
   int64_t rounds, steals, nodes_moved, open_left, depth_overflow;
   double seconds;       /* seeding + rounds, max over the ranks */
   double setup_seconds; /* pool creation, NCCL communicator and channel set-up */

@@ -30,7 +30,8 @@ vp = C.c_void_p
 
 class MgpuStats(C.Structure):
     """lpr_mgpu_stats of include/lprb200.h"""
-    _fields_ = [("n_gpus", C.c_int), ("nccl_version", C.c_int), ("rounds", C.c_int64), ("steals", C.c_int64),
+    _fields_ = [("n_gpus", C.c_int), ("nccl_version", C.c_int), ("ranks_per_gpu", C.c_int), ("reserved", C.c_int),
+                ("rounds", C.c_int64), ("steals", C.c_int64),
                 ("nodes_moved", C.c_int64), ("open_left", C.c_int64), ("depth_overflow", C.c_int64),
                 ("seconds", C.c_double), ("setup_seconds", C.c_double), ("seed_seconds", C.c_double),
                 ("exchange_seconds", C.c_double), ("steal_seconds", C.c_double), ("nodes_per_gpu", C.c_int64 * 16),
@@ -38,7 +39,7 @@ class MgpuStats(C.Structure):
 
     def as_dict(self):
         n = self.n_gpus
-        return dict(n_gpus=n, nccl_version=self.nccl_version, rounds=self.rounds, steals=self.steals,
+        return dict(n_gpus=n, nccl_version=self.nccl_version, ranks_per_gpu=self.ranks_per_gpu, rounds=self.rounds, steals=self.steals,
                     nodes_moved=self.nodes_moved, open_left=self.open_left, depth_overflow=self.depth_overflow,
                     seconds=self.seconds, setup_seconds=self.setup_seconds, seed_seconds=self.seed_seconds,
                     exchange_seconds=self.exchange_seconds, steal_seconds=self.steal_seconds,

@@ -802,6 +802,12 @@ static inline double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// pools created by the multi-GPU driver share a device: each carves 1/n of the slab budget (multi_gpu.cu)
+static std::atomic<int> g_prealloc_share{1};
+namespace lpr {
+void bb_set_prealloc_share(int pools_per_device) { g_prealloc_share.store(std::max(1, pools_per_device)); }
+}
+
 static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processed_out, int64_t* pivots_out,
                       bool* hit_limit, double max_seconds = 0.0) {
   int rc = select_device(h->device);
@@ -1017,9 +1023,10 @@ static int bb_create_empty(int device, int rows, int cols, int n_vars, int enabl
   }
   {  // pre-carve slabs so that steady-state node processing never calls cudaMalloc
     const char* pm = getenv("LPR_BB_PREALLOC_MB");
-    size_t want = (size_t)(pm ? std::max(0, atoi(pm)) : 1024) << 20;
+    const int share = std::max(1, g_prealloc_share.load());
+    size_t want = ((size_t)(pm ? std::max(0, atoi(pm)) : 1024) << 20) / share;
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) want = std::min(want, free_b - free_b / 4);
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) want = std::min(want, (free_b - free_b / 4) / share);
     size_t nsl = want / (sizeof(double) * h->slab_doubles);
     while (nsl > 0) {
       const size_t take = std::min<size_t>(nsl, 512);
@@ -1154,25 +1161,31 @@ int lpr_bb_export_nodes(lpr_bb* h, int max_nodes, void* buf, int64_t buf_cap, in
   char* p = (char*)buf;
   int64_t used = 0;
   int n = 0;
-  // shallowest nodes sit at the bottom of the stack: give those away (largest subtrees)
-  while (n < max_nodes && !h->open.empty()) {
-    BBNode& nd = h->open.front();
+  // shallowest nodes sit at the bottom of the stack: give those away (largest subtrees); the copies go through the
+  // handle's stream and are waited for once, at the end (the caller hands `buf` to NCCL on another stream)
+  size_t first = 0;
+  std::vector<std::vector<char>> heads;
+  while (n < max_nodes && first < h->open.size()) {
+    BBNode& nd = h->open[first];
     const int64_t kl = (int64_t)nd.key.size(), kpad = (kl + 7) / 8 * 8;
     const int64_t need = 16 + kpad + (int64_t)sizeof(double) * nd.R * nd.C;
     if (used + need > buf_cap) break;
-    std::vector<char> head(16 + kpad, 0);
+    heads.emplace_back(16 + kpad, 0);
+    std::vector<char>& head = heads.back();
     int32_t hdr[4] = {nd.R, nd.C, nd.depth, (int32_t)kl};
     memcpy(head.data(), hdr, 16);
     if (kl) memcpy(head.data() + 16, nd.key.data(), kl);
-    // cudaMemcpyDefault: buf may be pageable/pinned host memory or device memory (NCCL staging tensor)
-    LPR_CUDA(cudaMemcpy(p + used, head.data(), head.size(), cudaMemcpyDefault));
-    LPR_CUDA(cudaMemcpy2D(p + used + 16 + kpad, sizeof(double) * nd.C, nd.slab, sizeof(double) * h->ldmax,
-                          sizeof(double) * nd.C, nd.R, cudaMemcpyDefault));
+    // cudaMemcpyDefault: buf may be pageable/pinned host memory or device memory (NCCL staging buffer)
+    LPR_CUDA(cudaMemcpyAsync(p + used, head.data(), head.size(), cudaMemcpyDefault, h->stream));
+    LPR_CUDA(cudaMemcpy2DAsync(p + used + 16 + kpad, sizeof(double) * nd.C, nd.slab, sizeof(double) * h->ldmax,
+                               sizeof(double) * nd.C, nd.R, cudaMemcpyDefault, h->stream));
     used += need;
-    bb_give_slab(h, nd.slab);
-    h->open.erase(h->open.begin());
+    first++;
     n++;
   }
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < first; i++) bb_give_slab(h, h->open[i].slab);
+  h->open.erase(h->open.begin(), h->open.begin() + (ptrdiff_t)first);  // one erase, not one per node
   *bytes = used;
   *n_exported = n;
   return LPR_OK;

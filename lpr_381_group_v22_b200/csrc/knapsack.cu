@@ -670,13 +670,17 @@ int lpr_knap_export_nodes(lpr_knap* h, int max_nodes, void* buf, int64_t buf_cap
   long long k = std::min<long long>(std::min<long long>(max_nodes, h->open), (long long)(buf_cap / (int64_t)rb));
   if (k < 0) k = 0;
   if (k > 0) {
-    LPR_CUDA(cudaMemcpy(buf, h->pool, rb * k, cudaMemcpyDefault));  // buf: host or device
+    // on the handle's stream and waited for: a device-to-device cudaMemcpy returns before the copy has run, and the
+    // caller hands `buf` to NCCL on another stream right away
+    LPR_CUDA(cudaMemcpyAsync(buf, h->pool, rb * k, cudaMemcpyDefault, h->stream));  // buf: host or device
     // close the gap: move the top k records into the hole (order inside the pool does not matter,
     // the DFS keys decide ties)
     const long long rest = h->open - k;
     const long long mv = std::min(k, rest);
     if (mv > 0)
-      LPR_CUDA(cudaMemcpy(h->pool, h->pool + (size_t)(h->open - mv) * h->rec_words, rb * mv, cudaMemcpyDeviceToDevice));
+      LPR_CUDA(cudaMemcpyAsync(h->pool, h->pool + (size_t)(h->open - mv) * h->rec_words, rb * mv,
+                               cudaMemcpyDeviceToDevice, h->stream));
+    LPR_CUDA(cudaStreamSynchronize(h->stream));
     h->open -= k;
   }
   *bytes = (int64_t)(rb * k);
@@ -692,7 +696,10 @@ int lpr_knap_import_nodes(lpr_knap* h, const void* buf, int64_t bytes) {
   if (bytes % (int64_t)rb) return fail(LPR_E_BADARG, "byte count is not a multiple of the record size");
   const long long k = bytes / (int64_t)rb;
   if (h->open + k > h->pool_cap) return fail(LPR_E_CAPACITY, "knapsack node pool full");
-  if (k > 0) LPR_CUDA(cudaMemcpy(h->pool + (size_t)h->open * h->rec_words, buf, rb * k, cudaMemcpyDefault));
+  if (k > 0) {
+    LPR_CUDA(cudaMemcpyAsync(h->pool + (size_t)h->open * h->rec_words, buf, rb * k, cudaMemcpyDefault, h->stream));
+    LPR_CUDA(cudaStreamSynchronize(h->stream));  // `buf` may be reused by the caller as soon as this returns
+  }
   h->open += k;
   return LPR_OK;
 }

@@ -30,6 +30,10 @@
 
 #include "common.cuh"
 
+namespace lpr {
+void bb_set_prealloc_share(int pools_per_device);  // bb.cu: pools created from now on carve 1/n of LPR_BB_PREALLOC_MB
+}
+
 namespace {
 
 using namespace lpr;
@@ -323,11 +327,16 @@ struct Config {
   int64_t chunk_nodes = 4096;  // at most this many nodes per rank and round
   int64_t seed_nodes_per_rank = 8, low_water = 0;
   size_t stage_bytes = 256u << 20;
+  int ranks_per_gpu = 1;  // pools (host thread + stream each) per device: their kernels overlap on the GPU
 };
 
 struct Shared {
-  explicit Shared(int n) : barrier(n), slots(n), rc(n, LPR_OK), err(n), nodes(n, 0), run_s(n, 0.0), plan_bytes(64, 0) {}
+  explicit Shared(int n)
+      : barrier(n), slots(n), rc(n, LPR_OK), err(n), nodes(n, 0), run_s(n, 0.0), plan_bytes(64, 0),
+        vec_slots((size_t)n * (4 + n), 0.0), vec_result(4 + n, 0.0), stage_out_ptr(n, nullptr), stage_in_ptr(n, nullptr) {}
   Barrier barrier;
+  std::vector<double> vec_slots, vec_result;          // per-round status vectors of every rank / their maximum
+  std::vector<uint8_t*> stage_out_ptr, stage_in_ptr;  // device staging buffers of every rank (steals)
   std::vector<Incumbent> slots;
   std::vector<int> rc;
   std::vector<std::string> err;
@@ -342,8 +351,16 @@ struct Shared {
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-void rank_main(int rank, int world, int device, Pool* pool, ncclComm_t comm, const Config& cfg, Shared* sh) {
+// Ranks are host threads.  With ranks_per_gpu > 1 several pools share a device (each with its own stream, so the
+// bandwidth-bound child construction of one overlaps the latency-bound pivot chains of another); the first rank of a
+// device is its leader and owns the device's NCCL communicator: status vectors are combined in host memory inside a
+// device and all-reduced over NCCL between the leaders, node records move with cudaMemcpyAsync inside a device and
+// with ncclSend / ncclRecv (issued by the leaders) between devices.
+void rank_main(int rank, int world, int rpg, int device, Pool* pool, ncclComm_t comm, const Config& cfg, Shared* sh) {
   NcclApi& api = nccl_api();
+  const int gpu = rank / rpg, n_gpus = world / rpg;
+  const bool leader = rank % rpg == 0;
+  auto gpu_of = [&](int r) { return r / rpg; };
   int rc = LPR_OK;
   auto note = [&](int code) {  // remember the first failure of this rank (the message is thread local)
     if (code != LPR_OK && rc == LPR_OK) {
@@ -367,17 +384,33 @@ void rank_main(int rank, int world, int device, Pool* pool, ncclComm_t comm, con
     if (world > 1) {
       cuda_ok(cudaMalloc(&stage_out, cfg.stage_bytes), "cudaMalloc(stage)");
       cuda_ok(cudaMalloc(&stage_in, cfg.stage_bytes), "cudaMalloc(stage)");
+      sh->stage_out_ptr[rank] = stage_out;
+      sh->stage_in_ptr[rank] = stage_in;
     }
   }
+  // MAX over every rank's vector: host memory inside a device, ncclAllReduce between the devices' leaders
   auto allreduce = [&]() {
-    if (world == 1 || !d_vec) return;
-    cudaError_t e = cudaMemcpyAsync(d_vec, h_vec, sizeof(double) * nvec, cudaMemcpyHostToDevice, stream);
-    int nr = 0;
-    if (e == cudaSuccess) nr = api.AllReduce(d_vec, d_vec, nvec, kNcclFloat64, kNcclMax, comm, stream);
-    if (e == cudaSuccess && nr == 0) e = cudaMemcpyAsync(h_vec, d_vec, sizeof(double) * nvec, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess && nr == 0) e = cudaStreamSynchronize(stream);
-    if (nr != 0) note(fail(LPR_E_NCCL, "ncclAllReduce failed: %s", api.GetErrorString(nr)));
-    cuda_ok(e, "incumbent all-reduce");
+    if (world == 1 || !h_vec) return;
+    double* slot = &sh->vec_slots[(size_t)rank * nvec];
+    for (int i = 0; i < nvec; i++) slot[i] = h_vec[i];
+    sh->barrier.wait();
+    if (leader) {
+      for (int r = gpu * rpg + 1; r < (gpu + 1) * rpg; r++)
+        for (int i = 0; i < nvec; i++) h_vec[i] = std::max(h_vec[i], sh->vec_slots[(size_t)r * nvec + i]);
+      if (n_gpus > 1) {
+        cudaError_t e = cudaMemcpyAsync(d_vec, h_vec, sizeof(double) * nvec, cudaMemcpyHostToDevice, stream);
+        int nr = 0;
+        if (e == cudaSuccess) nr = api.AllReduce(d_vec, d_vec, nvec, kNcclFloat64, kNcclMax, comm, stream);
+        if (e == cudaSuccess && nr == 0) e = cudaMemcpyAsync(h_vec, d_vec, sizeof(double) * nvec, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && nr == 0) e = cudaStreamSynchronize(stream);
+        if (nr != 0) note(fail(LPR_E_NCCL, "ncclAllReduce failed: %s", api.GetErrorString(nr)));
+        cuda_ok(e, "incumbent all-reduce");
+      }
+      if (rank == 0)
+        for (int i = 0; i < nvec; i++) sh->vec_result[i] = h_vec[i];
+    }
+    sh->barrier.wait();
+    for (int i = 0; i < nvec; i++) h_vec[i] = sh->vec_result[i];
   };
   sh->rc[rank] = rc;
   sh->barrier.wait();  // every pool exists -- or some rank failed to set up, which all ranks learn here, before NCCL
@@ -455,13 +488,11 @@ void rank_main(int rank, int world, int device, Pool* pool, ncclComm_t comm, con
       std::vector<Steal> plan = steal_plan(counts, cfg.low_water);
       if (!plan.empty()) {
         if (plan.size() > sh->plan_bytes.size()) plan.resize(sh->plan_bytes.size());
-        std::vector<int64_t> off(plan.size(), 0);
         int64_t used = 0;
         for (size_t k = 0; k < plan.size(); k++) {
           if (plan[k].donor != rank) continue;
           int64_t bytes = 0;
           int n = 0;
-          off[k] = used;
           if (rc == LPR_OK)
             note(pool->export_nodes((int)std::min<int64_t>(plan[k].give, 1 << 30), stage_out + used,
                                     (int64_t)cfg.stage_bytes - used, &bytes, &n));
@@ -473,32 +504,40 @@ void rank_main(int rank, int world, int device, Pool* pool, ncclComm_t comm, con
             moved += n;
           }
         }
-        sh->barrier.wait();  // byte counts of every transfer are known to both ends
-        int64_t in_used = 0;
-        std::vector<int64_t> in_off(plan.size(), 0);
-        int nr = api.GroupStart();
-        for (size_t k = 0; k < plan.size() && nr == 0; k++) {
+        sh->barrier.wait();  // byte counts of every transfer are known to everybody
+        auto out_off = [&](size_t k) {  // where transfer k starts in its donor's staging buffer
+          int64_t o = 0;
+          for (size_t q = 0; q < k; q++)
+            if (plan[q].donor == plan[k].donor) o += sh->plan_bytes[q];
+          return o;
+        };
+        // inside a device the receiver copies; between devices the leaders of both ends drive NCCL
+        for (size_t k = 0; k < plan.size(); k++) {
           const int64_t bytes = sh->plan_bytes[k];
-          if (bytes <= 0) continue;
-          if (plan[k].donor == rank) nr = api.Send(stage_out + off[k], (size_t)bytes, kNcclUint8, plan[k].recv, comm, stream);
-          if (plan[k].recv == rank) {
-            in_off[k] = in_used;
-            if (in_used + bytes > (int64_t)cfg.stage_bytes) {
-              note(fail(LPR_E_CAPACITY, "steal staging buffer too small"));
-              continue;
-            }
-            nr = api.Recv(stage_in + in_used, (size_t)bytes, kNcclUint8, plan[k].donor, comm, stream);
-            in_used += bytes;
-          }
+          if (bytes <= 0 || plan[k].recv != rank || gpu_of(plan[k].donor) != gpu) continue;
+          cuda_ok(cudaMemcpyAsync(stage_in, sh->stage_out_ptr[plan[k].donor] + out_off(k), (size_t)bytes,
+                                  cudaMemcpyDeviceToDevice, stream), "node transfer inside a device");
         }
-        const int ne = api.GroupEnd();
-        if (nr == 0) nr = ne;
-        if (nr != 0) note(fail(LPR_E_NCCL, "node transfer failed: %s", api.GetErrorString(nr)));
+        if (leader && n_gpus > 1) {
+          int nr = api.GroupStart();
+          for (size_t k = 0; k < plan.size() && nr == 0; k++) {
+            const int64_t bytes = sh->plan_bytes[k];
+            const int gd = gpu_of(plan[k].donor), gr = gpu_of(plan[k].recv);
+            if (bytes <= 0 || gd == gr) continue;
+            if (gd == gpu)
+              nr = api.Send(sh->stage_out_ptr[plan[k].donor] + out_off(k), (size_t)bytes, kNcclUint8, gr, comm, stream);
+            if (gr == gpu && nr == 0)  // a receiver appears once in a plan: its staging buffer is filled from the start
+              nr = api.Recv(sh->stage_in_ptr[plan[k].recv], (size_t)bytes, kNcclUint8, gd, comm, stream);
+          }
+          const int ne = api.GroupEnd();
+          if (nr == 0) nr = ne;
+          if (nr != 0) note(fail(LPR_E_NCCL, "node transfer failed: %s", api.GetErrorString(nr)));
+        }
         cuda_ok(cudaStreamSynchronize(stream), "node transfer");
+        sh->barrier.wait();  // every record has landed
         for (size_t k = 0; k < plan.size(); k++)
           if (plan[k].recv == rank && sh->plan_bytes[k] > 0 && rc == LPR_OK)
-            note(pool->import_nodes(stage_in + in_off[k], sh->plan_bytes[k]));
-        sh->barrier.wait();  // plan_bytes may be rewritten
+            note(pool->import_nodes(stage_in, sh->plan_bytes[k]));
       }
     }
     const double tc = now_s();
@@ -563,28 +602,32 @@ int solve_mgpu(int n_gpus, const int* devices, const Config& cfg, MakePool make_
     int rc = get_comms(devs, &cs);
     if (rc) return rc;
   }
-  Shared* sh = new Shared(n_gpus);
-  std::vector<Pool*> pools(n_gpus);
-  for (int r = 0; r < n_gpus; r++) pools[r] = make_pool();
+  const int rpg = std::max(1, std::min(cfg.ranks_per_gpu, 8));
+  const int world = n_gpus * rpg;
+  Shared* sh = new Shared(world);
+  std::vector<Pool*> pools(world);
+  for (int r = 0; r < world; r++) pools[r] = make_pool();
   const double t0 = now_s();
   std::vector<std::thread> threads;
-  for (int r = 1; r < n_gpus; r++)
-    threads.emplace_back(rank_main, r, n_gpus, devs[r], pools[r], cs ? cs->comms[r] : nullptr, std::cref(cfg), sh);
-  rank_main(0, n_gpus, devs[0], pools[0], cs ? cs->comms[0] : nullptr, cfg, sh);
+  auto comm_of = [&](int r) { return (cs && r % rpg == 0) ? cs->comms[r / rpg] : (ncclComm_t) nullptr; };
+  for (int r = 1; r < world; r++)
+    threads.emplace_back(rank_main, r, world, rpg, devs[r / rpg], pools[r], comm_of(r), std::cref(cfg), sh);
+  rank_main(0, world, rpg, devs[0], pools[0], comm_of(0), cfg, sh);
   for (auto& t : threads) t.join();
   const double dt = now_s() - t0;
   for (Pool* p : pools) delete p;
   cudaSetDevice(devs[0]);
-  for (int r = 0; r < n_gpus; r++)
+  for (int r = 0; r < world; r++)
     if (sh->rc[r] != LPR_OK) {
       const int rc = sh->rc[r];
       const std::string msg = sh->err[r];
       delete sh;
-      return fail(rc, "rank %d (device %d): %s", r, devs[r], msg.c_str());
+      return fail(rc, "rank %d (device %d): %s", r, devs[r / rpg], msg.c_str());
     }
   if (stats) {
     memset(stats, 0, sizeof *stats);
     stats->n_gpus = n_gpus;
+    stats->ranks_per_gpu = rpg;
     stats->nccl_version = n_gpus > 1 ? nccl_api().version : 0;
     stats->rounds = sh->rounds;
     stats->steals = sh->steals;
@@ -596,9 +639,11 @@ int solve_mgpu(int n_gpus, const int* devices, const Config& cfg, MakePool make_
     stats->seed_seconds = sh->t_seed;
     stats->exchange_seconds = sh->t_exchange;
     stats->steal_seconds = sh->t_steal;
-    for (int r = 0; r < n_gpus && r < 16; r++) {
-      stats->nodes_per_gpu[r] = sh->nodes[r];
-      stats->run_seconds_per_gpu[r] = sh->run_s[r];
+    for (int r = 0; r < world; r++) {
+      const int g = r / rpg;
+      if (g >= 16) break;
+      stats->nodes_per_gpu[g] += sh->nodes[r];
+      stats->run_seconds_per_gpu[g] = std::max(stats->run_seconds_per_gpu[g], sh->run_s[r]);
     }
   }
   *inc_out = sh->final_inc;
@@ -625,9 +670,15 @@ int lpr_bb_solve_mgpu(int n_gpus, const int* devices, int rows, int cols, const 
   cfg.low_water = 0;
   const char* sm = getenv("LPR_MG_STAGE_MB");
   cfg.stage_bytes = (size_t)(sm ? std::max(16, atoi(sm)) : 512) << 20;
+  // two pools per device by default: the child construction of one (HBM bound) runs beside the pivot chains of the
+  // other (latency bound); each gets its share of the slab budget
+  const char* rp = getenv("LPR_MG_RANKS_PER_GPU");
+  cfg.ranks_per_gpu = rp ? std::max(1, atoi(rp)) : 2;
+  bb_set_prealloc_share(cfg.ranks_per_gpu);
   Incumbent inc;
   Shared* sh = nullptr;
   int rc = solve_mgpu(n_gpus, devices, cfg, [&]() -> Pool* { return new BBPoolC(prob); }, &inc, &sh, stats);
+  bb_set_prealloc_share(1);
   if (rc) return rc;
   int64_t total = 0;
   for (int64_t c : sh->nodes) total += c;
@@ -656,6 +707,8 @@ int lpr_knap_solve_mgpu(int n_gpus, const int* devices, double capacity, int n, 
   cfg.low_water = 64;
   const char* sm = getenv("LPR_MG_STAGE_MB");
   cfg.stage_bytes = (size_t)(sm ? std::max(16, atoi(sm)) : 256) << 20;
+  const char* rp = getenv("LPR_MG_KNAP_RANKS_PER_GPU");
+  cfg.ranks_per_gpu = rp ? std::max(1, atoi(rp)) : 1;
   Incumbent inc;
   Shared* sh = nullptr;
   int rc = solve_mgpu(n_gpus, devices, cfg, [&]() -> Pool* { return new KnapPoolC(prob); }, &inc, &sh, stats);

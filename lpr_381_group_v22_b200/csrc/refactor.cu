@@ -4,7 +4,7 @@
 //
 // B^-1 is maintained by product-form updates (revised.cu k_update) whose rounding errors accumulate.  Two paths:
 //
-//  (1) cheap refresh, used while the current inverse X is still a good one (max |I - B X| < 0.5): one Newton-Schulz
+//  (1) cheap refresh, used while the current inverse X is still a good one (||I - B X||_inf < 1e-5): one Newton-Schulz
 //      step   R = I - B X,   X' = X + X R   (quadratic error contraction) = two m^3 FP64 GEMMs;
 //  (2) full refactorisation FROM THE BASIS COLUMNS ALONE, used when X is unusable (the guard above fails, or the
 //      caller asks): blocked Gauss-Jordan inversion with partial pivoting.  With M = B and X = I, for every 64-column
@@ -148,18 +148,29 @@ __global__ void k_scatter_binv(double* Binv, int ldB, int m, const double* Xn, i
   const int i = blockIdx.y;
   if (j < m) Binv[(size_t)i * ldB + j] = Xn[(size_t)i * np + j];
 }
-__global__ void k_absmax(const double* R, size_t count, double* out) {
+// infinity norm of the n x n residual: max over rows of sum_j |R[i][j]| (one warp per row).  ||I - B X||_inf < 1 is a
+// sufficient condition for the Newton-Schulz refresh to contract (||E'|| <= ||E||^2); the largest entry alone is not.
+__global__ void k_inf_norm(const double* R, int n, int ld, double* out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   double mx = 0.0;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (size_t)gridDim.x * blockDim.x)
-    mx = fmax(mx, fabs(R[k]));
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(out), __double_as_longlong(mx));
+  for (int i = warp; i < n; i += nwarps) {
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) s += fabs(R[(size_t)i * ld + j]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (!(s <= mx)) mx = s;  // NaN propagates
+  }
+  if (lane == 0) {
+    if (mx != mx) mx = __longlong_as_double(0x7ff0000000000000LL);  // NaN -> +inf: never accepted by the guard
+    atomicMax(reinterpret_cast<unsigned long long*>(out), __double_as_longlong(mx));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // full refactorisation: blocked Gauss-Jordan inversion with partial pivoting
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int NB = 64;  // panel width = GEMM tile height: the pivot block K is exactly one tile row
+constexpr double kRefreshGuard = 1e-5;  // ||I - B X||_inf below which the Newton-Schulz refresh is used
 
 __global__ void k_set_identity(double* X, int np) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -479,7 +490,7 @@ int refactor_binv(cudaStream_t stream, int m, int n, const double* A, int ldA, d
   auto residual = [&](const double* X, double* out_host, int slot) -> int {  // Rm = I - B X, max |Rm|
     k_dgemm<<<grid, 128, 0, stream>>>(np, np, -1.0, Bm, X, 0.0, nullptr, 1, Rm);
     cudaMemsetAsync(ws.d_res + slot, 0, sizeof(double), stream);
-    k_absmax<<<296, 256, 0, stream>>>(Rm, (size_t)np * np, ws.d_res + slot);
+    k_inf_norm<<<296, 256, 0, stream>>>(Rm, np, np, ws.d_res + slot);
     count_launch(2);
     flops += 2.0 * (double)np * np * np;
     LPR_CUDA(cudaMemcpyAsync(out_host, ws.d_res + slot, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -492,14 +503,16 @@ int refactor_binv(cudaStream_t stream, int m, int n, const double* A, int ldA, d
   const double* result = nullptr;
   if (mode != 2) {
     if ((rc = residual(Xp, &res0, 0))) return rc;
-    if (mode == 1 || (res0 == res0 && res0 < 0.5)) {
+    // refresh only while it finishes the job in ONE step (error e -> e^2): beyond 1e-5 a chain of refreshes costs more
+    // than the full path, beyond 1 it diverges
+    if (mode == 1 || (res0 == res0 && res0 < kRefreshGuard)) {
       // X' = X + X R   (written over Bm: B is not needed any more on this path)
       k_dgemm<<<grid, 128, 0, stream>>>(np, np, 1.0, Xp, Rm, 1.0, Xp, 0, Bm);
       count_launch();
       flops += 2.0 * (double)np * np * np;
       result = Bm;
       path = 1;
-      res1 = res0 * res0 * np;  // bound, not measured: the refresh is the cheap path
+      res1 = res0 * res0;  // bound (||E'|| <= ||E||^2), not measured: the refresh is the cheap path
     }
   }
   if (!result) {

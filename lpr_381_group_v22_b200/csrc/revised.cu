@@ -169,17 +169,26 @@ __device__ int rev_hyst_min(int n, Cand cand, double b0, double eps, MinIdx* sm,
   }
   bad = block_sum_int(bad, smi);
   if (bad == 0) return m.i;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {  // literal replay, one ballot per 32 candidates (see block_hyst_min in select.cuh)
+    const int lane = threadIdx.x;
     double best = b0;
     int idx = -1;
-    for (int k = 0; k < n; k++) {
-      double val;
-      if (cand(k, val) && val < __dsub_rn(best, eps)) {
-        best = val;
-        idx = k;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      double val = 0.0;
+      const bool ok = k < n && cand(k, val);
+      int from = 0;
+      while (true) {
+        const bool acc = ok && lane >= from && val < __dsub_rn(best, eps);
+        const unsigned mask = __ballot_sync(0xffffffffu, acc);
+        if (!mask) break;
+        const int l = __ffs(mask) - 1;
+        best = __shfl_sync(0xffffffffu, val, l);
+        idx = base + l;
+        from = l + 1;
       }
     }
-    sh_res = idx;
+    if (lane == 0) sh_res = idx;
   }
   __syncthreads();
   int r = sh_res;
@@ -852,7 +861,8 @@ int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status,
   int slot = 0, pending = 0, bsize = std::min(batch, 2);
   long long launched = 0;
   long long next_refactor = refactor_every > 0 ? refactor_every : -1;
-  while (true) {
+  bool finished = false;
+  while (!finished) {
     for (int q = 0; q < bsize; q++) {
       if (rev_launch(k_price, gp, kT, h->stream, v) || rev_launch(k_rc, dim3((n + kT - 1) / kT), kT, h->stream, v) ||
           rev_launch(k_enter, dim3(1), 1024, h->stream, v) || rev_launch(k_dir, dim3(gdir), kT, h->stream, v) ||
@@ -865,13 +875,19 @@ int lpr_rev_solve(lpr_rev* h, int64_t max_iter, int refactor_every, int* status,
         LPR_CUDA(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(RevState), cudaMemcpyDeviceToHost, h->stream));
         LPR_CUDA(cudaStreamSynchronize(h->stream));
         pending = 0;
-        if (h->st_host[0].status == LPR_RUNNING) {
-          rc = lpr_rev_refactor(h);
-          if (rc) return rc;
+        if (h->st_host[0].status != LPR_RUNNING) {
+          // the run ended before this refactorisation point: stop here.  (Resetting `pending` and carrying on used
+          // to starve the status check below whenever every batch contained a refactorisation point: an endless
+          // stream of no-op launches once refactor_every <= batch.)
+          finished = true;
+          break;
         }
+        rc = lpr_rev_refactor(h);
+        if (rc) return rc;
         next_refactor += refactor_every;
       }
     }
+    if (finished) break;
     LPR_CUDA(cudaMemcpyAsync(&h->st_host[slot], h->st, sizeof(RevState), cudaMemcpyDeviceToHost, h->stream));
     LPR_CUDA(cudaEventRecord(h->evb[slot], h->stream));
     pending++;

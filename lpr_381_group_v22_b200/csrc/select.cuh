@@ -33,17 +33,31 @@ __device__ int block_hyst_min(int n, Cand cand, double b0, double eps, MinIdx* s
   }
   bad = block_sum_int(bad, smi);
   if (bad == 0) return m.i;
-  if (threadIdx.x == 0) {
+  // literal replay of the sequential scan, 32 candidates at a time by warp 0: inside a chunk the next element the scan
+  // accepts is the first lane (at or after the last accepted one) whose value beats the current best by more than eps
+  // -- earlier lanes were tested against the same best and rejected -- so one ballot finds it; acceptances are rare
+  // (each lowers the best by more than eps), a chunk without one costs a single ballot.  Integer-valued tableaux tie
+  // all the time (cfg5: nearly every pivot), which made the single-thread replay the most expensive step of a pivot.
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
     double best = b0;
     int idx = -1;
-    for (int k = 0; k < n; k++) {
-      double val;
-      if (cand(k, val) && val < __dsub_rn(best, eps)) {
-        best = val;
-        idx = k;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      double val = 0.0;
+      const bool ok = k < n && cand(k, val);
+      int from = 0;
+      while (true) {
+        const bool acc = ok && lane >= from && val < __dsub_rn(best, eps);
+        const unsigned mask = __ballot_sync(0xffffffffu, acc);
+        if (!mask) break;
+        const int l = __ffs(mask) - 1;
+        best = __shfl_sync(0xffffffffu, val, l);
+        idx = base + l;
+        from = l + 1;
       }
     }
-    sh_res = idx;
+    if (lane == 0) sh_res = idx;
   }
   __syncthreads();
   int r = sh_res;

@@ -104,7 +104,9 @@ class BBPool:
     def export_nodes(self, max_nodes, torch_device=None):
         md = self.stats()["max_depth"]
         per = 16 + md + 16 + 8 * (self.rows + md) * (self.cols + md)  # header + key + deepest possible tableau
-        cap = int(per) * max(1, max_nodes)
+        # the exporter stops when the buffer is full, so a steal is capped in bytes (256 MB) instead of sizing the
+        # buffer for `max_nodes` records of the deepest possible tableau (which asked for gigabytes per steal)
+        cap = max(int(per), min(int(per) * max(1, max_nodes), 256 << 20))
         buf, ptr = _alloc_bytes(cap, torch_device)
         nbytes, n = C.c_int64(), C.c_int()
         N.check(N.lib().lpr_bb_export_nodes(self._h, max_nodes, ptr, cap, C.byref(nbytes), C.byref(n)))

@@ -382,3 +382,17 @@ def test_bb_depth_overflow_is_reported(monkeypatch):
     bb.SetNumVars(n)
     bb.ExecuteBranchAndBound([Tf], True, max_nodes=-1)
     assert bb.LastRun["status"] == L.DEPTH_LIMIT
+
+
+@pytest.mark.parametrize("rpg", ["1", "2", "3"])
+def test_bb_solve_mgpu_several_pools_per_device(rpg, monkeypatch):
+    """ranks_per_gpu > 1: several pools (host thread + stream each) share one device; their status vectors are combined
+    in host memory and node records move with device-to-device copies (no NCCL inside a device).  Same incumbent."""
+    monkeypatch.setenv("LPR_MG_RANKS_PER_GPU", rpg)
+    seed, m, n, div = MID[3]
+    Tf = binary_ip_final(seed, m, n, div)
+    ref = O.bb_solve(Tf, n, prune=True, max_nodes=-1, log_cap=1 << 16)
+    r = L.solve_bb_mgpu(Tf, n, True, n_gpus=1, slice_seconds=1e-3)
+    assert r["status"] == L.OPTIMAL and r["stats"]["open_left"] == 0 and r["stats"]["ranks_per_gpu"] == int(rpg)
+    assert r["z"] == ref["z"]
+    assert_bit_equal(r["x"], ref["x"], "incumbent")

@@ -158,3 +158,22 @@ def test_node_budget_and_time_slices(batch, monkeypatch):
         assert inc[0] == ref["best"] and inc[2].astype(np.uint8).tolist() == ref["chosen"].tolist()
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("rpg", ["2", "4"])
+def test_knap_mgpu_several_pools_per_device_steal_inside_the_device(rpg, monkeypatch):
+    monkeypatch.setenv("LPR_MG_KNAP_RANKS_PER_GPU", rpg)
+    w, v, cap = O.gen_knapsack(19, 500)
+    ref = O.knap_bb(cap, w, v)
+    s = L.KnapsackBranchBoundSimplex(cap, w, v, n_gpus=2)  # n_gpus > 1 selects the driver; ...
+    import ctypes as C
+    best, nodes, st = C.c_double(), C.c_int64(), C.c_int()
+    ch = np.zeros(len(w), dtype=np.uint8)
+    stats = N.MgpuStats()
+    N.check(N.lib().lpr_knap_solve_mgpu(1, None, cap, len(w), N.pd(N.f64(w)), N.pd(N.f64(v)), -1, -1, 2e-4,
+                                        C.byref(best), ch.ctypes.data_as(N.bp), C.byref(nodes), C.byref(st),
+                                        C.byref(stats)))
+    assert st.value == L.OPTIMAL and stats.open_left == 0 and stats.ranks_per_gpu == int(rpg)
+    assert best.value == ref["best"] and ch.tolist() == ref["chosen"].tolist()
+    assert stats.steals > 0  # the root starts on rank 0: the other pools only get work by stealing
+    del s

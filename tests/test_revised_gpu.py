@@ -233,12 +233,18 @@ def test_full_refactorisation_from_the_basis_columns(m, n, seed):
     assert path.value == 2 and after.value < 1e-9
     X = s.BInverse
     assert err(X) < 1e-11 and np.max(np.abs(X - exact)) <= 1e-9 * max(1.0, np.max(np.abs(exact)))
-    # (2) multiplicative noise of 1e-3 on every entry: automatic mode; either path must land on the inverse
+    # (2) multiplicative noise of 1e-3 on every entry: too far for a one-step refresh, the guard takes the full path
     noisy = good * (1.0 + 1e-3 * rng.standard_normal(good.shape))
     N.check(lib.lpr_rev_write_binv(s._h, N.pd(N.f64(noisy))))
     N.check(lib.lpr_rev_refactor_ex(s._h, 0))
-    N.check(lib.lpr_rev_refactor_ex(s._h, 0))  # a refresh contracts quadratically: the second one finishes the job
-    assert err(s.BInverse) < 1e-11
+    N.check(lib.lpr_rev_last_refactor_path(s._h, C.byref(path), C.byref(after)))
+    assert path.value == 2 and err(s.BInverse) < 1e-11
+    # (2b) noise of 1e-11: the cheap refresh is enough and is what the guard picks
+    noisy = good * (1.0 + 1e-11 * rng.standard_normal(good.shape))
+    N.check(lib.lpr_rev_write_binv(s._h, N.pd(N.f64(noisy))))
+    N.check(lib.lpr_rev_refactor_ex(s._h, 0))
+    N.check(lib.lpr_rev_last_refactor_path(s._h, C.byref(path), C.byref(after)))
+    assert path.value == 1 and err(s.BInverse) < 1e-11
     # (3) garbage: the refresh would diverge (max |I - B X| >= 0.5), the guard must take the full path
     N.check(lib.lpr_rev_write_binv(s._h, N.pd(N.f64(rng.standard_normal(good.shape)))))
     N.check(lib.lpr_rev_refactor_ex(s._h, 0))

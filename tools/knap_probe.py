@@ -49,12 +49,20 @@ def run(kind, seed, n, n_gpus=1, cap_nodes=200_000_000, R=1000):
 
 if __name__ == "__main__":
     ng = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    os.environ.setdefault("LPR_KNAP_POOL_MB", "16384")
-    for kind, seed, n, R in [("weak", 384, 10000, 1000), ("weak", 384, 10000, 1000), ("weak", 385, 100000, 1000),
-                             ("weak", 386, 10000, 100000), ("uncorr", 387, 10000, 1000), ("almost_strong", 388, 2000, 1000),
-                             ("almost_strong", 388, 10000, 1000), ("strong", 389, 200, 1000), ("strong", 389, 1000, 1000),
-                             ("subset", 390, 1000, 100000)]:
+    which = sys.argv[2] if len(sys.argv) > 2 else "first"
+    os.environ.setdefault("LPR_KNAP_POOL_MB", "32768")
+    first = [("weak", 384, 10000, 1000), ("weak", 384, 10000, 1000), ("weak", 385, 100000, 1000),
+             ("weak", 386, 10000, 100000), ("uncorr", 387, 10000, 1000), ("almost_strong", 388, 2000, 1000),
+             ("almost_strong", 388, 10000, 1000), ("strong", 389, 200, 1000), ("strong", 389, 1000, 1000),
+             ("subset", 390, 1000, 100000)]
+    third = [("strong", 389, 110, 1000), ("strong", 389, 120, 1000), ("strong", 395, 110, 1000), ("almost_strong", 388, 250, 1000), ("almost_strong", 388, 300, 1000), ("subset", 392, 3000, 1000000), ("subset", 396, 5000, 1000000)]
+    second = [("subset", 390, 2000, 100000), ("subset", 390, 4000, 100000), ("subset", 391, 1000, 1000000),
+              ("subset", 392, 3000, 1000000), ("almost_strong", 388, 100, 1000), ("almost_strong", 388, 200, 1000),
+              ("almost_strong", 388, 400, 1000), ("strong", 389, 50, 1000), ("strong", 389, 100, 1000),
+              ("weak", 393, 10000, 100), ("weak", 394, 30000, 300)]
+    cap = int(os.environ.get("KNAP_PROBE_CAP", "1500000000"))
+    for kind, seed, n, R in {"first": first, "second": second, "third": third}[which]:
         try:
-            run(kind, seed, n, ng, R=R)
+            run(kind, seed, n, ng, cap_nodes=cap, R=R)
         except Exception as ex:
             print("FAIL", kind, seed, n, repr(ex), flush=True)
