@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <functional>
 #include <vector>
 
 #include "sweep.cuh"
@@ -310,6 +311,18 @@ __global__ void k_bb_count_running(const BBLp* lps, int n, int* ctl) {
   __shared__ int smi[32];
   c = block_sum_int(c, smi);
   if (threadIdx.x == 0) ctl[kCtlRunning] = c;
+}
+
+// the children a batch has just solved, as (tableau, dims) entries for the evaluation kernels: the final tableau of
+// LP j sits in buf[src]; a child that did not end OPTIMAL gets R = 0 (its evaluation is never read)
+__global__ void k_bb_child_tabs(const BBLp* __restrict__ lps, int n, const double** tabs, int* dims) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const BBLp& lp = lps[j];
+  tabs[j] = lp.buf[lp.src];
+  dims[3 * j] = lp.status == LPR_OPTIMAL ? lp.R : 0;
+  dims[3 * j + 1] = lp.C;
+  dims[3 * j + 2] = lp.ld;
 }
 
 // ---- node evaluation (:805-857, :892-921) ------------------------------------------------------
@@ -624,6 +637,12 @@ struct BBNode {
   double* slab = nullptr;
   int R = 0, C = 0, depth = 0;
   std::vector<uint8_t> key;  // DFS path: 0 = lower (<= floor) child, 1 = upper (>= ceil) child
+  // evaluation (objective, integrality, branching variable), computed on the device right after the node's LP was
+  // solved -- in the batch that created it -- so that popping it later needs no kernel and no round trip; roots and
+  // imported nodes come without one and are evaluated when popped
+  bool has_eval = false;
+  BBEval ev = {};
+  std::vector<double> x;  // only kept for all-integer nodes (incumbent candidates)
 };
 
 static int key_cmp(const std::vector<uint8_t>& a, const std::vector<uint8_t>& b) {
@@ -711,14 +730,14 @@ static int bb_alloc_scratch(lpr_bb* h, int cap) {
   A_HOST(h_lps, BBLp, nlp);
   A_DEV(d_jobs, BBAddc, nlp);
   A_HOST(h_jobs, BBAddc, nlp);
-  A_DEV(d_eval, BBEval, cap);
-  A_HOST(h_eval, BBEval, cap);
-  A_DEV(d_x, double, (size_t)cap * h->n_vars);
-  A_HOST(h_x, double, (size_t)cap * h->n_vars);
-  A_DEV(d_tabs, const double*, cap);
-  A_HOST(h_tabs, const double*, cap);
-  A_DEV(d_dims, int, 3 * cap);
-  A_HOST(h_dims, int, 3 * cap);
+  A_DEV(d_eval, BBEval, nlp);
+  A_HOST(h_eval, BBEval, nlp);
+  A_DEV(d_x, double, (size_t)nlp * h->n_vars);
+  A_HOST(h_x, double, (size_t)nlp * h->n_vars);
+  A_DEV(d_tabs, const double*, nlp);
+  A_HOST(h_tabs, const double*, nlp);
+  A_DEV(d_dims, int, 3 * nlp);
+  A_HOST(h_dims, int, 3 * nlp);
   A_DEV(d_col, double, (size_t)nlp * h->Rmax);
   A_DEV(d_prow, double, (size_t)nlp * h->ldmax);
   A_DEV(d_key, int, (size_t)nlp * h->ldmax);
@@ -736,7 +755,8 @@ static int bb_alloc_scratch(lpr_bb* h, int cap) {
 // ints (cap >= nlp).  skip_negzero: the start tableaux already have -0.0 -> 0.0 applied (BBAddc::negzero);
 // round_result: RoundAllTableaux on the finished LPs, skipping those d_dirty (optional) marks as already rounded.
 static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps, int nlp, int* d_ctl, int cap,
-                          int* h_running, size_t max_elems, bool skip_negzero, bool round_result, const int* d_dirty) {
+                          int* h_running, size_t max_elems, bool skip_negzero, bool round_result, const int* d_dirty,
+                          const std::function<int()>& before_readback = {}) {
   LPR_CUDA(cudaMemcpyAsync(d_lps, h_lps, sizeof(BBLp) * nlp, cudaMemcpyHostToDevice, stream));
   LPR_CUDA(cudaMemsetAsync(d_ctl, 0, sizeof(int) * kCtlLists, stream));
   const int tiles_max = (int)((max_elems / 2 + kSweepThreads * 8 - 1) / (kSweepThreads * 8));
@@ -772,6 +792,10 @@ static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps
   if (round_result) {
     k_bb_round<<<ge, 256, 0, stream>>>(d_lps, d_dirty);  // children are stored rounded (:1124, :1187)
     LPR_LAUNCH_CHECK();
+  }
+  if (before_readback) {  // more work on the finished LPs, enqueued behind them and waited for with the same sync
+    const int rc = before_readback();
+    if (rc) return rc;
   }
   LPR_CUDA(cudaMemcpyAsync(h_lps, d_lps, sizeof(BBLp) * nlp, cudaMemcpyDeviceToHost, stream));
   LPR_CUDA(cudaStreamSynchronize(stream));
@@ -830,18 +854,35 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
       cur.push_back(std::move(h->open.back()));
       h->open.pop_back();
     }
-    for (int i = 0; i < nb; i++) {
-      h->h_tabs[i] = cur[i].slab;
-      h->h_dims[3 * i] = cur[i].R;
-      h->h_dims[3 * i + 1] = cur[i].C;
-      h->h_dims[3 * i + 2] = h->ldmax;
+    // nodes created by this pool carry their evaluation; roots and imported nodes are evaluated here
+    int ne = 0;
+    std::vector<int> need;
+    for (int i = 0; i < nb; i++)
+      if (!cur[i].has_eval) need.push_back(i);
+    ne = (int)need.size();
+    if (ne > 0) {
+      for (int q = 0; q < ne; q++) {
+        const BBNode& nd = cur[need[q]];
+        h->h_tabs[q] = nd.slab;
+        h->h_dims[3 * q] = nd.R;
+        h->h_dims[3 * q + 1] = nd.C;
+        h->h_dims[3 * q + 2] = h->ldmax;
+      }
+      LPR_CUDA(cudaMemcpyAsync(h->d_tabs, h->h_tabs, sizeof(double*) * ne, cudaMemcpyHostToDevice, h->stream));
+      LPR_CUDA(cudaMemcpyAsync(h->d_dims, h->h_dims, sizeof(int) * 3 * ne, cudaMemcpyHostToDevice, h->stream));
+      if ((rc = bb_run_eval(h->stream, h->d_tabs, h->d_dims, ne, h->n_vars, h->d_eval, h->d_x))) return rc;
+      LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(BBEval) * ne, cudaMemcpyDeviceToHost, h->stream));
+      LPR_CUDA(cudaStreamSynchronize(h->stream));
+      for (int q = 0; q < ne; q++) {
+        BBNode& nd = cur[need[q]];
+        nd.ev = h->h_eval[q];
+        nd.has_eval = true;
+        if (nd.ev.all_integer) {  // x is only needed for incumbent candidates: fetched on demand
+          nd.x.resize(h->n_vars);
+          LPR_CUDA(cudaMemcpy(nd.x.data(), h->d_x + (size_t)q * h->n_vars, sizeof(double) * h->n_vars, cudaMemcpyDeviceToHost));
+        }
+      }
     }
-    LPR_CUDA(cudaMemcpyAsync(h->d_tabs, h->h_tabs, sizeof(double*) * nb, cudaMemcpyHostToDevice, h->stream));
-    LPR_CUDA(cudaMemcpyAsync(h->d_dims, h->h_dims, sizeof(int) * 3 * nb, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = bb_run_eval(h->stream, h->d_tabs, h->d_dims, nb, h->n_vars, h->d_eval, h->d_x))) return rc;
-    LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(BBEval) * nb, cudaMemcpyDeviceToHost, h->stream));
-    LPR_CUDA(cudaMemcpyAsync(h->h_x, h->d_x, sizeof(double) * (size_t)nb * h->n_vars, cudaMemcpyDeviceToHost, h->stream));
-    LPR_CUDA(cudaStreamSynchronize(h->stream));
 
     double tp1 = now_s();
     h->t_eval += tp1 - tp0;
@@ -849,7 +890,7 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
     struct Job { int node; int side; };
     std::vector<Job> jobs;
     for (int i = 0; i < nb; i++) {
-      const BBEval& ev = h->h_eval[i];
+      const BBEval& ev = cur[i].ev;
       const int64_t q = h->processed++;
       done++;
       bool pruned = false;
@@ -860,7 +901,7 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
         if (!h->has_inc || ev.z > h->inc_z || (ev.z == h->inc_z && key_cmp(cur[i].key, h->inc_key) < 0)) {
           h->has_inc = true;
           h->inc_z = ev.z;
-          h->inc_x.assign(h->h_x + (size_t)i * h->n_vars, h->h_x + (size_t)(i + 1) * h->n_vars);
+          h->inc_x = cur[i].x;
           h->inc_key = cur[i].key;
         }
       }
@@ -888,7 +929,7 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
         if ((rc = bb_take_slab(h, &slabA[j]))) return rc;
         if ((rc = bb_take_slab(h, &slabB[j]))) return rc;
         const BBNode& nd = cur[jobs[j].node];
-        const BBEval& ev = h->h_eval[jobs[j].node];
+        const BBEval& ev = nd.ev;
         BBAddc& jb = h->h_jobs[j];
         jb.parent = nd.slab;
         jb.child = slabA[j];
@@ -930,8 +971,16 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
       if (getenv("LPR_BB_PROFILE")) cudaStreamSynchronize(h->stream);
       double tp3 = now_s();
       h->t_addc += tp3 - tp2;
+      auto eval_children = [&]() -> int {
+        k_bb_child_tabs<<<(nj + 127) / 128, 128, 0, h->stream>>>(h->d_lps, nj, h->d_tabs, h->d_dims);
+        LPR_LAUNCH_CHECK();
+        int rc2 = bb_run_eval(h->stream, h->d_tabs, h->d_dims, nj, h->n_vars, h->d_eval, h->d_x);
+        if (rc2) return rc2;
+        LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(BBEval) * nj, cudaMemcpyDeviceToHost, h->stream));
+        return LPR_OK;
+      };
       if ((rc = bb_solve_batch(h->stream, h->sms, h->h_lps, h->d_lps, nj, h->d_ctl, 2 * h->cap, h->h_running, max_elems,
-                               true, true, h->d_dirty)))
+                               true, true, h->d_dirty, eval_children)))
         return rc;
       h->t_solve += now_s() - tp3;
       h->n_children += nj;
@@ -954,6 +1003,13 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
             ch.depth = cur[i].depth + 1;
             ch.key = cur[i].key;
             ch.key.push_back((uint8_t)side);
+            ch.ev = h->h_eval[j];
+            ch.has_eval = true;
+            if (ch.ev.all_integer) {  // an incumbent candidate: keep its x (rare, fetched on demand)
+              ch.x.resize(h->n_vars);
+              LPR_CUDA(cudaMemcpy(ch.x.data(), h->d_x + (size_t)j * h->n_vars, sizeof(double) * h->n_vars,
+                                  cudaMemcpyDeviceToHost));
+            }
             h->open.push_back(std::move(ch));
           } else {
             bb_give_slab(h, slabA[j]);

@@ -417,8 +417,22 @@ void rank_main(int rank, int world, int rpg, int device, Pool* pool, ncclComm_t 
   bool setup_failed = false;
   for (int r = 0; r < world; r++) setup_failed |= sh->rc[r] != LPR_OK;
   if (!setup_failed) {
+    // outside the timed region: NCCL builds the channels of a collective and of every point-to-point pair lazily
+    // (the first ncclSend/ncclRecv between two devices costs ~100 ms), so run each once
     for (int i = 0; i < nvec; i++) h_vec[i] = 0.0;
-    allreduce();  // one all-reduce outside the timed region: NCCL builds its channels lazily
+    allreduce();
+    if (leader && n_gpus > 1) {
+      int nr = api.GroupStart();
+      for (int g = 0; g < n_gpus && nr == 0; g++) {
+        if (g == gpu) continue;
+        nr = api.Send(stage_out, 8, kNcclUint8, g, comm, stream);
+        if (nr == 0) nr = api.Recv(stage_in + 64 * (size_t)g, 8, kNcclUint8, g, comm, stream);
+      }
+      const int ne = api.GroupEnd();
+      if (nr == 0) nr = ne;
+      if (nr != 0) note(fail(LPR_E_NCCL, "point-to-point warm-up failed: %s", api.GetErrorString(nr)));
+      cuda_ok(cudaStreamSynchronize(stream), "point-to-point warm-up");
+    }
   }
   sh->barrier.wait();
   const double t_begin = now_s();

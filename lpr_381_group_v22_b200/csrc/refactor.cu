@@ -463,26 +463,8 @@ int refactor_binv(cudaStream_t stream, int m, int n, const double* A, int ldA, d
                   double* flops_out, int* path_out) {
   const int np = round_up(m, 64);
   const size_t bytes = sizeof(double) * (size_t)np * np;
-  if (ws.np != np) {
-    refactor_ws_free(ws);
-    cudaError_t e = cudaMalloc(&ws.Bm, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.Xp, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.Rm, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.W, sizeof(double) * (size_t)np * NB);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.RK, sizeof(double) * (size_t)NB * 2 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.Dinv, sizeof(double) * NB * NB);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.d_res, sizeof(double) * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.used, sizeof(int) * np);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.piv_rows, sizeof(int) * np);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.sw, sizeof(int) * np);
-    if (e == cudaSuccess) e = cudaMalloc(&ws.singular, sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&ws.ticket, sizeof(unsigned));
-    if (e != cudaSuccess) {
-      refactor_ws_free(ws);
-      return fail(LPR_E_NOMEM, "refactorisation workspace (3 x %zu MB) allocation failed", bytes >> 20);
-    }
-    ws.np = np;
-  }
+  int rc0 = refactor_ws_ensure(ws, m);
+  if (rc0) return rc0;
   double *Bm = ws.Bm, *Xp = ws.Xp, *Rm = ws.Rm;
   dim3 gg((np + 255) / 256, np), grid(np / GN, np / GM);
   double flops = 0.0, res0 = 0.0, res1 = 0.0;
@@ -541,6 +523,32 @@ int refactor_binv(cudaStream_t stream, int m, int n, const double* A, int ldA, d
   if (residual_after_out) *residual_after_out = res1;
   if (flops_out) *flops_out = flops;
   if (path_out) *path_out = path;
+  return LPR_OK;
+}
+
+// allocate the workspace for order m (idempotent); lpr_rev_refactor_ex calls it before it starts its timer
+int refactor_ws_ensure(RefactorWs& ws, int m) {
+  const int np = round_up(m, 64);
+  const size_t bytes = sizeof(double) * (size_t)np * np;
+  if (ws.np == np) return LPR_OK;
+  refactor_ws_free(ws);
+  cudaError_t e = cudaMalloc(&ws.Bm, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.Xp, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.Rm, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.W, sizeof(double) * (size_t)np * NB);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.RK, sizeof(double) * (size_t)NB * 2 * np);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.Dinv, sizeof(double) * NB * NB);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.d_res, sizeof(double) * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.used, sizeof(int) * np);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.piv_rows, sizeof(int) * np);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.sw, sizeof(int) * np);
+  if (e == cudaSuccess) e = cudaMalloc(&ws.singular, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&ws.ticket, sizeof(unsigned));
+  if (e != cudaSuccess) {
+    refactor_ws_free(ws);
+    return fail(LPR_E_NOMEM, "refactorisation workspace (3 x %zu MB) allocation failed", bytes >> 20);
+  }
+  ws.np = np;
   return LPR_OK;
 }
 

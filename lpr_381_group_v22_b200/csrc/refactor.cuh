@@ -15,6 +15,7 @@ struct RefactorWs {
   unsigned* ticket = nullptr;
 };
 void refactor_ws_free(RefactorWs& ws);
+int refactor_ws_ensure(RefactorWs& ws, int m);
 int refactor_binv(cudaStream_t stream, int m, int n, const double* A, int ldA, double* Binv, int ldB, const int* basis,
                   RefactorWs& ws, int mode, double* residual_out, double* residual_after_out, double* flops_out,
                   int* path_out);

@@ -1075,6 +1075,7 @@ int lpr_rev_refactor_ex(lpr_rev* h, int mode) {
   if (mode < 0 || mode > 2) return fail(LPR_E_BADARG, "refactorisation mode %d", mode);
   int rc = select_device(h->device);
   if (rc) return rc;
+  if ((rc = refactor_ws_ensure(h->rws, h->m))) return rc;  // first call of a handle: allocated outside the timer
   LPR_CUDA(cudaEventRecord(h->ev0, h->stream));
   double res = 0.0, res_after = 0.0, flops = 0.0;
   int path = 0;

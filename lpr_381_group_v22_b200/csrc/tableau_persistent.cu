@@ -50,7 +50,7 @@ struct PersistArgs {
   unsigned* bar;
 };
 
-constexpr int kPT = 256;
+constexpr int kPT = 1024;  // one CTA per SM: a staging loop or a sweep pass over a row is one L2 round trip, not four
 
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 
@@ -326,16 +326,16 @@ __global__ void __launch_bounds__(kPT) k_persist(PersistArgs a) {
       const int Rn = (p == R) ? R + 1 : R;  // rows of the next tableau
       // rows are dealt to the CTAs in contiguous spans; a thread owns column chunks tid, tid + kPT, ...
       const int r0 = (int)((long long)Rn * blockIdx.x / gridDim.x), r1 = (int)((long long)Rn * (blockIdx.x + 1) / gridDim.x);
-      const double2* S2 = reinterpret_cast<const double2*>(T);
-      double2* D2 = reinterpret_cast<double2*>(D);
+      const double2* __restrict__ S2 = reinterpret_cast<const double2*>(T);
+      double2* __restrict__ D2 = reinterpret_cast<double2*>(D);
       for (int c = tid; c < ldv; c += kPT) {
         const int j0 = 2 * c, j1 = 2 * c + 1;
         double2 pr;
         pr.x = j0 < C ? __ddiv_rn(s_b[j0], piv) : 0.0;
         pr.y = j1 < C ? __ddiv_rn(s_b[j1], piv) : 0.0;
         for (int i0 = r0; i0 < r1; i0 += 4) {
-          double2 x[4];
-          double f[4];
+          double2 x[4] = {};
+          double f[4] = {};
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             const int i = i0 + u;
