@@ -62,7 +62,7 @@ struct BBAddc {  // one AddConstraint job
 // Control words of a batched DoDualSimplex run (device ints): the LPs that staged a pivot in round r are appended
 // to list[r & 1] by k_bb_select and swept by k_bb_sweep(r); count[r & 3] is their number (k_bb_sweep(r) clears
 // count[(r + 2) & 3] for the select after next).
-constexpr int kCtlRunning = 4, kCtlLists = 8;
+constexpr int kCtlRunning = 4, kCtlBar = 5, kCtlLists = 8;  // [kCtlBar]: grid-barrier counter of k_bb_chains
 
 constexpr int kBBT = 1024;
 
@@ -116,10 +116,10 @@ __global__ void k_round4(double* T, size_t n) {
 }
 
 // ---- DoDualSimplex state machine (:289-468), one CTA per LP --------------------------------------
-__global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps, int* ctl, int round, int cap) {
+__device__ __forceinline__ void bb_select_body(BBLp* lps, int lp_index, int* ctl, int round, int cap) {
   __shared__ MinIdx sm[32];
   __shared__ int smi[32];
-  BBLp& lp = lps[blockIdx.x];
+  BBLp& lp = lps[lp_index];
   const int tid = threadIdx.x;
   const int status = lp.status;
   const int did = lp.do_sweep;
@@ -279,8 +279,11 @@ __global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps, int* ctl, int rou
     lp.leave = r;
     lp.enter = c;
     lp.do_sweep = 1;
-    ctl[kCtlLists + (round & 1) * cap + atomicAdd(&ctl[round & 3], 1)] = blockIdx.x;
+    ctl[kCtlLists + (round & 1) * cap + atomicAdd(&ctl[round & 3], 1)] = lp_index;
   }
+}
+__global__ void __launch_bounds__(kBBT) k_bb_select(BBLp* lps, int* ctl, int round, int cap) {
+  bb_select_body(lps, blockIdx.x, ctl, round, cap);
 }
 
 // Sweeps of the LPs that staged a pivot this round.  The (LP, tile) pairs are dealt round-robin to a grid sized for
@@ -311,6 +314,63 @@ __global__ void k_bb_count_running(const BBLp* lps, int n, int* ctl) {
   __shared__ int smi[32];
   c = block_sum_int(c, smi);
   if (threadIdx.x == 0) ctl[kCtlRunning] = c;
+}
+
+// ---- all rounds of a batch's DoDualSimplex chains in ONE cooperative launch -----------------------------------------
+// Round r = select (one CTA per LP: the state machine above) -> grid barrier -> sweeps of the LPs that staged a pivot
+// (the (LP, tile) pairs dealt to every CTA, four 256-thread tiles per 1024-thread CTA) -> grid barrier; the loop ends
+// in the round in which no LP staged a pivot (then every LP is terminal).  Replaces per round two launches and, every
+// few rounds, a running-count kernel with a host synchronisation: for the ~0.3 pivots per node of cfg5 a batch's
+// chains were ~13 short launches and two round trips.
+__device__ __forceinline__ void bb_grid_barrier(unsigned* bar, unsigned& generation) {
+  __syncthreads();
+  generation++;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = generation * gridDim.x;
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(kBBT) k_bb_chains(BBLp* lps, int nlp, int* ctl, int cap, int tiles_max, unsigned* bar) {
+  unsigned generation = 0;
+  constexpr unsigned TILE = kSweepThreads * 8;
+  constexpr int kSub = kBBT / kSweepThreads;  // 256-thread tiles a CTA works on side by side
+  const int sub = threadIdx.x / kSweepThreads;
+  const unsigned tix = threadIdx.x % kSweepThreads;
+  for (int round = 0;; round++) {
+    for (int lp = blockIdx.x; lp < nlp; lp += gridDim.x) {
+      bb_select_body(lps, lp, ctl, round, cap);
+      __syncthreads();  // the body's shared scratch is reused by the next LP of this CTA
+    }
+    bb_grid_barrier(bar, generation);
+    const int na = *(volatile int*)&ctl[round & 3];
+    if (na == 0) break;  // uniform: every CTA reads the same counter after the barrier
+    const int* list = ctl + kCtlLists + (round & 1) * cap;
+    const long long total = (long long)na * tiles_max;
+    for (long long g = (long long)blockIdx.x * kSub + sub; g < total; g += (long long)gridDim.x * kSub) {
+      // the descriptor was updated by the LP's own CTA this round: read it from L2, not from a stale L1 line
+      const BBLp* lp = lps + __ldcg(&list[g / tiles_max]);
+      const int src = __ldcg(&lp->src), leave = __ldcg(&lp->leave);
+      const unsigned long long t = (unsigned long long)(g % tiles_max);
+      const unsigned ldv = (unsigned)(__ldcg(&lp->ld) >> 1);
+      const unsigned long long n = (unsigned long long)__ldcg(&lp->R) * ldv;
+      if (t * TILE >= n) continue;
+      const double* b0 = lp->buf[0];  // the buffer / scratch pointers never change during a launch
+      const double* b1 = lp->buf[1];
+      sweep_tile<0, true, false, 8, true>(reinterpret_cast<const double2*>(src ? b1 : b0),
+                                          reinterpret_cast<double2*>(const_cast<double*>(src ? b0 : b1)), lp->col,
+                                          reinterpret_cast<const double2*>(lp->prow), nullptr, nullptr, n, ldv, leave, t,
+                                          0.0, 0u, 0, 0xffffffffu, 0, tix);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl[(round + 2) & 3] = 0;
+    bb_grid_barrier(bar, generation);
+  }
 }
 
 // the children a batch has just solved, as (tableau, dims) entries for the evaluation kernels: the final tableau of
@@ -766,6 +826,18 @@ static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps
     k_bb_negzero<<<ge, 256, 0, stream>>>(d_lps);
     LPR_LAUNCH_CHECK();
   }
+  static const int persist = getenv("LPR_BB_PERSIST") ? atoi(getenv("LPR_BB_PERSIST")) : 1;
+  if (persist) {
+    // one cooperative launch for every round of the batch (k_bb_chains); the barrier counter sits behind the lists
+    unsigned* bar = reinterpret_cast<unsigned*>(d_ctl + kCtlBar);
+    int nlp_arg = nlp, cap_arg = cap, tiles_arg = tiles_max;
+    int* ctl_arg = d_ctl;
+    BBLp* lps_arg = d_lps;
+    void* args[] = {&lps_arg, &nlp_arg, &ctl_arg, &cap_arg, &tiles_arg, &bar};
+    const int grid = std::max(1, std::min(sms, std::max(nlp, 32)));
+    LPR_CUDA(cudaLaunchCooperativeKernel((void*)k_bb_chains, dim3(grid), dim3(kBBT), args, 0, stream));
+    count_launch();
+  } else {
   int round = 0, chunk = 2;
   auto pivot_round = [&](bool count) -> int {
     k_bb_select<<<nlp, kBBT, 0, stream>>>(d_lps, d_ctl, round, cap);
@@ -788,6 +860,7 @@ static int bb_solve_batch(cudaStream_t stream, int sms, BBLp* h_lps, BBLp* d_lps
     LPR_CUDA(cudaStreamSynchronize(stream));
     if (*h_running == 0) break;
     chunk = std::min(16, chunk * 2);
+  }
   }
   if (round_result) {
     k_bb_round<<<ge, 256, 0, stream>>>(d_lps, d_dirty);  // children are stored rounded (:1124, :1187)
@@ -922,6 +995,7 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
     }
     // children: AddConstraint + DoDualSimplex, batched
     const int nj = (int)jobs.size();
+    bool evaluated_children = false;
     std::vector<double*> slabA(nj, nullptr), slabB(nj, nullptr);
     if (nj > 0) {
       size_t max_elems = 0;
@@ -979,9 +1053,16 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
         LPR_CUDA(cudaMemcpyAsync(h->h_eval, h->d_eval, sizeof(BBEval) * nj, cudaMemcpyDeviceToHost, h->stream));
         return LPR_OK;
       };
+      // Evaluating children here saves the evaluation round trip of the batch that pops them, but a child that is
+      // still open when the search stops was evaluated for nothing: on trees that close it is a gain, on the
+      // time-sliced cfg5 run (which leaves as many nodes open as it processes) it doubles the evaluation work.
+      // Default: evaluate at pop; LPR_BB_EVAL_AT_CREATE=1 switches.
+      static const bool eval_at_create = getenv("LPR_BB_EVAL_AT_CREATE") && atoi(getenv("LPR_BB_EVAL_AT_CREATE")) != 0;
       if ((rc = bb_solve_batch(h->stream, h->sms, h->h_lps, h->d_lps, nj, h->d_ctl, 2 * h->cap, h->h_running, max_elems,
-                               true, true, h->d_dirty, eval_children)))
+                               true, true, h->d_dirty, eval_at_create ? std::function<int()>(eval_children)
+                                                                      : std::function<int()>())))
         return rc;
+      evaluated_children = eval_at_create;
       h->t_solve += now_s() - tp3;
       h->n_children += nj;
     }
@@ -1003,9 +1084,11 @@ static int bb_process(lpr_bb* h, int64_t max_nodes, int batch, int64_t* processe
             ch.depth = cur[i].depth + 1;
             ch.key = cur[i].key;
             ch.key.push_back((uint8_t)side);
-            ch.ev = h->h_eval[j];
-            ch.has_eval = true;
-            if (ch.ev.all_integer) {  // an incumbent candidate: keep its x (rare, fetched on demand)
+            if (evaluated_children) {
+              ch.ev = h->h_eval[j];
+              ch.has_eval = true;
+            }
+            if (evaluated_children && ch.ev.all_integer) {  // an incumbent candidate: keep its x (rare, on demand)
               ch.x.resize(h->n_vars);
               LPR_CUDA(cudaMemcpy(ch.x.data(), h->d_x + (size_t)j * h->n_vars, sizeof(double) * h->n_vars,
                                   cudaMemcpyDeviceToHost));

@@ -68,11 +68,21 @@ __host__ __device__ inline uint64_t knap_pack_state(int k, int side) {
   return (uint64_t)(uint32_t)k | ((uint64_t)(uint32_t)side << 32);
 }
 
-// Device-resident control block: the tree is walked level by level WITHOUT the host in the loop.  One level =
-// k_knap_eval (batch = top ev_nb records of the stack, evaluated in place) -> k_knap_plan (one CTA: incumbent from the
-// batch's candidates, pruning against it, stable compaction of the survivors, stack bookkeeping, next batch) ->
-// k_knap_gather (surviving parents -> staging, because children overwrite the batch's slots) -> k_knap_expand.  The
-// host enqueues several levels back to back and only then reads this block (lpr_knap_run).
+// Device-resident control block: the tree is walked level by level WITHOUT the host in the loop.  One level, six
+// launches back to back, all but two of them spread over the whole batch:
+//   k_knap_eval   one thread per node of the batch (top ev_nb records of the stack, in place): relaxation, and the
+//                 CTA's best candidate (value, then DFS-first key)
+//   k_knap_inc    one small CTA: best candidate of the level -> incumbent (strict improvement, or a tie with an
+//                 earlier key); the incumbent's record stays on the device
+//   k_knap_flag   per node: does it survive the (new) incumbent?  one ballot word per warp, one count per CTA
+//   k_knap_scan   one small CTA: exclusive scan of the CTA counts, stack bookkeeping, node budget, next batch window
+//   k_knap_gather surviving parents -> staging (children overwrite the batch's slots); the j-th survivor is found from
+//                 the scanned counts and the ballot words, so survivors stay in batch order (the stack order, hence
+//                 the node count, does not depend on scheduling)
+//   k_knap_expand both children of every survivor
+// Round 2's first cut did incumbent, pruning and compaction in ONE 1024-thread CTA (k_knap_plan): 75 us per 16384-node
+// level against 12 us for the evaluation (ncu: long-scoreboard stalls 95 per issue) -- the level loop ran at the
+// speed of that CTA.  The host enqueues several levels back to back and only then reads this block (lpr_knap_run).
 struct KnapCtl {
   long long open;       // stack size (records)
   long long processed;  // nodes evaluated since creation
@@ -84,80 +94,225 @@ struct KnapCtl {
   int has_inc, inc_bits, inc_crit, inc_version;
   double inc_val;
   int error, stop, levels, batch;
+  int ex_ncta, reserved;  // evaluation CTAs of the level being expanded (extent of the scanned counts)
 };
 
-// one thread per node: a walk from the parent's critical item (see the header)
-__global__ void __launch_bounds__(128) k_knap_eval(const KnapCtl* __restrict__ ctl, const uint64_t* __restrict__ pool,
-                                                   size_t rec_words, int W, int n, const double* __restrict__ w,
-                                                   const double* __restrict__ v, KnapEval* __restrict__ out) {
-  const int node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= ctl->ev_nb) return;
-  const uint64_t* rec = pool + (size_t)(ctl->ev_first + node) * rec_words;
-  const uint64_t st = rec[3 * (size_t)W + 1];
-  const int k = (int)(uint32_t)st, side = (int)(st >> 32);
-  double cap = __longlong_as_double((long long)rec[3 * (size_t)W + 2]);
-  double val = __longlong_as_double((long long)rec[3 * (size_t)W + 3]);
-  auto fixed = [&](int p) { return (rec[p >> 6] >> (p & 63)) & 1ull; };
-  int crit = -1;
-  bool infeasible = k < 0 && cap < 0.0;  // negative capacity at the root
-  if (infeasible) {
-  } else if (side == 1 && k >= 0) {
-    cap = __dsub_rn(cap, w[k]);  // < 0: k did not fit in the parent
-    val = __dadd_rn(val, v[k]);
-    int p = k - 1;
-    for (; p >= 0; p--) {
-      if (fixed(p)) continue;
-      cap = __dadd_rn(cap, w[p]);
-      val = __dsub_rn(val, v[p]);
-      if (cap >= 0.0) break;
-    }
-    if (p < 0) infeasible = true;  // the fixed-1 items alone exceed the capacity
-    crit = p;
-  } else {
-    for (int p = k + 1; p < n; p++) {  // k = -1 for the root
-      if (fixed(p)) continue;
-      const double wp = w[p];
-      if (wp <= cap) {
-        cap = __dsub_rn(cap, wp);
-        val = __dadd_rn(val, v[p]);
-      } else {
-        crit = p;
-        break;
-      }
-    }
-  }
-  KnapEval ev;
-  ev.cap = cap;
-  ev.base = val;
-  ev.crit = crit;
-  if (infeasible) {
-    ev.val = 0.0;
-    ev.crit = -1;
-    ev.type = 0;
-  } else if (crit < 0 || cap == 0.0) {
-    ev.val = val;
-    ev.type = 1;
-  } else {
-    ev.val = __dadd_rn(val, __dmul_rn(v[crit], __ddiv_rn(cap, w[crit])));
-    ev.type = 2;
-  }
-  ev.cmp = kCmpNone;
-  ev.pad = 0;
-  out[node] = ev;
+constexpr int kEvT = 128;  // threads per CTA of the per-node kernels (eval, flag, gather-by-node)
+struct KnapCand {          // best candidate of one evaluation CTA
+  double val;
+  int idx;  // node index inside the batch, -1 = none
+  int pad;
+};
+
+// is candidate node a (value va) ahead of candidate node b?  value first, then the DFS-first key
+__device__ __forceinline__ bool knap_cand_ahead(const uint64_t* pool, size_t rec_words, int W, long long first, double va,
+                                                int a, double vb, int b) {
+  if (b < 0) return a >= 0;
+  if (a < 0) return false;
+  if (va != vb) return va > vb;
+  const uint64_t* ra = pool + (size_t)(first + a) * rec_words;
+  const uint64_t* rb = pool + (size_t)(first + b) * rec_words;
+  return knap_key_order(ra + 2 * (size_t)W, (int)ra[3 * (size_t)W], rb + 2 * (size_t)W, (int)rb[3 * (size_t)W]) < 0;
 }
 
-// One CTA per level.  (1) best candidate of the batch: largest value, ties -> DFS-first key (a total order, so the
-// tree reduction is order independent); (2) it replaces the incumbent on strict improvement or on a tie with an
-// earlier key; (3) a branch node survives when its bound beats the incumbent, or ties with it while preceding it
-// in DFS order; (4) survivors are compacted in batch order (stable), so the stack order -- and with it the node
-// count -- does not depend on how the work was scheduled; (5) stack bookkeeping and the next batch.
-constexpr int kPlanT = 1024;
-__global__ void __launch_bounds__(kPlanT) k_knap_plan(KnapCtl* ctl, const uint64_t* __restrict__ pool, size_t rec_words,
-                                                      int W, KnapEval* __restrict__ evals, long long* __restrict__ parent,
-                                                      uint64_t* inc_key, uint64_t* inc_rec) {
-  __shared__ int s_idx[kPlanT];
-  __shared__ int s_cnt[kPlanT];
-  __shared__ int s_upd, s_total;
+// one thread per node: a walk from the parent's critical item (see the header), then the CTA's best candidate
+__global__ void __launch_bounds__(kEvT) k_knap_eval(const KnapCtl* __restrict__ ctl, const uint64_t* __restrict__ pool,
+                                                    size_t rec_words, int W, int n, const double* __restrict__ w,
+                                                    const double* __restrict__ v, KnapEval* __restrict__ out,
+                                                    KnapCand* __restrict__ cands) {
+  __shared__ double s_val[kEvT / 32];
+  __shared__ int s_idx[kEvT / 32];
+  const int nb = ctl->ev_nb;
+  const long long first = ctl->ev_first;
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  double cval = 0.0;
+  int cidx = -1;
+  if (node < nb) {
+    const uint64_t* rec = pool + (size_t)(first + node) * rec_words;
+    const uint64_t st = rec[3 * (size_t)W + 1];
+    const int k = (int)(uint32_t)st, side = (int)(st >> 32);
+    double cap = __longlong_as_double((long long)rec[3 * (size_t)W + 2]);
+    double val = __longlong_as_double((long long)rec[3 * (size_t)W + 3]);
+    auto fixed = [&](int p) { return (rec[p >> 6] >> (p & 63)) & 1ull; };
+    int crit = -1;
+    bool infeasible = k < 0 && cap < 0.0;  // negative capacity at the root
+    if (infeasible) {
+    } else if (side == 1 && k >= 0) {
+      cap = __dsub_rn(cap, w[k]);  // < 0: k did not fit in the parent
+      val = __dadd_rn(val, v[k]);
+      int p = k - 1;
+      for (; p >= 0; p--) {
+        if (fixed(p)) continue;
+        cap = __dadd_rn(cap, w[p]);
+        val = __dsub_rn(val, v[p]);
+        if (cap >= 0.0) break;
+      }
+      if (p < 0) infeasible = true;  // the fixed-1 items alone exceed the capacity
+      crit = p;
+    } else {
+      for (int p = k + 1; p < n; p++) {  // k = -1 for the root
+        if (fixed(p)) continue;
+        const double wp = w[p];
+        if (wp <= cap) {
+          cap = __dsub_rn(cap, wp);
+          val = __dadd_rn(val, v[p]);
+        } else {
+          crit = p;
+          break;
+        }
+      }
+    }
+    KnapEval ev;
+    ev.cap = cap;
+    ev.base = val;
+    ev.crit = crit;
+    if (infeasible) {
+      ev.val = 0.0;
+      ev.crit = -1;
+      ev.type = 0;
+    } else if (crit < 0 || cap == 0.0) {
+      ev.val = val;
+      ev.type = 1;
+    } else {
+      ev.val = __dadd_rn(val, __dmul_rn(v[crit], __ddiv_rn(cap, w[crit])));
+      ev.type = 2;
+    }
+    ev.cmp = kCmpNone;
+    ev.pad = 0;
+    out[node] = ev;
+    if (ev.type == 1) {
+      cval = ev.val;
+      cidx = node;
+    }
+  }
+  // best candidate of this CTA: warp shuffle reduction with the (value, key) order, then across the warps
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, cval, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, cidx, o);
+    if (knap_cand_ahead(pool, rec_words, W, first, ov, oi, cval, cidx)) {
+      cval = ov;
+      cidx = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_val[threadIdx.x >> 5] = cval;
+    s_idx[threadIdx.x >> 5] = cidx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < kEvT / 32; q++)
+      if (knap_cand_ahead(pool, rec_words, W, first, s_val[q], s_idx[q], cval, cidx)) {
+        cval = s_val[q];
+        cidx = s_idx[q];
+      }
+    KnapCand c;
+    c.val = cval;
+    c.idx = cidx;
+    c.pad = 0;
+    cands[blockIdx.x] = c;
+  }
+}
+
+// best candidate of the level (over the evaluation CTAs) -> incumbent
+constexpr int kIncT = 256;
+__global__ void __launch_bounds__(kIncT) k_knap_inc(KnapCtl* ctl, const uint64_t* __restrict__ pool, size_t rec_words, int W,
+                                                    const KnapEval* __restrict__ evals, const KnapCand* __restrict__ cands,
+                                                    uint64_t* inc_key, uint64_t* inc_rec) {
+  __shared__ double s_val[kIncT];
+  __shared__ int s_idx[kIncT];
+  __shared__ int s_upd;
+  const int tid = threadIdx.x;
+  const int nb = ctl->ev_nb;
+  if (nb <= 0 || ctl->stop) return;
+  const long long first = ctl->ev_first;
+  const int ncta = (nb + kEvT - 1) / kEvT;
+  double cval = 0.0;
+  int cidx = -1;
+  for (int q = tid; q < ncta; q += kIncT) {
+    const KnapCand c = cands[q];
+    if (knap_cand_ahead(pool, rec_words, W, first, c.val, c.idx, cval, cidx)) {
+      cval = c.val;
+      cidx = c.idx;
+    }
+  }
+  s_val[tid] = cval;
+  s_idx[tid] = cidx;
+  __syncthreads();
+  for (int o = kIncT / 2; o > 0; o >>= 1) {
+    if (tid < o && knap_cand_ahead(pool, rec_words, W, first, s_val[tid + o], s_idx[tid + o], s_val[tid], s_idx[tid])) {
+      s_val[tid] = s_val[tid + o];
+      s_idx[tid] = s_idx[tid + o];
+    }
+    __syncthreads();
+  }
+  const int best = s_idx[0];
+  if (tid == 0) {
+    int upd = 0;
+    if (best >= 0) {
+      const uint64_t* rb = pool + (size_t)(first + best) * rec_words;
+      const double bv = s_val[0];
+      if (!ctl->has_inc || bv > ctl->inc_val ||
+          (bv == ctl->inc_val && knap_key_order(rb + 2 * (size_t)W, (int)rb[3 * (size_t)W], inc_key, ctl->inc_bits) < 0))
+        upd = 1;
+    }
+    s_upd = upd;
+  }
+  __syncthreads();
+  if (!s_upd) return;
+  // the incumbent's record stays on the device; the host fetches it when asked (lpr_knap_get_incumbent)
+  const uint64_t* src = pool + (size_t)(first + best) * rec_words;
+  for (int t = tid; t < (int)rec_words; t += kIncT) inc_rec[t] = src[t];
+  for (int t = tid; t < W; t += kIncT) inc_key[t] = src[2 * (size_t)W + t];
+  __syncthreads();
+  if (tid == 0) {
+    ctl->has_inc = 1;
+    ctl->inc_val = s_val[0];
+    ctl->inc_bits = (int)src[3 * (size_t)W];
+    ctl->inc_crit = evals[best].crit;
+    ctl->inc_version++;
+  }
+}
+
+// a branch node survives when its bound beats the incumbent, or ties with it while preceding it in DFS order:
+// one ballot word per warp, one count per CTA
+__global__ void __launch_bounds__(kEvT) k_knap_flag(const KnapCtl* __restrict__ ctl, const uint64_t* __restrict__ pool,
+                                                    size_t rec_words, int W, const KnapEval* __restrict__ evals,
+                                                    const uint64_t* __restrict__ inc_key, unsigned* __restrict__ masks,
+                                                    int* __restrict__ counts) {
+  __shared__ int s_cnt[kEvT / 32];
+  const int nb = ctl->ev_nb;
+  if (nb <= 0 || ctl->stop) return;
+  const long long first = ctl->ev_first;
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (node < nb && evals[node].type == 2) {
+    const double bv = evals[node].val;
+    if (!ctl->has_inc || bv > ctl->inc_val) {
+      keep = true;
+    } else if (bv == ctl->inc_val) {
+      const uint64_t* rec = pool + (size_t)(first + node) * rec_words;
+      keep = knap_key_order(rec + 2 * (size_t)W, (int)rec[3 * (size_t)W], inc_key, ctl->inc_bits) <= 0;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    masks[blockIdx.x * (kEvT / 32) + warp] = m;
+    s_cnt[warp] = __popc(m);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int q = 0; q < kEvT / 32; q++) c += s_cnt[q];
+    counts[blockIdx.x] = c;
+  }
+}
+
+// exclusive scan of the CTA counts (in place: counts[b] becomes the index of CTA b's first survivor, counts[ncta] the
+// total), then stack bookkeeping, node budget and the next batch window
+constexpr int kScanT = 1024;
+__global__ void __launch_bounds__(kScanT) k_knap_scan(KnapCtl* ctl, int* counts) {
+  __shared__ int s_part[kScanT];
   const int tid = threadIdx.x;
   const int nb = ctl->ev_nb;
   if (nb <= 0 || ctl->stop) {
@@ -168,87 +323,30 @@ __global__ void __launch_bounds__(kPlanT) k_knap_plan(KnapCtl* ctl, const uint64
     }
     return;
   }
-  const long long first = ctl->ev_first;
-  auto rec_of = [&](int i) { return pool + (size_t)(first + i) * rec_words; };
-  auto key_of = [&](int i) { return rec_of(i) + 2 * (size_t)W; };
-  auto bits_of = [&](int i) { return (int)rec_of(i)[3 * (size_t)W]; };
-  auto cand_better = [&](int a, int b) {  // is candidate a ahead of candidate b?
-    if (b < 0) return a >= 0;
-    if (a < 0) return false;
-    const double va = evals[a].val, vb = evals[b].val;
-    if (va != vb) return va > vb;
-    return knap_key_order(key_of(a), bits_of(a), key_of(b), bits_of(b)) < 0;
-  };
-  int best = -1;
-  for (int i = tid; i < nb; i += kPlanT)
-    if (evals[i].type == 1 && cand_better(i, best)) best = i;
-  s_idx[tid] = best;
+  const int ncta = (nb + kEvT - 1) / kEvT;
+  const int per = (ncta + kScanT - 1) / kScanT;
+  const int q0 = tid * per, q1 = min(ncta, q0 + per);
+  int sum = 0;
+  for (int q = q0; q < q1; q++) sum += counts[q];
+  s_part[tid] = sum;
   __syncthreads();
-  for (int o = kPlanT / 2; o > 0; o >>= 1) {
-    if (tid < o && cand_better(s_idx[tid + o], s_idx[tid])) s_idx[tid] = s_idx[tid + o];
+  for (int o = 1; o < kScanT; o <<= 1) {  // inclusive scan of the per-thread sums
+    const int add = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += add;
     __syncthreads();
   }
-  best = s_idx[0];
+  int off = s_part[tid] - sum;
+  for (int q = q0; q < q1; q++) {
+    const int c = counts[q];
+    counts[q] = off;
+    off += c;
+  }
+  const int nj = s_part[kScanT - 1];
   if (tid == 0) {
-    int upd = 0;
-    if (best >= 0) {
-      const double bv = evals[best].val;
-      if (!ctl->has_inc || bv > ctl->inc_val ||
-          (bv == ctl->inc_val && knap_key_order(key_of(best), bits_of(best), inc_key, ctl->inc_bits) < 0))
-        upd = 1;
-    }
-    s_upd = upd;
-  }
-  __syncthreads();
-  if (s_upd) {  // the incumbent's record stays on the device; the host fetches it when asked (lpr_knap_get_incumbent)
-    const uint64_t* src = rec_of(best);
-    for (int t = tid; t < (int)rec_words; t += kPlanT) inc_rec[t] = src[t];
-    for (int t = tid; t < W; t += kPlanT) inc_key[t] = src[2 * (size_t)W + t];
-    __syncthreads();
-    if (tid == 0) {
-      ctl->has_inc = 1;
-      ctl->inc_val = evals[best].val;
-      ctl->inc_bits = bits_of(best);
-      ctl->inc_crit = evals[best].crit;
-      ctl->inc_version++;
-    }
-    __syncthreads();
-  }
-  const int has_inc = ctl->has_inc;
-  const double inc_val = ctl->inc_val;
-  const int inc_bits = ctl->inc_bits;
-  const int per = (nb + kPlanT - 1) / kPlanT;
-  const int i0 = tid * per, i1 = min(nb, i0 + per);
-  int cnt = 0;
-  for (int i = i0; i < i1; i++) {
-    int keep = 0;
-    if (evals[i].type == 2) {
-      const double bv = evals[i].val;
-      keep = !has_inc || bv > inc_val ||
-             (bv == inc_val && knap_key_order(key_of(i), bits_of(i), inc_key, inc_bits) <= 0);
-    }
-    evals[i].pad = keep;
-    cnt += keep;
-  }
-  s_cnt[tid] = cnt;
-  __syncthreads();
-  for (int o = 1; o < kPlanT; o <<= 1) {  // inclusive scan
-    const int add = tid >= o ? s_cnt[tid - o] : 0;
-    __syncthreads();
-    s_cnt[tid] += add;
-    __syncthreads();
-  }
-  if (tid == kPlanT - 1) s_total = s_cnt[tid];
-  int off = s_cnt[tid] - cnt;
-  __syncthreads();
-  const int nj = s_total;
-  const bool full = first + 2LL * nj > ctl->pool_cap;
-  if (!full)
-    for (int i = i0; i < i1; i++)
-      if (evals[i].pad) parent[off++] = i;
-  __syncthreads();
-  if (tid == 0) {
-    if (full) {  // the batch cannot be expanded: report, keep the nodes where they are
+    counts[ncta] = nj;
+    const long long first = ctl->ev_first;
+    if (first + 2LL * nj > ctl->pool_cap) {  // the batch cannot be expanded: report, keep the nodes where they are
       ctl->error = 1;
       ctl->stop = 1;
       ctl->ex_nj = 0;
@@ -260,6 +358,7 @@ __global__ void __launch_bounds__(kPlanT) k_knap_plan(KnapCtl* ctl, const uint64
       ctl->open = open;
       ctl->ex_first = first;
       ctl->ex_nj = nj;
+      ctl->ex_ncta = ncta;
       long long next = open < (long long)ctl->batch ? open : (long long)ctl->batch;
       if (ctl->max_nodes >= 0) {
         const long long left = ctl->max_nodes - ctl->processed;
@@ -272,16 +371,42 @@ __global__ void __launch_bounds__(kPlanT) k_knap_plan(KnapCtl* ctl, const uint64
   }
 }
 
-// surviving parents -> staging (their slots are about to be overwritten by children of other parents)
+// surviving parents -> staging (their slots are about to be overwritten by children of other parents).  Job j is the
+// j-th survivor in batch order: its evaluation CTA is found by binary search over the scanned counts, its lane from
+// the ballot words.  parent[j] is written for k_knap_expand.
 __global__ void __launch_bounds__(128) k_knap_gather(const KnapCtl* __restrict__ ctl, const uint64_t* __restrict__ pool,
-                                                     size_t rec_words, const long long* __restrict__ parent,
-                                                     uint64_t* __restrict__ stage) {
+                                                     size_t rec_words, const int* __restrict__ counts,
+                                                     const unsigned* __restrict__ masks,
+                                                     long long* __restrict__ parent, uint64_t* __restrict__ stage) {
+  __shared__ int s_node;
   const int nj = ctl->ex_nj;
   const long long first = ctl->ex_first;
   for (int job = blockIdx.x; job < nj; job += gridDim.x) {
-    const uint64_t* src = pool + (size_t)(first + parent[job]) * rec_words;
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = ctl->ex_ncta;  // counts[lo] <= job < counts[hi]: counts is non-decreasing, counts[ncta] = nj
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (counts[mid] <= job) lo = mid; else hi = mid;
+      }
+      int r = job - counts[lo];  // rank inside CTA lo
+      int node = -1;
+      for (int q = 0; q < kEvT / 32; q++) {
+        const unsigned m = masks[lo * (kEvT / 32) + q];
+        const int c = __popc(m);
+        if (r < c) {
+          node = lo * kEvT + q * 32 + (__fns(m, 0, r + 1));
+          break;
+        }
+        r -= c;
+      }
+      s_node = node;
+      parent[job] = node;
+    }
+    __syncthreads();
+    const uint64_t* src = pool + (size_t)(first + s_node) * rec_words;
     uint64_t* dst = stage + (size_t)job * rec_words;
     for (int t = threadIdx.x; t < (int)rec_words; t += blockDim.x) dst[t] = src[t];
+    __syncthreads();
   }
 }
 
@@ -416,6 +541,9 @@ struct lpr_knap {
   uint64_t* pool = nullptr;
   long long pool_cap = 0, open = 0;  // `open` mirrors ctl->open between runs (export / import work on it)
   KnapEval* d_eval = nullptr;
+  KnapCand* d_cands = nullptr;   // best candidate of every evaluation CTA
+  unsigned* d_masks = nullptr;   // survivor ballots, one word per warp of the batch
+  int* d_counts = nullptr;       // survivors per evaluation CTA, scanned in place (+ the total)
   long long* d_parent = nullptr;
   uint64_t* stage = nullptr;  // surviving parents of a level (children are written over the batch's slots)
   int batch = 0;
@@ -476,6 +604,7 @@ int lpr_knap_destroy(lpr_knap* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_w); cudaFree(h->d_v); cudaFree(h->d_rank); cudaFree(h->pool); cudaFree(h->d_eval);
   cudaFree(h->d_parent); cudaFree(h->stage); cudaFree(h->d_inc_key); cudaFree(h->d_inc_rec); cudaFree(h->d_chosen);
+  cudaFree(h->d_cands); cudaFree(h->d_masks); cudaFree(h->d_counts);
   cudaFree(h->d_ctl);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -512,7 +641,7 @@ int lpr_knap_create(int device, double capacity, int n, const double* weights, c
     rv[p] = values[h->rank[p]];
   }
   const char* be = getenv("LPR_KNAP_BATCH");
-  h->batch = be ? std::max(32, atoi(be)) : 16384;
+  h->batch = be ? std::max(32, atoi(be)) : 65536;  // wide trees: 630 M nodes/s at 65536 against 323 M at 16384
   const char* pe = getenv("LPR_KNAP_POOL_MB");
   const size_t pool_bytes = (size_t)(pe ? std::max(16, atoi(pe)) : 4096) << 20;
   h->pool_cap = std::max<long long>((long long)(pool_bytes / (h->rec_words * 8)), 4LL * h->batch);
@@ -531,6 +660,12 @@ int lpr_knap_create(int device, double capacity, int n, const double* weights, c
   TRY(cudaMalloc(&h->stage, sizeof(uint64_t) * h->rec_words * (size_t)h->batch));
   TRY(cudaMalloc(&h->d_eval, sizeof(KnapEval) * h->batch));
   TRY(cudaMalloc(&h->d_parent, sizeof(long long) * h->batch));
+  {
+    const int ncta = (h->batch + kEvT - 1) / kEvT;
+    TRY(cudaMalloc(&h->d_cands, sizeof(KnapCand) * ncta));
+    TRY(cudaMalloc(&h->d_masks, sizeof(unsigned) * ncta * (kEvT / 32)));
+    TRY(cudaMalloc(&h->d_counts, sizeof(int) * (ncta + 1)));
+  }
   TRY(cudaMalloc(&h->d_inc_key, sizeof(uint64_t) * h->W));
   TRY(cudaMalloc(&h->d_inc_rec, sizeof(uint64_t) * h->rec_words));
   TRY(cudaMalloc(&h->d_chosen, n));
@@ -571,7 +706,7 @@ int lpr_knap_open_count(lpr_knap* h, int64_t* n) {
 }
 
 // Levels are enqueued several at a time; the host only reads the control block between such groups (4, 8, ... 32
-// levels), so a level costs four back-to-back launches and no round trip.  A group enqueued after the device has
+// levels), so a level costs six back-to-back launches and no round trip.  A group enqueued after the device has
 // stopped (pool empty, budget reached) falls through: every kernel returns on ctl->stop / empty counts.
 int lpr_knap_run_timed(lpr_knap* h, int64_t max_nodes, double max_seconds, int64_t* processed, int* status) {
   if (!h) return fail(LPR_E_BADARG, "null handle");
@@ -579,19 +714,26 @@ int lpr_knap_run_timed(lpr_knap* h, int64_t max_nodes, double max_seconds, int64
   if (rc) return rc;
   const double t0 = knap_now();
   const long long before = h->h_ctl->processed;
-  const int g_eval = (h->batch + 127) / 128;
+  const int g_eval = (h->batch + kEvT - 1) / kEvT;
   const int g_exp = std::max(1, std::min(h->batch, h->sms * 8));
   k_knap_start<<<1, 1, 0, h->stream>>>(h->d_ctl, h->open, (long long)max_nodes, h->batch);
   LPR_LAUNCH_CHECK();
   int group = 4;
   while (true) {
     for (int l = 0; l < group; l++) {
-      k_knap_eval<<<g_eval, 128, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->n, h->d_w, h->d_v, h->d_eval);
+      k_knap_eval<<<g_eval, kEvT, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->n, h->d_w, h->d_v, h->d_eval,
+                                                   h->d_cands);
       LPR_LAUNCH_CHECK();
-      k_knap_plan<<<1, kPlanT, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->d_eval, h->d_parent,
-                                               h->d_inc_key, h->d_inc_rec);
+      k_knap_inc<<<1, kIncT, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->d_eval, h->d_cands, h->d_inc_key,
+                                             h->d_inc_rec);
       LPR_LAUNCH_CHECK();
-      k_knap_gather<<<g_exp, 128, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->d_parent, h->stage);
+      k_knap_flag<<<g_eval, kEvT, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->d_eval, h->d_inc_key,
+                                                   h->d_masks, h->d_counts);
+      LPR_LAUNCH_CHECK();
+      k_knap_scan<<<1, kScanT, 0, h->stream>>>(h->d_ctl, h->d_counts);
+      LPR_LAUNCH_CHECK();
+      k_knap_gather<<<g_exp, 128, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->d_counts, h->d_masks, h->d_parent,
+                                                  h->stage);
       LPR_LAUNCH_CHECK();
       k_knap_expand<<<g_exp, 128, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->d_parent, h->d_eval, h->stage);
       LPR_LAUNCH_CHECK();

@@ -20,15 +20,33 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
   return r;
 }
 
-// one TILE = kSweepThreads * UNROLL 16-byte chunks of the flat R x ld/2 array, tile index t
-template <int SKIP, bool OOP, bool EMIT, int UNROLL>
+// L1-cached loads with ordinary coherence rules (ld.global.ca): a line is dropped by the acquire fence of a grid
+// barrier, unlike the non-coherent read-only path (__ldg / const __restrict__), which is only refreshed at kernel
+// boundaries
+__device__ __forceinline__ double ld_ca(const double* p) {
+  double r;
+  asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_ca2(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.ca.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+// one TILE = kSweepThreads * UNROLL 16-byte chunks of the flat R x ld/2 array, tile index t.
+// COHERENT: the factor column and the pivot row are re-staged by OTHER CTAs of the same (persistent) kernel between
+// calls, so they must not come through the non-coherent read-only path (__ldg): ld.global.ca instead.
+template <int SKIP, bool OOP, bool EMIT, int UNROLL, bool COHERENT = false>
 __device__ __forceinline__ void sweep_tile(const double2* __restrict__ src, double2* __restrict__ dst,
                                            const double* __restrict__ f, const double2* __restrict__ prow2,
                                            double* __restrict__ cn, double* __restrict__ rhsb,
                                            unsigned long long n, unsigned ldv, int p, unsigned long long t,
-                                           double eps, unsigned rhs_chunk, int rhs_odd, unsigned e_chunk, int e_odd) {
+                                           double eps, unsigned rhs_chunk, int rhs_odd, unsigned e_chunk, int e_odd,
+                                           unsigned tix = threadIdx.x) {
+  // tix: this thread's position among the kSweepThreads threads working on tile t (a wider CTA runs several tiles)
   constexpr unsigned TILE = kSweepThreads * UNROLL;
-  const unsigned long long q0 = t * TILE + threadIdx.x;
+  const unsigned long long q0 = t * TILE + tix;
   unsigned row = (unsigned)(q0 / ldv);
   unsigned c = (unsigned)(q0 - (unsigned long long)row * ldv);
   double2 x[UNROLL];
@@ -43,7 +61,7 @@ __device__ __forceinline__ void sweep_tile(const double2* __restrict__ src, doub
     act[k] = q < n;
     if (act[k]) {
       if (SKIP != 0) {  // the skip decision needs f before the load is issued
-        fv[k] = __ldg(f + row);
+        fv[k] = COHERENT ? ld_ca(f + row) : __ldg(f + row);
         bool sk = ((int)row != p) && ((SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps));
         if (sk && !OOP) act[k] = false;
       }
@@ -56,8 +74,8 @@ __device__ __forceinline__ void sweep_tile(const double2* __restrict__ src, doub
   for (int k = 0; k < UNROLL; k++) {
     if (!act[k]) continue;
     const unsigned long long q = q0 + (unsigned long long)k * kSweepThreads;
-    if (SKIP == 0) fv[k] = __ldg(f + rw[k]);  // L1-resident: loaded late to keep registers low
-    const double2 pr = __ldg(prow2 + cc[k]);
+    if (SKIP == 0) fv[k] = COHERENT ? ld_ca(f + rw[k]) : __ldg(f + rw[k]);  // L1-resident: loaded late (registers)
+    const double2 pr = COHERENT ? ld_ca2(prow2 + cc[k]) : __ldg(prow2 + cc[k]);
     double2 y;
     bool sk = false;
     if (SKIP != 0 && OOP && (int)rw[k] != p) sk = (SKIP == 1) ? (fabs(fv[k]) <= eps) : (fabs(fv[k]) < eps);

@@ -61,7 +61,8 @@ if __name__ == "__main__":
               ("almost_strong", 388, 400, 1000), ("strong", 389, 50, 1000), ("strong", 389, 100, 1000),
               ("weak", 393, 10000, 100), ("weak", 394, 30000, 300)]
     cap = int(os.environ.get("KNAP_PROBE_CAP", "1500000000"))
-    for kind, seed, n, R in {"first": first, "second": second, "third": third}[which]:
+    lists = {"first": first, "second": second, "third": third, "cfg4": first[:1], "hard": [("strong", 395, 110, 1000)]}
+    for kind, seed, n, R in lists[which]:
         try:
             run(kind, seed, n, ng, cap_nodes=cap, R=R)
         except Exception as ex:
