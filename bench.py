@@ -313,6 +313,22 @@ def main():
     e2e_value = world * e2e_piv / te_max
     assert ze == zval, "e2e and resident solves disagree"
 
+    # -------- B&B simplex pool through the second driver (one process per GPU over torch.distributed / NCCL): every
+    # rank takes part.  Kept beside the in-library driver because a pool is host-API heavy (~40 CUDA calls per 0.7 ms
+    # batch) and eight pools driven by eight THREADS of one process contend inside the CUDA driver (4.4x at 8 GPUs),
+    # while eight processes do not (7.9x)
+    bb_tr = None
+    if world > 1 and not os.environ.get("LPR_BENCH_SKIP_BB"):
+        os.environ.setdefault("LPR_BB_PREALLOC_MB", "126976")
+        os.environ.setdefault("LPR_BB_MAX_DEPTH", "192")
+        from lpr_381_group_v22_b200.bench_workloads import run_bb_cfg5
+        try:
+            slices = int(os.environ.get("LPR_BENCH_BB_SLICES", "12"))
+            bb_tr = run_bb_cfg5(512, 1024, 385, dev, dist, slices * 1024, 1024,
+                                float(os.environ.get("LPR_BENCH_BB_SLICE_MS", "10")), with_cuts=False)
+        except Exception as ex:
+            bb_tr = {"error": repr(ex)}
+
     # -------- from here on rank 0 works alone; the other ranks wait on the rendezvous store (a CPU wait: a NCCL barrier
     # would park a spinning kernel on their GPUs, which rank 0's in-library multi-GPU legs are about to use) ------------
     barrier(dist, local)
@@ -347,6 +363,10 @@ def main():
             bb = run_bb_legs(W, O, world, dev)
         except Exception as ex:  # the headline line must still be printed
             bb = {"error": repr(ex)}
+        if bb_tr is not None:
+            keep = ("n_gpus", "nodes", "seconds", "nodes_per_s", "pivots_per_node", "open_left", "steals", "rounds",
+                    "run_seconds_per_rank", "depth_overflow", "error")
+            bb["process_per_gpu_driver"] = {k: bb_tr[k] for k in keep if k in bb_tr}
         try:
             knap = run_knap_legs(W, O, world, dev)
         except Exception as ex:
@@ -455,6 +475,11 @@ def main():
     if bb and "nodes_per_s" in bb:
         mg.update(bb_nodes_per_s=bb["nodes_per_s"], bb_gbs=bb["roofline"]["achieved"], bb_frac=bb["roofline"]["frac"],
                   bb_bytes_per_node=bb["roofline"]["bytes_per_node"], bb_pivots_per_node=bb["pivots_per_node"])
+        ppg = bb.get("process_per_gpu_driver") or {}
+        if "nodes_per_s" in ppg:
+            rcb = 16.0 * (512 + 2) * (1024 + 512 + 2)
+            mg.update(bb_process_per_gpu_nodes_per_s=ppg["nodes_per_s"],
+                      bb_process_per_gpu_gbs=rcb * (2.0 + ppg["pivots_per_node"]) * ppg["nodes_per_s"] / 1e9)
         if isinstance(bb.get("closed_instance"), dict):
             mg.update(bb_closed_nodes=bb["closed_instance"].get("nodes"), bb_closed_z=bb["closed_instance"].get("incumbent_z"),
                       bb_incumbent_sha=bb["closed_instance"].get("incumbent_sha"),
@@ -561,7 +586,7 @@ def run_knap_legs(W, O, world, dev):
     out["cpu_baseline"] = {"value": ref["nodes"] / dq, "unit": "nodes/s", "cores": 1, "kind": "port",
                            "sample": f"first {ref['nodes']} nodes of the oracle's depth-first B&B on cfg4 ({dq:.1f} s), single thread"}
     try:
-        hn, hseed = int(os.environ.get("LPR_BENCH_KNAP_HARD_N", "110")), 395
+        hn, hseed = int(os.environ.get("LPR_BENCH_KNAP_HARD_N", "120")), 395
         w2, v2, cap2 = W.gen_knapsack_hard(hseed, hn)
         hard, _ = W.knap_mgpu(w2, v2, cap2, world, max_nodes=int(os.environ.get("LPR_BENCH_KNAP_HARD_NODES", "-1")))
         hard["workload"] = (f"cfg4-hard: strongly correlated (v = w + 100) n={hn}, seed {hseed}, capacity {cap2:.0f}, "

@@ -277,12 +277,32 @@ class RevisedPrimalSimplexSolver {
   RevisedPrimalSimplexSolver(const RevisedPrimalSimplexSolver&) = delete;
   RevisedPrimalSimplexSolver& operator=(const RevisedPrimalSimplexSolver&) = delete;
 
+  std::vector<std::string> IterationSnapshots;  // one CaptureSnapshot block per iteration + "Optimal" (:226-246, :124-146)
+  // below this many table elements Solve() steps iteration by iteration and records the reference's text blocks
+  // (SURVEY 8b "Snapshots"); above it the loop runs entirely on the device and no text is built
+  long TraceMaxElements = 4096;
+
   void Solve() {  // :82-251; exceptions :91, :179, :267
     int st = 0;
-    int64_t nit = 0;
-    std::vector<int> log(3 * 65536);
-    Check(lpr_rev_solve(rev_, -1, 0, &st, &nit, log.data(), 65536));
-    for (int64_t k = 0; k < nit && k < 65536; k++) PivotLog.push_back({log[3 * k], log[3 * k + 1], log[3 * k + 2]});
+    if ((long)m_ * (n_ + m_ + 1) <= TraceMaxElements) {
+      Check(lpr_rev_begin(rev_));
+      while (true) {
+        int e = -1, lr = -1, lv = -1;
+        Check(lpr_rev_step(rev_, &st, &e, &lr, &lv));
+        if (st != LPR_RUNNING && st != LPR_OPTIMAL) break;
+        const char* text = nullptr;
+        int64_t len = 0;
+        Check(lpr_rev_format_snapshot(rev_, &text, &len));
+        IterationSnapshots.emplace_back(text, (size_t)len);
+        if (st == LPR_OPTIMAL) break;
+        PivotLog.push_back({lr, e, lv});
+      }
+    } else {
+      int64_t nit = 0;
+      std::vector<int> log(3 * 65536);
+      Check(lpr_rev_solve(rev_, -1, 0, &st, &nit, log.data(), 65536));
+      for (int64_t k = 0; k < nit && k < 65536; k++) PivotLog.push_back({log[3 * k], log[3 * k + 1], log[3 * k + 2]});
+    }
     if (st == LPR_INFEASIBLE) throw std::runtime_error("Infeasible basis (negative basic value).");
     if (st == LPR_UNBOUNDED) throw std::runtime_error("Unbounded problem (no positive component in direction).");
     if (st == LPR_PIVOT_TOO_SMALL) throw std::runtime_error("Pivot too small.");
@@ -531,9 +551,14 @@ class KnapsackBranchBoundSimplex {
  public:
   KnapsackBranchBoundSimplex(int capacity, std::vector<double> weights, std::vector<double> values)
       : cap_(capacity), w_(std::move(weights)), v_(std::move(values)), chosen_(w_.size(), 0) {}
+  int Gpus = 1;  // > 1: the open-node pool is partitioned over that many GPUs inside the library (lpr_knap_solve_mgpu)
   double Solve() {
     int st = 0;
-    Check(lpr_knap_solve(0, cap_, (int)w_.size(), w_.data(), v_.data(), -1, &best_, chosen_.data(), &nodes_, &st));
+    if (Gpus > 1)
+      Check(lpr_knap_solve_mgpu(Gpus, nullptr, cap_, (int)w_.size(), w_.data(), v_.data(), -1, -1, 0.0, &best_,
+                                chosen_.data(), &nodes_, &st, nullptr));
+    else
+      Check(lpr_knap_solve(0, cap_, (int)w_.size(), w_.data(), v_.data(), -1, &best_, chosen_.data(), &nodes_, &st));
     return best_;
   }
   std::vector<KnapsackItem> GetSelectedItemsOriginal() const {

@@ -255,6 +255,9 @@ int lpr_knap_run(lpr_knap* h, int64_t max_nodes, int64_t* processed, int* status
 /* same with a time slice: returns after the group of tree levels during which max_seconds (> 0) have elapsed */
 int lpr_knap_run_timed(lpr_knap* h, int64_t max_nodes, double max_seconds, int64_t* processed, int* status);
 int lpr_knap_open_count(lpr_knap* h, int64_t* n);
+/* keep the open nodes at stack positions == offset (mod stride), drop the others (start-up partition of the multi-GPU
+ * driver: every rank expands the same root identically, then keeps its share; same idea as lpr_bb_keep_stride) */
+int lpr_knap_keep_stride(lpr_knap* h, int offset, int stride);
 int lpr_knap_get_incumbent(lpr_knap* h, double* best, uint8_t* chosen /* n, original ids */,
                            uint64_t* key /* key_words */, int* key_bits);
 int lpr_knap_set_incumbent(lpr_knap* h, double best, const uint8_t* chosen, const uint64_t* key,

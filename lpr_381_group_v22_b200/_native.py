@@ -136,6 +136,7 @@ SIGNATURES = {
                                       lp, ip, C.POINTER(MgpuStats)]),
     "lpr_nccl_version": (C.c_int, [ip]),
     "lpr_knap_open_count": (C.c_int, [vp, lp]),
+    "lpr_knap_keep_stride": (C.c_int, [vp, C.c_int, C.c_int]),
     "lpr_knap_get_incumbent": (C.c_int, [vp, dp, bp, u64p, ip]),
     "lpr_knap_set_incumbent": (C.c_int, [vp, C.c_double, bp, u64p, C.c_int]),
     "lpr_knap_export_nodes": (C.c_int, [vp, C.c_int, vp, C.c_int64, lp, ip]),

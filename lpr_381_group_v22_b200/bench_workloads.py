@@ -130,7 +130,7 @@ def knap_dp_check(w, v, cap, device=0):
 
 def gen_knapsack_hard(seed, n, R=1000):
     """'cfg4-hard': Pisinger's strongly correlated family, v = w + R/10 -- every item has nearly the same value/weight
-    ratio, so the LP bound prunes late: n = 110 (seed 395) is a 577 M-node tree, 3.4 s of work for one B200, and it
+    ratio, so the LP bound prunes late: n = 120 (seed 395) is a 1.58 G-node tree, 2.5 s of work for one B200, and it
     CLOSES, so the selection can be compared between GPU counts (tools/knap_probe.py has the survey of families)"""
     idx = np.arange(n, dtype=np.uint64)
     w = 1.0 + np.floor(R * u01(seed, 0, idx))
@@ -141,7 +141,7 @@ def _sync_time(comm, t):
     return comm.allreduce_max(t)
 
 
-def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk, slice_ms=0.0):
+def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk, slice_ms=0.0, with_cuts=True):
     """LP relaxation with the tableau solver, then branch & bound simplex with reference semantics
     (4-d.p. rounding, dual-then-primal node solves), node cap lifted to `max_nodes` per rank-round budget,
     pruning on; the pool is partitioned across the ranks.  `slice_ms` > 0: rounds are time slices of that
@@ -164,7 +164,7 @@ def run_bb_cfg5(m, n, seed, device, dist, max_nodes, chunk, slice_ms=0.0):
     # on the relaxation's final tableau, cut rows generated on the device; reported beside the tree search, which like
     # the reference's menu path starts from the relaxation itself.  Rank 0 only, outside the timed region.
     cuts = None
-    if comm.rank == 0:
+    if comm.rank == 0 and with_cuts:
         try:
             with DeviceTableau.from_host(final, device=device, row_cap=final.shape[0] + 40) as tc:
                 tq = time.perf_counter()

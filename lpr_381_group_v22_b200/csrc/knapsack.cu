@@ -454,6 +454,16 @@ __global__ void __launch_bounds__(128) k_knap_expand(const KnapCtl* __restrict__
   }
 }
 
+// stage[j] = pool[offset + j * stride]: the records one rank keeps after every rank has expanded the same root
+__global__ void k_knap_pick_stride(const uint64_t* __restrict__ pool, size_t rec_words, long long kept, int offset,
+                                   int stride, uint64_t* __restrict__ stage) {
+  for (long long j = blockIdx.x; j < kept; j += gridDim.x) {
+    const uint64_t* src = pool + (size_t)(offset + j * stride) * rec_words;
+    uint64_t* dst = stage + (size_t)j * rec_words;
+    for (int t = threadIdx.x; t < (int)rec_words; t += blockDim.x) dst[t] = src[t];
+  }
+}
+
 // start of a run: the host's view of the stack (it may have exported / imported records) and the node budget
 __global__ void k_knap_start(KnapCtl* ctl, long long open, long long budget, int batch) {
   ctl->open = open;
@@ -747,7 +757,8 @@ int lpr_knap_run_timed(lpr_knap* h, int64_t max_nodes, double max_seconds, int64
     }
     if (h->h_ctl->stop) break;
     if (max_seconds > 0.0 && knap_now() - t0 >= max_seconds) break;
-    group = std::min(32, group * 2);
+    // a time slice is only checked between groups: keep the groups short then (a 65536-node level takes ~100 us)
+    group = std::min(max_seconds > 0.0 ? 8 : 32, group * 2);
   }
   h->open = h->h_ctl->open;
   const int64_t done = h->h_ctl->processed - before;
@@ -756,6 +767,27 @@ int lpr_knap_run_timed(lpr_knap* h, int64_t max_nodes, double max_seconds, int64
   h->t_run += knap_now() - t0;
   if (processed) *processed = done;
   if (status) *status = (h->open > 0 && max_nodes >= 0 && done >= max_nodes) ? LPR_NODE_LIMIT : LPR_OPTIMAL;
+  return LPR_OK;
+}
+
+// keep the open nodes whose position in the stack is == offset (mod stride) and drop the others: after every rank has
+// expanded the same root for the same number of nodes (the level loop is deterministic, so the pools are identical),
+// each keeps its own share -- a start-up partition without any transfer (csrc/multi_gpu.cu)
+int lpr_knap_keep_stride(lpr_knap* h, int offset, int stride) {
+  if (!h || stride < 1 || offset < 0 || offset >= stride) return fail(LPR_E_BADARG, "bad keep_stride arguments");
+  int rc = select_device(h->device);
+  if (rc) return rc;
+  const long long kept = h->open > offset ? (h->open - offset + stride - 1) / stride : 0;
+  if (kept > h->batch) return fail(LPR_E_CAPACITY, "keep_stride: %lld records exceed the staging area", kept);
+  if (kept > 0) {
+    k_knap_pick_stride<<<(int)std::min<long long>(kept, 1024), 128, 0, h->stream>>>(h->pool, h->rec_words, kept, offset,
+                                                                                   stride, h->stage);
+    LPR_LAUNCH_CHECK();
+    LPR_CUDA(cudaMemcpyAsync(h->pool, h->stage, sizeof(uint64_t) * h->rec_words * (size_t)kept, cudaMemcpyDeviceToDevice,
+                             h->stream));
+  }
+  LPR_CUDA(cudaStreamSynchronize(h->stream));
+  h->open = kept;
   return LPR_OK;
 }
 

@@ -225,16 +225,11 @@ struct KnapPoolC : Pool {
   const KnapProblem& p;
   lpr_knap* h = nullptr;
   explicit KnapPoolC(const KnapProblem& pp) : p(pp) {}
-  int create(int device, bool with_root) override {
-    int rc = lpr_knap_create(device, p.capacity, p.n, p.w, p.v, &h);
-    if (rc == LPR_OK && !with_root) {  // only rank 0 starts with the root
-      std::vector<uint64_t> drop(3 * ((size_t)p.n + 63) / 64 + 16);
-      int64_t bytes = 0;
-      int n = 0;
-      rc = lpr_knap_export_nodes(h, 1, drop.data(), (int64_t)drop.size() * 8, &bytes, &n);
-    }
-    return rc;
-  }
+  // every rank is given the root: all expand it identically (the level loop is deterministic) and keep every
+  // world-th node, so nobody starts empty and nothing is transferred
+  int create(int device, bool) override { return lpr_knap_create(device, p.capacity, p.n, p.w, p.v, &h); }
+  int keep_stride(int off, int stride) override { return lpr_knap_keep_stride(h, off, stride); }
+  bool replicated_root() const override { return true; }
   void destroy() override {
     lpr_knap_destroy(h);
     h = nullptr;
@@ -687,7 +682,10 @@ int lpr_bb_solve_mgpu(int n_gpus, const int* devices, int rows, int cols, const 
   // two pools per device by default: the child construction of one (HBM bound) runs beside the pivot chains of the
   // other (latency bound); each gets its share of the slab budget
   const char* rp = getenv("LPR_MG_RANKS_PER_GPU");
-  cfg.ranks_per_gpu = rp ? std::max(1, atoi(rp)) : 2;
+  // ... when the host has the cores for it: every pool is a host thread that spins on its stream (measured on a
+  // 16-core box: 8 GPUs x 2 pools ran at 4.4x one GPU, the threads were starving each other)
+  const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+  cfg.ranks_per_gpu = rp ? std::max(1, atoi(rp)) : ((unsigned)n_gpus * 4u <= cores ? 2 : 1);
   bb_set_prealloc_share(cfg.ranks_per_gpu);
   Incumbent inc;
   Shared* sh = nullptr;
@@ -717,8 +715,8 @@ int lpr_knap_solve_mgpu(int n_gpus, const int* devices, double capacity, int n, 
   cfg.max_rounds = max_rounds;
   cfg.slice_seconds = slice_seconds > 0.0 ? slice_seconds : 2e-3;
   cfg.chunk_nodes = 1LL << 40;
-  cfg.seed_nodes_per_rank = 64;
-  cfg.low_water = 64;
+  cfg.seed_nodes_per_rank = 256;
+  cfg.low_water = 4096;  // a rank that cannot fill a fraction of a batch is about to run dry: refill it early
   const char* sm = getenv("LPR_MG_STAGE_MB");
   cfg.stage_bytes = (size_t)(sm ? std::max(16, atoi(sm)) : 256) << 20;
   const char* rp = getenv("LPR_MG_KNAP_RANKS_PER_GPU");

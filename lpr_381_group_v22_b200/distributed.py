@@ -402,8 +402,11 @@ def run_distributed(pool, dist=None, device="cpu", chunk_nodes=4096, payload_len
         t_steal += t_c - t_b
         t_run += t_d - t_c
     best = exchange_incumbent(pool, comm, payload_len) if world > 1 else pool.get_incumbent()
-    totals = comm.allgather_ints([processed, steals, moved, int(t_run * 1e6)])
+    # subtrees cut at the slab depth headroom make the incumbent unproven: callers must see it
+    ovf = pool.stats().get("depth_overflow", 0) if hasattr(pool, "stats") else 0
+    totals = comm.allgather_ints([processed, steals, moved, int(t_run * 1e6), int(ovf)])
     return dict(incumbent=best, nodes_local=processed, nodes_total=sum(t[0] for t in totals),
+                depth_overflow=sum(t[4] for t in totals),
                 steals=sum(t[1] for t in totals), nodes_moved=sum(t[2] for t in totals), rounds=rounds,
                 world=world, rank=rank, run_seconds_per_rank=[t[3] * 1e-6 for t in totals],
                 seconds_rank0=dict(seed=t_seed, status_and_incumbent=t_inc, steal=t_steal, run=t_run))

@@ -83,6 +83,12 @@ int main() {
     rev.Solve();
     REQUIRE(rev.FinalZ == 16.25 && (rev.SolutionVector == std::vector<double>{4.375, 0, 1.875}));
     REQUIRE((rev.BasicVariables() == std::vector<int>{2, 0}));
+    // one CaptureSnapshot block per iteration plus the "Optimal" block (RevisedPrimalSimplexSolver.cs:226-246, :124-146)
+    REQUIRE(rev.IterationSnapshots.size() == 3);
+    REQUIRE(rev.IterationSnapshots[0].rfind("Iteration 1\r\nCurrent Tableau (Revised Simplex)\r\nProblem type: MAX\r\n", 0) == 0);
+    REQUIRE(rev.IterationSnapshots[0].find("Entering variable (chosen pre-pivot): x3  (reduced cost pre = 4)") != std::string::npos);
+    REQUIRE(rev.IterationSnapshots[2].rfind("Optimal\r\n", 0) == 0);
+    REQUIRE(rev.IterationSnapshots[2].find("Basic Variables: x3, x1") != std::string::npos);
     bool threw = false;
     try {
       Simplex::RevisedPrimalSimplexSolver bad({1.0, 0.0}, {{{-1.0, 1.0}, "<=", 1.0}}, false);

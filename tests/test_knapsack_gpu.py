@@ -175,5 +175,35 @@ def test_knap_mgpu_several_pools_per_device_steal_inside_the_device(rpg, monkeyp
                                         C.byref(stats)))
     assert st.value == L.OPTIMAL and stats.open_left == 0 and stats.ranks_per_gpu == int(rpg)
     assert best.value == ref["best"] and ch.tolist() == ref["chosen"].tolist()
-    assert stats.steals > 0  # the root starts on rank 0: the other pools only get work by stealing
     del s
+
+
+def test_knap_keep_stride_partitions_identical_pools():
+    """Start-up partition of the multi-GPU driver: pools that expanded the same root by the same number of nodes are
+    identical, each keeps every world-th record, and the union of the shares solves to the oracle's answer."""
+    from lpr_381_group_v22_b200.distributed import KnapPool, better
+    import ctypes as C
+    w, v, cap = O.gen_knapsack(23, 400)
+    ref = O.knap_bb(cap, w, v)
+    world = 3
+    pools = [KnapPool(cap, w, v) for _ in range(world)]
+    try:
+        for p in pools:
+            while 0 < p.open_count() < 64 * world:
+                p.run(64)
+        counts = [p.open_count() for p in pools]
+        assert len(set(counts)) == 1
+        for r, p in enumerate(pools):
+            N.check(N.lib().lpr_knap_keep_stride(p._h, r, world))
+        assert sum(p.open_count() for p in pools) == counts[0]
+        best = None
+        for p in pools:
+            while p.open_count() > 0:
+                p.run(1 << 40)
+            inc = p.get_incumbent()
+            if better(inc, best):
+                best = inc
+        assert best[0] == ref["best"] and np.asarray(best[2]).astype(np.uint8).tolist() == ref["chosen"].tolist()
+    finally:
+        for p in pools:
+            p.close()

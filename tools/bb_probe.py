@@ -13,7 +13,10 @@ os.environ.setdefault("LPR_BB_MAX_DEPTH", "192")
 A, b, c = W.gen_dense_ip(385, 512, 1024)
 final, lp, ms = W.lp_relaxation(A, b, c, 0)
 bytes_rc = 16.0 * 514 * 1538
-for batch, rpg in ((64, 1), (64, 2), (128, 1), (128, 2), (64, 3), (256, 1), (32, 4)):
+configs = ((64, 1), (64, 2), (128, 1), (128, 2), (64, 3), (256, 1), (32, 4))
+if os.environ.get("BB_PROBE_CONFIGS"):  # e.g. "128:1,256:1"
+    configs = tuple(tuple(int(x) for x in c.split(":")) for c in os.environ["BB_PROBE_CONFIGS"].split(","))
+for batch, rpg in configs:
     os.environ["LPR_BB_BATCH"] = str(batch)
     os.environ["LPR_MG_RANKS_PER_GPU"] = str(rpg)
     if os.environ.get("LPR_BB_PROFILE"):

@@ -55,13 +55,14 @@ if __name__ == "__main__":
              ("weak", 386, 10000, 100000), ("uncorr", 387, 10000, 1000), ("almost_strong", 388, 2000, 1000),
              ("almost_strong", 388, 10000, 1000), ("strong", 389, 200, 1000), ("strong", 389, 1000, 1000),
              ("subset", 390, 1000, 100000)]
+    fourth = [("strong", 395, 115, 1000), ("strong", 395, 120, 1000), ("strong", 397, 110, 1000), ("strong", 398, 110, 1000), ("strong", 399, 112, 1000)]
     third = [("strong", 389, 110, 1000), ("strong", 389, 120, 1000), ("strong", 395, 110, 1000), ("almost_strong", 388, 250, 1000), ("almost_strong", 388, 300, 1000), ("subset", 392, 3000, 1000000), ("subset", 396, 5000, 1000000)]
     second = [("subset", 390, 2000, 100000), ("subset", 390, 4000, 100000), ("subset", 391, 1000, 1000000),
               ("subset", 392, 3000, 1000000), ("almost_strong", 388, 100, 1000), ("almost_strong", 388, 200, 1000),
               ("almost_strong", 388, 400, 1000), ("strong", 389, 50, 1000), ("strong", 389, 100, 1000),
               ("weak", 393, 10000, 100), ("weak", 394, 30000, 300)]
     cap = int(os.environ.get("KNAP_PROBE_CAP", "1500000000"))
-    lists = {"first": first, "second": second, "third": third, "cfg4": first[:1], "hard": [("strong", 395, 110, 1000)]}
+    lists = {"first": first, "second": second, "third": third, "cfg4": first[:1], "hard": [("strong", 395, 110, 1000)], "fourth": fourth}
     for kind, seed, n, R in lists[which]:
         try:
             run(kind, seed, n, ng, cap_nodes=cap, R=R)
