@@ -373,23 +373,25 @@ __global__ void __launch_bounds__(kScanT) k_knap_scan(KnapCtl* ctl, int* counts)
 
 // surviving parents -> staging (their slots are about to be overwritten by children of other parents).  Job j is the
 // j-th survivor in batch order: its evaluation CTA is found by binary search over the scanned counts, its lane from
-// the ballot words.  parent[j] is written for k_knap_expand.
+// the ballot words.  parent[j] is written for k_knap_expand.  One WARP per job (records range from 80 bytes at
+// n = 110 to 3.8 KB at n = 10^4: a CTA per job left 118 of 128 threads idle on the small ones).
 __global__ void __launch_bounds__(128) k_knap_gather(const KnapCtl* __restrict__ ctl, const uint64_t* __restrict__ pool,
                                                      size_t rec_words, const int* __restrict__ counts,
                                                      const unsigned* __restrict__ masks,
                                                      long long* __restrict__ parent, uint64_t* __restrict__ stage) {
-  __shared__ int s_node;
   const int nj = ctl->ex_nj;
   const long long first = ctl->ex_first;
-  for (int job = blockIdx.x; job < nj; job += gridDim.x) {
-    if (threadIdx.x == 0) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int job = warp; job < nj; job += nwarps) {
+    int node = -1;
+    if (lane == 0) {
       int lo = 0, hi = ctl->ex_ncta;  // counts[lo] <= job < counts[hi]: counts is non-decreasing, counts[ncta] = nj
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (counts[mid] <= job) lo = mid; else hi = mid;
       }
       int r = job - counts[lo];  // rank inside CTA lo
-      int node = -1;
       for (int q = 0; q < kEvT / 32; q++) {
         const unsigned m = masks[lo * (kEvT / 32) + q];
         const int c = __popc(m);
@@ -399,26 +401,26 @@ __global__ void __launch_bounds__(128) k_knap_gather(const KnapCtl* __restrict__
         }
         r -= c;
       }
-      s_node = node;
       parent[job] = node;
     }
-    __syncthreads();
-    const uint64_t* src = pool + (size_t)(first + s_node) * rec_words;
+    node = __shfl_sync(0xffffffffu, node, 0);
+    const uint64_t* src = pool + (size_t)(first + node) * rec_words;
     uint64_t* dst = stage + (size_t)job * rec_words;
-    for (int t = threadIdx.x; t < (int)rec_words; t += blockDim.x) dst[t] = src[t];
-    __syncthreads();
+    for (int t = lane; t < (int)rec_words; t += 32) dst[t] = src[t];
   }
 }
 
 // children of surviving nodes: job = index among the survivors (its parent record sits in stage[job]); two records
-// per job, each carrying the parent's fill state at its critical item
+// per job, each carrying the parent's fill state at its critical item.  One warp per job.
 __global__ void __launch_bounds__(128) k_knap_expand(const KnapCtl* __restrict__ ctl, uint64_t* pool, size_t rec_words,
                                                      int W, const long long* __restrict__ parent,
                                                      const KnapEval* __restrict__ evals,
                                                      const uint64_t* __restrict__ stage) {
   const int nj = ctl->ex_nj;
   const long long dst_first = ctl->ex_first;
-  for (int job = blockIdx.x; job < nj; job += gridDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int job = warp; job < nj; job += nwarps) {
     const uint64_t* src = stage + (size_t)job * rec_words;
     const KnapEval ev = evals[parent[job]];
     const int depth = (int)src[3 * (size_t)W];
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(128) k_knap_expand(const KnapCtl* __restrict__
     // stack order: the x_k = 1 child below the x_k = 0 child (the zero child is DFS-first)
     uint64_t* one = pool + (size_t)(dst_first + 2 * (long long)job) * rec_words;
     uint64_t* zero = one + rec_words;
-    for (int t = threadIdx.x; t < (int)rec_words; t += blockDim.x) {
+    for (int t = lane; t < (int)rec_words; t += 32) {
       uint64_t x = src[t], x1 = x, x0 = x;
       const int word = t % W, sect = t / W;
       if (t < 3 * W) {
