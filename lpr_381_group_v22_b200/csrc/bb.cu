@@ -159,7 +159,7 @@ __device__ __forceinline__ void bb_select_body(BBLp* lps, int lp_index, int* ctl
         int other = 0;
         for (int j = tid; j < C - 1; j += blockDim.x) {
           double a = TAT(T, ld, r, j);
-          double th = (a < 0.0) ? fabs(__ddiv_rn(T[j], a)) : kPosInf;
+          double th = (a < 0.0) ? fabs(ddiv(T[j], a)) : kPosInf;
           if (!(th == 0.0 || th == kPosInf)) other++;
         }
         other = block_sum_int(other, smi);
@@ -167,13 +167,13 @@ __device__ __forceinline__ void bb_select_body(BBLp* lps, int lp_index, int* ctl
           c = block_first_min(C - 1, [&](int j, double& val) {
             double a = TAT(T, ld, r, j);
             if (!(a < 0.0)) return false;
-            val = fabs(__ddiv_rn(T[j], a));
+            val = fabs(ddiv(T[j], a));
             return val == 0.0;
           }, sm);
         } else {  // min over theta > 0 (inf included), IndexOf => first
           c = block_first_min(C - 1, [&](int j, double& val) {
             double a = TAT(T, ld, r, j);
-            val = (a < 0.0) ? fabs(__ddiv_rn(T[j], a)) : kPosInf;
+            val = (a < 0.0) ? fabs(ddiv(T[j], a)) : kPosInf;
             return val > 0.0;
           }, sm);
         }
@@ -208,7 +208,7 @@ __device__ __forceinline__ void bb_select_body(BBLp* lps, int lp_index, int* ctl
         int notneg = 0, posfin = 0, zero = 0;
         for (int i = 1 + tid; i < R; i += blockDim.x) {
           double a = TAT(T, ld, i, c);
-          double th = (a != 0.0) ? __ddiv_rn(TAT(T, ld, i, C - 1), a) : kPosInf;
+          double th = (a != 0.0) ? ddiv(TAT(T, ld, i, C - 1), a) : kPosInf;
           if (!(th < 0.0)) notneg++;
           if (th > 0.0 && th != kPosInf) posfin++;
           if (th == 0.0) zero++;
@@ -224,7 +224,7 @@ __device__ __forceinline__ void bb_select_body(BBLp* lps, int lp_index, int* ctl
           } else {
             int k = block_first_min(R - 1, [&](int q, double& val) {
               double a = TAT(T, ld, q + 1, c);
-              val = (a != 0.0) ? __ddiv_rn(TAT(T, ld, q + 1, C - 1), a) : kPosInf;
+              val = (a != 0.0) ? ddiv(TAT(T, ld, q + 1, C - 1), a) : kPosInf;
               return val == 0.0;
             }, sm);
             r = k + 1;
@@ -232,7 +232,7 @@ __device__ __forceinline__ void bb_select_body(BBLp* lps, int lp_index, int* ctl
         } else {
           int k = block_first_min(R - 1, [&](int q, double& val) {
             double a = TAT(T, ld, q + 1, c);
-            val = (a != 0.0) ? __ddiv_rn(TAT(T, ld, q + 1, C - 1), a) : kPosInf;
+            val = (a != 0.0) ? ddiv(TAT(T, ld, q + 1, C - 1), a) : kPosInf;
             return val > 0.0 && val != kPosInf;
           }, sm);
           r = k + 1;
@@ -262,7 +262,7 @@ __device__ __forceinline__ void bb_select_body(BBLp* lps, int lp_index, int* ctl
   for (int j = tid; j < ld; j += blockDim.x) {
     double v = 0.0;
     if (j < C) {
-      v = __ddiv_rn(TAT(T, ld, r, j), piv);
+      v = ddiv(TAT(T, ld, r, j), piv);
       if (v == 0.0) v = 0.0;
     }
     lp.prow[j] = v;

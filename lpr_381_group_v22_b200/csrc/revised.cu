@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
   for (int i = tid; i < m; i += blockDim.x) {
     double ui = v.u[i];
     if (ui > EPS) {
-      double r = __ddiv_rn(v.xB[i], ui);
+      double r = ddiv(v.xB[i], ui);
       if (r == r) mn = minidx_combine(mn, MinIdx{r, i});
     }
   }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
   for (int i = tid; i < m; i += blockDim.x) {
     double ui = v.u[i];
     if (i != mn.i && ui > EPS) {
-      double r = __ddiv_rn(v.xB[i], ui);
+      double r = ddiv(v.xB[i], ui);
       if (!(mn.v < __dsub_rn(r, EPS)) || fabs(__dsub_rn(r, mn.v)) <= EPS || !(r == r)) bad++;
     }
   }
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
       for (int i = 0; i < m; i++) {
         double ui = v.u[i];
         if (ui > EPS) {
-          double r = __ddiv_rn(v.xB[i], ui);
+          double r = ddiv(v.xB[i], ui);
           if (r < __dsub_rn(best, EPS) ||
               (fabs(__dsub_rn(r, best)) <= EPS && (leave == -1 || v.basis[i] < v.basis[leave]))) {
             best = r;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(1024) k_ratio(RevView v) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int i = i0 + q * 1024 + tid;
-      if (i < m) v.ecoef[i] = (i == r) ? __ddiv_rn(1.0, pivot) : __ddiv_rn(-tu[q], pivot);
+      if (i < m) v.ecoef[i] = (i == r) ? ddiv(1.0, pivot) : ddiv(-tu[q], pivot);
       if (i < v.ldB) v.brow[i] = tb[q];
     }
   }

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, in
     int k = block_first_min(R - 1, [&](int q, double& val) {
       double a = TAT(T, ld, q + 1, e);
       if (!(a > 1e-9)) return false;
-      val = __ddiv_rn(TAT(T, ld, q + 1, C - 1), a);
+      val = ddiv(TAT(T, ld, q + 1, C - 1), a);
       return val >= 0.0 && val < DBL_MAX;
     }, sm);
     if (k < 0) { finish(LPR_UNBOUNDED); return; }
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, in
     int k = block_hyst_min(R - 1, [&](int q, double& val) {
       double a = TAT(T, ld, q + 1, e);
       if (!(a > EPS)) return false;
-      val = __ddiv_rn(TAT(T, ld, q + 1, C - 1), a);
+      val = ddiv(TAT(T, ld, q + 1, C - 1), a);
       return val > EPS;
     }, kPosInf, EPS, sm, smi);
     if (k < 0) { finish(LPR_UNBOUNDED); return; }
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, in
       if (!(a < -EPS)) return false;
       double num = T[j];
       if (!(fabs(num) > EPS)) return false;
-      val = fabs(__ddiv_rn(num, a));
+      val = fabs(ddiv(num, a));
       return true;
     }, kPosInf, EPS, sm, smi);
     if (e < 0) { finish(LPR_INFEASIBLE); return; }
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, in
         e = block_hyst_min(C - 1, [&](int j, double& val) {
           double a = TAT(T, ld, p, j);
           if (!(a < -EPS)) return false;
-          val = __ddiv_rn(T[j], -a);
+          val = ddiv(T[j], -a);
           return true;
         }, kPosInf, EPS, sm, smi);
         if (e < 0) { finish(LPR_INFEASIBLE); return; }
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, in
       int k = block_hyst_min(R - 1, [&](int q, double& val) {
         double a = TAT(T, ld, q + 1, e);
         if (!(a > EPS)) return false;
-        val = __ddiv_rn(TAT(T, ld, q + 1, C - 1), a);
+        val = ddiv(TAT(T, ld, q + 1, C - 1), a);
         return true;
       }, kPosInf, EPS, sm, smi);
       if (k < 0) { finish(LPR_UNBOUNDED); return; }
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(TabView v, int flags, in
   const double piv = TAT(T, ld, p, e);
   const int cur = st->cur;
   double* colb = cur ? v.col[1] : v.col[0];
-  for (int j = tid; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? __ddiv_rn(TAT(T, ld, p, j), piv) : 0.0;
+  for (int j = tid; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? ddiv(TAT(T, ld, p, j), piv) : 0.0;
   for (int i = tid; i < R; i += blockDim.x) colb[i] = TAT(T, ld, i, e);
   if (tid == 0) {
     st->enter = e;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) k_primal_select_fused(TabView v, MinIdx* 
       for (int q = 0; q < UR; q++) {
         const int i = base + q * 256 + tid;
         if (i < R && a[q] > 1e-9) {
-          const double val = __ddiv_rn(b[q], a[q]);
+          const double val = ddiv(b[q], a[q]);
           if (val >= 0.0 && val < DBL_MAX) {
             MinIdx cnd{val, i - 1};
             MinIdx nb = minidx_combine(best, cnd);
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) k_primal_select_fused(TabView v, MinIdx* 
     if (j < ld) {
       double pr = 0.0;
       if (j < C) {
-        pr = __ddiv_rn(TAT(T, ld, p, j), piv);
+        pr = ddiv(TAT(T, ld, p, j), piv);
         if (j < C - 1) {
           double z = __dsub_rn(t0j, __dmul_rn(f0, pr));
           if (z < 0.0) m = MinIdx{z, j};
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(kSelThreads) k_cut_select(TabView v, int cut_r
     if (!(a < -EPS)) return false;
     double num = T[j];
     if (!(fabs(num) > EPS)) return false;
-    val = fabs(__ddiv_rn(num, a));
+    val = fabs(ddiv(num, a));
     return true;
   }, kPosInf, EPS, sm, smi);
   if (e < 0) {
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(kSelThreads) k_cut_select(TabView v, int cut_r
     return;
   }
   double* colb = st->cur ? v.col[1] : v.col[0];
-  for (int j = threadIdx.x; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? __ddiv_rn(TAT(T, ld, cut_row, j), piv) : 0.0;
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? ddiv(TAT(T, ld, cut_row, j), piv) : 0.0;
   for (int i = threadIdx.x; i < R; i += blockDim.x) colb[i] = TAT(T, ld, i, e);
   if (threadIdx.x == 0) {
     st->enter = e;
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(kSelThreads) k_stage_pivot(TabView v, int p, i
   const int R = v.R, C = v.C, ld = v.ld;
   const double piv = TAT(v.T, ld, p, e);
   double* colb = st->cur ? v.col[1] : v.col[0];
-  for (int j = threadIdx.x; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? __ddiv_rn(TAT(v.T, ld, p, j), piv) : 0.0;
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) v.prow[j] = (j < C) ? ddiv(TAT(v.T, ld, p, j), piv) : 0.0;
   for (int i = threadIdx.x; i < R; i += blockDim.x) colb[i] = TAT(v.T, ld, i, e);
   if (threadIdx.x == 0) {
     st->enter = e;

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_blk_select(BlkView b, int group_pos) {
           if (i == 0) f0 = col[q];
           if (blockIdx.x == 0) b.F[(size_t)i * KM + s] = col[q];  // factor column of this pivot
           if (i >= 1 && col[q] > 1e-9) {
-            const double val = __ddiv_rn(rv[q], col[q]);
+            const double val = ddiv(rv[q], col[q]);
             if (val >= 0.0 && val < DBL_MAX) {
               MinIdx nb = minidx_combine(best, MinIdx{val, i - 1});
               if (nb.i != best.i) best_a = col[q];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_blk_select(BlkView b, int group_pos) {
           const double upd = (p == pu[u]) ? pru[u] : __dsub_rn(x, __dmul_rn(fu, pru[u]));
           x = (u < s) ? upd : x;
         }
-        pr = __ddiv_rn(x, piv);
+        pr = ddiv(x, piv);
         z = __dsub_rn(r0j, __dmul_rn(f0, pr));
         if (j < C - 1 && z < 0.0) m = MinIdx{z, j};
       }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) k_blk_select(BlkView b, int group_pos) {
     m = block_minidx(m, sm);
     if (blockIdx.x == 0) {
       // RHS column mirror: new = (i == p) ? prow[C-1] : rhs[i] - f_i * prow[C-1], prow[C-1] = rhs[p]/piv
-      const double prc = __ddiv_rn(rhs[p], piv);
+      const double prc = ddiv(rhs[p], piv);
       for (int i = tid; i < R; i += blockDim.x) {
         const double fi = b.F[(size_t)i * KM + s];  // written by this same thread above
         rhs_next[i] = (i == p) ? prc : __dsub_rn(rhs[i], __dmul_rn(fi, prc));
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) k_blk_select2(BlkView b, int group_pos, R
           if (i == 0) *f0buf = colk[q];
           b.F[(size_t)i * KM + s] = colk[q];  // factor column of this pivot
           if (i >= 1 && colk[q] > 1e-9) {
-            const double val = __ddiv_rn(rv[q], colk[q]);
+            const double val = ddiv(rv[q], colk[q]);
             if (val >= 0.0 && val < DBL_MAX) {
               MinIdx nb = minidx_combine(best, MinIdx{val, i - 1});
               if (nb.i != best.i) best_a = colk[q];
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) k_blk_select2(BlkView b, int group_pos, R
           const double upd = (p == pu[u]) ? pru[u] : __dsub_rn(x, __dmul_rn(fu, pru[u]));
           x = (u < s) ? upd : x;
         }
-        pr = __ddiv_rn(x, piv);
+        pr = ddiv(x, piv);
         z = __dsub_rn(r0j, __dmul_rn(f0, pr));
         if (j < C - 1 && z < 0.0) m = MinIdx{z, j};
       }
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) k_blk_select2(BlkView b, int group_pos, R
     }
     m = block_minidx(m, sm);
     // RHS mirror for this CTA's rows: new = (i == p) ? prow[C-1] : rhs[i] - f_i * prow[C-1]
-    const double prc = __ddiv_rn(rhsp, piv);
+    const double prc = ddiv(rhsp, piv);
     if (rpc <= 256 * UR) {
 #pragma unroll
       for (int q = 0; q < UR; q++) {
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
     double best_a = 0.0;
     auto ratio_cand = [&](int i, double col, double rv) {
       if (i >= 1 && col > 1e-9) {
-        const double val = __ddiv_rn(rv, col);
+        const double val = ddiv(rv, col);
         if (val >= 0.0 && val < DBL_MAX) {
           MinIdx nb = minidx_combine(best, MinIdx{val, i - 1});
           if (nb.i != best.i) best_a = col;
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
           const double upd = (p == s_pu[u]) ? pru[u] : __dsub_rn(x, __dmul_rn(s_fp[u], pru[u]));
           x = (u < s) ? upd : x;
         }
-        pr = __ddiv_rn(x, piv);
+        pr = ddiv(x, piv);
         z = __dsub_rn(r0j, __dmul_rn(f0, pr));
         if (j < C - 1 && z < 0.0) m = minidx_combine(m, MinIdx{z, j});
       }
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(NT) k_blk_select_cluster(BlkView b, int K) {
       finish_col(j, (j < C) ? TAT(T, ld, p, j) : 0.0, (j < C) ? b.row0[j] : 0.0, pru);
     }
     {
-      const double prc = __ddiv_rn(rhsp, piv);
+      const double prc = ddiv(rhsp, piv);
       if (own_row) rhs_next[gid] = (gid == p) ? prc : __dsub_rn(rv0, __dmul_rn(col0, prc));
       for (int i = gid + nthr; i < R; i += nthr)
         rhs_next[i] = (i == p) ? prc : __dsub_rn(rhs[i], __dmul_rn(b.F[(size_t)i * KM + s], prc));

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
         sFc[s * PRT + tid] = col;
         // FindLeavingVariable :169-191
         if (col > 1e-9) {
-          const double val = __ddiv_rn(rv, col);
+          const double val = ddiv(rv, col);
           if (val >= 0.0 && val < DBL_MAX) {
             key = (val == 0.0) ? 0ull : (unsigned long long)__double_as_longlong(val);
             idx = i - 1;
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
             xx = (p == s_pu[PK + u]) ? pv : __dsub_rn(xx, __dmul_rn(s_fp[PK + u], pv));
           }
         }
-        const double pr = __ddiv_rn(xx, piv);                  // :197-199
+        const double pr = ddiv(xx, piv);                  // :197-199
         const double z = __dsub_rn(r0[c], __dmul_rn(f0, pr));  // :206-208 on the objective row
         if (z < 0.0) {
           const unsigned long long kb = ~(unsigned long long)__double_as_longlong(z);
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(NT, 1) k_pipe_select3(PipeArgs a) {
         r0[c] = z;
       }
     }
-    const double prc = __ddiv_rn(rhsp, piv);  // normalised pivot row at the RHS column
+    const double prc = ddiv(rhsp, piv);  // normalised pivot row at the RHS column
     if (own_row) {
       rv = (i == p) ? prc : __dsub_rn(rv, __dmul_rn(col, prc));
       hit_row |= (i == p);
