@@ -78,6 +78,8 @@ __device__ int block_hyst_min(int n, Cand cand, double b0, double eps, MinIdx* s
 // cycles per scheduler at 1024 threads, which made the all-threads form slower than the replay it replaced.
 // All threads of the block must call it; blockDim.x >= kScanThreads.
 constexpr int kScanThreads = 256;
+// minimum of two non-NaN doubles: fmin() costs ten instructions for its NaN rules, this is a compare and two selects
+__device__ __forceinline__ double dmin(double x, double y) { return y < x ? y : x; }
 __device__ __forceinline__ void scan_threads_barrier() {  // named barrier 1: the scanning warps only
   asm volatile("bar.sync 1, %0;" ::"n"(kScanThreads) : "memory");
 }
@@ -107,12 +109,12 @@ __device__ int hyst_min_scan_threads(int n, Cand cand, double b0, double eps) {
       double t;
       if (j < per && k0 + j < n && cand(k0 + j, t) && t == t) v[j] = t;
     }
-    double lm = fmin(fmin(fmin(v[0], v[1]), fmin(v[2], v[3])), fmin(fmin(v[4], v[5]), fmin(v[6], v[7])));
+    double lm = dmin(dmin(dmin(v[0], v[1]), dmin(v[2], v[3])), dmin(dmin(v[4], v[5]), dmin(v[6], v[7])));
     double inc = lm;  // inclusive prefix minimum over the threads of the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double t = __shfl_up_sync(kFull, inc, o);
-      if (lane >= o) inc = fmin(inc, t);
+      if (lane >= o) inc = dmin(inc, t);
     }
     double m = __shfl_up_sync(kFull, inc, 1);  // minimum of the valid values before k0 (inside the warp so far)
     if (lane == 0) m = kPosInf;
@@ -121,14 +123,14 @@ __device__ int hyst_min_scan_threads(int n, Cand cand, double b0, double eps) {
 #pragma unroll
     for (int w = 0; w < kScanThreads / 32 - 1; w++) {
       const double t = s_tot[w];
-      if (w < warp) m = fmin(m, t);
+      if (w < warp) m = dmin(m, t);
     }
 #pragma unroll
-    for (int j = 0; j < kRegs; j++) {  // only m = fmin(m, v) is a dependent chain; the thresholds hang off it
+    for (int j = 0; j < kRegs; j++) {  // only m = dmin(m, v) is a dependent chain; the thresholds hang off it
       const double mk = m;
-      m = fmin(m, v[j]);
-      const bool sure = v[j] < __dsub_rn(fmin(b0, mk), eps);
-      const bool unsure = !sure && v[j] < fmin(q0, mk);
+      m = dmin(m, v[j]);
+      const bool sure = v[j] < __dsub_rn(dmin(b0, mk), eps);
+      const bool unsure = !sure && v[j] < dmin(q0, mk);
       if (sure) last_sure = k0 + j;
       if (unsure) {
         first_unsure = min(first_unsure, k0 + j);
@@ -139,20 +141,20 @@ __device__ int hyst_min_scan_threads(int n, Cand cand, double b0, double eps) {
     double lm = kPosInf;
     for (int k = k0; k < k1; k++) {
       double v;
-      if (cand(k, v) && v == v) lm = fmin(lm, v);
+      if (cand(k, v) && v == v) lm = dmin(lm, v);
     }
     double inc = lm;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double t = __shfl_up_sync(kFull, inc, o);
-      if (lane >= o) inc = fmin(inc, t);
+      if (lane >= o) inc = dmin(inc, t);
     }
     double m = __shfl_up_sync(kFull, inc, 1);
     if (lane == 0) m = kPosInf;
     if (lane == 31) s_tot[warp] = inc;
     scan_threads_barrier();
-    for (int w = 0; w < warp; w++) m = fmin(m, s_tot[w]);
-    double sure_below = __dsub_rn(fmin(b0, m), eps), unsure_below = fmin(q0, m);
+    for (int w = 0; w < warp; w++) m = dmin(m, s_tot[w]);
+    double sure_below = __dsub_rn(dmin(b0, m), eps), unsure_below = dmin(q0, m);
     for (int k = k0; k < k1; k++) {
       double v;
       if (!(cand(k, v) && v == v)) continue;
@@ -164,8 +166,8 @@ __device__ int hyst_min_scan_threads(int n, Cand cand, double b0, double eps) {
       }
       if (v < m) {
         m = v;
-        sure_below = __dsub_rn(fmin(b0, m), eps);
-        unsure_below = fmin(q0, m);
+        sure_below = __dsub_rn(dmin(b0, m), eps);
+        unsure_below = dmin(q0, m);
       }
     }
   }
