@@ -31,6 +31,8 @@
 #include <numeric>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lpr {
@@ -115,7 +117,88 @@ __device__ __forceinline__ bool knap_cand_ahead(const uint64_t* pool, size_t rec
   return knap_key_order(ra + 2 * (size_t)W, (int)ra[3 * (size_t)W], rb + 2 * (size_t)W, (int)rb[3 * (size_t)W]) < 0;
 }
 
-// one thread per node: a walk from the parent's critical item (see the header), then the CTA's best candidate
+// relaxation of one node: a walk from the parent's critical item (see the header)
+__device__ __forceinline__ KnapEval knap_eval_node(const uint64_t* __restrict__ rec, int W, int n,
+                                                   const double* __restrict__ w, const double* __restrict__ v) {
+  const uint64_t st = rec[3 * (size_t)W + 1];
+  const int k = (int)(uint32_t)st, side = (int)(st >> 32);
+  double cap = __longlong_as_double((long long)rec[3 * (size_t)W + 2]);
+  double val = __longlong_as_double((long long)rec[3 * (size_t)W + 3]);
+  // free (not yet branched on) positions are found a 64-bit word of the fix mask at a time: deep nodes have hundreds of
+  // fixed items around their critical item, and testing them one by one was most of the walk
+  auto prev_free = [&](int p) {  // highest free position <= p, -1 if none
+    if (p < 0) return -1;
+    int wi = p >> 6;
+    uint64_t m = ~rec[wi] & (((p & 63) == 63) ? ~0ull : ((2ull << (p & 63)) - 1ull));
+    while (true) {
+      if (m) return wi * 64 + 63 - __clzll((long long)m);
+      if (--wi < 0) return -1;
+      m = ~rec[wi];
+    }
+  };
+  auto next_free = [&](int p) {  // lowest free position >= p, n if none
+    if (p >= n) return n;
+    int wi = p >> 6;
+    uint64_t m = ~rec[wi] & (~0ull << (p & 63));
+    while (true) {
+      if (m) {
+        const int q = wi * 64 + __ffsll((long long)m) - 1;
+        return q < n ? q : n;
+      }
+      if (++wi >= W) return n;
+      m = ~rec[wi];
+    }
+  };
+  int crit = -1;
+  bool infeasible = k < 0 && cap < 0.0;  // negative capacity at the root
+  if (infeasible) {
+  } else if (side == 1 && k >= 0) {
+    cap = __dsub_rn(cap, w[k]);  // < 0: k did not fit in the parent
+    val = __dadd_rn(val, v[k]);
+    int p = prev_free(k - 1);
+    while (p >= 0) {
+      cap = __dadd_rn(cap, w[p]);
+      val = __dsub_rn(val, v[p]);
+      if (cap >= 0.0) break;
+      p = prev_free(p - 1);
+    }
+    if (p < 0) infeasible = true;  // the fixed-1 items alone exceed the capacity
+    crit = p;
+  } else {
+    int p = next_free(k + 1);  // k = -1 for the root
+    while (p < n) {
+      const double wp = w[p];
+      if (wp <= cap) {
+        cap = __dsub_rn(cap, wp);
+        val = __dadd_rn(val, v[p]);
+        p = next_free(p + 1);
+      } else {
+        crit = p;
+        break;
+      }
+    }
+  }
+  KnapEval ev;
+  ev.cap = cap;
+  ev.base = val;
+  ev.crit = crit;
+  if (infeasible) {
+    ev.val = 0.0;
+    ev.crit = -1;
+    ev.type = 0;
+  } else if (crit < 0 || cap == 0.0) {
+    ev.val = val;
+    ev.type = 1;
+  } else {
+    ev.val = __dadd_rn(val, __dmul_rn(v[crit], __ddiv_rn(cap, w[crit])));
+    ev.type = 2;
+  }
+  ev.cmp = kCmpNone;
+  ev.pad = 0;
+  return ev;
+}
+
+// one thread per node, then the CTA's best candidate
 __global__ void __launch_bounds__(kEvT) k_knap_eval(const KnapCtl* __restrict__ ctl, const uint64_t* __restrict__ pool,
                                                     size_t rec_words, int W, int n, const double* __restrict__ w,
                                                     const double* __restrict__ v, KnapEval* __restrict__ out,
@@ -128,57 +211,7 @@ __global__ void __launch_bounds__(kEvT) k_knap_eval(const KnapCtl* __restrict__ 
   double cval = 0.0;
   int cidx = -1;
   if (node < nb) {
-    const uint64_t* rec = pool + (size_t)(first + node) * rec_words;
-    const uint64_t st = rec[3 * (size_t)W + 1];
-    const int k = (int)(uint32_t)st, side = (int)(st >> 32);
-    double cap = __longlong_as_double((long long)rec[3 * (size_t)W + 2]);
-    double val = __longlong_as_double((long long)rec[3 * (size_t)W + 3]);
-    auto fixed = [&](int p) { return (rec[p >> 6] >> (p & 63)) & 1ull; };
-    int crit = -1;
-    bool infeasible = k < 0 && cap < 0.0;  // negative capacity at the root
-    if (infeasible) {
-    } else if (side == 1 && k >= 0) {
-      cap = __dsub_rn(cap, w[k]);  // < 0: k did not fit in the parent
-      val = __dadd_rn(val, v[k]);
-      int p = k - 1;
-      for (; p >= 0; p--) {
-        if (fixed(p)) continue;
-        cap = __dadd_rn(cap, w[p]);
-        val = __dsub_rn(val, v[p]);
-        if (cap >= 0.0) break;
-      }
-      if (p < 0) infeasible = true;  // the fixed-1 items alone exceed the capacity
-      crit = p;
-    } else {
-      for (int p = k + 1; p < n; p++) {  // k = -1 for the root
-        if (fixed(p)) continue;
-        const double wp = w[p];
-        if (wp <= cap) {
-          cap = __dsub_rn(cap, wp);
-          val = __dadd_rn(val, v[p]);
-        } else {
-          crit = p;
-          break;
-        }
-      }
-    }
-    KnapEval ev;
-    ev.cap = cap;
-    ev.base = val;
-    ev.crit = crit;
-    if (infeasible) {
-      ev.val = 0.0;
-      ev.crit = -1;
-      ev.type = 0;
-    } else if (crit < 0 || cap == 0.0) {
-      ev.val = val;
-      ev.type = 1;
-    } else {
-      ev.val = __dadd_rn(val, __dmul_rn(v[crit], __ddiv_rn(cap, w[crit])));
-      ev.type = 2;
-    }
-    ev.cmp = kCmpNone;
-    ev.pad = 0;
+    const KnapEval ev = knap_eval_node(pool + (size_t)(first + node) * rec_words, W, n, w, v);
     out[node] = ev;
     if (ev.type == 1) {
       cval = ev.val;
@@ -410,8 +443,45 @@ __global__ void __launch_bounds__(128) k_knap_gather(const KnapCtl* __restrict__
   }
 }
 
+// both children of one surviving node (its record at src): the x_k = 1 child below the x_k = 0 child (the zero child is
+// DFS-first), each carrying the parent's fill state at its critical item k.  All 32 lanes of a warp.
+__device__ __forceinline__ void knap_child_words(int t, uint64_t x, int W, int k, int depth, double cap, double base,
+                                                 uint64_t& x0, uint64_t& x1) {
+  x0 = x1 = x;
+  const int word = t % W, sect = t / W;
+  if (t < 3 * W) {
+    if (sect == 0 && word == (k >> 6)) {  // fixmask: mark k fixed
+      x0 |= 1ull << (k & 63);
+      x1 |= 1ull << (k & 63);
+    } else if (sect == 1 && word == (k >> 6)) {  // fixval
+      x1 |= 1ull << (k & 63);
+    } else if (sect == 2 && word == (depth >> 6)) {  // key: append the branch bit
+      x1 |= 1ull << (depth & 63);
+    }
+  } else if (t == 3 * W) {
+    x0 = x1 = (uint64_t)(depth + 1);
+  } else if (t == 3 * W + 1) {
+    x0 = knap_pack_state(k, 0);
+    x1 = knap_pack_state(k, 1);
+  } else if (t == 3 * W + 2) {
+    x0 = x1 = (uint64_t)__double_as_longlong(cap);
+  } else {
+    x0 = x1 = (uint64_t)__double_as_longlong(base);
+  }
+}
+__device__ __forceinline__ void knap_write_children(int lane, const uint64_t* __restrict__ src, uint64_t* one, uint64_t* zero,
+                                                    int rec_words, int W, int k, double cap, double base) {
+  const int depth = (int)src[3 * (size_t)W];
+  for (int t = lane; t < rec_words; t += 32) {
+    uint64_t x0, x1;
+    knap_child_words(t, src[t], W, k, depth, cap, base, x0, x1);
+    zero[t] = x0;
+    one[t] = x1;
+  }
+}
+
 // children of surviving nodes: job = index among the survivors (its parent record sits in stage[job]); two records
-// per job, each carrying the parent's fill state at its critical item.  One warp per job.
+// per job.  One warp per job.
 __global__ void __launch_bounds__(128) k_knap_expand(const KnapCtl* __restrict__ ctl, uint64_t* pool, size_t rec_words,
                                                      int W, const long long* __restrict__ parent,
                                                      const KnapEval* __restrict__ evals,
@@ -421,38 +491,10 @@ __global__ void __launch_bounds__(128) k_knap_expand(const KnapCtl* __restrict__
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int job = warp; job < nj; job += nwarps) {
-    const uint64_t* src = stage + (size_t)job * rec_words;
     const KnapEval ev = evals[parent[job]];
-    const int depth = (int)src[3 * (size_t)W];
-    const int k = ev.crit;
-    // stack order: the x_k = 1 child below the x_k = 0 child (the zero child is DFS-first)
     uint64_t* one = pool + (size_t)(dst_first + 2 * (long long)job) * rec_words;
-    uint64_t* zero = one + rec_words;
-    for (int t = lane; t < (int)rec_words; t += 32) {
-      uint64_t x = src[t], x1 = x, x0 = x;
-      const int word = t % W, sect = t / W;
-      if (t < 3 * W) {
-        if (sect == 0 && word == (k >> 6)) {  // fixmask: mark k fixed
-          x0 |= 1ull << (k & 63);
-          x1 |= 1ull << (k & 63);
-        } else if (sect == 1 && word == (k >> 6)) {  // fixval
-          x1 |= 1ull << (k & 63);
-        } else if (sect == 2 && word == (depth >> 6)) {  // key: append the branch bit
-          x1 |= 1ull << (depth & 63);
-        }
-      } else if (t == 3 * W) {
-        x0 = x1 = (uint64_t)(depth + 1);
-      } else if (t == 3 * W + 1) {
-        x0 = knap_pack_state(k, 0);
-        x1 = knap_pack_state(k, 1);
-      } else if (t == 3 * W + 2) {
-        x0 = x1 = (uint64_t)__double_as_longlong(ev.cap);
-      } else {
-        x0 = x1 = (uint64_t)__double_as_longlong(ev.base);
-      }
-      zero[t] = x0;
-      one[t] = x1;
-    }
+    knap_write_children(lane, stage + (size_t)job * rec_words, one, one + rec_words, (int)rec_words, W, ev.crit, ev.cap,
+                        ev.base);
   }
 }
 
@@ -490,6 +532,289 @@ __global__ void k_knap_set_inc(KnapCtl* ctl, double val, int bits) {
   ctl->inc_version++;
 }
 
+
+// ---- narrow levels: one thread-block cluster walks them without kernel boundaries ---------------------------------
+// A level of the six-kernel pipeline costs ~45 us whatever its width (six dependent launches); the tree of cfg4
+// (n = 10^4) has ~540 open nodes per level, so it ran at the speed of the launches.  While the WHOLE stack fits one
+// thread per node of a cluster (16 CTAs x 256 threads, 8 x 256 where 16 is not available), this kernel loops over
+// levels on its own: evaluation -> best candidate of every CTA into every CTA's shared memory (DSMEM) -> incumbent ->
+// survivor ballots, CTA counts through DSMEM, prefix -> survivors to the staging area -> children, with a hardware
+// cluster barrier where the pipeline has a kernel boundary.  Same stack discipline, same order, same incumbent
+// rule as the pipeline, which takes over (same control block) as soon as a level outgrows the cluster, the node
+// budget would cut a level, or max_levels is reached.
+namespace cg = cooperative_groups;
+constexpr int kNarrowT = 256;
+constexpr int kNarrowMaxCtas = 16;
+struct KnapCandN {
+  double val;
+  int idx;   // node index in the stack, -1 = none
+  int crit;  // its critical item (-1 for a candidate that used every item)
+};
+
+__global__ void __launch_bounds__(kNarrowT, 1)
+k_knap_narrow(KnapCtl* ctl, uint64_t* pool, size_t rec_words, int W, int n_items, const double* __restrict__ w,
+              const double* __restrict__ v, uint64_t* stage, uint64_t* inc_key, uint64_t* inc_rec, int max_levels,
+              unsigned long long* prof) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int ncta = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  const int cap_nodes = ncta * kNarrowT;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = kNarrowT / 32;
+  __shared__ KnapCandN s_cand[kNarrowMaxCtas];  // written by every CTA of the cluster (slot = its rank)
+  __shared__ int s_cnt[kNarrowMaxCtas];         // survivors per CTA, likewise
+  __shared__ KnapCandN s_wc[NW];
+  __shared__ int s_wcnt[NW];
+  // the copy jobs (survivors) are dealt evenly to the CTAs, whatever CTA evaluated them: written through DSMEM by the
+  // evaluating thread, slot = job - first job of the target CTA
+  __shared__ int s_jnode[kNarrowT];     // stack position of the survivor
+  __shared__ int s_jcrit[kNarrowT];     // its critical item and the fill state there (what the children inherit)
+  __shared__ double s_jcap[kNarrowT], s_jbase[kNarrowT];
+  __shared__ int s_depth[kNarrowT];     // its depth (read off the record while it is copied)
+
+  // entry: the whole stack must be the next batch (uniform over the cluster: nobody has written the block yet)
+  if (ctl->stop || ctl->error) return;
+  long long open = ctl->open;
+  if (open <= 0 || open > cap_nodes || ctl->ev_first != 0 || ctl->ev_nb != open) return;
+  long long processed = ctl->processed;
+  const long long max_nodes = ctl->max_nodes, pool_cap = ctl->pool_cap;
+  const int batch = ctl->batch;
+  int has_inc = ctl->has_inc, inc_bits = ctl->inc_bits, inc_crit = ctl->inc_crit, inc_version = ctl->inc_version;
+  double inc_val = ctl->inc_val;
+  int levels = 0, error = 0;
+  cluster.sync();  // everybody has read the block before CTA 0 may leave and rewrite it
+
+  auto ahead = [&](double va, int a, double vb, int b) { return knap_cand_ahead(pool, rec_words, W, 0, va, a, vb, b); };
+  long long t_last = prof ? clock64() : 0;  // LPR_KNAP_PROFILE=1: clocks of CTA 0 per section
+  auto stamp = [&](int slot) {
+    if (prof && crank == 0 && tid == 0) {
+      const long long t = clock64();
+      prof[slot] += (unsigned long long)(t - t_last);
+      t_last = t;
+    }
+  };
+
+  while (true) {
+    const int n = (int)open;
+    const int node = crank * kNarrowT + tid;
+    // ---- relaxation, best candidate of the CTA --------------------------------------------------------------------
+    KnapEval ev;
+    ev.type = 0;
+    ev.val = 0.0;
+    ev.crit = -1;
+    const uint64_t* rec = pool + (size_t)node * rec_words;
+    if (node < n) ev = knap_eval_node(rec, W, n_items, w, v);
+    stamp(0);
+    double cval = ev.type == 1 ? ev.val : 0.0;
+    int cidx = (node < n && ev.type == 1) ? node : -1;
+    int ccrit = ev.crit;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, cval, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, cidx, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, ccrit, o);
+      if (ahead(ov, oi, cval, cidx)) {
+        cval = ov;
+        cidx = oi;
+        ccrit = oc;
+      }
+    }
+    if (lane == 0) {
+      s_wc[wid].val = cval;
+      s_wc[wid].idx = cidx;
+      s_wc[wid].crit = ccrit;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      KnapCandN c;
+      c.val = 0.0;
+      c.idx = -1;
+      c.crit = -1;
+      if (lane < NW) c = s_wc[lane];
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, c.val, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, c.idx, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, c.crit, o);
+        if (ahead(ov, oi, c.val, c.idx)) {
+          c.val = ov;
+          c.idx = oi;
+          c.crit = oc;
+        }
+      }
+      if (lane < ncta) cluster.map_shared_rank(s_cand, lane)[crank] = c;
+    }
+    stamp(1);
+    cluster.sync();
+    stamp(2);
+    // ---- incumbent (k_knap_inc's rule), evaluated by every warp from the same slots -------------------------------
+    {
+      KnapCandN c;
+      c.val = 0.0;
+      c.idx = -1;
+      c.crit = -1;
+      if (lane < ncta) c = s_cand[lane];
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, c.val, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, c.idx, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, c.crit, o);
+        if (ahead(ov, oi, c.val, c.idx)) {
+          c.val = ov;
+          c.idx = oi;
+          c.crit = oc;
+        }
+      }
+      bool upd = false;
+      if (c.idx >= 0) {
+        const uint64_t* rb = pool + (size_t)c.idx * rec_words;
+        upd = !has_inc || c.val > inc_val ||
+              (c.val == inc_val && knap_key_order(rb + 2 * (size_t)W, (int)rb[3 * (size_t)W], inc_key, inc_bits) < 0);
+      }
+      if (upd) {  // uniform over the cluster
+        const uint64_t* src = pool + (size_t)c.idx * rec_words;
+        const int bits = (int)src[3 * (size_t)W];
+        cluster.sync();  // every warp of every CTA has compared against the OLD key
+        if (crank == 0) {
+          for (int t = tid; t < (int)rec_words; t += kNarrowT) inc_rec[t] = src[t];
+          for (int t = tid; t < W; t += kNarrowT) inc_key[t] = src[2 * (size_t)W + t];
+        }
+        has_inc = 1;
+        inc_val = c.val;
+        inc_bits = bits;
+        inc_crit = c.crit;
+        inc_version++;
+        cluster.sync();  // the new key is in place before the survivor test reads it
+      }
+    }
+    // ---- survivors (k_knap_flag's rule), counts of all CTAs, prefix ----------------------------------------------------
+    bool keep = false;
+    if (node < n && ev.type == 2) {
+      if (!has_inc || ev.val > inc_val) keep = true;
+      else if (ev.val == inc_val)
+        keep = knap_key_order(rec + 2 * (size_t)W, (int)rec[3 * (size_t)W], inc_key, inc_bits) <= 0;
+    }
+    stamp(3);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_wcnt[wid] = __popc(m);
+    __syncthreads();
+    int before = 0, mine = 0;  // survivors of this CTA before my warp / in all of it
+#pragma unroll
+    for (int q = 0; q < NW; q++) {
+      const int c = s_wcnt[q];
+      if (q < wid) before += c;
+      mine += c;
+    }
+    if (tid < ncta) cluster.map_shared_rank(s_cnt, tid)[crank] = mine;
+    cluster.sync();
+    stamp(4);
+    int base = 0, nj = 0;
+    for (int q = 0; q < ncta; q++) {
+      const int c = s_cnt[q];
+      if (q < crank) base += c;
+      nj += c;
+    }
+    if (2LL * nj > pool_cap) {  // cannot happen below cap_nodes, kept for symmetry with k_knap_scan
+      error = 1;
+      break;
+    }
+    // survivors -> copy jobs: job = rank of the survivor in stack order, per jobs to every CTA
+    const int per = (nj + ncta - 1) / ncta;
+    if (keep) {
+      const int job = base + before + __popc(m & ((1u << lane) - 1u));
+      const int target = job / per, slot = job - target * per;
+      cluster.map_shared_rank(s_jnode, target)[slot] = node;
+      cluster.map_shared_rank(s_jcrit, target)[slot] = ev.crit;
+      cluster.map_shared_rank(s_jcap, target)[slot] = ev.cap;
+      cluster.map_shared_rank(s_jbase, target)[slot] = ev.base;
+    }
+    cluster.sync();
+    const int j0 = crank * per;                      // my first job
+    const int mine_jobs = max(0, min(per, nj - j0));  // and how many
+    // ---- surviving parents -> staging (their slots are about to be overwritten) ------------------------------------
+    // The CTA's survivors are consecutive jobs, so its share of the staging area is ONE flat array of mine x rec_words
+    // words: all threads walk it with eight independent loads in flight each (a warp per record, one load at a time,
+    // made a level cost more than the six launches it replaces).
+    constexpr int kU = 16;
+    const int rw = (int)rec_words;
+    const int total = mine_jobs * rw;
+    uint64_t* my_stage = stage + (size_t)j0 * rec_words;
+    for (int b0 = 0; b0 < total; b0 += kNarrowT * kU) {
+      uint64_t x[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int idx = b0 + u * kNarrowT + tid;
+        if (idx < total) {
+          const int r = idx / rw, t = idx - r * rw;
+          x[u] = pool[(size_t)s_jnode[r] * rec_words + t];
+          if (t == 3 * W) s_depth[r] = (int)x[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int idx = b0 + u * kNarrowT + tid;
+        if (idx < total) my_stage[idx] = x[u];
+      }
+    }
+    stamp(5);
+    cluster.sync();
+    stamp(6);
+    // ---- children --------------------------------------------------------------------------------------------------------
+    for (int b0 = 0; b0 < total; b0 += kNarrowT * kU) {
+      uint64_t x[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int idx = b0 + u * kNarrowT + tid;
+        if (idx < total) x[u] = my_stage[idx];
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int idx = b0 + u * kNarrowT + tid;
+        if (idx < total) {
+          const int r = idx / rw, t = idx - r * rw;
+          uint64_t x0, x1;
+          knap_child_words(t, x[u], W, s_jcrit[r], s_depth[r], s_jcap[r], s_jbase[r], x0, x1);
+          uint64_t* one = pool + (size_t)(2 * (long long)(j0 + r)) * rec_words;
+          one[t] = x1;
+          one[rec_words + t] = x0;
+        }
+      }
+    }
+    processed += n;
+    levels++;
+    open = 2LL * nj;
+    stamp(7);
+    cluster.sync();
+    stamp(8);  // children visible to every CTA; shared arrays free for the next level
+    if (open <= 0 || open > cap_nodes || levels >= max_levels) break;
+    if (open > batch) break;
+    if (max_nodes >= 0 && processed + open > max_nodes) break;  // the budget cuts the next level: the pipeline's job
+  }
+
+  if (crank == 0 && tid == 0) {  // the block as k_knap_scan leaves it
+    ctl->has_inc = has_inc;
+    ctl->inc_val = inc_val;
+    ctl->inc_bits = inc_bits;
+    ctl->inc_crit = inc_crit;
+    ctl->inc_version = inc_version;
+    ctl->ex_nj = 0;
+    ctl->ex_ncta = 0;
+    if (error) {
+      ctl->error = 1;
+      ctl->stop = 1;
+      ctl->ev_nb = 0;
+    } else {
+      ctl->open = open;
+      ctl->processed = processed;
+      ctl->levels += levels;
+      ctl->ex_first = open;
+      long long next = open < (long long)batch ? open : (long long)batch;
+      if (max_nodes >= 0) {
+        const long long left = max_nodes - processed;
+        if (left < next) next = left < 0 ? 0 : left;
+      }
+      ctl->ev_nb = (int)next;
+      ctl->ev_first = open - next;
+      if (next == 0) ctl->stop = 1;
+    }
+  }
+}
 
 // selection of a candidate node, in ORIGINAL item ids (warp per call)
 __global__ void k_knap_selection(const uint64_t* rec, int W, int n, double capacity, const double* w, int crit,
@@ -559,6 +884,8 @@ struct lpr_knap {
   long long* d_parent = nullptr;
   uint64_t* stage = nullptr;  // surviving parents of a level (children are written over the batch's slots)
   int batch = 0;
+  unsigned long long* d_nprof = nullptr;  // LPR_KNAP_PROFILE=1
+  int narrow_ctas = -1;  // cluster size of k_knap_narrow on this device: -1 not probed yet, 0 unavailable / switched off
   KnapCtl* d_ctl = nullptr;
   KnapCtl* h_ctl = nullptr;       // pinned copy, refreshed at every host synchronisation of lpr_knap_run
   uint64_t* d_inc_key = nullptr;  // incumbent key (device copy, read by k_knap_plan)
@@ -605,6 +932,60 @@ static int knap_refresh_incumbent(lpr_knap* h) {
   return LPR_OK;
 }
 
+// cluster size for k_knap_narrow: 16 CTAs where the device grants the non-portable size, else 8 (LPR_KNAP_NARROW=0: none)
+static int knap_narrow_probe() {
+  const char* e = getenv("LPR_KNAP_NARROW");
+  if (e && atoi(e) == 0) return 0;
+  for (int ncta : {kNarrowMaxCtas, 8}) {
+    if (ncta > 8 && cudaFuncSetAttribute(k_knap_narrow, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncta);
+    cfg.blockDim = dim3(kNarrowT);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_knap_narrow, &cfg) == cudaSuccess && n >= 1) return ncta;
+    cudaGetLastError();
+  }
+  return 0;
+}
+
+static int knap_launch_narrow(lpr_knap* h, int max_levels) {
+  if (h->narrow_ctas < 0) {
+    h->narrow_ctas = knap_narrow_probe();
+    if (h->narrow_ctas > 0 && getenv("LPR_KNAP_PROFILE")) {
+      LPR_CUDA(cudaMalloc(&h->d_nprof, 16 * sizeof(unsigned long long)));
+      LPR_CUDA(cudaMemset(h->d_nprof, 0, 16 * sizeof(unsigned long long)));
+    }
+  }
+  if (h->narrow_ctas == 0) return LPR_OK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(h->narrow_ctas);
+  cfg.blockDim = dim3(kNarrowT);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = h->narrow_ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t ce = cudaLaunchKernelEx(&cfg, k_knap_narrow, h->d_ctl, h->pool, h->rec_words, h->W, h->n,
+                                            (const double*)h->d_w, (const double*)h->d_v, h->stage, h->d_inc_key,
+                                            h->d_inc_rec, max_levels, h->d_nprof);
+  if (ce != cudaSuccess) return fail(LPR_E_CUDA, "knapsack cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  count_launch();
+  return LPR_OK;
+}
+
 extern "C" {
 
 int lpr_knap_destroy(lpr_knap* h) {
@@ -614,6 +995,14 @@ int lpr_knap_destroy(lpr_knap* h) {
     fprintf(stderr, "[lpr_knap] nodes=%lld levels=%lld host syncs=%lld incumbents=%lld | run %.4fs\n",
             (long long)h->processed, (long long)h->n_levels, (long long)h->n_syncs, (long long)h->n_incumbents, h->t_run);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->d_nprof) {
+    unsigned long long hp[16];
+    if (cudaMemcpy(hp, h->d_nprof, sizeof(hp), cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "[lpr_knap] k_knap_narrow clocks of CTA 0: eval %llu | CTA candidate %llu | barrier %llu | incumbent + "
+              "survivor test %llu | counts + barrier %llu | gather %llu | barrier %llu | children %llu | barrier %llu\n",
+              hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7], hp[8]);
+    cudaFree(h->d_nprof);
+  }
   cudaFree(h->d_w); cudaFree(h->d_v); cudaFree(h->d_rank); cudaFree(h->pool); cudaFree(h->d_eval);
   cudaFree(h->d_parent); cudaFree(h->stage); cudaFree(h->d_inc_key); cudaFree(h->d_inc_rec); cudaFree(h->d_chosen);
   cudaFree(h->d_cands); cudaFree(h->d_masks); cudaFree(h->d_counts);
@@ -731,7 +1120,11 @@ int lpr_knap_run_timed(lpr_knap* h, int64_t max_nodes, double max_seconds, int64
   k_knap_start<<<1, 1, 0, h->stream>>>(h->d_ctl, h->open, (long long)max_nodes, h->batch);
   LPR_LAUNCH_CHECK();
   int group = 4;
+  // narrow stacks are walked by one cluster without kernel boundaries (k_knap_narrow): it returns at once when the
+  // stack is wider than the cluster, and the pipeline below is a no-op once the device has stopped
+  const int narrow_levels = max_seconds > 0.0 ? 64 : 4096;
   while (true) {
+    if ((rc = knap_launch_narrow(h, narrow_levels))) return rc;
     for (int l = 0; l < group; l++) {
       k_knap_eval<<<g_eval, kEvT, 0, h->stream>>>(h->d_ctl, h->pool, h->rec_words, h->W, h->n, h->d_w, h->d_v, h->d_eval,
                                                    h->d_cands);
