@@ -541,7 +541,12 @@ def run_bb_legs(W, O, world, dev):
         cuts = {"error": repr(ex)}
     slices = int(os.environ.get("LPR_BENCH_BB_SLICES", "12"))
     slice_ms = float(os.environ.get("LPR_BENCH_BB_SLICE_MS", "10"))
-    out = W.bb_mgpu(final, n, world, max_rounds=slices, slice_seconds=slice_ms * 1e-3)
+    # the pools are driven by host threads: a neighbour's burst on the box's CPUs shows up as a slow run, so the
+    # measurement is repeated and the median run is the one reported (all of them are listed)
+    reps = [W.bb_mgpu(final, n, world, max_rounds=slices, slice_seconds=slice_ms * 1e-3)
+            for _ in range(int(os.environ.get("LPR_BENCH_BB_REPEATS", "3")))]
+    out = sorted(reps, key=lambda r: r["nodes_per_s"])[len(reps) // 2]
+    out["repeats_nodes_per_s"] = [r["nodes_per_s"] for r in reps]
     out.update(workload=f"cfg5 dense IP m={m} n={n} B&B simplex (root {final.shape[0]}x{final.shape[1]}), "
                         f"{slices} slices of {slice_ms:g} ms per GPU",
                lp_relaxation_pivots=lp["n_pivots"], lp_relaxation_ms=lp_ms, root_cuts=cuts,

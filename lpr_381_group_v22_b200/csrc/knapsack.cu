@@ -731,7 +731,7 @@ k_knap_narrow(KnapCtl* ctl, uint64_t* pool, size_t rec_words, int W, int n_items
     // The CTA's survivors are consecutive jobs, so its share of the staging area is ONE flat array of mine x rec_words
     // words: all threads walk it with eight independent loads in flight each (a warp per record, one load at a time,
     // made a level cost more than the six launches it replaces).
-    constexpr int kU = 16;
+    constexpr int kU = 8;
     const int rw = (int)rec_words;
     const int total = mine_jobs * rw;
     uint64_t* my_stage = stage + (size_t)j0 * rec_words;

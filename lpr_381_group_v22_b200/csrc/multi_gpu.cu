@@ -319,6 +319,7 @@ struct Config {
   int64_t max_nodes = -1;      // total node budget over all ranks, < 0 = none
   int64_t max_rounds = -1;     // < 0 = until the pools are empty
   double slice_seconds = 0.0;  // > 0: a round is a time slice
+  bool untimed_when_alone = false;  // one rank and no round limit: nobody to exchange with, run to the end in one go
   int64_t chunk_nodes = 4096;  // at most this many nodes per rank and round
   int64_t seed_nodes_per_rank = 8, low_water = 0;
   size_t stage_bytes = 256u << 20;
@@ -556,7 +557,8 @@ void rank_main(int rank, int world, int rpg, int device, Pool* pool, ncclComm_t 
       int64_t budget = cfg.chunk_nodes;
       if (share >= 0) budget = std::min<int64_t>(budget, std::max<int64_t>(0, share - processed));
       int64_t done = 0;
-      if (budget > 0) note(pool->run(budget, cfg.slice_seconds, &done));
+      const bool alone = world == 1 && cfg.untimed_when_alone && cfg.max_rounds < 0;
+      if (budget > 0) note(pool->run(budget, alone ? 0.0 : cfg.slice_seconds, &done));
       processed += done;
     }
     t_run += now_s() - tc;
@@ -714,6 +716,7 @@ int lpr_knap_solve_mgpu(int n_gpus, const int* devices, double capacity, int n, 
   cfg.max_nodes = max_nodes;
   cfg.max_rounds = max_rounds;
   cfg.slice_seconds = slice_seconds > 0.0 ? slice_seconds : 2e-3;
+  cfg.untimed_when_alone = true;
   cfg.chunk_nodes = 1LL << 40;
   cfg.seed_nodes_per_rank = 256;
   cfg.low_water = 4096;  // a rank that cannot fill a fraction of a batch is about to run dry: refill it early
