@@ -115,6 +115,34 @@ def test_cfg4_size_matches_oracle_and_dp():
     assert float(np.dot(ch, v)) == dp and float(np.dot(ch, w)) <= cap
 
 
+@pytest.mark.parametrize("seed,n,batch", [(21, 120, 0), (22, 600, 0), (23, 2000, 0), (24, 600, 512), (384, 10000, 0)])
+def test_cluster_kernel_and_pipeline_walk_the_same_tree(seed, n, batch, monkeypatch):
+    """k_knap_narrow (one thread-block cluster looping over narrow levels) and the six-kernel pipeline share the stack
+    discipline: same node count, same incumbent, same selection, whichever of them walks which levels (a small batch
+    makes them alternate); node budgets that cut a level go to the pipeline."""
+    from lpr_381_group_v22_b200.distributed import KnapPool
+    w, v, cap = O.gen_knapsack(seed, n)
+    if batch:
+        monkeypatch.setenv("LPR_KNAP_BATCH", str(batch))
+    got = {}
+    for narrow in ("1", "0"):
+        monkeypatch.setenv("LPR_KNAP_NARROW", narrow)
+        p = KnapPool(cap, w, v)
+        try:
+            nodes = p.run(777)  # a budget in the middle of a level
+            assert nodes == 777 or p.open_count() == 0
+            while p.open_count() > 0:
+                nodes += p.run(1 << 40)
+            inc = p.get_incumbent()
+            got[narrow] = (nodes, inc[0], inc[2].astype(np.uint8).tolist())
+        finally:
+            p.close()
+    assert got["1"] == got["0"]
+    if n <= 2000:
+        ref = O.knap_bb(cap, w, v)
+        assert got["1"][1] == ref["best"] and got["1"][2] == ref["chosen"].tolist()
+
+
 @pytest.mark.parametrize("n_gpus", [1, 2, 4])
 def test_knap_solve_mgpu_in_library(n_gpus):
     """lpr_knap_solve_mgpu (host threads + NCCL inside the library): value and selection are the oracle's for any
