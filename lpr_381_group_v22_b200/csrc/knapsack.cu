@@ -595,13 +595,16 @@ k_knap_narrow(KnapCtl* ctl, uint64_t* pool, size_t rec_words, int W, int n_items
 
   while (true) {
     const int n = (int)open;
-    const int node = crank * kNarrowT + tid;
+    // the stack is dealt to the CTAs in contiguous blocks of B nodes (stack order = CTA-major order), B as small as the
+    // level allows: 540 nodes are 16 x 64 threads walking, not 3 x 256 on three SMs
+    const int B = min(kNarrowT, max(32, (((n + ncta - 1) / ncta) + 31) & ~31));
+    const int node = tid < B ? crank * B + tid : n;
     // ---- relaxation, best candidate of the CTA --------------------------------------------------------------------
     KnapEval ev;
     ev.type = 0;
     ev.val = 0.0;
     ev.crit = -1;
-    const uint64_t* rec = pool + (size_t)node * rec_words;
+    const uint64_t* rec = pool + (size_t)min(node, n) * rec_words;  // (only dereferenced when node < n)
     if (node < n) ev = knap_eval_node(rec, W, n_items, w, v);
     stamp(0);
     double cval = ev.type == 1 ? ev.val : 0.0;
