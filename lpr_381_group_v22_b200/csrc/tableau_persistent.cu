@@ -556,7 +556,8 @@ int tab_run_persistent(lpr_tab* h, int program, int64_t max_pivots, int print_st
   void (*kfn)(PersistArgs) = want_prof ? k_persist<true> : k_persist<false>;
   size_t smem = 3 * (size_t)a.vec_cap * sizeof(double);
   a.xrows = 0;
-  if (smem + 4 * (size_t)h->ld * sizeof(double) <= 200u * 1024u) {
+  const char* xr = getenv("LPR_PERSIST_XROWS");  // 0: as for tableaux too wide for the row prefetch (read per call: tests)
+  if (!(xr && atoi(xr) == 0) && smem + 4 * (size_t)h->ld * sizeof(double) <= 200u * 1024u) {
     a.xrows = 4;
     smem += 4 * (size_t)h->ld * sizeof(double);
   }

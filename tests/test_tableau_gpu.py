@@ -572,12 +572,14 @@ def test_model_to_device_equals_list_constructor(tmp_path):
         assert np.array_equal(e.read().view(np.uint64), f.read().view(np.uint64))
 
 
-@pytest.mark.parametrize("persist", ["0", "1"])
+@pytest.mark.parametrize("persist", ["0", "1", "1-no-row-prefetch"])
 def test_generic_rules_persistent_and_two_kernel_paths_agree_with_oracle(persist, monkeypatch):
     """PrimalSimplexSolver2 / DualSimplexSolver / CuttingPlaneSolver loops run by default as ONE cooperative launch
     (tableau_persistent.cu: redundant selection per CTA, out-of-place update, one grid barrier per pivot);
     LPR_TAB_PERSIST=0 keeps the two-kernel path.  Both must match the oracle bit for bit on mid-size tableaux."""
-    monkeypatch.setenv("LPR_TAB_PERSIST", persist)
+    monkeypatch.setenv("LPR_TAB_PERSIST", persist[0])
+    if persist.endswith("no-row-prefetch"):  # the path of tableaux too wide for the shared-memory row prefetch
+        monkeypatch.setenv("LPR_PERSIST_XROWS", "0")
     rng = np.random.default_rng(77)
     for R, C in ((40, 100), (150, 333), (257, 700)):
         T = _random_tableau(rng, R, C)
