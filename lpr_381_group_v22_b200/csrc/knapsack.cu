@@ -554,7 +554,7 @@ struct KnapCandN {
 __global__ void __launch_bounds__(kNarrowT, 1)
 k_knap_narrow(KnapCtl* ctl, uint64_t* pool, size_t rec_words, int W, int n_items, const double* __restrict__ w,
               const double* __restrict__ v, uint64_t* stage, uint64_t* inc_key, uint64_t* inc_rec, int max_levels,
-              unsigned long long* prof) {
+              unsigned long long* prof, int wv_in_smem) {
   cg::cluster_group cluster = cg::this_cluster();
   const int ncta = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
   const int cap_nodes = ncta * kNarrowT;
@@ -575,6 +575,20 @@ k_knap_narrow(KnapCtl* ctl, uint64_t* pool, size_t rec_words, int W, int n_items
   if (ctl->stop || ctl->error) return;
   long long open = ctl->open;
   if (open <= 0 || open > cap_nodes || ctl->ev_first != 0 || ctl->ev_nb != open) return;
+  // weights and values on chip when they fit (2 x 80 KB at n = 10^4): every acquire of a cluster barrier empties L1, so
+  // the walk's w[p] / v[p] would otherwise be an L2 round trip each, level after level
+  extern __shared__ double s_wv[];
+  const double* wq = w;
+  const double* vq = v;
+  if (wv_in_smem) {
+    for (int t = tid; t < n_items; t += kNarrowT) {
+      s_wv[t] = w[t];
+      s_wv[n_items + t] = v[t];
+    }
+    wq = s_wv;
+    vq = s_wv + n_items;
+    __syncthreads();
+  }
   long long processed = ctl->processed;
   const long long max_nodes = ctl->max_nodes, pool_cap = ctl->pool_cap;
   const int batch = ctl->batch;
@@ -605,7 +619,7 @@ k_knap_narrow(KnapCtl* ctl, uint64_t* pool, size_t rec_words, int W, int n_items
     ev.val = 0.0;
     ev.crit = -1;
     const uint64_t* rec = pool + (size_t)min(node, n) * rec_words;  // (only dereferenced when node < n)
-    if (node < n) ev = knap_eval_node(rec, W, n_items, w, v);
+    if (node < n) ev = knap_eval_node(rec, W, n_items, wq, vq);
     stamp(0);
     double cval = ev.type == 1 ? ev.val : 0.0;
     int cidx = (node < n && ev.type == 1) ? node : -1;
@@ -936,9 +950,17 @@ static int knap_refresh_incumbent(lpr_knap* h) {
 }
 
 // cluster size for k_knap_narrow: 16 CTAs where the device grants the non-portable size, else 8 (LPR_KNAP_NARROW=0: none)
-static int knap_narrow_probe() {
+static size_t knap_narrow_smem(int n_items) {  // weights + values in shared memory when they fit beside the static arrays
+  const size_t bytes = 2 * (size_t)n_items * sizeof(double);
+  return bytes <= 200u * 1024u ? bytes : 0;
+}
+static int knap_narrow_probe(size_t smem) {
   const char* e = getenv("LPR_KNAP_NARROW");
   if (e && atoi(e) == 0) return 0;
+  if (smem && cudaFuncSetAttribute(k_knap_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
   for (int ncta : {kNarrowMaxCtas, 8}) {
     if (ncta > 8 && cudaFuncSetAttribute(k_knap_narrow, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
       cudaGetLastError();
@@ -947,6 +969,7 @@ static int knap_narrow_probe() {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta);
     cfg.blockDim = dim3(kNarrowT);
+    cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = ncta;
@@ -963,7 +986,7 @@ static int knap_narrow_probe() {
 
 static int knap_launch_narrow(lpr_knap* h, int max_levels) {
   if (h->narrow_ctas < 0) {
-    h->narrow_ctas = knap_narrow_probe();
+    h->narrow_ctas = knap_narrow_probe(knap_narrow_smem(h->n));
     if (h->narrow_ctas > 0 && getenv("LPR_KNAP_PROFILE")) {
       LPR_CUDA(cudaMalloc(&h->d_nprof, 16 * sizeof(unsigned long long)));
       LPR_CUDA(cudaMemset(h->d_nprof, 0, 16 * sizeof(unsigned long long)));
@@ -973,6 +996,7 @@ static int knap_launch_narrow(lpr_knap* h, int max_levels) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(h->narrow_ctas);
   cfg.blockDim = dim3(kNarrowT);
+  cfg.dynamicSmemBytes = knap_narrow_smem(h->n);
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -983,7 +1007,7 @@ static int knap_launch_narrow(lpr_knap* h, int max_levels) {
   cfg.numAttrs = 1;
   const cudaError_t ce = cudaLaunchKernelEx(&cfg, k_knap_narrow, h->d_ctl, h->pool, h->rec_words, h->W, h->n,
                                             (const double*)h->d_w, (const double*)h->d_v, h->stage, h->d_inc_key,
-                                            h->d_inc_rec, max_levels, h->d_nprof);
+                                            h->d_inc_rec, max_levels, h->d_nprof, cfg.dynamicSmemBytes ? 1 : 0);
   if (ce != cudaSuccess) return fail(LPR_E_CUDA, "knapsack cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   count_launch();
   return LPR_OK;
