@@ -1,0 +1,505 @@
+#!/usr/bin/env python
+"""Runs the REFERENCE'S OWN C# SOURCES (read from /root/reference, unmodified) on the reference's fixtures and on
+seeded random models, through the small C# interpreter under oracle/csharp/, and writes what the reference's
+classes returned to tests/golden/reference_run.json.
+
+Run in the build container only (the GPU box has no /root/reference and needs none: the JSON is committed):
+
+    python tests/golden/make_reference_run.py            # writes tests/golden/reference_run.json
+    python tests/golden/make_reference_run.py --check    # regenerates in memory and compares with the committed file
+
+What is executed (class -> entry points):
+    IO/InputFileParser.cs                      ReadInputFile on data/TextFile.txt, TextFile/textfile.txt, README model, edge texts
+    Simplex/PrimalSimplexSolver.cs             ctor, Solve, FinalZ, SolutionVector, BasicVariables, FinalTableau, IterationSnapshots
+    Simplex/PrimalSimplexSolver2.cs            ctor, Solve(maxIters, printSteps), GetRows(false), IterationSnapshots
+    Simplex/DualSimplex.cs                     DualSimplexSolver.Solve(objectiveRow, constraintRows, maxIters, printSteps)
+    IntegerProgramming/CuttingPlaneSolver.cs   CuttingPlaneSolution(objectiveRow, constraintRows)
+    Simplex/RevisedPrimalSimplexSolver.cs      ctor, Solve, FinalZ, SolutionVector, BasicVariables, IterationSnapshots, BInverse, xB
+    IntegerProgramming/BranchAndBoundAdapter.cs + BranchBoundSimplexSolver.cs
+                                               SolveFromPrimal(primal, enablePruning, isMin) and the console trace of
+                                               ExecuteBranchAndBound; DualSimplexSolverBB.FormulateTableau / DoDualSimplex
+    SensitivityAnalysis/SensitivityAnalyzer.cs ctor (RebuildBasicsFromTableau), AddNewConstraintNonInteractive, ResolveAll
+    Utilities/TableIterationFormater.cs, NumFormat.N3   (number formatting is the interpreter's restatement of the BCL)
+
+Doubles are stored as C99 hex strings (bit exact); inputs as decimal literals that round-trip.
+"""
+import hashlib
+import json
+import os
+import random
+import re
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+from csharp import CsException, Interpreter  # noqa: E402
+from csharp.csrun import CsList, from_cs, to_array, to_array2d, to_list  # noqa: E402
+
+REF = "/root/reference/LPR_381_Group_V22/"
+OUT = os.path.join(HERE, "reference_run.json")
+SOURCES = [
+    "IO/InputFileParser.cs", "Utilities/TableIterationFormater.cs", "Simplex/PrimalSimplexSolver.cs",
+    "Simplex/PrimalSimplexSolver2.cs", "Simplex/DualSimplex.cs", "IntegerProgramming/CuttingPlaneSolver.cs",
+    "Simplex/RevisedPrimalSimplexSolver.cs", "IntegerProgramming/BranchBoundSimplexSolver.cs",
+    "IntegerProgramming/BranchAndBoundAdapter.cs", "SensitivityAnalysis/SensitivityAnalyzer.cs",
+]
+
+
+def hx(v):
+    return float(v).hex()
+
+
+def hexes(vals):
+    return [hx(v) for v in vals]
+
+
+def mat(rows):
+    rows = [list(r) for r in rows]
+    return {"shape": [len(rows), len(rows[0]) if rows else 0], "hex": [hx(v) for r in rows for v in r]}
+
+
+def sha(text):
+    return hashlib.sha256(text.encode("utf-8")).hexdigest()
+
+
+def source_digest():
+    h = hashlib.sha256()
+    for s in SOURCES:
+        with open(REF + s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+class Runner:
+    def __init__(self):
+        self.it = Interpreter()
+        for s in SOURCES:
+            self.it.load_file(REF + s)
+
+    def constraints(self, cons):
+        it = self.it
+        return CsList([it.new("Constraint", to_list(co), rel, float(rhs)) for co, rel, rhs in cons], None)
+
+    @staticmethod
+    def rows_list(T):
+        return CsList([to_array(r) for r in T[1:]], None)
+
+    # ------------------------------------------------------------------ PrimalSimplexSolver
+    def primal(self, objective, cons, is_max=True, keep_text=False):
+        it = self.it
+        it.console.clear()
+        s = it.new("PrimalSimplexSolver", to_list(objective), self.constraints(cons), is_max)
+        n = len(objective)
+        initial = from_cs(s.f["tableau"])
+        it.call(s, "Solve")
+        text = it.console_text()
+        piv = []
+        for r, lab in re.findall(r"Iteration \d+: pivot @ constraint (\d+), column (\w+)", text):
+            piv.append([int(r), int(lab[1:]) - 1 if lab[0] == "x" else n + int(lab[1:]) - 1])
+        x = it.get(s, "SolutionVector")
+        snaps = from_cs(it.get(s, "IterationSnapshots"))
+        rec = {
+            "objective": list(objective), "constraints": [[list(co), rel, rhs] for co, rel, rhs in cons],
+            "is_max": is_max,
+            "status": "optimal" if "Optimal Solution Found!" in text else "unbounded",
+            "initial_tableau": mat(initial), "pivots": piv,
+            "final_z": hx(it.get(s, "FinalZ")), "x": hexes(from_cs(x)) if x is not None else None,
+            "basis": from_cs(it.get(s, "BasicVariables")),
+            "final_tableau": mat(from_cs(it.get(s, "FinalTableau"))),
+            "get_final_tableau": mat(from_cs(it.call(s, "GetFinalTableau"))),
+            "n_snapshots": len(snaps), "snapshots_sha256": sha("".join(snaps)),
+            "final_table_sha256": sha(it.get(s, "FinalTable")),
+        }
+        if keep_text:
+            rec["snapshots"] = snaps
+        return rec, s
+
+    # ------------------------------------------------------------------ PrimalSimplexSolver2 / DualSimplexSolver
+    def primal2(self, T, max_iters, print_steps):
+        it = self.it
+        it.console.clear()
+        s = it.new("PrimalSimplexSolver2", to_array(T[0]), self.rows_list(T))
+        ok = it.call(s, "Solve", max_iters, print_steps)
+        rows = it.call(s, "GetRows", False)
+        final = [from_cs(rows.vals[0])] + from_cs(rows.vals[1])
+        piv = [[int(r), int(c)] for r, c in re.findall(r"Before pivot \(iter \d+\) at row (\d+), col (\d+)",
+                                                       "".join(from_cs(it.get(s, "IterationSnapshots"))))]
+        snaps = from_cs(it.get(s, "IterationSnapshots"))
+        return {"tableau": mat(T), "max_iters": max_iters, "print_steps": print_steps, "returned": bool(ok),
+                "pivots": piv, "final_tableau": mat(final), "final_z": hx(it.get(s, "FinalZ")),
+                "n_snapshots": len(snaps), "snapshots_sha256": sha("".join(snaps))}
+
+    def dual(self, T, max_iters, print_steps):
+        it = self.it
+        it.console.clear()
+        obj = to_array(T[0])
+        rows = self.rows_list(T)
+        s = it.new("DualSimplexSolver")
+        err = None
+        try:
+            ok = it.call(s, "Solve", obj, rows, max_iters, print_steps)
+        except CsException as e:
+            ok, err = None, e.tname
+        text = it.console_text()
+        n = len(T[0]) - 1 - (len(T) - 1)
+        piv = []
+        for r, lab in re.findall(r"Iteration \d+: pivot @ constraint (\d+), column (\w+)", text):
+            piv.append([int(r), int(lab[1:]) - 1 if lab[0] == "x" else n + int(lab[1:]) - 1])
+        return {"tableau": mat(T), "max_iters": max_iters, "print_steps": print_steps,
+                "returned": ok, "exception": err, "printed_pivots": piv,
+                "final_tableau": mat([from_cs(obj)] + from_cs(rows))}
+
+    # ------------------------------------------------------------------ CuttingPlaneSolver
+    def cutting_plane(self, T):
+        it = self.it
+        it.console.clear()
+        obj = to_array(T[0])
+        rows = self.rows_list(T)
+        s = it.new("CuttingPlaneSolver")
+        it.call(s, "CuttingPlaneSolution", obj, rows)
+        text = it.console_text()
+        cuts = [[int(r), int(c)] for r, c in re.findall(r"Before pivot on cut: row (\d+), col (\d+)", text)]
+        last = [ln for ln in text.split("\r\n") if ln.strip()][-1]
+        return {"tableau": mat(T), "final_tableau": mat([from_cs(obj)] + from_cs(rows)),
+                "cut_pivots_1based": cuts, "last_console_line": last}
+
+    # ------------------------------------------------------------------ RevisedPrimalSimplexSolver
+    def revised(self, c, A, b, rels, is_min, keep_text=False):
+        it = self.it
+        it.console.clear()
+        cons = [(A[i], rels[i], b[i]) for i in range(len(A))]
+        s = it.new("RevisedPrimalSimplexSolver", to_list(c), self.constraints(cons), is_min)
+        err = None
+        try:
+            it.call(s, "Solve")
+        except CsException as e:
+            err = e.message
+        snaps = from_cs(it.get(s, "IterationSnapshots"))
+        entering = re.findall(r"Entering variable \(chosen pre-pivot\): (\w+)", "".join(snaps))
+        rec = {"c": list(c), "A": [list(r) for r in A], "b": list(b), "relations": list(rels), "is_min": is_min,
+               "exception": err, "n_iterations": len(entering), "entering_labels": entering,
+               "final_z": hx(it.get(s, "FinalZ")), "x": hexes(from_cs(it.get(s, "SolutionVector"))),
+               "basis": from_cs(it.get(s, "BasicVariables")), "binv": mat(from_cs(s.f["BInverse"])),
+               "xb": hexes(from_cs(s.f["xB"])), "n_snapshots": len(snaps), "snapshots_sha256": sha("".join(snaps))}
+        if keep_text:
+            rec["snapshots"] = snaps
+        return rec
+
+    # ------------------------------------------------------------------ B&B simplex
+    def bb(self, objective, cons, prune, is_min=False):
+        it = self.it
+        prec, p = self.primal(objective, cons, True)
+        it.console.clear()
+        res = it.call_static("BranchAndBoundAdapter", "SolveFromPrimal", p, prune, is_min)
+        text = it.console_text()
+        nodes = []
+        blocks = re.split(r"\n--- Processing branch ", text)
+        for blk in blocks[1:]:
+            m = re.match(r"(\S+) \(Depth (\d+)\) ---", blk)
+            br = re.search(r"Branching on x(\d+) = (\S+)", blk)
+            nodes.append({"label": m.group(1), "depth": int(m.group(2)),
+                          "pruned": bool(re.search(r"branch \S+ pruned", blk)),
+                          "branch_var": int(br.group(1)) - 1 if br else -1,
+                          "branch_value_text": br.group(2) if br else None,
+                          "integer": bool(re.search(r"branch \S+: Integer solution", blk)),
+                          "new_incumbent": bool(re.search(r"New optimal integer solution found", blk))})
+        x, z = from_cs(res.vals[0]), res.vals[1]
+        return {"objective": list(objective), "constraints": [[list(co), rel, rhs] for co, rel, rhs in cons],
+                "enable_pruning": prune, "is_min": is_min, "primal_status": prec["status"],
+                "root_tableau": prec["final_tableau"],
+                "n_vars": len(prec["x"]) if prec["x"] is not None else max(1, prec["final_tableau"]["shape"][1] - 1),
+                "x": hexes(x), "z": hx(z), "nodes": nodes,
+                "hit_node_cap": "Potential infinite loop detected" in text,
+                "console_sha256": sha(text)}
+
+    def bb_formulate(self, objective, rows, is_min):
+        """DualSimplexSolverBB.FormulateTableau / DoDualSimplex without a tableau override (RunBranchAndBound's path)"""
+        it = self.it
+        it.console.clear()
+        s = it.new("DualSimplexSolverBB")
+        cs_rows = CsList([to_list(r) for r in rows], None)
+        T = it.call(s, "FormulateTableau", to_list(objective), cs_rows)
+        rec = {"objective": list(objective), "rows": [list(r) for r in rows], "is_min": is_min,
+               "tableau": mat(from_cs(T)), "rows_after": [hexes(r) for r in from_cs(cs_rows)]}
+        s2 = it.new("DualSimplexSolverBB")
+        cs_rows2 = CsList([to_list(r) for r in rows], None)
+        res = it.call(s2, "DoDualSimplex", to_list(objective), cs_rows2, is_min)
+        tabs, dec, opt, pc, pr, hdr = res.vals
+        rec.update({"n_tableaux": len(tabs.items), "final_tableau": mat(from_cs(tabs.items[-1])),
+                    "optimal_value": hx(opt) if opt is not None else None,
+                    "pivot_cols": from_cs(pc) if pc is not None else None,
+                    "pivot_rows": from_cs(pr) if pr is not None else None})
+        return rec
+
+    # ------------------------------------------------------------------ SensitivityAnalyzer
+    def sensitivity(self, objective, cons, tech, rhs):
+        it = self.it
+        prec, p = self.primal(objective, cons, True)
+        it.console.clear()
+        s = it.new("SensitivityAnalyzer", it.get(p, "FinalTableau"), it.get(p, "SolutionVector"), it.get(p, "FinalZ"),
+                   it.get(p, "BasicVariables"))
+        rec = {"objective": list(objective), "constraints": [[list(co), rel, r] for co, rel, r in cons],
+               "tech": list(tech), "rhs": rhs, "final_tableau": prec["final_tableau"],
+               "basis_rebuilt": from_cs(s.f["basicVars"])}
+        err = None
+        try:
+            it.call(s, "AddNewConstraintNonInteractive", to_array(tech), float(rhs))
+        except CsException as e:
+            err = e.message
+        rec.update({"exception": err, "tableau_after": mat(from_cs(it.get(s, "CurrentTableau"))),
+                    "z_after": hx(it.get(s, "CurrentZ")), "x_after": hexes(from_cs(it.get(s, "CurrentSolutionVector"))),
+                    "basis_after": from_cs(s.f["basicVars"])})
+        return rec
+
+    def sensitivity_rhs(self, objective, cons, row, new_rhs_delta):
+        """what ChangeRHS does after reading its input: RHS column += delta * (slack column of the row), ResolveAll"""
+        it = self.it
+        prec, p = self.primal(objective, cons, True)
+        it.console.clear()
+        s = it.new("SensitivityAnalyzer", it.get(p, "FinalTableau"), it.get(p, "SolutionVector"), it.get(p, "FinalZ"),
+                   it.get(p, "BasicVariables"))
+        t = s.f["tableau"]
+        R, C = t.dims
+        slack = it.call(s, "SlackColForConstraint", row)
+        for i in range(R):
+            t.set([i, C - 1], t.get([i, C - 1]) + new_rhs_delta * t.get([i, slack]))
+        before = from_cs(t)
+        err = None
+        try:
+            it.call(s, "ResolveAll")
+        except CsException as e:
+            err = e.message
+        return {"objective": list(objective), "constraints": [[list(co), rel, r] for co, rel, r in cons],
+                "tableau_before_resolve": mat(before), "exception": err,
+                "tableau_after": mat(from_cs(it.get(s, "CurrentTableau"))), "z_after": hx(it.get(s, "CurrentZ")),
+                "x_after": hexes(from_cs(it.get(s, "CurrentSolutionVector"))), "basis_after": from_cs(s.f["basicVars"])}
+
+    # ------------------------------------------------------------------ parser / formatting
+    def parse(self, text):
+        it = self.it
+        it.console.clear()
+        it.files["model.txt"] = text
+        p = it.new("InputFileParser")
+        err = None
+        try:
+            it.call(p, "ReadInputFile", "model.txt")
+        except CsException as e:
+            err = e.tname
+        cons = it.get(p, "Constraints")
+        return {"text": text, "exception": err, "console": it.console_text(),
+                "problem_type": it.get(p, "ProblemType"), "objective": hexes(from_cs(it.get(p, "ObjectiveCoefficients"))),
+                "constraints": [[hexes(from_cs(it.get(c, "Coefficients"))), it.get(c, "Relation"), hx(it.get(c, "RHS"))]
+                                for c in cons.items],
+                "signs": from_cs(it.get(p, "SignRestrictions"))}
+
+    def fmt(self, values):
+        it = self.it
+        tab = to_array2d([values[i:i + 4] for i in range(0, len(values) - len(values) % 4, 4)])
+        return {"values": hexes(values), "n3": [it.call_static("NumFormat", "N3", float(v)) for v in values],
+                "table": it.call_static("TableIterationFormater", "Format", tab, 2, "T")}
+
+
+def cli_rows(n):
+    """the bound rows Program.cs:114-124 appends for a binary model (one entry too long, stray 1: SURVEY Q1)"""
+    rows = []
+    for i in range(n):
+        co = [0.0] * (n + 3)
+        co[i] = 1.0
+        co[n + 1] = 1.0
+        rows.append((co, "<=", 1.0))
+    return rows
+
+
+def generate():
+    run = Runner()
+    rng = random.Random(381)
+    out = {"meta": {
+        "what": "outputs of the reference's own C# sources executed by oracle/csharp (see this script's header)",
+        "reference_sources": SOURCES, "reference_sources_sha256": source_digest(),
+        "generator": "tests/golden/make_reference_run.py"}}
+
+    # ---- parser: the reference's fixtures first
+    texts = []
+    for f in ("data/TextFile.txt", "TextFile/textfile.txt"):
+        with open(REF + f, encoding="utf-8-sig", newline="") as fh:
+            texts.append(fh.read())
+    texts += [
+        "max +2 +3 +4\n+1 +2 +3 <= 10\n+3 +2 +1 >= 15\n+ + +\n",                    # README.md example
+        "MIN 1.5 -2 1e1\r\n1 1 1 = 4\r\n  2   0.5  -1   >=  -3.25  \r\nurs + -",     # CRLF, extra blanks, no final newline
+        "max 1 2\n1 1 <= 4\n",                                                         # fewer than 3 lines: early return
+        "max 1 2\n1 x <= 4\nbin bin\n",                                                # FormatException
+        "max 1 2\n1 1 <=\n+ +\n",                                                      # IndexOutOfRangeException
+        "max  1 2\n1 1 <= 4\n+ +\n",                                                   # double blank in the objective line
+        "max 1,000 2\n1 1 <= 4\n+ +\n",                                                # thousands separator
+    ]
+    out["parser"] = [run.parse(t) for t in texts]
+
+    # ---- primal tableau simplex
+    model_a = ([2, 3, 3, 5, 2, 4], [([11, 8, 6, 14, 10, 10], "<=", 40)])
+    model_b = ([2, 3, 4], [([1, 2, 3], "<=", 10), ([3, 2, 1], ">=", 15)])
+    primal = []
+    for obj, cons, keep in ((model_a[0], model_a[1], True), (model_a[0], model_a[1] + cli_rows(6), True),
+                            (model_b[0], model_b[1], True), (model_b[0], model_b[1] + cli_rows(3), False)):
+        primal.append(run.primal(obj, cons, True, keep_text=keep)[0])
+    for case in range(24):
+        n = rng.randint(2, 12)
+        m = rng.randint(1, 10)
+        obj = [rng.randint(-3, 9) for _ in range(n)]
+        cons = []
+        for _ in range(m):
+            k = n if rng.random() < 0.8 else rng.randint(1, n + 2)
+            co = [rng.randint(-2, 9) + (rng.randint(0, 9) / 10 if rng.random() < 0.3 else 0) for _ in range(k)]
+            cons.append((co, rng.choice(["<=", "<=", "<=", ">=", "="]), rng.randint(0, 40)))
+        primal.append(run.primal(obj, cons, rng.random() < 0.8)[0])
+    out["primal"] = primal
+
+    # ---- PrimalSimplexSolver2 / DualSimplexSolver on complete tableaux
+    p2, du = [], []
+    for case in range(16):
+        n, m = rng.randint(2, 9), rng.randint(1, 8)
+        T = [[0.0] * (n + m + 1) for _ in range(m + 1)]
+        for j in range(n):
+            T[0][j] = -float(rng.randint(-2, 9))
+        for i in range(m):
+            for j in range(n):
+                T[i + 1][j] = float(rng.randint(-3, 9)) + (rng.randint(0, 9) / 10 if rng.random() < 0.2 else 0)
+            T[i + 1][n + i] = 1.0
+            T[i + 1][-1] = float(rng.randint(0, 30))
+        p2.append(run.primal2(T, rng.choice([10000, 10000, 10000, 2, 0]), rng.random() < 0.5))
+    for case in range(16):
+        n, m = rng.randint(2, 9), rng.randint(1, 8)
+        T = [[0.0] * (n + m + 1) for _ in range(m + 1)]
+        for j in range(n):
+            T[0][j] = float(rng.randint(0, 9))
+        for i in range(m):
+            for j in range(n):
+                T[i + 1][j] = float(rng.randint(-6, 4)) + (rng.randint(0, 9) / 10 if rng.random() < 0.2 else 0)
+            T[i + 1][n + i] = 1.0
+            T[i + 1][-1] = float(rng.randint(-20, 10))
+        du.append(run.dual(T, rng.choice([10000, 10000, 10000, 2, 0]), rng.random() < 0.6))
+    out["primal2"] = p2
+    out["dual"] = du
+
+    # ---- cutting plane: from the optimal tableau of small integer programs (what Program.cs feeds it)
+    cp = []
+    ip_models = [(model_a[0], model_a[1] + cli_rows(6))]
+    while len(ip_models) < 14:
+        n, m = rng.randint(2, 6), rng.randint(1, 5)
+        obj = [rng.randint(1, 9) for _ in range(n)]
+        cons = [([rng.randint(0, 9) for _ in range(n)], "<=", rng.randint(5, 40)) for _ in range(m)]
+        cons += [([1.0 if j == i else 0.0 for j in range(n)], "<=", float(rng.randint(1, 4))) for i in range(n)]
+        ip_models.append((obj, cons))
+    for obj, cons in ip_models:
+        prec, p = run.primal(obj, cons, True)
+        if prec["status"] != "optimal":
+            continue
+        T = from_cs(run.it.get(p, "FinalTableau"))
+        run.it.max_steps = run.it.steps + 5_000_000
+        try:
+            cp.append(run.cutting_plane(T))
+        except RuntimeError:
+            pass        # a cut sequence that does not end within the step budget is not a fixture
+        run.it.max_steps = None
+    out["cutting_plane"] = cp
+
+    # ---- revised simplex
+    rv = [run.revised([2, 3, 4], [[1, 2, 3], [3, 2, 1]], [10, 15], ["<=", ">="], False, keep_text=True),
+          run.revised(model_a[0], [model_a[1][0][0]] + [[1.0 if j == i else 0.0 for j in range(6)] for i in range(6)],
+                      [40] + [1] * 6, ["<="] * 7, False, keep_text=True)]
+    for case in range(18):
+        n, m = rng.randint(2, 9), rng.randint(1, 8)
+        c = [rng.randint(-2, 9) for _ in range(n)]
+        A = [[rng.randint(-2, 9) + (rng.randint(0, 9) / 10 if rng.random() < 0.3 else 0) for _ in range(n)]
+             for _ in range(m)]
+        b = [rng.randint(0, 40) for _ in range(m)]
+        rels = [rng.choice(["<=", ">=", "="]) for _ in range(m)]
+        rv.append(run.revised(c, A, b, rels, rng.random() < 0.3))
+    out["revised"] = rv
+
+    # ---- branch & bound simplex through the adapter (the reference's menu path, Program.cs:385-389)
+    bb = [run.bb(model_a[0], model_a[1] + cli_rows(6), False), run.bb(model_a[0], model_a[1] + cli_rows(6), True),
+          run.bb(model_b[0], model_b[1] + cli_rows(3), False)]
+    for case in range(10):
+        n, m = rng.randint(2, 5), rng.randint(1, 4)
+        obj = [rng.randint(1, 9) for _ in range(n)]
+        cons = [([rng.randint(0, 9) for _ in range(n)], "<=", rng.randint(5, 40)) for _ in range(m)]
+        if rng.random() < 0.75:
+            cons += [([1.0 if j == i else 0.0 for j in range(n)], "<=", float(rng.randint(1, 4))) for i in range(n)]
+        bb.append(run.bb(obj, cons, rng.random() < 0.5))
+    out["bb"] = bb
+    fm = []
+    for case in range(6):
+        n, m = rng.randint(2, 4), rng.randint(1, 3)
+        obj = [rng.randint(1, 9) for _ in range(n)]
+        rows = [[float(rng.randint(0, 9)) for _ in range(n)] + [float(rng.randint(3, 30)), float(rng.choice([0, 0, 1]))]
+                for _ in range(m)]
+        run.it.max_steps = run.it.steps + 3_000_000
+        try:
+            fm.append(run.bb_formulate(obj, rows, case % 3 == 2))
+        except (RuntimeError, CsException) as e:
+            fm.append({"objective": obj, "rows": rows, "is_min": case % 3 == 2, "error": str(e)[:120]})
+        run.it.max_steps = None
+    out["bb_formulate"] = fm
+
+    # ---- sensitivity re-optimisation
+    se = []
+    sens_models = [(model_a[0], model_a[1] + [([1.0 if j == i else 0.0 for j in range(6)], "<=", 1.0) for i in range(6)])]
+    while len(sens_models) < 8:
+        n, m = rng.randint(2, 5), rng.randint(2, 5)
+        obj = [rng.randint(1, 9) for _ in range(n)]
+        cons = [([rng.randint(0, 9) for _ in range(n)], "<=", rng.randint(5, 40)) for _ in range(m)]
+        sens_models.append((obj, cons))
+    for obj, cons in sens_models:
+        prec, _ = run.primal(obj, cons, True)
+        if prec["status"] != "optimal":
+            continue
+        ncols = len(obj) + len(cons)
+        tech = [float(rng.randint(0, 5)) for _ in range(len(obj))] + [0.0] * len(cons)
+        assert len(tech) == ncols
+        se.append(run.sensitivity(obj, cons, tech, float(rng.randint(2, 20))))
+        se.append(run.sensitivity(obj, cons, [-t for t in tech], float(-rng.randint(2, 20))))
+    out["sensitivity"] = se
+    sr = []
+    for obj, cons in sens_models:
+        prec, _ = run.primal(obj, cons, True)
+        if prec["status"] != "optimal":
+            continue
+        sr.append(run.sensitivity_rhs(obj, cons, rng.randint(1, len(cons)), float(rng.choice([-30, -12, -5, 4, 9]))))
+    out["sensitivity_rhs"] = sr
+
+    # ---- text rules
+    vals = [0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 0.0005, -0.0005, 0.0015, 2.0005, 1234.5675, 1e-13, -1e-13, 1e15, 1e16,
+            123456789.12345679, 0.1 + 0.2, 1 / 3, -2 / 3, 2.5, 3.5, 1e-5, 99999.9995, 6.666666666666667,
+            0.4999999999999999, 1000000.0, 7.0005000000000015, -7.9995]
+    vals += [rng.uniform(-100, 100) for _ in range(12)] + [round(rng.uniform(-10, 10), 4) for _ in range(12)]
+    out["format"] = run.fmt(vals)
+    return out
+
+
+def main():
+    data = generate()
+    # one record per line: diffable, a third of the size of an indented dump
+    lines = []
+    for key in sorted(data):
+        val = data[key]
+        if isinstance(val, list):
+            body = ",\n".join("  " + json.dumps(rec, sort_keys=True) for rec in val)
+            lines.append(f' {json.dumps(key)}: [\n{body}\n ]')
+        else:
+            lines.append(f" {json.dumps(key)}: {json.dumps(val, sort_keys=True)}")
+    text = "{\n" + ",\n".join(lines) + "\n}\n"
+    assert json.loads(text) == data
+    if "--check" in sys.argv:
+        with open(OUT) as f:
+            same = f.read() == text
+        print("reference_run.json is", "up to date" if same else "DIFFERENT from a fresh run")
+        sys.exit(0 if same else 1)
+    with open(OUT, "w") as f:
+        f.write(text)
+    print("wrote", OUT, len(text), "bytes;", {k: len(v) for k, v in data.items() if isinstance(v, list)})
+
+
+if __name__ == "__main__":
+    main()

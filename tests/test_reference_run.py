@@ -1,0 +1,384 @@
+"""CPU tests: the oracle (oracle/lpr_oracle.cpp) and the native host code against OUTPUTS OF THE REFERENCE'S OWN C#
+SOURCES, executed in the build container by the interpreter under oracle/csharp/ and committed as
+tests/golden/reference_run.json (generator: tests/golden/make_reference_run.py).
+
+This is what pins the oracle: every value below was produced by running Storm-Tarran/LPR_381_Group_V22's unmodified
+.cs files, not by reading them.  The GPU leg of the same comparison is tests/test_reference_run_gpu.py.
+"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_run.json")))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def unmat(m):
+    return np.array([float.fromhex(h) for h in m["hex"]], dtype=np.float64).reshape(m["shape"])
+
+
+def unhex(v):
+    return np.array([float.fromhex(h) for h in v], dtype=np.float64)
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def cons_of(rec):
+    return [(co, rel, rhs) for co, rel, rhs in rec["constraints"]]
+
+
+# ------------------------------------------------------------------------------------------- the golden file itself
+def test_golden_covers_the_reference_fixtures_and_every_solver():
+    assert GOLD["meta"]["generator"] == "tests/golden/make_reference_run.py"
+    assert len(GOLD["meta"]["reference_sources"]) == 10
+    for key, least in (("parser", 9), ("primal", 28), ("primal2", 16), ("dual", 16), ("cutting_plane", 12),
+                       ("revised", 20), ("bb", 13), ("bb_formulate", 6), ("sensitivity", 12), ("sensitivity_rhs", 6)):
+        assert len(GOLD[key]) >= least, key
+    # data/TextFile.txt parsed by the reference's own InputFileParser
+    p = GOLD["parser"][0]
+    assert p["problem_type"] == "max" and unhex(p["objective"]).tolist() == [2, 3, 3, 5, 2, 4]
+    assert p["signs"] == ["bin"] * 6 and p["constraints"][0][1] == "<="
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/LPR_381_Group_V22"), reason="the reference tree is only in the build container")
+def test_golden_is_what_the_reference_sources_produce_today():
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_run.py"), "--check"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------------------------------- primal tableau simplex
+@pytest.mark.parametrize("i", range(len(GOLD["primal"])))
+def test_primal_simplex_solver(i):
+    g = GOLD["primal"][i]
+    T0, basis0 = O.primal_build(g["objective"], cons_of(g), g["is_max"])
+    assert same_bits(T0, unmat(g["initial_tableau"]))
+    r = O.primal_solve(T0, basis0)
+    assert r["log"].tolist() == g["pivots"]
+    assert r["status"] == (O.OPTIMAL if g["status"] == "optimal" else O.UNBOUNDED)
+    assert same_bits(r["T"], unmat(g["final_tableau"])) and same_bits(r["T"], unmat(g["get_final_tableau"]))
+    assert r["basis"].tolist() == g["basis"]
+    if g["status"] == "optimal":
+        assert float(r["T"][0, -1]).hex() == g["final_z"]
+        assert same_bits(O.primal_extract(r["T"], len(g["objective"])), unhex(g["x"]))
+    else:
+        assert g["x"] is None and float.fromhex(g["final_z"]) == 0.0   # FinalZ / SolutionVector are never set
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["primal2"])))
+def test_primal_simplex_solver2(i):
+    g = GOLD["primal2"][i]
+    r = O.primal2_solve(unmat(g["tableau"]), g["max_iters"], g["print_steps"])
+    assert same_bits(r["T"], unmat(g["final_tableau"]))
+    assert (r["status"] == O.OPTIMAL) == g["returned"]
+    assert r["log"].tolist() == g["pivots"]
+    if g["returned"]:
+        assert float(r["T"][0, -1]).hex() == g["final_z"]
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["dual"])))
+def test_dual_simplex_solver(i):
+    g = GOLD["dual"][i]
+    r = O.dual_solve(unmat(g["tableau"]), g["max_iters"], g["print_steps"])
+    assert same_bits(r["T"], unmat(g["final_tableau"]))
+    if g["exception"] is not None:
+        assert g["exception"] == "InvalidOperationException" and r["status"] == O.PIVOT_TOO_SMALL
+    else:
+        assert (r["status"] == O.OPTIMAL) == g["returned"]
+    if g["print_steps"]:   # the reference prints "constraint {pivotRow + 1}" (DualSimplex.cs:94) = the tableau row
+        assert r["log"].tolist() == g["printed_pivots"]
+
+
+CUT_END = {"Displayed the Optimal Tableau.": O.OPTIMAL, "All RHS are integers. No Gomory cut needed.": O.NO_CUT_NEEDED,
+           "No valid pivot column on the cut (need a negative cut coeff with non-zero obj coeff).": O.NO_PIVOT_COL,
+           "Dual Simplex failed (infeasible or max iters).": None, "Pivot too small/zero.": O.PIVOT_TOO_SMALL,
+           "Cutting-plane step finished (further steps may be required).": O.CUT_STEP_DONE}
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["cutting_plane"])))
+def test_cutting_plane_solver(i):
+    g = GOLD["cutting_plane"][i]
+    T = unmat(g["tableau"])
+    r = O.cutting_plane(T, extra_rows=64)
+    assert same_bits(r["T"], unmat(g["final_tableau"]))
+    # a cut that finds no pivot column is appended all the same (CuttingPlaneSolver.cs:107-131)
+    appended = unmat(g["final_tableau"]).shape[0] - T.shape[0]
+    assert appended in (len(g["cut_pivots_1based"]), len(g["cut_pivots_1based"]) + 1)
+    got = [[T.shape[0] + k, int(c) + 1] for k, c in enumerate(r["log"][:len(g["cut_pivots_1based"]), 1])]
+    assert got == g["cut_pivots_1based"]          # "row {cutRowIdx + 1}, col {pivotCol + 1}" (:136)
+    want = CUT_END[g["last_console_line"]]
+    if want is None:
+        assert r["status"] in (O.INFEASIBLE, O.ITER_LIMIT)
+    else:
+        assert r["status"] == want
+
+
+# ------------------------------------------------------------------------------------------- revised simplex
+@pytest.mark.parametrize("i", range(len(GOLD["revised"])))
+def test_revised_primal_simplex_solver(i):
+    g = GOLD["revised"][i]
+    n = len(g["c"])
+    r = O.rev_solve(np.array(g["A"], dtype=float), g["b"], g["c"], g["is_min"], want_binv=True)
+    labels = [f"x{e + 1}" if e < n else f"S{e - n + 1}" for e in r["log"][:, 1].tolist()]
+    assert labels == g["entering_labels"] and r["n_iter"] == g["n_iterations"]
+    assert r["basis"].tolist() == g["basis"]
+    assert same_bits(r["Binv"], unmat(g["binv"]))
+    if g["exception"] is None:
+        assert r["status"] == O.OPTIMAL
+        assert same_bits(r["xB"], unhex(g["xb"])) and same_bits(r["x"], unhex(g["x"]))
+        assert float(r["z"]).hex() == g["final_z"]
+    elif g["exception"].startswith("Unbounded"):
+        assert r["status"] == O.UNBOUNDED
+    elif g["exception"].startswith("Infeasible"):
+        assert r["status"] == O.INFEASIBLE
+    else:
+        assert r["status"] == O.PIVOT_TOO_SMALL
+
+
+def test_revised_snapshot_text_restatement():
+    """tests/net_reference.py (the checker of the native CaptureSnapshot text, b9) against the text the reference's
+    own CaptureSnapshot produced"""
+    import net_reference as R
+    for g in GOLD["revised"]:
+        if g["exception"] is not None:
+            continue
+        snaps, *_ = R.revised_solve_with_snapshots(g["c"], g["A"], g["b"], g["is_min"])
+        text = "".join(snaps)
+        assert len(snaps) == g["n_snapshots"]
+        assert hashlib.sha256(text.encode("utf-8")).hexdigest() == g["snapshots_sha256"]
+        if "snapshots" in g:
+            assert snaps == g["snapshots"]
+
+
+# ------------------------------------------------------------------------------------------- B&B simplex
+@pytest.mark.parametrize("i", range(len(GOLD["bb"])))
+def test_branch_and_bound_adapter(i):
+    g = GOLD["bb"][i]
+    r = O.bb_solve(unmat(g["root_tableau"]), g["n_vars"], prune=g["enable_pruning"], max_nodes=20)
+    nodes = g["nodes"]
+    assert r["nodes"] == len(nodes)
+    log = r["node_log"]
+    assert log[:, 0].tolist() == [nd["depth"] for nd in nodes]
+    assert log[:, 3].astype(bool).tolist() == [nd["pruned"] for nd in nodes]
+    for k, nd in enumerate(nodes):
+        if not nd["pruned"]:
+            assert int(log[k, 1]) == nd["branch_var"], (k, nd)
+            assert bool(log[k, 2]) == nd["integer"], (k, nd)
+    x, z = unhex(g["x"]), float.fromhex(g["z"])
+    if r["has_solution"]:
+        assert same_bits(r["x"], x) and float(r["z"]).hex() == g["z"]
+    else:
+        assert x.size == 0 and z == float("-inf")     # (x ?? new List<double>(), z) with z = -infinity
+    assert (r["status"] == O.NODE_LIMIT) == g["hit_node_cap"]
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["bb_formulate"])))
+def test_dual_simplex_solver_bb_formulate_and_solve(i):
+    g = GOLD["bb_formulate"][i]
+    assert "error" not in g
+    T = O.bb_formulate(g["objective"], g["rows"])
+    assert same_bits(T, unmat(g["tableau"]))
+    r = O.bb_node_solve_ex(T, g["is_min"])
+    if g["optimal_value"] is None:
+        assert r["status"] == O.INFEASIBLE
+    else:
+        assert r["status"] == O.OPTIMAL
+        assert same_bits(r["T"], unmat(g["final_tableau"]))
+        assert float(r["T"][0, -1]).hex() == g["optimal_value"]
+        assert r["log"][:, 0].tolist() == g["pivot_rows"] and r["log"][:, 1].tolist() == g["pivot_cols"]
+
+
+# ------------------------------------------------------------------------------------------- sensitivity
+def _sens_root(g):
+    T0, b0 = O.primal_build(g["objective"], cons_of(g), True)
+    opt = O.primal_solve(T0, b0)
+    assert opt["status"] == O.OPTIMAL
+    return opt["T"]
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["sensitivity"])))
+def test_sensitivity_add_constraint(i):
+    g = GOLD["sensitivity"][i]
+    T = _sens_root(g)
+    assert same_bits(T, unmat(g["final_tableau"]))
+    n = len(g["objective"])
+    basis = O.sens_rebuild_basis(T)
+    assert basis.tolist() == g["basis_rebuilt"]
+    x = O.primal_extract(T, n)
+    ax = 0.0
+    for j in range(min(len(g["tech"]), n)):
+        ax += g["tech"][j] * x[j]
+    T1, b1 = O.sens_add_constraint(T, basis, g["tech"], g["rhs"] - ax)
+    res = O.sens_resolve(T1, O.sens_rebuild_basis(T1))
+    assert same_bits(res["T"], unmat(g["tableau_after"]))
+    assert res["basis"].tolist() == g["basis_after"]
+    if g["exception"] is None:
+        assert res["status"] == O.OPTIMAL
+        assert float(res["T"][0, -1]).hex() == g["z_after"]
+        assert same_bits(O.sens_solution(res["T"]), unhex(g["x_after"]))
+    else:
+        assert res["status"] in (O.INFEASIBLE, O.UNBOUNDED, O.ITER_LIMIT)
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["sensitivity_rhs"])))
+def test_sensitivity_resolve_after_rhs_change(i):
+    g = GOLD["sensitivity_rhs"][i]
+    T = unmat(g["tableau_before_resolve"])
+    res = O.sens_resolve(T, O.sens_rebuild_basis(T))
+    assert same_bits(res["T"], unmat(g["tableau_after"]))
+    assert res["basis"].tolist() == g["basis_after"]
+    if g["exception"] is None:
+        assert res["status"] == O.OPTIMAL
+        assert float(res["T"][0, -1]).hex() == g["z_after"]
+        assert same_bits(O.sens_solution(res["T"]), unhex(g["x_after"]))
+    else:
+        assert res["status"] in (O.INFEASIBLE, O.UNBOUNDED, O.ITER_LIMIT)
+
+
+# ------------------------------------------------------------------------------------------- native host code
+def test_native_parser_against_the_reference_parser():
+    from lpr_381_group_v22_b200.io import Model
+    for g in GOLD["parser"]:
+        if g["exception"] == "FormatException":
+            with pytest.raises(ValueError, match="FormatException"):
+                Model.parse_text(g["text"])
+            continue
+        if g["exception"] == "IndexOutOfRangeException":
+            with pytest.raises(IndexError, match="IndexOutOfRangeException"):
+                Model.parse_text(g["text"])
+            continue
+        m = Model.parse_text(g["text"])
+        assert m.message == g["console"].strip()
+        if g["problem_type"] is None:
+            assert m.info()[0] is False
+            continue
+        assert m.problem_type == g["problem_type"]
+        assert same_bits(m.objective(), unhex(g["objective"]))
+        cons = m.constraints()
+        assert len(cons) == len(g["constraints"])
+        for c, (co, rel, rhs) in zip(cons, g["constraints"]):
+            assert same_bits(c.Coefficients, unhex(co)) and c.Relation == rel and float(c.RHS).hex() == rhs
+        assert m.signs() == g["signs"]
+
+
+def test_native_number_formatting_against_the_interpreted_formatter():
+    """three independent statements of the .NET Framework rules -- csrc/host_io.cu, tests/net_reference.py and
+    oracle/csharp/csrun.py (which ran the reference's NumFormat.N3 / TableIterationFormater.Format) -- agree"""
+    import net_reference as R
+    from lpr_381_group_v22_b200.utilities import NumFormat, TableIterationFormater
+    g = GOLD["format"]
+    vals = unhex(g["values"])
+    assert [NumFormat.N3(float(v)) for v in vals] == g["n3"]
+    assert [R.N3(float(v)) for v in vals] == g["n3"]
+    k = len(vals) - len(vals) % 4
+    tab = vals[:k].reshape(-1, 4)
+    assert TableIterationFormater.Format(tab, 2, "T") == g["table"]
+    assert R.format_table(tab.tolist(), 2, "T") == g["table"]
+
+
+def test_native_snapshot_text_of_the_primal_solver():
+    """IterationSnapshots of PrimalSimplexSolver as the reference built them, against the native formatter fed with
+    the oracle's tableaux (the GPU path produces the same tableaux bit for bit, tests/test_reference_run_gpu.py)"""
+    from lpr_381_group_v22_b200.utilities import TableIterationFormater
+    for g in GOLD["primal"]:
+        if "snapshots" not in g:
+            continue
+        n = len(g["objective"])
+        T, basis = O.primal_build(g["objective"], cons_of(g), g["is_max"])
+        texts = [TableIterationFormater.Format(T, n, "Initial Tableau")]
+        for k, (pr, pc) in enumerate(g["pivots"]):
+            O.lib().orc_primal_pivot(T.shape[0], T.shape[1], T.ctypes.data_as(O._dp), pr, pc, 1)
+            texts.append(TableIterationFormater.Format(T, n, f"Iteration {k + 1} - After pivot"))
+        assert texts == g["snapshots"][:-1]
+        assert g["snapshots"][-1].startswith(TableIterationFormater.Format(T, n, "Final Tableau (Optimal)"))
+
+
+# ------------------------------------------------------------------------------------------- the interpreter itself
+def _run(src, cls="T", method="F", *args):
+    from csharp import Interpreter
+    it = Interpreter()
+    it.load_source(src)
+    return it, it.call_static(cls, method, *args)
+
+
+def test_interpreter_numeric_typing_rules():
+    src = """
+    using System; using System.Collections.Generic; using System.Linq;
+    public static class T {
+        public static double Half(int a, int b) { double s = 0; s += a / b; return s; }          // int / int truncates
+        public static double Conv() { double x = 7; return x / 2; }                              // int -> double on store
+        public static double Tern(bool c) { return (c ? 1 : 2.5) / 2; }                         // ?: unifies to double
+        public static int Rem() { return (-7 / 2) * 10 + (-7 % 3); }
+        public static double ListConv() { var l = new List<double> { 1, 2 }; l.Add(3); return l[2] / 2; }
+        public static double NegZero() { double z = -0.0; return 1 / z; }
+        public static int Cast(double d) { return (int)d; }
+        public static double Prec() { return 1 + 2 * 3 - 4 / 8.0 % 3; }
+        public static string Interp(double v, int w) { return $"[{v,8:F3}|{w:D3}|{v:0.##}|{(w > 2 ? "a:b" : "c")}]"; }
+    }"""
+    from csharp import Interpreter
+    it = Interpreter()
+    it.load_source(src)
+    c = lambda m, *a: it.call_static("T", m, *a)
+    assert c("Half", 7, 2) == 3.0 and c("Conv") == 3.5 and c("Tern", True) == 0.5 and c("Tern", False) == 1.25
+    assert c("Rem") == -31 and c("ListConv") == 1.5 and c("NegZero") == float("-inf")
+    assert c("Cast", -2.9) == -2 and c("Cast", float("nan")) == -2147483648 and c("Prec") == 6.5
+    assert c("Interp", 3.14159, 7) == "[   3.142|007|3.14|a:b]"
+
+
+def test_interpreter_bcl_rules():
+    from csharp.csrun import CsException, format_double, introsort, math_round, math_round_digits
+    # Math.Round: banker's at the integer, the Framework's scale / round / unscale at digits
+    assert [math_round(v) for v in (0.5, 1.5, 2.5, -0.5, -1.5, 0.49999999999999994)] == [0, 2, 2, -0.0, -2, 0]
+    assert math_round_digits(2.00005, 4) == 2.0 and math_round_digits(2.00015, 4) == 2.0002
+    assert math_round_digits(1.0005, 3, away=True) == 1.001 and math_round_digits(-1.0005, 3, away=True) == -1.001
+    # number formatting: 15 significant digits, then half up on the digit string
+    assert format_double(0.1 + 0.2) == "0.3" and format_double(1e15) == "1E+15" and format_double(123456789012345.0) == "123456789012345"
+    assert format_double(2.5, "F0") == "3" and format_double(-0.0004, "F3") == "0.000" and format_double(1.0005, "F3") == "1.001"
+    assert format_double(0.00001) == "1E-05" and format_double(-1234.5, "N1") == "-1,234.5"
+    assert format_double(12.3456, "0.###") == "12.346" and format_double(5.0, "0.###") == "5" and format_double(0.5, "0.00") == "0.50"
+    assert format_double(0.1, "R") == "0.1" and format_double(1 / 3, "R") == "0.33333333333333331"
+    # LINQ
+    src = """
+    using System; using System.Collections.Generic; using System.Linq;
+    public static class T {
+        public static string F() {
+            var l = new List<double> { 3, double.NaN, 1 };
+            var s = "";
+            s += l.Min() + "|" + l.Max() + "|" + l.IndexOf(double.NaN) + "|" + l.Contains(-0.0 + 1);
+            try { new List<double>().Min(); } catch (InvalidOperationException) { s += "|empty"; }
+            try { var x = l[-1]; } catch (ArgumentOutOfRangeException) { s += "|range"; }
+            try { double[] a = new double[2]; a[2] = 1; } catch (IndexOutOfRangeException) { s += "|index"; }
+            try { List<double> n = null; n.ToList(); } catch (ArgumentNullException) { s += "|argnull"; }
+            try { List<double> n = null; n.Add(1); } catch (NullReferenceException) { s += "|nullref"; }
+            try { foreach (var v in l) l.Add(v); } catch (InvalidOperationException) { s += "|modified"; }
+            int? q = null; s += "|" + (q + 1 == null) + (q > 0) + q.HasValue;
+            var o = new[] { 5, 3, 9, 3 }.Select((v, i) => new { v, i }).OrderBy(p => p.v).Select(p => p.i);
+            s += "|" + string.Join(",", o);
+            return s;
+        }
+    }"""
+    _, out = _run(src)
+    assert out == "NaN|3|1|True|empty|range|index|argnull|nullref|modified|TrueFalseFalse|1,3,0,2"
+    # List<T>.Sort is the Framework's introspective sort: unstable above 16 elements
+    keys = [(i % 3, i) for i in range(40)]
+    introsort(keys, lambda a, b: (a[0] > b[0]) - (a[0] < b[0]))
+    assert [k[0] for k in keys] == sorted(k[0] for k in keys)
+    assert [k[1] for k in keys if k[0] == 0] != sorted(k[1] for k in keys if k[0] == 0)
+    small = [(i % 3, i) for i in range(16)]
+    introsort(small, lambda a, b: (a[0] > b[0]) - (a[0] < b[0]))
+    assert small == sorted(small)                     # insertion sort up to 16 elements: stable
+    with pytest.raises(CsException):
+        _run("public static class T { public static int F() { int z = 0; return 1 / z; } }")
