@@ -563,6 +563,8 @@ def cs_tostring(v, fmt=None):
         return "{ " + ", ".join(f"{k} = {cs_tostring(x)}" for k, x in v.f.items()) + " }"
     if t is CsObject:
         return (v.cls.ns + "." if v.cls.ns else "") + v.cls.name
+    if t is CsDateTime:
+        return v.text          # the injected clock already has the "yyyy-MM-dd HH:mm:ss" form the reference asks for
     return str(v)
 
 
@@ -2565,11 +2567,15 @@ def bcl_static_call(interp, tname, name, args, named):
             if lines and lines[-1] == "":
                 lines.pop()
             return CsArray("string", (len(lines),), lines)
+        # File.WriteAllText / AppendAllText(path, text, Encoding.UTF8): the StreamWriter emits the UTF-8 preamble when
+        # it starts at stream position 0 (a new or empty file), never in the middle of an existing file
+        bom = "\ufeff" if len(args) > 2 and args[2] == "UTF8" else ""
         if name == "WriteAllText":
-            interp.files[path] = args[1]
+            interp.files[path] = bom + args[1]
             return None
         if name == "AppendAllText":
-            interp.files[path] = interp.files.get(path, "") + args[1]
+            old = interp.files.get(path, "")
+            interp.files[path] = old + (bom if old == "" else "") + args[1]
             return None
         if name in ("WriteAllLines", "AppendAllLines"):
             text = "".join(cs_tostring(v) + "\r\n" for v in iterate(args[1]))
@@ -2588,7 +2594,7 @@ def bcl_static_call(interp, tname, name, args, named):
         if name == "GetExtension":
             return os.path.splitext(args[0])[1]
         if name == "GetDirectoryName":
-            return re.sub(r"[\\/][^\\/]*$", "", args[0])
+            return re.sub(r"[\\/][^\\/]*$", "", args[0]) if re.search(r"[\\/]", args[0]) else ""
         if name == "GetFullPath":
             return args[0]
     if tname == "Directory":
@@ -3082,6 +3088,8 @@ def str_call(s, name, args):
             raise CsException("ArgumentOutOfRangeException", param="startIndex" if start < 0 or start > len(s) else "length")
         return s[start:start + n]
     if name == "IndexOf":
+        if len(args) > 1 and type(args[-1]) is CsEnum and args[-1].value in (1, 3, 5):
+            return s.lower().find(args[0].lower())
         return s.find(args[0], *(args[1:2] if len(args) > 1 and type(args[1]) is int else []))
     if name == "LastIndexOf":
         return s.rfind(args[0])

@@ -19,6 +19,9 @@ What is executed (class -> entry points):
                                                SolveFromPrimal(primal, enablePruning, isMin) and the console trace of
                                                ExecuteBranchAndBound; DualSimplexSolverBB.FormulateTableau / DoDualSimplex
     SensitivityAnalysis/SensitivityAnalyzer.cs ctor (RebuildBasicsFromTableau), AddNewConstraintNonInteractive, ResolveAll
+    IO/OutputFileWrite.cs, Utilities/CanonicalFormConverter.cs
+                                               WriteFullResults, WriteSnapshotsOnly (append), CanonicalFormForFile
+    Program.cs                                 AddUpperBoundConstraints (the only callable helper; Main is the menu)
     Utilities/TableIterationFormater.cs, NumFormat.N3   (number formatting is the interpreter's restatement of the BCL)
 
 Doubles are stored as C99 hex strings (bit exact); inputs as decimal literals that round-trip.
@@ -28,6 +31,7 @@ import json
 import os
 import random
 import re
+import struct
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -44,6 +48,7 @@ SOURCES = [
     "Simplex/PrimalSimplexSolver2.cs", "Simplex/DualSimplex.cs", "IntegerProgramming/CuttingPlaneSolver.cs",
     "Simplex/RevisedPrimalSimplexSolver.cs", "IntegerProgramming/BranchBoundSimplexSolver.cs",
     "IntegerProgramming/BranchAndBoundAdapter.cs", "SensitivityAnalysis/SensitivityAnalyzer.cs",
+    "IO/OutputFileWrite.cs", "Utilities/CanonicalFormConverter.cs", "Program.cs",
 ]
 
 
@@ -276,6 +281,36 @@ class Runner:
                 "tableau_after": mat(from_cs(it.get(s, "CurrentTableau"))), "z_after": hx(it.get(s, "CurrentZ")),
                 "x_after": hexes(from_cs(it.get(s, "CurrentSolutionVector"))), "basis_after": from_cs(s.f["basicVars"])}
 
+    # ------------------------------------------------------------------ result files, canonical form, bound rows
+    def output(self, text, solver_name, add_bounds):
+        """menu option 1 + the export option of Program.cs in the reference's own order: parse, (bound rows),
+        PrimalSimplexSolver, WriteFullResults (overwrite), then WriteSnapshotsOnly appended to the same file"""
+        it = self.it
+        it.console.clear()
+        it.files.clear()
+        it.files["model.txt"] = text
+        p = it.new("InputFileParser")
+        it.call(p, "ReadInputFile", "model.txt")
+        obj, cons, signs = it.get(p, "ObjectiveCoefficients"), it.get(p, "Constraints"), it.get(p, "SignRestrictions")
+        n_before = len(cons.items)
+        if add_bounds:
+            it.call_static("Program", "AddUpperBoundConstraints", len(obj.items), signs, cons)
+        added = [[hexes(from_cs(it.get(c, "Coefficients"))), it.get(c, "Relation"), hx(it.get(c, "RHS"))]
+                 for c in cons.items[n_before:]]
+        s = it.new("PrimalSimplexSolver", obj, cons, it.get(p, "ProblemType") == "max")
+        it.call(s, "Solve")
+        snaps, z, x = it.get(s, "IterationSnapshots"), it.get(s, "FinalZ"), it.get(s, "SolutionVector")
+        canon = it.call_static("CanonicalFormConverter", "CanonicalFormForFile", it.get(p, "ProblemType"), obj, cons, signs)
+        path = "data\\output_results.txt"
+        it.call_static("OutputFileWrite", "WriteFullResults", path, solver_name, it.get(p, "ProblemType"), obj, cons,
+                       signs, snaps, z, x)
+        first = it.files[path]
+        it.call_static("OutputFileWrite", "WriteSnapshotsOnly", path, solver_name + " (again)", snaps, z, x)
+        return {"text": text, "solver": solver_name, "add_upper_bound_rows": add_bounds, "timestamp": it.now,
+                "rows_added": added, "canonical_form": canon, "snapshots": from_cs(snaps), "final_z": hx(z),
+                "x": hexes(from_cs(x)) if x is not None else None,
+                "file_after_full_results": first, "file_after_append": it.files[path]}
+
     # ------------------------------------------------------------------ parser / formatting
     def parse(self, text):
         it = self.it
@@ -468,6 +503,33 @@ def generate():
             continue
         sr.append(run.sensitivity_rhs(obj, cons, rng.randint(1, len(cons)), float(rng.choice([-30, -12, -5, 4, 9]))))
     out["sensitivity_rhs"] = sr
+
+    # ---- result files
+    out["output"] = [
+        run.output(texts[0], "Primal Simplex Algorithm", True),
+        run.output(texts[2], "Primal Simplex Algorithm", False),
+        run.output("max 1.5 -2 0.25\n1 1 1 <= 4.5\n2 0.5 -1 <= 3\n0<=x1<=1 + x3 <= 1\n", "Primal Simplex Algorithm", True),
+    ]
+
+    # ---- mid-size runs (digests instead of full matrices): longer pivot sequences, accumulated rounding
+    mid = []
+    for (m, n) in ((18, 24), (30, 40), (40, 28)):
+        obj = [rng.randint(1, 20) + rng.randint(0, 99) / 100 for _ in range(n)]
+        cons = [([(rng.randint(1, 12) + rng.randint(0, 99) / 100) if rng.random() < 0.3 else 0.0 for _ in range(n)],
+                 "<=", float(rng.randint(20, 90))) for _ in range(m)]
+        prec, _ = run.primal(obj, cons, True)
+        rv_rec = run.revised(obj, [c[0] for c in cons], [c[2] for c in cons], ["<="] * m, False)
+        for rec in (prec, rv_rec):
+            for key in ("initial_tableau", "final_tableau", "get_final_tableau", "binv"):
+                if key in rec:
+                    mtx = rec.pop(key)
+                    rec[key + "_shape"] = mtx["shape"]
+                    rec[key + "_sha256"] = hashlib.sha256(
+                        b"".join(struct.pack("<d", float.fromhex(h)) for h in mtx["hex"])).hexdigest()
+        mid.append({"objective": obj, "constraints": [[list(co), rel, rhs] for co, rel, rhs in cons],
+                    "primal": {k: v for k, v in prec.items() if k not in ("objective", "constraints")},
+                    "revised": {k: v for k, v in rv_rec.items() if k not in ("c", "A", "b", "relations")}})
+    out["mid_size"] = mid
 
     # ---- text rules
     vals = [0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 0.0005, -0.0005, 0.0015, 2.0005, 1234.5675, 1e-13, -1e-13, 1e15, 1e16,

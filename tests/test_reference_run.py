@@ -43,9 +43,10 @@ def cons_of(rec):
 # ------------------------------------------------------------------------------------------- the golden file itself
 def test_golden_covers_the_reference_fixtures_and_every_solver():
     assert GOLD["meta"]["generator"] == "tests/golden/make_reference_run.py"
-    assert len(GOLD["meta"]["reference_sources"]) == 10
+    assert len(GOLD["meta"]["reference_sources"]) == 13
     for key, least in (("parser", 9), ("primal", 28), ("primal2", 16), ("dual", 16), ("cutting_plane", 12),
-                       ("revised", 20), ("bb", 13), ("bb_formulate", 6), ("sensitivity", 12), ("sensitivity_rhs", 6)):
+                       ("revised", 20), ("bb", 13), ("bb_formulate", 6), ("sensitivity", 12), ("sensitivity_rhs", 6),
+                       ("output", 3), ("mid_size", 3)):
         assert len(GOLD[key]) >= least, key
     # data/TextFile.txt parsed by the reference's own InputFileParser
     p = GOLD["parser"][0]
@@ -304,6 +305,54 @@ def test_native_snapshot_text_of_the_primal_solver():
             texts.append(TableIterationFormater.Format(T, n, f"Iteration {k + 1} - After pivot"))
         assert texts == g["snapshots"][:-1]
         assert g["snapshots"][-1].startswith(TableIterationFormater.Format(T, n, "Final Tableau (Optimal)"))
+
+
+def test_native_result_files_against_output_file_write(tmp_path):
+    """OutputFileWrite.WriteFullResults / WriteSnapshotsOnly, CanonicalFormConverter.CanonicalFormForFile and
+    Program.AddUpperBoundConstraints as the reference executed them, against lpr_out_* / lpr_model_* (csrc/host_io.cu)"""
+    import lpr_381_group_v22_b200 as L
+    from lpr_381_group_v22_b200.io import Model
+    for k, g in enumerate(GOLD["output"]):
+        m = Model.parse_text(g["text"])
+        before = len(m.constraints())
+        if g["add_upper_bound_rows"]:
+            m.add_upper_bound_rows()
+        added = m.constraints()[before:]
+        assert len(added) == len(g["rows_added"])
+        for c, (co, rel, rhs) in zip(added, g["rows_added"]):
+            assert same_bits(c.Coefficients, unhex(co)) and c.Relation == rel and float(c.RHS).hex() == rhs
+        assert m.canonical_form() == g["canonical_form"]
+        path = str(tmp_path / f"out{k}" / "output_results.txt")
+        x = unhex(g["x"]).tolist()
+        z = float.fromhex(g["final_z"])
+        L.io.OutputFileWrite.WriteFullResults(path, g["solver"], m, g["snapshots"], z, x, append=False,
+                                              timestamp=g["timestamp"])
+        assert open(path, "rb").read() == g["file_after_full_results"].encode("utf-8")
+        L.io.OutputFileWrite.WriteSnapshotsOnly(path, g["solver"] + " (again)", g["snapshots"], z, x, append=True,
+                                                timestamp=g["timestamp"])
+        assert open(path, "rb").read() == g["file_after_append"].encode("utf-8")
+        assert g["file_after_append"].count("\ufeff") == 1     # one byte-order mark, at the start
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["mid_size"])))
+def test_mid_size_runs(i):
+    """longer pivot sequences (12-15 pivots on 19x43 .. 41x69 tableaux): digests of what the reference computed"""
+    g = GOLD["mid_size"][i]
+    cons = cons_of(g)
+    n = len(g["objective"])
+    pg, rg = g["primal"], g["revised"]
+    T0, b0 = O.primal_build(g["objective"], cons, True)
+    assert hashlib.sha256(T0.tobytes()).hexdigest() == pg["initial_tableau_sha256"]
+    r = O.primal_solve(T0, b0)
+    assert r["log"].tolist() == pg["pivots"] and r["basis"].tolist() == pg["basis"]
+    assert list(r["T"].shape) == pg["final_tableau_shape"]
+    assert hashlib.sha256(r["T"].tobytes()).hexdigest() == pg["final_tableau_sha256"]
+    assert float(r["T"][0, -1]).hex() == pg["final_z"] and same_bits(O.primal_extract(r["T"], n), unhex(pg["x"]))
+    rr = O.rev_solve(np.array([c[0] for c in cons], dtype=float), [c[2] for c in cons], g["objective"], False, want_binv=True)
+    labels = [f"x{e + 1}" if e < n else f"S{e - n + 1}" for e in rr["log"][:, 1].tolist()]
+    assert labels == rg["entering_labels"] and rr["basis"].tolist() == rg["basis"]
+    assert hashlib.sha256(rr["Binv"].tobytes()).hexdigest() == rg["binv_sha256"]
+    assert float(rr["z"]).hex() == rg["final_z"] and same_bits(rr["x"], unhex(rg["x"])) and same_bits(rr["xB"], unhex(rg["xb"]))
 
 
 # ------------------------------------------------------------------------------------------- the interpreter itself

@@ -220,3 +220,29 @@ def test_sensitivity_resolve_after_rhs_change(i):
         if g["exception"] is None:
             assert float(t.objective()).hex() == g["z_after"]
             assert_bits(t.sens_solution(), unhex(g["x_after"]), "solution")
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["mid_size"])))
+def test_mid_size_runs(i):
+    """12-15 pivots on 19x43 .. 41x69 tableaux: digests of what the reference's classes computed"""
+    g = GOLD["mid_size"][i]
+    n = len(g["objective"])
+    pg, rg = g["primal"], g["revised"]
+    s = L.PrimalSimplexSolver(g["objective"], constraints_of(g), True, trace=False)
+    assert hashlib.sha256(s.DeviceTableau.read().tobytes()).hexdigest() == pg["initial_tableau_sha256"]
+    s.Solve()
+    assert [list(p) for p in s.PivotLog] == pg["pivots"] and s.BasicVariables == pg["basis"]
+    assert list(s.FinalTableau.shape) == pg["final_tableau_shape"]
+    assert hashlib.sha256(np.ascontiguousarray(s.FinalTableau).tobytes()).hexdigest() == pg["final_tableau_sha256"]
+    assert float(s.FinalZ).hex() == pg["final_z"]
+    assert_bits(s.SolutionVector, unhex(pg["x"]), "SolutionVector")
+    rv = L.RevisedPrimalSimplexSolver(g["objective"], constraints_of(g), False, trace=False)
+    try:
+        rv.Solve()
+        labels = [f"x{e + 1}" if e < n else f"S{e - n + 1}" for _, e, _ in rv.PivotLog]
+        assert labels == rg["entering_labels"] and rv.BasicVariables == rg["basis"]
+        z, x = float.fromhex(rg["final_z"]), unhex(rg["x"])
+        assert abs(rv.FinalZ - z) <= 1e-9 * abs(z)
+        assert np.allclose(rv.SolutionVector, x, rtol=1e-9, atol=1e-9 * float(np.abs(x).max()))
+    finally:
+        rv.close()
