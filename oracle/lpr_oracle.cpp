@@ -5,8 +5,12 @@
  * cites the reference file:line it follows (relative to /root/reference/LPR_381_Group_V22/).
  * Arithmetic model: IEEE binary64, round-to-nearest-even, multiply and subtract as separate
  * roundings (RyuJIT never contracts to FMA) => build with -ffp-contract=off.
- * Parity is pinned to restated known answers, not to executed C#:
- * the reference ships no tests and cannot be built in this image.
+ * Pinning: the reference ships no tests and no .NET toolchain exists in this image, so the reference's
+ * own .cs files are EXECUTED by the C# interpreter under oracle/csharp/ (tests/golden/make_reference_run.py)
+ * and every function here is compared bit for bit with what the reference's classes returned
+ * (tests/golden/reference_run.json, tests/test_reference_run.py), on top of the restated known answers of
+ * SURVEY.md Appendix C (tests/test_oracle_golden.py).  The knapsack functions have no reference body to run
+ * (missing upstream) and stay pinned to DP equality, the reference's own check (Program.cs:467-470).
  */
 #include "lpr_oracle.h"
 

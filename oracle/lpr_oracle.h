@@ -14,13 +14,19 @@
  *
  * Parity pinning: the reference ships NO tests, golden vectors or expected outputs
  *  and cannot be compiled here (no .NET toolchain; Program.cs:444,468 do not
- * compile anyway).  The oracle is pinned against (1) the only result check the reference
- * has -- knapsack B&B value == DP value, Program.cs:467-470, (2) the reference's shipped
- * fixtures (data/TextFile.txt, README model, Program.cs:433-435) whose known answers were
- * derived independently in SURVEY.md Appendix C and are reproduced bit-for-bit by
- * tests/test_oracle_golden.py, and (3) scipy HiGHS objective cross-checks.  Because no
- * executed-C# output exists, DESIGN.md states "parity pinned to restated known answers,
- * not to executed reference output".
+ * compile anyway).  The oracle is therefore pinned to the reference EXECUTED by other means:
+ * (0) oracle/csharp/ is a C# interpreter that runs the reference's own, unmodified .cs files in
+ * the build container; tests/golden/make_reference_run.py records what every solver class
+ * returned on the reference's fixtures and on seeded models (tests/golden/reference_run.json)
+ * and tests/test_reference_run.py compares every function below with that, bit for bit;
+ * (1) the only result check the reference has -- knapsack B&B value == DP value,
+ * Program.cs:467-470 (the knapsack bodies are missing upstream, so there is nothing to execute);
+ * (2) the reference's shipped fixtures (data/TextFile.txt, README model, Program.cs:433-435)
+ * whose known answers were derived independently in SURVEY.md Appendix C and are reproduced
+ * bit-for-bit by tests/test_oracle_golden.py; (3) scipy HiGHS objective cross-checks.
+ * What (0) does not give: output of the CLR itself -- the interpreter restates the C# semantics
+ * and the BCL rules it needs (listed in oracle/csharp/csrun.py); the arithmetic is the same
+ * IEEE binary64 in both.
  */
 #ifndef LPR_ORACLE_H
 #define LPR_ORACLE_H
