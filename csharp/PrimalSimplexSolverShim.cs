@@ -79,7 +79,16 @@ namespace LPR_381_Group_V22.Simplex
                 Lpr.Check(Lpr.lpr_tab_extract_solution(tab.DangerousGetHandle(), numVariables, x));
                 SolutionVector = x.ToList();
                 Console.WriteLine("Optimal Solution Found!");
-                if (trace) IterationSnapshots.Add(TableIterationFormater.Format(FinalTableau, numVariables, "Final Tableau (Optimal)"));
+                if (trace)
+                {
+                    // :118-122: the last snapshot is the final tableau followed by the solution summary
+                    var finalBlock = new StringBuilder();
+                    finalBlock.AppendLine(TableIterationFormater.Format(FinalTableau, numVariables, "Final Tableau (Optimal)"));
+                    finalBlock.AppendLine(SolutionSummary());
+                    IterationSnapshots.Add(finalBlock.ToString());
+                }
+                Console.WriteLine(SolutionSummary());
+                Console.WriteLine(new string('-', 100));
             }
             else if (status == Lpr.UNBOUNDED)
             {
@@ -97,6 +106,16 @@ namespace LPR_381_Group_V22.Simplex
 
         private double[,] Read() { var t = new double[rows, cols]; Lpr.Check(Lpr.lpr_tab_read(tab.DangerousGetHandle(), t)); return t; }
         private string ColLabel(int col) => col < numVariables ? $"x{col + 1}" : $"t{col - numVariables + 1}";
+
+        private string SolutionSummary(string title = "Optimal solution")   // :256-267
+        {
+            var sb = new StringBuilder();
+            sb.AppendLine(title + ":");
+            sb.AppendLine($"Z = {FinalZ:F6}");
+            if (SolutionVector != null)
+                for (int i = 0; i < numVariables; i++) sb.AppendLine($"x{i + 1} = {SolutionVector[i]:F6}");
+            return sb.ToString();
+        }
         public void Dispose() { tab.Dispose(); }
     }
 }

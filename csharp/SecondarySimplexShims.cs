@@ -47,33 +47,57 @@ namespace LPR_381_Group_V22.Simplex
             tableau = RowTableau.Pack(objectiveRow, constraintRows);
         }
 
-        /// <summary>PrimalSimplexSolver2.Solve (:46-97).  printSteps keeps the reference's quirk that the iteration counter only
-        /// advances when printing (flags bit0); with printSteps the shim steps pivot by pivot to print/capture like the reference.</summary>
+        /// <summary>text snapshots (three per pivot, like the reference) only for console-sized tableaux</summary>
+        public static long TraceMaxElements = 4096;
+
+        /// <summary>PrimalSimplexSolver2.Solve (:46-97).  Below TraceMaxElements the loop steps pivot by pivot and records the
+        /// reference's snapshots ("Start of iter k", "Before pivot ...", "After pivot ...", :50-79) and console lines; above it
+        /// the whole loop is one native call.  Either way the iteration counter only advances when printing (:70), so
+        /// maxIters only bites with printSteps (flags bit0).</summary>
         public bool Solve(int maxIters = 10_000, bool printSteps = false)
         {
             Lpr.Check(Lpr.lpr_tab_create(0, rows, cols, 0, 0, tableau, out IntPtr h));
             using (var tab = new TabHandle(h))
             {
                 int status;
-                if (!printSteps)
+                if ((long)rows * cols > TraceMaxElements)
                 {
-                    Lpr.Check(Lpr.lpr_tab_solve(h, Lpr.RULE_PRIMAL2, maxIters, 0, out status, out long _, null, 0));
+                    Lpr.Check(Lpr.lpr_tab_solve(h, Lpr.RULE_PRIMAL2, maxIters, printSteps ? 1 : 0, out status, out long _, null, 0));
+                    Lpr.Check(Lpr.lpr_tab_read(h, tableau));
                 }
                 else
                 {
                     int iter = 0;
-                    Capture(h, "Initial");
                     while (true)
                     {
-                        if (iter >= maxIters) { status = Lpr.ITER_LIMIT; break; }
-                        Lpr.Check(Lpr.lpr_tab_step(h, Lpr.RULE_PRIMAL2, out int e, out int l, out status));
-                        if (status != Lpr.RUNNING) break;
-                        iter++;
-                        Console.WriteLine($"Iteration {iter}: pivot row {l}, column {e}");
-                        Capture(h, $"Iteration {iter}");
+                        CaptureSnapshot($"Start of iter {iter}");                                        // :50
+                        Lpr.Check(Lpr.lpr_tab_step(h, Lpr.RULE_PRIMAL2, out int pivotCol, out int pivotRow, out status));
+                        if (status != Lpr.RUNNING)
+                        {
+                            if (printSteps) Console.WriteLine(status == Lpr.OPTIMAL ? "Optimal reached." : "Unbounded: no valid leaving row.");
+                            break;
+                        }
+                        CaptureSnapshot($"Before pivot (iter {iter + 1}) at row {pivotRow}, col {pivotCol}");   // :68, tableau still pre-pivot
+                        if (printSteps)
+                        {
+                            Console.WriteLine($"\nIter {++iter}: pivot @ row {pivotRow}, col {pivotCol}");
+                            PrintTableau();
+                        }
+                        Lpr.Check(Lpr.lpr_tab_read(h, tableau));
+                        CaptureSnapshot($"After pivot (iter {iter}) at row {pivotRow}, col {pivotCol}");        // :79
+                        if (printSteps)
+                        {
+                            Console.WriteLine("After pivot:");
+                            PrintTableau();
+                        }
+                        if (iter >= maxIters)                                                            // :87-92
+                        {
+                            if (printSteps) Console.WriteLine("Max iterations reached.");
+                            status = Lpr.ITER_LIMIT;
+                            break;
+                        }
                     }
                 }
-                Lpr.Check(Lpr.lpr_tab_read(h, tableau));
                 if (status == Lpr.PIVOT_TOO_SMALL) throw new InvalidOperationException("Pivot too small/zero.");   // :148-149
                 _isOptimal = status == Lpr.OPTIMAL;
                 if (_isOptimal) FinalZ = tableau[0, cols - 1];
@@ -81,15 +105,22 @@ namespace LPR_381_Group_V22.Simplex
             }
         }
 
-        private void Capture(IntPtr h, string title)   // :167-181, "0.###" = NumFormat-free custom format
+        private void CaptureSnapshot(string title)   // :167-181 on the host copy of the tableau
         {
-            Lpr.Check(Lpr.lpr_tab_read(h, tableau));
             var sb = new StringBuilder();
             if (!string.IsNullOrWhiteSpace(title)) sb.AppendLine(title);
             sb.AppendLine("Current Tableau:");
-            for (int i = 0; i < rows; i++)
-                sb.AppendLine((i == 0 ? "OBJ" : $"r{i}") + "\t" + string.Join("\t", Enumerable.Range(0, cols).Select(j => tableau[i, j].ToString("0.###"))));
+            sb.AppendLine("OBJ\t" + string.Join("\t", Enumerable.Range(0, cols).Select(j => tableau[0, j].ToString("0.###"))));
+            for (int i = 1; i < rows; i++)
+                sb.AppendLine($"r{i}\t" + string.Join("\t", Enumerable.Range(0, cols).Select(j => tableau[i, j].ToString("0.###"))));
             IterationSnapshots.Add(sb.ToString());
+        }
+
+        private void PrintTableau()   // :183-188
+        {
+            Console.WriteLine("OBJ: " + string.Join("\t", Enumerable.Range(0, cols).Select(j => tableau[0, j].ToString("0.####"))));
+            for (int i = 1; i < rows; i++)
+                Console.WriteLine($"r{i}: " + string.Join("\t", Enumerable.Range(0, cols).Select(j => tableau[i, j].ToString("0.####"))));
         }
 
         public double[] GetObjectiveRow(bool solveIfNeeded = true)

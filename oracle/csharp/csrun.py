@@ -247,6 +247,7 @@ class CsClass:
     def __init__(self, decl, outer, interp):
         _, self.name, self.mods, self.bases, members, self.kind, self.ns = decl
         self.outer = outer
+        self.base_names = [b[1].split(".")[-1] for b in self.bases if b[0] == "type"]
         self.fields = {}        # name -> (type, init, static)
         self.field_order = []
         self.props = {}         # name -> decl
@@ -1094,7 +1095,7 @@ def type_name(ty):
     if ty is None or ty[0] != "type" or ty[3] or ty[4]:
         return None
     return {"float": "double", "Double": "double", "System.Double": "double", "Int32": "int", "long": "int",
-            "String": "string"}.get(ty[1], ty[1])
+            "String": "string", "Byte": "byte"}.get(ty[1], ty[1])
 
 
 def default_value(ty):
@@ -1107,7 +1108,7 @@ def default_value(ty):
     if ty[3] or ty[4]:
         return None
     n = ty[1]
-    if n in ("int", "long", "short", "byte", "uint", "ulong", "ushort", "sbyte", "Int32", "Int64"):
+    if n in ("int", "long", "short", "byte", "uint", "ulong", "ushort", "sbyte", "Int32", "Int64", "IntPtr"):
         return 0
     if n in ("double", "float", "decimal", "Double"):
         return 0.0
@@ -1146,6 +1147,7 @@ class Interpreter:
         self.now = now
         self.steps = 0
         self.max_steps = None
+        self.native = None     # P/Invoke target: an object with call(name, params, values, return_type)
 
     # ---- loading
     def register(self, c):
@@ -1212,6 +1214,9 @@ class Interpreter:
         self.ensure_static(cls)
         obj = CsObject(cls)
         env = Env(None, obj, cls)
+        if "SafeHandle" in cls.base_names:       # System.Runtime.InteropServices.SafeHandle: protected IntPtr handle
+            obj.f["handle"] = 0
+            obj.f["$released"] = False
         for nm in cls.field_order:
             ty, init, st = cls.fields[nm]
             if not st:
@@ -1300,6 +1305,10 @@ class Interpreter:
             if ty[0] == "type" and ty[1] in ("double", "float") and not ty[3]:
                 env.types[nm] = ty
         if body is None:
+            if "extern" in decl[1]:          # [DllImport] static extern: platform invoke
+                if self.native is None:
+                    raise RuntimeError(f"no native library bound for P/Invoke {decl[3]}")
+                return self.native.call(decl[3], ps, [env.vars[p[1]] for p in ps], rettype)
             return None
         if body[0] == "exprbody":
             return coerce(self.ev(body[1], env), rettype)
@@ -1307,6 +1316,33 @@ class Interpreter:
         if sig is not None and sig[0] == "ret":
             return coerce(sig[1], rettype)
         return None
+
+    def safehandle_call(self, obj, name, args):
+        """the members of SafeHandle a derived handle class inherits"""
+        if name == "SetHandle":
+            obj.f["handle"] = args[0]
+            return None
+        if name == "DangerousGetHandle":
+            return obj.f["handle"]
+        if name in ("Dispose", "Close"):
+            if not obj.f["$released"]:
+                obj.f["$released"] = True
+                if not self.get_member(obj, "IsInvalid", None):
+                    self.invoke(obj.cls, "ReleaseHandle", obj, [], {})
+            return None
+        if name == "SetHandleAsInvalid":
+            obj.f["$released"] = True
+            return None
+        raise AttributeError(f"SafeHandle has no member {name}")
+
+    def dispose(self, v):
+        if type(v) is CsObject:
+            if "Dispose" in v.cls.methods:
+                self.invoke(v.cls, "Dispose", v, [], {})
+            elif "SafeHandle" in v.cls.base_names:
+                self.safehandle_call(v, "Dispose", [])
+        elif v is not None and type(v) in (CsStringWriter, CsStreamWriter):
+            bcl_instance_call(self, v, "Dispose", [], {})
 
     # ---- statements
     def exec_block(self, stmts, env):
@@ -1458,8 +1494,17 @@ class Interpreter:
                 return sig
             return None
         if k == "using":
-            self.exec(s[1], env)
-            return self.exec(s[2], env)
+            res = s[1]
+            if res[0] == "local":
+                self.exec(res, env)
+                held = [env.vars[nm] for nm, _ in res[2]]
+            else:
+                held = [self.ev(res[1], env)]
+            try:
+                return self.exec(s[2], env)
+            finally:
+                for v in reversed(held):
+                    self.dispose(v)
         if k == "localfunc":
             m = s[1]
             interp = self
@@ -1840,6 +1885,8 @@ class Interpreter:
                 c = obj.cls
                 if name in c.methods:
                     return self.invoke(c, name, obj, args, named)
+                if "SafeHandle" in c.base_names and name not in obj.f:
+                    return self.safehandle_call(obj, name, args)
                 fld = self.get_member(obj, name, env)   # a delegate-typed field
                 return fld(*args)
             if t is NamespaceVal:
@@ -1864,6 +1911,8 @@ class Interpreter:
                 for c in cls.chain():
                     if name in c.methods:
                         return self.invoke(c, name, this if (this is not None and this.cls is c) else None, args, named)
+            if this is not None and "SafeHandle" in this.cls.base_names and name in ("SetHandle", "DangerousGetHandle", "Dispose"):
+                return self.safehandle_call(this, name, args)
             v = self.lookup(name, env)
             return v(*args)
         if f[0] == "base":
@@ -2220,7 +2269,7 @@ def eq_op(a, b):
 
 
 # ----------------------------------------------------------------------------------------------------- BCL surface
-BCL_TYPES = {"Math", "Console", "Enumerable", "String", "Array", "Tuple", "Convert", "CultureInfo", "File", "Path",
+BCL_TYPES = {"IntPtr", "Marshal", "Math", "Console", "Enumerable", "String", "Array", "Tuple", "Convert", "CultureInfo", "File", "Path",
              "Environment", "DateTime", "MidpointRounding", "StringSplitOptions", "NumberStyles", "Double", "Int32",
              "Encoding", "StringComparison", "Directory", "ValueTuple", "ConsoleColor", "Char", "GC", "Boolean"}
 LINQ_NAMES = {"ToList", "ToArray", "Select", "Where", "Any", "All", "Count", "Min", "Max", "Sum", "Average", "First",
@@ -2279,7 +2328,9 @@ def bcl_static_member(interp, tname, name):
     if tname == "Console" and name == "Out":
         return ConsoleOut(interp)
     if tname == "Encoding":
-        return name
+        return CsEncoding(name)
+    if tname == "IntPtr" and name == "Zero":
+        return 0
     # a method group: Select(Math.Abs), Select(NumFormat.N3) ...
     return lambda *args: bcl_static_call(interp, tname, name, list(args), {})
 
@@ -2287,6 +2338,19 @@ def bcl_static_member(interp, tname, name):
 class ConsoleOut:
     def __init__(self, interp):
         self.interp = interp
+
+
+class CsEncoding:
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __eq__(self, o):
+        return (isinstance(o, CsEncoding) and o.name == self.name) or o == self.name
+
+    def __hash__(self):
+        return hash(self.name)
 
 
 class CsDateTime:
@@ -2604,6 +2668,19 @@ def bcl_static_call(interp, tname, name, args, named):
             return True
         if name == "GetCurrentDirectory":
             return "."
+    if tname == "Marshal":
+        import ctypes
+        if name == "PtrToStringAnsi":
+            if not args[0]:
+                return None
+            raw = ctypes.string_at(args[0], args[1]) if len(args) > 1 else ctypes.string_at(args[0])
+            return raw.decode("utf-8")
+        if name == "Copy":          # Marshal.Copy(IntPtr source, byte[] destination, int startIndex, int length)
+            src, dst, start, n = args
+            dst.data[start:start + n] = list(ctypes.string_at(src, n))
+            return None
+    if tname == "IntPtr":
+        raise NotImplementedError(f"IntPtr.{name}")
     if tname == "Environment" and name == "Exit":
         raise SystemExit(args[0])
     if tname == "GC":
@@ -3015,6 +3092,20 @@ def bcl_instance_call(interp, obj, name, args, named):
             return obj.text
     elif t is ConsoleOut:
         return bcl_static_call(interp, "Console", name, args, named)
+    elif t is CsEncoding:
+        if name == "GetString":
+            data = args[0].data
+            if len(args) == 3:
+                if args[1] < 0 or args[2] < 0 or args[1] + args[2] > len(data):
+                    raise CsException("ArgumentOutOfRangeException", param="count")
+                data = data[args[1]:args[1] + args[2]]
+            return bytes(data).decode("utf-8", errors="replace")
+        if name == "GetBytes":
+            b = list(args[0].encode("utf-8"))
+            return CsArray("byte", (len(b),), b)
+        if name == "GetPreamble":
+            b = [0xEF, 0xBB, 0xBF] if obj.name == "UTF8" else []
+            return CsArray("byte", (len(b),), b)
     elif t is CsAnon:
         if name == "ToString":
             return cs_tostring(obj)

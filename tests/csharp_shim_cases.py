@@ -1,0 +1,285 @@
+"""The C# P/Invoke shims under csharp/ EXECUTED (oracle/csharp interpreter, P/Invoke through ctypes) and compared with
+what the reference's own classes returned on the same inputs (tests/golden/reference_run.json).
+
+Shared by tests/test_csharp_shims.py (CPU: host-only entry points hit the real liblprb200.so, compute entry points the
+oracle-backed test double tests/lprb200_double.py) and tests/test_csharp_shims_gpu.py (B200: everything hits the real
+library).  The shims are the drop-in a maintainer adds to the reference; the image has no .NET, so
+this is the only way they ever run here.
+"""
+import glob
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+from csharp import CsException, Interpreter  # noqa: E402
+from csharp.csrun import CsList, from_cs, to_array, to_array2d, to_list  # noqa: E402
+from csharp.pinvoke import NativeLibrary  # noqa: E402
+
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_run.json")))
+SHIMS = sorted(glob.glob(os.path.join(ROOT, "csharp", "*.cs")))
+
+
+def unmat(m):
+    return np.array([float.fromhex(h) for h in m["hex"]], dtype=np.float64).reshape(m["shape"])
+
+
+def unhex(v):
+    return np.array([float.fromhex(h) for h in v], dtype=np.float64)
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def sha(text):
+    return hashlib.sha256(text.encode("utf-8")).hexdigest()
+
+
+def real_library():
+    from lpr_381_group_v22_b200 import _native as N
+    return NativeLibrary(N.lib())
+
+
+class Shims:
+    """one interpreter with every file of csharp/ loaded and `native` bound"""
+
+    def __init__(self, native):
+        self.it = Interpreter()
+        self.it.native = native
+        for f in SHIMS:
+            self.it.load_file(f)
+
+    def constraints(self, cons):
+        it = self.it
+        return CsList([it.new("Constraint", to_list(co), rel, float(rhs)) for co, rel, rhs in cons], None)
+
+    @staticmethod
+    def rows(T):
+        return CsList([to_array(r) for r in T[1:]], None)
+
+    # ---- each returns the list of mismatches (empty = parity)
+    def primal(self, g, exact=True):
+        it, bad = self.it, []
+        it.console.clear()
+        s = it.new("PrimalSimplexSolver", to_list(g["objective"]), self.constraints(g["constraints"]), g["is_max"])
+        if not bits_equal(from_cs(it.call(s, "GetFinalTableau")), unmat(g["initial_tableau"])):
+            bad.append("initial tableau")
+        it.call(s, "Solve")
+        if not bits_equal(from_cs(it.get(s, "FinalTableau")), unmat(g["final_tableau"])):
+            bad.append("FinalTableau")
+        if from_cs(it.get(s, "BasicVariables")) != g["basis"]:
+            bad.append("BasicVariables")
+        if float(it.get(s, "FinalZ")).hex() != g["final_z"]:
+            bad.append("FinalZ")
+        x = it.get(s, "SolutionVector")
+        if g["x"] is None:
+            if x is not None:
+                bad.append("SolutionVector should stay null")
+        elif x is None or not bits_equal(from_cs(x), unhex(g["x"])):
+            bad.append("SolutionVector")
+        if sha(it.get(s, "FinalTable")) != g["final_table_sha256"]:
+            bad.append("FinalTable")
+        snaps = from_cs(it.get(s, "IterationSnapshots"))
+        if "snapshots" in g and snaps != g["snapshots"]:
+            bad.append("IterationSnapshots")
+        elif len(snaps) != g["n_snapshots"] or sha("".join(snaps)) != g["snapshots_sha256"]:
+            bad.append("IterationSnapshots (digest)")
+        it.call(s, "Dispose")
+        return bad, s
+
+    def primal2(self, g):
+        it, bad = self.it, []
+        T = unmat(g["tableau"]).tolist()
+        s = it.new("PrimalSimplexSolver2", to_array(T[0]), self.rows(T))
+        ok = it.call(s, "Solve", g["max_iters"], g["print_steps"])
+        if bool(ok) != g["returned"]:
+            bad.append(f"Solve returned {ok}")
+        rows = it.call(s, "GetRows", False)
+        if not bits_equal([from_cs(rows.vals[0])] + from_cs(rows.vals[1]), unmat(g["final_tableau"])):
+            bad.append("GetRows(false)")
+        if g["returned"] and float(it.get(s, "FinalZ")).hex() != g["final_z"]:
+            bad.append("FinalZ")
+        snaps = from_cs(it.get(s, "IterationSnapshots"))
+        if len(snaps) != g["n_snapshots"] or sha("".join(snaps)) != g["snapshots_sha256"]:
+            bad.append("IterationSnapshots")
+        return bad
+
+    def dual(self, g):
+        it, bad = self.it, []
+        T = unmat(g["tableau"]).tolist()
+        obj, rows = to_array(T[0]), self.rows(T)
+        s = it.new("DualSimplexSolver")
+        err = None
+        try:
+            ok = it.call(s, "Solve", obj, rows, g["max_iters"], g["print_steps"])
+        except CsException as e:
+            ok, err = None, e.tname
+        if err != g["exception"]:
+            bad.append(f"exception {err}")
+        if err is None and bool(ok) != g["returned"]:
+            bad.append(f"Solve returned {ok}")
+        if not bits_equal([from_cs(obj)] + from_cs(rows), unmat(g["final_tableau"])):
+            bad.append("rows after Solve")
+        return bad
+
+    def cutting_plane(self, g):
+        it, bad = self.it, []
+        T = unmat(g["tableau"]).tolist()
+        obj, rows = to_array(T[0]), self.rows(T)
+        s = it.new("CuttingPlaneSolver")
+        it.call(s, "CuttingPlaneSolution", obj, rows)
+        if not bits_equal([from_cs(obj)] + from_cs(rows), unmat(g["final_tableau"])):
+            bad.append("rows after CuttingPlaneSolution")
+        log = from_cs(it.get(s, "CutLog"))
+        k = len(g["cut_pivots_1based"])
+        if [[len(T) + j, c[1] + 1] for j, c in enumerate(log[:k])] != g["cut_pivots_1based"]:
+            bad.append("CutLog")
+        return bad
+
+    def revised(self, g, text=True):
+        it, bad = self.it, []
+        cons = [(g["A"][i], g["relations"][i], g["b"][i]) for i in range(len(g["A"]))]
+        s = it.new("RevisedPrimalSimplexSolver", to_list(g["c"]), self.constraints(cons), g["is_min"])
+        err = None
+        try:
+            it.call(s, "Solve")
+        except CsException as e:
+            err = e.message
+        if err != g["exception"]:
+            bad.append(f"exception {err!r}")
+        if from_cs(it.get(s, "BasicVariables")) != g["basis"]:
+            bad.append("BasicVariables")
+        if err is None:
+            z, x = float.fromhex(g["final_z"]), unhex(g["x"])
+            if abs(it.get(s, "FinalZ") - z) > 1e-9 * max(1.0, abs(z)):
+                bad.append("FinalZ")
+            if not np.allclose(from_cs(it.get(s, "SolutionVector")), x, rtol=1e-9, atol=1e-9 * max(1.0, float(np.abs(x).max()))):
+                bad.append("SolutionVector")
+            snaps = from_cs(it.get(s, "IterationSnapshots"))
+            if len(snaps) != g["n_snapshots"]:
+                bad.append(f"{len(snaps)} snapshots")
+            elif text and sha("".join(snaps)) != g["snapshots_sha256"]:
+                bad.append("IterationSnapshots text")
+        it.call(s, "Dispose")
+        return bad
+
+    def bb(self, g):
+        it, bad = self.it, []
+        pg = {"objective": g["objective"], "constraints": g["constraints"], "is_max": True}
+        it.console.clear()
+        p = it.new("PrimalSimplexSolver", to_list(pg["objective"]), self.constraints(pg["constraints"]), True)
+        it.call(p, "Solve")
+        if not bits_equal(from_cs(it.get(p, "FinalTableau")), unmat(g["root_tableau"])):
+            bad.append("root tableau")
+        res = it.call_static("BranchAndBoundAdapter", "SolveFromPrimal", p, g["enable_pruning"], g["is_min"])
+        x, z = from_cs(res.vals[0]), res.vals[1]
+        if not bits_equal(np.array(x, dtype=np.float64), unhex(g["x"])):
+            bad.append("x")
+        if float(z).hex() != g["z"]:
+            bad.append("z")
+        it.call(p, "Dispose")
+        return bad
+
+    def bb_formulate(self, g):
+        it, bad = self.it, []
+        s = it.new("DualSimplexSolverBB")
+        rows = CsList([to_list(r) for r in g["rows"]], None)
+        T = it.call(s, "FormulateTableau", to_list(g["objective"]), rows)
+        if not bits_equal(from_cs(T), unmat(g["tableau"])):
+            bad.append("FormulateTableau")
+        if [[float(v).hex() for v in r] for r in from_cs(rows)] != g["rows_after"]:
+            bad.append("caller's rows after FormulateTableau")
+        res = it.call(it.new("DualSimplexSolverBB"), "DoDualSimplex", to_list(g["objective"]),
+                      CsList([to_list(r) for r in g["rows"]], None), g["is_min"])
+        tabs, _dec, opt, pc, pr, _hdr = res.vals
+        if (opt is None) != (g["optimal_value"] is None):
+            bad.append("optimalValue null-ness")
+        elif opt is not None:
+            if float(opt).hex() != g["optimal_value"]:
+                bad.append("optimalValue")
+            if not bits_equal(from_cs(tabs.items[-1]), unmat(g["final_tableau"])):
+                bad.append("final tableau")
+            if from_cs(pc) != g["pivot_cols"] or from_cs(pr) != g["pivot_rows"]:
+                bad.append("pivot lists")
+        return bad
+
+    def sensitivity(self, g):
+        it, bad = self.it, []
+        p = it.new("PrimalSimplexSolver", to_list(g["objective"]), self.constraints(g["constraints"]), True)
+        it.call(p, "Solve")
+        s = it.new("SensitivityAnalyzer", it.get(p, "FinalTableau"), it.get(p, "SolutionVector"), it.get(p, "FinalZ"),
+                   it.get(p, "BasicVariables"))
+        err = None
+        try:
+            it.call(s, "AddNewConstraintNonInteractive", to_array(g["tech"]), float(g["rhs"]))
+        except CsException as e:
+            err = e.message
+        if err != g["exception"]:
+            bad.append(f"exception {err!r}")
+        if not bits_equal(from_cs(it.get(s, "CurrentTableau")), unmat(g["tableau_after"])):
+            bad.append("CurrentTableau")
+        if float(it.get(s, "CurrentZ")).hex() != g["z_after"]:
+            bad.append("CurrentZ")
+        it.call(s, "Dispose")
+        it.call(p, "Dispose")
+        return bad
+
+    def parser(self, g, tmp_path):
+        it, bad = self.it, []
+        path = os.path.join(str(tmp_path), "model.txt")
+        with open(path, "w", encoding="utf-8", newline="") as f:
+            f.write(g["text"])
+        it.console.clear()
+        p = it.new("InputFileParser")
+        err = None
+        try:
+            it.call(p, "ReadInputFile", path)
+        except CsException as e:
+            err = e.tname
+        if err != g["exception"]:
+            bad.append(f"exception {err}")
+            return bad
+        if err is not None:
+            return bad
+        if it.console_text() != g["console"]:
+            bad.append("console message")
+        if it.get(p, "ProblemType") != g["problem_type"]:
+            bad.append("ProblemType")
+        if not bits_equal(from_cs(it.get(p, "ObjectiveCoefficients")), unhex(g["objective"])):
+            bad.append("ObjectiveCoefficients")
+        cons = it.get(p, "Constraints").items
+        if len(cons) != len(g["constraints"]):
+            bad.append("Constraints.Count")
+        for c, (co, rel, rhs) in zip(cons, g["constraints"]):
+            if not bits_equal(from_cs(it.get(c, "Coefficients")), unhex(co)) or it.get(c, "Relation") != rel \
+                    or float(it.get(c, "RHS")).hex() != rhs:
+                bad.append("a constraint")
+        if from_cs(it.get(p, "SignRestrictions")) != g["signs"]:
+            bad.append("SignRestrictions")
+        return bad
+
+    def format_table(self):
+        g = GOLD["format"]
+        vals = unhex(g["values"])
+        k = len(vals) - len(vals) % 4
+        text = self.it.call_static("TableIterationFormater", "Format", to_array2d(vals[:k].reshape(-1, 4).tolist()), 2, "T")
+        return [] if text == g["table"] else ["TableIterationFormater.Format"]
+
+    def knapsack(self, capacity, weights, values):
+        it = self.it
+        s = it.new("KnapsackBranchBoundSimplex", int(capacity), to_array(weights), to_array(values))
+        best = it.call(s, "Solve")
+        items = it.call(s, "GetSelectedItemsOriginal")
+        dp = it.call_static("KnapsackBranchBoundSolver", "Solve", int(capacity), to_array([int(w) for w in weights], "int"),
+                            to_array([int(v) for v in values], "int"))
+        chosen = [it.get(i, "Id") for i in items.items]
+        return best, dp, chosen

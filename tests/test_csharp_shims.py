@@ -1,0 +1,197 @@
+"""CPU tests that EXECUTE the C# P/Invoke shims under csharp/ (the drop-in a maintainer adds to the reference,
+INTEGRATION.md) and hold them to what the reference's own classes returned (tests/golden/reference_run.json).
+
+The image has no .NET toolchain, so the shims were source-only until oracle/csharp/ could run them: the interpreter
+executes the shim classes, `[DllImport] static extern` calls go through ctypes with the CLR's default marshalling
+(oracle/csharp/pinvoke.py).  Here host-only entry points (parser, formatters) hit the REAL liblprb200.so and the compute
+entry points an oracle-backed test double (tests/lprb200_double.py); tests/test_csharp_shims_gpu.py runs the same cases
+against the real library for everything.  Also checked statically: every DllImport declaration against the prototype in
+include/lprb200.h, and that the shims release every native handle they create.
+"""
+import os
+import re
+
+import pytest
+
+import csharp_shim_cases as S
+from lprb200_double import OracleBackedDouble
+
+GOLD = S.GOLD
+ROOT = S.ROOT
+
+
+@pytest.fixture(scope="module")
+def shims():
+    double = OracleBackedDouble(S.real_library())
+    sh = S.Shims(double)
+    yield sh
+    assert double.handles == {}, "the shims leaked native handles"
+
+
+def test_every_shim_file_parses_and_declares_the_reference_class_surface():
+    from csharp.csparse import parse_source
+    classes = {}
+    for f in S.SHIMS:
+        unit = parse_source(open(f, encoding="utf-8-sig").read(), os.path.basename(f))
+        for c in unit[2]:
+            classes[c[1]] = c
+    for name in ("PrimalSimplexSolver", "PrimalSimplexSolver2", "DualSimplexSolver", "RevisedPrimalSimplexSolver",
+                 "CuttingPlaneSolver", "BranchBoundSimplexSolver", "BranchAndBoundAdapter", "SensitivityAnalyzer",
+                 "InputFileParser", "TableIterationFormater", "KnapsackBranchBoundSimplex", "KnapsackBranchBoundSolver"):
+        assert name in classes, name
+    nested = {m[1] for m in classes["BranchBoundSimplexSolver"][4] if m[0] == "class"}
+    assert {"DualSimplexSolverBB", "BranchAndBound", "TeeTextWriter"} <= nested
+
+
+C_KIND = {"int": "int", "int64_t": "long", "double": "double", "uint64_t": "ulong", "float": "float"}
+
+
+def _header_prototypes():
+    text = open(os.path.join(ROOT, "include", "lprb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos = {}
+    for ret, name, params in re.findall(r"\b(int|int64_t|const char\*|void)\s+(lpr_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        plist = [] if params.strip() in ("", "void") else [" ".join(p.split()) for p in params.split(",")]
+        kinds = []
+        for p in plist:
+            if "*" in p:
+                kinds.append("pointer")
+            else:
+                kinds.append(C_KIND.get(p.split()[-2] if len(p.split()) > 1 else p.split()[0], p))
+        protos[name] = (ret, kinds)
+    return protos
+
+
+def test_dllimport_declarations_match_the_c_header():
+    from csharp.csparse import parse_source
+    unit = parse_source(open(os.path.join(ROOT, "csharp", "LprNative.cs"), encoding="utf-8-sig").read(), "LprNative.cs")
+    lpr = [c for c in unit[2] if c[1] == "Lpr"][0]
+    protos = _header_prototypes()
+    seen = 0
+    for m in lpr[4]:
+        if m[0] != "method" or "extern" not in m[1]:
+            continue
+        name, params, ret = m[3], m[4], m[2]
+        assert name in protos, f"{name} is not declared in include/lprb200.h"
+        cret, kinds = protos[name]
+        assert len(params) == len(kinds), f"{name}: {len(params)} managed parameters, {len(kinds)} in the header"
+        assert (ret[1], cret) in (("int", "int"), ("IntPtr", "const char*"), ("long", "int64_t")), (name, ret[1], cret)
+        for (ty, pname, _d, mod), kind in zip(params, kinds):
+            managed_pointer = bool(ty[3]) or mod in ("out", "ref") or ty[1] in ("IntPtr", "string")
+            if kind == "pointer":
+                assert managed_pointer, f"{name}.{pname}: the header takes a pointer, the shim passes {ty[1]} by value"
+            else:
+                assert not managed_pointer and ty[1] == kind, f"{name}.{pname}: header {kind}, shim {ty[1]}"
+        seen += 1
+    assert seen >= 70
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["primal"])))
+def test_primal_simplex_solver_shim(shims, i):
+    bad, _ = shims.primal(GOLD["primal"][i])
+    assert bad == []
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["primal2"])))
+def test_primal_simplex_solver2_shim(shims, i):
+    assert shims.primal2(GOLD["primal2"][i]) == []
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["dual"])))
+def test_dual_simplex_solver_shim(shims, i):
+    assert shims.dual(GOLD["dual"][i]) == []
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["cutting_plane"])))
+def test_cutting_plane_solver_shim(shims, i):
+    assert shims.cutting_plane(GOLD["cutting_plane"][i]) == []
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["revised"])))
+def test_revised_primal_simplex_solver_shim(shims, i):
+    assert shims.revised(GOLD["revised"][i]) == []
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["bb"])))
+def test_branch_and_bound_adapter_shim(shims, i):
+    assert shims.bb(GOLD["bb"][i]) == []
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["bb_formulate"])))
+def test_dual_simplex_solver_bb_shim(shims, i):
+    assert shims.bb_formulate(GOLD["bb_formulate"][i]) == []
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["sensitivity"])))
+def test_sensitivity_analyzer_shim(shims, i):
+    assert shims.sensitivity(GOLD["sensitivity"][i]) == []
+
+
+def test_input_file_parser_and_formatter_shims_on_the_real_library(shims, tmp_path):
+    """no double involved: lpr_model_* and lpr_fmt_table are host code"""
+    before = len(shims.it.native.calls)
+    for k, g in enumerate(GOLD["parser"]):
+        d = tmp_path / f"p{k}"
+        d.mkdir()
+        assert shims.parser(g, d) == [], g["text"]
+    assert shims.format_table() == []
+    assert len(shims.it.native.calls) == before          # nothing was answered by the double
+    assert "lpr_model_parse_file" in shims.it.native.real.calls and "lpr_fmt_table" in shims.it.native.real.calls
+
+
+def test_run_branch_and_bound_entry_shim(shims):
+    """BranchAndBound.RunBranchAndBound (:1253-1298) on model A == the reference's menu path result (Appendix C3)"""
+    from csharp.csrun import CsList, to_list
+    it = shims.it
+    bb = it.new("BranchAndBound")
+    it.console.clear()
+    it.call(bb, "RunBranchAndBound", to_list([2, 3, 3, 5, 2, 4]), CsList([to_list([11, 8, 6, 14, 10, 10, 40, 0])], None), False)
+    assert "Best integer solution: z = 15" in it.console_text()
+    # AddConstraint on a rounded tableau == the oracle's (the double answers, so this checks the shim's marshalling)
+    g = GOLD["bb"][0]
+    root = S.unmat(g["root_tableau"])
+    it.call(bb, "SetNumVars", g["n_vars"])
+    first = g["nodes"][0]
+    row = [1.0 if j == first["branch_var"] else 0.0 for j in range(g["n_vars"])] + [0.0, 0.0]
+    out = it.call(bb, "AddConstraint", CsList([to_list(row)], None), CsList([to_list(r) for r in root.tolist()], None))
+    import oracle_lib as O
+    assert S.bits_equal(S.from_cs(out.vals[0]), O.bb_add_constraint(O.bb_round(root), g["n_vars"], first["branch_var"], 0.0, 0))
+
+
+def test_knapsack_shims(shims):
+    import oracle_lib as O
+    w, v, cap = O.gen_knapsack(384, 40)
+    best, dp, chosen = shims.knapsack(cap, w.tolist(), v.tolist())
+    assert best == dp                                   # the reference's own check, Program.cs:467-470
+    assert sum(v[i] for i in chosen) == best and sum(w[i] for i in chosen) <= cap
+
+
+def test_compute_shims_fail_loudly_without_a_gpu():
+    """with the REAL library and no CUDA device every compute shim throws InvalidOperationException("liblprb200: ...")
+    from its first native call: the managed arguments were marshalled, the library answered, nothing fell back"""
+    import lpr_381_group_v22_b200 as L
+    if L.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from csharp import CsException
+    from csharp.csrun import CsList, to_array, to_list
+    sh = S.Shims(S.real_library())
+    it = sh.it
+    g = GOLD["primal"][0]
+    T = S.unmat(GOLD["primal2"][0]["tableau"]).tolist()
+    attempts = {
+        "PrimalSimplexSolver": lambda: it.new("PrimalSimplexSolver", to_list(g["objective"]), sh.constraints(g["constraints"]), True),
+        "PrimalSimplexSolver2": lambda: it.call(it.new("PrimalSimplexSolver2", to_array(T[0]), sh.rows(T)), "Solve"),
+        "DualSimplexSolver": lambda: it.call(it.new("DualSimplexSolver"), "Solve", to_array(T[0]), sh.rows(T), 10, False),
+        "CuttingPlaneSolver": lambda: it.call(it.new("CuttingPlaneSolver"), "CuttingPlaneSolution", to_array(T[0]), sh.rows(T)),
+        "RevisedPrimalSimplexSolver": lambda: it.new("RevisedPrimalSimplexSolver", to_list([1, 2]),
+                                                     sh.constraints([([1, 1], "<=", 4)]), False),
+        "DualSimplexSolverBB": lambda: it.call(it.new("DualSimplexSolverBB"), "FormulateTableau", to_list([1, 2]),
+                                               CsList([to_list([1, 1, 4, 0])], None)),
+        "KnapsackBranchBoundSolver": lambda: it.call_static("KnapsackBranchBoundSolver", "Solve", 10, to_array([3, 4], "int"),
+                                                            to_array([5, 6], "int")),
+    }
+    for name, attempt in attempts.items():
+        with pytest.raises(CsException) as err:
+            attempt()
+        assert err.value.tname == "InvalidOperationException" and err.value.message.startswith("liblprb200: "), name
