@@ -283,3 +283,36 @@ class Shims:
                             to_array([int(v) for v in values], "int"))
         chosen = [it.get(i, "Id") for i in items.items]
         return best, dp, chosen
+
+
+def run_all_against_real_library():
+    """every compute case against the real liblprb200.so; {category: {index: [mismatches]}} -- run in a child process by
+    tests/test_csharp_shims_gpu.py so that nothing the interop layer does can take the pytest process down"""
+    sh = Shims(real_library())
+    out = {}
+    plan = [("primal", lambda g: sh.primal(g)[0]), ("primal2", sh.primal2), ("dual", sh.dual),
+            ("cutting_plane", sh.cutting_plane), ("revised", lambda g: sh.revised(g, text=False)), ("bb", sh.bb),
+            ("bb_formulate", sh.bb_formulate), ("sensitivity", sh.sensitivity)]
+    for name, fn in plan:
+        res = {}
+        for i, g in enumerate(GOLD[name]):
+            try:
+                res[str(i)] = fn(g)
+            except Exception as e:      # an interpreter / interop error is a finding too, not a crash of the run
+                res[str(i)] = [f"{type(e).__name__}: {e}"[:300]]
+        out[name] = res
+    from lpr_381_group_v22_b200.bench_workloads import gen_knapsack
+    w, v, cap = gen_knapsack(384, 40)
+    try:
+        best, dp, chosen = sh.knapsack(cap, w.tolist(), v.tolist())
+        ok = best == dp and sum(v[i] for i in chosen) == best and sum(w[i] for i in chosen) <= cap
+        out["knapsack"] = {"0": [] if ok else [f"B&B {best} vs DP {dp}"]}
+    except Exception as e:
+        out["knapsack"] = {"0": [f"{type(e).__name__}: {e}"[:300]]}
+    out["native_calls"] = sorted(set(sh.it.native.calls))
+    return out
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, ROOT)
+    print("SHIM_RESULTS " + json.dumps(run_all_against_real_library()))
