@@ -1,6 +1,6 @@
 // Replacement bodies for IntegerProgramming/BranchBoundSimplexSolver.cs: DualSimplexSolverBB (:12-469), TeeTextWriter
 // (:471-487) and BranchAndBound (:490-1312).  List<List<double>> tableaux are marshalled as rectangular arrays; every
-// pivot, AddConstraint and the tree search itself run in liblprb200.  Source only (no .NET toolchain in the build image).
+// pivot, AddConstraint and the tree search itself run in liblprb200.  Not compiled here (no .NET toolchain in the build image); executed by tests/test_csharp_shims*.py.
 using LPR_381_Group_V22.Native;
 using System;
 using System.Collections.Generic;

@@ -1,6 +1,6 @@
 // Replacement body for IntegerProgramming/CuttingPlaneSolver.cs:64-229.  The whole recursion (Gomory row generated on the
 // device, cut pivot, dual then primal clean-up, next cut) is one native call; objectiveRow / constraintRows are mutated in
-// place and the cut rows appended, exactly what the reference's in-place version leaves behind.  Source only (no .NET here).
+// place and the cut rows appended, exactly what the reference's in-place version leaves behind.  Not compiled here (no .NET); executed by tests/test_csharp_shims*.py.
 using LPR_381_Group_V22.Native;
 using LPR_381_Group_V22.Simplex;
 using System;

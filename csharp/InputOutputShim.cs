@@ -1,6 +1,6 @@
 // InputOutputShim.cs -- replacements for IO/InputFileParser.cs (ReadInputFile :19-68, Constraint :70-82) and
 // Utilities/TableIterationFormater.cs (Format :19-48) over liblprb200 (SURVEY 8f rows 2-3).  Same public members
-// and signatures as the reference's classes; source only (no .NET toolchain in the build image) -- the same entry points are driven by
+// and signatures as the reference's classes; not compiled here (no .NET toolchain), executed by tests/test_csharp_shims.py -- the same entry points are driven by
 // lpr_381_group_v22_b200/io.py, utilities.py and host/lpr_solvers.hpp in the tests.
 using System;
 using System.Collections.Generic;

@@ -1,5 +1,5 @@
 // LprNative.cs -- P/Invoke binding of liblprb200 (include/lprb200.h).  Drop into the reference project
-// (LPR_381_Group_V22/Native/); cannot be compiled in the build image (no .NET toolchain) -- see INTEGRATION.md.
+// (LPR_381_Group_V22/Native/); cannot be compiled in the build image (no .NET toolchain); executed by the interpreter of oracle/csharp -- see INTEGRATION.md.
 using System;
 using System.Runtime.InteropServices;
 

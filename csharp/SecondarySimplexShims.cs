@@ -1,6 +1,6 @@
 // Replacement bodies for Simplex/PrimalSimplexSolver2.cs (:24-229) and Simplex/DualSimplex.cs (:14-241): the pivot loops
 // run on the GPU through lpr_tab_solve(rule = PRIMAL2 / DUAL); signatures, in-place semantics and exceptions are the
-// reference's.  Source only: the build image has no .NET toolchain (INTEGRATION.md).
+// reference's.  Not compiled here (no .NET toolchain); executed by tests/test_csharp_shims*.py (INTEGRATION.md).
 using LPR_381_Group_V22.Native;
 using LPR_381_Group_V22.Utilities;
 using System;
