@@ -195,3 +195,48 @@ def test_compute_shims_fail_loudly_without_a_gpu():
         with pytest.raises(CsException) as err:
             attempt()
         assert err.value.tname == "InvalidOperationException" and err.value.message.startswith("liblprb200: "), name
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/LPR_381_Group_V22"), reason="needs the reference's own .cs files (build container only)")
+def test_reference_files_run_unchanged_on_top_of_the_shims():
+    """the deployment INTEGRATION.md describes: the solver classes are replaced by the shims, everything else stays the
+    reference's file -- here OutputFileWrite.cs, CanonicalFormConverter.cs, NumFormat and Program.AddUpperBoundConstraints,
+    unmodified, consume the shim classes' members and must write the very files the all-reference run wrote"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_run", os.path.join(S.HERE, "golden", "make_reference_run.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    double = OracleBackedDouble(S.real_library())
+    sh = S.Shims(double)                                  # shim classes are registered first and win name lookups
+    for f in ("IO/OutputFileWrite.cs", "Utilities/CanonicalFormConverter.cs", "Simplex/RevisedPrimalSimplexSolver.cs", "Program.cs"):
+        sh.it.load_file(gen.REF + f)
+    assert sh.it.find_class("PrimalSimplexSolver").methods["Solve"][0][5] is not None
+    assert "lpr_tab_create_primal" in open(os.path.join(ROOT, "csharp", "PrimalSimplexSolverShim.cs")).read()
+    run = gen.Runner.__new__(gen.Runner)
+    run.it = sh.it
+    import tempfile
+    for g in GOLD["output"]:
+        with tempfile.TemporaryDirectory() as d:        # the shim parser is native code: it reads a real file
+            path = os.path.join(d, "model.txt")
+            with open(path, "w", encoding="utf-8", newline="") as f:
+                f.write(g["text"])
+            rec = _output_through_shims(run, path, g)
+        for key in ("rows_added", "canonical_form", "snapshots", "final_z", "x", "file_after_full_results", "file_after_append"):
+            assert rec[key] == g[key], key
+    assert "lpr_tab_step" in double.calls and "lpr_model_parse_file" in double.real.calls
+
+
+def _output_through_shims(run, model_path, g):
+    """Runner.output of the generator with the model read from a real file (the shim parser is native code)"""
+    it = run.it
+    orig_call = it.call
+
+    def call(obj, method, *args, **named):
+        if method == "ReadInputFile":
+            args = (model_path,)
+        return orig_call(obj, method, *args, **named)
+    it.call = call
+    try:
+        return run.output(g["text"], g["solver"], g["add_upper_bound_rows"])
+    finally:
+        it.call = orig_call
