@@ -238,6 +238,40 @@ class Runner:
                     "pivot_rows": from_cs(pr) if pr is not None else None})
         return rec
 
+    def bb_parts(self, T, n, var, bound, typ):
+        """the members ExecuteBranchAndBound is made of, one by one, on an arbitrary tableau"""
+        it = self.it
+        it.console.clear()
+
+        def ll(rows):
+            return CsList([to_list(r) for r in rows], None)
+        bbo = it.new("BranchAndBound")
+        it.call(bbo, "SetNumVars", n)
+        rounded = from_cs(it.call(bbo, "RoundTableau", ll(T)))
+        basic = from_cs(it.call(bbo, "IdentifyBasicVariables", CsList([ll(rounded)], None)))
+        row = [1.0 if j == var else 0.0 for j in range(n)] + [float(bound), float(typ)]
+        added = it.call(bbo, "AddConstraint", CsList([to_list(row)], None), ll(T))
+        vi = it.call(bbo, "CheckIntegerBasicVar", CsList([ll(rounded)], None))
+        x = from_cs(it.call(bbo, "ExtractSolution", CsList([ll(rounded)], None)))
+        s = it.new("DualSimplexSolverBB")
+        dp = it.call(s, "PerformDualPivot", ll(rounded))
+        pp = it.call(s, "PerformPrimalPivot", ll(rounded), False)
+        pm = it.call(s, "PerformPrimalPivot", ll(rounded), True)
+        return {"tableau": mat(T), "n_vars": n, "var": var, "bound": bound, "type": typ,
+                "rounded": mat(rounded), "identify_basic": basic, "add_constraint": mat(from_cs(added.vals[0])),
+                "branch_var": vi.vals[0] if vi.vals[0] is not None else -1,
+                "branch_value": hx(vi.vals[1]) if vi.vals[1] is not None else None, "extract": hexes(x),
+                "dual_pivot": mat(from_cs(dp.vals[0])) if dp.vals[1] is not None else None,
+                "primal_pivot": mat(from_cs(pp.vals[0])) if pp.vals[0] is not None else None,
+                "primal_pivot_min": mat(from_cs(pm.vals[0])) if pm.vals[0] is not None else None}
+
+    def rounding(self, values):
+        it = self.it
+        bbo = it.new("BranchAndBound")
+        return {"values": hexes(values), "round4": [hx(it.call(bbo, "RoundNumber", float(v))) for v in values],
+                "is_integer": [bool(it.call(bbo, "IsInteger", float(v))) for v in values],
+                "frac": [hx(it.call_static("CuttingPlaneSolver", "Frac", float(v))) for v in values]}
+
     # ------------------------------------------------------------------ SensitivityAnalyzer
     def sensitivity(self, objective, cons, tech, rhs):
         it = self.it
@@ -477,6 +511,25 @@ def generate():
             fm.append({"objective": obj, "rows": rows, "is_min": case % 3 == 2, "error": str(e)[:120]})
         run.it.max_steps = None
     out["bb_formulate"] = fm
+
+    # ---- the parts of the B&B node step on adversarial tableaux: columns that sum to 1 without being unit columns
+    # (SURVEY Q11), entries a hair off 0 / 1, ties of the 4-d.p. rounding, negative right-hand sides
+    pool = [0, 0, 0, 0, 1, 1, -1, 0.5, 0.25, 0.3333, 2, 1e-5, 0.99995, 1.00004, 0.33335, -0.00005, 3, 7.5, 0.66665]
+    parts = []
+    rng2 = random.Random(382)       # its own stream: sections added later must not shift the inputs of earlier ones
+    for case in range(40):
+        R_, C_ = rng2.randint(3, 7), rng2.randint(5, 10)
+        n = rng2.randint(2, C_ - 2)
+        T = [[float(rng2.choice(pool)) for _ in range(C_)] for _ in range(R_)]
+        for i in range(1, R_):
+            if rng2.random() < 0.6:
+                T[i][-1] = float(rng2.choice([2.5, 3, 0.75, 1.99995, 4.00004, -1.5, 0, 6.5]))
+        parts.append(run.bb_parts(T, n, rng2.randrange(n), float(rng2.randint(0, 5)), rng2.choice([0, 1])))
+    out["bb_parts"] = parts
+    out["rounding"] = run.rounding(
+        [0.00005, 0.00015, -0.00005, 2.5e-5, 12345.67895, -0.99995, 0.5, 1.5, 2.5, -0.5, -2.5, 1e16, 2.675, 1.00005,
+         0.49999999999999994, 4503599627370497.0, 3.0, -3.0, 2.9999999999, -0.2, 7.000000001, 0.9999995, 1.0000005,
+         123.45675, 123.45685, -7.00005, 1e-7, -1e-7] + [round(rng2.uniform(-50, 50), 5) for _ in range(30)])
 
     # ---- sensitivity re-optimisation
     se = []

@@ -46,7 +46,7 @@ def test_golden_covers_the_reference_fixtures_and_every_solver():
     assert len(GOLD["meta"]["reference_sources"]) == 13
     for key, least in (("parser", 9), ("primal", 28), ("primal2", 16), ("dual", 16), ("cutting_plane", 12),
                        ("revised", 20), ("bb", 13), ("bb_formulate", 6), ("sensitivity", 12), ("sensitivity_rhs", 6),
-                       ("output", 3), ("mid_size", 3)):
+                       ("output", 3), ("mid_size", 3), ("bb_parts", 40)):
         assert len(GOLD[key]) >= least, key
     # data/TextFile.txt parsed by the reference's own InputFileParser
     p = GOLD["parser"][0]
@@ -200,6 +200,44 @@ def test_dual_simplex_solver_bb_formulate_and_solve(i):
         assert same_bits(r["T"], unmat(g["final_tableau"]))
         assert float(r["T"][0, -1]).hex() == g["optimal_value"]
         assert r["log"][:, 0].tolist() == g["pivot_rows"] and r["log"][:, 1].tolist() == g["pivot_cols"]
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["bb_parts"])))
+def test_branch_and_bound_members_one_by_one(i):
+    """RoundTableau, IdentifyBasicVariables, AddConstraint, CheckIntegerBasicVar, ExtractSolution, PerformDualPivot and
+    PerformPrimalPivot (both senses) of the reference, executed on adversarial tableaux: columns that sum to 1 without
+    being unit columns, entries a hair off 0 and 1, rounding ties, negative right-hand sides"""
+    g = GOLD["bb_parts"][i]
+    T = unmat(g["tableau"])
+    Tr = O.bb_round(T)
+    assert same_bits(Tr, unmat(g["rounded"]))
+    assert O.bb_identify_basic(Tr).tolist() == g["identify_basic"]
+    assert same_bits(O.bb_add_constraint(T, g["n_vars"], g["var"], g["bound"], g["type"]), unmat(g["add_constraint"]))
+    var, val = O.bb_branch_var(Tr, g["n_vars"])
+    assert var == g["branch_var"] and (var < 0 or float(val).hex() == g["branch_value"])
+    assert same_bits(O.bb_extract(Tr, g["n_vars"]), unhex(g["extract"]))
+    ok, out, _, _ = O.bb_dual_pivot(Tr)
+    assert bool(ok) == (g["dual_pivot"] is not None) and (not ok or same_bits(out, unmat(g["dual_pivot"])))
+    ok, out, _, _ = O.bb_primal_pivot(Tr)
+    assert bool(ok) == (g["primal_pivot"] is not None) and (not ok or same_bits(out, unmat(g["primal_pivot"])))
+    # isMinimization = true has no single-pivot function in the oracle: one pivot of its DoDualSimplex state machine is
+    # the same pivot when no RHS is negative before or after it (no dual phase, no "drop the last tableau"), up to the
+    # -0.0 -> 0.0 clean-up DoDualSimplex applies to every tableau (:307-313)
+    if g["primal_pivot_min"] is not None and not (Tr[1:, -1] < -1e-9).any():
+        want = unmat(g["primal_pivot_min"])
+        if not (want[:, -1] < 0).any():
+            r = O.bb_node_solve_ex(Tr, True, max_pivots=1)
+            assert r["n_pivots"] == 1 and same_bits(r["T"] + 0.0, want + 0.0)
+
+
+def test_rounding_rules():
+    """Math.Round(x, 4) as BranchAndBound.RoundNumber calls it, IsInteger, CuttingPlaneSolver.Frac"""
+    g = GOLD["rounding"]
+    vals = unhex(g["values"])
+    lib = O.lib()
+    assert [float(lib.orc_net_round4(float(v))).hex() for v in vals] == g["round4"]
+    assert [float(lib.orc_frac(float(v))).hex() for v in vals] == g["frac"]
+    assert [abs(lib.orc_net_round4(float(v)) - lib.orc_net_round(lib.orc_net_round4(float(v)))) <= 1e-6 for v in vals] == g["is_integer"]
 
 
 # ------------------------------------------------------------------------------------------- sensitivity
