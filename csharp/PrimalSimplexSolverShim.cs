@@ -56,14 +56,19 @@ namespace LPR_381_Group_V22.Simplex
             if (trace)
             {
                 int iteration = 0;
+                var before = Read();
                 while (true)
                 {
                     Lpr.Check(Lpr.lpr_tab_step(tab.DangerousGetHandle(), Lpr.RULE_PRIMAL, out int e, out int r, out status));
                     if (status != Lpr.RUNNING) break;
+                    // the console lines of :137-146, in the reference's order (the pivot position is known after the step)
                     Console.WriteLine($"\nIteration {++iteration}: pivot @ constraint {r}, column {ColLabel(e)}");
+                    Console.WriteLine(TableIterationFormater.Format(before, numVariables, "Before pivot"));
                     var t = Read();
+                    Console.WriteLine($"After pivot (constraint {r}, column {ColLabel(e)}):");
                     Console.WriteLine(TableIterationFormater.Format(t, numVariables, "After pivot"));
                     IterationSnapshots.Add(TableIterationFormater.Format(t, numVariables, $"Iteration {iteration} - After pivot"));
+                    before = t;
                 }
             }
             else

@@ -24,6 +24,14 @@ namespace LPR_381_Group_V22.SensitivityAnalysis
             finalZ = zValue;
             Lpr.Check(Lpr.lpr_tab_create(0, rows, cols, rows + HEADROOM, cols + HEADROOM, t, out h));
             Lpr.Check(Lpr.lpr_tab_sens_rebuild_basis(h));                       // :36
+            ValidateBinaryConstraints();                                        // :39
+        }
+
+        private void ValidateBinaryConstraints()                               // :43-51
+        {
+            for (int i = 0; i < Math.Min(solutionVector.Count, 6); i++)
+                if (Math.Abs(solutionVector[i] - Math.Round(solutionVector[i])) > 1e-9)
+                    Console.WriteLine($"Warning: x{i + 1} = {solutionVector[i]:0.###} violates binary constraint.");
         }
 
         public double[,] CurrentTableau
@@ -44,6 +52,7 @@ namespace LPR_381_Group_V22.SensitivityAnalysis
             var x = new double[cols - 1];
             Lpr.Check(Lpr.lpr_tab_sens_solution(h, x));
             solutionVector = new List<double>(x);
+            ValidateBinaryConstraints();                                        // :165
         }
 
         public void AddNewConstraintNonInteractive(double[] tech, double rhs)  // :609-659

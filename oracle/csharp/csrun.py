@@ -1148,6 +1148,9 @@ class Interpreter:
         self.steps = 0
         self.max_steps = None
         self.native = None     # P/Invoke target: an object with call(name, params, values, return_type)
+        self.out_writer = None  # Console.SetOut(user TextWriter)
+        self.base_dir = "C:\\LPR_381_Group_V22\\bin\\Debug\\"   # AppDomain.CurrentDomain.BaseDirectory
+        self.path_sep = "\\"
 
     # ---- loading
     def register(self, c):
@@ -1831,14 +1834,14 @@ class Interpreter:
     def e_member(self, e, env):
         obj = self.ev(e[1], env)
         if obj is None:
-            if e[3]:
+            if e[3] or chain_has_nullcond(e[1]):
                 return None
             return nullable_member(e[2])
         return self.get_member(obj, e[2], env)
 
     def e_index(self, e, env):
         obj = self.ev(e[1], env)
-        if obj is None and e[3]:
+        if obj is None and (e[3] or chain_has_nullcond(e[1])):
             return None
         idx = [self.ev(i, env) for i in e[2]]
         return self.get_index(obj, idx)
@@ -1872,7 +1875,7 @@ class Interpreter:
             obj = self.ev(f[1], env)
             name = f[2]
             if obj is None:
-                if f[3]:
+                if f[3] or chain_has_nullcond(f[1]):
                     return None
                 # an extension method called on null reaches the method: Enumerable.* throws ArgumentNullException
                 args, named = self.eval_args(e[2], env)
@@ -2154,6 +2157,22 @@ class Interpreter:
         raise TypeError("out variable outside an argument list")
 
 
+def chain_has_nullcond(e):
+    """`a?.B().C`: when a is null the WHOLE chain is null (ECMA-334 12.8.8), not only `a?.B()`"""
+    while True:
+        k = e[0]
+        if k == "member" or k == "index":
+            if e[3]:
+                return True
+            e = e[1]
+        elif k == "call":
+            e = e[1]
+        elif k == "paren":
+            return False
+        else:
+            return False
+
+
 def is_double_expr(e):
     k = e[0]
     if k == "lit":
@@ -2269,7 +2288,7 @@ def eq_op(a, b):
 
 
 # ----------------------------------------------------------------------------------------------------- BCL surface
-BCL_TYPES = {"IntPtr", "Marshal", "Math", "Console", "Enumerable", "String", "Array", "Tuple", "Convert", "CultureInfo", "File", "Path",
+BCL_TYPES = {"AppDomain", "IntPtr", "Marshal", "Math", "Console", "Enumerable", "String", "Array", "Tuple", "Convert", "CultureInfo", "File", "Path",
              "Environment", "DateTime", "MidpointRounding", "StringSplitOptions", "NumberStyles", "Double", "Int32",
              "Encoding", "StringComparison", "Directory", "ValueTuple", "ConsoleColor", "Char", "GC", "Boolean"}
 LINQ_NAMES = {"ToList", "ToArray", "Select", "Where", "Any", "All", "Count", "Min", "Max", "Sum", "Average", "First",
@@ -2331,6 +2350,8 @@ def bcl_static_member(interp, tname, name):
         return CsEncoding(name)
     if tname == "IntPtr" and name == "Zero":
         return 0
+    if tname == "AppDomain" and name == "CurrentDomain":
+        return CsAppDomain()
     # a method group: Select(Math.Abs), Select(NumFormat.N3) ...
     return lambda *args: bcl_static_call(interp, tname, name, list(args), {})
 
@@ -2338,6 +2359,17 @@ def bcl_static_member(interp, tname, name):
 class ConsoleOut:
     def __init__(self, interp):
         self.interp = interp
+
+
+class CsDirectoryInfo:
+    __slots__ = ("path",)
+
+    def __init__(self, path):
+        self.path = path
+
+
+class CsAppDomain:
+    pass
 
 
 class CsEncoding:
@@ -2462,11 +2494,49 @@ def bcl_static_call(interp, tname, name, args, named):
                 s = format_composite(args[0], rest)
             else:
                 s = cs_tostring(args[0])
-            interp.console.append(s + ("\r\n" if name == "WriteLine" else ""))
+            w = interp.out_writer
+            if w is None:
+                interp.console.append(s + ("\r\n" if name == "WriteLine" else ""))
+                return None
+            # Console.SetOut(user TextWriter): TextWriter funnels everything it does not override into Write(char)
+            def overload(mname, ptype):
+                for d in w.cls.methods.get(mname, []):
+                    if len(d[4]) == 1 and d[4][0][0][1] == ptype:
+                        return d
+                return None
+
+            def write_text(text):
+                d = overload("Write", "string")
+                if d is not None:
+                    interp.run_method(w.cls, d, 4, d[5], d[2], w, [text], {})
+                    return
+                d = overload("Write", "char")
+                for ch in text:
+                    interp.run_method(w.cls, d, 4, d[5], d[2], w, [ch], {})
+            if name == "WriteLine" and args:
+                d = overload("WriteLine", "string")
+                if d is not None:
+                    interp.run_method(w.cls, d, 4, d[5], d[2], w, [s], {})
+                    return None
+                write_text(s)
+                write_text("\r\n")
+                return None
+            if name == "WriteLine":
+                d = overload("Write", "char")
+                if d is not None:
+                    for ch in "\r\n":
+                        interp.run_method(w.cls, d, 4, d[5], d[2], w, [ch], {})
+                else:
+                    write_text("\r\n")
+                return None
+            write_text(s)
+            return None
+        if name == "SetOut":
+            interp.out_writer = args[0] if type(args[0]) is CsObject else None
             return None
         if name == "ReadLine":
             return interp.stdin.pop(0) if interp.stdin else None
-        if name in ("ReadKey", "Clear", "SetOut", "ResetColor", "Beep", "SetCursorPosition"):
+        if name in ("ReadKey", "Clear", "ResetColor", "Beep", "SetCursorPosition"):
             return None
     if tname in ("string", "String"):
         if name == "Join":
@@ -2494,6 +2564,8 @@ def bcl_static_call(interp, tname, name, args, named):
                 return "".join(cs_tostring(v) for v in iterate(args[0]))
             return "".join(cs_tostring(v) for v in args)
         if name == "Equals":
+            if len(args) > 2 and type(args[2]) is CsEnum and args[2].value in (1, 3, 5):
+                return args[0] is not None and args[1] is not None and args[0].lower() == args[1].lower()
             return args[0] == args[1]
         if name == "Compare":
             return cs_compare(args[0], args[1])
@@ -2650,7 +2722,7 @@ def bcl_static_call(interp, tname, name, args, named):
             return None
     if tname == "Path":
         if name == "Combine":
-            return "\\".join(a.rstrip("\\/") if i < len(args) - 1 else a for i, a in enumerate(args))
+            return interp.path_sep.join(a.rstrip("\\/") if i < len(args) - 1 else a for i, a in enumerate(args))
         if name == "GetFileName":
             return re.split(r"[\\/]", args[0])[-1]
         if name == "GetFileNameWithoutExtension":
@@ -2662,6 +2734,11 @@ def bcl_static_call(interp, tname, name, args, named):
         if name == "GetFullPath":
             return args[0]
     if tname == "Directory":
+        if name == "GetParent":
+            p = args[0]
+            if p.endswith(("\\", "/")):        # a trailing separator names the directory itself
+                return CsDirectoryInfo(p[:-1])
+            return CsDirectoryInfo(re.sub(r"[\\/][^\\/]*$", "", p))
         if name in ("CreateDirectory",):
             return None
         if name == "Exists":
@@ -2805,7 +2882,16 @@ def bcl_instance_member(interp, obj, name):
     if t is CsDateTime:
         return obj
     if t is ConsoleOut and name == "Encoding":
-        return "UTF8"
+        return CsEncoding("UTF8")
+    if t is CsAppDomain and name == "BaseDirectory":
+        return interp.base_dir
+    if t is CsDirectoryInfo:
+        if name == "FullName":
+            return obj.path
+        if name == "Parent":
+            return CsDirectoryInfo(re.sub(r"[\\/][^\\/]*$", "", obj.path))
+        if name == "Name":
+            return re.split(r"[\\/]", obj.path)[-1]
     # a method group on an instance: list.Add, sb.Append ...
     return lambda *args: bcl_instance_call(interp, obj, name, list(args), {})
 
@@ -3091,6 +3177,12 @@ def bcl_instance_call(interp, obj, name, args, named):
         if name == "ToString":
             return obj.text
     elif t is ConsoleOut:
+        if name in ("Write", "WriteLine"):      # the original Console.Out: never through Console.SetOut's writer
+            saved, interp.out_writer = interp.out_writer, None
+            try:
+                return bcl_static_call(interp, "Console", name, args, named)
+            finally:
+                interp.out_writer = saved
         return bcl_static_call(interp, "Console", name, args, named)
     elif t is CsEncoding:
         if name == "GetString":

@@ -45,8 +45,11 @@ def sha(text):
 
 
 def real_library():
+    """its own CDLL object: pinvoke sets restype / argtypes per call and must not touch the product binding's prototypes"""
+    import ctypes
     from lpr_381_group_v22_b200 import _native as N
-    return NativeLibrary(N.lib())
+    N.lib()                                   # fails loudly when the library is missing
+    return NativeLibrary(ctypes.CDLL(N.LIB_PATH))
 
 
 class Shims:

@@ -345,6 +345,28 @@ class Runner:
                 "x": hexes(from_cs(x)) if x is not None else None,
                 "file_after_full_results": first, "file_after_append": it.files[path]}
 
+    # ------------------------------------------------------------------ the application itself
+    def program(self, model_text, keys):
+        """Program.Main with a scripted keyboard: file name, menu choices ... (Console.ReadLine answers)"""
+        it = self.it
+        it.console.clear()
+        it.files.clear()
+        it.out_writer = None
+        root = it.base_dir.rstrip("\\/")
+        for _ in range(2):
+            root = re.sub(r"[\\/][^\\/]*$", "", root)
+        it.files[root + it.path_sep + "data" + it.path_sep + "model.txt"] = model_text
+        it.stdin = ["model.txt"] + list(keys)
+        err = None
+        try:
+            it.call_static("Program", "Main", None)
+        except CsException as e:
+            err = e.cs_tostring()
+        text = it.console_text()
+        return {"model": model_text, "keys": list(keys), "unhandled_exception": err, "console": text,
+                "console_sha256": sha(text), "output_file": it.files.get("data/output_results.txt"),
+                "keys_left": list(it.stdin)}
+
     # ------------------------------------------------------------------ parser / formatting
     def parse(self, text):
         it = self.it
@@ -563,6 +585,19 @@ def generate():
         run.output(texts[2], "Primal Simplex Algorithm", False),
         run.output("max 1.5 -2 0.25\n1 1 1 <= 4.5\n2 0.5 -1 <= 3\n0<=x1<=1 + x3 <= 1\n", "Primal Simplex Algorithm", True),
     ]
+
+    # ---- Program.Main, menu options 1-4 on the shipped model, each in its own session, plus the session that shows the
+    # reference's state leak: option 1 appends its 9-entry bound rows to the parser's list, so option 2 then throws
+    out["program"] = [run.program(texts[0], keys) for keys in
+                      (["1", "13", "7"], ["2", "7"], ["3", "7"], ["4", "7"], ["1", "13", "2"], ["9", "7"])]
+    for rec in out["program"]:
+        if len(rec["console"]) > 20000:       # the B&B session prints every tableau of every node: keep head, tail, digest
+            rec["console_head"], rec["console_tail"] = rec["console"][:3000], rec["console"][-3000:]
+            del rec["console"]
+        if rec["output_file"] is not None and len(rec["output_file"]) > 20000:
+            rec["output_file_sha256"] = sha(rec["output_file"])
+            rec["output_file_tail"] = rec["output_file"][-1500:]
+            del rec["output_file"]
 
     # ---- mid-size runs (digests instead of full matrices): longer pivot sequences, accumulated rounding
     mid = []

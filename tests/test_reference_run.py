@@ -46,7 +46,7 @@ def test_golden_covers_the_reference_fixtures_and_every_solver():
     assert len(GOLD["meta"]["reference_sources"]) == 13
     for key, least in (("parser", 9), ("primal", 28), ("primal2", 16), ("dual", 16), ("cutting_plane", 12),
                        ("revised", 20), ("bb", 13), ("bb_formulate", 6), ("sensitivity", 12), ("sensitivity_rhs", 6),
-                       ("output", 3), ("mid_size", 3), ("bb_parts", 40)):
+                       ("output", 3), ("mid_size", 3), ("bb_parts", 40), ("program", 6)):
         assert len(GOLD[key]) >= least, key
     # data/TextFile.txt parsed by the reference's own InputFileParser
     p = GOLD["parser"][0]
@@ -391,6 +391,36 @@ def test_mid_size_runs(i):
     assert labels == rg["entering_labels"] and rr["basis"].tolist() == rg["basis"]
     assert hashlib.sha256(rr["Binv"].tobytes()).hexdigest() == rg["binv_sha256"]
     assert float(rr["z"]).hex() == rg["final_z"] and same_bits(rr["x"], unhex(rg["x"])) and same_bits(rr["xB"], unhex(rg["xb"]))
+
+
+def test_program_main_sessions():
+    """the reference's whole application (Program.Main, scripted keyboard) on its shipped model: the answers of SURVEY
+    Appendix C as the application itself printed and wrote them, and the state leak between menu options"""
+    prog = {tuple(g["keys"]): g for g in GOLD["program"]}
+    one = prog[("1", "13", "7")]
+    assert one["unhandled_exception"] is None and one["keys_left"] == []
+    assert "Optimal Solution Found!" in one["console"] and "Warning: x5 = 0.2 violates binary constraint." in one["console"]
+    assert one["output_file"].endswith("=== Final Results ===\r\nZ* = 15.4\r\nx1 = 0\r\nx2 = 1\r\nx3 = 1\r\nx4 = 1\r\nx5 = 0.2\r\nx6 = 1\r\n")
+    r = final_a_oracle()
+    assert float(r["T"][0, -1]).hex() == float(15.4).hex() or abs(r["T"][0, -1] - 15.4) < 1e-12
+    two = prog[("2", "7")]
+    assert "Solver: Revised Primal Simplex Algorithm (T-*)" in two["output_file"] and "Z* = 15.4" in two["output_file"]
+    three = prog[("3", "7")]
+    assert "Total branchs processed: 20" in three["console_tail"] and "Z* = 15\r\nx1 = 0\r\nx2 = 1\r\nx3 = 1\r\nx4 = 1\r\nx5 = 0\r\nx6 = 1" in three["console_tail"]
+    assert prog[("4", "7")]["output_file"] is None            # option 4 only prints the canonical form (Program.cs:420-429)
+    leak = prog[("1", "13", "2")]
+    assert leak["unhandled_exception"] == "System.ArgumentException: Constraint 2 has incorrect number of coefficients."
+
+
+def final_a_oracle():
+    rows = []
+    for i in range(6):
+        co = [0.0] * 9
+        co[i] = 1.0
+        co[7] = 1.0
+        rows.append((co, "<=", 1.0))
+    T, b = O.primal_build([2, 3, 3, 5, 2, 4], [([11, 8, 6, 14, 10, 10], "<=", 40)] + rows)
+    return O.primal_solve(T, b)
 
 
 # ------------------------------------------------------------------------------------------- the interpreter itself
