@@ -141,6 +141,8 @@ class CsList:
     def co(self, v):
         if self.elem == "double" and type(v) is int:
             return float(v)
+        if type(self.elem) is tuple and type(v) is CsTuple:      # List<(T1 a, T2 b)>: the element type names the fields
+            return coerce(v, self.elem)
         return v
 
 
@@ -186,17 +188,19 @@ class CsSet:
 
 
 class CsStack:
-    __slots__ = ("items",)
+    __slots__ = ("items", "elem")
 
-    def __init__(self, items=None):
+    def __init__(self, items=None, elem=None):
         self.items = items or []
+        self.elem = elem
 
 
 class CsQueue:
-    __slots__ = ("items",)
+    __slots__ = ("items", "elem")
 
-    def __init__(self, items=None):
+    def __init__(self, items=None, elem=None):
         self.items = items or []
+        self.elem = elem
 
 
 class CsAnon:
@@ -2769,6 +2773,8 @@ def bcl_construct(interp, name, ty, args, named):
     targs = ty[2]
     if name in ("List", "IList"):
         elem = type_name(targs[0]) if targs else None
+        if targs and targs[0][0] == "tupletype":
+            elem = targs[0]
         if args and type(args[0]) is not int:
             if args[0] is None:
                 raise CsException("ArgumentNullException", param="collection")
@@ -2787,9 +2793,11 @@ def bcl_construct(interp, name, ty, args, named):
     if name == "HashSet":
         return CsSet(iterate(args[0])) if args and type(args[0]) is not int else CsSet()
     if name == "Stack":
-        return CsStack(list(iterate(args[0])) if args and type(args[0]) is not int else None)
+        return CsStack(list(iterate(args[0])) if args and type(args[0]) is not int else None,
+                       targs[0] if targs and targs[0][0] == "tupletype" else None)
     if name == "Queue":
-        return CsQueue(list(iterate(args[0])) if args and type(args[0]) is not int else None)
+        return CsQueue(list(iterate(args[0])) if args and type(args[0]) is not int else None,
+                       targs[0] if targs and targs[0][0] == "tupletype" else None)
     if name == "StringBuilder":
         return CsStringBuilder(args[0] if args and type(args[0]) is str else "")
     if name == "StringWriter":
@@ -3136,7 +3144,7 @@ def bcl_instance_call(interp, obj, name, args, named):
             return None
     elif t is CsStack:
         if name == "Push":
-            obj.items.append(args[0])
+            obj.items.append(coerce(args[0], obj.elem) if obj.elem is not None else args[0])
             return None
         if name == "Pop" or name == "Peek":
             if not obj.items:
@@ -3149,7 +3157,7 @@ def bcl_instance_call(interp, obj, name, args, named):
             return any(cs_equals(v, args[0]) for v in obj.items)
     elif t is CsQueue:
         if name == "Enqueue":
-            obj.items.append(args[0])
+            obj.items.append(coerce(args[0], obj.elem) if obj.elem is not None else args[0])
             return None
         if name == "Dequeue" or name == "Peek":
             if not obj.items:
