@@ -1386,23 +1386,26 @@ class Interpreter:
         if k == "block":
             return self.exec_block(s[1], env)
         if k == "for":
+            # scopes as in ECMA-334 7.7: the loop variable lives once per loop, what the body declares once per
+            # iteration (so that a lambda created in the body captures that iteration's variables)
+            loop = Env(env, env.this, env.cls)
             for init in s[1]:
-                self.exec(init, env)
+                self.exec(init, loop)
             cond, iters, body = s[2], s[3], s[4]
-            while cond is None or self.ev(cond, env):
-                sig = self.exec(body, env)
+            while cond is None or self.ev(cond, loop):
+                sig = self.exec(body, Env(loop, env.this, env.cls))
                 if sig is not None:
                     if sig is BREAK:
                         break
                     if sig is not CONTINUE:
                         return sig
                 for it in iters:
-                    self.ev(it, env)
+                    self.ev(it, loop)
                 self.tick()
             return None
         if k == "while":
             while self.ev(s[1], env):
-                sig = self.exec(s[2], env)
+                sig = self.exec(s[2], Env(env, env.this, env.cls))
                 if sig is not None:
                     if sig is BREAK:
                         break
@@ -1412,7 +1415,7 @@ class Interpreter:
             return None
         if k == "dowhile":
             while True:
-                sig = self.exec(s[1], env)
+                sig = self.exec(s[1], Env(env, env.this, env.cls))
                 if sig is not None:
                     if sig is BREAK:
                         break
@@ -1425,11 +1428,12 @@ class Interpreter:
         if k == "foreach":
             _, ty, names, e, body = s
             for v in iterate(self.ev(e, env)):
+                scope = Env(env, env.this, env.cls)      # a fresh iteration variable every time round (C# 5)
                 if isinstance(names, list):
-                    self.deconstruct(names, v, env, declare=True)
+                    self.deconstruct(names, v, scope, declare=True)
                 else:
-                    self.declare(env, names, coerce(v, ty) if ty and ty[1] != "var" else v, ty)
-                sig = self.exec(body, env)
+                    self.declare(scope, names, coerce(v, ty) if ty and ty[1] != "var" else v, ty)
+                sig = self.exec(body, scope)
                 if sig is not None:
                     if sig is BREAK:
                         break

@@ -178,9 +178,7 @@ def test_control_flow_exceptions_and_closures():
     got = run(src)
     assert got.startswith("023|6six|fin|boom")
     assert "|baseTrue|" in got and got.endswith("|5|True12False0")
-    # foreach closures: a single method-level scope is used, so the captured variable is shared -- the reference never
-    # stores a lambda past its loop iteration (every LINQ call is evaluated on the spot); stated here as a known limit
-    assert "|10,20,30|" in got or "|30,30,30|" in got
+    assert "|10,20,30|" in got
 
 
 def test_classes_properties_tuples_and_nullables():
