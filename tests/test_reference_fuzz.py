@@ -7,7 +7,6 @@ oracle on random models of the same families by the -m gpu tests.)
 import importlib.util
 import os
 import random
-import re
 
 import numpy as np
 import pytest
