@@ -180,7 +180,8 @@ def run_reference_arm(args, rank, world):
                    "step": f"{sample} consecutive pivots of the same solve (bounded sample)", "seed": SEED},
         "cpu_baseline": {"value": val, "unit": "pivots/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} pivots per step x {len(t_step)} steps; C++ restatement of the "
-                                   "reference C# loops (no .NET toolchain in the image), row loop of Pivot "
+                                   "reference C# loops (no .NET toolchain in the image; pinned bit for bit to the "
+                                   "reference's own sources executed by oracle/csharp), row loop of Pivot "
                                    f"split over {threads} threads (bit-identical)"},
         "e2e": {"value": val, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "tableau_gbs": 16.0 * R * CC * val / 1e9,
@@ -354,7 +355,8 @@ def main():
         del T0, r
         cpu = {"value": sample / dtc, "unit": "pivots/s", "cores": 1, "kind": "port",
                "sample": f"first {sample} pivots of the same cfg2 solve ({dtc:.1f} s); C++ restatement of "
-                         "PrimalSimplexSolver.cs:152-211 (no .NET toolchain in the image), single thread like "
+                         "PrimalSimplexSolver.cs:152-211 (no .NET toolchain in the image; pinned bit for bit to "
+                         "the reference's own sources executed by oracle/csharp), single thread like "
                          f"the reference; host has {os.cpu_count()} cores"}
     del Ah, outT
 
