@@ -15,7 +15,13 @@ GPU box needs /root/reference: only the committed JSON travels.
 
     csparse.py  lexer + recursive-descent parser for the C# 7.3 subset the reference uses -> AST (tuples)
     csrun.py    tree-walking evaluator + the BCL subset (List, Dictionary, Stack, HashSet, LINQ, Math, String,
-                StringBuilder, Console, File, Array, Tuple, Nullable, exceptions, number formatting)
+                StringBuilder, Console incl. SetOut, File, Path, Array, Tuple, Nullable, SafeHandle, Marshal, Encoding,
+                exceptions, number formatting)
+    pinvoke.py  `[DllImport] static extern` -> ctypes with the CLR's default marshalling: how the C# shims under
+                csharp/ are executed against liblprb200.so (tests/test_csharp_shims*.py)
+
+Also run with it: the reference's whole application (`Program.Main`, scripted keyboard) and the conformance tests of the
+interpreter itself (tests/test_csharp_interpreter.py).
 """
 from .csparse import parse_source  # noqa: F401
 from .csrun import Interpreter, CsException  # noqa: F401

@@ -7,6 +7,7 @@ Run in the build container only (the GPU box has no /root/reference and needs no
 
     python tests/golden/make_reference_run.py            # writes tests/golden/reference_run.json
     python tests/golden/make_reference_run.py --check    # regenerates in memory and compares with the committed file
+    python tests/golden/make_reference_run.py --large    # two longer runs -> reference_run_large.json (several minutes)
 
 What is executed (class -> entry points):
     IO/InputFileParser.cs                      ReadInputFile on data/TextFile.txt, TextFile/textfile.txt, README model, edge texts
@@ -628,7 +629,48 @@ def generate():
     return out
 
 
+LARGE = os.path.join(HERE, "reference_run_large.json")
+
+
+def generate_large():
+    """two longer runs of the reference's PrimalSimplexSolver (61 x 161 and 101 x 301 tableaux) and one of its
+    RevisedPrimalSimplexSolver (m = 60, n = 100; every CaptureSnapshot forms B^-1 A, so the second size would take
+    hours): minutes in the interpreter, so they live in their own file, are written by `--large` only and are not
+    re-generated by the test suite; digests instead of matrices"""
+    run = Runner()
+    out = []
+    for seed, (m, n) in ((99, (60, 100)), (100, (100, 200))):
+        rng = random.Random(seed)
+        obj = [rng.randint(1, 20) + rng.randint(0, 99) / 100 for _ in range(n)]
+        cons = [([(rng.randint(1, 12) + rng.randint(0, 99) / 100) if rng.random() < 0.3 else 0.0 for _ in range(n)],
+                 "<=", float(rng.randint(20, 90))) for _ in range(m)]
+        prec, _ = run.primal(obj, cons, True)
+        print("large case", seed, m, n, len(prec["pivots"]), "pivots", flush=True)
+        rv_rec = run.revised(obj, [c[0] for c in cons], [c[2] for c in cons], ["<="] * m, False) if m <= 60 else None
+        for rec in (prec, rv_rec):
+            for key in ("initial_tableau", "final_tableau", "get_final_tableau", "binv"):
+                if rec is not None and key in rec:
+                    mtx = rec.pop(key)
+                    rec[key + "_shape"] = mtx["shape"]
+                    rec[key + "_sha256"] = hashlib.sha256(
+                        b"".join(struct.pack("<d", float.fromhex(h)) for h in mtx["hex"])).hexdigest()
+        out.append({"seed": seed, "m": m, "n": n, "objective": obj,
+                    "constraints": [[list(co), rel, rhs] for co, rel, rhs in cons],
+                    "primal": {k: v for k, v in prec.items() if k not in ("objective", "constraints")},
+                    "revised": None if rv_rec is None else
+                    {k: v for k, v in rv_rec.items() if k not in ("c", "A", "b", "relations")}})
+        print("  revised done" if rv_rec else "  (no revised run at this size)", flush=True)
+    return {"meta": {"generator": "tests/golden/make_reference_run.py --large",
+                     "reference_sources_sha256": source_digest()}, "runs": out}
+
+
 def main():
+    if "--large" in sys.argv:
+        text = json.dumps(generate_large(), sort_keys=True) + "\n"
+        with open(LARGE, "w") as f:
+            f.write(text)
+        print("wrote", LARGE)
+        return
     data = generate()
     # one record per line: diffable, a third of the size of an indented dump
     lines = []

@@ -59,3 +59,6 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle_lib", src, flags=re.M), f
                 assert not re.search(r"#include\s*[<\"][^>\"]*lpr_oracle", src), f
                 assert "liblpr_oracle" not in src and "oracle/" not in src.replace("oracle/lpr_oracle.cpp", ""), f
+                # nor the C# interpreter, the P/Invoke layer or the oracle-backed double of the shim tests
+                assert not re.search(r"^\s*(import|from)\s+(csharp|lprb200_double|csharp_shim_cases|net_reference)", src, flags=re.M), f
+                assert "lprb200_double" not in src and "pinvoke" not in src, f

@@ -423,6 +423,30 @@ def final_a_oracle():
     return O.primal_solve(T, b)
 
 
+def test_longer_runs():
+    """longer runs, 61 x 161 and 101 x 301 tableaux (tests/golden/reference_run_large.json, written once by
+    `make_reference_run.py --large`): pivot sequence, basis, digests of the final tableau and of B^-1, z, x"""
+    large = json.load(open(os.path.join(HERE, "golden", "reference_run_large.json")))
+    assert large["meta"]["reference_sources_sha256"] == GOLD["meta"]["reference_sources_sha256"]
+    for g in large["runs"]:
+        cons = cons_of(g)
+        n = len(g["objective"])
+        pg, rg = g["primal"], g["revised"]
+        T0, b0 = O.primal_build(g["objective"], cons, True)
+        assert hashlib.sha256(T0.tobytes()).hexdigest() == pg["initial_tableau_sha256"]
+        r = O.primal_solve(T0, b0)
+        assert len(pg["pivots"]) >= 70 and r["log"].tolist() == pg["pivots"] and r["basis"].tolist() == pg["basis"]
+        assert hashlib.sha256(r["T"].tobytes()).hexdigest() == pg["final_tableau_sha256"]
+        assert float(r["T"][0, -1]).hex() == pg["final_z"] and same_bits(O.primal_extract(r["T"], n), unhex(pg["x"]))
+        if rg is None:
+            continue
+        rr = O.rev_solve(np.array([c[0] for c in cons], dtype=float), [c[2] for c in cons], g["objective"], False, want_binv=True)
+        labels = [f"x{e + 1}" if e < n else f"S{e - n + 1}" for e in rr["log"][:, 1].tolist()]
+        assert labels == rg["entering_labels"] and rr["basis"].tolist() == rg["basis"]
+        assert hashlib.sha256(rr["Binv"].tobytes()).hexdigest() == rg["binv_sha256"]
+        assert float(rr["z"]).hex() == rg["final_z"] and same_bits(rr["x"], unhex(rg["x"]))
+
+
 # ------------------------------------------------------------------------------------------- the interpreter itself
 def _run(src, cls="T", method="F", *args):
     from csharp import Interpreter
