@@ -151,3 +151,113 @@ def test_cutting_plane_and_branch_and_bound(run, seed):
             assert same(r["x"], x) and float(r["z"]).hex() == g["z"]
         else:
             assert x == [] and g["z"] == "-inf"
+
+
+# ------------------------------------------------------------------------------------------- native host code
+TOKENS = ["1", "2", "-3", "+4", "0", "2.5", "-0.5", "1e1", "1,000", ".5", "5.", "x", "", "<=", ">=", "=", "max", "min", "MAX",
+          "bin", "+", "-", "urs", "int", "1e", "--1", "0x10", "NaN", "1e999", "\t7"]
+
+
+def _random_model_text(rng):
+    n = rng.randint(1, 4)
+    lines = []
+    head = [rng.choice(["max", "min", "MAX", "Min", "maximize", "x"])] + [rng.choice(TOKENS[:12]) for _ in range(n)]
+    lines.append((" " if rng.random() < 0.1 else "") + " ".join(head) + (" " if rng.random() < 0.2 else ""))
+    for _ in range(rng.randint(0, 4)):
+        k = n + 2 + rng.choice([0, 0, 0, 0, -1, -2, 1, 2])
+        toks = [rng.choice(TOKENS[:10]) for _ in range(max(0, n))] + [rng.choice(["<=", ">=", "=", "<", "5"])] + [rng.choice(TOKENS[:11])]
+        toks = toks[:max(0, k)] if k < len(toks) else toks + [rng.choice(TOKENS) for _ in range(k - len(toks))]
+        if rng.random() < 0.15:
+            toks[rng.randrange(len(toks))] = rng.choice(TOKENS) if toks else "1"
+        sep = "  " if rng.random() < 0.2 else " "
+        lines.append(("  " if rng.random() < 0.2 else "") + sep.join(toks))
+    if rng.random() < 0.9:
+        lines.append(" ".join(rng.choice(["+", "-", "urs", "bin", "int"]) for _ in range(rng.randint(0, n + 1))))
+    eol = rng.choice(["\n", "\r\n", "\n", "\r"])
+    return eol.join(lines) + (eol if rng.random() < 0.5 else "")
+
+
+def test_native_parser_against_the_executed_reference_parser(run):
+    """InputFileParser.ReadInputFile as the reference executes it, against lpr_model_parse_text (csrc/host_io.cu), on
+    random texts: which exception comes first, the two silent early returns, every parsed value"""
+    from lpr_381_group_v22_b200.io import Model
+    rng = random.Random(5000)
+    seen = {"ok": 0, "FormatException": 0, "IndexOutOfRangeException": 0, "early": 0}
+    for _ in range(400):
+        text = _random_model_text(rng)
+        g = run.parse(text)
+        if g["exception"] == "FormatException":
+            with pytest.raises(ValueError, match="FormatException"):
+                Model.parse_text(text)
+            seen["FormatException"] += 1
+            continue
+        if g["exception"] == "IndexOutOfRangeException":
+            with pytest.raises(IndexError, match="IndexOutOfRangeException"):
+                Model.parse_text(text)
+            seen["IndexOutOfRangeException"] += 1
+            continue
+        if g["exception"] == "OverflowException":          # 1e999: double.Parse overflows on the Framework
+            with pytest.raises(ValueError):
+                Model.parse_text(text)
+            continue
+        assert g["exception"] is None, (text, g["exception"])
+        m = Model.parse_text(text)
+        assert m.message == g["console"].strip(), text
+        if g["problem_type"] is None:
+            assert m.info()[0] is False
+            seen["early"] += 1
+            continue
+        seen["ok"] += 1
+        assert m.problem_type == g["problem_type"], text
+        assert same(m.objective(), [float.fromhex(h) for h in g["objective"]]), text
+        cons = m.constraints()
+        assert len(cons) == len(g["constraints"]), text
+        for c, (co, rel, rhs) in zip(cons, g["constraints"]):
+            assert same(c.Coefficients, [float.fromhex(h) for h in co]) and c.Relation == rel and float(c.RHS).hex() == rhs, text
+        assert m.signs() == g["signs"], text
+    assert min(seen.values()) >= 5, seen
+
+
+def test_native_result_files_against_the_executed_output_file_write(run, tmp_path):
+    """OutputFileWrite / CanonicalFormForFile executed by the interpreter against lpr_out_* on random models, snapshot
+    strings and special values"""
+    import lpr_381_group_v22_b200 as L
+    from lpr_381_group_v22_b200.io import Model
+    from csharp.csrun import CsList, to_list
+    rng = random.Random(6000)
+    it = run.it
+    specials = [0.0, -0.0, 1e-13, -1e-13, 0.0005, 2.5, 1e15, 1e16, 123456789.123456, -7.9995, 1 / 3, 100000.0]
+    for k in range(25):
+        n, m = rng.randint(1, 4), rng.randint(1, 3)
+        obj = [rng.choice([1.0, -2.0, 0.5, 0.0, 12.25, -0.125, 1000.0, 1e-5]) for _ in range(n)]
+        rows = [([rng.choice([0.0, 1.0, -1.5, 2.0, 0.1, 1e7]) for _ in range(n)], rng.choice(["<=", ">=", "="]),
+                 rng.choice([4.0, 0.0, -3.5, 1e6, 0.3])) for _ in range(m)]
+        signs = [rng.choice(["+", "-", "urs", "bin", "int"]) for _ in range(n)]
+        ptype = rng.choice(["max", "min"])
+
+        def tok(v):
+            return repr(float(v)) if v != int(v) or abs(v) >= 1e15 else str(int(v))
+        text = "\n".join([ptype + " " + " ".join(tok(v) for v in obj)] +
+                         [" ".join(tok(v) for v in co) + f" {rel} {tok(rhs)}" for co, rel, rhs in rows] + [" ".join(signs)])
+        snaps = [rng.choice(["", "one line", "ends with a newline\n", "a\r\nb\r\n", "tab\there", "unicode ≤ ∞"]) for _ in range(rng.randint(0, 3))]
+        z = rng.choice(specials)
+        x = [rng.choice(specials) for _ in range(rng.randint(0, n))]
+        # the reference, executed
+        it.files.clear()
+        it.files["model.txt"] = text
+        p = it.new("InputFileParser")
+        it.call(p, "ReadInputFile", "model.txt")
+        args = (it.get(p, "ProblemType"), it.get(p, "ObjectiveCoefficients"), it.get(p, "Constraints"), it.get(p, "SignRestrictions"))
+        canon = it.call_static("CanonicalFormConverter", "CanonicalFormForFile", *args)
+        it.call_static("OutputFileWrite", "WriteFullResults", "out.txt", "Solver X", *args, CsList(list(snaps), "string"),
+                       float(z), to_list(x))
+        it.call_static("OutputFileWrite", "WriteSnapshotsOnly", "out.txt", "Solver Y", CsList(list(snaps), "string"), float(z),
+                       to_list(x) if x else None)
+        want = it.files["out.txt"]
+        # the native writer
+        mdl = Model.parse_text(text)
+        assert mdl.canonical_form() == canon, text
+        path = str(tmp_path / f"o{k}.txt")
+        L.io.OutputFileWrite.WriteFullResults(path, "Solver X", mdl, snaps, z, x, append=False, timestamp=it.now)
+        L.io.OutputFileWrite.WriteSnapshotsOnly(path, "Solver Y", snaps, z, x if x else None, append=True, timestamp=it.now)
+        assert open(path, "rb").read() == want.encode("utf-8"), (text, snaps, z, x)
