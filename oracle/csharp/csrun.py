@@ -32,6 +32,16 @@ BCL rules restated here, with the rule each follows (.NET Framework 4.7.2 refere
   * List<T> indexer / RemoveAt / Insert out of range: ArgumentOutOfRangeException; array index: IndexOutOfRange;
     a foreach over a List<T> that is modified meanwhile: InvalidOperationException.
   * (int)double: truncation toward zero; NaN or out of range gives int.MinValue (x64 cvttsd2si).
+  * [DllImport] static extern methods call `Interpreter.native` (pinvoke.py); SafeHandle, IDisposable and `using`
+    release handles as the CLR does (minus finalizers: there is no garbage collector to run them).
+
+Known simplifications (none is reached by the reference's solver paths; tests/test_csharp_interpreter.py states the
+rules that are): int arithmetic does not wrap at 32 bits; the current culture is the invariant one ("." decimal point,
+"," group separator -- a machine set to a decimal-comma culture would print the reference's "{x:F3}" differently);
+exception text has no stack trace; overloads are resolved by argument count and a type score, not by the full better-
+conversion rules; value tuples are immutable; static constructors, operators, events, generics declarations, async,
+unsafe code and goto are not implemented (the parser rejects what it does not know); Math.Pow / Exp / Log go to the
+C library, whose last bit may differ from the CLR's.
 """
 import functools
 import math
