@@ -141,12 +141,20 @@ class CsArray:
 
 
 class CsList:
-    __slots__ = ("items", "elem", "ver")
+    __slots__ = ("items", "elem", "ver", "cap")
 
-    def __init__(self, items=None, elem=None):
+    def __init__(self, items=None, elem=None, cap=None):
         self.items = items if items is not None else []
         self.elem = elem
         self.ver = 0
+        self.cap = len(self.items) if cap is None else cap      # length of the backing array (List.cs)
+
+    def capacity(self):
+        """List<T>.EnsureCapacity: 4 when empty, then doubling; what Sort's depth limit is computed from"""
+        n = len(self.items)
+        while self.cap < n:
+            self.cap = 4 if self.cap == 0 else self.cap * 2
+        return self.cap
 
     def co(self, v):
         if self.elem == "double" and type(v) is int:
@@ -745,8 +753,9 @@ def cs_compare(a, b):
     return -1 if a < b else (1 if a > b else 0)
 
 
-def introsort(keys, cmp):
-    """ArraySortHelper<T>.IntrospectiveSort (mscorlib, .NET Framework 4.5+)"""
+def introsort(keys, cmp, capacity=None):
+    """ArraySortHelper<T>.IntrospectiveSort (mscorlib, .NET Framework 4.5+); `capacity` = length of the array that is
+    sorted in place (a List<T>'s backing array), from which the depth limit is computed"""
     n = len(keys)
     if n < 2:
         return
@@ -829,7 +838,7 @@ def introsort(keys, cmp):
             intro(p + 1, hi, depth)
             hi = p - 1
 
-    log2, m = 0, n
+    log2, m = 0, max(n, capacity or 0)
     while m >= 1:
         log2 += 1
         m //= 2
@@ -2798,7 +2807,7 @@ def bcl_construct(interp, name, ty, args, named):
             return lst
         if args and args[0] < 0 or named.get("capacity", 0) < 0:
             raise CsException("ArgumentOutOfRangeException", param="capacity")
-        return CsList([], elem)
+        return CsList([], elem, cap=(args[0] if args else named.get("capacity", 0)))
     if name == "Dictionary" or name == "SortedDictionary":
         d = CsDict()
         if args and type(args[0]) is CsDict:
@@ -2932,6 +2941,7 @@ def bcl_instance_call(interp, obj, name, args, named):
         items = obj.items
         if name == "Add":
             items.append(obj.co(args[0])); obj.ver += 1
+            obj.capacity()
             return None
         if name == "AddRange":
             if args[0] is None:
@@ -2986,9 +2996,9 @@ def bcl_instance_call(interp, obj, name, args, named):
             return -1
         if name == "Sort":
             if args and callable(args[0]):
-                introsort(items, args[0])
+                introsort(items, args[0], obj.capacity())
             else:
-                introsort(items, cs_compare)
+                introsort(items, cs_compare, obj.capacity())
             obj.ver += 1
             return None
         if name == "Reverse" and not args:

@@ -559,25 +559,156 @@ int orc_sens_resolve(int R, int C, double* T, int* basis, int max_iter, int* sta
 }
 
 /* ======================= CuttingPlaneSolver =============================================== */
-/* IntegerProgramming/CuttingPlaneSolver.cs:76-107: choose the constraint row whose RHS
- * fractional part is closest to 0.5 (List.Sort is an unstable introsort; below 17 entries it
- * is an insertion sort = first minimum; exact ties beyond that are unpinned, SURVEY Q14 --
- * the oracle takes the first minimum) and build cut = -Frac(row). */
+/* IntegerProgramming/CuttingPlaneSolver.cs:76-107: choose the constraint row whose RHS fractional part is closest
+ * to 0.5 and build cut = -Frac(row).  The reference collects the fractional rows in row order, SORTS them with
+ * List<T>.Sort(Comparison) by |Frac(rhs) - 0.5| and takes element 0 (:94-96).  List<T>.Sort is the .NET Framework's
+ * introspective sort (ArraySortHelper<T>.IntrospectiveSort, mscorlib 4.5+): insertion sort up to 16 elements -- stable,
+ * so element 0 is the FIRST minimum -- and median-of-three quicksort (heapsort at the depth limit) above that, which is
+ * not stable: when MORE THAN 16 rows are fractional AND several of them tie exactly for the smallest key, element 0 is
+ * whichever of them the sort's swaps leave there.  dotnet_introsort_first() restates that sort literally (it was
+ * checked against the reference executed by oracle/csharp, tests/test_reference_run.py); outside that corner it returns
+ * the first minimum.  orc_set_gomory_first_min(1) switches to the plain first minimum, which is what the CUDA kernels
+ * implement ("known deviation"). */
+namespace {
+int g_gomory_first_min = 0;
+int64_t g_gomory_tie_corners = 0;  // selections in which the literal sort and the first minimum disagree
+
+struct FracRow {
+  int idx;
+  double key;
+};
+inline int cmp_key(const FracRow& a, const FracRow& b) {  // double.CompareTo on non-NaN keys
+  return a.key < b.key ? -1 : (a.key > b.key ? 1 : 0);
+}
+
+// ArraySortHelper<T>.IntrospectiveSort(keys, 0, n, comparer) with depthLimit = 2 * FloorLog2(capacity), where
+// capacity is the length of the List<T>'s backing array (4, 8, 16, ... for a list filled by Add, List.cs EnsureCapacity)
+struct DotnetIntroSort {
+  std::vector<FracRow>& k;
+  explicit DotnetIntroSort(std::vector<FracRow>& keys) : k(keys) {}
+  void swap_if_greater(int a, int b) {
+    if (a != b && cmp_key(k[a], k[b]) > 0) std::swap(k[a], k[b]);
+  }
+  void insertion(int lo, int hi) {
+    for (int i = lo; i < hi; i++) {
+      int j = i;
+      FracRow t = k[i + 1];
+      while (j >= lo && cmp_key(t, k[j]) < 0) {
+        k[j + 1] = k[j];
+        j--;
+      }
+      k[j + 1] = t;
+    }
+  }
+  void down_heap(int i, int n, int lo) {
+    FracRow d = k[lo + i - 1];
+    while (i <= n / 2) {
+      int child = 2 * i;
+      if (child < n && cmp_key(k[lo + child - 1], k[lo + child]) < 0) child++;
+      if (!(cmp_key(d, k[lo + child - 1]) < 0)) break;
+      k[lo + i - 1] = k[lo + child - 1];
+      i = child;
+    }
+    k[lo + i - 1] = d;
+  }
+  void heapsort(int lo, int hi) {
+    int n = hi - lo + 1;
+    for (int i = n / 2; i >= 1; i--) down_heap(i, n, lo);
+    for (int i = n; i > 1; i--) {
+      std::swap(k[lo], k[lo + i - 1]);
+      down_heap(1, i - 1, lo);
+    }
+  }
+  int partition(int lo, int hi) {
+    int mid = lo + (hi - lo) / 2;
+    swap_if_greater(lo, mid);
+    swap_if_greater(lo, hi);
+    swap_if_greater(mid, hi);
+    FracRow pivot = k[mid];
+    std::swap(k[mid], k[hi - 1]);
+    int left = lo, right = hi - 1;
+    while (left < right) {
+      while (cmp_key(k[++left], pivot) < 0) {
+      }
+      while (cmp_key(pivot, k[--right]) < 0) {
+      }
+      if (left >= right) break;
+      std::swap(k[left], k[right]);
+    }
+    std::swap(k[left], k[hi - 1]);
+    return left;
+  }
+  void intro(int lo, int hi, int depth) {
+    while (hi > lo) {
+      int size = hi - lo + 1;
+      if (size <= 16) {
+        if (size == 1) return;
+        if (size == 2) {
+          swap_if_greater(lo, hi);
+          return;
+        }
+        if (size == 3) {
+          swap_if_greater(lo, hi - 1);
+          swap_if_greater(lo, hi);
+          swap_if_greater(hi - 1, hi);
+          return;
+        }
+        insertion(lo, hi);
+        return;
+      }
+      if (depth == 0) {
+        heapsort(lo, hi);
+        return;
+      }
+      depth--;
+      int p = partition(lo, hi);
+      intro(p + 1, hi, depth);
+      hi = p - 1;
+    }
+  }
+  void sort() {
+    int n = (int)k.size();
+    if (n < 2) return;
+    int cap = 4;
+    while (cap < n) cap *= 2;
+    int log2 = 0;
+    for (int c = cap; c >= 1; c /= 2) log2++;
+    intro(0, n - 1, 2 * log2);
+  }
+};
+
+int dotnet_introsort_first(std::vector<FracRow> rows) {
+  DotnetIntroSort(rows).sort();
+  return rows[0].idx;
+}
+}  // namespace
+
+void orc_set_gomory_first_min(int on) { g_gomory_first_min = on; }
+int64_t orc_gomory_tie_corners(void) { return g_gomory_tie_corners; }
+
 int orc_gomory_cut(int R, int C, const double* T, double* cut) {
   const double EPS = 1e-9;
-  int chosen = -1;
+  int first_min = -1;
   double bestKey = kInf;
+  std::vector<FracRow> rows;
   for (int i = 0; i < R - 1; i++) {
     double rhsFrac = orc_frac(at(T, C, i + 1, C - 1));
     if (rhsFrac > EPS) {
       double key = std::fabs(rhsFrac - 0.5);
+      rows.push_back({i, key});
       if (key < bestKey) {
         bestKey = key;
-        chosen = i;
+        first_min = i;
       }
     }
   }
-  if (chosen < 0) return -1;
+  if (first_min < 0) return -1;
+  int chosen = first_min;
+  if (rows.size() > 16) {
+    int literal = dotnet_introsort_first(rows);
+    if (literal != first_min) g_gomory_tie_corners++;
+    if (!g_gomory_first_min) chosen = literal;
+  }
   for (int j = 0; j < C; j++) cut[j] = -orc_frac(at(T, C, chosen + 1, j));
   return chosen;
 }

@@ -117,6 +117,11 @@ int orc_cutting_plane(int* R, int C, double* T, int row_cap, int max_cuts, int* 
 /* one cut row only (steps 1-4, :76-107): returns chosen constraint row (0-based among
  * constraint rows) or -1; cut has C entries */
 int orc_gomory_cut(int R, int C, const double* T, double* cut);
+/* the row choice above follows List<T>.Sort literally (the Framework's unstable introspective sort); 1 = take the
+ * plain first minimum instead (what the CUDA kernels do: identical unless more than 16 fractional rows tie exactly
+ * for the best key).  orc_gomory_tie_corners() counts the selections in which the two rules disagreed. */
+void orc_set_gomory_first_min(int on);
+int64_t orc_gomory_tie_corners(void);
 
 /* ---- BranchBoundSimplexSolver (IntegerProgramming/BranchBoundSimplexSolver.cs) ---------- */
 void orc_bb_round_tableau(int64_t count, double* T); /* RoundTableau :552-567 */

@@ -496,6 +496,30 @@ def generate():
         run.it.max_steps = None
     out["cutting_plane"] = cp
 
+    # ---- the cut-row choice is element 0 of List<T>.Sort: more than 16 fractional rows with exact ties for the best key
+    # is where the Framework's unstable introspective sort and "the first minimum" part ways (SURVEY d1 "ties unpinned")
+    rng3 = random.Random(383)
+    ties = []
+    while len(ties) < 8:
+        m, n = rng3.randint(17, 40), rng3.randint(2, 4)
+        T = [[0.0] * (n + m + 1) for _ in range(m + 1)]
+        for j in range(n):
+            T[0][j] = float(rng3.randint(1, 5))
+        for j in range(m):
+            T[0][n + j] = float(rng3.choice([0, 0.5, 1]))
+        for i in range(m):
+            for j in range(n):
+                T[i + 1][j] = float(rng3.choice([0.5, 0.25, 1, 0, -0.5, 2]))
+            T[i + 1][n + i] = 1.0
+            T[i + 1][-1] = rng3.randint(0, 6) + rng3.choice([0.5, 0.25, 0.75, 0.5, 0.125, 0.0])
+        run.it.max_steps = run.it.steps + 3_000_000
+        try:
+            ties.append(run.cutting_plane(T))
+        except RuntimeError:
+            pass
+        run.it.max_steps = None
+    out["cutting_plane_ties"] = ties
+
     # ---- revised simplex
     rv = [run.revised([2, 3, 4], [[1, 2, 3], [3, 2, 1]], [10, 15], ["<=", ">="], False, keep_text=True),
           run.revised(model_a[0], [model_a[1][0][0]] + [[1.0 if j == i else 0.0 for j in range(6)] for i in range(6)],

@@ -167,19 +167,34 @@ def sens_add_constraint(T, basis, tech, rhs_minus_ax):
 
 
 # ---------------------------------------------------------------- cutting plane
-def gomory_cut(T):
+def gomory_cut(T, literal_sort=False):
+    """literal_sort: see cutting_plane"""
     T = f64(T); R, Cc = T.shape; cut = np.zeros(Cc)
+    lib().orc_set_gomory_first_min(0 if literal_sort else 1)
     row = lib().orc_gomory_cut(R, Cc, _d(T), _d(cut))
+    lib().orc_set_gomory_first_min(0)
     return row, cut
 
 
-def cutting_plane(T, max_cuts=-1, extra_rows=64):
+def cutting_plane(T, max_cuts=-1, extra_rows=64, literal_sort=False):
+    """literal_sort=True: the cut row is element 0 of the reference's List<T>.Sort (the Framework's unstable
+    introspective sort), which is what the executed reference does (tests/test_reference_run.py).  The default is the
+    plain first minimum, which is what the CUDA kernels implement and what the GPU parity tests compare with: the two
+    differ only when more than 16 fractional rows tie exactly for the best key."""
     T = f64(T); R, Cc = T.shape
     cap = R + (extra_rows if max_cuts < 0 else max_cuts + 1)
     buf = np.zeros((cap, Cc)); buf[:R] = T
     Rio = C.c_int(R); st = C.c_int(); nc = C.c_int(); log = np.zeros((cap, 4), dtype=np.int32)
+    lib().orc_set_gomory_first_min(0 if literal_sort else 1)
     lib().orc_cutting_plane(C.byref(Rio), Cc, _d(buf), cap, max_cuts, C.byref(st), C.byref(nc), _i(log), cap)
+    lib().orc_set_gomory_first_min(0)
     return dict(T=buf[:Rio.value].copy(), status=st.value, n_cuts=nc.value, log=log[:nc.value].copy())
+
+
+def gomory_tie_corners():
+    """how many cut-row choices so far had the literal sort and the first minimum disagree"""
+    lib().orc_gomory_tie_corners.restype = C.c_int64
+    return lib().orc_gomory_tie_corners()
 
 
 # ---------------------------------------------------------------- branch & bound simplex

@@ -135,7 +135,7 @@ def test_cutting_plane_and_branch_and_bound(run, seed):
         run.it.max_steps = run.it.steps + 4_000_000
         try:
             g = run.cutting_plane(T.tolist())
-            r = O.cutting_plane(T, extra_rows=64)
+            r = O.cutting_plane(T, extra_rows=64, literal_sort=True)
             assert same(r["T"], unmat(g["final_tableau"]))
         except RuntimeError:
             pass                                    # a cut sequence longer than the step budget

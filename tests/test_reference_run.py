@@ -46,7 +46,7 @@ def test_golden_covers_the_reference_fixtures_and_every_solver():
     assert len(GOLD["meta"]["reference_sources"]) == 13
     for key, least in (("parser", 9), ("primal", 28), ("primal2", 16), ("dual", 16), ("cutting_plane", 12),
                        ("revised", 20), ("bb", 13), ("bb_formulate", 6), ("sensitivity", 12), ("sensitivity_rhs", 6),
-                       ("output", 3), ("mid_size", 3), ("bb_parts", 40), ("program", 6)):
+                       ("output", 3), ("mid_size", 3), ("bb_parts", 40), ("program", 6), ("cutting_plane_ties", 8)):
         assert len(GOLD[key]) >= least, key
     # data/TextFile.txt parsed by the reference's own InputFileParser
     p = GOLD["parser"][0]
@@ -113,7 +113,7 @@ CUT_END = {"Displayed the Optimal Tableau.": O.OPTIMAL, "All RHS are integers. N
 def test_cutting_plane_solver(i):
     g = GOLD["cutting_plane"][i]
     T = unmat(g["tableau"])
-    r = O.cutting_plane(T, extra_rows=64)
+    r = O.cutting_plane(T, extra_rows=64, literal_sort=True)
     assert same_bits(r["T"], unmat(g["final_tableau"]))
     # a cut that finds no pivot column is appended all the same (CuttingPlaneSolver.cs:107-131)
     appended = unmat(g["final_tableau"]).shape[0] - T.shape[0]
@@ -125,6 +125,26 @@ def test_cutting_plane_solver(i):
         assert r["status"] in (O.INFEASIBLE, O.ITER_LIMIT)
     else:
         assert r["status"] == want
+
+
+def test_gomory_row_choice_follows_list_sort():
+    """CuttingPlaneSolver.cs:94-96 sorts the fractional rows with List<T>.Sort and takes element 0.  That sort is the
+    Framework's UNSTABLE introspective sort: with more than 16 fractional rows and exact ties for the best key the row
+    it leaves in front is not the first minimum.  The oracle restates the sort literally and reproduces the executed
+    reference on tie-heavy tableaux; the plain first minimum -- what the CUDA kernels implement, DESIGN.md section 2
+    "known deviation" -- does not, on the same inputs."""
+    before = O.gomory_tie_corners()
+    first_min_differs = 0
+    for g in GOLD["cutting_plane_ties"]:
+        T = unmat(g["tableau"])
+        want = unmat(g["final_tableau"])
+        r = O.cutting_plane(T, extra_rows=128, literal_sort=True)
+        assert same_bits(r["T"], want)
+        got = [[T.shape[0] + k, int(c) + 1] for k, c in enumerate(r["log"][:len(g["cut_pivots_1based"]), 1])]
+        assert got == g["cut_pivots_1based"]
+        first_min_differs += not same_bits(O.cutting_plane(T, extra_rows=128)["T"], want)
+    assert O.gomory_tie_corners() > before
+    assert first_min_differs >= 2         # the corner is real: the stable choice leaves the reference's path
 
 
 # ------------------------------------------------------------------------------------------- revised simplex
