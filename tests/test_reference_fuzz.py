@@ -261,3 +261,42 @@ def test_native_result_files_against_the_executed_output_file_write(run, tmp_pat
         L.io.OutputFileWrite.WriteFullResults(path, "Solver X", mdl, snaps, z, x, append=False, timestamp=it.now)
         L.io.OutputFileWrite.WriteSnapshotsOnly(path, "Solver Y", snaps, z, x if x else None, append=True, timestamp=it.now)
         assert open(path, "rb").read() == want.encode("utf-8"), (text, snaps, z, x)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_sensitivity_reoptimisation(run, seed):
+    """SensitivityAnalyzer(finalTableau, ...).AddNewConstraintNonInteractive and ResolveAll after an RHS change,
+    executed, against orc_sens_*"""
+    rng = random.Random(7000 + seed)
+    done = 0
+    while done < 12:
+        n, m = rng.randint(2, 6), rng.randint(2, 6)
+        obj = [float(rng.randint(1, 9)) for _ in range(n)]
+        cons = [([float(rng.randint(0, 9)) for _ in range(n)], "<=", float(rng.randint(5, 40))) for _ in range(m)]
+        T0, b0 = O.primal_build(obj, cons, True)
+        opt = O.primal_solve(T0, b0)
+        if opt["status"] != O.OPTIMAL:
+            continue
+        done += 1
+        tech = [float(rng.randint(-2, 5)) for _ in range(n)] + [0.0] * m
+        rhs = float(rng.randint(-10, 20))
+        g = run.sensitivity(obj, cons, tech, rhs)
+        T = opt["T"]
+        basis = O.sens_rebuild_basis(T)
+        assert basis.tolist() == g["basis_rebuilt"]
+        x = O.primal_extract(T, n)
+        ax = 0.0
+        for j in range(n):
+            ax += tech[j] * x[j]
+        T1, _ = O.sens_add_constraint(T, basis, tech, rhs - ax)
+        res = O.sens_resolve(T1, O.sens_rebuild_basis(T1))
+        assert same(res["T"], unmat(g["tableau_after"])) and res["basis"].tolist() == g["basis_after"]
+        assert (res["status"] == O.OPTIMAL) == (g["exception"] is None)
+        if g["exception"] is None:
+            assert float(res["T"][0, -1]).hex() == g["z_after"]
+            assert same(O.sens_solution(res["T"]), [float.fromhex(h) for h in g["x_after"]])
+        g2 = run.sensitivity_rhs(obj, cons, rng.randint(1, m), float(rng.choice([-30, -12, -5, 4, 9])))
+        Tb = unmat(g2["tableau_before_resolve"])
+        res = O.sens_resolve(Tb, O.sens_rebuild_basis(Tb))
+        assert same(res["T"], unmat(g2["tableau_after"])) and res["basis"].tolist() == g2["basis_after"]
+        assert (res["status"] == O.OPTIMAL) == (g2["exception"] is None)
