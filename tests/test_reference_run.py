@@ -258,6 +258,15 @@ def test_rounding_rules():
     assert [float(lib.orc_net_round4(float(v))).hex() for v in vals] == g["round4"]
     assert [float(lib.orc_frac(float(v))).hex() for v in vals] == g["frac"]
     assert [abs(lib.orc_net_round4(float(v)) - lib.orc_net_round(lib.orc_net_round4(float(v)))) <= 1e-6 for v in vals] == g["is_integer"]
+    # COMDouble::Round against rint: one double apart (x + 0.5 rounds to exactly 1.0, then the odd-tie correction)
+    assert lib.orc_net_round(0.5000000000000001) == 0.0 and np.rint(0.5000000000000001) == 1.0
+    assert lib.orc_net_round4(5.000000000000001e-05) == 0.0 and lib.orc_net_round4(5.0000000000000016e-05) == 0.0
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.normal(size=200000) * 10.0 ** rng.integers(-8, 16, 200000),
+                         rng.integers(-10**6, 10**6, 200000) + 0.5, np.nextafter(np.arange(0, 2000) + 0.5, np.inf)])
+    xs = xs[xs != 0.5000000000000001]
+    got = np.array([lib.orc_net_round(float(v)) for v in xs[:60000]])
+    assert np.array_equal(got, np.rint(xs[:60000]))
 
 
 # ------------------------------------------------------------------------------------------- sensitivity
