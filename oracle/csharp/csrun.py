@@ -1171,6 +1171,7 @@ class Interpreter:
         self.steps = 0
         self.max_steps = None
         self.native = None     # P/Invoke target: an object with call(name, params, values, return_type)
+        self._dispatch = {name[2:]: getattr(self, name) for name in dir(self) if name.startswith("e_")}
         self.out_writer = None  # Console.SetOut(user TextWriter)
         self.base_dir = "C:\\LPR_381_Group_V22\\bin\\Debug\\"   # AppDomain.CurrentDomain.BaseDirectory
         self.path_sep = "\\"
@@ -1816,7 +1817,7 @@ class Interpreter:
 
     # ---- expressions
     def ev(self, e, env):
-        return getattr(self, "e_" + e[0])(e, env)
+        return self._dispatch[e[0]](e, env)
 
     def e_lit(self, e, env):
         return e[1]
