@@ -239,6 +239,26 @@ class Runner:
                     "pivot_rows": from_cs(pr) if pr is not None else None})
         return rec
 
+    def run_bb(self, objective, rows, is_min):
+        """BranchAndBound.RunBranchAndBound (:1253-1298): ConfigureProblem, DoDualSimplex on the formulated tableau,
+        rounding, ExecuteBranchAndBound -- the result is only printed, so it is parsed from the console"""
+        it = self.it
+        it.console.clear()
+        bbo = it.new("BranchAndBound")
+        err = None
+        try:
+            it.call(bbo, "RunBranchAndBound", to_list(objective), CsList([to_list(r) for r in rows], None), is_min)
+        except CsException as e:
+            err = e.tname
+        text = it.console_text()
+        sol = re.search(r"Optimal integer solution: \[(.*?)\]\r\nOptimal value: (\S+)", text)
+        nodes = [int(d) for d in re.findall(r"--- Processing branch \S+ \(Depth (\d+)\) ---", text)]
+        init = re.search(r"Initial objective value: (\S+)", text)
+        return {"objective": list(objective), "rows": [list(r) for r in rows], "is_min": is_min, "exception": err,
+                "initial_objective_text": init.group(1) if init else None, "node_depths": nodes,
+                "solution_text": sol.group(1) if sol else None, "value_text": sol.group(2) if sol else None,
+                "no_integer_solution": "No integer solution found" in text, "console_sha256": sha(text)}
+
     def bb_parts(self, T, n, var, bound, typ):
         """the members ExecuteBranchAndBound is made of, one by one, on an arbitrary tableau"""
         it = self.it
@@ -573,6 +593,19 @@ def generate():
                 T[i][-1] = float(rng2.choice([2.5, 3, 0.75, 1.99995, 4.00004, -1.5, 0, 6.5]))
         parts.append(run.bb_parts(T, n, rng2.randrange(n), float(rng2.randint(0, 5)), rng2.choice([0, 1])))
     out["bb_parts"] = parts
+    rbb = [run.run_bb([2, 3, 3, 5, 2, 4], [[11, 8, 6, 14, 10, 10, 40, 0]], False)]
+    rng4 = random.Random(384)
+    while len(rbb) < 5:
+        n, m = rng4.randint(2, 4), rng4.randint(1, 3)
+        obj = [float(rng4.randint(1, 9)) for _ in range(n)]
+        rows = [[float(rng4.randint(1, 9)) for _ in range(n)] + [float(rng4.randint(4, 25)), 0.0] for _ in range(m)]
+        run.it.max_steps = run.it.steps + 6_000_000
+        try:
+            rbb.append(run.run_bb(obj, rows, False))
+        except RuntimeError:
+            pass
+        run.it.max_steps = None
+    out["run_bb"] = rbb
     out["rounding"] = run.rounding(
         [0.00005, 0.00015, -0.00005, 2.5e-5, 12345.67895, -0.99995, 0.5, 1.5, 2.5, -0.5, -2.5, 1e16, 2.675, 1.00005,
          0.49999999999999994, 4503599627370497.0, 3.0, -3.0, 2.9999999999, -0.2, 7.000000001, 0.9999995, 1.0000005,

@@ -46,7 +46,8 @@ def test_golden_covers_the_reference_fixtures_and_every_solver():
     assert len(GOLD["meta"]["reference_sources"]) == 13
     for key, least in (("parser", 9), ("primal", 28), ("primal2", 16), ("dual", 16), ("cutting_plane", 12),
                        ("revised", 20), ("bb", 13), ("bb_formulate", 6), ("sensitivity", 12), ("sensitivity_rhs", 6),
-                       ("output", 3), ("mid_size", 3), ("bb_parts", 40), ("program", 6), ("cutting_plane_ties", 8)):
+                       ("output", 3), ("mid_size", 3), ("bb_parts", 40), ("program", 6), ("cutting_plane_ties", 8),
+                       ("run_bb", 5)):
         assert len(GOLD[key]) >= least, key
     # data/TextFile.txt parsed by the reference's own InputFileParser
     p = GOLD["parser"][0]
@@ -248,6 +249,30 @@ def test_branch_and_bound_members_one_by_one(i):
         if not (want[:, -1] < 0).any():
             r = O.bb_node_solve_ex(Tr, True, max_pivots=1)
             assert r["n_pivots"] == 1 and same_bits(r["T"] + 0.0, want + 0.0)
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["run_bb"])))
+def test_run_branch_and_bound_entry(i):
+    """BranchAndBound.RunBranchAndBound executed (its result is only printed: parsed from the reference's console)
+    against the oracle's composite ConfigureProblem -> FormulateTableau -> DoDualSimplex -> RoundTableau ->
+    ExecuteBranchAndBound"""
+    g = GOLD["run_bb"][i]
+    assert g["exception"] is None
+    o2, c2 = O.bb_configure_problem(g["objective"], g["rows"])
+    T = O.bb_formulate(o2, c2)
+    lp = O.bb_node_solve_ex(T, g["is_min"])
+    assert lp["status"] == O.OPTIMAL
+    root = O.bb_round(lp["T"])
+    import net_reference as R
+    assert R.net_general(float(root[0, -1])) == g["initial_objective_text"]
+    r = O.bb_solve(root, len(g["objective"]), prune=False, max_nodes=20)
+    assert r["node_log"][:, 0].tolist() == g["node_depths"]
+    if g["no_integer_solution"]:
+        assert not r["has_solution"]
+    else:
+        assert r["has_solution"]
+        assert ", ".join(R.net_general(float(v)) for v in r["x"]) == g["solution_text"]
+        assert R.net_general(float(r["z"])) == g["value_text"]
 
 
 def test_rounding_rules():
