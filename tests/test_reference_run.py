@@ -466,6 +466,18 @@ def test_program_main_sessions():
     assert leak["unhandled_exception"] == "System.ArgumentException: Constraint 2 has incorrect number of coefficients."
 
 
+def test_native_cli_bound_rows_against_program_main():
+    """the x_i <= 1 rows menu option 1 appends inline (Program.cs:114-124, one entry too long with a stray 1: SURVEY
+    Q1), as Main itself built them and OutputFileWrite printed them, against lpr_model_add_cli_bound_rows"""
+    from lpr_381_group_v22_b200.io import Model
+    g = {tuple(r["keys"]): r for r in GOLD["program"]}[("1", "13", "7")]
+    m = Model.parse_text(g["model"])
+    m.add_cli_bound_rows()
+    canon = m.canonical_form()
+    assert "+ 1x1 + 0x2 + 0x3 + 0x4 + 0x5 + 0x6 + 0x7 + 1x8 + 0x9 + S2 = 1" in canon
+    assert canon in g["output_file"]
+
+
 def final_a_oracle():
     rows = []
     for i in range(6):
