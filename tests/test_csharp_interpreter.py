@@ -241,3 +241,28 @@ def test_the_parser_rejects_what_it_does_not_understand():
     unit = parse_source("namespace A.B { public sealed class C<T> : D, I { [Attr(1)] public static extern int f(out int x, [In] double[,] m); } }")
     cls = unit[2][0]
     assert cls[1] == "C" and cls[6] == "A.B" and cls[4][0][0] == "method" and "extern" in cls[4][0][1] and cls[4][0][5] is None
+
+
+def test_three_statements_of_the_number_formatting_rules_agree():
+    """csrc/host_io.cu (native), tests/net_reference.py and oracle/csharp/csrun.py were written separately; on random and
+    edge doubles "F3", "F6", NumFormat.N3's building blocks and double.ToString() must come out the same from all three"""
+    import ctypes as C
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import net_reference as R
+    from lpr_381_group_v22_b200 import _native as N
+    from lpr_381_group_v22_b200.utilities import F3, NumFormat
+
+    def general(x):
+        buf = C.create_string_buffer(64)
+        N.check(N.lib().lpr_fmt_general(float(x), buf, 64))
+        return buf.value.decode()
+    rng = np.random.default_rng(21)
+    xs = list((rng.normal(size=1500) * 10.0 ** rng.integers(-9, 17, 1500)).tolist())
+    xs += [round(float(v), 4) + 0.0005 for v in rng.uniform(-50, 50, 300)]        # ties of the third decimal
+    xs += [0.0, -0.0, 0.0005, -0.0005, 1e-13, 2.5, 0.125, 1e15, 1e16, 123456789.123456789, -7.9995, 1 / 3, 5e-5, 99999.9995]
+    for x in xs:
+        assert F3(x) == R.F3(x) == format_double(x, "F3"), x
+        assert NumFormat.Fixed(x, 6) == R.net_fixed(x, 6) == format_double(x, "F6"), x
+        assert general(x) == R.net_general(x) == format_double(x), x
+        assert NumFormat.N3(x) == R.N3(x), x
