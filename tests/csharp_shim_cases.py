@@ -134,6 +134,47 @@ class Shims:
             bad.append("rows after Solve")
         return bad
 
+    def accessors(self, g):
+        it, bad = self.it, []
+        T = unmat(g["tableau"]).tolist()
+        if g["dual"]:
+            obj, rows = to_array(T[0]), self.rows(T)
+            s = it.new("DualSimplexSolver")
+            if bool(it.call_static("DualSimplexSolver", "AnyNegativeRhs", rows)) != g["any_negative_rhs"]:
+                bad.append("AnyNegativeRhs")
+            err = None
+            try:
+                r = it.call(s, "GetRows", obj, rows)
+                if not bits_equal([from_cs(r.vals[0])] + from_cs(r.vals[1]), unmat(g["rows"])):
+                    bad.append("GetRows")
+                o2, c2 = it.call(s, "GetObjectiveRow", obj, rows), it.call(s, "GetConstraintRows", obj, rows)
+                if not bits_equal([from_cs(o2)] + from_cs(c2), unmat(g["rows_again"])):
+                    bad.append("GetObjectiveRow / GetConstraintRows")
+            except CsException as e:
+                err = [e.tname, e.message]
+            if err != g["exception"]:
+                bad.append(f"exception {err}")
+            if not bits_equal([from_cs(obj)] + from_cs(rows), unmat(g["inputs_after"])):
+                bad.append("caller's rows after GetRows")
+            return bad
+        s = it.new("PrimalSimplexSolver2", to_array(T[0]), self.rows(T))
+        err = None
+        try:
+            r = it.call(s, "GetRows")
+            if not bits_equal([from_cs(r.vals[0])] + from_cs(r.vals[1]), unmat(g["rows"])):
+                bad.append("GetRows")
+            if not bits_equal(from_cs(it.call(s, "GetObjectiveRow")), unhex(g["objective_row"])):
+                bad.append("GetObjectiveRow")
+            if len(it.call(s, "GetConstraintRows", False).items) != g["n_constraint_rows"]:
+                bad.append("GetConstraintRows")
+            if float(it.get(s, "FinalZ")).hex() != g["final_z"]:
+                bad.append("FinalZ")
+        except CsException as e:
+            err = [e.tname, e.message]
+        if err != g["exception"]:
+            bad.append(f"exception {err}")
+        return bad
+
     def cutting_plane(self, g):
         it, bad = self.it, []
         T = unmat(g["tableau"]).tolist()
@@ -293,7 +334,7 @@ def run_all_against_real_library():
     tests/test_csharp_shims_gpu.py so that nothing the interop layer does can take the pytest process down"""
     sh = Shims(real_library())
     out = {}
-    plan = [("primal", lambda g: sh.primal(g)[0]), ("primal2", sh.primal2), ("dual", sh.dual),
+    plan = [("primal", lambda g: sh.primal(g)[0]), ("primal2", sh.primal2), ("dual", sh.dual), ("accessors", sh.accessors),
             ("cutting_plane", sh.cutting_plane), ("revised", lambda g: sh.revised(g, text=False)), ("bb", sh.bb),
             ("bb_formulate", sh.bb_formulate), ("sensitivity", sh.sensitivity)]
     for name, fn in plan:

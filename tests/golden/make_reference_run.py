@@ -157,6 +157,39 @@ class Runner:
                 "returned": ok, "exception": err, "printed_pivots": piv,
                 "final_tableau": mat([from_cs(obj)] + from_cs(rows))}
 
+    def accessors(self, T, dual):
+        """the read accessors that solve on demand: PrimalSimplexSolver2.GetRows / GetObjectiveRow / GetConstraintRows
+        (:193-227) and DualSimplexSolver.GetRows / GetObjectiveRow / GetConstraintRows / AnyNegativeRhs (:119-148, :180)"""
+        it = self.it
+        it.console.clear()
+        rec = {"tableau": mat(T), "dual": dual}
+        if dual:
+            obj, rows = to_array(T[0]), self.rows_list(T)
+            s = it.new("DualSimplexSolver")
+            rec["any_negative_rhs"] = bool(it.call_static("DualSimplexSolver", "AnyNegativeRhs", rows))
+            try:
+                r = it.call(s, "GetRows", obj, rows)
+                rec["exception"] = None
+                rec["rows"] = mat([from_cs(r.vals[0])] + from_cs(r.vals[1]))
+                o2 = it.call(s, "GetObjectiveRow", obj, rows)
+                c2 = it.call(s, "GetConstraintRows", obj, rows)
+                rec["rows_again"] = mat([from_cs(o2)] + from_cs(c2))
+            except CsException as e:
+                rec["exception"] = [e.tname, e.message]
+            rec["inputs_after"] = mat([from_cs(obj)] + from_cs(rows))     # solved in place
+        else:
+            s = it.new("PrimalSimplexSolver2", to_array(T[0]), self.rows_list(T))
+            try:
+                r = it.call(s, "GetRows")
+                rec["exception"] = None
+                rec["rows"] = mat([from_cs(r.vals[0])] + from_cs(r.vals[1]))
+                rec["objective_row"] = hexes(from_cs(it.call(s, "GetObjectiveRow")))
+                rec["n_constraint_rows"] = len(it.call(s, "GetConstraintRows", False).items)
+                rec["final_z"] = hx(it.get(s, "FinalZ"))
+            except CsException as e:
+                rec["exception"] = [e.tname, e.message]
+        return rec
+
     # ------------------------------------------------------------------ CuttingPlaneSolver
     def cutting_plane(self, T):
         it = self.it
@@ -493,6 +526,21 @@ def generate():
         du.append(run.dual(T, rng.choice([10000, 10000, 10000, 2, 0]), rng.random() < 0.6))
     out["primal2"] = p2
     out["dual"] = du
+    rng5 = random.Random(385)
+    acc = []
+    for case in range(12):
+        n, m = rng5.randint(2, 6), rng5.randint(1, 5)
+        dual = case % 2 == 1
+        T = [[0.0] * (n + m + 1) for _ in range(m + 1)]
+        for j in range(n):
+            T[0][j] = float(rng5.randint(0, 9)) if dual else -float(rng5.randint(-2, 9))
+        for i in range(m):
+            for j in range(n):
+                T[i + 1][j] = float(rng5.randint(-6, 4)) if dual else float(rng5.randint(-3, 9))
+            T[i + 1][n + i] = 1.0
+            T[i + 1][-1] = float(rng5.randint(-20, 10)) if dual else float(rng5.randint(0, 30))
+        acc.append(run.accessors(T, dual))
+    out["accessors"] = acc
 
     # ---- cutting plane: from the optimal tableau of small integer programs (what Program.cs feeds it)
     cp = []

@@ -103,6 +103,12 @@ def test_dual_simplex_solver_shim(shims, i):
     assert shims.dual(GOLD["dual"][i]) == []
 
 
+@pytest.mark.parametrize("i", range(len(GOLD["accessors"])))
+def test_solve_on_demand_accessors_of_the_shims(shims, i):
+    """GetRows / GetObjectiveRow / GetConstraintRows / AnyNegativeRhs and their InvalidOperationException messages"""
+    assert shims.accessors(GOLD["accessors"][i]) == []
+
+
 @pytest.mark.parametrize("i", range(len(GOLD["cutting_plane"])))
 def test_cutting_plane_solver_shim(shims, i):
     assert shims.cutting_plane(GOLD["cutting_plane"][i]) == []

@@ -47,7 +47,7 @@ def test_golden_covers_the_reference_fixtures_and_every_solver():
     for key, least in (("parser", 9), ("primal", 28), ("primal2", 16), ("dual", 16), ("cutting_plane", 12),
                        ("revised", 20), ("bb", 13), ("bb_formulate", 6), ("sensitivity", 12), ("sensitivity_rhs", 6),
                        ("output", 3), ("mid_size", 3), ("bb_parts", 40), ("program", 6), ("cutting_plane_ties", 8),
-                       ("run_bb", 5)):
+                       ("run_bb", 5), ("accessors", 12)):
         assert len(GOLD[key]) >= least, key
     # data/TextFile.txt parsed by the reference's own InputFileParser
     p = GOLD["parser"][0]
