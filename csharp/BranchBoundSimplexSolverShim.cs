@@ -67,7 +67,10 @@ namespace LPR_381_Group_V22.IntegerProgramming
                 {
                     var log = new int[2];
                     // one pivot of the DoDualSimplex state machine: a dual pivot while some RHS is negative (which is when the
-                    // reference calls PerformDualPivot, :315-343), otherwise a primal one (:345-390)
+                    // reference calls PerformDualPivot, :315-343), otherwise a primal one (:345-390).  As standalone calls the
+                    // two members therefore equal the reference's only in those states, a primal pivot that leaves a negative
+                    // RHS is dropped like DoDualSimplex drops it (:392-400), and -0.0 entries come back as 0.0 (:307-313);
+                    // nothing outside DoDualSimplex calls them upstream.
                     Lpr.Check(Lpr.lpr_tab_bb_node_solve_ex(h, isMinimization ? 1 : 0, 1, out int _, out long done, log, 1));
                     if (done == 0) return (tableau, null);   // no pivot possible: the reference's catch -> (tableau, null) (:152-172)
                     int r = log[0], c = log[1];

@@ -256,6 +256,37 @@ class Shims:
                 bad.append("pivot lists")
         return bad
 
+    def bb_parts(self, g):
+        """BranchAndBound.RoundTableau / AddConstraint and DualSimplexSolverBB.PerformDualPivot / PerformPrimalPivot.  The
+        two pivot members are one step of the native DoDualSimplex state machine (the C ABI has no single-pivot entry for
+        this rule): compared in the states DoDualSimplex calls them from -- a dual pivot while a RHS is negative, a
+        primal one when none is and none becomes negative (such a pivot is dropped, :392-400) -- and up to the
+        -0.0 -> 0.0 clean-up DoDualSimplex applies to every tableau (:307-313)"""
+        it, bad = self.it, []
+        T = unmat(g["tableau"]).tolist()
+
+        def ll(rows):
+            return CsList([to_list(r) for r in rows], None)
+        bbo = it.new("BranchAndBound")
+        it.call(bbo, "SetNumVars", g["n_vars"])
+        if not bits_equal(from_cs(it.call(bbo, "RoundTableau", ll(T))), unmat(g["rounded"])):
+            bad.append("RoundTableau")
+        row = [1.0 if j == g["var"] else 0.0 for j in range(g["n_vars"])] + [float(g["bound"]), float(g["type"])]
+        out = it.call(bbo, "AddConstraint", CsList([to_list(row)], None), ll(T))
+        if not bits_equal(from_cs(out.vals[0]), unmat(g["add_constraint"])):
+            bad.append("AddConstraint")
+        s = it.new("DualSimplexSolverBB")
+        Tr = unmat(g["rounded"])
+        if g["dual_pivot"] is not None:
+            dp = it.call(s, "PerformDualPivot", ll(Tr.tolist()))
+            if dp.vals[1] is None or not bits_equal(np.array(from_cs(dp.vals[0])) + 0.0, unmat(g["dual_pivot"]) + 0.0):
+                bad.append("PerformDualPivot")
+        if g["primal_pivot"] is not None and not (Tr[:, -1] < 0).any() and not (unmat(g["primal_pivot"])[:, -1] < 0).any():
+            pp = it.call(s, "PerformPrimalPivot", ll(Tr.tolist()), False)
+            if pp.vals[1] is None or not bits_equal(np.array(from_cs(pp.vals[0])) + 0.0, unmat(g["primal_pivot"]) + 0.0):
+                bad.append("PerformPrimalPivot")
+        return bad
+
     def sensitivity(self, g):
         it, bad = self.it, []
         p = it.new("PrimalSimplexSolver", to_list(g["objective"]), self.constraints(g["constraints"]), True)
@@ -336,7 +367,7 @@ def run_all_against_real_library():
     out = {}
     plan = [("primal", lambda g: sh.primal(g)[0]), ("primal2", sh.primal2), ("dual", sh.dual), ("accessors", sh.accessors),
             ("cutting_plane", sh.cutting_plane), ("revised", lambda g: sh.revised(g, text=False)), ("bb", sh.bb),
-            ("bb_formulate", sh.bb_formulate), ("sensitivity", sh.sensitivity)]
+            ("bb_formulate", sh.bb_formulate), ("bb_parts", sh.bb_parts), ("sensitivity", sh.sensitivity)]
     for name, fn in plan:
         res = {}
         for i, g in enumerate(GOLD[name]):

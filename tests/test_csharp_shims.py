@@ -129,6 +129,11 @@ def test_dual_simplex_solver_bb_shim(shims, i):
     assert shims.bb_formulate(GOLD["bb_formulate"][i]) == []
 
 
+@pytest.mark.parametrize("i", range(len(GOLD["bb_parts"])))
+def test_branch_and_bound_members_of_the_shim(shims, i):
+    assert shims.bb_parts(GOLD["bb_parts"][i]) == []
+
+
 @pytest.mark.parametrize("i", range(len(GOLD["sensitivity"])))
 def test_sensitivity_analyzer_shim(shims, i):
     assert shims.sensitivity(GOLD["sensitivity"][i]) == []

@@ -37,7 +37,7 @@ def results():
         return {"error": f"{type(e).__name__}: {e}"[:800]}
 
 
-CASES = [(k, i) for k in ("primal", "primal2", "dual", "accessors", "cutting_plane", "revised", "bb", "bb_formulate", "sensitivity")
+CASES = [(k, i) for k in ("primal", "primal2", "dual", "accessors", "cutting_plane", "revised", "bb", "bb_formulate", "bb_parts", "sensitivity")
          for i in range(len(GOLD[k]))] + [("knapsack", 0)]
 
 
