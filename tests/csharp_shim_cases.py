@@ -156,6 +156,11 @@ class Shims:
                 bad.append(f"exception {err}")
             if not bits_equal([from_cs(obj)] + from_cs(rows), unmat(g["inputs_after"])):
                 bad.append("caller's rows after GetRows")
+            it.console.clear()
+            it.call_static("DualSimplexSolver", "PrintTableau", obj, rows, len(T[0]) - len(T), None)
+            it.call_static("DualSimplexSolver", "PrintTableau", obj, rows, 1, "Custom title")
+            if it.console_text() != g["print_tableau"]:
+                bad.append("PrintTableau")
             return bad
         s = it.new("PrimalSimplexSolver2", to_array(T[0]), self.rows(T))
         err = None

@@ -177,6 +177,10 @@ class Runner:
             except CsException as e:
                 rec["exception"] = [e.tname, e.message]
             rec["inputs_after"] = mat([from_cs(obj)] + from_cs(rows))     # solved in place
+            it.console.clear()
+            it.call_static("DualSimplexSolver", "PrintTableau", obj, rows, len(T[0]) - len(T), None)
+            it.call_static("DualSimplexSolver", "PrintTableau", obj, rows, 1, "Custom title")
+            rec["print_tableau"] = it.console_text()
         else:
             s = it.new("PrimalSimplexSolver2", to_array(T[0]), self.rows_list(T))
             try:
