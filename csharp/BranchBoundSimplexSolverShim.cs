@@ -136,7 +136,7 @@ namespace LPR_381_Group_V22.IntegerProgramming
             public void SetNumVars(int n) { objectiveCoefficients = Enumerable.Repeat(0.0, n).ToList(); }   // :497-500
             public double RoundNumber(double number) => Math.Round(number, 4);                              // :540-550
             public List<double> RoundVector(List<double> v) => v.Select(RoundNumber).ToList();
-            public bool IsInteger(double value) => Math.Abs(value - Math.Round(value)) <= 1e-6;             // :595-599
+            public bool IsInteger(double value) { double r = RoundNumber(value); return Math.Abs(r - Math.Round(r)) <= 1e-6; }   // :595-599
 
             public List<List<double>> RoundTableau(List<List<double>> tableau)   // :552-567, on the device
             {

@@ -307,3 +307,59 @@ def test_reference_program_main_runs_on_the_shims():
         # Program.cs never disposes its solvers (the reference's classes are not IDisposable): the three solver objects and
         # the SensitivityAnalyzer of these sessions keep their handles until the SafeHandle finalizers run under a real GC
         assert len(double.handles) == 4
+
+
+def test_untraced_paths_and_small_members_of_the_shims(shims):
+    """what the recorded cases do not reach: the one-call paths above TraceMaxElements (no snapshots), DualPrices,
+    PrepareInput, RoundVector / RoundNumber / IsInteger / RoundAllTableaux"""
+    from csharp.csrun import CsList, from_cs, to_array, to_list
+    import numpy as np
+    it = shims.it
+    p2 = it.find_class("PrimalSimplexSolver2")
+    rv = it.find_class("RevisedPrimalSimplexSolver")
+    it.ensure_static(p2)
+    it.ensure_static(rv)
+    saved = p2.statics["TraceMaxElements"], rv.statics["TraceMaxElements"]
+    p2.statics["TraceMaxElements"] = rv.statics["TraceMaxElements"] = 0
+    try:
+        for g in GOLD["primal2"]:
+            T = S.unmat(g["tableau"]).tolist()
+            s = it.new("PrimalSimplexSolver2", to_array(T[0]), shims.rows(T))
+            assert bool(it.call(s, "Solve", g["max_iters"], g["print_steps"])) == g["returned"]
+            rows = it.call(s, "GetRows", False)
+            assert S.bits_equal([from_cs(rows.vals[0])] + from_cs(rows.vals[1]), S.unmat(g["final_tableau"]))
+            assert from_cs(it.get(s, "IterationSnapshots")) == []
+        for g in GOLD["revised"]:
+            if g["exception"] is not None:
+                continue
+            cons = [(g["A"][i], g["relations"][i], g["b"][i]) for i in range(len(g["A"]))]
+            s = it.new("RevisedPrimalSimplexSolver", to_list(g["c"]), shims.constraints(cons), g["is_min"])
+            it.call(s, "Solve")
+            assert float(it.get(s, "FinalZ")).hex() == g["final_z"] and from_cs(it.get(s, "BasicVariables")) == g["basis"]
+            assert from_cs(it.get(s, "IterationSnapshots")) == []
+            y = np.array(from_cs(it.get(s, "DualPrices")))
+            binv, basis = S.unmat(g["binv"]), g["basis"]
+            c = np.array(g["c"], dtype=float) * (-1.0 if g["is_min"] else 1.0)
+            cb = np.array([c[b] if b < len(c) else 0.0 for b in basis])
+            assert np.allclose(y, cb @ binv, rtol=1e-12, atol=1e-12)          # y = c_B B^-1
+            it.call(s, "Dispose")
+    finally:
+        p2.statics["TraceMaxElements"], rv.statics["TraceMaxElements"] = saved
+    bbo = it.new("BranchAndBound")
+    assert it.call(bbo, "RoundNumber", 1.00005) == 1.0001 and it.call(bbo, "IsInteger", 2.0000004) and not it.call(bbo, "IsInteger", 2.001)
+    r = GOLD["rounding"]
+    vals = [float.fromhex(h) for h in r["values"]]
+    assert [float(it.call(bbo, "RoundNumber", v)).hex() for v in vals] == r["round4"]
+    assert [bool(it.call(bbo, "IsInteger", v)) for v in vals] == r["is_integer"]
+    import oracle_lib as O
+    vec = [0.12345, 2.5, -0.00005, 7.00005]
+    assert from_cs(it.call(bbo, "RoundVector", to_list(vec))) == [O.lib().orc_net_round4(v) for v in vec]
+    g = GOLD["bb_parts"][0]
+    both = it.call(bbo, "RoundAllTableaux", CsList([CsList([to_list(r) for r in S.unmat(g["tableau"]).tolist()], None)] * 2, None))
+    assert all(S.bits_equal(from_cs(t), S.unmat(g["rounded"])) for t in both.items)
+    f = GOLD["bb_formulate"][0]
+    prep = it.call(it.new("DualSimplexSolverBB"), "PrepareInput", to_list(f["objective"]),
+                   CsList([to_list(r) for r in f["rows"]], None), f["is_min"])
+    assert S.bits_equal(from_cs(prep.vals[0]), S.unmat(f["tableau"])) and prep.vals[1] == f["is_min"]
+    assert prep.vals[2] == sum(1 for r in f["rows"] if r[-1] in (1, 2)) and prep.vals[3] == len(f["rows"]) - prep.vals[2]
+    assert prep.vals[4] == len(f["objective"])
