@@ -213,11 +213,11 @@ class Shims:
                 bad.append("FinalZ")
             if not np.allclose(from_cs(it.get(s, "SolutionVector")), x, rtol=1e-9, atol=1e-9 * max(1.0, float(np.abs(x).max()))):
                 bad.append("SolutionVector")
-            snaps = from_cs(it.get(s, "IterationSnapshots"))
-            if len(snaps) != g["n_snapshots"]:
-                bad.append(f"{len(snaps)} snapshots")
-            elif text and sha("".join(snaps)) != g["snapshots_sha256"]:
-                bad.append("IterationSnapshots text")
+        snaps = from_cs(it.get(s, "IterationSnapshots"))      # also when Solve threw: the iterations completed before it
+        if len(snaps) != g["n_snapshots"]:
+            bad.append(f"{len(snaps)} snapshots")
+        elif text and sha("".join(snaps)) != g["snapshots_sha256"]:
+            bad.append("IterationSnapshots text")
         it.call(s, "Dispose")
         return bad
 
