@@ -367,6 +367,38 @@ def test_native_parser_against_the_reference_parser():
         assert m.signs() == g["signs"]
 
 
+def test_python_mirror_of_the_input_classes_against_the_reference(tmp_path, capsys):
+    """lpr_381_group_v22_b200.InputFileParser (class surface of IO/InputFileParser.cs) and the list helpers of
+    Program.cs's bound rows against what the reference's classes did with the same texts"""
+    import lpr_381_group_v22_b200 as L
+    for k, g in enumerate(GOLD["parser"]):
+        path = tmp_path / f"m{k}.txt"
+        path.write_bytes(g["text"].encode("utf-8"))
+        p = L.InputFileParser()
+        if g["exception"] is not None:
+            with pytest.raises((ValueError, IndexError)):
+                p.ReadInputFile(str(path))
+            continue
+        p.ReadInputFile(str(path))
+        assert capsys.readouterr().out.strip() == g["console"].strip()
+        assert p.ProblemType == g["problem_type"]
+        if g["problem_type"] is None:
+            continue
+        assert same_bits(p.ObjectiveCoefficients, unhex(g["objective"])) and list(p.SignRestrictions) == g["signs"]
+        for c, (co, rel, rhs) in zip(p.Constraints, g["constraints"]):
+            assert same_bits(c.Coefficients, unhex(co)) and c.Relation == rel and float(c.RHS).hex() == rhs
+    for g in GOLD["output"]:
+        p = L.InputFileParser()
+        path = tmp_path / "o.txt"
+        path.write_bytes(g["text"].encode("utf-8"))
+        p.ReadInputFile(str(path))
+        cons = list(p.Constraints)
+        before = len(cons)
+        if g["add_upper_bound_rows"]:
+            L.add_upper_bound_constraints(len(p.ObjectiveCoefficients), list(p.SignRestrictions), cons)
+        assert [[[float(v).hex() for v in c.Coefficients], c.Relation, float(c.RHS).hex()] for c in cons[before:]] == g["rows_added"]
+
+
 def test_native_number_formatting_against_the_interpreted_formatter():
     """three independent statements of the .NET Framework rules -- csrc/host_io.cu, tests/net_reference.py and
     oracle/csharp/csrun.py (which ran the reference's NumFormat.N3 / TableIterationFormater.Format) -- agree"""
